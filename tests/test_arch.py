@@ -1,0 +1,30 @@
+import json
+import os
+
+import torch
+
+from conftest import GOLDEN_DIR
+from gimmvfi_b200.arch import param_spec_r
+from gimmvfi_b200.weights import random_state_dict
+
+
+def test_param_spec_matches_reference_state_dict():
+    """The 414-key layout dumped from the reference model."""
+    with open(os.path.join(GOLDEN_DIR, "state_dict_spec_r.json")) as f:
+        ref = json.load(f)
+    mine = param_spec_r()
+    assert len(mine) == len(ref) == 414
+    for (k, s, d), (k2, s2, d2) in zip(ref, mine):
+        assert (k, tuple(s), d) == (k2, tuple(s2), d2)
+    import math
+
+    n = sum(math.prod(s) for _, s, _ in mine)  # math.prod(()) == 1 for the int64 scalars
+    assert n == 19789980
+
+
+def test_random_state_dict_deterministic():
+    a, b = random_state_dict(7), random_state_dict(7)
+    assert list(a) == [k for k, _, _ in param_spec_r()]
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    k = "flow_estimator.cnet.layer2.0."
+    assert torch.equal(a[k + "norm3.weight"], a[k + "downsample.1.weight"])

@@ -1,0 +1,92 @@
+"""CPU tests of the oracle (oracle/gimmvfi_r_oracle.py) against the golden
+fixtures, which are outputs of the UNMODIFIED reference (oracle/make_golden.py).
+This is the oracle's pin: the reference itself ships no tests."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gimmvfi_r_oracle as O
+from conftest import GOLDEN_DIR
+from gimmvfi_b200.synth import synth_batch
+
+# oracle == reference bit-for-bit in the build container (manifest records 0.0);
+# allow for a different BLAS/oneDNN thread split on another host.
+TOL = 2e-5
+
+
+def run_case(name, meta, sd):
+    torch.set_grad_enabled(False)
+    B, H, W, ts, ds = meta["B"], meta["H"], meta["W"], meta["timesteps"], meta["ds_factor"]
+    xs = synth_batch(B, H, W, seed=meta["input_seed"])
+    ratio = 1.0 if ds is None else ds
+    coord = [(O.sample_coord_input(B, (H, W), [t], ratio), None) for t in ts]
+    tt = [t * torch.ones(B) for t in ts]
+    return O.gimmvfi_r_forward(sd, xs, coord, tt, ds_factor=ds)
+
+
+@pytest.mark.parametrize("name", ["r_128x160_t0.5", "r_b2_128x192_t0.25_0.75", "r_ds0.5_256x320_t0.5"])
+def test_oracle_matches_reference_golden(name, golden_manifest, weights0):
+    meta = golden_manifest[name]
+    assert meta["oracle_vs_reference_max_abs"] <= 2e-6
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    s = int(g["stride"])
+    out = run_case(name, meta, weights0)
+    for i in range(len(meta["timesteps"])):
+        a = out["imgt_pred"][i][..., ::s, ::s].numpy()
+        assert a.shape == g["imgt_pred_%d" % i].shape
+        assert np.abs(a - g["imgt_pred_%d" % i]).max() <= TOL
+        f = out["flowt"][i][..., ::s, ::s].numpy()
+        assert np.abs(f - g["flowt_%d" % i]).max() <= 50 * TOL
+        w4 = out["other_pred"][i][0][..., :: 2 * s, :: 2 * s].numpy()
+        assert np.abs(w4 - g["img_warp_4_%d" % i]).max() <= TOL
+    rf = out["raft_flow"][..., :: 2 * s, :: 2 * s].numpy()
+    assert np.abs(rf - g["raft_flow"]).max() <= 50 * TOL
+
+
+def test_output_contract(golden_manifest, weights0):
+    """Keys / shapes of the returned dict (gimmvfi_r.py:398-407), incl. the B=1 flowt squeeze."""
+    meta = golden_manifest["r_128x160_t0.5"]
+    out = run_case("r_128x160_t0.5", meta, weights0)
+    assert set(out) == {"imgt_pred", "other_pred", "flowt0_pred", "flowt1_pred", "raft_flow", "ninrflow", "nflow", "flowt"}
+    assert out["imgt_pred"][0].shape == (1, 3, 128, 160)
+    assert out["flowt"][0].shape == (2, 128, 160)
+    assert out["ninrflow"][0].shape == (1, 2, 1, 128, 160)
+    assert out["raft_flow"].shape == (1, 2, 2, 128, 160)
+    assert out["flowt0_pred"][0][0].shape == (1, 3, 2, 128, 160)
+    assert out["flowt0_pred"][0][1].shape == (1, 2, 32, 40)
+
+
+def test_splat_restatement_vs_bruteforce():
+    """forward_splat_sum vs a literal double loop over the kernel body
+    (modules/softsplat.py:384-420) incl. out-of-frame targets and non-finite flow."""
+    torch.manual_seed(0)
+    N, C, H, W = 1, 3, 6, 7
+    inp = torch.randn(N, C, H, W)
+    flow = torch.randn(N, 2, H, W) * 3
+    flow[0, 0, 1, 1] = float("nan")
+    flow[0, 1, 2, 3] = float("inf")
+    flow[0, :, 0, 0] = torch.tensor([2.0, 1.0])  # integer landing: three zero-weight corners
+    got = O.forward_splat_sum(inp, flow)
+    exp = torch.zeros_like(inp)
+    for y in range(H):
+        for x in range(W):
+            fx = x + flow[0, 0, y, x].item()
+            fy = y + flow[0, 1, y, x].item()
+            if not (np.isfinite(fx) and np.isfinite(fy)):
+                continue
+            x0, y0 = int(np.floor(fx)), int(np.floor(fy))
+            for xx, yy, w in ((x0, y0, (x0 + 1 - fx) * (y0 + 1 - fy)), (x0 + 1, y0, (fx - x0) * (y0 + 1 - fy)),
+                              (x0, y0 + 1, (x0 + 1 - fx) * (fy - y0)), (x0 + 1, y0 + 1, (fx - x0) * (fy - y0))):
+                if 0 <= xx < W and 0 <= yy < H:
+                    exp[0, :, yy, xx] += inp[0, :, y, x] * w
+    assert torch.allclose(got, exp, atol=1e-5)
+
+
+def test_zeroeps_holes():
+    """'zeroeps': a target that receives no weight outputs 0 (softsplat.py:333-344)."""
+    inp = torch.ones(1, 2, 4, 4)
+    flow = torch.full((1, 2, 4, 4), 10.0)  # everything leaves the frame
+    out = O.softsplat_linear_zeroeps(inp, flow, torch.ones(1, 1, 4, 4))
+    assert torch.count_nonzero(out) == 0
