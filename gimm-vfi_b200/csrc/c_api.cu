@@ -1,0 +1,167 @@
+// extern "C" boundary (include/gimmvfi_b200.h).  No exceptions cross it.
+#include "../../include/gimmvfi_b200.h"
+#include "engine.h"
+
+using namespace gv;
+
+struct gimmvfi_engine {
+  Engine eng;
+  std::string err;
+  explicit gimmvfi_engine(int dev) : eng(dev) {}
+};
+
+static thread_local std::string g_static_err;
+
+#define GV_TRY(e_, body)                                          \
+  try { body; return 0; }                                         \
+  catch (const std::exception& ex) { if (e_) (e_)->err = ex.what(); else g_static_err = ex.what(); return 1; } \
+  catch (...) { if (e_) (e_)->err = "unknown error"; else g_static_err = "unknown error"; return 1; }
+
+static TV to_tv(const gimmvfi_view* v) {
+  TV t;
+  if (!v) return t;
+  t.p = v->data; t.n = v->n; t.h = v->h; t.w = v->w; t.c = v->c; t.ld = v->pixel_stride; t.sn = v->batch_stride;
+  return t;
+}
+static Ctx op_ctx(void* stream) {
+  Ctx cx; cx.stream = (gvStream_t)stream;
+#ifndef GV_HOSTSIM
+  int dev = 0; cudaGetDevice(&dev); int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); cx.sm_count = sms;
+#endif
+  return cx;
+}
+static Problem to_problem(const gimmvfi_problem* p) {
+  Problem q; q.B = p->batch; q.Hf = p->height; q.Wf = p->width; q.T = p->timesteps; q.ds = p->ds_factor; q.Hc = p->coord_height; q.Wc = p->coord_width;
+  return q;
+}
+
+extern "C" {
+
+int gimmvfi_create(int device, gimmvfi_engine** out) {
+  gimmvfi_engine* none = nullptr;
+  GV_TRY(none, { *out = new gimmvfi_engine(device); })
+}
+void gimmvfi_destroy(gimmvfi_engine* e) { delete e; }
+
+int gimmvfi_load_weight(gimmvfi_engine* e, const char* key, const float* host_data, const int64_t* shape, int ndim) {
+  GV_TRY(e, { e->eng.load_weight(key, host_data, shape, ndim); })
+}
+int gimmvfi_finalize_weights(gimmvfi_engine* e) { GV_TRY(e, { e->eng.finalize_weights(); }) }
+
+int gimmvfi_plan(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes) {
+  GV_TRY(e, { *workspace_bytes = e->eng.plan(to_problem(p)); })
+}
+
+int gimmvfi_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_io* io, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream) {
+  GV_TRY(e, {
+    IO q;
+    q.img_xs = io->img_xs; q.coords = io->coords; q.t = io->t; q.imgt_pred = io->imgt_pred; q.img_warp_4 = io->img_warp_4;
+    q.flowt0_1 = io->flowt0_1; q.flowt1_1 = io->flowt1_1; q.flowt0_4 = io->flowt0_4; q.flowt1_4 = io->flowt1_4;
+    q.raft_flow = io->raft_flow; q.nflow = io->nflow; q.ninrflow = io->ninrflow; q.flowt = io->flowt;
+    e->eng.forward(to_problem(p), q, workspace, workspace_bytes, (gvStream_t)cuda_stream);
+  })
+}
+
+const char* gimmvfi_last_error(gimmvfi_engine* e) { return e ? e->err.c_str() : g_static_err.c_str(); }
+int64_t gimmvfi_last_launches(gimmvfi_engine* e) { return e->eng.last_launches(); }
+int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters) { GV_TRY(e, { if (iters < 1) throw std::runtime_error("iters must be >= 1"); e->eng.raft_iters = iters; }) }
+int gimmvfi_set_debug(gimmvfi_engine* e, int on) { GV_TRY(e, { e->eng.set_debug(on != 0); }) }
+int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out) {
+  GV_TRY(e, {
+    auto it = e->eng.taps().find(name);
+    if (it == e->eng.taps().end()) throw std::runtime_error(std::string("no tap named '") + name + "'");
+    const TV& t = it->second;
+    out->data = t.p; out->n = t.n; out->h = t.h; out->w = t.w; out->c = t.c; out->pixel_stride = t.ld; out->batch_stride = t.sn;
+  })
+}
+const char* gimmvfi_build_info(void) {
+#ifdef GV_HOSTSIM
+  return "gimmvfi_b200 HOSTSIM (test-only CPU emulation of the kernels; not a product build)";
+#else
+  return "gimmvfi_b200 sm_100a CUDA build";
+#endif
+}
+
+// ------------------------------------------------------------ per-kernel entry points
+int gimmvfi_op_softsplat(const gimmvfi_view* lat, const gimmvfi_view* flow, const gimmvfi_view* metric, const float* t, int t_mode,
+                         const gimmvfi_view* scratch, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    TV acc = to_tv(scratch); acc.c = 17;
+    if (acc.ld < 17 || to_tv(lat).c != 16) throw std::runtime_error("softsplat: lat must have 16 channels and scratch pixel_stride >= 17");
+    for (int n = 0; n < acc.n; ++n) dev_memset(acc.p + (int64_t)n * acc.sn, 0, (size_t)acc.h * acc.w * acc.ld * sizeof(float), cx.stream);
+    softsplat_accumulate(cx, to_tv(lat), to_tv(flow), to_tv(metric), t, t_mode, acc);
+    softsplat_normalize(cx, acc, to_tv(out));
+  })
+}
+int gimmvfi_op_backwarp(const gimmvfi_view* src, const gimmvfi_view* flow, const gimmvfi_view* dst, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); backwarp(cx, to_tv(src), to_tv(flow), to_tv(dst)); })
+}
+int gimmvfi_op_resize(const gimmvfi_view* src, const gimmvfi_view* dst, float scale_factor, float mult, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    float r = (float)(1.0 / (double)scale_factor);
+    resize_bilinear(cx, to_tv(src), to_tv(dst), r, r, mult, 0, ACT_NONE);
+  })
+}
+int gimmvfi_op_corr_volume(const gimmvfi_view* fa, const gimmvfi_view* fb, float* vol, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); TV a = to_tv(fa); corr_volume(cx, a, to_tv(fb), vol, 1.0f / std::sqrt((float)a.c)); })
+}
+int gimmvfi_op_corr_pool(const float* src, float* dst, int64_t rows, int h, int w, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); corr_pool(cx, src, dst, rows, h, w); })
+}
+int gimmvfi_op_corr_lookup(const float* const lvl[4], const int32_t lvl_h[4], const int32_t lvl_w[4], const gimmvfi_view* coords,
+                           const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    TV c = to_tv(coords);
+    CorrPyr p;
+    for (int l = 0; l < 4; ++l) { p.lvl[l] = lvl[l]; p.h[l] = lvl_h[l]; p.w[l] = lvl_w[l]; }
+    p.rows_per_sample = (int64_t)c.h * c.w;
+    corr_lookup(cx, p, c, to_tv(out));
+  })
+}
+int gimmvfi_op_conv2d(const gimmvfi_view* in0, const gimmvfi_view* in1, const float* w_packed, const float* bias, int cin, int cout,
+                      int cout_ld, int kh, int kw, int stride, int pad_h, int pad_w, int reflect, int act, const float* slope,
+                      const gimmvfi_view* residual, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    ConvW w; w.w = w_packed; w.b = bias; w.cin = cin; w.cout = cout; w.cout_ld = cout_ld; w.kh = kh; w.kw = kw;
+    ConvGeom g; g.stride = stride; g.ph = pad_h; g.pw = pad_w; g.reflect = reflect;
+    ConvEpi ep; ep.act1 = act; ep.slope1 = slope; ep.res = to_tv(residual);
+    conv2d(cx, to_tv(in0), to_tv(in1), w, g, ep, to_tv(out));
+  })
+}
+int64_t gimmvfi_instnorm_scratch_floats(int n, int c) {
+  TV t; t.n = n; t.c = c;
+  return instnorm_scratch_floats(t) + (int64_t)n * c * 2;
+}
+int gimmvfi_op_instnorm(const gimmvfi_view* x, int relu, float* scratch, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    TV t = to_tv(x);
+    float* mr = scratch + instnorm_scratch_floats(t);
+    instnorm_stats(cx, t, mr, scratch, 0);
+    instnorm_apply(cx, t, mr, relu ? ACT_RELU : ACT_NONE, TV(), ACT_NONE, to_tv(out));
+  })
+}
+int gimmvfi_op_convex_upsample(const gimmvfi_view* flow, const gimmvfi_view* mask, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); convex_upsample(cx, to_tv(flow), to_tv(mask), to_tv(out)); })
+}
+int gimmvfi_op_pixel_shuffle(const gimmvfi_view* src, const gimmvfi_view* dst, int times, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); pixel_shuffle(cx, to_tv(src), to_tv(dst), times); })
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// gimmvfi_b200 — shared declarations for the sm_100a engine.
+//
+// Two build modes of the SAME sources:
+//   * product:  nvcc -gencode arch=compute_100a,code=sm_100a  -> libgimmvfi_b200.so
+//   * GV_HOSTSIM (tests/hostsim only): g++ -x c++ -DGV_HOSTSIM -fopenmp.  Every
+//     "thread-per-element" kernel body is a __host__ __device__ functor, so the
+//     identical code runs as an OpenMP loop on the CPU.  This exists to validate
+//     the host orchestration and kernel arithmetic in the GPU-less build
+//     container; it is never loaded by the product package.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+
+#ifdef GV_HOSTSIM
+#define GV_HD inline
+#define GV_DEV inline
+typedef void* gvStream_t;
+#else
+#include <cuda_runtime.h>
+#define GV_HD __host__ __device__ __forceinline__
+#define GV_DEV __device__ __forceinline__
+typedef cudaStream_t gvStream_t;
+#endif
+
+namespace gv {
+
+// ---------------------------------------------------------------------------
+// Tensor view: NHWC, fp32.  element (n,y,x,ch) = p[n*sn + (y*w + x)*ld + ch].
+// `c` is the number of channels visible through the view, `ld` the pixel stride
+// of the underlying buffer (>= c): a channel slice of a concat buffer is a view.
+// ---------------------------------------------------------------------------
+struct TV {
+  float* p = nullptr;
+  int n = 0, h = 0, w = 0, c = 0;
+  int ld = 0;
+  int64_t sn = 0;
+  GV_HD int64_t off(int in, int y, int x) const { return (int64_t)in * sn + ((int64_t)y * w + x) * ld; }
+  TV slice(int c0, int cnt) const { TV t = *this; t.p = p + c0; t.c = cnt; return t; }
+  TV batch(int n0, int cnt) const { TV t = *this; t.p = p + (int64_t)n0 * sn; t.n = cnt; return t; }
+  int64_t pixels() const { return (int64_t)n * h * w; }
+};
+
+inline TV make_tv(float* p, int n, int h, int w, int c, int ld = 0) {
+  TV t; t.p = p; t.n = n; t.h = h; t.w = w; t.c = c; t.ld = ld ? ld : c; t.sn = (int64_t)h * w * t.ld; return t;
+}
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_PRELU = 3, ACT_SIGMOID = 4, ACT_TANH = 5, ACT_SIN = 6 };
+
+GV_HD float apply_act(float v, int act, const float* slope, int ch) {
+  switch (act) {
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    case ACT_LRELU: return v > 0.f ? v : 0.1f * v;
+    case ACT_PRELU: return v > 0.f ? v : slope[ch] * v;
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case ACT_TANH: return tanhf(v);
+    case ACT_SIN: return sinf(v);
+    default: return v;
+  }
+}
+
+// Packed convolution weights (device memory): w[(ky*kw+kx)*cin + ci][cout_ld], bias[cout].
+struct ConvW {
+  const float* w = nullptr;
+  const float* b = nullptr;
+  int cin = 0, cout = 0, kh = 1, kw = 1;
+  int cout_ld = 0;  // row stride of w (cout rounded up to 4)
+};
+
+// y = act2( res + act1(conv(x) + b) ) * mul      (res / mul optional)
+// gru:  y = (1 - z) * hprev + z * y               (SepConvGRU update, raft/update.py:58,66)
+struct ConvEpi {
+  int act1 = ACT_NONE; const float* slope1 = nullptr;
+  int act2 = ACT_NONE; const float* slope2 = nullptr;
+  TV res;   // optional residual (same n,h,w as output; res.p == nullptr -> none)
+  TV mul;   // optional elementwise multiplier
+  TV gru_z, gru_h;  // optional GRU blend
+};
+
+struct ConvGeom {
+  int stride = 1;
+  int ph = 0, pw = 0;
+  int reflect = 0;  // 0: zero padding, 1: reflect padding (padding_mode="reflect")
+};
+
+// ---------------------------------------------------------------------------
+// Execution context
+// ---------------------------------------------------------------------------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, top = 0, peak = 0;
+  bool dry = false;  // planning pass: only track the high-water mark
+  float* alloc_f(size_t n_floats) {
+    size_t bytes = (n_floats * sizeof(float) + 255) & ~size_t(255);
+    size_t o = top;
+    top += bytes;
+    if (top > peak) peak = top;
+    if (dry) return reinterpret_cast<float*>(size_t(4096) + o);  // fake, never dereferenced
+    if (top > cap) throw std::runtime_error("gimmvfi: workspace too small (need " + std::to_string(top) + " bytes, have " + std::to_string(cap) + ")");
+    return reinterpret_cast<float*>(base + o);
+  }
+  TV tensor(int n, int h, int w, int c, int ld = 0) { if (!ld) ld = c; return make_tv(alloc_f((size_t)n * h * w * ld), n, h, w, c, ld); }
+  size_t mark() const { return top; }
+  void release(size_t m) { top = m; }
+};
+
+struct Ctx {
+  gvStream_t stream = nullptr;
+  Arena arena;
+  bool dry = false;       // skip kernel launches (planning)
+  int64_t launches = 0;   // kernels launched by the last forward
+  int sm_count = 148;
+};
+
+void gv_check_launch(const char* what);
+
+// ---------------------------------------------------------------------------
+// thread-per-element launcher
+// ---------------------------------------------------------------------------
+#ifndef GV_HOSTSIM
+template <class F>
+__global__ void __launch_bounds__(256) gv_elementwise_kernel(F f, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) f(i);
+}
+#endif
+
+template <class F>
+inline void parallel_for(Ctx& cx, int64_t n, const F& f, const char* name) {
+  if (cx.dry || n <= 0) return;
+  cx.launches++;
+#ifdef GV_HOSTSIM
+  (void)name;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) f(i);
+#else
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)cx.sm_count * 32;  // grid-stride beyond 32 CTAs/SM
+  if (blocks > cap) blocks = cap;
+  gv_elementwise_kernel<F><<<(unsigned)blocks, 256, 0, cx.stream>>>(f, n);
+  gv_check_launch(name);
+#endif
+}
+
+GV_HD bool gv_isfinite(float v) { return fabsf(v) <= 3.402823466e+38f; }  // false for NaN / +-inf
+
+GV_HD float atomic_add_f(float* addr, float v) {
+#if defined(GV_HOSTSIM)
+  float old;
+#pragma omp atomic capture
+  { old = *addr; *addr += v; }
+  return old;
+#elif defined(__CUDA_ARCH__)
+  return atomicAdd(addr, v);
+#else
+  float old = *addr; *addr += v; return old;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// op library (ops_*.cu)
+// ---------------------------------------------------------------------------
+// conv.cu
+void conv2d(Ctx& cx, const TV& in0, const TV& in1 /*optional 2nd channel segment*/, const ConvW& w, const ConvGeom& g,
+            const ConvEpi& e, const TV& out);
+// corr.cu
+void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale);   // vol[n][i][j] = <fa[n,i], fb[n,j]> * scale
+void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w); // rows x (h*w) -> rows x (h/2*w/2)
+struct CorrPyr { const float* lvl[4]; int h[4], w[4]; int64_t rows_per_sample; };
+void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords /*n,h,w,2 (x,y)*/, const TV& out /*324 ch*/);
+// ops_pointwise.cu
+void nchw_to_nhwc(Ctx& cx, const float* src, int64_t src_sn, int64_t src_sc, const TV& dst, float scale, float shift);
+void nhwc_to_nchw(Ctx& cx, const TV& src, float* dst, int64_t dst_sn, int64_t dst_sc, float scale, float shift, int clamp01);  // (v + shift) * scale
+void copy_channels(Ctx& cx, const TV& src, const TV& dst);
+void fill(Ctx& cx, const TV& dst, float v);
+void axpby(Ctx& cx, const TV& a, float alpha, const TV& b, float beta, const TV& out);  // out = alpha*a + beta*b (b optional)
+void resize_bilinear(Ctx& cx, const TV& src, const TV& dst, float scale_y, float scale_x, float mult, int accumulate, int act);
+void backwarp(Ctx& cx, const TV& src, const TV& flow /*2ch at dst res*/, const TV& dst);
+void pixel_shuffle(Ctx& cx, const TV& src, const TV& dst, int times);
+void instnorm_stats(Ctx& cx, const TV& x, float* mean_rstd /*n*c*2*/, float* scratch, int64_t scratch_floats);
+void instnorm_apply(Ctx& cx, const TV& x, const float* mean_rstd, int act1, const TV& res, int act2, const TV& out);
+int64_t instnorm_scratch_floats(const TV& x);
+void absmax_per_sample(Ctx& cx, const TV& a, const TV& b, float* out_n, float* scratch);  // out[n] = max(|a|,|b|)
+int64_t absmax_scratch_floats(const TV& a);
+void convex_upsample(Ctx& cx, const TV& flow, const TV& mask, const TV& out);
+void coords_minus_grid(Ctx& cx, const TV& coords1, const TV& flow_out_a, const TV& flow_out_b);
+void init_coords(Ctx& cx, const TV& coords);
+void splat_weights(Ctx& cx, const TV& f_self, const TV& f_other, const float* g9, const float* alpha_fe, const float* alpha_v, const TV& out);
+void normalize_flow_pair(Ctx& cx, const TV& f01, const TV& f10, const float* scaler, const TV& n0, const TV& n1);
+void softsplat_accumulate(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const TV& acc);
+void softsplat_normalize(Ctx& cx, const TV& acc, const TV& out);
+void scale_flow_t(Ctx& cx, const TV& flow_t, const float* t_per_sample, const TV& f0, const TV& f1);
+void hypo_pack_input(Ctx& cx, const float* coord /*B,Hc,Wc,3*/, const TV& dst /*slice of 3 ch*/);
+void unnormalize_flow(Ctx& cx, const TV& ninr, const float* scaler, const TV& out);
+void lookup_coords(Ctx& cx, const TV& flow, const float* t_per_sample, int mode, const TV& out);
+void flow_mask_split(Ctx& cx, const TV& out133, const TV& f0_in, const TV& f1_in, const TV& f0, const TV& f1, const TV& mask);
+void add_inplace_slices(Ctx& cx, const TV& dst, const TV& src);
+void final_heads(Ctx& cx, const TV& out24, const TV& flow0, const TV& flow1, const TV& mask, const TV& oflow0, const TV& oflow1,
+                 const TV& omask, const TV& ores);
+void warp_blend(Ctx& cx, const TV& img0, const TV& img1, const TV& f0, const TV& f1, const TV& mask_logit, const TV& out_nhwc);
+void multi_flow_blend(Ctx& cx, const TV& img0, const TV& img1, const TV& f0, const TV& f1, const TV& mask, const TV& res,
+                      const TV& warps9, const TV& mean3);
+void combine_output(Ctx& cx, const TV& mean3, const TV& conv3, float* dst_nchw);
+
+// device memory helpers (hostsim: plain host memory)
+void* dev_alloc(size_t bytes);
+void dev_free(void* p);
+void dev_upload(void* dst, const void* src, size_t bytes);
+void dev_download(void* dst, const void* src, size_t bytes, gvStream_t s);
+void dev_memset(void* dst, int v, size_t bytes, gvStream_t s);
+void dev_copy(void* dst, const void* src, size_t bytes, gvStream_t s);
+void dev_sync(gvStream_t s);
+
+}  // namespace gv

@@ -1,0 +1,204 @@
+// fp32 implicit-GEMM convolution on NHWC activations with fused epilogues
+// (bias, ReLU/LeakyReLU/PReLU/sigmoid/tanh/sin, residual add, gate multiply,
+// ConvGRU blend).  This is the exact-precision CUDA-core path used where the
+// recurrence amplifies rounding (RAFT) and for small-channel layers; the
+// tensor-core path for the wide synthesis layers lives in conv_tc.cu.
+//
+// GEMM view: M = n*oh*ow output pixels, N = cout, K = kh*kw*cin.  The input may
+// be the channel concatenation of two views (in0 | in1) so torch.cat never
+// materialises (ResBlock side-channel splice fi_components.py:137-148, GRU
+// cat[r*h, x] raft/update.py:57,65).
+#include "common.h"
+
+namespace gv {
+
+struct ConvArgs {
+  TV in0, in1, out;
+  ConvW w;
+  ConvGeom g;
+  ConvEpi e;
+  int c0;      // channels taken from in0 (rest from in1)
+  int M;       // total output pixels
+  int vec_ok;  // float4 loads allowed on the activation side
+};
+
+GV_HD int reflect_idx(int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
+
+GV_HD float conv_epilogue(const ConvArgs& a, float v, int n, int oy, int ox, int co) {
+  const ConvEpi& e = a.e;
+  if (a.w.b) v += a.w.b[co];
+  v = apply_act(v, e.act1, e.slope1, co);
+  if (e.res.p) v += e.res.p[e.res.off(n, oy, ox) + co];
+  v = apply_act(v, e.act2, e.slope2, co);
+  if (e.mul.p) v *= e.mul.p[e.mul.off(n, oy, ox) + co];
+  if (e.gru_z.p) {
+    float z = e.gru_z.p[e.gru_z.off(n, oy, ox) + co];
+    float h = e.gru_h.p[e.gru_h.off(n, oy, ox) + co];
+    v = (1.f - z) * h + z * v;
+  }
+  return v;
+}
+
+#ifndef GV_HOSTSIM
+template <int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) conv2d_simt_kernel(ConvArgs a) {
+  constexpr int BM = 128, BK = 16;
+  constexpr int NT = BN / TN;  // threads along N
+  static_assert((BM / TM) * NT == 256, "thread tiling");
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tn = (tid % NT) * TN, tm = (tid / NT) * TM;
+  const int OH = a.out.h, OW = a.out.w, IH = a.in0.h, IW = a.in0.w;
+  const int cin = a.w.cin, KW = a.w.kw, taps = a.w.kh * a.w.kw;
+
+  // the two activation rows (pixels) this thread stages per K-step
+  int pn[2], py[2], px[2]; bool pv[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    int m = m0 + ((tid + it * 256) >> 2);
+    pv[it] = m < a.M;
+    int mm = pv[it] ? m : 0;
+    px[it] = mm % OW; int r = mm / OW; py[it] = r % OH; pn[it] = r / OH;
+  }
+  const int q4 = (tid & 3) * 4;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int tap = 0; tap < taps; ++tap) {
+    const int ky = tap / KW, kx = tap % KW;
+    const float* rowp0[2]; const float* rowp1[2]; bool rv[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      int iy = py[it] * a.g.stride - a.g.ph + ky, ix = px[it] * a.g.stride - a.g.pw + kx;
+      if (a.g.reflect) { iy = reflect_idx(iy, IH); ix = reflect_idx(ix, IW); }
+      rv[it] = pv[it] && iy >= 0 && iy < IH && ix >= 0 && ix < IW;
+      int64_t o = rv[it] ? ((int64_t)iy * IW + ix) : 0;
+      rowp0[it] = a.in0.p + (int64_t)pn[it] * a.in0.sn + o * a.in0.ld;
+      rowp1[it] = a.in1.p ? a.in1.p + (int64_t)pn[it] * a.in1.sn + o * a.in1.ld : nullptr;
+    }
+    for (int k0 = 0; k0 < cin; k0 += BK) {
+      // ---- stage A: 128 pixels x 16 channels
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        int row = (tid + it * 256) >> 2;
+        int ch = k0 + q4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rv[it]) {
+          const float* src; int lim, cc;
+          if (ch < a.c0) { src = rowp0[it]; lim = a.c0; cc = ch; } else { src = rowp1[it]; lim = cin - a.c0; cc = ch - a.c0; }
+          if (a.vec_ok && cc + 3 < lim) {
+            v = *reinterpret_cast<const float4*>(src + cc);
+          } else if (ch < cin) {
+            float t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              int c = ch + u; float x = 0.f;
+              if (c < cin) x = (c < a.c0) ? rowp0[it][c] : rowp1[it][c - a.c0];
+              t[u] = x;
+            }
+            v = make_float4(t[0], t[1], t[2], t[3]);
+          }
+        }
+        As[q4 + 0][row] = v.x; As[q4 + 1][row] = v.y; As[q4 + 2][row] = v.z; As[q4 + 3][row] = v.w;
+      }
+      // ---- stage B: 16 x BN weights
+      if (tid < BK * BN / 4) {
+        int k = tid / (BN / 4), n4 = (tid % (BN / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + k < cin && n0 + n4 < a.w.cout_ld)
+          v = *reinterpret_cast<const float4*>(a.w.w + ((int64_t)tap * cin + k0 + k) * a.w.cout_ld + n0 + n4);
+        *reinterpret_cast<float4*>(&Bs[k][n4]) = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float av[TM], bv[TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) av[i] = As[k][tm + i];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bv[j] = Bs[k][tn + j];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + tm + i;
+    if (m >= a.M) continue;
+    int ox = m % OW; int r = m / OW; int oy = r % OH; int n = r / OH;
+    float* o = a.out.p + a.out.off(n, oy, ox);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int co = n0 + tn + j;
+      if (co < a.w.cout) o[co] = conv_epilogue(a, acc[i][j], n, oy, ox, co);
+    }
+  }
+}
+#endif
+
+void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out) {
+  if (cx.dry) return;
+  ConvArgs a;
+  a.in0 = in0; a.in1 = in1; a.out = out; a.w = w; a.g = g; a.e = e;
+  a.c0 = in0.c;
+  a.M = out.n * out.h * out.w;
+  const int cin_total = in0.c + (in1.p ? in1.c : 0);
+  if (cin_total != w.cin) throw std::runtime_error("conv2d: cin mismatch (" + std::to_string(cin_total) + " vs " + std::to_string(w.cin) + ")");
+  if (out.c != w.cout) throw std::runtime_error("conv2d: cout mismatch");
+  {
+    int eh = (in0.h + 2 * g.ph - w.kh) / g.stride + 1, ew = (in0.w + 2 * g.pw - w.kw) / g.stride + 1;
+    if (eh != out.h || ew != out.w || in0.n != out.n) throw std::runtime_error("conv2d: output geometry mismatch");
+  }
+  cx.launches++;
+#ifdef GV_HOSTSIM
+  const int OH = out.h, OW = out.w, IH = in0.h, IW = in0.w;
+#pragma omp parallel for schedule(static)
+  for (int m = 0; m < a.M; ++m) {
+    int ox = m % OW; int r = m / OW; int oy = r % OH; int n = r / OH;
+    std::vector<float> acc(w.cout, 0.f);
+    for (int ky = 0; ky < w.kh; ++ky)
+      for (int kx = 0; kx < w.kw; ++kx) {
+        int iy = oy * g.stride - g.ph + ky, ix = ox * g.stride - g.pw + kx;
+        if (g.reflect) { iy = reflect_idx(iy, IH); ix = reflect_idx(ix, IW); }
+        if (iy < 0 || iy >= IH || ix < 0 || ix >= IW) continue;
+        const float* p0 = in0.p + in0.off(n, iy, ix);
+        const float* p1 = in1.p ? in1.p + in1.off(n, iy, ix) : nullptr;
+        const float* wt = w.w + (int64_t)(ky * w.kw + kx) * w.cin * w.cout_ld;
+        for (int ci = 0; ci < w.cin; ++ci) {
+          float x = ci < a.c0 ? p0[ci] : p1[ci - a.c0];
+          const float* wr = wt + (int64_t)ci * w.cout_ld;
+          for (int co = 0; co < w.cout; ++co) acc[co] += x * wr[co];
+        }
+      }
+    float* o = out.p + out.off(n, oy, ox);
+    for (int co = 0; co < w.cout; ++co) o[co] = conv_epilogue(a, acc[co], n, oy, ox, co);
+  }
+#else
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  a.vec_ok = in0.ld % 4 == 0 && al16(in0.p) && (in0.sn % 4 == 0) &&
+             (!in1.p || (in1.ld % 4 == 0 && al16(in1.p) && in1.sn % 4 == 0 && in0.c % 4 == 0));
+  if (in1.p && in0.c % 16 != 0) throw std::runtime_error("conv2d: first concat segment must be a multiple of 16 channels");
+  if (w.cout_ld % 4 != 0) throw std::runtime_error("conv2d: cout_ld must be a multiple of 4");
+  if (w.cout <= 16) {
+    dim3 grid((a.M + 127) / 128, (w.cout + 15) / 16);
+    conv2d_simt_kernel<16, 4, 2><<<grid, 256, 0, cx.stream>>>(a);
+  } else {
+    dim3 grid((a.M + 127) / 128, (w.cout + 63) / 64);
+    conv2d_simt_kernel<64, 8, 4><<<grid, 256, 0, cx.stream>>>(a);
+  }
+  gv_check_launch("conv2d");
+#endif
+}
+
+}  // namespace gv

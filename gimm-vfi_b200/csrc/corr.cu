@@ -1,0 +1,145 @@
+// All-pairs correlation volume, its 2x2 average-pooled pyramid and the 4-level
+// 9x9 bilinear lookup (reference: raft/corr.py:127-175, :23-93; sampler
+// raft/utils/utils.py:66-80).  fp32 throughout (the RAFT recurrence amplifies
+// rounding: see DESIGN.md "precision plan").
+#include "common.h"
+
+namespace gv {
+
+// ----------------------------------------------------------------- volume
+#ifndef GV_HOSTSIM
+// C[n][i][j] = scale * sum_k A[n,i,k] * B[n,j,k];  128x128 tile, BK=16, 8x8 per thread.
+__global__ void __launch_bounds__(256) corr_gemm_nt_kernel(TV fa, TV fb, float* __restrict__ vol, float scale) {
+  const int M = fa.h * fa.w, K = fa.c;
+  const int n = blockIdx.z;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+  __shared__ float As[16][128 + 4];
+  __shared__ float Bs[16][128 + 4];
+  const int tid = threadIdx.x;
+  const int tm = (tid / 16) * 8, tn = (tid % 16) * 8;
+  const float* A = fa.p + (int64_t)n * fa.sn;
+  const float* B = fb.p + (int64_t)n * fb.sn;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      int f4 = tid + it * 256;       // 512 float4 per operand tile
+      int row = f4 >> 2, q = f4 & 3;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      if (m0 + row < M) va = *reinterpret_cast<const float4*>(A + (int64_t)(m0 + row) * fa.ld + k0 + q * 4);
+      if (n0 + row < M) vb = *reinterpret_cast<const float4*>(B + (int64_t)(n0 + row) * fb.ld + k0 + q * 4);
+      As[q * 4 + 0][row] = va.x; As[q * 4 + 1][row] = va.y; As[q * 4 + 2][row] = va.z; As[q * 4 + 3][row] = va.w;
+      Bs[q * 4 + 0][row] = vb.x; Bs[q * 4 + 1][row] = vb.y; Bs[q * 4 + 2][row] = vb.z; Bs[q * 4 + 3][row] = vb.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] = As[k][tm + i]; b[i] = Bs[k][tn + i]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* C = vol + (int64_t)n * M * M;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int r = m0 + tm + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = n0 + tn + j;
+      if (c < M) C[(int64_t)r * M + c] = acc[i][j] * scale;
+    }
+  }
+}
+#endif
+
+void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale) {
+  if (cx.dry) return;
+  cx.launches++;
+  const int M = fa.h * fa.w;
+#ifdef GV_HOSTSIM
+  const int K = fa.c;
+  for (int n = 0; n < fa.n; ++n) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < M; ++i) {
+      const float* a = fa.p + (int64_t)n * fa.sn + (int64_t)i * fa.ld;
+      for (int j = 0; j < M; ++j) {
+        const float* b = fb.p + (int64_t)n * fb.sn + (int64_t)j * fb.ld;
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s += a[k] * b[k];
+        vol[((int64_t)n * M + i) * M + j] = s * scale;
+      }
+    }
+  }
+#else
+  if (fa.c % 16 != 0 || fa.ld % 4 != 0 || fb.ld % 4 != 0) throw std::runtime_error("corr_volume: feature dim must be a multiple of 16");
+  dim3 grid((M + 127) / 128, (M + 127) / 128, fa.n);
+  corr_gemm_nt_kernel<<<grid, 256, 0, cx.stream>>>(fa, fb, vol, scale);
+  gv_check_launch("corr_volume");
+#endif
+}
+
+// ------------------------------------------------------------------- pool
+// F.avg_pool2d(corr, 2, stride=2) over the trailing (h, w) image of every row (raft/corr.py:139-142).
+struct CorrPoolK {
+  const float* src; float* dst; int h, w, ho, wo;
+  GV_HD void operator()(int64_t i) const {
+    int x = (int)(i % wo); int64_t r = i / wo; int y = (int)(r % ho); int64_t row = r / ho;
+    const float* s = src + row * ((int64_t)h * w) + (int64_t)(2 * y) * w + 2 * x;
+    dst[i] = (s[0] + s[1] + s[w] + s[w + 1]) * 0.25f;
+  }
+};
+void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w) {
+  int ho = h / 2, wo = w / 2;
+  parallel_for(cx, rows * ho * wo, CorrPoolK{src, dst, h, w, ho, wo}, "corr_pool");
+}
+
+// ----------------------------------------------------------------- lookup
+// raft/corr.py:144-165.  out channel = lvl*81 + a*9 + b samples level `lvl` of row
+// (n, pixel) at (x/2^lvl + (a-4), y/2^lvl + (b-4)) — the "transposed window" of the
+// reference's meshgrid(dy, dx) — bilinear, zero padding, align_corners=True, going
+// through the same normalise / un-normalise float round trip as bilinear_sampler +
+// grid_sample.
+struct CorrLookupK {
+  CorrPyr pyr; TV coords, out;
+  GV_HD void operator()(int64_t i) const {
+    int ch = (int)(i % 324); int64_t r = i / 324;
+    int x = (int)(r % coords.w); r /= coords.w; int y = (int)(r % coords.h); int n = (int)(r / coords.h);
+    int lvl = ch / 81, k = ch % 81, a = k / 9, b = k % 9;
+    const float* c = coords.p + coords.off(n, y, x);
+    float inv = 1.0f / (float)(1 << lvl);
+    int H = pyr.h[lvl], W = pyr.w[lvl];
+    float px = c[0] * inv + (float)(a - 4);
+    float py = c[1] * inv + (float)(b - 4);
+    float xg = 2.f * px / (float)(W - 1) - 1.f;
+    float yg = 2.f * py / (float)(H - 1) - 1.f;
+    float ix = ((xg + 1.f) / 2.f) * (float)(W - 1);
+    float iy = ((yg + 1.f) / 2.f) * (float)(H - 1);
+    float x0f = floorf(ix), y0f = floorf(iy);
+    int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+    float wx1 = ix - x0f, wx0 = (x0f + 1.f) - ix, wy1 = iy - y0f, wy0 = (y0f + 1.f) - iy;
+    int64_t row = (int64_t)n * pyr.rows_per_sample + (int64_t)y * coords.w + x;
+    const float* img = pyr.lvl[lvl] + row * ((int64_t)H * W);
+    float v = 0.f;
+    bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    if (vy0 && vx0) v += img[(int64_t)y0 * W + x0] * (wx0 * wy0);
+    if (vy0 && vx1) v += img[(int64_t)y0 * W + x1] * (wx1 * wy0);
+    if (vy1 && vx0) v += img[(int64_t)y1 * W + x0] * (wx0 * wy1);
+    if (vy1 && vx1) v += img[(int64_t)y1 * W + x1] * (wx1 * wy1);
+    out.p[out.off(n, y, x) + ch] = v;
+  }
+};
+void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords, const TV& out) {
+  parallel_for(cx, coords.pixels() * 324, CorrLookupK{pyr, coords, out}, "corr_lookup");
+}
+
+}  // namespace gv

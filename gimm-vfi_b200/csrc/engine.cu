@@ -1,0 +1,732 @@
+// Host orchestration of the GIMM-VFI-R per-pair interpolation path.
+// One stream, one pre-planned workspace, zero allocations / host syncs in
+// forward().  Reference call stack: gimmvfi_r.py:324-407.
+#include "engine.h"
+
+#include <algorithm>
+
+namespace gv {
+
+// ---------------------------------------------------------------------------
+// device memory helpers
+// ---------------------------------------------------------------------------
+#ifdef GV_HOSTSIM
+void gv_check_launch(const char*) {}
+void* dev_alloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
+void dev_free(void* p) { std::free(p); }
+void dev_upload(void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); }
+void dev_download(void* dst, const void* src, size_t bytes, gvStream_t) { std::memcpy(dst, src, bytes); }
+void dev_memset(void* dst, int v, size_t bytes, gvStream_t) { std::memset(dst, v, bytes); }
+void dev_copy(void* dst, const void* src, size_t bytes, gvStream_t) { std::memcpy(dst, src, bytes); }
+void dev_sync(gvStream_t) {}
+#else
+static void cuda_ok(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+void gv_check_launch(const char* what) { cuda_ok(cudaGetLastError(), what); }
+void* dev_alloc(size_t bytes) { void* p = nullptr; cuda_ok(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc"); return p; }
+void dev_free(void* p) { cudaFree(p); }
+void dev_upload(void* dst, const void* src, size_t bytes) { cuda_ok(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy H2D"); }
+void dev_download(void* dst, const void* src, size_t bytes, gvStream_t s) {
+  cuda_ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpy D2H");
+  cuda_ok(cudaStreamSynchronize(s), "sync");
+}
+void dev_memset(void* dst, int v, size_t bytes, gvStream_t s) { cuda_ok(cudaMemsetAsync(dst, v, bytes, s), "cudaMemsetAsync"); }
+void dev_copy(void* dst, const void* src, size_t bytes, gvStream_t s) { cuda_ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpy D2D"); }
+void dev_sync(gvStream_t s) { cuda_ok(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+#endif
+
+// ---------------------------------------------------------------------------
+// Engine: weights
+// ---------------------------------------------------------------------------
+Engine::Engine(int device) : device_(device) {
+#ifndef GV_HOSTSIM
+  cuda_ok(cudaSetDevice(device), "cudaSetDevice");
+  cudaDeviceProp prop;
+  cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  sm_count_ = prop.multiProcessorCount;
+#endif
+}
+
+Engine::~Engine() {
+  for (void* p : dev_allocs_) dev_free(p);
+}
+
+void Engine::load_weight(const std::string& key, const float* host, const int64_t* shape, int ndim) {
+  HostTensor t;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= shape[i]; }
+  t.data.assign(host, host + n);
+  raw_[key] = std::move(t);
+  finalized_ = false;
+}
+
+const HostTensor& Engine::raw(const std::string& key) const {
+  auto it = raw_.find(key);
+  if (it == raw_.end()) throw std::runtime_error("gimmvfi: missing weight '" + key + "'");
+  return it->second;
+}
+
+const float* Engine::upload(const std::vector<float>& v) {
+  void* d = dev_alloc(v.size() * sizeof(float));
+  dev_allocs_.push_back(d);
+  dev_upload(d, v.data(), v.size() * sizeof(float));
+  return static_cast<const float*>(d);
+}
+
+const float* Engine::vec(const std::string& key) {
+  auto it = vec_.find(key);
+  if (it != vec_.end()) return it->second;
+  const float* d = upload(raw(key).data);
+  vec_[key] = d;
+  return d;
+}
+
+// Conv2d weight (cout,cin,kh,kw) -> [tap][cin][cout_ld]; optional eval-mode BatchNorm
+// folding (bn = name of the BatchNorm2d), output scale and output-channel permutation.
+ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float out_scale, const std::vector<int>* perm) {
+  const HostTensor& W = raw(name + ".weight");
+  const HostTensor& Bv = raw(name + ".bias");
+  if (W.shape.size() != 4) throw std::runtime_error("gimmvfi: '" + name + ".weight' is not 4-D");
+  const int cout = (int)W.shape[0], cin = (int)W.shape[1], kh = (int)W.shape[2], kw = (int)W.shape[3];
+  std::vector<float> s(cout, out_scale), sh(cout, 0.f);
+  if (!bn.empty()) {
+    const auto& g = raw(bn + ".weight").data; const auto& be = raw(bn + ".bias").data;
+    const auto& mu = raw(bn + ".running_mean").data; const auto& var = raw(bn + ".running_var").data;
+    for (int co = 0; co < cout; ++co) {
+      float k = g[co] / std::sqrt(var[co] + 1e-5f);
+      s[co] = k * out_scale; sh[co] = (be[co] - mu[co] * k) * out_scale;
+    }
+  }
+  const int cout_ld = (cout + 3) & ~3;
+  std::vector<float> pw((size_t)kh * kw * cin * cout_ld, 0.f), pb(cout_ld, 0.f);
+  for (int co = 0; co < cout; ++co) {
+    const int src = perm ? (*perm)[co] : co;
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < kh * kw; ++t)
+        pw[((size_t)t * cin + ci) * cout_ld + co] = W.data[((size_t)src * cin + ci) * kh * kw + t] * s[src];
+    pb[co] = Bv.data[src] * s[src] + sh[src];
+  }
+  ConvW c;
+  c.w = upload(pw); c.b = upload(pb); c.cin = cin; c.cout = cout; c.kh = kh; c.kw = kw; c.cout_ld = cout_ld;
+  conv_[name] = c;
+  return c;
+}
+
+void Engine::finalize_weights() {
+  for (void* p : dev_allocs_) dev_free(p);
+  dev_allocs_.clear(); conv_.clear(); vec_.clear();
+  // --- RAFT encoders (raft/extractor.py:122-171); cnet's BatchNorm is folded
+  for (int e = 0; e < 2; ++e) {
+    const std::string p = e == 0 ? "flow_estimator.fnet" : "flow_estimator.cnet";
+    const bool bn = e == 1;
+    pack_conv(p + ".conv1", bn ? p + ".norm1" : "");
+    for (int li = 1; li <= 3; ++li)
+      for (int bi = 0; bi < 2; ++bi) {
+        const std::string q = p + ".layer" + std::to_string(li) + "." + std::to_string(bi);
+        pack_conv(q + ".conv1", bn ? q + ".norm1" : "");
+        pack_conv(q + ".conv2", bn ? q + ".norm2" : "");
+        if (bi == 0 && li > 1) pack_conv(q + ".downsample.0", bn ? q + ".downsample.1" : "");
+      }
+    pack_conv(p + ".conv2");
+  }
+  // --- RAFT update block (raft/update.py:94-154)
+  const std::string u = "flow_estimator.update_block";
+  for (const char* n : {".encoder.convc1", ".encoder.convc2", ".encoder.convf1", ".encoder.convf2", ".encoder.conv",
+                        ".gru.convz1", ".gru.convr1", ".gru.convq1", ".gru.convz2", ".gru.convr2", ".gru.convq2",
+                        ".flow_head.conv1", ".flow_head.conv2", ".mask.0"})
+    pack_conv(u + n);
+  pack_conv(u + ".mask.2", "", 0.25f);  // "scale mask to balance gradients" raft/update.py:153
+  // --- feature projections (gimmvfi_r.py:51-53)
+  pack_conv("amt_last_cproj"); pack_conv("amt_second_last_cproj"); pack_conv("amt_fproj");
+  // --- decoders (fi_components.py:229-305)
+  {
+    const std::string p = "amt_init_decoder";
+    for (int i = 1; i <= 5; ++i) { pack_conv(p + ".upsample." + std::to_string(i) + ".0"); vec(p + ".upsample." + std::to_string(i) + ".1.weight"); }
+    pack_conv(p + ".upsample.6", p + ".upsample.7");
+    pack_conv(p + ".convblock.0.0"); vec(p + ".convblock.0.1.weight");
+    // head re-ordered to [ft(128) | dflow0(2) | dflow1(2) | mask(1)] so ft_ is an aligned slice
+    std::vector<int> perm(133);
+    for (int i = 0; i < 128; ++i) perm[i] = 5 + i;
+    for (int i = 0; i < 5; ++i) perm[128 + i] = i;
+    pack_conv(p + ".convblock.4", "", 1.f, &perm);
+  }
+  {
+    const std::string p = "amt_final_decoder";
+    for (int i = 2; i <= 6; ++i) { pack_conv(p + ".upsample." + std::to_string(i) + ".0"); vec(p + ".upsample." + std::to_string(i) + ".1.weight"); }
+    pack_conv(p + ".upsample.7", p + ".upsample.8");
+    pack_conv(p + ".convblock.0.0"); vec(p + ".convblock.0.1.weight");
+    pack_conv(p + ".convblock.4");
+  }
+  for (const char* d : {"amt_init_decoder", "amt_final_decoder"})
+    for (int k = 1; k <= 3; ++k) {
+      const std::string q = std::string(d) + ".convblock." + std::to_string(k);
+      for (int c = 1; c <= 4; ++c) { pack_conv(q + ".conv" + std::to_string(c) + ".0"); vec(q + ".conv" + std::to_string(c) + ".1.weight"); }
+      pack_conv(q + ".conv5"); vec(q + ".prelu.weight");
+    }
+  for (const char* d : {"amt_update4_low", "amt_update4_high"})
+    for (const char* n : {".convc1", ".convc2", ".convf1", ".convf2", ".conv", ".gru.0", ".gru.2", ".feat_head.0", ".feat_head.2", ".flow_head.0", ".flow_head.2"})
+      pack_conv(std::string(d) + n);
+  pack_conv("amt_comb_block.0"); vec("amt_comb_block.1.weight"); pack_conv("amt_comb_block.2");
+  // --- GIMM encoders (gimmvfi_r.py:86-109)
+  for (const char* n : {"cnn_encoder.0", "cnn_encoder.1", "cnn_encoder.3.layers.0", "cnn_encoder.3.layers.2", "cnn_encoder.4.layers.0",
+                        "cnn_encoder.4.layers.2", "cnn_encoder.5.layers.0", "cnn_encoder.5.layers.2", "cnn_encoder.7", "res_conv.0",
+                        "res_conv.1", "res_conv.3.layers.0", "res_conv.3.layers.2", "res_conv.5"})
+    pack_conv(n);
+  // --- HypoNet (hyponet.py:99-143): fan-in-normalised columns, bias row, +output_bias on the last layer
+  for (int l = 0; l < 5; ++l) {
+    const std::string key = "hyponet.params_dict.linear_wb" + std::to_string(l);
+    const HostTensor& wb = raw(key);
+    const int fin = (int)wb.shape[0] - 1, fout = (int)wb.shape[1];
+    const int ld = (fout + 3) & ~3;
+    std::vector<float> pw((size_t)fin * ld, 0.f), pb(ld, 0.f);
+    for (int co = 0; co < fout; ++co) {
+      double nrm = 0.0;
+      for (int ci = 0; ci < fin; ++ci) { double v = wb.data[(size_t)ci * fout + co]; nrm += v * v; }
+      float d = std::max((float)std::sqrt(nrm), 1e-12f);
+      for (int ci = 0; ci < fin; ++ci) pw[(size_t)ci * ld + co] = wb.data[(size_t)ci * fout + co] / d;
+      pb[co] = wb.data[(size_t)fin * fout + co] + (l == 4 ? 0.5f : 0.f);
+    }
+    ConvW c; c.w = upload(pw); c.b = upload(pb); c.cin = fin; c.cout = fout; c.kh = c.kw = 1; c.cout_ld = ld;
+    conv_[key] = c;
+  }
+  g9_ = vec("g_filter"); alpha_fe_ = vec("alpha_fe"); alpha_v_ = vec("alpha_v");
+  finalized_ = true;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+struct Net {
+  Engine& E; Ctx& cx;
+  const ConvW& W(const std::string& n) const {
+    auto it = E.conv_.find(n);
+    if (it == E.conv_.end()) throw std::runtime_error("gimmvfi: conv '" + n + "' not packed");
+    return it->second;
+  }
+  const float* V(const std::string& n) const { return E.vec_.at(n); }
+  static ConvGeom geom(const ConvW& w, int stride = 1, bool reflect = false) {
+    ConvGeom g; g.stride = stride; g.ph = w.kh / 2; g.pw = w.kw / 2; g.reflect = reflect ? 1 : 0; return g;
+  }
+  // plain conv + activation
+  void conv(const std::string& name, const TV& in, const TV& out, int act = ACT_NONE, const float* slope = nullptr, int stride = 1,
+            bool reflect = false) {
+    const ConvW& w = W(name); ConvEpi e; e.act1 = act; e.slope1 = slope;
+    conv2d(cx, in, TV(), w, geom(w, stride, reflect), e, out);
+  }
+  void conv_e(const std::string& name, const TV& in0, const TV& in1, const TV& out, const ConvEpi& e, int stride = 1, bool reflect = false) {
+    const ConvW& w = W(name);
+    conv2d(cx, in0, in1, w, geom(w, stride, reflect), e, out);
+  }
+  // Sequential(Conv2d, PReLU)  (fi_components.py:32-54)
+  void convrelu(const std::string& name, const TV& in, const TV& out) { conv(name + ".0", in, out, ACT_PRELU, V(name + ".1.weight")); }
+};
+
+static ConvW slice_cout(const ConvW& w, int co0, int cnt) {
+  ConvW s = w; s.w = w.w + co0; s.b = w.b + co0; s.cout = cnt; return s;
+}
+
+// raft/extractor.py:173-220.  x: (n,H,W,3) -> fmap (n,H/8,W/8,256) [+ layer2/layer3 outputs]
+static void raft_encoder(Net& N, const std::string& p, bool instance, const TV& x, const TV& out256, TV* feat4, TV* feat8,
+                         const ConvW* split_tanh_relu_out /*cnet: tanh/relu halves*/, const TV& net_out, const TV& inp_out) {
+  Ctx& cx = N.cx; Arena& A = cx.arena;
+  const int n = x.n, H2 = x.h / 2, W2 = x.w / 2;
+  float* mr = nullptr; float* scratch = nullptr;
+  if (instance) {
+    mr = A.alloc_f((size_t)n * 128 * 2);
+    TV probe = make_tv(nullptr, n, H2, W2, 128);
+    scratch = A.alloc_f((size_t)instnorm_scratch_floats(probe));
+  }
+  auto norm_act = [&](const TV& raw, int act1, const TV& res, int act2, const TV& dst) {
+    instnorm_stats(cx, raw, mr, scratch, 0);
+    instnorm_apply(cx, raw, mr, act1, res, act2, dst);
+  };
+  // stem
+  TV a = A.tensor(n, H2, W2, 64);
+  if (instance) {
+    TV r = A.tensor(n, H2, W2, 64);
+    N.conv(p + ".conv1", x, r, ACT_NONE, nullptr, 2);
+    norm_act(r, ACT_RELU, TV(), ACT_NONE, a);
+  } else {
+    N.conv(p + ".conv1", x, a, ACT_RELU, nullptr, 2);
+  }
+  TV cur = a;
+  int cin = 64;
+  const int dims[3] = {64, 96, 128};
+  for (int li = 1; li <= 3; ++li) {
+    const int dim = dims[li - 1];
+    for (int bi = 0; bi < 2; ++bi) {
+      const std::string q = p + ".layer" + std::to_string(li) + "." + std::to_string(bi);
+      const int stride = (bi == 0 && li > 1) ? 2 : 1;
+      const int oh = cur.h / stride, ow = cur.w / stride;
+      TV y1 = A.tensor(n, oh, ow, dim), y2 = A.tensor(n, oh, ow, dim), outb = A.tensor(n, oh, ow, dim);
+      TV skip = cur;
+      if (instance) {
+        TV r = A.tensor(n, oh, ow, dim);
+        N.conv(q + ".conv1", cur, r, ACT_NONE, nullptr, stride);
+        norm_act(r, ACT_RELU, TV(), ACT_NONE, y1);
+        N.conv(q + ".conv2", y1, r, ACT_NONE);
+        if (stride != 1) {
+          TV d = A.tensor(n, oh, ow, dim);
+          N.conv(q + ".downsample.0", cur, d, ACT_NONE, nullptr, stride);
+          norm_act(d, ACT_NONE, TV(), ACT_NONE, y2);  // y2 reused as the normalised skip
+          skip = y2;
+        }
+        norm_act(r, ACT_RELU, skip, ACT_RELU, outb);  // relu(x + relu(norm2(conv2)))
+      } else {
+        N.conv(q + ".conv1", cur, y1, ACT_RELU, nullptr, stride);
+        if (stride != 1) { N.conv(q + ".downsample.0", cur, y2, ACT_NONE, nullptr, stride); skip = y2; }
+        ConvEpi e; e.act1 = ACT_RELU; e.res = skip; e.act2 = ACT_RELU;
+        N.conv_e(q + ".conv2", y1, TV(), outb, e);
+      }
+      cur = outb; cin = dim;
+    }
+    if (li == 2 && feat4) *feat4 = cur;
+    if (li == 3 && feat8) *feat8 = cur;
+  }
+  (void)cin;
+  if (split_tanh_relu_out) {
+    // cnet: net = tanh(first 128), inp = relu(last 128)  (raft/raft.py:133-136)
+    const ConvW& w = *split_tanh_relu_out;
+    ConvEpi e1; e1.act1 = ACT_TANH;
+    conv2d(cx, cur, TV(), slice_cout(w, 0, 128), ConvGeom(), e1, net_out);
+    ConvEpi e2; e2.act1 = ACT_RELU;
+    conv2d(cx, cur, TV(), slice_cout(w, 128, 128), ConvGeom(), e2, inp_out);
+  } else {
+    N.conv(p + ".conv2", cur, out256);
+  }
+}
+
+struct Pyramid {
+  float* lvl[4]; int h[4], w[4]; int64_t N;  // rows per sample
+  CorrPyr view(int sample0) const {
+    CorrPyr c;
+    for (int l = 0; l < 4; ++l) { c.lvl[l] = lvl[l] + (int64_t)sample0 * N * h[l] * w[l]; c.h[l] = h[l]; c.w[l] = w[l]; }
+    c.rows_per_sample = N;
+    return c;
+  }
+};
+
+// Volumes for both directions stacked on the batch axis: samples [0,B) hold
+// <F[s], F[s+B]>, samples [B,2B) hold <F[s], F[s-B]> (= the transposed volume,
+// raft/corr.py:32).  Level l is (2B*N) x (h_l*w_l).
+static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B) {
+  Arena& A = cx.arena;
+  Pyramid P; P.N = (int64_t)F.h * F.w;
+  int h = F.h, w = F.w;
+  for (int l = 0; l < 4; ++l) { P.h[l] = h; P.w[l] = w; P.lvl[l] = A.alloc_f((size_t)2 * B * P.N * h * w); h /= 2; w /= 2; }
+  corr_volume(cx, F.batch(0, B), F.batch(B, B), P.lvl[0], 1.0f / std::sqrt((float)F.c));
+  corr_volume(cx, F.batch(B, B), F.batch(0, B), P.lvl[0] + (int64_t)B * P.N * P.N, 1.0f / std::sqrt((float)F.c));
+  for (int l = 1; l < 4; ++l) corr_pool(cx, P.lvl[l - 1], P.lvl[l], (int64_t)2 * B * P.N, P.h[l - 1], P.w[l - 1]);
+  return P;
+}
+
+// AMT update block (fi_components.py:157-222).  `ft` (128 ch view) and `fl4` (4 ch) are updated in place.
+static void amt_update(Net& N, const std::string& p, bool low, const TV& ft, const TV& fl4, const TV& flow_in /*4ch at block res*/,
+                       const TV& corr648) {
+  Ctx& cx = N.cx; Arena& A = cx.arena;
+  const size_t mk = A.mark();
+  const int n = corr648.n, h = corr648.h, w = corr648.w;
+  TV inp = A.tensor(n, h, w, 320);
+  if (low) resize_bilinear(cx, ft, inp.slice(192, 128), 2.f, 2.f, 1.f, 0, ACT_NONE);  // resize(net, 1/2)
+  else copy_channels(cx, ft, inp.slice(192, 128));
+  copy_channels(cx, flow_in, inp.slice(188, 4));
+  TV cor = A.tensor(n, h, w, 256), cf = A.tensor(n, h, w, 256), flo = A.tensor(n, h, w, 128);
+  N.conv(p + ".convc1", corr648, cor, ACT_LRELU);
+  N.conv(p + ".convc2", cor, cf.slice(0, 192), ACT_LRELU);
+  N.conv(p + ".convf1", flow_in, flo, ACT_LRELU);
+  N.conv(p + ".convf2", flo, cf.slice(192, 64), ACT_LRELU);
+  N.conv(p + ".conv", cf, inp.slice(0, 188), ACT_LRELU);
+  TV g1 = A.tensor(n, h, w, 192), g2 = A.tensor(n, h, w, 192), hd = A.tensor(n, h, w, 192);
+  N.conv(p + ".gru.0", inp, g1, ACT_LRELU);
+  N.conv(p + ".gru.2", g1, g2);
+  TV dnet = A.tensor(n, h, w, 128), dflow = A.tensor(n, h, w, 4);
+  N.conv(p + ".feat_head.0", g2, hd, ACT_LRELU);
+  N.conv(p + ".feat_head.2", hd, dnet);
+  N.conv(p + ".flow_head.0", g2, hd, ACT_LRELU);
+  N.conv(p + ".flow_head.2", hd, dflow);
+  if (low) {
+    resize_bilinear(cx, dnet, ft, 0.5f, 0.5f, 1.f, 1, ACT_NONE);
+    resize_bilinear(cx, dflow, fl4, 0.5f, 0.5f, 2.f, 1, ACT_NONE);
+  } else {
+    add_inplace_slices(cx, ft, dnet);
+    add_inplace_slices(cx, fl4, dflow);
+  }
+  A.release(mk);
+}
+
+// ResBlock (fi_components.py:97-154), in place on x.
+static void resblock(Net& N, const std::string& q, const TV& x, int C, int S) {
+  Ctx& cx = N.cx; Arena& A = cx.arena;
+  const size_t mk = A.mark();
+  TV a = A.tensor(x.n, x.h, x.w, C), b = A.tensor(x.n, x.h, x.w, C), s1 = A.tensor(x.n, x.h, x.w, S), s2 = A.tensor(x.n, x.h, x.w, S);
+  N.convrelu(q + ".conv1", x, a);
+  N.convrelu(q + ".conv2", a.slice(C - S, S), s1);
+  { ConvEpi e; e.act1 = ACT_PRELU; e.slope1 = N.V(q + ".conv3.1.weight"); N.conv_e(q + ".conv3.0", a.slice(0, C - S), s1, b, e); }
+  N.convrelu(q + ".conv4", b.slice(C - S, S), s2);
+  { ConvEpi e; e.res = x; e.act2 = ACT_PRELU; e.slope2 = N.V(q + ".prelu.weight"); N.conv_e(q + ".conv5", b.slice(0, C - S), s2, x, e); }
+  A.release(mk);
+}
+
+struct RaftPrepK {  // image = 2 * ((255 * x) / 255) - 1   (gimmvfi_r.py:349 + raft/raft.py:111-112)
+  TV src, dst;
+  GV_HD void operator()(int64_t i) const {
+    float v = src.p[i];
+    dst.p[i] = 2.f * ((255.f * v) / 255.0f) - 1.0f;
+  }
+};
+struct ScaleShiftK {  // y = a*x + b on a dense tensor
+  const float* src; float* dst; float a, b;
+  GV_HD void operator()(int64_t i) const { dst[i] = a * src[i] - b; }
+};
+
+static void check_problem(const Problem& p) {
+  if (p.B < 1 || p.T < 1) throw std::runtime_error("gimmvfi: B and T must be >= 1");
+  const int H = p.H(), W = p.W();
+  if (H % 8 || W % 8 || H < 128 || W < 128)
+    throw std::runtime_error("gimmvfi: network resolution must be a multiple of 8 and >= 128 (got " + std::to_string(H) + "x" + std::to_string(W) + ")");
+  if (p.Hc != H || p.Wc != W)
+    throw std::runtime_error("gimmvfi: coordinate grid must match the network resolution (frame_synthesize consumes flow_t at that size)");
+}
+
+void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
+  check_problem(P);
+  Net N{*this, cx};
+  Arena& A = cx.arena;
+  const int B = P.B, Hf = P.Hf, Wf = P.Wf, H = P.H(), W = P.W(), T = P.T;
+  const int h = H / 8, w = W / 8, H4 = H / 4, W4 = W / 4;
+  const bool ds = P.ds > 0.f;
+  const float rds = ds ? (float)(1.0 / (double)P.ds) : 1.f;       // resize(x, ds): src = rds*(dst+.5)-.5
+  const double inv_d = ds ? (double)Hf / (double)H : 1.0;          // gimmvfi_r.py:297
+  const float inv = (float)inv_d, rinv = (float)(1.0 / inv_d);
+
+  // ------------------------------------------------------------ inputs
+  // frames as NHWC, stacked [I0 batch ; I1 batch]
+  TV full01 = A.tensor(2 * B, Hf, Wf, 3, 4);
+  for (int f = 0; f < 2; ++f)
+    nchw_to_nhwc(cx, io.img_xs + (int64_t)f * Hf * Wf, (int64_t)6 * Hf * Wf, (int64_t)2 * Hf * Wf, full01.batch(f * B, B), 1.f, 0.f);
+  TV img01 = full01;
+  if (ds) {
+    img01 = A.tensor(2 * B, H, W, 3, 4);
+    resize_bilinear(cx, full01, img01, rds, rds, 1.f, 0, ACT_NONE);  // gimmvfi_r.py:329-337
+  }
+  TV raft_in = A.tensor(2 * B, H, W, 3, 4);
+  TV syn = A.tensor(2 * B, H, W, 3, 4);       // 2*x - 1  (gimmvfi_r.py:230-231)
+  {
+    // dense views (ld == 4): run over the padded buffers, padding lane included (harmless)
+    int64_t cnt = (int64_t)2 * B * H * W * 4;
+    TV s = img01; s.c = 4; TV d = raft_in; d.c = 4;
+    parallel_for(cx, cnt, RaftPrepK{s, d}, "raft_prep");
+    parallel_for(cx, cnt, ScaleShiftK{img01.p, syn.p, 2.f, 1.0f}, "img_to_pm1");
+  }
+  TV synf = syn;
+  if (ds) {
+    synf = A.tensor(2 * B, Hf, Wf, 3, 4);
+    parallel_for(cx, (int64_t)2 * B * Hf * Wf * 4, ScaleShiftK{full01.p, synf.p, 2.f, 1.0f}, "img_to_pm1_full");
+  }
+
+  // persistent across stages
+  TV flow_up = A.tensor(2 * B, H, W, 2);            // [f01 ; f10]
+  TV fmap = A.tensor(2 * B, h, w, 256);             // fnet features of [I0 ; I1]
+  TV feat4 = A.tensor(2 * B, H4, W4, 128), feat8 = A.tensor(2 * B, h, w, 256);  // projected context features
+  float* scaler = A.alloc_f(std::max(B, 64));
+
+  // ------------------------------------------------------------ RAFT (both directions batched)
+  {
+    const size_t mk = A.mark();
+    TV hx = A.tensor(2 * B, h, w, 384);              // [h | inp | motion]
+    TV c4, c8;
+    {
+      raft_encoder(N, "flow_estimator.fnet", true, raft_in, fmap, nullptr, nullptr, nullptr, TV(), TV());
+      // the encoder's temporaries stay allocated until `mk` is released (bump allocator)
+      const ConvW& wc = N.W("flow_estimator.cnet.conv2");
+      raft_encoder(N, "flow_estimator.cnet", false, raft_in, TV(), &c4, &c8, &wc, hx.slice(0, 128), hx.slice(128, 128));
+    }
+    tap("raft.fmap", fmap);
+    // context features for the synthesis net (gimmvfi_r.py:134-141)
+    N.conv("amt_second_last_cproj", c4, feat4);
+    N.conv("amt_last_cproj", c8, feat8);
+
+    Pyramid pyr = build_pyramid(cx, fmap, B);
+    const std::string u = "flow_estimator.update_block";
+    TV coords1 = A.tensor(2 * B, h, w, 2);
+    TV flow = A.tensor(2 * B, h, w, 2);
+    TV corr = A.tensor(2 * B, h, w, 324), cor1 = A.tensor(2 * B, h, w, 256), corflo = A.tensor(2 * B, h, w, 256);
+    TV flo1 = A.tensor(2 * B, h, w, 128), zb = A.tensor(2 * B, h, w, 128), rh = A.tensor(2 * B, h, w, 128);
+    TV fh = A.tensor(2 * B, h, w, 256), mask = A.tensor(2 * B, h, w, 576);
+    init_coords(cx, coords1);
+    TV hcur = hx.slice(0, 128), xin = hx.slice(128, 256);
+    for (int it = 0; it < raft_iters; ++it) {
+      corr_lookup(cx, pyr.view(0), coords1, corr);
+      coords_minus_grid(cx, coords1, flow, hx.slice(382, 2));
+      if (it == 0) tap("raft.corr_it0", corr);
+      // BasicMotionEncoder raft/update.py:94-112
+      N.conv(u + ".encoder.convc1", corr, cor1, ACT_RELU);
+      N.conv(u + ".encoder.convc2", cor1, corflo.slice(0, 192), ACT_RELU);
+      N.conv(u + ".encoder.convf1", flow, flo1, ACT_RELU);
+      N.conv(u + ".encoder.convf2", flo1, corflo.slice(192, 64), ACT_RELU);
+      N.conv(u + ".encoder.conv", corflo, hx.slice(256, 126), ACT_RELU);
+      // SepConvGRU raft/update.py:35-73 (horizontal 1x5 then vertical 5x1)
+      for (const char* sfx : {"1", "2"}) {
+        ConvEpi ez; ez.act1 = ACT_SIGMOID;
+        N.conv_e(u + ".gru.convz" + sfx, hx, TV(), zb, ez);
+        ConvEpi er; er.act1 = ACT_SIGMOID; er.mul = hcur;
+        N.conv_e(u + ".gru.convr" + sfx, hx, TV(), rh, er);
+        ConvEpi eq; eq.act1 = ACT_TANH; eq.gru_z = zb; eq.gru_h = hcur;
+        N.conv_e(u + ".gru.convq" + sfx, rh, xin, hcur, eq);
+      }
+      // FlowHead raft/update.py:6-14; coords1 += delta_flow (raft/raft.py:153)
+      N.conv(u + ".flow_head.conv1", hcur, fh, ACT_RELU);
+      { ConvEpi e; e.res = coords1; N.conv_e(u + ".flow_head.conv2", fh, TV(), coords1, e); }
+      if (it == 0 || it == 4) { /* debug snapshots are cheap copies */
+        if (debug_) { TV snap = A.tensor(2 * B, h, w, 2); coords_minus_grid(cx, coords1, snap, TV()); tap("raft.lowres_flow_it" + std::to_string(it), snap); }
+      }
+      if (it == raft_iters - 1) {
+        // only the last iteration's mask / upsample is consumed (raft/raft.py:159-167)
+        N.conv(u + ".mask.0", hcur, fh, ACT_RELU);
+        N.conv(u + ".mask.2", fh, mask);
+        coords_minus_grid(cx, coords1, flow, TV());
+        tap("raft.lowres_flow_final", flow);
+        convex_upsample(cx, flow, mask, flow_up);
+      }
+    }
+    tap("raft.net_final", hcur);
+    if (!debug_) A.release(mk);
+  }
+  if (io.raft_flow)
+    for (int j = 0; j < 2; ++j)
+      nhwc_to_nchw(cx, flow_up.batch(j * B, B), io.raft_flow + (int64_t)j * H * W, (int64_t)4 * H * W, (int64_t)2 * H * W, 1.f, 0.f, 0);
+
+  // ------------------------------------------------------------ bidirectional volume on projected features
+  TV fproj = A.tensor(2 * B, h, w, 256);
+  N.conv("amt_fproj", fmap, fproj);
+  Pyramid bpyr = build_pyramid(cx, fproj, B);   // gimmvfi_r.py:133, raft/corr.py:23-44
+
+  // ------------------------------------------------------------ hoisted (t-independent) decoder feature upsampling
+  TV fup4 = A.tensor(2 * B, H4, W4, 128);   // NewInitDecoder.upsample   fi_components.py:234-244
+  TV fup1 = A.tensor(2 * B, H, W, 64);      // NewMultiFlowDecoder.upsample fi_components.py:284-295
+  {
+    const size_t mk = A.mark();
+    const std::string p = "amt_init_decoder.upsample.";
+    TV a = A.tensor(2 * B, H4, W4, 64), b = A.tensor(2 * B, H4, W4, 64), c = A.tensor(2 * B, H4, W4, 128);
+    pixel_shuffle(cx, feat8, a, 1);
+    N.convrelu(p + "1", a, b); N.convrelu(p + "2", b, a); N.convrelu(p + "3", a, b); N.convrelu(p + "4", b, a);
+    N.convrelu(p + "5", a, c);
+    N.conv(p + "6", c, fup4, ACT_RELU);  // 1x1 + folded BatchNorm + ReLU
+    A.release(mk);
+  }
+  {
+    const size_t mk = A.mark();
+    const std::string p = "amt_final_decoder.upsample.";
+    TV a = A.tensor(2 * B, H, W, 8), b = A.tensor(2 * B, H, W, 32), c = A.tensor(2 * B, H, W, 32), d = A.tensor(2 * B, H, W, 64);
+    pixel_shuffle(cx, feat4, a, 2);
+    N.convrelu(p + "2", a, b); N.convrelu(p + "3", b, c); N.convrelu(p + "4", c, b); N.convrelu(p + "5", b, c);
+    N.convrelu(p + "6", c, d);
+    N.conv(p + "7", d, fup1, ACT_RELU);
+    A.release(mk);
+  }
+
+  // ------------------------------------------------------------ GIMM (t-independent part)  gimmvfi_r.py:158-168
+  TV f01 = flow_up.batch(0, B), f10 = flow_up.batch(B, B);
+  {
+    float* sc = A.alloc_f((size_t)absmax_scratch_floats(f01));
+    absmax_per_sample(cx, f01, f10, scaler, sc);
+  }
+  TV nf = A.tensor(2 * B, H, W, 2);
+  normalize_flow_pair(cx, f01, f10, scaler, nf.batch(0, B), nf.batch(B, B));
+  if (io.nflow)
+    for (int j = 0; j < 2; ++j)
+      nhwc_to_nchw(cx, nf.batch(j * B, B), io.nflow + (int64_t)j * H * W, (int64_t)4 * H * W, (int64_t)2 * H * W, 1.f, 0.f, 0);
+  TV wts = A.tensor(2 * B, H, W, 1);
+  splat_weights(cx, f01, f10, g9_, alpha_fe_, alpha_v_, wts.batch(0, B));
+  splat_weights(cx, f10, f01, g9_, alpha_fe_, alpha_v_, wts.batch(B, B));
+  tap("gimm.splat_w", wts);
+  TV X64 = A.tensor(B, H, W, 64);   // [lat0 | lat1 | splat0 | splat1]
+  {
+    const size_t mk = A.mark();
+    TV a = A.tensor(2 * B, H, W, 16), x = A.tensor(2 * B, H, W, 32), y = A.tensor(2 * B, H, W, 32), m = A.tensor(2 * B, H, W, 32);
+    N.conv("cnn_encoder.0", nf, a);
+    N.conv("cnn_encoder.1", a, x, ACT_LRELU);
+    for (int i = 3; i <= 5; ++i) {  // LateralBlock fi_components.py:17-29 (+ the LeakyReLU after the last one)
+      const std::string q = "cnn_encoder." + std::to_string(i);
+      N.conv(q + ".layers.0", x, m, ACT_LRELU);
+      ConvEpi e; e.res = x; e.act2 = (i == 5) ? ACT_LRELU : ACT_NONE;
+      N.conv_e(q + ".layers.2", m, TV(), y, e);
+      std::swap(x, y);
+    }
+    N.conv("cnn_encoder.7", x.batch(0, B), X64.slice(0, 16), ACT_NONE, nullptr, 1, true);
+    N.conv("cnn_encoder.7", x.batch(B, B), X64.slice(16, 16), ACT_NONE, nullptr, 1, true);
+    A.release(mk);
+  }
+  tap("gimm.lat0", X64.slice(0, 16));
+
+  // ------------------------------------------------------------ per-timestep: GIMM decode + frame synthesis
+  TV grid_flow = A.tensor(B, h, w, 4);   // flow_4_lr = cat(fl0, fl1)
+  const size_t t_mark = A.mark();
+  for (int ti = 0; ti < T; ++ti) {
+    A.release(t_mark);
+    const float* tdev = io.t + (int64_t)ti * B;
+    // ---- forward splat of both latents to time t (gimmvfi_r.py:171-193)
+    TV acc = A.tensor(2 * B, H, W, 17, 20);
+    if (!cx.dry) dev_memset(acc.p, 0, (size_t)2 * B * H * W * 20 * sizeof(float), cx.stream);
+    softsplat_accumulate(cx, X64.slice(0, 16), f01, wts.batch(0, B), tdev, 0, acc.batch(0, B));
+    softsplat_accumulate(cx, X64.slice(16, 16), f10, wts.batch(B, B), tdev, 1, acc.batch(B, B));
+    softsplat_normalize(cx, acc.batch(0, B), X64.slice(32, 16));
+    softsplat_normalize(cx, acc.batch(B, B), X64.slice(48, 16));
+    if (ti == 0) tap("gimm.splat0", X64.slice(32, 16));
+    TV hin = A.tensor(B, H, W, 35, 36);  // HypoNet input [latent32 | t,y,x]
+    {
+      const size_t mk = A.mark();
+      TV a = A.tensor(B, H, W, 32), x = A.tensor(B, H, W, 64), m = A.tensor(B, H, W, 64), y = A.tensor(B, H, W, 64);
+      N.conv("res_conv.0", X64, a);
+      N.conv("res_conv.1", a, x, ACT_LRELU);
+      N.conv("res_conv.3.layers.0", x, m, ACT_LRELU);
+      { ConvEpi e; e.res = x; e.act2 = ACT_LRELU; N.conv_e("res_conv.3.layers.2", m, TV(), y, e); }
+      { ConvEpi e; e.res = X64.slice(32, 32); N.conv_e("res_conv.5", y, TV(), hin.slice(0, 32), e, 1, true); }
+      A.release(mk);
+    }
+    if (ti == 0) tap("gimm.latent", hin.slice(0, 32));
+    hypo_pack_input(cx, io.coords + (int64_t)ti * B * P.Hc * P.Wc * 3, hin.slice(32, 3));
+    TV ninr = A.tensor(B, H, W, 2);
+    {
+      const size_t mk = A.mark();
+      TV a = A.tensor(B, H, W, 128), b = A.tensor(B, H, W, 128);
+      N.conv("hyponet.params_dict.linear_wb0", hin, a, ACT_SIN);
+      N.conv("hyponet.params_dict.linear_wb1", a, b, ACT_SIN);
+      N.conv("hyponet.params_dict.linear_wb2", b, a, ACT_SIN);
+      N.conv("hyponet.params_dict.linear_wb3", a, b, ACT_SIN);
+      N.conv("hyponet.params_dict.linear_wb4", b, ninr);
+      A.release(mk);
+    }
+    if (io.ninrflow) nhwc_to_nchw(cx, ninr, io.ninrflow + (int64_t)ti * B * 2 * H * W, (int64_t)2 * H * W, (int64_t)H * W, 1.f, 0.f, 0);
+    TV flow_t = A.tensor(B, H, W, 2);
+    unnormalize_flow(cx, ninr, scaler, flow_t);
+    if (io.flowt) nhwc_to_nchw(cx, flow_t, io.flowt + (int64_t)ti * B * 2 * H * W, (int64_t)2 * H * W, (int64_t)H * W, 1.f, 0.f, 0);
+
+    // ---- frame_synthesize (gimmvfi_r.py:222-322)
+    TV s0 = syn.batch(0, B), s1 = syn.batch(B, B);
+    TV ft0 = A.tensor(B, H, W, 2), ft1 = A.tensor(B, H, W, 2);
+    scale_flow_t(cx, flow_t, tdev, ft0, ft1);
+    // NewInitDecoder (fi_components.py:255-276)
+    TV fin = A.tensor(B, H4, W4, 272);
+    TV f0in = fin.slice(256, 2), f1in = fin.slice(258, 2);
+    resize_bilinear(cx, ft0, f0in, 4.f, 4.f, 0.25f, 0, ACT_NONE);
+    resize_bilinear(cx, ft1, f1in, 4.f, 4.f, 0.25f, 0, ACT_NONE);
+    backwarp(cx, fup4.batch(0, B), f0in, fin.slice(0, 128));
+    backwarp(cx, fup4.batch(B, B), f1in, fin.slice(128, 128));
+    resize_bilinear(cx, s0, fin.slice(260, 3), 4.f, 4.f, 1.f, 0, ACT_NONE);
+    resize_bilinear(cx, s1, fin.slice(263, 3), 4.f, 4.f, 1.f, 0, ACT_NONE);
+    backwarp(cx, fin.slice(260, 3), f0in, fin.slice(266, 3));
+    backwarp(cx, fin.slice(263, 3), f1in, fin.slice(269, 3));
+    TV x4 = A.tensor(B, H4, W4, 128);
+    N.convrelu("amt_init_decoder.convblock.0", fin, x4);
+    for (int k = 1; k <= 3; ++k) resblock(N, "amt_init_decoder.convblock." + std::to_string(k), x4, 128, 64);
+    TV o136 = A.tensor(B, H4, W4, 133, 136);
+    N.conv("amt_init_decoder.convblock.4", x4, o136);
+    TV ft_4 = o136.slice(0, 128);
+    TV fl4 = A.tensor(B, H4, W4, 4), mask4 = A.tensor(B, H4, W4, 1);
+    flow_mask_split(cx, o136, f0in, f1in, fl4.slice(0, 2), fl4.slice(2, 2), mask4);
+    // warp_w_mask(scale=4) -> img_warp_4 (aux output, gimmvfi_r.py:259-261)
+    if (io.img_warp_4) {
+      const size_t mk = A.mark();
+      TV a0 = A.tensor(B, H, W, 2), a1 = A.tensor(B, H, W, 2), am = A.tensor(B, H, W, 1), wb = A.tensor(B, H, W, 3, 4);
+      resize_bilinear(cx, fl4.slice(0, 2), a0, 0.25f, 0.25f, 4.f, 0, ACT_NONE);
+      resize_bilinear(cx, fl4.slice(2, 2), a1, 0.25f, 0.25f, 4.f, 0, ACT_NONE);
+      resize_bilinear(cx, mask4, am, 0.25f, 0.25f, 1.f, 0, ACT_SIGMOID);
+      warp_blend(cx, s0, s1, a0, a1, am, wb);
+      nhwc_to_nchw(cx, wb, io.img_warp_4 + (int64_t)ti * B * 3 * H * W, (int64_t)3 * H * W, (int64_t)H * W, 0.5f, 1.0f, 1);
+      A.release(mk);
+    }
+    // _amt_corr_scale_lookup(downsample=2)  (gimmvfi_r.py:494-507)
+    TV corr648 = A.tensor(B, h, w, 648);
+    {
+      resize_bilinear(cx, fl4, grid_flow, 2.f, 2.f, 0.5f, 0, ACT_NONE);
+      TV cA = A.tensor(B, h, w, 2), cB = A.tensor(B, h, w, 2);
+      lookup_coords(cx, grid_flow.slice(2, 2), tdev, 0, cA);  // coord + flow1 * 1/(1-t) -> volume
+      lookup_coords(cx, grid_flow.slice(0, 2), tdev, 1, cB);  // coord + flow0 * 1/t     -> transposed volume
+      corr_lookup(cx, bpyr.view(0), cA, corr648.slice(0, 324));
+      corr_lookup(cx, bpyr.view(B), cB, corr648.slice(324, 324));
+    }
+    amt_update(N, "amt_update4_low", true, ft_4, fl4, grid_flow, corr648);
+    {
+      TV corr_hi = A.tensor(B, H4, W4, 648);
+      resize_bilinear(cx, corr648, corr_hi, 0.5f, 0.5f, 1.f, 0, ACT_NONE);  // gimmvfi_r.py:274
+      amt_update(N, "amt_update4_high", false, ft_4, fl4, fl4, corr_hi);
+      if (ti == 0) tap("syn.corr_4_hi", corr_hi);
+    }
+    if (ti == 0) { tap("syn.ft_4", ft_4); tap("syn.fl4", fl4); }
+    if (io.flowt0_4) nhwc_to_nchw(cx, fl4.slice(0, 2), io.flowt0_4 + (int64_t)ti * B * 2 * H4 * W4, (int64_t)2 * H4 * W4, (int64_t)H4 * W4, 1.f, 0.f, 0);
+    if (io.flowt1_4) nhwc_to_nchw(cx, fl4.slice(2, 2), io.flowt1_4 + (int64_t)ti * B * 2 * H4 * W4, (int64_t)2 * H4 * W4, (int64_t)H4 * W4, 1.f, 0.f, 0);
+
+    // NewMultiFlowDecoder (fi_components.py:307-340)
+    TV F0 = A.tensor(B, H, W, 6, 8), F1 = A.tensor(B, H, W, 6, 8), Mk = A.tensor(B, H, W, 3, 4), Rs = A.tensor(B, H, W, 9, 12);
+    {
+      const size_t mk = A.mark();
+      TV fin1 = A.tensor(B, H, W, 273, 276);
+      TV fl0 = fin1.slice(256, 2), fl1 = fin1.slice(258, 2), mk1 = fin1.slice(260, 1);
+      resize_bilinear(cx, fl4.slice(0, 2), fl0, 0.25f, 0.25f, 4.f, 0, ACT_NONE);
+      resize_bilinear(cx, fl4.slice(2, 2), fl1, 0.25f, 0.25f, 4.f, 0, ACT_NONE);
+      resize_bilinear(cx, ft_4, fin1.slice(0, 128), 0.25f, 0.25f, 1.f, 0, ACT_NONE);
+      resize_bilinear(cx, mask4, mk1, 0.25f, 0.25f, 1.f, 0, ACT_NONE);
+      backwarp(cx, fup1.batch(0, B), fl0, fin1.slice(128, 64));
+      backwarp(cx, fup1.batch(B, B), fl1, fin1.slice(192, 64));
+      copy_channels(cx, s0, fin1.slice(261, 3));
+      copy_channels(cx, s1, fin1.slice(264, 3));
+      backwarp(cx, s0, fl0, fin1.slice(267, 3));
+      backwarp(cx, s1, fl1, fin1.slice(270, 3));
+      TV x1 = A.tensor(B, H, W, 256);
+      N.convrelu("amt_final_decoder.convblock.0", fin1, x1);
+      for (int k = 1; k <= 3; ++k) resblock(N, "amt_final_decoder.convblock." + std::to_string(k), x1, 256, 64);
+      TV o24 = A.tensor(B, H, W, 24);
+      N.conv("amt_final_decoder.convblock.4", x1, o24);
+      final_heads(cx, o24, fl0, fl1, mk1, F0, F1, Mk, Rs);
+      A.release(mk);
+    }
+    TV F0f = F0, F1f = F1, Mkf = Mk, Rsf = Rs;
+    if (ds) {  // gimmvfi_r.py:294-303
+      F0f = A.tensor(B, Hf, Wf, 6, 8); F1f = A.tensor(B, Hf, Wf, 6, 8); Mkf = A.tensor(B, Hf, Wf, 3, 4); Rsf = A.tensor(B, Hf, Wf, 9, 12);
+      resize_bilinear(cx, F0, F0f, rinv, rinv, inv, 0, ACT_NONE);
+      resize_bilinear(cx, F1, F1f, rinv, rinv, inv, 0, ACT_NONE);
+      resize_bilinear(cx, Mk, Mkf, rinv, rinv, 1.f, 0, ACT_NONE);
+      resize_bilinear(cx, Rs, Rsf, rinv, rinv, 1.f, 0, ACT_NONE);
+    }
+    if (io.flowt0_1) nhwc_to_nchw(cx, F0f, io.flowt0_1 + (int64_t)ti * B * 6 * Hf * Wf, (int64_t)6 * Hf * Wf, (int64_t)Hf * Wf, 1.f, 0.f, 0);
+    if (io.flowt1_1) nhwc_to_nchw(cx, F1f, io.flowt1_1 + (int64_t)ti * B * 6 * Hf * Wf, (int64_t)6 * Hf * Wf, (int64_t)Hf * Wf, 1.f, 0.f, 0);
+    // multi_flow_combine + amt_comb_block at FULL resolution (fi_components.py:57-94)
+    {
+      TV w9 = A.tensor(B, Hf, Wf, 9, 12), mean3 = A.tensor(B, Hf, Wf, 3, 4), c18 = A.tensor(B, Hf, Wf, 18, 20), c3 = A.tensor(B, Hf, Wf, 3, 4);
+      multi_flow_blend(cx, synf.batch(0, B), synf.batch(B, B), F0f, F1f, Mkf, Rsf, w9, mean3);
+      N.conv("amt_comb_block.0", w9, c18, ACT_PRELU, N.V("amt_comb_block.1.weight"));
+      N.conv("amt_comb_block.2", c18, c3);
+      combine_output(cx, mean3, c3, io.imgt_pred + (int64_t)ti * B * 3 * Hf * Wf);
+    }
+  }
+}
+
+size_t Engine::plan(const Problem& p) {
+  if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
+  Ctx cx; cx.dry = true; cx.arena.dry = true; cx.sm_count = sm_count_;
+  IO io;  // null pointers; dry run never dereferences them, but optional outputs must be "present"
+  float* fake = reinterpret_cast<float*>(size_t(64));
+  io.img_xs = io.coords = io.t = fake;
+  io.imgt_pred = io.img_warp_4 = io.flowt0_1 = io.flowt1_1 = io.flowt0_4 = io.flowt1_4 = io.raft_flow = io.nflow = io.ninrflow = io.flowt = fake;
+  bool dbg = debug_;
+  run(cx, p, io);
+  debug_ = dbg;
+  taps_.clear();
+  return cx.arena.peak + 256;
+}
+
+void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t workspace_bytes, gvStream_t stream) {
+  if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
+  if (!io.img_xs || !io.coords || !io.t || !io.imgt_pred) throw std::runtime_error("gimmvfi: img_xs, coords, t and imgt_pred are required");
+  Ctx cx; cx.stream = stream; cx.sm_count = sm_count_;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  cx.arena.base = reinterpret_cast<char*>(base);
+  cx.arena.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
+  taps_.clear();
+  run(cx, p, io);
+  launches_ = cx.launches;
+}
+
+}  // namespace gv

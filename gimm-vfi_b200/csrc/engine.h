@@ -1,0 +1,84 @@
+// Engine: weights, workspace planning and the stream-ordered forward pass of
+// GIMM-VFI-R (reference hot path: gimmvfi_r.py:324-407).  See DESIGN.md.
+#pragma once
+#include "common.h"
+
+namespace gv {
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct Problem {
+  int B = 1;        // pairs in this call
+  int Hf = 0, Wf = 0;  // full (caller-padded) resolution
+  int T = 1;        // timesteps
+  float ds = 0.f;   // ds_factor (0 -> None)
+  int Hc = 0, Wc = 0;  // HypoNet coordinate grid (== network resolution at inference)
+  int H() const { return ds > 0.f ? (int)std::floor((double)Hf * (double)ds) : Hf; }
+  int W() const { return ds > 0.f ? (int)std::floor((double)Wf * (double)ds) : Wf; }
+};
+
+// Device pointers, caller-owned.  Layouts are the reference's (NCHW-style), one
+// contiguous block per output with the timestep as the outermost dimension.
+struct IO {
+  const float* img_xs = nullptr;   // (B,3,2,Hf,Wf) in [0,1]
+  const float* coords = nullptr;   // (T,B,1,Hc,Wc,3)  last dim (t,y,x)
+  const float* t = nullptr;        // (T,B)
+  float* imgt_pred = nullptr;      // (T,B,3,Hf,Wf)
+  float* img_warp_4 = nullptr;     // (T,B,3,H,W)
+  float* flowt0_1 = nullptr;       // (T,B,3,2,Hf,Wf)
+  float* flowt1_1 = nullptr;
+  float* flowt0_4 = nullptr;       // (T,B,2,H/4,W/4)
+  float* flowt1_4 = nullptr;
+  float* raft_flow = nullptr;      // (B,2,2,H,W)
+  float* nflow = nullptr;          // (B,2,2,H,W)
+  float* ninrflow = nullptr;       // (T,B,2,1,Hc,Wc)
+  float* flowt = nullptr;          // (T,B,2,Hc,Wc)
+};
+
+struct DebugTap { TV tv; };
+
+class Engine {
+ public:
+  explicit Engine(int device);
+  ~Engine();
+  void load_weight(const std::string& key, const float* host, const int64_t* shape, int ndim);
+  void finalize_weights();
+  size_t plan(const Problem& p);                       // dry run -> workspace bytes
+  void forward(const Problem& p, const IO& io, void* workspace, size_t workspace_bytes, gvStream_t stream);
+  int64_t last_launches() const { return launches_; }
+  // debug taps: name -> NHWC view inside the workspace of the last forward
+  void set_debug(bool on) { debug_ = on; }
+  const std::map<std::string, TV>& taps() const { return taps_; }
+  std::string last_error;
+  int raft_iters = 20;  // GIMMVFI_R hard-codes iters=20 (gimmvfi_r.py:126-132)
+  int device() const { return device_; }
+  bool finalized() const { return finalized_; }
+
+ private:
+  struct Impl;
+  void run(Ctx& cx, const Problem& p, const IO& io);
+  ConvW pack_conv(const std::string& name, const std::string& bn = "", float out_scale = 1.f, const std::vector<int>* perm = nullptr);
+  const float* upload(const std::vector<float>& v);
+  const float* vec(const std::string& key);
+  const HostTensor& raw(const std::string& key) const;
+  void tap(const std::string& name, const TV& tv) { if (debug_) taps_[name] = tv; }
+
+  int device_ = 0;
+  bool finalized_ = false, debug_ = false;
+  int64_t launches_ = 0;
+  int sm_count_ = 148;
+  std::map<std::string, HostTensor> raw_;
+  std::map<std::string, ConvW> conv_;
+  std::map<std::string, const float*> vec_;
+  std::vector<void*> dev_allocs_;
+  std::map<std::string, TV> taps_;
+  const float* g9_ = nullptr; const float* alpha_fe_ = nullptr; const float* alpha_v_ = nullptr;
+
+  // op helpers used by run()
+  friend struct Net;
+};
+
+}  // namespace gv

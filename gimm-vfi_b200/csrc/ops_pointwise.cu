@@ -1,0 +1,575 @@
+// HBM-bound thread-per-element kernels of the GIMM-VFI-R path (warp / resize /
+// splat / normalise / blend ...).  Every kernel body is a functor executed by
+// gv::parallel_for (CUDA grid-stride kernel, or an OpenMP loop under GV_HOSTSIM).
+// Reference semantics are cited per kernel (paths relative to
+// /root/reference/src/models/generalizable_INR/).
+#include "common.h"
+
+namespace gv {
+
+// ------------------------------------------------------------------ helpers
+// torch.linspace(-1, 1, n)[i]  (symmetric evaluation used by ATen's linspace)
+GV_HD float linspace_m1_1(int i, int n) {
+  if (n <= 1) return -1.f;
+  float step = 2.f / (float)(n - 1);
+  return (i < n / 2) ? (-1.f + step * (float)i) : (1.f - step * (float)(n - 1 - i));
+}
+
+struct BilinearTap {
+  int x0, y0, x1, y1;
+  float wx0, wx1, wy0, wy1;  // weights of x0/x1 and y0/y1
+  bool vx0, vx1, vy0, vy1;
+};
+
+// grid_sample(bilinear, padding_mode="border", align_corners=True) at pixel
+// (x + fx, y + fy) expressed the way modules/fi_utils.py:19-49 builds the grid:
+// base = linspace(-1,1,W_flow), offset = flow / ((W_src-1)/2).
+GV_HD BilinearTap border_tap(int x, int y, float fx, float fy, int wf, int hf, int ws, int hs) {
+  float gx = linspace_m1_1(x, wf) + fx / (((float)ws - 1.0f) / 2.0f);
+  float gy = linspace_m1_1(y, hf) + fy / (((float)hs - 1.0f) / 2.0f);
+  float ix = ((gx + 1.f) / 2.f) * (float)(ws - 1);
+  float iy = ((gy + 1.f) / 2.f) * (float)(hs - 1);
+  ix = fminf(fmaxf(ix, 0.f), (float)(ws - 1));
+  iy = fminf(fmaxf(iy, 0.f), (float)(hs - 1));
+  BilinearTap t;
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  t.x0 = (int)fx0; t.y0 = (int)fy0; t.x1 = t.x0 + 1; t.y1 = t.y0 + 1;
+  t.wx1 = ix - fx0; t.wx0 = (fx0 + 1.f) - ix;
+  t.wy1 = iy - fy0; t.wy0 = (fy0 + 1.f) - iy;
+  t.vx0 = t.x0 >= 0 && t.x0 < ws; t.vx1 = t.x1 >= 0 && t.x1 < ws;
+  t.vy0 = t.y0 >= 0 && t.y0 < hs; t.vy1 = t.y1 >= 0 && t.y1 < hs;
+  return t;
+}
+
+GV_HD float tap_fetch(const TV& s, int n, const BilinearTap& t, int ch) {
+  const float* b = s.p + (int64_t)n * s.sn + ch;
+  float v = 0.f;
+  if (t.vy0 && t.vx0) v += b[((int64_t)t.y0 * s.w + t.x0) * s.ld] * (t.wx0 * t.wy0);
+  if (t.vy0 && t.vx1) v += b[((int64_t)t.y0 * s.w + t.x1) * s.ld] * (t.wx1 * t.wy0);
+  if (t.vy1 && t.vx0) v += b[((int64_t)t.y1 * s.w + t.x0) * s.ld] * (t.wx0 * t.wy1);
+  if (t.vy1 && t.vx1) v += b[((int64_t)t.y1 * s.w + t.x1) * s.ld] * (t.wx1 * t.wy1);
+  return v;
+}
+
+// decode a flat index over (n, y, x, c)
+struct Idx4 { int n, y, x, c; };
+GV_HD Idx4 decode4(int64_t i, int h, int w, int c) {
+  Idx4 r;
+  r.c = (int)(i % c); i /= c;
+  r.x = (int)(i % w); i /= w;
+  r.y = (int)(i % h); r.n = (int)(i / h);
+  return r;
+}
+
+// ------------------------------------------------------------- layout moves
+struct NchwToNhwcK {
+  const float* src; int64_t sn, sc; TV dst; float scale, shift;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    float v = src[(int64_t)q.n * sn + (int64_t)q.c * sc + (int64_t)q.y * dst.w + q.x];
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = v * scale + shift;
+  }
+};
+void nchw_to_nhwc(Ctx& cx, const float* src, int64_t src_sn, int64_t src_sc, const TV& dst, float scale, float shift) {
+  parallel_for(cx, dst.pixels() * dst.c, NchwToNhwcK{src, src_sn, src_sc, dst, scale, shift}, "nchw_to_nhwc");
+}
+
+struct NhwcToNchwK {
+  TV src; float* dst; int64_t sn, sc; float scale, shift; int clamp01;
+  GV_HD void operator()(int64_t i) const {
+    // iterate in NCHW order so the writes are coalesced
+    int x = (int)(i % src.w); int64_t r = i / src.w;
+    int y = (int)(r % src.h); r /= src.h;
+    int c = (int)(r % src.c); int n = (int)(r / src.c);
+    float v = (src.p[src.off(n, y, x) + c] + shift) * scale;
+    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+    dst[(int64_t)n * sn + (int64_t)c * sc + (int64_t)y * src.w + x] = v;
+  }
+};
+void nhwc_to_nchw(Ctx& cx, const TV& src, float* dst, int64_t dst_sn, int64_t dst_sc, float scale, float shift, int clamp01) {
+  parallel_for(cx, src.pixels() * src.c, NhwcToNchwK{src, dst, dst_sn, dst_sc, scale, shift, clamp01}, "nhwc_to_nchw");
+}
+
+struct CopyK {
+  TV src, dst;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = src.p[src.off(q.n, q.y, q.x) + q.c];
+  }
+};
+void copy_channels(Ctx& cx, const TV& src, const TV& dst) {
+  parallel_for(cx, dst.pixels() * dst.c, CopyK{src, dst}, "copy_channels");
+}
+
+struct FillK {
+  TV dst; float v;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = v;
+  }
+};
+void fill(Ctx& cx, const TV& dst, float v) { parallel_for(cx, dst.pixels() * dst.c, FillK{dst, v}, "fill"); }
+
+struct AxpbyK {
+  TV a, b, out; float alpha, beta;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, out.h, out.w, out.c);
+    float v = alpha * a.p[a.off(q.n, q.y, q.x) + q.c];
+    if (b.p) v += beta * b.p[b.off(q.n, q.y, q.x) + q.c];
+    out.p[out.off(q.n, q.y, q.x) + q.c] = v;
+  }
+};
+void axpby(Ctx& cx, const TV& a, float alpha, const TV& b, float beta, const TV& out) {
+  parallel_for(cx, out.pixels() * out.c, AxpbyK{a, b, out, alpha, beta}, "axpby");
+}
+
+// ------------------------------------------------------------------ resize
+// F.interpolate(mode="bilinear", align_corners=False) — modules/fi_utils.py:67-70.
+// src coordinate = rscale * (dst + 0.5) - 0.5 clamped at 0 (ATen area_pixel_compute_source_index).
+struct ResizeK {
+  TV src, dst; float rsy, rsx, mult; int accumulate, act;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    float sy = rsy * ((float)q.y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+    float sx = rsx * ((float)q.x + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+    int y0 = (int)sy, x0 = (int)sx;
+    if (y0 > src.h - 1) y0 = src.h - 1;
+    if (x0 > src.w - 1) x0 = src.w - 1;
+    int y1 = y0 + (y0 < src.h - 1 ? 1 : 0), x1 = x0 + (x0 < src.w - 1 ? 1 : 0);
+    float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+    float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* b = src.p + (int64_t)q.n * src.sn + q.c;
+    float v00 = b[((int64_t)y0 * src.w + x0) * src.ld], v01 = b[((int64_t)y0 * src.w + x1) * src.ld];
+    float v10 = b[((int64_t)y1 * src.w + x0) * src.ld], v11 = b[((int64_t)y1 * src.w + x1) * src.ld];
+    float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    v *= mult;
+    if (act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+    float* o = dst.p + dst.off(q.n, q.y, q.x) + q.c;
+    *o = accumulate ? (*o + v) : v;
+  }
+};
+void resize_bilinear(Ctx& cx, const TV& src, const TV& dst, float rscale_y, float rscale_x, float mult, int accumulate, int act) {
+  parallel_for(cx, dst.pixels() * dst.c, ResizeK{src, dst, rscale_y, rscale_x, mult, accumulate, act}, "resize_bilinear");
+}
+
+// ---------------------------------------------------------------- backwarp
+// modules/fi_utils.py:19-49.
+struct BackwarpK {
+  TV src, flow, dst;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    const float* f = flow.p + flow.off(q.n, q.y, q.x);
+    BilinearTap t = border_tap(q.x, q.y, f[0], f[1], flow.w, flow.h, src.w, src.h);
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = tap_fetch(src, q.n, t, q.c);
+  }
+};
+void backwarp(Ctx& cx, const TV& src, const TV& flow, const TV& dst) {
+  parallel_for(cx, dst.pixels() * dst.c, BackwarpK{src, flow, dst}, "backwarp");
+}
+
+// ----------------------------------------------------------- pixel shuffle
+// nn.PixelShuffle(2) applied `times` times (fi_components.py:235, :285-286).
+struct PixelShuffleK {
+  TV src, dst; int times;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    int y = q.y, x = q.x, c = q.c;
+    for (int k = 0; k < times; ++k) {
+      c = c * 4 + (y & 1) * 2 + (x & 1);
+      y >>= 1; x >>= 1;
+    }
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = src.p[src.off(q.n, y, x) + c];
+  }
+};
+void pixel_shuffle(Ctx& cx, const TV& src, const TV& dst, int times) {
+  parallel_for(cx, dst.pixels() * dst.c, PixelShuffleK{src, dst, times}, "pixel_shuffle");
+}
+
+// ----------------------------------------------------------- instance norm
+// nn.InstanceNorm2d(C): no affine, biased variance, eps 1e-5 (raft/extractor.py:30-34,133-134).
+static const int IN_CHUNKS = 64;
+int64_t instnorm_scratch_floats(const TV& x) { return (int64_t)x.n * IN_CHUNKS * x.c * 4; }
+
+struct InPartialK {
+  TV x; double* part; int chunks;
+  GV_HD void operator()(int64_t i) const {
+    int c = (int)(i % x.c); int64_t r = i / x.c;
+    int ch = (int)(r % chunks); int n = (int)(r / chunks);
+    int64_t hw = (int64_t)x.h * x.w;
+    int64_t per = (hw + chunks - 1) / chunks;
+    int64_t a = (int64_t)ch * per, b = a + per; if (b > hw) b = hw;
+    const float* p = x.p + (int64_t)n * x.sn + c;
+    double s = 0.0, s2 = 0.0;
+    for (int64_t k = a; k < b; ++k) { double v = (double)p[k * x.ld]; s += v; s2 += v * v; }
+    part[i * 2] = s; part[i * 2 + 1] = s2;
+  }
+};
+struct InFinalK {
+  const double* part; float* mr; int c, chunks; double inv_hw;
+  GV_HD void operator()(int64_t i) const {
+    int ch = (int)(i % c); int n = (int)(i / c);
+    double s = 0.0, s2 = 0.0;
+    for (int k = 0; k < chunks; ++k) { int64_t j = ((int64_t)n * chunks + k) * c + ch; s += part[j * 2]; s2 += part[j * 2 + 1]; }
+    double m = s * inv_hw; double var = s2 * inv_hw - m * m; if (var < 0.0) var = 0.0;
+    mr[i * 2] = (float)m; mr[i * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+};
+void instnorm_stats(Ctx& cx, const TV& x, float* mean_rstd, float* scratch, int64_t) {
+  double* part = reinterpret_cast<double*>(scratch);
+  parallel_for(cx, (int64_t)x.n * IN_CHUNKS * x.c, InPartialK{x, part, IN_CHUNKS}, "instnorm_partial");
+  parallel_for(cx, (int64_t)x.n * x.c, InFinalK{part, mean_rstd, x.c, IN_CHUNKS, 1.0 / ((double)x.h * x.w)}, "instnorm_final");
+}
+struct InApplyK {
+  TV x, res, out; const float* mr; int act1, act2;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, out.h, out.w, out.c);
+    const float* s = mr + ((int64_t)q.n * x.c + q.c) * 2;
+    float v = (x.p[x.off(q.n, q.y, q.x) + q.c] - s[0]) * s[1];
+    v = apply_act(v, act1, nullptr, 0);
+    if (res.p) v += res.p[res.off(q.n, q.y, q.x) + q.c];
+    v = apply_act(v, act2, nullptr, 0);
+    out.p[out.off(q.n, q.y, q.x) + q.c] = v;
+  }
+};
+void instnorm_apply(Ctx& cx, const TV& x, const float* mean_rstd, int act1, const TV& res, int act2, const TV& out) {
+  parallel_for(cx, out.pixels() * out.c, InApplyK{x, res, out, mean_rstd, act1, act2}, "instnorm_apply");
+}
+
+// ------------------------------------------------------- flow normalisation
+// modules/fi_utils.py:52-60: scaler[n] = max |cat[f01, -f10]|.
+static const int AM_CHUNKS = 256;
+int64_t absmax_scratch_floats(const TV& a) { return (int64_t)a.n * AM_CHUNKS; }
+struct AbsmaxPartK {
+  TV a, b; float* part; int chunks;
+  GV_HD void operator()(int64_t i) const {
+    int ch = (int)(i % chunks); int n = (int)(i / chunks);
+    int64_t hw = (int64_t)a.h * a.w; int64_t per = (hw + chunks - 1) / chunks;
+    int64_t s = (int64_t)ch * per, e = s + per; if (e > hw) e = hw;
+    float m = 0.f;
+    for (int64_t k = s; k < e; ++k) {
+      const float* pa = a.p + (int64_t)n * a.sn + k * a.ld;
+      const float* pb = b.p + (int64_t)n * b.sn + k * b.ld;
+      for (int c = 0; c < a.c; ++c) { m = fmaxf(m, fabsf(pa[c])); m = fmaxf(m, fabsf(pb[c])); }
+    }
+    part[i] = m;
+  }
+};
+struct AbsmaxFinK {
+  const float* part; float* out; int chunks;
+  GV_HD void operator()(int64_t n) const {
+    float m = 0.f; for (int k = 0; k < chunks; ++k) m = fmaxf(m, part[n * chunks + k]);
+    out[n] = m;
+  }
+};
+void absmax_per_sample(Ctx& cx, const TV& a, const TV& b, float* out_n, float* scratch) {
+  parallel_for(cx, (int64_t)a.n * AM_CHUNKS, AbsmaxPartK{a, b, scratch, AM_CHUNKS}, "absmax_partial");
+  parallel_for(cx, (int64_t)a.n, AbsmaxFinK{scratch, out_n, AM_CHUNKS}, "absmax_final");
+}
+
+struct NormFlowK {
+  TV f01, f10, n0, n1; const float* s;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, f01.h, f01.w, 2);
+    float sc = s[q.n];
+    float a = f01.p[f01.off(q.n, q.y, q.x) + q.c];
+    float b = -f10.p[f10.off(q.n, q.y, q.x) + q.c];
+    n0.p[n0.off(q.n, q.y, q.x) + q.c] = (a / sc + 1.0f) / 2.0f;
+    n1.p[n1.off(q.n, q.y, q.x) + q.c] = (b / sc + 1.0f) / 2.0f;
+  }
+};
+void normalize_flow_pair(Ctx& cx, const TV& f01, const TV& f10, const float* scaler, const TV& n0, const TV& n1) {
+  parallel_for(cx, f01.pixels() * 2, NormFlowK{f01, f10, n0, n1, scaler}, "normalize_flow");
+}
+
+struct UnnormK {
+  TV a, out; const float* s;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, out.h, out.w, out.c);
+    out.p[out.off(q.n, q.y, q.x) + q.c] = (a.p[a.off(q.n, q.y, q.x) + q.c] * 2.0f - 1.0f) * s[q.n];
+  }
+};
+void unnormalize_flow(Ctx& cx, const TV& ninr, const float* scaler, const TV& out) {
+  parallel_for(cx, out.pixels() * out.c, UnnormK{ninr, out, scaler}, "unnormalize_flow");
+}
+
+// ------------------------------------------------------ RAFT coordinate ops
+struct InitCoordsK {
+  TV c;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, c.h, c.w, 2);
+    c.p[c.off(q.n, q.y, q.x) + q.c] = q.c == 0 ? (float)q.x : (float)q.y;
+  }
+};
+void init_coords(Ctx& cx, const TV& coords) { parallel_for(cx, coords.pixels() * 2, InitCoordsK{coords}, "init_coords"); }
+
+// flow = coords1 - coords0 (raft/raft.py:148), written to up to two consumers.
+struct CoordsMinusGridK {
+  TV c, a, b;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, c.h, c.w, 2);
+    float v = c.p[c.off(q.n, q.y, q.x) + q.c] - (q.c == 0 ? (float)q.x : (float)q.y);
+    if (a.p) a.p[a.off(q.n, q.y, q.x) + q.c] = v;
+    if (b.p) b.p[b.off(q.n, q.y, q.x) + q.c] = v;
+  }
+};
+void coords_minus_grid(Ctx& cx, const TV& coords1, const TV& a, const TV& b) {
+  parallel_for(cx, coords1.pixels() * 2, CoordsMinusGridK{coords1, a, b}, "coords_minus_grid");
+}
+
+// Convex x8 upsampling, raft/raft.py:86-97.  mask (n,h,w,576) already holds 0.25*conv
+// (folded into the weights); channel = k*64 + i*8 + j, k = ky*3 + kx.
+struct ConvexUpK {
+  TV flow, mask, out;
+  GV_HD void operator()(int64_t i) const {
+    int X = (int)(i % out.w); int64_t r = i / out.w;
+    int Y = (int)(r % out.h); int n = (int)(r / out.h);
+    int x = X >> 3, j = X & 7, y = Y >> 3, ii = Y & 7;
+    const float* m = mask.p + mask.off(n, y, x) + ii * 8 + j;
+    float e[9]; float mx = -3.4e38f;
+    for (int k = 0; k < 9; ++k) { e[k] = m[k * 64]; mx = fmaxf(mx, e[k]); }
+    float sum = 0.f;
+    for (int k = 0; k < 9; ++k) { e[k] = expf(e[k] - mx); sum += e[k]; }
+    float ox = 0.f, oy = 0.f;
+    for (int k = 0; k < 9; ++k) {
+      int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+      float fx = 0.f, fy = 0.f;
+      if (yy >= 0 && yy < flow.h && xx >= 0 && xx < flow.w) {
+        const float* f = flow.p + flow.off(n, yy, xx);
+        fx = 8.f * f[0]; fy = 8.f * f[1];
+      }
+      float wk = e[k] / sum;
+      ox += wk * fx; oy += wk * fy;
+    }
+    float* o = out.p + out.off(n, Y, X);
+    o[0] = ox; o[1] = oy;
+  }
+};
+void convex_upsample(Ctx& cx, const TV& flow, const TV& mask, const TV& out) {
+  parallel_for(cx, out.pixels(), ConvexUpK{flow, mask, out}, "convex_upsample");
+}
+
+// ----------------------------------------------------- GIMM splat weights
+// gimmvfi_r.py:444-492 for one direction: var of a 3x3 gaussian (reflect pad) +
+// forward/backward consistency  w = 1/(1+err*a_fe) + 1/(1+var*a_v).
+struct SplatWeightsK {
+  TV fs, fo, out; const float* g9; const float* afe; const float* av;
+  GV_HD int refl(int v, int n) const { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
+  GV_HD void operator()(int64_t i) const {
+    int x = (int)(i % fs.w); int64_t r = i / fs.w;
+    int y = (int)(r % fs.h); int n = (int)(r / fs.h);
+    float var = 0.f;
+    for (int c = 0; c < 2; ++c) {
+      float sq = 0.f, m = 0.f;
+      for (int k = 0; k < 9; ++k) {
+        int yy = refl(y + k / 3 - 1, fs.h), xx = refl(x + k % 3 - 1, fs.w);
+        float v = fs.p[fs.off(n, yy, xx) + c];
+        sq += g9[k] * (v * v); m += g9[k] * v;
+      }
+      float d = sq - m * m; if (d < 1e-9f) d = 1e-9f;
+      var += sqrtf(d);
+    }
+    var = var / 2.f;
+    const float* f = fs.p + fs.off(n, y, x);
+    BilinearTap t = border_tap(x, y, f[0], f[1], fs.w, fs.h, fo.w, fo.h);
+    float e0 = fabsf(-tap_fetch(fo, n, t, 0) - f[0]);
+    float e1 = fabsf(-tap_fetch(fo, n, t, 1) - f[1]);
+    float err = (e0 + e1) / 2.f;
+    out.p[out.off(n, y, x)] = 1.f / (1.f + err * afe[0]) + 1.f / (1.f + var * av[0]);
+  }
+};
+void splat_weights(Ctx& cx, const TV& f_self, const TV& f_other, const float* g9, const float* alpha_fe, const float* alpha_v, const TV& out) {
+  parallel_for(cx, out.pixels(), SplatWeightsK{f_self, f_other, out, g9, alpha_fe, alpha_v}, "splat_weights");
+}
+
+// ----------------------------------------------------------- forward splat
+// "linear" softmax-splatting, modules/softsplat.py:307-308 + kernel :376-421.
+// acc holds 17 channels per target pixel: 16 x sum(in*metric*w) and sum(metric*w).
+// One thread per (source pixel, channel): NHWC makes the 17 atomics of a pixel
+// land on consecutive addresses (the reference strides them by H*W).
+struct SplatAccK {
+  TV lat, flow, metric, acc; const float* t; int t_mode;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, lat.h, lat.w, 17);
+    float tt = t[q.n]; float sc = t_mode ? (1.f - tt) : tt;
+    const float* f = flow.p + flow.off(q.n, q.y, q.x);
+    float fx = (float)q.x + f[0] * sc;
+    float fy = (float)q.y + f[1] * sc;
+    if (!gv_isfinite(fx) || !gv_isfinite(fy)) return;
+    float m = metric.p[metric.off(q.n, q.y, q.x)];
+    float v = q.c < 16 ? lat.p[lat.off(q.n, q.y, q.x) + q.c] * m : m;
+    float x0f = floorf(fx), y0f = floorf(fy);
+    int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+    float wnw = ((float)x1 - fx) * ((float)y1 - fy);
+    float wne = (fx - (float)x0) * ((float)y1 - fy);
+    float wsw = ((float)x1 - fx) * (fy - (float)y0);
+    float wse = (fx - (float)x0) * (fy - (float)y0);
+    int W = acc.w, H = acc.h;
+    float* base = acc.p + (int64_t)q.n * acc.sn + q.c;
+    if (x0 >= 0 && x0 < W && y0 >= 0 && y0 < H) atomic_add_f(base + ((int64_t)y0 * W + x0) * acc.ld, v * wnw);
+    if (x1 >= 0 && x1 < W && y0 >= 0 && y0 < H) atomic_add_f(base + ((int64_t)y0 * W + x1) * acc.ld, v * wne);
+    if (x0 >= 0 && x0 < W && y1 >= 0 && y1 < H) atomic_add_f(base + ((int64_t)y1 * W + x0) * acc.ld, v * wsw);
+    if (x1 >= 0 && x1 < W && y1 >= 0 && y1 < H) atomic_add_f(base + ((int64_t)y1 * W + x1) * acc.ld, v * wse);
+  }
+};
+void softsplat_accumulate(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const TV& acc) {
+  parallel_for(cx, lat.pixels() * 17, SplatAccK{lat, flow, metric, acc, t_per_sample, t_mode}, "softsplat_accumulate");
+}
+// "zeroeps" normalisation, modules/softsplat.py:330-344.
+struct SplatNormK {
+  TV acc, out;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, out.h, out.w, 16);
+    const float* a = acc.p + acc.off(q.n, q.y, q.x);
+    float d = a[16]; if (d == 0.f) d = 1.f;
+    out.p[out.off(q.n, q.y, q.x) + q.c] = a[q.c] / d;
+  }
+};
+void softsplat_normalize(Ctx& cx, const TV& acc, const TV& out) {
+  parallel_for(cx, out.pixels() * 16, SplatNormK{acc, out}, "softsplat_normalize");
+}
+
+// ------------------------------------------------------------ synthesis glue
+// gimmvfi_r.py:239-240: flow_t->0 = flow_t * (-t), flow_t->1 = flow_t * (1 - t)
+struct ScaleFlowTK {
+  TV ft, f0, f1; const float* t;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, ft.h, ft.w, 2);
+    float v = ft.p[ft.off(q.n, q.y, q.x) + q.c]; float tt = t[q.n];
+    f0.p[f0.off(q.n, q.y, q.x) + q.c] = v * (-tt);
+    f1.p[f1.off(q.n, q.y, q.x) + q.c] = v * (1.0f - tt);
+  }
+};
+void scale_flow_t(Ctx& cx, const TV& flow_t, const float* t_per_sample, const TV& f0, const TV& f1) {
+  parallel_for(cx, flow_t.pixels() * 2, ScaleFlowTK{flow_t, f0, f1, t_per_sample}, "scale_flow_t");
+}
+
+struct HypoPackK {
+  const float* coord; TV dst;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, 3);
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = coord[i];
+  }
+};
+void hypo_pack_input(Ctx& cx, const float* coord, const TV& dst) {
+  parallel_for(cx, dst.pixels() * 3, HypoPackK{coord, dst}, "hypo_pack_input");
+}
+
+// gimmvfi_r.py:494-504: coord + flow * (1/(1-t))  (mode 0)  |  coord + flow * (1/t)  (mode 1)
+struct LookupCoordsK {
+  TV flow, out; const float* t; int mode;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, out.h, out.w, 2);
+    float tt = t[q.n];
+    float sc = mode == 0 ? 1.0f / (1.0f - tt) : 1.0f / tt;
+    float g = q.c == 0 ? (float)q.x : (float)q.y;
+    out.p[out.off(q.n, q.y, q.x) + q.c] = g + flow.p[flow.off(q.n, q.y, q.x) + q.c] * sc;
+  }
+};
+void lookup_coords(Ctx& cx, const TV& flow, const float* t_per_sample, int mode, const TV& out) {
+  parallel_for(cx, out.pixels() * 2, LookupCoordsK{flow, out, t_per_sample, mode}, "lookup_coords");
+}
+
+// fi_components.py:272-275 with the init-decoder head re-ordered at pack time to
+// [ft(128) | dflow0(2) | dflow1(2) | mask(1)].
+struct FlowMaskSplitK {
+  TV o, f0i, f1i, f0, f1, mask;
+  GV_HD void operator()(int64_t i) const {
+    int x = (int)(i % o.w); int64_t r = i / o.w; int y = (int)(r % o.h); int n = (int)(r / o.h);
+    const float* s = o.p + o.off(n, y, x) + 128;
+    const float* a = f0i.p + f0i.off(n, y, x); const float* b = f1i.p + f1i.off(n, y, x);
+    float* A = f0.p + f0.off(n, y, x); float* B = f1.p + f1.off(n, y, x);
+    A[0] = a[0] + s[0]; A[1] = a[1] + s[1]; B[0] = b[0] + s[2]; B[1] = b[1] + s[3];
+    mask.p[mask.off(n, y, x)] = s[4];
+  }
+};
+void flow_mask_split(Ctx& cx, const TV& out133, const TV& f0_in, const TV& f1_in, const TV& f0, const TV& f1, const TV& mask) {
+  parallel_for(cx, out133.pixels(), FlowMaskSplitK{out133, f0_in, f1_in, f0, f1, mask}, "flow_mask_split");
+}
+
+struct AddInplaceK {
+  TV dst, src;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] += src.p[src.off(q.n, q.y, q.x) + q.c];
+  }
+};
+void add_inplace_slices(Ctx& cx, const TV& dst, const TV& src) {
+  parallel_for(cx, dst.pixels() * dst.c, AddInplaceK{dst, src}, "add_inplace");
+}
+
+// fi_components.py:331-340: split 24 -> 6/6/3/9, add the repeated base flows / mask, sigmoid.
+struct FinalHeadsK {
+  TV o, fl0, fl1, m, of0, of1, om, ores;
+  GV_HD void operator()(int64_t i) const {
+    int x = (int)(i % o.w); int64_t r = i / o.w; int y = (int)(r % o.h); int n = (int)(r / o.h);
+    const float* s = o.p + o.off(n, y, x);
+    const float* a = fl0.p + fl0.off(n, y, x); const float* b = fl1.p + fl1.off(n, y, x);
+    float mm = m.p[m.off(n, y, x)];
+    float* A = of0.p + of0.off(n, y, x); float* B = of1.p + of1.off(n, y, x);
+    float* M = om.p + om.off(n, y, x); float* R = ores.p + ores.off(n, y, x);
+    for (int k = 0; k < 6; ++k) { A[k] = s[k] + a[k & 1]; B[k] = s[6 + k] + b[k & 1]; }
+    for (int k = 0; k < 3; ++k) M[k] = 1.f / (1.f + expf(-(s[12 + k] + mm)));
+    for (int k = 0; k < 9; ++k) R[k] = s[15 + k];
+  }
+};
+void final_heads(Ctx& cx, const TV& out24, const TV& flow0, const TV& flow1, const TV& mask, const TV& oflow0, const TV& oflow1,
+                 const TV& omask, const TV& ores) {
+  parallel_for(cx, out24.pixels(), FinalHeadsK{out24, flow0, flow1, mask, oflow0, oflow1, omask, ores}, "final_heads");
+}
+
+// warp_w_mask, gimmvfi_r.py:213-220 (flows / sigmoid(mask) already at full res).
+struct WarpBlendK {
+  TV i0, i1, f0, f1, m, out;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, out.h, out.w, 3);
+    const float* a = f0.p + f0.off(q.n, q.y, q.x); const float* b = f1.p + f1.off(q.n, q.y, q.x);
+    BilinearTap t0 = border_tap(q.x, q.y, a[0], a[1], f0.w, f0.h, i0.w, i0.h);
+    BilinearTap t1 = border_tap(q.x, q.y, b[0], b[1], f1.w, f1.h, i1.w, i1.h);
+    float mm = m.p[m.off(q.n, q.y, q.x)];
+    out.p[out.off(q.n, q.y, q.x) + q.c] = mm * tap_fetch(i0, q.n, t0, q.c) + (1.f - mm) * tap_fetch(i1, q.n, t1, q.c);
+  }
+};
+void warp_blend(Ctx& cx, const TV& img0, const TV& img1, const TV& f0, const TV& f1, const TV& mask, const TV& out) {
+  parallel_for(cx, out.pixels() * 3, WarpBlendK{img0, img1, f0, f1, mask, out}, "warp_blend");
+}
+
+// multi_flow_combine, fi_components.py:57-88: 3 x (2 warps, blend, + residual) and their mean.
+struct MultiFlowBlendK {
+  TV i0, i1, f0, f1, m, res, w9, mean3;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, w9.h, w9.w, 3);
+    float acc = 0.f;
+    for (int k = 0; k < 3; ++k) {
+      const float* a = f0.p + f0.off(q.n, q.y, q.x) + 2 * k; const float* b = f1.p + f1.off(q.n, q.y, q.x) + 2 * k;
+      BilinearTap t0 = border_tap(q.x, q.y, a[0], a[1], f0.w, f0.h, i0.w, i0.h);
+      BilinearTap t1 = border_tap(q.x, q.y, b[0], b[1], f1.w, f1.h, i1.w, i1.h);
+      float mm = m.p[m.off(q.n, q.y, q.x) + k];
+      float v = mm * tap_fetch(i0, q.n, t0, q.c) + (1.f - mm) * tap_fetch(i1, q.n, t1, q.c);
+      v += res.p[res.off(q.n, q.y, q.x) + 3 * k + q.c];
+      w9.p[w9.off(q.n, q.y, q.x) + 3 * k + q.c] = v;
+      acc += v;
+    }
+    mean3.p[mean3.off(q.n, q.y, q.x) + q.c] = acc / 3.f;
+  }
+};
+void multi_flow_blend(Ctx& cx, const TV& img0, const TV& img1, const TV& f0, const TV& f1, const TV& mask, const TV& res,
+                      const TV& warps9, const TV& mean3) {
+  parallel_for(cx, warps9.pixels() * 3, MultiFlowBlendK{img0, img1, f0, f1, mask, res, warps9, mean3}, "multi_flow_blend");
+}
+
+// fi_components.py:89-92 + gimmvfi_r.py:308: clamp((mean + comb + 1)/2, 0, 1) -> NCHW
+struct CombineOutK {
+  TV mean3, conv3; float* dst;
+  GV_HD void operator()(int64_t i) const {
+    int x = (int)(i % mean3.w); int64_t r = i / mean3.w;
+    int y = (int)(r % mean3.h); r /= mean3.h; int c = (int)(r % 3); int n = (int)(r / 3);
+    float v = mean3.p[mean3.off(n, y, x) + c] + conv3.p[conv3.off(n, y, x) + c];
+    v = (v + 1.0f) / 2.f;
+    dst[i] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+};
+void combine_output(Ctx& cx, const TV& mean3, const TV& conv3, float* dst_nchw) {
+  parallel_for(cx, mean3.pixels() * 3, CombineOutK{mean3, conv3, dst_nchw}, "combine_output");
+}
+
+}  // namespace gv

@@ -1,0 +1,112 @@
+"""EngineHandle: owns one native engine (one per GPU / host thread), the packed
+weights and a cached workspace; turns torch tensors into the raw pointers of the
+C ABI (include/gimmvfi_b200.h).  PyTorch is used for device memory and streams only."""
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from ._lib import IO, Lib, Problem, View, default_lib
+
+
+class EngineHandle:
+    def __init__(self, device, lib: Optional[Lib] = None, allow_hostsim: bool = False):
+        self.lib = lib if lib is not None else default_lib()
+        self.device = torch.device(device)
+        info = self.lib.build_info()
+        self.hostsim = "HOSTSIM" in info
+        if self.hostsim and not allow_hostsim:
+            raise RuntimeError("gimmvfi_b200: refusing to run the test-only host simulation as a product path")
+        if not self.hostsim and self.device.type != "cuda":
+            raise RuntimeError("gimmvfi_b200 runs on CUDA devices only (got %s); there is no CPU fallback" % self.device)
+        h = C.c_void_p()
+        idx = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
+        if self.device.type == "cuda":
+            idx = torch.cuda.current_device() if self.device.index is None else self.device.index
+        self.lib.check(self.lib.dll.gimmvfi_create(idx, C.byref(h)))
+        self._h = h
+        self._ws = None
+        self._plans: Dict[tuple, int] = {}
+        self.weights_loaded = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.dll.gimmvfi_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        for k, v in sd.items():
+            if not v.dtype.is_floating_point:
+                continue  # num_batches_tracked
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            self.lib.check(self.lib.dll.gimmvfi_load_weight(self._h, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()), self._h)
+        self.lib.check(self.lib.dll.gimmvfi_finalize_weights(self._h), self._h)
+        self.weights_loaded = True
+
+    def set_debug(self, on: bool):
+        self.lib.check(self.lib.dll.gimmvfi_set_debug(self._h, int(on)), self._h)
+        self._plans.clear()
+
+    def set_raft_iters(self, iters: int):
+        self.lib.check(self.lib.dll.gimmvfi_set_raft_iters(self._h, int(iters)), self._h)
+
+    @property
+    def last_launches(self) -> int:
+        return int(self.lib.dll.gimmvfi_last_launches(self._h))
+
+    # ------------------------------------------------------------------ forward
+    def _problem(self, B, Hf, Wf, T, ds, Hc, Wc) -> Problem:
+        return Problem(B, Hf, Wf, T, float(ds) if ds else 0.0, Hc, Wc)
+
+    def workspace_bytes(self, B, Hf, Wf, T, ds, Hc, Wc) -> int:
+        key = (B, Hf, Wf, T, float(ds) if ds else 0.0, Hc, Wc)
+        if key not in self._plans:
+            p = self._problem(*key)
+            n = C.c_size_t()
+            self.lib.check(self.lib.dll.gimmvfi_plan(self._h, C.byref(p), C.byref(n)), self._h)
+            self._plans[key] = int(n.value)
+        return self._plans[key]
+
+    def forward(self, img_xs: torch.Tensor, coords: torch.Tensor, t: torch.Tensor, ds: Optional[float] = None,
+                aux_outputs: bool = True) -> Dict[str, torch.Tensor]:
+        """img_xs (B,3,2,Hf,Wf), coords (T,B,1,Hc,Wc,3), t (T,B): contiguous fp32 on self.device."""
+        for x in (img_xs, coords, t):
+            assert x.dtype == torch.float32 and x.is_contiguous() and x.device.type == self.device.type
+        B, _, _, Hf, Wf = img_xs.shape
+        T, _, _, Hc, Wc, _ = coords.shape
+        H, W = (Hf, Wf) if not ds else (int(Hf * ds), int(Wf * ds))
+        nbytes = self.workspace_bytes(B, Hf, Wf, T, ds, Hc, Wc)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        E = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        out = {"imgt_pred": E(T, B, 3, Hf, Wf)}
+        if aux_outputs:
+            out.update(
+                img_warp_4=E(T, B, 3, H, W), flowt0_1=E(T, B, 3, 2, Hf, Wf), flowt1_1=E(T, B, 3, 2, Hf, Wf),
+                flowt0_4=E(T, B, 2, H // 4, W // 4), flowt1_4=E(T, B, 2, H // 4, W // 4), raft_flow=E(B, 2, 2, H, W),
+                nflow=E(B, 2, 2, H, W), ninrflow=E(T, B, 2, 1, Hc, Wc), flowt=E(T, B, 2, Hc, Wc))
+        io = IO()
+        io.img_xs, io.coords, io.t = img_xs.data_ptr(), coords.data_ptr(), t.data_ptr()
+        for k, v in out.items():
+            setattr(io, k, v.data_ptr())
+        p = self._problem(B, Hf, Wf, T, ds, Hc, Wc)
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+        self.lib.check(self.lib.dll.gimmvfi_forward(self._h, C.byref(p), C.byref(io), C.c_void_p(self._ws.data_ptr()),
+                                                    self._ws.numel(), C.c_void_p(stream)), self._h)
+        return out
+
+    def tap(self, name: str) -> torch.Tensor:
+        """Debug: copy of an intermediate NHWC tensor of the last forward (set_debug(True) first)."""
+        v = View()
+        self.lib.check(self.lib.dll.gimmvfi_get_tap(self._h, name.encode(), C.byref(v)), self._h)
+        base = self._ws.data_ptr()
+        off = (v.data - base) // 4
+        flat = self._ws.view(torch.float32)
+        t = torch.as_strided(flat, (v.n, v.h, v.w, v.c), (v.batch_stride, v.w * v.pixel_stride, v.pixel_stride, 1), off)
+        return t.clone()

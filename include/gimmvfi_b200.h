@@ -1,0 +1,119 @@
+/* gimmvfi_b200 — C ABI of the B200-native GIMM-VFI-R inference path.
+ *
+ * The reference (GSeanCDAT/GIMM-VFI) is pure Python; it has no FFI for this path.
+ * Its only native boundaries are
+ *   - the CuPy-JIT'd splat kernel launched with raw data_ptr()s on the current
+ *     torch stream (src/models/generalizable_INR/modules/softsplat.py:358-446), and
+ *   - the (unused) pybind extension alt_cuda_corr.forward(fmap1, fmap2, coords, r)
+ *     (.../flowformer/alt_cuda_corr/correlation.cpp:19-53).
+ * This header is what a maintainer binds (ctypes) to replace the
+ * body of GIMMVFI_R.forward() (src/models/generalizable_INR/gimmvfi_r.py:324-407):
+ * raw device pointers + sizes + a cudaStream_t, no torch types, no exceptions across
+ * the boundary (every call returns 0 on success; gimmvfi_last_error() explains).
+ *
+ * Threading / ownership: one engine per GPU and per host thread; all work is
+ * enqueued on the caller's stream; the caller owns inputs, outputs and the
+ * workspace; forward() performs no allocation and no host synchronisation.
+ */
+#ifndef GIMMVFI_B200_H_
+#define GIMMVFI_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gimmvfi_engine gimmvfi_engine;
+
+/* One call of GIMMVFI_R.forward(img_xs, coord, t, ds_factor=ds). */
+typedef struct gimmvfi_problem {
+  int32_t batch;       /* B: frame pairs                                            */
+  int32_t height;      /* Hf, Wf: caller-padded (x32) input size,                    */
+  int32_t width;       /*   src/utils/utils.py:156-185 InputPadder                   */
+  int32_t timesteps;   /* T = len(t) = len(coord)                                    */
+  float ds_factor;     /* 0 -> None; else gimmvfi_r.py:329-337                       */
+  int32_t coord_height; /* Hc, Wc of the coord grids = int(H*ds), coord_sampler.py:35 */
+  int32_t coord_width;
+} gimmvfi_problem;
+
+/* Device pointers (fp32).  Optional outputs may be NULL.  Layouts are the
+ * reference's, with the python list index (timestep) as the outermost dim.
+ * H, W = network resolution (= Hf,Wf, or floor(Hf*ds), floor(Wf*ds)). */
+typedef struct gimmvfi_io {
+  const float* img_xs;   /* (B,3,2,Hf,Wf) in [0,1]                      gimmvfi_r.py:324 */
+  const float* coords;   /* (T,B,1,Hc,Wc,3) last dim (t,y,x)     coord_sampler.py:21-43 */
+  const float* t;        /* (T,B)                                                        */
+  float* imgt_pred;      /* (T,B,3,Hf,Wf)   required                    gimmvfi_r.py:399 */
+  float* img_warp_4;     /* (T,B,3,H,W)     other_pred[i][0]                         :400 */
+  float* flowt0_1;       /* (T,B,3,2,Hf,Wf) flowt0_pred[i][0]                        :401 */
+  float* flowt1_1;       /* (T,B,3,2,Hf,Wf) flowt1_pred[i][0]                        :402 */
+  float* flowt0_4;       /* (T,B,2,H/4,W/4) flowt0_pred[i][1]                             */
+  float* flowt1_4;       /* (T,B,2,H/4,W/4) flowt1_pred[i][1]                             */
+  float* raft_flow;      /* (B,2,2,H,W)                                              :403 */
+  float* nflow;          /* (B,2,2,H,W)                                              :405 */
+  float* ninrflow;       /* (T,B,2,1,Hc,Wc)                                          :404 */
+  float* flowt;          /* (T,B,2,Hc,Wc)                                            :406 */
+} gimmvfi_io;
+
+/* NHWC fp32 view used by the per-kernel entry points and debug taps:
+ * element (n,y,x,c) = data[n*batch_stride + (y*w + x)*pixel_stride + c]. */
+typedef struct gimmvfi_view {
+  float* data;
+  int32_t n, h, w, c;
+  int32_t pixel_stride;
+  int64_t batch_stride;
+} gimmvfi_view;
+
+/* ---- engine life cycle ---- */
+int gimmvfi_create(int device, gimmvfi_engine** out);
+void gimmvfi_destroy(gimmvfi_engine* e);
+/* state_dict entry (HOST pointer, fp32; int64 buffers are skipped by the caller).
+ * Keys are the reference's 414 state_dict keys (gimmvfi_r.py:37-111). */
+int gimmvfi_load_weight(gimmvfi_engine* e, const char* key, const float* host_data, const int64_t* shape, int ndim);
+/* Packs (layout change, BatchNorm folding, HypoNet column normalisation) and uploads. */
+int gimmvfi_finalize_weights(gimmvfi_engine* e);
+int gimmvfi_plan(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes);
+int gimmvfi_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_io* io, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream);
+const char* gimmvfi_last_error(gimmvfi_engine* e);
+int64_t gimmvfi_last_launches(gimmvfi_engine* e);
+int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters);
+/* debug taps: intermediate tensors of the last forward (views into the workspace) */
+int gimmvfi_set_debug(gimmvfi_engine* e, int on);
+int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out);
+const char* gimmvfi_build_info(void);
+
+/* ---- per-kernel entry points (unit tests; all NHWC fp32 device views) ---- */
+/* softsplat "linear-zeroeps": modules/softsplat.py:286-352 (kernel :371-421).
+ * lat (n,h,w,16) flow (n,h,w,2) metric (n,h,w,1) t (n) scratch (n,h,w,>=17 ch, pixel_stride>=17) out (n,h,w,16);
+ * the splat flow is flow*t (t_mode 0) or flow*(1-t) (t_mode 1). */
+int gimmvfi_op_softsplat(const gimmvfi_view* lat, const gimmvfi_view* flow, const gimmvfi_view* metric, const float* t, int t_mode,
+                         const gimmvfi_view* scratch, const gimmvfi_view* out, void* stream);
+/* backward warp: modules/fi_utils.py:19-49 */
+int gimmvfi_op_backwarp(const gimmvfi_view* src, const gimmvfi_view* flow, const gimmvfi_view* dst, void* stream);
+/* F.interpolate(bilinear, align_corners=False): modules/fi_utils.py:67-70; dst = mult * resize(src) */
+int gimmvfi_op_resize(const gimmvfi_view* src, const gimmvfi_view* dst, float scale_factor, float mult, void* stream);
+/* all-pairs correlation raft/corr.py:167-175: vol[n][i][j] = <fa[n,i,:], fb[n,j,:]> / sqrt(C) */
+int gimmvfi_op_corr_volume(const gimmvfi_view* fa, const gimmvfi_view* fb, float* vol, void* stream);
+/* 2x2 average pooling of every row's (h,w) image: raft/corr.py:139-142 */
+int gimmvfi_op_corr_pool(const float* src, float* dst, int64_t rows, int h, int w, void* stream);
+/* 4-level 9x9 lookup raft/corr.py:144-165: lvl[k] = (n*h*w) x (h_k*w_k) pyramids; out (n,h,w,324) */
+int gimmvfi_op_corr_lookup(const float* const lvl[4], const int32_t lvl_h[4], const int32_t lvl_w[4], const gimmvfi_view* coords,
+                           const gimmvfi_view* out, void* stream);
+/* conv2d on NHWC: weight packed [kh*kw][cin][cout_ld], act: 0 none,1 relu,2 lrelu(0.1),3 prelu,4 sigmoid,5 tanh,6 sin */
+int gimmvfi_op_conv2d(const gimmvfi_view* in0, const gimmvfi_view* in1_or_null, const float* w_packed, const float* bias, int cin,
+                      int cout, int cout_ld, int kh, int kw, int stride, int pad_h, int pad_w, int reflect, int act,
+                      const float* slope, const gimmvfi_view* residual_or_null, const gimmvfi_view* out, void* stream);
+/* nn.InstanceNorm2d + optional relu: raft/extractor.py:133-134; scratch >= gimmvfi_instnorm_scratch_floats */
+int64_t gimmvfi_instnorm_scratch_floats(int n, int c);
+int gimmvfi_op_instnorm(const gimmvfi_view* x, int relu, float* scratch, const gimmvfi_view* out, void* stream);
+/* convex x8 upsampling raft/raft.py:86-97: flow (n,h,w,2), mask (n,h,w,576), out (n,8h,8w,2) */
+int gimmvfi_op_convex_upsample(const gimmvfi_view* flow, const gimmvfi_view* mask, const gimmvfi_view* out, void* stream);
+/* nn.PixelShuffle(2) applied `times` times */
+int gimmvfi_op_pixel_shuffle(const gimmvfi_view* src, const gimmvfi_view* dst, int times, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIMMVFI_B200_H_ */
