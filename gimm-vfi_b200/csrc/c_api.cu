@@ -6,7 +6,7 @@ using namespace gv;
 
 struct gimmvfi_engine {
   Engine eng;
-  std::string err;
+  std::string err, prof_json;
   explicit gimmvfi_engine(int dev) : eng(dev) {}
 };
 
@@ -75,6 +75,11 @@ int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out) {
     const TV& t = it->second;
     out->data = t.p; out->n = t.n; out->h = t.h; out->w = t.w; out->c = t.c; out->pixel_stride = t.ld; out->batch_stride = t.sn;
   })
+}
+int gimmvfi_set_profile(gimmvfi_engine* e, int on) { GV_TRY(e, { e->eng.set_profile(on != 0); }) }
+const char* gimmvfi_profile_json(gimmvfi_engine* e, void* stream) {
+  try { e->prof_json = e->eng.profile_json((gvStream_t)stream); } catch (const std::exception& ex) { e->err = ex.what(); e->prof_json = "{}"; }
+  return e->prof_json.c_str();
 }
 const char* gimmvfi_build_info(void) {
 #ifdef GV_HOSTSIM

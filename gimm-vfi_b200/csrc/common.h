@@ -110,7 +110,20 @@ struct Arena {
   void release(size_t m) { top = m; }
 };
 
+// Optional per-launch timing (CUDA events on the launching stream), keyed by kernel name.
+struct ProfRec { const char* name; double work; void* ev0; void* ev1; };
+struct Profiler {
+  std::vector<ProfRec> recs;
+  std::vector<void*> pool; size_t used = 0;
+  void* get_event();
+  void begin(gvStream_t s, const char* name, double work);
+  void end(gvStream_t s);
+  void reset() { recs.clear(); used = 0; }
+  ~Profiler();
+};
+
 struct Ctx {
+  Profiler* prof = nullptr;
   gvStream_t stream = nullptr;
   Arena arena;
   bool dry = false;       // skip kernel launches (planning)
@@ -141,11 +154,13 @@ inline void parallel_for(Ctx& cx, int64_t n, const F& f, const char* name) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) f(i);
 #else
+  if (cx.prof) cx.prof->begin(cx.stream, name, (double)n);
   int64_t blocks = (n + 255) / 256;
   int64_t cap = (int64_t)cx.sm_count * 32;  // grid-stride beyond 32 CTAs/SM
   if (blocks > cap) blocks = cap;
   gv_elementwise_kernel<F><<<(unsigned)blocks, 256, 0, cx.stream>>>(f, n);
   gv_check_launch(name);
+  if (cx.prof) cx.prof->end(cx.stream);
 #endif
 }
 

@@ -83,8 +83,10 @@ void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale) {
 #else
   if (fa.c % 16 != 0 || fa.ld % 4 != 0 || fb.ld % 4 != 0) throw std::runtime_error("corr_volume: feature dim must be a multiple of 16");
   dim3 grid((M + 127) / 128, (M + 127) / 128, fa.n);
+  if (cx.prof) cx.prof->begin(cx.stream, "corr_gemm_nt", 2.0 * fa.n * (double)M * M * fa.c);
   corr_gemm_nt_kernel<<<grid, 256, 0, cx.stream>>>(fa, fb, vol, scale);
   gv_check_launch("corr_volume");
+  if (cx.prof) cx.prof->end(cx.stream);
 #endif
 }
 

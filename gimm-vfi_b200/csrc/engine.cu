@@ -37,6 +37,52 @@ void dev_sync(gvStream_t s) { cuda_ok(cudaStreamSynchronize(s), "cudaStreamSynch
 #endif
 
 // ---------------------------------------------------------------------------
+// Profiler (CUDA events around every launch; off by default)
+// ---------------------------------------------------------------------------
+#ifdef GV_HOSTSIM
+void* Profiler::get_event() { return nullptr; }
+void Profiler::begin(gvStream_t, const char*, double) {}
+void Profiler::end(gvStream_t) {}
+Profiler::~Profiler() {}
+#else
+void* Profiler::get_event() {
+  if (used == pool.size()) { cudaEvent_t e; cuda_ok(cudaEventCreate(&e), "cudaEventCreate"); pool.push_back(e); }
+  return pool[used++];
+}
+void Profiler::begin(gvStream_t s, const char* name, double work) {
+  ProfRec r; r.name = name; r.work = work; r.ev0 = get_event(); r.ev1 = get_event();
+  cuda_ok(cudaEventRecord((cudaEvent_t)r.ev0, s), "cudaEventRecord");
+  recs.push_back(r);
+}
+void Profiler::end(gvStream_t s) { cuda_ok(cudaEventRecord((cudaEvent_t)recs.back().ev1, s), "cudaEventRecord"); }
+Profiler::~Profiler() { for (void* e : pool) cudaEventDestroy((cudaEvent_t)e); }
+#endif
+
+std::string Engine::profile_json(gvStream_t stream) {
+  std::string out = "{";
+#ifndef GV_HOSTSIM
+  cuda_ok(cudaStreamSynchronize(stream), "sync");
+  struct Acc { double ms = 0, work = 0; int64_t n = 0; };
+  std::map<std::string, Acc> acc;
+  for (const ProfRec& r : prof_.recs) {
+    float ms = 0.f;
+    cuda_ok(cudaEventElapsedTime(&ms, (cudaEvent_t)r.ev0, (cudaEvent_t)r.ev1), "cudaEventElapsedTime");
+    Acc& a = acc[r.name]; a.ms += ms; a.work += r.work; a.n++;
+  }
+  bool first = true;
+  for (auto& kv : acc) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"ms\": %.6f, \"work\": %.6e, \"launches\": %lld}", first ? "" : ", ", kv.first.c_str(), kv.second.ms,
+             kv.second.work, (long long)kv.second.n);
+    out += buf; first = false;
+  }
+#else
+  (void)stream;
+#endif
+  return out + "}";
+}
+
+// ---------------------------------------------------------------------------
 // Engine: weights
 // ---------------------------------------------------------------------------
 Engine::Engine(int device) : device_(device) {
@@ -721,6 +767,8 @@ void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t wor
   if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
   if (!io.img_xs || !io.coords || !io.t || !io.imgt_pred) throw std::runtime_error("gimmvfi: img_xs, coords, t and imgt_pred are required");
   Ctx cx; cx.stream = stream; cx.sm_count = sm_count_;
+  prof_.reset();
+  cx.prof = profile_ ? &prof_ : nullptr;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
   cx.arena.base = reinterpret_cast<char*>(base);
   cx.arena.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));

@@ -51,6 +51,9 @@ class Engine {
   int64_t last_launches() const { return launches_; }
   // debug taps: name -> NHWC view inside the workspace of the last forward
   void set_debug(bool on) { debug_ = on; }
+  // per-kernel CUDA-event timing of the next forward(s): {"name": {"ms", "work", "launches"}}
+  void set_profile(bool on) { profile_ = on; }
+  std::string profile_json(gvStream_t stream);
   const std::map<std::string, TV>& taps() const { return taps_; }
   std::string last_error;
   int raft_iters = 20;  // GIMMVFI_R hard-codes iters=20 (gimmvfi_r.py:126-132)
@@ -67,7 +70,8 @@ class Engine {
   void tap(const std::string& name, const TV& tv) { if (debug_) taps_[name] = tv; }
 
   int device_ = 0;
-  bool finalized_ = false, debug_ = false;
+  bool finalized_ = false, debug_ = false, profile_ = false;
+  Profiler prof_;
   int64_t launches_ = 0;
   int sm_count_ = 148;
   std::map<std::string, HostTensor> raw_;

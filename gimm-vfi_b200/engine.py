@@ -52,6 +52,16 @@ class EngineHandle:
         self.lib.check(self.lib.dll.gimmvfi_set_debug(self._h, int(on)), self._h)
         self._plans.clear()
 
+    def set_profile(self, on: bool):
+        self.lib.check(self.lib.dll.gimmvfi_set_profile(self._h, int(on)), self._h)
+
+    def profile(self) -> dict:
+        """Per-kernel CUDA-event totals of the last forward (set_profile(True) first)."""
+        import json
+
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+        return json.loads(self.lib.dll.gimmvfi_profile_json(self._h, C.c_void_p(stream)).decode())
+
     def set_raft_iters(self, iters: int):
         self.lib.check(self.lib.dll.gimmvfi_set_raft_iters(self._h, int(iters)), self._h)
 

@@ -1,0 +1,167 @@
+"""Drop-in ``GIMMVFI_R`` for inference (reference: src/models/generalizable_INR/
+gimmvfi_r.py:34-507).  Same constructor argument (``config.arch`` node), same
+``forward(img_xs, coord, t, iters, ds_factor)`` signature and returned dict, same
+414-key ``state_dict`` — but ``forward`` is one call into the sm_100a engine through
+the C ABI.  CUDA only; there is no PyTorch / CPU fallback path.
+"""
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .arch import param_spec_r
+from .config import default_arch_config
+from .engine import EngineHandle
+from .weights import random_state_dict
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's module tree names."""
+
+
+def sample_coords(batch_size, s_shape, t_ids, coord_range=(-1.0, 1.0), upsample_ratio=1.0, device=None):
+    """CoordSampler3D.shape2coordinate (modules/coord_sampler.py:21-43): (B, T, Hc, Wc, 3), last dim (t, y, x)."""
+    assert isinstance(t_ids, list)
+    cs = [(torch.tensor(t_ids, device=device) / 1.0).to(torch.float32)]
+    for n in s_shape:
+        n = int(n * upsample_ratio)
+        c = (0.5 + torch.arange(n, device=device)) / n
+        cs.append(coord_range[0] + (coord_range[1] - coord_range[0]) * c)
+    g = torch.stack(torch.meshgrid(*cs, indexing="ij"), dim=-1)
+    return g.unsqueeze(0).repeat(batch_size, 1, 1, 1, 1)
+
+
+class GIMMVFI_R(nn.Module):
+    def __init__(self, config=None, seed: int = 0):
+        super().__init__()
+        self.config = config = (config.copy() if config is not None else default_arch_config())
+        self.hyponet_config = config.hyponet
+        self.raft_iter = 20  # gimmvfi_r.py:41 (config.raft_iter is ignored by the reference too)
+        self.num_flows = 3
+        self.fwarp_type = getattr(config, "fwarp_type", "linear")
+        if self.fwarp_type != "linear":
+            raise NotImplementedError("only fwarp_type='linear' (the shipped configs' default, configs.py:44) is built")
+        self.coord_range = list(config.coord_range)
+        init = random_state_dict(seed)
+        shared = {}
+        for key, shape, dt in param_spec_r():
+            mod, leaf = self._container(key)
+            alias = key.replace(".downsample.1.", ".norm3.") if ".downsample.1." in key else None
+            if alias is not None and alias in shared:  # norm3 and downsample.1 are one module (raft/extractor.py:44-47)
+                obj = shared[alias]
+            elif dt == "int64" or leaf in ("running_mean", "running_var"):
+                obj = init[key].clone()
+            else:
+                obj = nn.Parameter(init[key].clone(), requires_grad=False)
+            shared[key] = obj
+            if isinstance(obj, nn.Parameter):
+                mod.register_parameter(leaf, obj)
+            else:
+                mod.register_buffer(leaf, obj)
+        self._engine: Optional[EngineHandle] = None
+        self._weights_dirty = True
+        self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_weights_dirty", True))
+        self.aux_outputs = True  # False: skip the auxiliary outputs (only imgt_pred is produced)
+
+    def _container(self, key: str):
+        parts = key.split(".")
+        mod = self
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, _Node())
+            mod = mod._modules[p]
+        return mod, parts[-1]
+
+    # ---------------------------------------------------------------- engine plumbing
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._weights_dirty = True
+        return r
+
+    def refresh_weights(self):
+        """Re-pack + upload the weights (automatic after load_state_dict / .to())."""
+        dev = self.g_filter.device
+        if dev.type != "cuda":
+            raise RuntimeError("GIMMVFI_R (gimmvfi_b200) runs on CUDA devices only; call model.to('cuda') first — there is no CPU path")
+        if self._engine is None or self._engine.device != dev:
+            self._engine = EngineHandle(dev)
+        self._engine.load_state_dict(self.state_dict())
+        self._weights_dirty = False
+
+    @property
+    def engine(self) -> EngineHandle:
+        if self._engine is None or self._weights_dirty:
+            self.refresh_weights()
+        return self._engine
+
+    # ---------------------------------------------------------------- reference API
+    def sample_coord_input(self, batch_size, s_shape, t_ids, coord_range=None, upsample_ratio=1.0, device=None):
+        """gimmvfi_r.py:428-442"""
+        assert device is not None
+        assert coord_range is None
+        return sample_coords(batch_size, s_shape, t_ids, self.coord_range, upsample_ratio, device)
+
+    @torch.no_grad()
+    def forward(self, img_xs, coord=None, t=None, iters=None, ds_factor=None):
+        """gimmvfi_r.py:324-407 (inference form).  ``iters`` is accepted and ignored, as in
+        the reference (cal_bidirection_flow hard-codes 20, gimmvfi_r.py:126-132)."""
+        assert isinstance(t, list)
+        assert isinstance(coord, list)
+        assert len(t) == len(coord)
+        assert coord is not None
+        for c in coord:
+            assert isinstance(c, tuple)
+            if c[1] is not None:
+                raise NotImplementedError("sub-sampled coordinates are the training path (gimmvfi_r.py:358-367); inference passes None")
+        if img_xs.device.type != "cuda":
+            raise RuntimeError("GIMMVFI_R (gimmvfi_b200): inputs must live on a CUDA device; there is no CPU path")
+        eng = self.engine
+        B = img_xs.shape[0]
+        xs = img_xs.to(torch.float32).contiguous()
+        coords = torch.stack([c[0].to(torch.float32) for c in coord], 0).contiguous()  # (T,B,1,Hc,Wc,3)
+        tt = torch.stack([x.reshape(-1).to(torch.float32).expand(B) for x in t], 0).contiguous()  # (T,B)
+        o = eng.forward(xs, coords, tt, ds_factor, aux_outputs=self.aux_outputs)
+        T = len(t)
+        out = {"imgt_pred": [o["imgt_pred"][i] for i in range(T)]}
+        if self.aux_outputs:
+            out.update({
+                "other_pred": [[o["img_warp_4"][i]] for i in range(T)],
+                "flowt0_pred": [[o["flowt0_1"][i], o["flowt0_4"][i]] for i in range(T)],
+                "flowt1_pred": [[o["flowt1_1"][i], o["flowt1_4"][i]] for i in range(T)],
+                "raft_flow": o["raft_flow"],
+                "ninrflow": [o["ninrflow"][i] for i in range(T)],
+                "nflow": o["nflow"],
+                "flowt": [o["flowt"][i].squeeze() for i in range(T)],  # .squeeze() as gimmvfi_r.py:370
+            })
+        return out
+
+    def warp_frame(self, frame, flow):
+        """gimmvfi_r.py:409-410 — backward warp of an NCHW frame by an NCHW flow."""
+        import ctypes as C
+
+        from ._lib import default_lib, view_of
+
+        lib = default_lib()
+        src = frame.to(torch.float32).permute(0, 2, 3, 1).contiguous()
+        fl = flow.to(torch.float32).permute(0, 2, 3, 1).contiguous()
+        dst = torch.empty(fl.shape[0], fl.shape[1], fl.shape[2], src.shape[3], device=src.device)
+        s = C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)
+        lib.check(lib.dll.gimmvfi_op_backwarp(C.byref(view_of(src)), C.byref(view_of(fl)), C.byref(view_of(dst)), s))
+        return dst.permute(0, 3, 1, 2).contiguous()
+
+    def compute_psnr(self, preds, targets, reduction="mean"):
+        """gimmvfi_r.py:412-426"""
+        assert reduction in ["mean", "sum", "none"]
+        mse = torch.reshape((preds - targets) ** 2, (preds.shape[0], -1)).mean(dim=-1)
+        psnr = -10 * torch.log10(mse)
+        return psnr.mean() if reduction == "mean" else (psnr.sum() if reduction == "sum" else psnr)
+
+
+def create_model(config, ema: bool = False):
+    """src/models/__init__.py:15-37 for the built model types."""
+    model_type = config.type.lower()
+    if model_type != "gimmvfi_r":
+        raise ValueError("%s is not built in gimmvfi_b200 (GIMM-VFI-R only; see DESIGN.md scope)" % model_type)
+    if ema:
+        raise NotImplementedError("EMA wrappers are training-only (src/models/ema.py) and out of scope")
+    return GIMMVFI_R(config), None

@@ -82,6 +82,10 @@ int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters);
 /* debug taps: intermediate tensors of the last forward (views into the workspace) */
 int gimmvfi_set_debug(gimmvfi_engine* e, int on);
 int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out);
+/* per-kernel CUDA-event timing of subsequent forwards; profile_json() synchronises the stream and
+ * returns {"kernel": {"ms": total, "work": flops-or-elements, "launches": n}, ...} for the LAST forward */
+int gimmvfi_set_profile(gimmvfi_engine* e, int on);
+const char* gimmvfi_profile_json(gimmvfi_engine* e, void* cuda_stream);
 const char* gimmvfi_build_info(void);
 
 /* ---- per-kernel entry points (unit tests; all NHWC fp32 device views) ---- */

@@ -1,0 +1,126 @@
+"""Helpers that call the per-kernel C-ABI entry points with torch tensors (NHWC fp32)."""
+import ctypes as C
+
+import torch
+
+from gimmvfi_b200._lib import View, default_lib, view_of
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream) if t.is_cuda else None
+
+
+def nhwc(x):  # NCHW -> contiguous NHWC
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def pack_weight(w):  # (cout,cin,kh,kw) -> [kh*kw][cin][cout_ld]
+    cout, cin, kh, kw = w.shape
+    ld = (cout + 3) // 4 * 4
+    p = torch.zeros(kh * kw, cin, ld, device=w.device)
+    p[:, :, :cout] = w.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    return p.contiguous(), ld
+
+
+def conv2d(x_nhwc, w, b, stride=1, pad=(0, 0), reflect=False, act=0, slope=None, residual=None, x1_nhwc=None, lib=None,
+           in_view=None, in1_view=None):
+    lib = lib or default_lib()
+    cout, cin, kh, kw = w.shape
+    pw, ld = pack_weight(w)
+    bb = torch.zeros(ld, device=w.device)
+    bb[:cout] = b
+    n, h, wd, _ = x_nhwc.shape
+    oh = (h + 2 * pad[0] - kh) // stride + 1
+    ow = (wd + 2 * pad[1] - kw) // stride + 1
+    out = torch.empty(n, oh, ow, cout, device=w.device)
+    v0 = in_view if in_view is not None else view_of(x_nhwc)
+    v1 = in1_view if in1_view is not None else (view_of(x1_nhwc) if x1_nhwc is not None else None)
+    rv = view_of(residual) if residual is not None else None
+    rc = lib.dll.gimmvfi_op_conv2d(C.byref(v0), C.byref(v1) if v1 is not None else None, C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()),
+                                   cin, cout, ld, kh, kw, stride, pad[0], pad[1], int(reflect), act,
+                                   C.c_void_p(slope.data_ptr()) if slope is not None else None,
+                                   C.byref(rv) if rv is not None else None, C.byref(view_of(out)), _stream(out))
+    lib.check(rc)
+    return out
+
+
+def softsplat(lat, flow, metric, t, t_mode, lib=None):
+    lib = lib or default_lib()
+    n, h, w, _ = lat.shape
+    scratch = torch.empty(n, h, w, 20, device=lat.device)
+    out = torch.empty(n, h, w, 16, device=lat.device)
+    lib.check(lib.dll.gimmvfi_op_softsplat(C.byref(view_of(lat)), C.byref(view_of(flow)), C.byref(view_of(metric)), C.c_void_p(t.data_ptr()),
+                                           t_mode, C.byref(view_of(scratch)), C.byref(view_of(out)), _stream(out)))
+    return out
+
+
+def backwarp(src, flow, lib=None):
+    lib = lib or default_lib()
+    out = torch.empty(flow.shape[0], flow.shape[1], flow.shape[2], src.shape[3], device=src.device)
+    lib.check(lib.dll.gimmvfi_op_backwarp(C.byref(view_of(src)), C.byref(view_of(flow)), C.byref(view_of(out)), _stream(out)))
+    return out
+
+
+def resize(src, scale, mult=1.0, lib=None):
+    lib = lib or default_lib()
+    n, h, w, c = src.shape
+    out = torch.empty(n, int(h * scale), int(w * scale), c, device=src.device)
+    lib.check(lib.dll.gimmvfi_op_resize(C.byref(view_of(src)), C.byref(view_of(out)), float(scale), float(mult), _stream(out)))
+    return out
+
+
+def corr_pyramid(fa, fb, lib=None):
+    """fa, fb (n,h,w,C) -> [level tensors (n*h*w, h_l, w_l)]"""
+    lib = lib or default_lib()
+    n, h, w, _ = fa.shape
+    N = h * w
+    lv = [torch.empty(n * N, h, w, device=fa.device)]
+    lib.check(lib.dll.gimmvfi_op_corr_volume(C.byref(view_of(fa)), C.byref(view_of(fb)), C.c_void_p(lv[0].data_ptr()), _stream(fa)))
+    hh, ww = h, w
+    for _ in range(3):
+        nxt = torch.empty(n * N, hh // 2, ww // 2, device=fa.device)
+        lib.check(lib.dll.gimmvfi_op_corr_pool(C.c_void_p(lv[-1].data_ptr()), C.c_void_p(nxt.data_ptr()), n * N, hh, ww, _stream(fa)))
+        lv.append(nxt)
+        hh, ww = hh // 2, ww // 2
+    return lv
+
+
+def corr_lookup(levels, coords, lib=None):
+    lib = lib or default_lib()
+    n, h, w, _ = coords.shape
+    out = torch.empty(n, h, w, 324, device=coords.device)
+    ptrs = (C.c_void_p * 4)(*[l.data_ptr() for l in levels])
+    hs = (C.c_int32 * 4)(*[l.shape[1] for l in levels])
+    ws = (C.c_int32 * 4)(*[l.shape[2] for l in levels])
+    lib.check(lib.dll.gimmvfi_op_corr_lookup(ptrs, hs, ws, C.byref(view_of(coords)), C.byref(view_of(out)), _stream(out)))
+    return out
+
+
+def instnorm(x, relu, lib=None):
+    lib = lib or default_lib()
+    n, h, w, c = x.shape
+    scratch = torch.empty(int(lib.dll.gimmvfi_instnorm_scratch_floats(n, c)) + 64, device=x.device)
+    out = torch.empty_like(x)
+    lib.check(lib.dll.gimmvfi_op_instnorm(C.byref(view_of(x)), int(relu), C.c_void_p(scratch.data_ptr()), C.byref(view_of(out)), _stream(x)))
+    return out
+
+
+def convex_upsample(flow, mask, lib=None):
+    lib = lib or default_lib()
+    n, h, w, _ = flow.shape
+    out = torch.empty(n, 8 * h, 8 * w, 2, device=flow.device)
+    lib.check(lib.dll.gimmvfi_op_convex_upsample(C.byref(view_of(flow)), C.byref(view_of(mask)), C.byref(view_of(out)), _stream(out)))
+    return out
+
+
+def pixel_shuffle(src, times, lib=None):
+    lib = lib or default_lib()
+    n, h, w, c = src.shape
+    r = 2 ** times
+    out = torch.empty(n, h * r, w * r, c // (r * r), device=src.device)
+    lib.check(lib.dll.gimmvfi_op_pixel_shuffle(C.byref(view_of(src)), C.byref(view_of(out)), times, _stream(out)))
+    return out

@@ -1,0 +1,145 @@
+"""GPU parity tests of every C-ABI kernel entry point against the oracle / plain
+PyTorch fp32 of the same op.  Tolerances are written next to each check."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gimmvfi_r_oracle as O
+import gpu_ops as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*s, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*s, generator=g) * scale).to(DEV)
+
+
+CONV_CASES = [
+    # cin, cout, kh, kw, stride, pad, reflect, act, H, W, n
+    (64, 64, 3, 3, 1, (1, 1), False, 0, 24, 40, 2),
+    (273, 256, 3, 3, 1, (1, 1), False, 3, 16, 24, 1),     # final-decoder stem: odd cin, PReLU
+    (3, 64, 7, 7, 2, (3, 3), False, 1, 64, 96, 2),        # RAFT stem: tiny cin, stride 2
+    (384, 128, 1, 5, 1, (0, 2), False, 4, 16, 20, 2),     # SepConvGRU horizontal, sigmoid
+    (384, 128, 5, 1, 1, (2, 0), False, 5, 16, 20, 1),     # vertical, tanh
+    (256, 2, 3, 3, 1, (1, 1), False, 0, 16, 20, 2),       # flow head: tiny cout
+    (9, 18, 7, 7, 1, (3, 3), False, 3, 32, 48, 1),        # comb block
+    (32, 16, 3, 3, 1, (1, 1), True, 0, 20, 28, 2),        # reflect padding
+    (324, 256, 1, 1, 1, (0, 0), False, 1, 16, 20, 2),     # 1x1 on the lookup
+    (35, 128, 1, 1, 1, (0, 0), False, 6, 24, 24, 1),      # HypoNet layer 0: sin
+    (64, 96, 1, 1, 2, (0, 0), False, 0, 32, 48, 2),       # 1x1 stride-2 downsample
+    (256, 126, 3, 3, 1, (1, 1), False, 1, 16, 20, 1),     # cout not a multiple of 4... 126
+    (128, 133, 3, 3, 1, (1, 1), False, 0, 16, 24, 1),
+    (8, 32, 5, 5, 1, (2, 2), False, 3, 32, 32, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d(case):
+    cin, cout, kh, kw, stride, pad, reflect, act, H, W, n = case
+    x = rnd(n, cin, H, W, seed=1)
+    w = rnd(cout, cin, kh, kw, seed=2, scale=1.0 / (cin * kh * kw) ** 0.5)
+    b = rnd(cout, seed=3, scale=0.1)
+    slope = (0.25 + 0.1 * rnd(cout, seed=4)) if act == 3 else None
+    got = K.nchw(K.conv2d(K.nhwc(x), w, b, stride, pad, reflect, act, slope))
+    xp = F.pad(x, (pad[1], pad[1], pad[0], pad[0]), mode="reflect") if reflect else x
+    ref = F.conv2d(xp.double(), w.double(), b.double(), stride=stride, padding=(0, 0) if reflect else pad)
+    ref = {0: lambda v: v, 1: F.relu, 2: lambda v: F.leaky_relu(v, 0.1), 3: lambda v: F.prelu(v, slope.double()),
+           4: torch.sigmoid, 5: torch.tanh, 6: torch.sin}[act](ref).float()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 2e-5  # fp32 accumulate vs fp64 reference
+
+
+def test_conv2d_two_segments_and_residual():
+    """cat([a[:, :192], s]) input (ResBlock splice) + residual epilogue."""
+    a = rnd(1, 256, 16, 24, seed=1)
+    s = rnd(1, 64, 16, 24, seed=2)
+    w = rnd(256, 256, 3, 3, seed=3, scale=0.02)
+    b = rnd(256, seed=4, scale=0.1)
+    res = rnd(1, 256, 16, 24, seed=5)
+    a_nhwc, s_nhwc = K.nhwc(a), K.nhwc(s)
+    got = K.nchw(K.conv2d(a_nhwc, w, b, 1, (1, 1), residual=K.nhwc(res), x1_nhwc=s_nhwc, in_view=K.view_of(a_nhwc, channels=192)))
+    ref = F.conv2d(torch.cat([a[:, :192], s], 1).double(), w.double(), b.double(), padding=1).float() + res
+    assert (got - ref).abs().max().item() <= 2e-5
+
+
+def test_softsplat_vs_oracle():
+    n, h, w = 2, 40, 56
+    lat = rnd(n, 16, h, w, seed=1)
+    flow = rnd(n, 2, h, w, seed=2, scale=4.0)
+    flow[0, 0, 3, 3] = float("nan")
+    flow[1, 1, 5, 7] = float("inf")
+    flow[0, :, 0, 0] = torch.tensor([2.0, 1.0], device=DEV)   # integer landing
+    flow[0, :, 10:14, 10:14] = 100.0                           # leaves the frame -> holes stay 0
+    metric = 0.5 + rnd(n, 1, h, w, seed=3).abs()
+    t = torch.tensor([0.5, 0.25], device=DEV)
+    for mode in (0, 1):
+        got = K.nchw(K.softsplat(K.nhwc(lat), K.nhwc(flow), K.nhwc(metric), t, mode))
+        sc = (t if mode == 0 else (1 - t)).view(n, 1, 1, 1)
+        ref = O.softsplat_linear_zeroeps(lat.cpu(), (flow * sc).cpu(), metric.cpu()).to(DEV)
+        assert (got - ref).abs().max().item() <= 2e-5  # atomics order only
+
+
+def test_backwarp_vs_oracle():
+    src = rnd(2, 19, 24, 40, seed=1)
+    flow = rnd(2, 2, 24, 40, seed=2, scale=6.0)   # includes out-of-frame targets (border clamp)
+    got = K.nchw(K.backwarp(K.nhwc(src), K.nhwc(flow)))
+    ref = O.backwarp(src.cpu(), flow.cpu()).to(DEV)
+    assert (got - ref).abs().max().item() <= 1e-4  # coordinate round trip differs by ~1 ulp of 40 px
+
+
+@pytest.mark.parametrize("scale", [0.25, 0.5, 2.0, 4.0])
+def test_resize_vs_interpolate(scale):
+    x = rnd(2, 5, 24, 40, seed=1)
+    got = K.nchw(K.resize(K.nhwc(x), scale, 1.5))
+    ref = 1.5 * F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 1e-5
+
+
+def test_corr_volume_pyramid_lookup():
+    n, h, w, C = 2, 16, 20, 256
+    fa, fb = rnd(n, C, h, w, seed=1), rnd(n, C, h, w, seed=2)
+    lv = K.corr_pyramid(K.nhwc(fa), K.nhwc(fb))
+    vol = O.all_pairs_corr(fa.cpu(), fb.cpu())
+    pyr = O.corr_pyramid(vol.reshape(n * h * w, 1, h, w))
+    for a, b in zip(lv, pyr):
+        assert a.shape == b[:, 0].shape
+        assert (a.cpu() - b[:, 0]).abs().max().item() <= 1e-4   # K=256 fp32 dot products, |v| ~ 16
+    coords = O.coords_grid(n, h, w) + 3.0 * torch.randn(n, 2, h, w, generator=torch.Generator().manual_seed(3))
+    coords[0, :, 0, 0] = torch.tensor([-20.0, 50.0])  # far outside: zero padding
+    got = K.nchw(K.corr_lookup(lv, K.nhwc(coords.to(DEV))))
+    ref = O.corr_lookup(pyr, coords)
+    assert (got.cpu() - ref).abs().max().item() <= 2e-3  # bilinear weights after a float normalise round trip x |v|~16
+    # the transposed-window quirk (raft/corr.py:152-158): channel a*9+b <-> (dx, dy) = (a-4, b-4)
+    c0 = O.coords_grid(1, h, w)
+    g2 = K.nchw(K.corr_lookup([l[: h * w] for l in lv], K.nhwc(c0.to(DEV))))
+    v0 = lv[0][: h * w].view(h, w, h, w)
+    y, x = 8, 9
+    assert abs(g2[0, 5 * 9 + 3, y, x].item() - v0[y, x, y - 1, x + 1].item()) <= 1e-4  # a=5 -> dx=+1, b=3 -> dy=-1
+
+
+def test_instnorm():
+    x = rnd(2, 96, 20, 28, seed=1, scale=3.0) + 2.0
+    got = K.nchw(K.instnorm(K.nhwc(x), True))
+    ref = F.relu(F.instance_norm(x.double(), eps=1e-5)).float()
+    assert (got - ref).abs().max().item() <= 2e-5
+
+
+def test_convex_upsample():
+    flow = rnd(2, 2, 16, 20, seed=1, scale=2.0)
+    mask = rnd(2, 576, 16, 20, seed=2)
+    got = K.nchw(K.convex_upsample(K.nhwc(flow), K.nhwc(mask)))
+    ref = O.convex_upsample(flow.cpu(), mask.cpu()).to(DEV)
+    assert (got - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("times", [1, 2])
+def test_pixel_shuffle(times):
+    x = rnd(2, 128, 8, 12, seed=1)
+    got = K.nchw(K.pixel_shuffle(K.nhwc(x), times))
+    ref = x
+    for _ in range(times):
+        ref = F.pixel_shuffle(ref, 2)
+    assert torch.equal(got, ref)
