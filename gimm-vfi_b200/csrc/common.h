@@ -71,6 +71,9 @@ struct ConvW {
   const float* b = nullptr;
   int cin = 0, cout = 0, kh = 1, kw = 1;
   int cout_ld = 0;  // row stride of w (cout rounded up to 4)
+  // tensor-core layout (conv_tc.cu): w_tc[tap][cout_pad][cin_pad], TF32-rounded, zero padded
+  const float* w_tc = nullptr;
+  int cout_pad = 0, cin_pad = 0;
 };
 
 // y = act2( res + act1(conv(x) + b) ) * mul      (res / mul optional)
@@ -124,6 +127,7 @@ struct Profiler {
 
 struct Ctx {
   Profiler* prof = nullptr;
+  bool tc = false;        // route eligible convolutions to the tcgen05 path
   gvStream_t stream = nullptr;
   Arena arena;
   bool dry = false;       // skip kernel launches (planning)
@@ -185,6 +189,9 @@ GV_HD float atomic_add_f(float* addr, float v) {
 // conv.cu
 void conv2d(Ctx& cx, const TV& in0, const TV& in1 /*optional 2nd channel segment*/, const ConvW& w, const ConvGeom& g,
             const ConvEpi& e, const TV& out);
+// conv_tc.cu (sm_100a tcgen05 / TMA path; not part of the host simulation)
+bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out);
+void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out);
 // corr.cu
 void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale);   // vol[n][i][j] = <fa[n,i], fb[n,j]> * scale
 void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w); // rows x (h*w) -> rows x (h/2*w/2)

@@ -160,6 +160,9 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
     int eh = (in0.h + 2 * g.ph - w.kh) / g.stride + 1, ew = (in0.w + 2 * g.pw - w.kw) / g.stride + 1;
     if (eh != out.h || ew != out.w || in0.n != out.n) throw std::runtime_error("conv2d: output geometry mismatch");
   }
+#ifndef GV_HOSTSIM
+  if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out)) { conv2d_tc(cx, in0, in1, w, g, e, out); return; }
+#endif
   cx.launches++;
 #ifdef GV_HOSTSIM
   const int OH = out.h, OW = out.w, IH = in0.h, IW = in0.w;

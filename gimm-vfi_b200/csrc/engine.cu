@@ -155,8 +155,31 @@ ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float ou
   }
   ConvW c;
   c.w = upload(pw); c.b = upload(pb); c.cin = cin; c.cout = cout; c.kh = kh; c.kw = kw; c.cout_ld = cout_ld;
+  pack_tc(c, pw);
   conv_[name] = c;
   return c;
+}
+
+// round-to-nearest-even to TF32 (10-bit mantissa): the tensor core ignores the low 13 bits
+static float tf32_rn(float x) {
+  uint32_t u; std::memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u += 0xfffu + ((u >> 13) & 1u);
+  u &= 0xffffe000u;
+  float y; std::memcpy(&y, &u, 4);
+  return y;
+}
+
+// [tap][cin][cout_ld] fp32  ->  [tap][cout_pad][cin_pad] TF32 (K-major rows for the UMMA B operand)
+void Engine::pack_tc(ConvW& c, const std::vector<float>& pw) {
+  const int cout_pad = (c.cout + 15) & ~15, cin_pad = (c.cin + 31) & ~31, taps = c.kh * c.kw;
+  if (cout_pad > 256) return;
+  std::vector<float> t((size_t)taps * cout_pad * cin_pad, 0.f);
+  for (int tp = 0; tp < taps; ++tp)
+    for (int ci = 0; ci < c.cin; ++ci)
+      for (int co = 0; co < c.cout; ++co)
+        t[((size_t)tp * cout_pad + co) * cin_pad + ci] = tf32_rn(pw[((size_t)tp * c.cin + ci) * c.cout_ld + co]);
+  c.w_tc = upload(t); c.cout_pad = cout_pad; c.cin_pad = cin_pad;
 }
 
 void Engine::finalize_weights() {
@@ -234,6 +257,7 @@ void Engine::finalize_weights() {
       pb[co] = wb.data[(size_t)fin * fout + co] + (l == 4 ? 0.5f : 0.f);
     }
     ConvW c; c.w = upload(pw); c.b = upload(pb); c.cin = fin; c.cout = fout; c.kh = c.kw = 1; c.cout_ld = ld;
+    pack_tc(c, pw);
     conv_[key] = c;
   }
   g9_ = vec("g_filter"); alpha_fe_ = vec("alpha_fe"); alpha_v_ = vec("alpha_v");
@@ -543,6 +567,8 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     for (int j = 0; j < 2; ++j)
       nhwc_to_nchw(cx, flow_up.batch(j * B, B), io.raft_flow + (int64_t)j * H * W, (int64_t)4 * H * W, (int64_t)2 * H * W, 1.f, 0.f, 0);
 
+  // Everything downstream of RAFT tolerates TF32 operands (DESIGN.md precision plan).
+  cx.tc = use_tc_;
   // ------------------------------------------------------------ bidirectional volume on projected features
   TV fproj = A.tensor(2 * B, h, w, 256);
   N.conv("amt_fproj", fmap, fproj);

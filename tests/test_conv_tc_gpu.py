@@ -1,0 +1,85 @@
+"""tcgen05 / TMA TF32 convolution (csrc/conv_tc.cu) vs PyTorch.
+
+Strict check: against an fp64 convolution of the SAME operands the tensor core sees
+(activations truncated to TF32 as the MMA does, weights rounded RN at pack time) — only
+the fp32 accumulation order differs -> tolerance 5e-5 relative to the output scale.
+Loose check: against the un-rounded fp32 convolution -> TF32 operand rounding, 3e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gpu_ops as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*s, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*s, generator=g) * scale).to(DEV)
+
+
+def act_fn(a, slope):
+    return {0: lambda v: v, 1: F.relu, 2: lambda v: F.leaky_relu(v, 0.1), 3: lambda v: F.prelu(v, slope.double()), 6: torch.sin}[a]
+
+
+CASES = [
+    # cin, cout, k, H, W, n, act1
+    (32, 16, 1, 8, 16, 1, 0),      # one tile, one K block, 1x1: the minimal MMA
+    (32, 16, 1, 16, 32, 2, 0),     # several tiles / persistent loop
+    (128, 64, 1, 16, 32, 1, 1),    # 4 K blocks
+    (64, 64, 3, 16, 32, 1, 0),     # 3x3 halo via TMA OOB zero fill
+    (64, 64, 3, 20, 28, 2, 2),     # ragged tiles (H, W not multiples of 8 / 16)
+    (256, 256, 3, 24, 40, 1, 3),   # the dominant final-decoder shape, N=256, PReLU
+    (273, 256, 3, 16, 24, 1, 3),   # cin tail block zero-filled
+    (64, 64, 5, 16, 32, 1, 3),     # 5x5
+    (256, 24, 3, 16, 32, 1, 0),    # cout 24 -> N=32 padded
+    (256, 188, 3, 16, 20, 1, 2),   # cout 188 -> N=192
+    (648, 256, 1, 16, 20, 2, 2),   # K=648 1x1 (corr features)
+    (35, 128, 1, 24, 24, 1, 6),    # HypoNet layer 0, sin
+    (8, 32, 5, 32, 32, 1, 3),      # tiny cin
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv2d_tc(case):
+    cin, cout, k, H, W, n, act1 = case
+    x = rnd(n, cin, H, W, seed=1)
+    w = rnd(cout, cin, k, k, seed=2, scale=1.0 / (cin * k * k) ** 0.5)
+    b = rnd(cout, seed=3, scale=0.1)
+    slope = (0.25 + 0.1 * rnd(cout, seed=4)) if act1 == 3 else None
+    got = K.nchw(K.conv2d_tc(K.nhwc(x), w, b, act1, slope))
+    f = act_fn(act1, slope)
+    strict = f(F.conv2d(K.tf32_trunc(x).double(), K.tf32_rn(w).double(), b.double(), padding=k // 2)).float()
+    loose = f(F.conv2d(x.double(), w.double(), b.double(), padding=k // 2)).float()
+    e_strict = (got - strict).abs().max().item()
+    e_loose = (got - loose).abs().max().item()
+    print("case", case, "strict %.3e loose %.3e ref absmax %.3e" % (e_strict, e_loose, loose.abs().max().item()))
+    assert e_strict <= 5e-5
+    assert e_loose <= 3e-3
+
+
+def test_conv2d_tc_two_segments_residual_act2():
+    """ResBlock conv5: prelu(x + conv(cat[b[:, :192], s2]))  (fi_components.py:147-153)."""
+    a = rnd(1, 256, 16, 32, seed=1)
+    s = rnd(1, 64, 16, 32, seed=2)
+    w = rnd(256, 256, 3, 3, seed=3, scale=0.02)
+    b = rnd(256, seed=4, scale=0.1)
+    res = rnd(1, 256, 16, 32, seed=5)
+    slope = 0.25 + 0.1 * rnd(256, seed=6)
+    a_nhwc = K.nhwc(a)
+    got = K.nchw(K.conv2d_tc(a_nhwc, w, b, 0, None, K.nhwc(res), 3, slope, x1_nhwc=K.nhwc(s), in_view=K.view_of(a_nhwc, channels=192)))
+    xin = torch.cat([a[:, :192], s], 1)
+    ref = F.prelu(res.double() + F.conv2d(K.tf32_trunc(xin).double(), K.tf32_rn(w).double(), b.double(), padding=1), slope.double()).float()
+    assert (got - ref).abs().max().item() <= 5e-5
+
+
+def test_conv2d_tc_channel_slice_views():
+    """Input = channel slice of a wider buffer (ld > c), output into a slice."""
+    buf = rnd(1, 276, 16, 32, seed=1)
+    w = rnd(64, 64, 3, 3, seed=2, scale=0.05)
+    b = rnd(64, seed=3, scale=0.1)
+    buf_nhwc = K.nhwc(buf)
+    got = K.nchw(K.conv2d_tc(buf_nhwc, w, b, in_view=K.view_of(buf_nhwc, channels=64, offset=128)))
+    ref = F.conv2d(K.tf32_trunc(buf[:, 128:192]).double(), K.tf32_rn(w).double(), b.double(), padding=1).float()
+    assert (got - ref).abs().max().item() <= 5e-5
