@@ -115,6 +115,7 @@ struct Arena {
 
 // Optional per-launch timing (CUDA events on the launching stream), keyed by kernel name.
 struct ProfRec { const char* name; double work; void* ev0; void* ev1; };
+const char* prof_intern(const std::string& s);  // stable storage for dynamically built kernel labels
 struct Profiler {
   std::vector<ProfRec> recs;
   std::vector<void*> pool; size_t used = 0;

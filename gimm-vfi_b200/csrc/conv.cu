@@ -193,7 +193,11 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
              (!in1.p || (in1.ld % 4 == 0 && al16(in1.p) && in1.sn % 4 == 0 && in0.c % 4 == 0));
   if (in1.p && in0.c % 16 != 0) throw std::runtime_error("conv2d: first concat segment must be a multiple of 16 channels");
   if (w.cout_ld % 4 != 0) throw std::runtime_error("conv2d: cout_ld must be a multiple of 4");
-  if (cx.prof) cx.prof->begin(cx.stream, w.cout <= 16 ? "conv2d_simt_n16" : "conv2d_simt_n64", 2.0 * a.M * w.cout * (double)w.cin * w.kh * w.kw);
+  if (cx.prof) {
+    char nm[128];
+    snprintf(nm, sizeof nm, "conv2d_simt_n%d k%dx%d s%d c%d>%d @%dx%dx%d", w.cout <= 16 ? 16 : 64, w.kh, w.kw, g.stride, w.cin, w.cout, out.n, out.h, out.w);
+    cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * a.M * w.cout * (double)w.cin * w.kh * w.kw);
+  }
   if (w.cout <= 16) {
     dim3 grid((a.M + 127) / 128, (w.cout + 15) / 16);
     conv2d_simt_kernel<16, 4, 2><<<grid, 256, 0, cx.stream>>>(a);

@@ -253,6 +253,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 f = apply_act(f, p.act1, p.slope1, c);
                 if (rptr) f += rptr[c];
                 f = apply_act(f, p.act2, p.slope2, c);
+                // store TF32-representable values (round-to-nearest-even): the next tensor-core layer then
+                // truncates nothing, i.e. operands are RN- instead of toward-zero-rounded (unbiased)
+                uint32_t bits = __float_as_uint(f);
+                bits += 0xfffu + ((bits >> 13) & 1u);
+                f = __uint_as_float(bits & 0xffffe000u);
               }
               o[u] = f;
             }
@@ -352,7 +357,11 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   }
   const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
   cx.launches++;
-  if (cx.prof) cx.prof->begin(cx.stream, "conv2d_tc_tf32", 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
+  if (cx.prof) {
+    char nm[128];
+    snprintf(nm, sizeof nm, "conv2d_tc_tf32 k%dx%d c%d>%d @%dx%dx%d", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
+    cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
+  }
   conv2d_tc_kernel<<<grid, NUM_THREADS, smem, cx.stream>>>(mA0, mA1, mB, p);
   gv_check_launch("conv2d_tc");
   if (cx.prof) cx.prof->end(cx.stream);

@@ -39,6 +39,12 @@ void dev_sync(gvStream_t s) { cuda_ok(cudaStreamSynchronize(s), "cudaStreamSynch
 // ---------------------------------------------------------------------------
 // Profiler (CUDA events around every launch; off by default)
 // ---------------------------------------------------------------------------
+const char* prof_intern(const std::string& s) {
+  static std::map<std::string, std::string> pool;
+  auto it = pool.find(s);
+  if (it == pool.end()) it = pool.emplace(s, s).first;
+  return it->second.c_str();
+}
 #ifdef GV_HOSTSIM
 void* Profiler::get_event() { return nullptr; }
 void Profiler::begin(gvStream_t, const char*, double) {}

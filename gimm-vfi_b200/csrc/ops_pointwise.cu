@@ -187,8 +187,12 @@ void pixel_shuffle(Ctx& cx, const TV& src, const TV& dst, int times) {
 
 // ----------------------------------------------------------- instance norm
 // nn.InstanceNorm2d(C): no affine, biased variance, eps 1e-5 (raft/extractor.py:30-34,133-134).
-static const int IN_CHUNKS = 64;
-int64_t instnorm_scratch_floats(const TV& x) { return (int64_t)x.n * IN_CHUNKS * x.c * 4; }
+static const int IN_CHUNKS_MAX = 1024;
+static int in_chunks(const TV& x) {  // ~64 pixels per thread, enough threads to fill 148 SMs
+  int64_t hw = (int64_t)x.h * x.w; int64_t c = hw / 64;
+  return (int)(c < 1 ? 1 : (c > IN_CHUNKS_MAX ? IN_CHUNKS_MAX : c));
+}
+int64_t instnorm_scratch_floats(const TV& x) { return (int64_t)x.n * IN_CHUNKS_MAX * x.c * 4; }
 
 struct InPartialK {
   TV x; double* part; int chunks;
@@ -216,8 +220,9 @@ struct InFinalK {
 };
 void instnorm_stats(Ctx& cx, const TV& x, float* mean_rstd, float* scratch, int64_t) {
   double* part = reinterpret_cast<double*>(scratch);
-  parallel_for(cx, (int64_t)x.n * IN_CHUNKS * x.c, InPartialK{x, part, IN_CHUNKS}, "instnorm_partial");
-  parallel_for(cx, (int64_t)x.n * x.c, InFinalK{part, mean_rstd, x.c, IN_CHUNKS, 1.0 / ((double)x.h * x.w)}, "instnorm_final");
+  const int chunks = in_chunks(x);
+  parallel_for(cx, (int64_t)x.n * chunks * x.c, InPartialK{x, part, chunks}, "instnorm_partial");
+  parallel_for(cx, (int64_t)x.n * x.c, InFinalK{part, mean_rstd, x.c, chunks, 1.0 / ((double)x.h * x.w)}, "instnorm_final");
 }
 struct InApplyK {
   TV x, res, out; const float* mr; int act1, act2;
@@ -237,7 +242,7 @@ void instnorm_apply(Ctx& cx, const TV& x, const float* mean_rstd, int act1, cons
 
 // ------------------------------------------------------- flow normalisation
 // modules/fi_utils.py:52-60: scaler[n] = max |cat[f01, -f10]|.
-static const int AM_CHUNKS = 256;
+static const int AM_CHUNKS = 4096;
 int64_t absmax_scratch_floats(const TV& a) { return (int64_t)a.n * AM_CHUNKS; }
 struct AbsmaxPartK {
   TV a, b; float* part; int chunks;

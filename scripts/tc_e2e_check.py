@@ -15,6 +15,7 @@ from gimmvfi_b200.synth import synth_batch
 
 dev = "cuda"
 model = GIMMVFI_R(seed=0).to(dev).eval()
+model.tensor_cores = False
 sd = {k: v.cpu() for k, v in model.state_dict().items()}
 eng = model.engine
 
@@ -30,7 +31,7 @@ def run(B, H, W, t=0.5, seed=3):
 for (B, H, W) in [(1, 128, 160), (1, 256, 448)]:
     res = {}
     for tc in (False, True):
-        eng.set_tensor_cores(tc)
+        model.tensor_cores = tc
         xs, out = run(B, H, W)
         res[tc] = out
     with torch.no_grad():
@@ -43,7 +44,7 @@ for (B, H, W) in [(1, 128, 160), (1, 256, 448)]:
 H, W = 1088, 1920
 outs = {}
 for tc in (False, True):
-    eng.set_tensor_cores(tc)
+    model.tensor_cores = tc
     for _ in range(2):
         xs, out = run(1, H, W, seed=100)
     t0 = time.perf_counter()
@@ -57,9 +58,9 @@ for tc in (False, True):
     eng.set_profile(False)
     tot = sum(v["ms"] for v in prof.values())
     print("1080p tc=%s: %.1f ms/forward (incl. synth+H2D), kernels sum %.1f ms" % (tc, dt * 1e3, tot))
-    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]:
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:(30 if tc else 6)]:
         extra = " %.1f TFLOP/s" % (v["work"] / v["ms"] / 1e9) if k.startswith(("conv2d", "corr_gemm")) else ""
-        print("   %-22s %8.2f ms %4d launches%s" % (k, v["ms"], v["launches"], extra))
+        print("   %-62s %8.2f ms %4d launches%s" % (k, v["ms"], v["launches"], extra))
     with open(os.path.join(ROOT, "gpurun_out", "profile_1080p_tc%d.json" % int(tc)), "w") as f:
         json.dump(prof, f)
 d = (outs[True] - outs[False]).abs()

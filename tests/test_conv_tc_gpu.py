@@ -48,14 +48,21 @@ def test_conv2d_tc(case):
     w = rnd(cout, cin, k, k, seed=2, scale=1.0 / (cin * k * k) ** 0.5)
     b = rnd(cout, seed=3, scale=0.1)
     slope = (0.25 + 0.1 * rnd(cout, seed=4)) if act1 == 3 else None
-    got = K.nchw(K.conv2d_tc(K.nhwc(x), w, b, act1, slope))
+    xn = K.nhwc(x)
+    if cin % 4:  # TMA needs 16-byte pixel strides: the engine pads such buffers (ld 276 / 36), so does the test
+        pad = torch.full((n, H, W, (cin + 3) // 4 * 4), 7.0, device=DEV)   # non-zero padding lanes must be ignored
+        pad[..., :cin] = xn
+        got = K.nchw(K.conv2d_tc(pad, w, b, act1, slope, in_view=K.view_of(pad, channels=cin)))
+    else:
+        got = K.nchw(K.conv2d_tc(xn, w, b, act1, slope))
     f = act_fn(act1, slope)
     strict = f(F.conv2d(K.tf32_trunc(x).double(), K.tf32_rn(w).double(), b.double(), padding=k // 2)).float()
     loose = f(F.conv2d(x.double(), w.double(), b.double(), padding=k // 2)).float()
     e_strict = (got - strict).abs().max().item()
     e_loose = (got - loose).abs().max().item()
     print("case", case, "strict %.3e loose %.3e ref absmax %.3e" % (e_strict, e_loose, loose.abs().max().item()))
-    assert e_strict <= 5e-5
+    # outputs are stored rounded to TF32 (RN): |err| <= 2^-11 * |value| on top of the accumulation-order term
+    assert e_strict <= 5e-5 + 2.0 ** -11 * loose.abs().max().item()
     assert e_loose <= 3e-3
 
 
@@ -71,7 +78,7 @@ def test_conv2d_tc_two_segments_residual_act2():
     got = K.nchw(K.conv2d_tc(a_nhwc, w, b, 0, None, K.nhwc(res), 3, slope, x1_nhwc=K.nhwc(s), in_view=K.view_of(a_nhwc, channels=192)))
     xin = torch.cat([a[:, :192], s], 1)
     ref = F.prelu(res.double() + F.conv2d(K.tf32_trunc(xin).double(), K.tf32_rn(w).double(), b.double(), padding=1), slope.double()).float()
-    assert (got - ref).abs().max().item() <= 5e-5
+    assert (got - ref).abs().max().item() <= 5e-5 + 2.0 ** -11 * ref.abs().max().item()
 
 
 def test_conv2d_tc_channel_slice_views():
@@ -82,4 +89,4 @@ def test_conv2d_tc_channel_slice_views():
     buf_nhwc = K.nhwc(buf)
     got = K.nchw(K.conv2d_tc(buf_nhwc, w, b, in_view=K.view_of(buf_nhwc, channels=64, offset=128)))
     ref = F.conv2d(K.tf32_trunc(buf[:, 128:192]).double(), K.tf32_rn(w).double(), b.double(), padding=1).float()
-    assert (got - ref).abs().max().item() <= 5e-5
+    assert (got - ref).abs().max().item() <= 5e-5 + 2.0 ** -11 * ref.abs().max().item()

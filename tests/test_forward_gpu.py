@@ -22,10 +22,12 @@ DEV = "cuda"
 TOL_IMG = 1e-3
 
 
-@pytest.fixture(scope="module")
-def model(weights0):
+@pytest.fixture(scope="module", params=["tf32_tensor_cores", "fp32"])
+def model(request, weights0):
+    """Both precisions: the default (post-RAFT convs on tcgen05 TF32, RAFT fp32) and fp32 everywhere."""
     m = GIMMVFI_R(seed=0).to(DEV).eval()
     m.load_state_dict(weights0, strict=True)
+    m.tensor_cores = request.param == "tf32_tensor_cores"
     return m
 
 
@@ -58,7 +60,7 @@ def test_forward_matches_reference_golden(name, golden_manifest, model):
         assert mx <= TOL_IMG and rmse <= 1e-4
         fmx, fp, frm = stats(out["flowt"][i][..., ::s, ::s].cpu(), torch.from_numpy(g["flowt_%d" % i]))
         print(name, i, "flowt max %.3e p99.99 %.3e rmse %.3e" % (fmx, fp, frm))
-        assert fp <= 2e-2 and frm <= 5e-3   # flow in pixels, |flow| ~ 15
+        assert fp <= 5e-2 and frm <= 1e-2   # flow in pixels, |flow| ~ 15 (TF32 HypoNet: ~4e-3 mean)
         w4 = out["other_pred"][i][0][..., :: 2 * s, :: 2 * s].cpu()
         assert stats(w4, torch.from_numpy(g["img_warp_4_%d" % i]))[0] <= TOL_IMG
         f4 = out["flowt0_pred"][i][1][..., ::s, ::s].cpu()
@@ -123,10 +125,10 @@ def test_batch_consistency_and_determinism(model):
     both = model(xs, c2, t=t2)["imgt_pred"][0]
     a = model(xs[:1].contiguous(), c1, t=t1)["imgt_pred"][0]
     b = model(xs[1:].contiguous(), c1, t=t1)["imgt_pred"][0]
-    assert (both[0] - a[0]).abs().max().item() <= 1e-5
-    assert (both[1] - b[0]).abs().max().item() <= 1e-5
+    assert (both[0] - a[0]).abs().max().item() <= 2e-5
+    assert (both[1] - b[0]).abs().max().item() <= 2e-5
     again = model(xs, c2, t=t2)["imgt_pred"][0]
-    assert (both - again).abs().max().item() <= 1e-5
+    assert (both - again).abs().max().item() <= 2e-5
 
 
 def test_full_size_properties(model):
