@@ -23,7 +23,9 @@ namespace gv {
 
 namespace tc {
 
-constexpr int TILE_H = 8, TILE_W = 16, BM = 128, BK = 32, STAGES = 4;
+constexpr int TILE_H = 8, TILE_W = 16, BM = 128, BK = 32, MAX_STAGES = 8;
+constexpr int STG_PITCH = 36;                       // floats per staged row (32 + 4: keeps float4 alignment)
+constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;   // 4 epilogue warps x 32 rows
 constexpr int A_BYTES = BM * BK * 4;  // 16 KB
 constexpr int NUM_THREADS = 192;
 
@@ -33,6 +35,7 @@ struct Params {
   int tiles_x, tiles_y, n_img;
   int H, W;
   int BN;                          // MMA N (multiple of 16)
+  int stages;                      // smem ring depth (<= MAX_STAGES), sized from BN on the host
   int cout;
   const float* bias;
   int act1; const float* slope1;
@@ -137,12 +140,14 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.BN * BK * 4;
   const int stage_bytes = A_BYTES + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const int STAGES = p.stages;
+  float* stg_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + STG_BYTES);
+  uint64_t* full_bar = bars;                          // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.n_img * p.tiles_y * p.tiles_x;
@@ -221,55 +226,86 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else {
     // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+    // TMEM gives each thread one pixel (row) x 32 consecutive channels.  Writing that straight to NHWC
+    // scatters 16-byte pieces over 32 different lines per store (measured: ~230 GB/s chip-wide), so the
+    // 32x32 chunk is transposed through shared memory and written as full 128-byte rows.
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;                 // pixel within the 8x16 tile
-    const int py = row / TILE_W, px = row % TILE_W;
+    float* stg = stg_base + (warp - 2) * 32 * STG_PITCH;
+    const int q8 = lane & 7, rsub = lane >> 3;      // write phase: 8 lanes x float4 = one 128-byte row, 4 rows / instruction
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tx = tile % p.tiles_x; const int r = tile / p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
-      const int y = ty * TILE_H + py, x = tx * TILE_W + px;
-      const bool valid = y < p.H && x < p.W;
+      // rows this lane writes in the coalesced phase: rr = quarter*32 + it*4 + rsub
+      int64_t ooff[8], roff[8]; uint32_t vmask = 0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = quarter * 32 + it * 4 + rsub;
+        const int y = ty * TILE_H + rr / TILE_W, x = tx * TILE_W + rr % TILE_W;
+        const bool ok = y < p.H && x < p.W;
+        vmask |= (ok ? 1u : 0u) << it;
+        ooff[it] = ok ? p.out.off(n, y, x) : 0;
+        roff[it] = (ok && p.res.p) ? p.res.off(n, y, x) : 0;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-      float* optr = valid ? p.out.p + p.out.off(n, y, x) : nullptr;
-      const float* rptr = (valid && p.res.p) ? p.res.p + p.res.off(n, y, x) : nullptr;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (valid) {
+        // phase 1 (thread = pixel row): bias + act1, stage to smem
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int co = c0 + j;
-            if (co >= p.cout) break;
-            float o[4];
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + j + u;
+            float f = __uint_as_float(v[j + u]);
+            if (c < p.cout) { f += p.bias[c]; f = apply_act(f, p.act1, p.slope1, c); }
+            o[u] = f;
+          }
+          *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+        // phase 2 (8 lanes = one 128-byte row): + residual, act2, TF32 round-to-nearest, coalesced store
+        const int c = c0 + q8 * 4;
+        if (c < p.cout) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (!((vmask >> it) & 1u)) continue;
+            const float4 sv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * STG_PITCH + q8 * 4);
+            float o[4] = {sv.x, sv.y, sv.z, sv.w};
+            float* optr = p.out.p + ooff[it] + c;
+            const float* rptr = p.res.p ? p.res.p + roff[it] + c : nullptr;
+            const bool full4 = c + 3 < p.cout;
+            if (rptr) {
+              if (full4 && ((reinterpret_cast<uintptr_t>(rptr) & 15) == 0)) {
+                const float4 rv = *reinterpret_cast<const float4*>(rptr);
+                o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (c + u < p.cout) o[u] += rptr[u];
+              }
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const int c = co + u;
-              float f = __uint_as_float(v[j + u]);
-              if (c < p.cout) {
-                f += p.bias[c];
-                f = apply_act(f, p.act1, p.slope1, c);
-                if (rptr) f += rptr[c];
-                f = apply_act(f, p.act2, p.slope2, c);
-                // store TF32-representable values (round-to-nearest-even): the next tensor-core layer then
-                // truncates nothing, i.e. operands are RN- instead of toward-zero-rounded (unbiased)
-                uint32_t bits = __float_as_uint(f);
-                bits += 0xfffu + ((bits >> 13) & 1u);
-                f = __uint_as_float(bits & 0xffffe000u);
-              }
-              o[u] = f;
+              float f = o[u];
+              if (c + u < p.cout) f = apply_act(f, p.act2, p.slope2, c + u);
+              // store TF32-representable values (round-to-nearest-even): the next tensor-core layer then
+              // truncates nothing, i.e. its operands are RN- instead of toward-zero-rounded (unbiased)
+              uint32_t bits = __float_as_uint(f);
+              bits += 0xfffu + ((bits >> 13) & 1u);
+              o[u] = __uint_as_float(bits & 0xffffe000u);
             }
-            if (co + 3 < p.cout && ((reinterpret_cast<uintptr_t>(optr + co) & 15) == 0)) {
-              *reinterpret_cast<float4*>(optr + co) = make_float4(o[0], o[1], o[2], o[3]);
+            if (full4 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+              *reinterpret_cast<float4*>(optr) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (co + u < p.cout) optr[co + u] = o[u];
+              for (int u = 0; u < 4; ++u) if (c + u < p.cout) optr[u] = o[u];
             }
           }
         }
+        __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -348,7 +384,12 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.H = out.h; p.W = out.w; p.BN = w.cout_pad; p.cout = w.cout;
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2; p.res = e.res; p.out = out;
   const int num_tiles = p.n_img * p.tiles_y * p.tiles_x;
-  const int smem = STAGES * (A_BYTES + p.BN * BK * 4) + 256 + 1024;
+  const int stage_bytes = A_BYTES + p.BN * BK * 4;
+  const int budget = 227 * 1024 - 1024 /*align*/ - STG_BYTES - 512 /*barriers*/;
+  p.stages = budget / stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (p.stages < 2) throw std::runtime_error("conv_tc: not enough shared memory for 2 pipeline stages");
+  const int smem = p.stages * stage_bytes + STG_BYTES + 512 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t er = cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -63,7 +63,7 @@ def test_conv2d_tc(case):
     print("case", case, "strict %.3e loose %.3e ref absmax %.3e" % (e_strict, e_loose, loose.abs().max().item()))
     # outputs are stored rounded to TF32 (RN): |err| <= 2^-11 * |value| on top of the accumulation-order term
     assert e_strict <= 5e-5 + 2.0 ** -11 * loose.abs().max().item()
-    assert e_loose <= 3e-3
+    assert e_loose <= 3e-3 + 2.0 ** -10 * loose.abs().max().item()
 
 
 def test_conv2d_tc_two_segments_residual_act2():
