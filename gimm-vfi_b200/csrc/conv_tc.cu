@@ -132,6 +132,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
+// Rare activations (sigmoid / tanh / sin) go through ONE out-of-line copy: inlining the accurate sinf/tanhf/expf
+// paths at every element site made the epilogue ~25k SASS instructions (instruction-cache bound, ~10 us per
+// 32-column chunk measured).
+__device__ __noinline__ float act_slow(float v, int act) {
+  switch (act) {
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case ACT_TANH: return tanhf(v);
+    case ACT_SIN: return sinf(v);
+    default: return v;
+  }
+}
+// 4 consecutive channels starting at c (c % 4 == 0; slope padded like the bias is not guaranteed -> bounds via cout)
+__device__ __forceinline__ void act4(float* o, int act, const float* slope, int c, int cout) {
+  if (act == ACT_NONE) return;
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o[u] = fmaxf(o[u], 0.f);
+  } else if (act == ACT_LRELU) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o[u] = o[u] > 0.f ? o[u] : 0.1f * o[u];
+  } else if (act == ACT_PRELU) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const float sl = (c + u < cout) ? slope[c + u] : 0.f; o[u] = o[u] > 0.f ? o[u] : sl * o[u]; }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o[u] = act_slow(o[u], act);
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
                  const Params p) {
@@ -253,17 +282,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // phase 1 (thread = pixel row): bias + act1, stage to smem
+        // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to BN on the host.
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c0 + j + u;
-            float f = __uint_as_float(v[j + u]);
-            if (c < p.cout) { f += p.bias[c]; f = apply_act(f, p.act1, p.slope1, c); }
-            o[u] = f;
-          }
+          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + j);
+          float o[4] = {__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y, __uint_as_float(v[j + 2]) + b4.z,
+                        __uint_as_float(v[j + 3]) + b4.w};
+          act4(o, p.act1, p.slope1, c0 + j, p.cout);
           *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
         __syncwarp();
@@ -287,13 +312,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int u = 0; u < 4; ++u) if (c + u < p.cout) o[u] += rptr[u];
               }
             }
+            act4(o, p.act2, p.slope2, c, p.cout);
+            // store TF32-representable values (round-to-nearest-even): the next tensor-core layer then
+            // truncates nothing, i.e. its operands are RN- instead of toward-zero-rounded (unbiased)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float f = o[u];
-              if (c + u < p.cout) f = apply_act(f, p.act2, p.slope2, c + u);
-              // store TF32-representable values (round-to-nearest-even): the next tensor-core layer then
-              // truncates nothing, i.e. its operands are RN- instead of toward-zero-rounded (unbiased)
-              uint32_t bits = __float_as_uint(f);
+              uint32_t bits = __float_as_uint(o[u]);
               bits += 0xfffu + ((bits >> 13) & 1u);
               o[u] = __uint_as_float(bits & 0xffffe000u);
             }

@@ -151,7 +151,7 @@ ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float ou
     }
   }
   const int cout_ld = (cout + 3) & ~3;
-  std::vector<float> pw((size_t)kh * kw * cin * cout_ld, 0.f), pb(cout_ld, 0.f);
+  std::vector<float> pw((size_t)kh * kw * cin * cout_ld, 0.f), pb((cout + 15) & ~15, 0.f);  // bias padded for float4 reads
   for (int co = 0; co < cout; ++co) {
     const int src = perm ? (*perm)[co] : co;
     for (int ci = 0; ci < cin; ++ci)
@@ -254,7 +254,7 @@ void Engine::finalize_weights() {
     const HostTensor& wb = raw(key);
     const int fin = (int)wb.shape[0] - 1, fout = (int)wb.shape[1];
     const int ld = (fout + 3) & ~3;
-    std::vector<float> pw((size_t)fin * ld, 0.f), pb(ld, 0.f);
+    std::vector<float> pw((size_t)fin * ld, 0.f), pb((fout + 15) & ~15, 0.f);
     for (int co = 0; co < fout; ++co) {
       double nrm = 0.0;
       for (int ci = 0; ci < fin; ++ci) { double v = wb.data[(size_t)ci * fout + co]; nrm += v * v; }
@@ -299,7 +299,8 @@ struct Net {
 };
 
 static ConvW slice_cout(const ConvW& w, int co0, int cnt) {
-  ConvW s = w; s.w = w.w + co0; s.b = w.b + co0; s.cout = cnt; return s;
+  ConvW s = w; s.w = w.w + co0; s.b = w.b + co0; s.cout = cnt; s.w_tc = nullptr;  // TC layout is not sliceable this way
+  return s;
 }
 
 // raft/extractor.py:173-220.  x: (n,H,W,3) -> fmap (n,H/8,W/8,256) [+ layer2/layer3 outputs]
