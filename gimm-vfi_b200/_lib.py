@@ -87,7 +87,7 @@ class Lib:
         d.gimmvfi_build_info.restype = C.c_char_p
         d.gimmvfi_set_profile.argtypes = [vp, i32]
         d.gimmvfi_set_tensor_cores.argtypes = [vp, i32]
-        d.gimmvfi_op_conv2d_tc.argtypes = [PV, PV, vp, vp, i32, i32, i32, i32, i32, vp, PV, i32, vp, PV, vp]
+        d.gimmvfi_op_conv2d_tc.argtypes = [PV, PV, vp, vp, i32, i32, i32, i32, i32, vp, PV, i32, vp, PV, PV, PV, i32, PV, vp]
         d.gimmvfi_profile_json.argtypes = [vp, vp]
         d.gimmvfi_profile_json.restype = C.c_char_p
         d.gimmvfi_op_softsplat.argtypes = [PV, PV, PV, vp, i32, PV, PV, vp]

@@ -76,7 +76,7 @@ int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out) {
     out->data = t.p; out->n = t.n; out->h = t.h; out->w = t.w; out->c = t.c; out->pixel_stride = t.ld; out->batch_stride = t.sn;
   })
 }
-int gimmvfi_set_tensor_cores(gimmvfi_engine* e, int on) { GV_TRY(e, { e->eng.set_tensor_cores(on != 0); }) }
+int gimmvfi_set_tensor_cores(gimmvfi_engine* e, int mode) { GV_TRY(e, { e->eng.set_tensor_cores(mode); }) }
 int gimmvfi_set_profile(gimmvfi_engine* e, int on) { GV_TRY(e, { e->eng.set_profile(on != 0); }) }
 const char* gimmvfi_profile_json(gimmvfi_engine* e, void* stream) {
   try { e->prof_json = e->eng.profile_json((gvStream_t)stream); } catch (const std::exception& ex) { e->err = ex.what(); e->prof_json = "{}"; }
@@ -149,6 +149,7 @@ int gimmvfi_op_conv2d(const gimmvfi_view* in0, const gimmvfi_view* in1, const fl
 }
 int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1, const float* w_tc, const float* bias, int cin, int cout, int kh,
                          int kw, int act1, const float* slope1, const gimmvfi_view* residual, int act2, const float* slope2,
+                         const gimmvfi_view* mul, const gimmvfi_view* gru_z, const gimmvfi_view* gru_h, int split,
                          const gimmvfi_view* out, void* stream) {
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, {
@@ -156,12 +157,13 @@ int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1, const
     throw std::runtime_error("conv2d_tc is a tcgen05 kernel; not available in the host simulation");
 #else
     Ctx cx = op_ctx(stream);
-    ConvW w; w.b = bias; w.cin = cin; w.cout = cout; w.kh = kh; w.kw = kw; w.w_tc = w_tc;
-    w.cout_pad = (cout + 15) & ~15; w.cin_pad = (cin + 31) & ~31;
+    ConvW w; w.b = bias; w.cin = cin; w.cout = cout; w.kh = kh; w.kw = kw; w.w_tc = w_tc; w.has_lo = true;
+    w.cout_pad = tc_cout_pad(cout); w.cin_pad = (cin + 31) & ~31;
     ConvGeom g; g.stride = 1; g.ph = kh / 2; g.pw = kw / 2;
     ConvEpi ep; ep.act1 = act1; ep.slope1 = slope1; ep.res = to_tv(residual); ep.act2 = act2; ep.slope2 = slope2;
-    if (!conv2d_tc_supported(to_tv(in0), to_tv(in1), w, g, ep, to_tv(out))) throw std::runtime_error("conv2d_tc: unsupported configuration");
-    conv2d_tc(cx, to_tv(in0), to_tv(in1), w, g, ep, to_tv(out));
+    ep.mul = to_tv(mul); ep.gru_z = to_tv(gru_z); ep.gru_h = to_tv(gru_h);
+    if (!conv2d_tc_supported(to_tv(in0), to_tv(in1), w, g, ep, to_tv(out), split != 0)) throw std::runtime_error("conv2d_tc: unsupported configuration");
+    conv2d_tc(cx, to_tv(in0), to_tv(in1), w, g, ep, to_tv(out), split != 0);
 #endif
   })
 }

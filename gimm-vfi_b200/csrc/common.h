@@ -71,10 +71,21 @@ struct ConvW {
   const float* b = nullptr;
   int cin = 0, cout = 0, kh = 1, kw = 1;
   int cout_ld = 0;  // row stride of w (cout rounded up to 4)
-  // tensor-core layout (conv_tc.cu): w_tc[tap][cout_pad][cin_pad], TF32-rounded, zero padded
+  // tensor-core layout (conv_tc.cu): w_tc[2][tap][cout_pad][cin_pad] zero padded; plane 0 = tf32_rn(w),
+  // plane 1 = tf32_rn(w - plane0) (the "lo" term of the 3xTF32 split, present when has_lo)
   const float* w_tc = nullptr;
   int cout_pad = 0, cin_pad = 0;
+  bool has_lo = false;
 };
+
+// N tiling of the tensor-core path: cout padded to 16, split into <= 256-wide tiles of equal width.
+inline void tc_tile_n(int cout, int* bn, int* tiles_n) {
+  const int c16 = (cout + 15) & ~15;
+  const int tn = (c16 + 255) / 256;
+  *tiles_n = tn;
+  *bn = (((c16 + tn - 1) / tn) + 15) & ~15;
+}
+inline int tc_cout_pad(int cout) { int bn, tn; tc_tile_n(cout, &bn, &tn); return bn * tn; }
 
 // y = act2( res + act1(conv(x) + b) ) * mul      (res / mul optional)
 // gru:  y = (1 - z) * hprev + z * y               (SepConvGRU update, raft/update.py:58,66)
@@ -129,6 +140,7 @@ struct Profiler {
 struct Ctx {
   Profiler* prof = nullptr;
   bool tc = false;        // route eligible convolutions to the tcgen05 path
+  bool tc_split = false;  // ... with 3xTF32 operand splitting (fp32-class accuracy)
   gvStream_t stream = nullptr;
   Arena arena;
   bool dry = false;       // skip kernel launches (planning)
@@ -191,8 +203,8 @@ GV_HD float atomic_add_f(float* addr, float v) {
 void conv2d(Ctx& cx, const TV& in0, const TV& in1 /*optional 2nd channel segment*/, const ConvW& w, const ConvGeom& g,
             const ConvEpi& e, const TV& out);
 // conv_tc.cu (sm_100a tcgen05 / TMA path; not part of the host simulation)
-bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out);
-void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out);
+bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
+void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 // corr.cu
 void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale);   // vol[n][i][j] = <fa[n,i], fb[n,j]> * scale
 void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w); // rows x (h*w) -> rows x (h/2*w/2)

@@ -161,7 +161,7 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
     if (eh != out.h || ew != out.w || in0.n != out.n) throw std::runtime_error("conv2d: output geometry mismatch");
   }
 #ifndef GV_HOSTSIM
-  if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out)) { conv2d_tc(cx, in0, in1, w, g, e, out); return; }
+  if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out, cx.tc_split)) { conv2d_tc(cx, in0, in1, w, g, e, out, cx.tc_split); return; }
 #endif
   cx.launches++;
 #ifdef GV_HOSTSIM

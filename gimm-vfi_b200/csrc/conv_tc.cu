@@ -1,19 +1,26 @@
 // Tensor-core implicit-GEMM convolution for sm_100a: TMA tile loads with halo
 // coordinates -> 128B-swizzled shared memory -> tcgen05.mma (kind::tf32, fp32
-// accumulate in TMEM) -> fused epilogue from TMEM.
+// accumulate in TMEM) -> fused, coalesced epilogue from TMEM.
 //
 //   GEMM view   M = 128 output pixels (an 8 x 16 spatial tile of one image)
-//               N = cout (padded to 16, <= 256, one tile)
+//               N = BN <= 256 output channels per tile (cout tiled if larger)
 //               K = taps x cin, walked as (tap, 32-channel block): each K step is ONE
 //                   TMA box {32 ch, 16 x, 8 y, 1 n} of the NHWC activation at the
 //                   tap-shifted coordinate (out-of-bounds -> zero fill = zero padding,
-//                   no im2col, no halo staging code) plus one {32 k, N} weight box.
+//                   no im2col, no halo staging code) plus one {32 k, BN} weight box.
 //   roles       warp 0: TMA producer | warp 1: MMA issuer (+TMEM alloc) | warps 2-5: epilogue
-//   pipelines   smem full/empty ring (4 stages), 2 TMEM accumulators (full/empty) so the
-//               epilogue of tile i overlaps the MMAs of tile i+1; persistent over tiles.
+//               | warps 6-9 (SPLIT only): operand splitter
+//   pipelines   smem full/empty ring, 2 TMEM accumulators (full/empty) so the epilogue of
+//               tile i overlaps the MMAs of tile i+1; persistent over tiles.
 //
-// Used for the post-RAFT networks (DESIGN.md "precision plan": TF32 operands there
-// move imgt_pred by < 3e-4; the RAFT recurrence stays on the fp32 path in conv.cu).
+// Two precisions:
+//   SPLIT=false  plain TF32 operands (the tensor core ignores the low 13 mantissa bits of A;
+//                weights are rounded RN at pack time; outputs are stored TF32-rounded so the
+//                next layer's truncation is exact).  Used after RAFT (DESIGN.md precision plan).
+//   SPLIT=true   "3xTF32": D += A*Bhi + A*Blo + Alo*Bhi with Alo = a - trunc_tf32(a) computed
+//                in shared memory by the splitter warps and Bhi/Blo pre-split at pack time:
+//                ~2^-21 relative error, i.e. fp32-class accuracy at 3 MMAs per K step.  Used
+//                for the RAFT recurrence, which amplifies operand rounding.
 #include "common.h"
 
 #ifndef GV_HOSTSIM
@@ -24,23 +31,25 @@ namespace gv {
 namespace tc {
 
 constexpr int TILE_H = 8, TILE_W = 16, BM = 128, BK = 32, MAX_STAGES = 8;
+constexpr int A_BYTES = BM * BK * 4;                // 16 KB
 constexpr int STG_PITCH = 36;                       // floats per staged row (32 + 4: keeps float4 alignment)
 constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;   // 4 epilogue warps x 32 rows
-constexpr int A_BYTES = BM * BK * 4;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int BAR_BYTES = 512;
 
 struct Params {
   int taps, kw, ph, pw;
   int kblocks, c0_blocks;          // 32-channel K blocks in total / from segment 0
-  int tiles_x, tiles_y, n_img;
+  int tiles_x, tiles_y, n_img, tiles_n;
   int H, W;
   int BN;                          // MMA N (multiple of 16)
-  int stages;                      // smem ring depth (<= MAX_STAGES), sized from BN on the host
+  int stages;                      // smem ring depth (<= MAX_STAGES), sized on the host
   int cout;
-  const float* bias;
+  int round_out;                   // store TF32-rounded (RN) values
+  int spin_limit;                  // mbarrier try_wait attempts before trapping (0 = wait forever)
+  const float* bias;               // padded to tiles_n * BN
   int act1; const float* slope1;
   int act2; const float* slope2;
-  TV res, out;
+  TV res, mul, gru_z, gru_h, out;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,11 +57,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// try_wait suspends the thread up to ~10 ms per attempt; a pipeline that makes no progress for
+// spin_limit attempts (default ~4 s) is a bug -> trap, so a would-be hang becomes a launch failure.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int spin_limit) {
   const uint32_t addr = smem_u32(bar);
-  // try_wait suspends the thread up to ~10 ms per attempt; a pipeline that makes no progress for
-  // ~4 s is a bug -> trap (turns a would-be hang into a launch failure the host reports).
-  for (int spin = 0; spin < 400; ++spin) {
+  for (int spin = 0; spin_limit == 0 || spin < spin_limit; ++spin) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
@@ -143,7 +152,7 @@ __device__ __noinline__ float act_slow(float v, int act) {
     default: return v;
   }
 }
-// 4 consecutive channels starting at c (c % 4 == 0; slope padded like the bias is not guaranteed -> bounds via cout)
+// 4 consecutive channels starting at c (c % 4 == 0)
 __device__ __forceinline__ void act4(float* o, int act, const float* slope, int c, int cout) {
   if (act == ACT_NONE) return;
   if (act == ACT_RELU) {
@@ -160,27 +169,41 @@ __device__ __forceinline__ void act4(float* o, int act, const float* slope, int 
     for (int u = 0; u < 4; ++u) o[u] = act_slow(o[u], act);
   }
 }
+// 4 channels of an optional side tensor at (pixel, channel c): float4 when in range and 16B aligned
+__device__ __forceinline__ void load4(const float* p, int c, int cout, float* r) {
+  if (c + 3 < cout && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = (c + u < cout) ? p[u] : 0.f;
+  }
+}
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 320 : 192, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
                  const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stage A (16 KB) | stage B (BN*128 B)] x STAGES, then barriers
+  // carve: per stage [A 16 KB | (A_lo 16 KB) | B BN*128 B | (B_lo)], then the epilogue staging area, then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.BN * BK * 4;
-  const int stage_bytes = A_BYTES + b_bytes;
+  const int a_all = SPLIT ? 2 * A_BYTES : A_BYTES;
+  const int stage_bytes = a_all + (SPLIT ? 2 * b_bytes : b_bytes);
   const int STAGES = p.stages;
   float* stg_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + STG_BYTES);
-  uint64_t* full_bar = bars;                          // [MAX_STAGES]
-  uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]
-  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]
-  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  uint64_t* full_bar = bars;                          // [MAX_STAGES]  TMA bytes landed
+  uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]  MMAs reading the stage retired
+  uint64_t* xf_bar = bars + 2 * MAX_STAGES;           // [MAX_STAGES]  (SPLIT) A_lo written
+  uint64_t* tfull_bar = bars + 3 * MAX_STAGES;        // [2]
+  uint64_t* tempty_bar = bars + 3 * MAX_STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.n_img * p.tiles_y * p.tiles_x;
+  const int num_tiles = p.n_img * p.tiles_y * p.tiles_x * p.tiles_n;
   const int ksteps = p.taps * p.kblocks;
+  const int SPIN = p.spin_limit;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0)) : "memory");
@@ -189,7 +212,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&xf_bar[s], 4); }
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -208,18 +231,20 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tx = tile % p.tiles_x; const int r = tile / p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
+        const int nt = tile % p.tiles_n; int r = tile / p.tiles_n;
+        const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int ky = tap / p.kw, kx = tap % p.kw;
           const int x0 = tx * TILE_W + kx - p.pw, y0 = ty * TILE_H + ky - p.ph;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait(&empty_bar[stage], phase ^ 1, SPIN);
             uint8_t* a_dst = smem + stage * stage_bytes;
-            uint8_t* b_dst = a_dst + A_BYTES;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + b_bytes));
+            uint8_t* b_dst = a_dst + a_all;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + (SPLIT ? 2 * b_bytes : b_bytes)));
             if (kb < p.c0_blocks) tma_load_4d(a_dst, &tmA0, &full_bar[stage], kb * BK, x0, y0, n);
             else tma_load_4d(a_dst, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * BK, x0, y0, n);
-            tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * BK, 0, tap);
+            tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * BK, nt * p.BN, tap);
+            if (SPLIT) tma_load_3d(b_dst + b_bytes, &tmB, &full_bar[stage], kb * BK, nt * p.BN, tap + p.taps);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -232,19 +257,27 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, SPIN);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
       for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(SPLIT ? &xf_bar[stage] : &full_bar[stage], phase, SPIN);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(a_addr);
-          const uint64_t bdesc = make_smem_desc(a_addr + A_BYTES);
+          const uint64_t bdesc = make_smem_desc(a_addr + a_all);
+          const uint64_t alo = make_smem_desc(a_addr + A_BYTES);
+          const uint64_t blo = make_smem_desc(a_addr + a_all + b_bytes);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k)  // UMMA_K = 8 tf32 = 32 B -> +2 in the (addr >> 4) field
-            mma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 B -> +2 in the (addr >> 4) field
+            const uint64_t ko = (uint64_t)(k * 2);
+            mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+            if (SPLIT) {
+              mma_tf32(d_tmem, adesc + ko, blo + ko, idesc, 1u);   // A_hi * B_lo
+              mma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, 1u);   // A_lo * B_hi
+            }
+          }
           mma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs retire
           if (ks == ksteps - 1) mma_commit(&tfull_bar[acc]);   // accumulator complete
         }
@@ -253,75 +286,77 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (warp < 6) {
     // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
-    // TMEM gives each thread one pixel (row) x 32 consecutive channels.  Writing that straight to NHWC
-    // scatters 16-byte pieces over 32 different lines per store (measured: ~230 GB/s chip-wide), so the
-    // 32x32 chunk is transposed through shared memory and written as full 128-byte rows.
+    // TMEM gives each thread one pixel (row) x 32 consecutive channels; the 32x32 chunk is transposed
+    // through shared memory so global reads/writes are full 128-byte rows (8 lanes x float4).
     const int quarter = warp & 3;
     float* stg = stg_base + (warp - 2) * 32 * STG_PITCH;
-    const int q8 = lane & 7, rsub = lane >> 3;      // write phase: 8 lanes x float4 = one 128-byte row, 4 rows / instruction
+    const int q8 = lane & 7, rsub = lane >> 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tx = tile % p.tiles_x; const int r = tile / p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
-      // rows this lane writes in the coalesced phase: rr = quarter*32 + it*4 + rsub
-      int64_t ooff[8], roff[8]; uint32_t vmask = 0;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = quarter * 32 + it * 4 + rsub;
-        const int y = ty * TILE_H + rr / TILE_W, x = tx * TILE_W + rr % TILE_W;
-        const bool ok = y < p.H && x < p.W;
-        vmask |= (ok ? 1u : 0u) << it;
-        ooff[it] = ok ? p.out.off(n, y, x) : 0;
-        roff[it] = (ok && p.res.p) ? p.res.off(n, y, x) : 0;
-      }
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      const int nt = tile % p.tiles_n; int r = tile / p.tiles_n;
+      const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
+      mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        const int cbase = nt * p.BN + c0;
+        if (cbase >= p.cout) break;   // warp-uniform
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to BN on the host.
+        // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to tiles_n*BN on the host.
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + j);
+          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cbase + j);
           float o[4] = {__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y, __uint_as_float(v[j + 2]) + b4.z,
                         __uint_as_float(v[j + 3]) + b4.w};
-          act4(o, p.act1, p.slope1, c0 + j, p.cout);
+          act4(o, p.act1, p.slope1, cbase + j, p.cout);
           *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
         __syncwarp();
-        // phase 2 (8 lanes = one 128-byte row): + residual, act2, TF32 round-to-nearest, coalesced store
-        const int c = c0 + q8 * 4;
+        // phase 2 (8 lanes = one 128-byte row, 4 rows per instruction): + residual, act2, gate multiply,
+        // ConvGRU blend, optional TF32 rounding, coalesced store
+        const int c = cbase + q8 * 4;
         if (c < p.cout) {
-#pragma unroll
+#pragma unroll 2
           for (int it = 0; it < 8; ++it) {
-            if (!((vmask >> it) & 1u)) continue;
+            const int rr = quarter * 32 + it * 4 + rsub;
+            const int y = ty * TILE_H + rr / TILE_W, x = tx * TILE_W + rr % TILE_W;
+            if (y >= p.H || x >= p.W) continue;
             const float4 sv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * STG_PITCH + q8 * 4);
             float o[4] = {sv.x, sv.y, sv.z, sv.w};
-            float* optr = p.out.p + ooff[it] + c;
-            const float* rptr = p.res.p ? p.res.p + roff[it] + c : nullptr;
-            const bool full4 = c + 3 < p.cout;
-            if (rptr) {
-              if (full4 && ((reinterpret_cast<uintptr_t>(rptr) & 15) == 0)) {
-                const float4 rv = *reinterpret_cast<const float4*>(rptr);
-                o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-              } else {
+            if (p.res.p) {
+              float t[4]; load4(p.res.p + p.res.off(n, y, x) + c, c, p.cout, t);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) if (c + u < p.cout) o[u] += rptr[u];
-              }
+              for (int u = 0; u < 4; ++u) o[u] += t[u];
             }
             act4(o, p.act2, p.slope2, c, p.cout);
-            // store TF32-representable values (round-to-nearest-even): the next tensor-core layer then
-            // truncates nothing, i.e. its operands are RN- instead of toward-zero-rounded (unbiased)
+            if (p.mul.p) {
+              float t[4]; load4(p.mul.p + p.mul.off(n, y, x) + c, c, p.cout, t);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint32_t bits = __float_as_uint(o[u]);
-              bits += 0xfffu + ((bits >> 13) & 1u);
-              o[u] = __uint_as_float(bits & 0xffffe000u);
+              for (int u = 0; u < 4; ++u) o[u] *= t[u];
             }
-            if (full4 && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
+            if (p.gru_z.p) {  // h = (1 - z) * h + z * q   (raft/update.py:58,66)
+              float z[4], h[4];
+              load4(p.gru_z.p + p.gru_z.off(n, y, x) + c, c, p.cout, z);
+              load4(p.gru_h.p + p.gru_h.off(n, y, x) + c, c, p.cout, h);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) o[u] = (1.f - z[u]) * h[u] + z[u] * o[u];
+            }
+            if (p.round_out) {
+              // store TF32-representable values (round-to-nearest-even): the next TF32 layer then truncates
+              // nothing, i.e. its operands are RN- instead of toward-zero-rounded (unbiased)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint32_t bits = __float_as_uint(o[u]);
+                bits += 0xfffu + ((bits >> 13) & 1u);
+                o[u] = __uint_as_float(bits & 0xffffe000u);
+              }
+            }
+            float* optr = p.out.p + p.out.off(n, y, x) + c;
+            if (c + 3 < p.cout && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
               *reinterpret_cast<float4*>(optr) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
@@ -335,6 +370,32 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (SPLIT) {
+    // ===================================================== operand splitter (warps 6..9)
+    // A_lo = a - trunc_tf32(a), written at the same (swizzled) offsets as A so one descriptor shape serves both.
+    const int t = threadIdx.x - 192;  // 0..127
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase, SPIN);
+        const float4* a = reinterpret_cast<const float4*>(smem + stage * stage_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem + stage * stage_bytes + A_BYTES);
+#pragma unroll
+        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+          const float4 v = a[t + i * 128];
+          float4 l;
+          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          lo[t + i * 128] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   }
   __syncthreads();
@@ -377,11 +438,11 @@ static void encode_act(CUtensorMap* m, const TV& t) {
 
 }  // namespace tc
 
-bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out) {
+bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  (void)e;
   if (!w.w_tc || g.stride != 1 || g.reflect) return false;
-  if (e.mul.p || e.gru_z.p) return false;
-  if (w.cout_pad > 256) return false;
+  if (split && !w.has_lo) return false;
   if (g.ph != w.kh / 2 || g.pw != w.kw / 2) return false;
   if (!al16(in0.p) || in0.ld % 4 || in0.sn % 4) return false;
   if (in1.p && (!al16(in1.p) || in1.ld % 4 || in1.sn % 4 || in0.c % 32)) return false;
@@ -389,34 +450,44 @@ bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const Con
   return true;
 }
 
-void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out) {
+void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
   using namespace tc;
   CUtensorMap mA0, mA1, mB;
   encode_act(&mA0, in0);
   if (in1.p) encode_act(&mA1, in1); else mA1 = mA0;
+  int BN, tiles_n;
+  tc_tile_n(w.cout, &BN, &tiles_n);
+  if (BN * tiles_n != w.cout_pad) throw std::runtime_error("conv_tc: weight padding does not match the N tiling");
+  const int taps = w.kh * w.kw;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)(w.kh * w.kw)};
+    cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)(taps * (w.has_lo ? 2 : 1))};
     cuuint64_t str[2] = {(cuuint64_t)w.cin_pad * 4, (cuuint64_t)w.cin_pad * w.cout_pad * 4};
-    cuuint32_t box[3] = {BK, (cuuint32_t)w.cout_pad, 1};
+    cuuint32_t box[3] = {BK, (cuuint32_t)BN, 1};
     encode(&mB, w.w_tc, 3, dims, str, box);
   }
   Params p;
-  p.taps = w.kh * w.kw; p.kw = w.kw; p.ph = g.ph; p.pw = g.pw;
+  p.taps = taps; p.kw = w.kw; p.ph = g.ph; p.pw = g.pw;
   p.c0_blocks = in1.p ? in0.c / 32 : (in0.c + 31) / 32;
   p.kblocks = w.cin_pad / 32;
-  p.tiles_x = (out.w + TILE_W - 1) / TILE_W; p.tiles_y = (out.h + TILE_H - 1) / TILE_H; p.n_img = out.n;
-  p.H = out.h; p.W = out.w; p.BN = w.cout_pad; p.cout = w.cout;
-  p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2; p.res = e.res; p.out = out;
-  const int num_tiles = p.n_img * p.tiles_y * p.tiles_x;
-  const int stage_bytes = A_BYTES + p.BN * BK * 4;
-  const int budget = 227 * 1024 - 1024 /*align*/ - STG_BYTES - 512 /*barriers*/;
+  p.tiles_x = (out.w + TILE_W - 1) / TILE_W; p.tiles_y = (out.h + TILE_H - 1) / TILE_H; p.n_img = out.n; p.tiles_n = tiles_n;
+  p.H = out.h; p.W = out.w; p.BN = BN; p.cout = w.cout;
+  p.round_out = split ? 0 : 1;
+  static int spin = -1;
+  if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
+  p.spin_limit = spin;
+  p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2;
+  p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
+  const int num_tiles = p.n_img * p.tiles_y * p.tiles_x * tiles_n;
+  const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
+  const int budget = 227 * 1024 - 1024 /*align*/ - STG_BYTES - BAR_BYTES;
   p.stages = budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.stages < 2) throw std::runtime_error("conv_tc: not enough shared memory for 2 pipeline stages");
-  const int smem = p.stages * stage_bytes + STG_BYTES + 512 + 1024;
+  const int smem = p.stages * stage_bytes + STG_BYTES + BAR_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t er = cudaFuncSetAttribute(conv2d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (er == cudaSuccess) er = cudaFuncSetAttribute(conv2d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
     attr_set = true;
   }
@@ -424,10 +495,11 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   cx.launches++;
   if (cx.prof) {
     char nm[128];
-    snprintf(nm, sizeof nm, "conv2d_tc_tf32 k%dx%d c%d>%d @%dx%dx%d", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
+    snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? "3xtf32" : "tf32", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
   }
-  conv2d_tc_kernel<<<grid, NUM_THREADS, smem, cx.stream>>>(mA0, mA1, mB, p);
+  if (split) conv2d_tc_kernel<true><<<grid, 320, smem, cx.stream>>>(mA0, mA1, mB, p);
+  else conv2d_tc_kernel<false><<<grid, 192, smem, cx.stream>>>(mA0, mA1, mB, p);
   gv_check_launch("conv2d_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }

@@ -151,7 +151,7 @@ ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float ou
     }
   }
   const int cout_ld = (cout + 3) & ~3;
-  std::vector<float> pw((size_t)kh * kw * cin * cout_ld, 0.f), pb((cout + 15) & ~15, 0.f);  // bias padded for float4 reads
+  std::vector<float> pw((size_t)kh * kw * cin * cout_ld, 0.f), pb(tc_cout_pad(cout), 0.f);  // bias padded to the tensor-core N tiling (float4 reads)
   for (int co = 0; co < cout; ++co) {
     const int src = perm ? (*perm)[co] : co;
     for (int ci = 0; ci < cin; ++ci)
@@ -176,16 +176,21 @@ static float tf32_rn(float x) {
   return y;
 }
 
-// [tap][cin][cout_ld] fp32  ->  [tap][cout_pad][cin_pad] TF32 (K-major rows for the UMMA B operand)
+// [tap][cin][cout_ld] fp32  ->  [2][tap][cout_pad][cin_pad]: plane 0 = TF32(w) (K-major rows for the UMMA B
+// operand), plane 1 = TF32(w - plane0), the low term of the 3xTF32 split
 void Engine::pack_tc(ConvW& c, const std::vector<float>& pw) {
-  const int cout_pad = (c.cout + 15) & ~15, cin_pad = (c.cin + 31) & ~31, taps = c.kh * c.kw;
-  if (cout_pad > 256) return;
-  std::vector<float> t((size_t)taps * cout_pad * cin_pad, 0.f);
+  const int cout_pad = tc_cout_pad(c.cout), cin_pad = (c.cin + 31) & ~31, taps = c.kh * c.kw;
+  const size_t plane = (size_t)taps * cout_pad * cin_pad;
+  std::vector<float> t(2 * plane, 0.f);
   for (int tp = 0; tp < taps; ++tp)
     for (int ci = 0; ci < c.cin; ++ci)
-      for (int co = 0; co < c.cout; ++co)
-        t[((size_t)tp * cout_pad + co) * cin_pad + ci] = tf32_rn(pw[((size_t)tp * c.cin + ci) * c.cout_ld + co]);
-  c.w_tc = upload(t); c.cout_pad = cout_pad; c.cin_pad = cin_pad;
+      for (int co = 0; co < c.cout; ++co) {
+        const float w = pw[((size_t)tp * c.cin + ci) * c.cout_ld + co];
+        const float hi = tf32_rn(w);
+        const size_t o = ((size_t)tp * cout_pad + co) * cin_pad + ci;
+        t[o] = hi; t[plane + o] = tf32_rn(w - hi);
+      }
+  c.w_tc = upload(t); c.cout_pad = cout_pad; c.cin_pad = cin_pad; c.has_lo = true;
 }
 
 void Engine::finalize_weights() {
@@ -254,7 +259,7 @@ void Engine::finalize_weights() {
     const HostTensor& wb = raw(key);
     const int fin = (int)wb.shape[0] - 1, fout = (int)wb.shape[1];
     const int ld = (fout + 3) & ~3;
-    std::vector<float> pw((size_t)fin * ld, 0.f), pb((fout + 15) & ~15, 0.f);
+    std::vector<float> pw((size_t)fin * ld, 0.f), pb(tc_cout_pad(fout), 0.f);
     for (int co = 0; co < fout; ++co) {
       double nrm = 0.0;
       for (int ci = 0; ci < fin; ++ci) { double v = wb.data[(size_t)ci * fout + co]; nrm += v * v; }
@@ -509,6 +514,8 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   float* scaler = A.alloc_f(std::max(B, 64));
 
   // ------------------------------------------------------------ RAFT (both directions batched)
+  // The recurrence amplifies operand rounding -> fp32-class arithmetic only: 3xTF32 tensor cores or CUDA cores.
+  cx.tc = tc_mode_ >= 2; cx.tc_split = true;
   {
     const size_t mk = A.mark();
     TV hx = A.tensor(2 * B, h, w, 384);              // [h | inp | motion]
@@ -527,7 +534,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     Pyramid pyr = build_pyramid(cx, fmap, B);
     const std::string u = "flow_estimator.update_block";
     TV coords1 = A.tensor(2 * B, h, w, 2);
-    TV flow = A.tensor(2 * B, h, w, 2);
+    TV flow = A.tensor(2 * B, h, w, 2, 4);   // ld 4: 16-byte pixel stride so the 7x7 2->128 conv can use TMA
     TV corr = A.tensor(2 * B, h, w, 324), cor1 = A.tensor(2 * B, h, w, 256), corflo = A.tensor(2 * B, h, w, 256);
     TV flo1 = A.tensor(2 * B, h, w, 128), zb = A.tensor(2 * B, h, w, 128), rh = A.tensor(2 * B, h, w, 128);
     TV fh = A.tensor(2 * B, h, w, 256), mask = A.tensor(2 * B, h, w, 576);
@@ -575,7 +582,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       nhwc_to_nchw(cx, flow_up.batch(j * B, B), io.raft_flow + (int64_t)j * H * W, (int64_t)4 * H * W, (int64_t)2 * H * W, 1.f, 0.f, 0);
 
   // Everything downstream of RAFT tolerates TF32 operands (DESIGN.md precision plan).
-  cx.tc = use_tc_;
+  cx.tc = tc_mode_ >= 1; cx.tc_split = false;
   // ------------------------------------------------------------ bidirectional volume on projected features
   TV fproj = A.tensor(2 * B, h, w, 256);
   N.conv("amt_fproj", fmap, fproj);

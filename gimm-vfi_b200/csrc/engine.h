@@ -53,7 +53,8 @@ class Engine {
   void set_debug(bool on) { debug_ = on; }
   // per-kernel CUDA-event timing of the next forward(s): {"name": {"ms", "work", "launches"}}
   void set_profile(bool on) { profile_ = on; }
-  void set_tensor_cores(bool on) { use_tc_ = on; }
+  // 0: fp32 CUDA cores everywhere; 1: post-RAFT convs on TF32 tensor cores; 2: + RAFT convs on 3xTF32 tensor cores
+  void set_tensor_cores(int mode) { tc_mode_ = mode; }
   std::string profile_json(gvStream_t stream);
   const std::map<std::string, TV>& taps() const { return taps_; }
   std::string last_error;
@@ -71,7 +72,8 @@ class Engine {
   void tap(const std::string& name, const TV& tv) { if (debug_) taps_[name] = tv; }
 
   int device_ = 0;
-  bool finalized_ = false, debug_ = false, profile_ = false, use_tc_ = false;
+  bool finalized_ = false, debug_ = false, profile_ = false;
+  int tc_mode_ = 0;
   void pack_tc(ConvW& c, const std::vector<float>& packed);
   Profiler prof_;
   int64_t launches_ = 0;

@@ -52,10 +52,10 @@ class EngineHandle:
         self.lib.check(self.lib.dll.gimmvfi_set_debug(self._h, int(on)), self._h)
         self._plans.clear()
 
-    def set_tensor_cores(self, on: bool):
-        """Route the post-RAFT convolutions to the tcgen05 TF32 kernels (conv_tc.cu)."""
-        self.lib.check(self.lib.dll.gimmvfi_set_tensor_cores(self._h, int(on)), self._h)
-        self.tensor_cores = bool(on)
+    def set_tensor_cores(self, mode: int):
+        """0: fp32 CUDA cores; 1: post-RAFT convs on tcgen05 TF32; 2: + RAFT convs on tcgen05 3xTF32 (conv_tc.cu)."""
+        self.lib.check(self.lib.dll.gimmvfi_set_tensor_cores(self._h, int(mode)), self._h)
+        self.tensor_cores = int(mode)
 
     def set_profile(self, on: bool):
         self.lib.check(self.lib.dll.gimmvfi_set_profile(self._h, int(on)), self._h)

@@ -62,8 +62,9 @@ class GIMMVFI_R(nn.Module):
         self._weights_dirty = True
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_weights_dirty", True))
         self.aux_outputs = True  # False: skip the auxiliary outputs (only imgt_pred is produced)
-        # True: post-RAFT convolutions on the tcgen05 TF32 kernels (RAFT stays fp32); False: fp32 everywhere
-        self.tensor_cores = True
+        # 0/False: fp32 CUDA cores everywhere; 1/True: post-RAFT convolutions on tcgen05 TF32 (RAFT on CUDA cores);
+        # 2: additionally RAFT on tcgen05 with 3xTF32 operand splitting (fp32-class accuracy)
+        self.tensor_cores = 1
 
     def _container(self, key: str):
         parts = key.split(".")
@@ -119,8 +120,8 @@ class GIMMVFI_R(nn.Module):
         if img_xs.device.type != "cuda":
             raise RuntimeError("GIMMVFI_R (gimmvfi_b200): inputs must live on a CUDA device; there is no CPU path")
         eng = self.engine
-        if getattr(eng, "tensor_cores", None) != bool(self.tensor_cores):
-            eng.set_tensor_cores(bool(self.tensor_cores))
+        if getattr(eng, "tensor_cores", None) != int(self.tensor_cores):
+            eng.set_tensor_cores(int(self.tensor_cores))
         B = img_xs.shape[0]
         xs = img_xs.to(torch.float32).contiguous()
         coords = torch.stack([c[0].to(torch.float32) for c in coord], 0).contiguous()  # (T,B,1,Hc,Wc,3)

@@ -82,8 +82,9 @@ int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters);
 /* debug taps: intermediate tensors of the last forward (views into the workspace) */
 int gimmvfi_set_debug(gimmvfi_engine* e, int on);
 int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out);
-/* 1 (default 0 until validated): run the post-RAFT convolutions on the tcgen05 TF32 path */
-int gimmvfi_set_tensor_cores(gimmvfi_engine* e, int on);
+/* 0: fp32 CUDA cores everywhere; 1: post-RAFT convolutions on the tcgen05 TF32 path (fp32 accumulate);
+ * 2: additionally the RAFT convolutions on tcgen05 with 3xTF32 operand splitting (fp32-class accuracy) */
+int gimmvfi_set_tensor_cores(gimmvfi_engine* e, int mode);
 /* per-kernel CUDA-event timing of subsequent forwards; profile_json() synchronises the stream and
  * returns {"kernel": {"ms": total, "work": flops-or-elements, "launches": n}, ...} for the LAST forward */
 int gimmvfi_set_profile(gimmvfi_engine* e, int on);
@@ -111,11 +112,13 @@ int gimmvfi_op_corr_lookup(const float* const lvl[4], const int32_t lvl_h[4], co
 int gimmvfi_op_conv2d(const gimmvfi_view* in0, const gimmvfi_view* in1_or_null, const float* w_packed, const float* bias, int cin,
                       int cout, int cout_ld, int kh, int kw, int stride, int pad_h, int pad_w, int reflect, int act,
                       const float* slope, const gimmvfi_view* residual_or_null, const gimmvfi_view* out, void* stream);
-/* tcgen05/TMA TF32 implicit-GEMM conv (stride 1, "same" zero padding): w_tc packed [kh*kw][cout_pad16][cin_pad32];
- * y = act2(residual + act1(conv + bias)) */
+/* tcgen05/TMA implicit-GEMM conv (stride 1, "same" zero padding).  w_tc packed [2][kh*kw][cout_pad][cin_pad32]
+ * (plane 0 = TF32(w), plane 1 = TF32(w - plane 0); cout_pad = N tiling of cout, see tc_tile_n); bias padded to cout_pad.
+ * y = gru( act2(residual + act1(conv + bias)) * mul );  split != 0 -> 3xTF32 (fp32-class accuracy, unrounded output) */
 int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1_or_null, const float* w_tc, const float* bias, int cin,
                          int cout, int kh, int kw, int act1, const float* slope1, const gimmvfi_view* residual_or_null, int act2,
-                         const float* slope2, const gimmvfi_view* out, void* stream);
+                         const float* slope2, const gimmvfi_view* mul_or_null, const gimmvfi_view* gru_z_or_null,
+                         const gimmvfi_view* gru_h_or_null, int split, const gimmvfi_view* out, void* stream);
 /* nn.InstanceNorm2d + optional relu: raft/extractor.py:133-134; scratch >= gimmvfi_instnorm_scratch_floats */
 int64_t gimmvfi_instnorm_scratch_floats(int n, int c);
 int gimmvfi_op_instnorm(const gimmvfi_view* x, int relu, float* scratch, const gimmvfi_view* out, void* stream);

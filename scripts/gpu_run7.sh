@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_conv_tc_gpu.py -q -rA -s 2>&1 | grep -E "^split case|FAILED|passed|failed|Error|rror:" | head -40 | tee gpurun_out/pytest_tc.log
+timeout 500 python scripts/tc_e2e_check.py 2>&1 | grep -v Warn | tail -62 | tee gpurun_out/tc_e2e.log

@@ -136,27 +136,38 @@ def tf32_trunc(x):
     return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
-def pack_weight_tc(w):  # (cout,cin,kh,kw) -> [kh*kw][cout_pad16][cin_pad32], TF32-RN
+def tc_cout_pad(cout):
+    c16 = (cout + 15) // 16 * 16
+    tn = (c16 + 255) // 256
+    bn = ((c16 + tn - 1) // tn + 15) // 16 * 16
+    return bn * tn
+
+
+def pack_weight_tc(w):  # (cout,cin,kh,kw) -> [2][kh*kw][cout_pad][cin_pad32]: TF32(w) and TF32(w - TF32(w))
     cout, cin, kh, kw = w.shape
-    cp, kp = (cout + 15) // 16 * 16, (cin + 31) // 32 * 32
-    p = torch.zeros(kh * kw, cp, kp, device=w.device)
-    p[:, :cout, :cin] = tf32_rn(w).permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    cp, kp = tc_cout_pad(cout), (cin + 31) // 32 * 32
+    p = torch.zeros(2, kh * kw, cp, kp, device=w.device)
+    hi = tf32_rn(w)
+    lo = tf32_rn(w - hi)
+    p[0, :, :cout, :cin] = hi.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    p[1, :, :cout, :cin] = lo.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
     return p.contiguous()
 
 
-def conv2d_tc(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2=None, x1_nhwc=None, in_view=None, lib=None):
+def conv2d_tc(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2=None, x1_nhwc=None, in_view=None, lib=None,
+              mul=None, gru_z=None, gru_h=None, split=False, out=None):
     lib = lib or default_lib()
     cout, cin, kh, kw = w.shape
     pw = pack_weight_tc(w)
-    bb = torch.zeros((cout + 15) // 16 * 16, device=w.device)
+    bb = torch.zeros(tc_cout_pad(cout), device=w.device)
     bb[:cout] = b
     n, h, wd, _ = x_nhwc.shape
-    out = torch.empty(n, h, wd, cout, device=w.device)
+    if out is None:
+        out = torch.empty(n, h, wd, cout, device=w.device)
     v0 = in_view if in_view is not None else view_of(x_nhwc)
-    v1 = view_of(x1_nhwc) if x1_nhwc is not None else None
-    rv = view_of(residual) if residual is not None else None
+    V = lambda t: C.byref(view_of(t)) if t is not None else None
     P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-    rc = lib.dll.gimmvfi_op_conv2d_tc(C.byref(v0), C.byref(v1) if v1 is not None else None, P(pw), P(bb), cin, cout, kh, kw, act1, P(slope1),
-                                      C.byref(rv) if rv is not None else None, act2, P(slope2), C.byref(view_of(out)), _stream(out))
+    rc = lib.dll.gimmvfi_op_conv2d_tc(C.byref(v0), V(x1_nhwc), P(pw), P(bb), cin, cout, kh, kw, act1, P(slope1), V(residual), act2, P(slope2),
+                                      V(mul), V(gru_z), V(gru_h), int(split), C.byref(view_of(out)), _stream(out))
     lib.check(rc)
     return out

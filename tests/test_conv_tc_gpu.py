@@ -41,7 +41,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + [(256, 576, 1, 16, 20, 1, 0)])
 def test_conv2d_tc(case):
     cin, cout, k, H, W, n, act1 = case
     x = rnd(n, cin, H, W, seed=1)
@@ -90,3 +90,61 @@ def test_conv2d_tc_channel_slice_views():
     got = K.nchw(K.conv2d_tc(buf_nhwc, w, b, in_view=K.view_of(buf_nhwc, channels=64, offset=128)))
     ref = F.conv2d(K.tf32_trunc(buf[:, 128:192]).double(), K.tf32_rn(w).double(), b.double(), padding=1).float()
     assert (got - ref).abs().max().item() <= 5e-5 + 2.0 ** -11 * ref.abs().max().item()
+
+
+SPLIT_CASES = [
+    # cin, cout, kh, kw, H, W, n, act1
+    (64, 64, 3, 3, 16, 32, 1, 0),
+    (384, 128, 1, 5, 16, 20, 2, 4),     # SepConvGRU horizontal gate (sigmoid)
+    (384, 128, 5, 1, 16, 20, 2, 5),     # vertical, tanh
+    (324, 256, 1, 1, 16, 20, 2, 1),     # lookup features -> 256
+    (256, 126, 3, 3, 16, 20, 1, 1),     # cout 126
+    (2, 128, 7, 7, 16, 20, 2, 1),       # flow encoder: cin 2 (ld 4)
+    (256, 576, 1, 1, 16, 20, 1, 0),     # mask head: cout 576 -> 3 N tiles of 192
+    (256, 2, 3, 3, 16, 20, 2, 0),       # flow head: cout 2
+    (128, 256, 3, 3, 24, 40, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES)
+def test_conv2d_tc_3xtf32(case):
+    """3xTF32 operand splitting: fp32-class accuracy (vs an fp64 convolution of the UNROUNDED operands)."""
+    cin, cout, kh, kw, H, W, n, act1 = case
+    x = rnd(n, cin, H, W, seed=1)
+    w = rnd(cout, cin, kh, kw, seed=2, scale=1.0 / (cin * kh * kw) ** 0.5)
+    b = rnd(cout, seed=3, scale=0.1)
+    xn = K.nhwc(x)
+    if cin % 4:
+        pad = torch.full((n, H, W, (cin + 3) // 4 * 4), 7.0, device=DEV)
+        pad[..., :cin] = xn
+        got = K.nchw(K.conv2d_tc(pad, w, b, act1, in_view=K.view_of(pad, channels=cin), split=True))
+    else:
+        got = K.nchw(K.conv2d_tc(xn, w, b, act1, split=True))
+    f = {0: lambda v: v, 1: F.relu, 4: torch.sigmoid, 5: torch.tanh}[act1]
+    ref = f(F.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))).float()
+    err = (got - ref).abs().max().item()
+    print("split case", case, "err %.3e ref absmax %.3e" % (err, ref.abs().max().item()))
+    assert err <= 1e-5
+
+
+def test_conv2d_tc_gru_epilogues():
+    """r-gate: sigmoid(conv) * h;  q-gate: h' = (1-z) h + z tanh(conv(cat[r*h, x]))  (raft/update.py:52-59)."""
+    n, H, W = 2, 16, 20
+    hx = rnd(n, 384, H, W, seed=1)
+    wr = rnd(128, 384, 1, 5, seed=2, scale=0.03)
+    wq = rnd(128, 384, 1, 5, seed=3, scale=0.03)
+    br, bq = rnd(128, seed=4, scale=0.1), rnd(128, seed=5, scale=0.1)
+    z = torch.sigmoid(rnd(n, 128, H, W, seed=6))
+    hxn = K.nhwc(hx)
+    h_view = K.view_of(hxn, channels=128)
+    # r * h
+    hbuf = K.nhwc(hx[:, :128])
+    rh = K.conv2d_tc(hxn, wr, br, 4, mul=hbuf, split=True)
+    rh_ref = torch.sigmoid(F.conv2d(hx.double(), wr.double(), br.double(), padding=(0, 2))).float() * hx[:, :128]
+    assert (K.nchw(rh) - rh_ref).abs().max().item() <= 1e-5
+    # q with two input segments and the GRU blend
+    xin = K.nhwc(hx[:, 128:])
+    got = K.conv2d_tc(rh, wq, bq, 5, x1_nhwc=xin, gru_z=K.nhwc(z), gru_h=hbuf, split=True)
+    q = torch.tanh(F.conv2d(torch.cat([rh_ref, hx[:, 128:]], 1).double(), wq.double(), bq.double(), padding=(0, 2))).float()
+    ref = (1 - z) * hx[:, :128] + z * q
+    assert (K.nchw(got) - ref).abs().max().item() <= 2e-5
