@@ -17,7 +17,7 @@
 //   SPLIT=false  plain TF32 operands (the tensor core ignores the low 13 mantissa bits of A;
 //                weights are rounded RN at pack time; outputs are stored TF32-rounded so the
 //                next layer's truncation is exact).  Used after RAFT (DESIGN.md precision plan).
-//   SPLIT=true   "3xTF32": D += A*Bhi + A*Blo + Alo*Bhi with Alo = a - trunc_tf32(a) computed
+//   SPLIT=true   "3xTF32": D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with Ahi = rn_tf32(a), Alo = rn_tf32(a - Ahi) computed
 //                in shared memory by the splitter warps and Bhi/Blo pre-split at pack time:
 //                ~2^-21 relative error, i.e. fp32-class accuracy at 3 MMAs per K step.  Used
 //                for the RAFT recurrence, which amplifies operand rounding.
@@ -46,6 +46,7 @@ struct Params {
   int cout;
   int round_out;                   // store TF32-rounded (RN) values
   int spin_limit;                  // mbarrier try_wait attempts before trapping (0 = wait forever)
+  float out_scale;                 // accumulator scale applied before the bias (all-pairs correlation: 1/sqrt(C))
   const float* bias;               // padded to tiles_n * BN
   int act1; const float* slope1;
   int act2; const float* slope2;
@@ -139,6 +140,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+
+__device__ __forceinline__ float rn_tf32(float x) {  // round-to-nearest-even to 10 mantissa bits
+  uint32_t u = __float_as_uint(x);
+  u += 0xfffu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xffffe000u);
 }
 
 // Rare activations (sigmoid / tanh / sin) go through ONE out-of-line copy: inlining the accurate sinf/tanhf/expf
@@ -310,8 +317,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cbase + j);
-          float o[4] = {__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y, __uint_as_float(v[j + 2]) + b4.z,
-                        __uint_as_float(v[j + 3]) + b4.w};
+          float o[4] = {__uint_as_float(v[j]) * p.out_scale + b4.x, __uint_as_float(v[j + 1]) * p.out_scale + b4.y,
+                        __uint_as_float(v[j + 2]) * p.out_scale + b4.z, __uint_as_float(v[j + 3]) * p.out_scale + b4.w};
           act4(o, p.act1, p.slope1, cbase + j, p.cout);
           *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
@@ -373,23 +380,26 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (SPLIT) {
     // ===================================================== operand splitter (warps 6..9)
-    // A_lo = a - trunc_tf32(a), written at the same (swizzled) offsets as A so one descriptor shape serves both.
+    // A is rewritten in place as A_hi = rn_tf32(a) and A_lo = rn_tf32(a - A_hi) goes to the second buffer at the
+    // same (swizzled) offsets, so one descriptor shape serves both.  Round-to-nearest on both terms keeps the
+    // split unbiased (truncation left a coherent ~2^-20 relative error per product, i.e. ~1e-6*sqrt(K)).
     const int t = threadIdx.x - 192;  // 0..127
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase, SPIN);
-        const float4* a = reinterpret_cast<const float4*>(smem + stage * stage_bytes);
+        float4* a = reinterpret_cast<float4*>(smem + stage * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + stage * stage_bytes + A_BYTES);
 #pragma unroll
         for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
           const float4 v = a[t + i * 128];
-          float4 l;
-          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          lo[t + i * 128] = l;
+          float4 hh, ll;
+          hh.x = rn_tf32(v.x); ll.x = rn_tf32(v.x - hh.x);
+          hh.y = rn_tf32(v.y); ll.y = rn_tf32(v.y - hh.y);
+          hh.z = rn_tf32(v.z); ll.z = rn_tf32(v.z - hh.z);
+          hh.w = rn_tf32(v.w); ll.w = rn_tf32(v.w - hh.w);
+          a[t + i * 128] = hh;
+          lo[t + i * 128] = ll;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
@@ -472,6 +482,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.tiles_x = (out.w + TILE_W - 1) / TILE_W; p.tiles_y = (out.h + TILE_H - 1) / TILE_H; p.n_img = out.n; p.tiles_n = tiles_n;
   p.H = out.h; p.W = out.w; p.BN = BN; p.cout = w.cout;
   p.round_out = split ? 0 : 1;
+  p.out_scale = 1.f;
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin;
@@ -501,6 +512,51 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   if (split) conv2d_tc_kernel<true><<<grid, 320, smem, cx.stream>>>(mA0, mA1, mB, p);
   else conv2d_tc_kernel<false><<<grid, 192, smem, cx.stream>>>(mA0, mA1, mB, p);
   gv_check_launch("conv2d_tc");
+  if (cx.prof) cx.prof->end(cx.stream);
+}
+
+
+// All-pairs correlation vol[i][j] = scale * <fa[i,:], fb[j,:]> (raft/corr.py:167-175) as a 3xTF32 GEMM on the
+// same kernel: A = fa pixels (M), "weights" = the other frame's features, K-major as they lie in NHWC memory.
+// fb_planes = [2][N][C]: plane 0 = rn_tf32(x), plane 1 = rn_tf32(x - plane 0)  (split_planes in corr.cu).
+void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale) {
+  using namespace tc;
+  if (fa.n != 1) throw std::runtime_error("corr_volume_tc: one sample per launch");
+  const int N = fa.h * fa.w, C = fa.c;
+  CUtensorMap mA, mB;
+  encode_act(&mA, fa);
+  const int BN = 256, tiles_n = (N + BN - 1) / BN;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, 2};
+    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
+    cuuint32_t box[3] = {BK, (cuuint32_t)BN, 1};
+    encode(&mB, fb_planes, 3, dims, str, box);
+  }
+  Params p;
+  p.taps = 1; p.kw = 1; p.ph = 0; p.pw = 0;
+  p.kblocks = C / 32; p.c0_blocks = p.kblocks;
+  p.tiles_x = (fa.w + TILE_W - 1) / TILE_W; p.tiles_y = (fa.h + TILE_H - 1) / TILE_H; p.n_img = 1; p.tiles_n = tiles_n;
+  p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale;
+  static int spin = -1;
+  if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
+  p.spin_limit = spin;
+  p.bias = zero_bias; p.act1 = ACT_NONE; p.slope1 = nullptr; p.act2 = ACT_NONE; p.slope2 = nullptr;
+  p.out = make_tv(vol, 1, fa.h, fa.w, N, N);
+  const int stage_bytes = 2 * (A_BYTES + BN * BK * 4);
+  p.stages = (227 * 1024 - 1024 - STG_BYTES - BAR_BYTES) / stage_bytes;
+  const int smem = p.stages * stage_bytes + STG_BYTES + BAR_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t er = cudaFuncSetAttribute(conv2d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (er != cudaSuccess) throw std::runtime_error(std::string("corr_volume_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
+    attr_set = true;
+  }
+  const int num_tiles = p.tiles_y * p.tiles_x * tiles_n;
+  const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
+  cx.launches++;
+  if (cx.prof) cx.prof->begin(cx.stream, "corr_gemm_tc_3xtf32", 2.0 * (double)N * N * C);
+  conv2d_tc_kernel<true><<<grid, 320, smem, cx.stream>>>(mA, mA, mB, p);
+  gv_check_launch("corr_volume_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }
 

@@ -90,6 +90,27 @@ void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale) {
 #endif
 }
 
+// [2][pixels][c] planes for the 3xTF32 correlation GEMM: rn_tf32(x) and rn_tf32(x - rn_tf32(x))
+struct SplitPlanesK {
+  TV src; float* planes; int64_t plane;
+  GV_HD float rn(float x) const {  // round-to-nearest-even to TF32
+    uint32_t u; memcpy(&u, &x, 4);
+    u += 0xfffu + ((u >> 13) & 1u); u &= 0xffffe000u;
+    float y; memcpy(&y, &u, 4); return y;
+  }
+  GV_HD void operator()(int64_t i) const {
+    int c = (int)(i % src.c); int64_t px = i / src.c;
+    int x = (int)(px % src.w); int64_t r = px / src.w; int y = (int)(r % src.h); int n = (int)(r / src.h);
+    float v = src.p[src.off(n, y, x) + c];
+    float hi = rn(v);
+    planes[i] = hi; planes[plane + i] = rn(v - hi);
+  }
+};
+void split_planes(Ctx& cx, const TV& src, float* planes) {
+  int64_t n = src.pixels() * src.c;
+  parallel_for(cx, n, SplitPlanesK{src, planes, n}, "split_planes");
+}
+
 // ------------------------------------------------------------------- pool
 // F.avg_pool2d(corr, 2, stride=2) over the trailing (h, w) image of every row (raft/corr.py:139-142).
 struct CorrPoolK {

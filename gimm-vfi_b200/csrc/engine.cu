@@ -392,13 +392,34 @@ struct Pyramid {
 // Volumes for both directions stacked on the batch axis: samples [0,B) hold
 // <F[s], F[s+B]>, samples [B,2B) hold <F[s], F[s-B]> (= the transposed volume,
 // raft/corr.py:32).  Level l is (2B*N) x (h_l*w_l).
-static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B) {
+static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, bool tensor_cores) {
   Arena& A = cx.arena;
   Pyramid P; P.N = (int64_t)F.h * F.w;
   int h = F.h, w = F.w;
   for (int l = 0; l < 4; ++l) { P.h[l] = h; P.w[l] = w; P.lvl[l] = A.alloc_f((size_t)2 * B * P.N * h * w); h /= 2; w /= 2; }
-  corr_volume(cx, F.batch(0, B), F.batch(B, B), P.lvl[0], 1.0f / std::sqrt((float)F.c));
-  corr_volume(cx, F.batch(B, B), F.batch(0, B), P.lvl[0] + (int64_t)B * P.N * P.N, 1.0f / std::sqrt((float)F.c));
+  const float scale = 1.0f / std::sqrt((float)F.c);
+#ifndef GV_HOSTSIM
+  if (tensor_cores && F.c % 32 == 0 && F.ld % 4 == 0) {
+    // 3xTF32 tcgen05 GEMM; the other frame's features act as the K-major "weights"
+    const size_t mk = A.mark();
+    const int64_t plane = (int64_t)P.N * F.c;
+    float* planes = A.alloc_f((size_t)2 * plane);
+    const int64_t nz = ((P.N + 255) / 256) * 256 + 256;
+    float* zeros = A.alloc_f((size_t)nz);
+    if (!cx.dry) dev_memset(zeros, 0, (size_t)nz * sizeof(float), cx.stream);
+    for (int s = 0; s < 2 * B; ++s) {
+      const int other = s < B ? s + B : s - B;
+      split_planes(cx, F.batch(other, 1), planes);
+      if (!cx.dry) corr_volume_tc(cx, F.batch(s, 1), planes, zeros, P.lvl[0] + (int64_t)s * P.N * P.N, scale);
+    }
+    A.release(mk);
+  } else
+#endif
+  {
+    (void)tensor_cores;
+    corr_volume(cx, F.batch(0, B), F.batch(B, B), P.lvl[0], scale);
+    corr_volume(cx, F.batch(B, B), F.batch(0, B), P.lvl[0] + (int64_t)B * P.N * P.N, scale);
+  }
   for (int l = 1; l < 4; ++l) corr_pool(cx, P.lvl[l - 1], P.lvl[l], (int64_t)2 * B * P.N, P.h[l - 1], P.w[l - 1]);
   return P;
 }
@@ -531,7 +552,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     N.conv("amt_second_last_cproj", c4, feat4);
     N.conv("amt_last_cproj", c8, feat8);
 
-    Pyramid pyr = build_pyramid(cx, fmap, B);
+    Pyramid pyr = build_pyramid(cx, fmap, B, tc_mode_ >= 2);
     const std::string u = "flow_estimator.update_block";
     TV coords1 = A.tensor(2 * B, h, w, 2);
     TV flow = A.tensor(2 * B, h, w, 2, 4);   // ld 4: 16-byte pixel stride so the 7x7 2->128 conv can use TMA
@@ -586,7 +607,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   // ------------------------------------------------------------ bidirectional volume on projected features
   TV fproj = A.tensor(2 * B, h, w, 256);
   N.conv("amt_fproj", fmap, fproj);
-  Pyramid bpyr = build_pyramid(cx, fproj, B);   // gimmvfi_r.py:133, raft/corr.py:23-44
+  Pyramid bpyr = build_pyramid(cx, fproj, B, tc_mode_ >= 2);   // gimmvfi_r.py:133, raft/corr.py:23-44
 
   // ------------------------------------------------------------ hoisted (t-independent) decoder feature upsampling
   TV fup4 = A.tensor(2 * B, H4, W4, 128);   // NewInitDecoder.upsample   fi_components.py:234-244

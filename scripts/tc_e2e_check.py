@@ -52,6 +52,8 @@ for tc in (0, 1, 2):
         xs, out = run(1, H, W, seed=100)
     dt = (time.perf_counter() - t0) / 3
     outs[tc] = out["imgt_pred"][0].clone()
+    outs[("raft", tc)] = out["raft_flow"].clone()
+    outs[("flowt", tc)] = out["flowt"][0].clone()
     eng.set_profile(True)
     run(1, H, W, seed=100)
     prof = eng.profile()
@@ -66,3 +68,5 @@ for tc in (0, 1, 2):
 for m in (1, 2):
     d = (outs[m] - outs[0]).abs()
     print("1080p tc mode %d vs fp32 imgt_pred: max %.3e mean %.3e p99.99 %.3e" % (m, d.max(), d.mean(), torch.quantile(d.flatten()[::7], 0.9999)))
+    r = (outs[("raft", m)] - outs[("raft", 0)]).abs(); f = (outs[("flowt", m)] - outs[("flowt", 0)]).abs()
+    print("      raft_flow max %.3e mean %.3e | flowt max %.3e mean %.3e p99.99 %.3e" % (r.max(), r.mean(), f.max(), f.mean(), torch.quantile(f.flatten()[::3], 0.9999)))
