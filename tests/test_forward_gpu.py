@@ -27,7 +27,7 @@ def model(request, weights0):
     """Both precisions: the default (post-RAFT convs on tcgen05 TF32, RAFT fp32) and fp32 everywhere."""
     m = GIMMVFI_R(seed=0).to(DEV).eval()
     m.load_state_dict(weights0, strict=True)
-    m.tensor_cores = request.param == "tf32_tensor_cores"
+    m.tensor_cores = 1 if request.param == "tf32_tensor_cores" else 0
     return m
 
 
