@@ -35,6 +35,7 @@ constexpr int A_BYTES = BM * BK * 4;                // 16 KB
 constexpr int STG_PITCH = 36;                       // floats per staged row (32 + 4: keeps float4 alignment)
 constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;   // 4 epilogue warps x 32 rows
 constexpr int BAR_BYTES = 512;
+constexpr int SEG_KSTEPS = 4;                       // SPLIT: K steps accumulated in TMEM before promotion to registers
 
 struct Params {
   int taps, kw, ph, pw;
@@ -264,10 +265,18 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, SPIN);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      // plain: one TMEM accumulator per tile.  SPLIT: the K loop is cut into segments of SEG_KSTEPS; every segment
+      // starts a fresh accumulator (alternating buffers) that the epilogue warps drain into fp32 registers.
+      // The tensor core's accumulator add truncates; short chains + a true fp32 sum across segments keep the
+      // result at CUDA-core fp32 accuracy (measured: whole-K chains were ~10x worse).
       for (int ks = 0; ks < ksteps; ++ks) {
+        const bool seg_start = SPLIT ? (ks % SEG_KSTEPS == 0) : (ks == 0);
+        const bool seg_end = SPLIT ? (ks % SEG_KSTEPS == SEG_KSTEPS - 1 || ks == ksteps - 1) : (ks == ksteps - 1);
+        if (seg_start) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1, SPIN);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
         mbar_wait(SPLIT ? &xf_bar[stage] : &full_bar[stage], phase, SPIN);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -279,19 +288,21 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 B -> +2 in the (addr >> 4) field
             const uint64_t ko = (uint64_t)(k * 2);
-            mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, (ks > 0 || k > 0) ? 1u : 0u);
-            if (SPLIT) {
-              mma_tf32(d_tmem, adesc + ko, blo + ko, idesc, 1u);   // A_hi * B_lo
-              mma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, 1u);   // A_lo * B_hi
+            if (SPLIT) {   // small terms first
+              mma_tf32(d_tmem, adesc + ko, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);   // A_hi * B_lo
+              mma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
+              mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, 1u);                               // A_hi * B_hi
+            } else {
+              mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
             }
           }
-          mma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs retire
-          if (ks == ksteps - 1) mma_commit(&tfull_bar[acc]);   // accumulator complete
+          mma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+          if (seg_end) mma_commit(&tfull_bar[acc]);      // accumulator (segment) complete
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (seg_end) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp < 6) {
     // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
@@ -304,15 +315,49 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n; int r = tile / p.tiles_n;
       const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
-      mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float racc[SPLIT ? 128 : 1];   // SPLIT: fp32 register accumulators (BN <= 128), summed across K segments
+      if (SPLIT) {
+#pragma unroll
+        for (int i = 0; i < (SPLIT ? 128 : 1); ++i) racc[i] = 0.f;
+        const int nseg = (ksteps + SEG_KSTEPS - 1) / SEG_KSTEPS;
+        for (int sg = 0; sg < nseg; ++sg) {
+          mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            if (ch * 32 < p.BN) {
+              uint32_t t[32];
+              tmem_ld32(ta + (uint32_t)(ch * 32), t);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < 32; ++j) racc[(SPLIT ? ch * 32 : 0) + (SPLIT ? j : 0)] += __uint_as_float(t[j]);
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+#pragma unroll
+      for (int chq = 0; chq < (SPLIT ? 4 : 8); ++chq) {
+        const int c0 = chq * 32;
+        if (c0 >= p.BN) break;
         const int cbase = nt * p.BN + c0;
         if (cbase >= p.cout) break;   // warp-uniform
         uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (SPLIT) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(racc[(SPLIT ? chq * 32 : 0) + (SPLIT ? j : 0)]);
+        } else {
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to tiles_n*BN on the host.
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -373,10 +418,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         __syncwarp();
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (!SPLIT) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   } else if (SPLIT) {
     // ===================================================== operand splitter (warps 6..9)
@@ -466,8 +513,14 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   encode_act(&mA0, in0);
   if (in1.p) encode_act(&mA1, in1); else mA1 = mA0;
   int BN, tiles_n;
-  tc_tile_n(w.cout, &BN, &tiles_n);
-  if (BN * tiles_n != w.cout_pad) throw std::runtime_error("conv_tc: weight padding does not match the N tiling");
+  if (split) {  // register-promoted accumulation holds BN fp32 accumulators per thread -> BN <= 128
+    const int c16 = (w.cout + 15) & ~15;
+    tiles_n = (c16 + 127) / 128;
+    BN = (((c16 + tiles_n - 1) / tiles_n) + 15) & ~15;   // weight rows beyond cout_pad are TMA zero-fill
+  } else {
+    tc_tile_n(w.cout, &BN, &tiles_n);
+    if (BN * tiles_n != w.cout_pad) throw std::runtime_error("conv_tc: weight padding does not match the N tiling");
+  }
   const int taps = w.kh * w.kw;
   {
     cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)(taps * (w.has_lo ? 2 : 1))};
@@ -525,7 +578,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   const int N = fa.h * fa.w, C = fa.c;
   CUtensorMap mA, mB;
   encode_act(&mA, fa);
-  const int BN = 256, tiles_n = (N + BN - 1) / BN;
+  const int BN = 128, tiles_n = (N + BN - 1) / BN;   // SPLIT mode: BN <= 128 (register-promoted accumulation)
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, 2};
     cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};

@@ -151,7 +151,7 @@ ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float ou
     }
   }
   const int cout_ld = (cout + 3) & ~3;
-  std::vector<float> pw((size_t)kh * kw * cin * cout_ld, 0.f), pb(tc_cout_pad(cout), 0.f);  // bias padded to the tensor-core N tiling (float4 reads)
+  std::vector<float> pw((size_t)kh * kw * cin * cout_ld, 0.f), pb(((tc_cout_pad(cout) + 31) & ~31) + 128, 0.f);  // bias padded past any tensor-core N tiling (float4 reads)
   for (int co = 0; co < cout; ++co) {
     const int src = perm ? (*perm)[co] : co;
     for (int ci = 0; ci < cin; ++ci)
@@ -259,7 +259,7 @@ void Engine::finalize_weights() {
     const HostTensor& wb = raw(key);
     const int fin = (int)wb.shape[0] - 1, fout = (int)wb.shape[1];
     const int ld = (fout + 3) & ~3;
-    std::vector<float> pw((size_t)fin * ld, 0.f), pb(tc_cout_pad(fout), 0.f);
+    std::vector<float> pw((size_t)fin * ld, 0.f), pb(((tc_cout_pad(fout) + 31) & ~31) + 128, 0.f);
     for (int co = 0; co < fout; ++co) {
       double nrm = 0.0;
       for (int ci = 0; ci < fin; ++ci) { double v = wb.data[(size_t)ci * fout + co]; nrm += v * v; }
@@ -404,7 +404,7 @@ static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, bool te
     const size_t mk = A.mark();
     const int64_t plane = (int64_t)P.N * F.c;
     float* planes = A.alloc_f((size_t)2 * plane);
-    const int64_t nz = ((P.N + 255) / 256) * 256 + 256;
+    const int64_t nz = ((P.N + 255) / 256) * 256 + 512;
     float* zeros = A.alloc_f((size_t)nz);
     if (!cx.dry) dev_memset(zeros, 0, (size_t)nz * sizeof(float), cx.stream);
     for (int s = 0; s < 2 * B; ++s) {

@@ -159,7 +159,7 @@ def conv2d_tc(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2=N
     lib = lib or default_lib()
     cout, cin, kh, kw = w.shape
     pw = pack_weight_tc(w)
-    bb = torch.zeros(tc_cout_pad(cout), device=w.device)
+    bb = torch.zeros((tc_cout_pad(cout) + 31) // 32 * 32 + 128, device=w.device)
     bb[:cout] = b
     n, h, wd, _ = x_nhwc.shape
     if out is None:
