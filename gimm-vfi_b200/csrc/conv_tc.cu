@@ -35,7 +35,6 @@ constexpr int A_BYTES = BM * BK * 4;                // 16 KB
 constexpr int STG_PITCH = 36;                       // floats per staged row (32 + 4: keeps float4 alignment)
 constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;   // 4 epilogue warps x 32 rows
 constexpr int BAR_BYTES = 512;
-constexpr int SEG_KSTEPS = 4;                       // SPLIT: K steps accumulated in TMEM before promotion to registers
 
 struct Params {
   int taps, kw, ph, pw;
@@ -47,6 +46,7 @@ struct Params {
   int cout;
   int round_out;                   // store TF32-rounded (RN) values
   int spin_limit;                  // mbarrier try_wait attempts before trapping (0 = wait forever)
+  int seg;                         // SPLIT: K steps accumulated in TMEM before promotion to fp32 registers
   float out_scale;                 // accumulator scale applied before the bias (all-pairs correlation: 1/sqrt(C))
   const float* bias;               // padded to tiles_n * BN
   int act1; const float* slope1;
@@ -265,13 +265,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      // plain: one TMEM accumulator per tile.  SPLIT: the K loop is cut into segments of SEG_KSTEPS; every segment
-      // starts a fresh accumulator (alternating buffers) that the epilogue warps drain into fp32 registers.
+      // plain: one TMEM accumulator per tile.  SPLIT: the K loop is cut into segments; every segment
+      // (p.seg K steps) starts a fresh accumulator (alternating buffers) that the epilogue warps drain into fp32 registers.
       // The tensor core's accumulator add truncates; short chains + a true fp32 sum across segments keep the
       // result at CUDA-core fp32 accuracy (measured: whole-K chains were ~10x worse).
       for (int ks = 0; ks < ksteps; ++ks) {
-        const bool seg_start = SPLIT ? (ks % SEG_KSTEPS == 0) : (ks == 0);
-        const bool seg_end = SPLIT ? (ks % SEG_KSTEPS == SEG_KSTEPS - 1 || ks == ksteps - 1) : (ks == ksteps - 1);
+        const bool seg_start = SPLIT ? (ks % p.seg == 0) : (ks == 0);
+        const bool seg_end = SPLIT ? (ks % p.seg == p.seg - 1 || ks == ksteps - 1) : (ks == ksteps - 1);
         if (seg_start) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1, SPIN);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -319,7 +319,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (SPLIT) {
 #pragma unroll
         for (int i = 0; i < (SPLIT ? 128 : 1); ++i) racc[i] = 0.f;
-        const int nseg = (ksteps + SEG_KSTEPS - 1) / SEG_KSTEPS;
+        const int nseg = (ksteps + p.seg - 1) / p.seg;
         for (int sg = 0; sg < nseg; ++sg) {
           mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -344,7 +344,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-#pragma unroll
+#pragma unroll (SPLIT ? 4 : 1)
       for (int chq = 0; chq < (SPLIT ? 4 : 8); ++chq) {
         const int c0 = chq * 32;
         if (c0 >= p.BN) break;
@@ -495,6 +495,12 @@ static void encode_act(CUtensorMap* m, const TV& t) {
 
 }  // namespace tc
 
+static int tc_seg() {
+  static int seg = -1;
+  if (seg < 0) { const char* s = getenv("GIMMVFI_TC_SEG"); seg = s ? atoi(s) : 2; if (seg < 1) seg = 1; }
+  return seg;
+}
+
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   (void)e;
@@ -536,6 +542,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.H = out.h; p.W = out.w; p.BN = BN; p.cout = w.cout;
   p.round_out = split ? 0 : 1;
   p.out_scale = 1.f;
+  p.seg = tc_seg();
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin;
@@ -589,7 +596,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   p.taps = 1; p.kw = 1; p.ph = 0; p.pw = 0;
   p.kblocks = C / 32; p.c0_blocks = p.kblocks;
   p.tiles_x = (fa.w + TILE_W - 1) / TILE_W; p.tiles_y = (fa.h + TILE_H - 1) / TILE_H; p.n_img = 1; p.tiles_n = tiles_n;
-  p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale;
+  p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale; p.seg = tc_seg();
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin;
