@@ -62,9 +62,10 @@ class GIMMVFI_R(nn.Module):
         self._weights_dirty = True
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_weights_dirty", True))
         self.aux_outputs = True  # False: skip the auxiliary outputs (only imgt_pred is produced)
-        # 0/False: fp32 CUDA cores everywhere; 1/True: post-RAFT convolutions on tcgen05 TF32 (RAFT on CUDA cores);
-        # 2: additionally RAFT on tcgen05 with 3xTF32 operand splitting (fp32-class accuracy)
-        self.tensor_cores = 1
+        # 0: fp32 CUDA cores everywhere; 1: post-RAFT convolutions on tcgen05 TF32 (RAFT on CUDA cores);
+        # 2 (default): additionally RAFT + correlation on tcgen05 with 3xTF32 operand splitting and register-promoted
+        # accumulation (fp32-class accuracy).  All three meet max|d imgt_pred| <= 1e-3 vs the reference.
+        self.tensor_cores = 2
 
     def _container(self, key: str):
         parts = key.split(".")

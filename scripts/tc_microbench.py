@@ -26,10 +26,10 @@ for cin, cout, k, H, W, n in shapes:
     from gimmvfi_b200._lib import default_lib, view_of
     lib = default_lib()
     out = torch.empty(n, H, W, cout, device=dev)
-    bb = torch.zeros((cout + 15) // 16 * 16, device=dev); bb[:cout] = b
+    bb = torch.zeros((cout + 31) // 32 * 32 + 256, device=dev); bb[:cout] = b
     s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     def call():
-        lib.check(lib.dll.gimmvfi_op_conv2d_tc(C.byref(view_of(x)), None, C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()), cin, cout, k, k, 0, None, None, 0, None, C.byref(view_of(out)), s))
+        lib.check(lib.dll.gimmvfi_op_conv2d_tc(C.byref(view_of(x)), None, C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()), cin, cout, k, k, 0, None, None, 0, None, None, None, None, 0, C.byref(view_of(out)), s))
     call(); torch.cuda.synchronize()
     e0.record()
     for _ in range(5):
