@@ -1,4 +1,6 @@
-"""GPU micro-benchmark of the tcgen05 conv kernel on the dominant layer shapes (CUDA events)."""
+"""GPU micro-benchmark of the tcgen05 conv kernel on the dominant layer shapes (CUDA events).
+usage: tc_microbench.py [plain|split|all] [max_shapes]"""
+import ctypes as C
 import os
 import sys
 
@@ -8,34 +10,36 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 
 import gpu_ops as K
+from gimmvfi_b200._lib import default_lib, view_of
 
 dev = "cuda"
-shapes = [(256, 256, 3, 1088, 1920, 1), (128, 128, 1, 1088, 1920, 1), (32, 32, 3, 1088, 1920, 2), (64, 64, 3, 1088, 1920, 1), (128, 128, 3, 272, 480, 1)]
-if len(sys.argv) > 1:
-    shapes = shapes[: int(sys.argv[1])]
-for cin, cout, k, H, W, n in shapes:
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+limit = int(sys.argv[2]) if len(sys.argv) > 2 else 99
+PLAIN = [(256, 256, 3, 3, 1088, 1920, 1), (128, 128, 1, 1, 1088, 1920, 1), (32, 32, 3, 3, 1088, 1920, 2), (64, 64, 3, 3, 1088, 1920, 1)]
+SPLIT = [(384, 128, 1, 5, 136, 240, 2), (256, 192, 3, 3, 136, 240, 2), (64, 64, 3, 3, 544, 960, 2), (324, 256, 1, 1, 136, 240, 2)]
+jobs = ([(s, False) for s in PLAIN] if which in ("plain", "all") else []) + ([(s, True) for s in SPLIT] if which in ("split", "all") else [])
+lib = default_lib()
+for (cin, cout, kh, kw, H, W, n), split in jobs[:limit]:
     x = torch.randn(n, H, W, cin, device=dev)
-    w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
-    b = torch.randn(cout, device=dev)
-    for _ in range(2):
-        K.conv2d_tc(x, w, b)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # weights are re-packed by the helper each call: time only the kernel by pre-packing
+    w = torch.randn(cout, cin, kh, kw, device=dev) / (cin * kh * kw) ** 0.5
     pw = K.pack_weight_tc(w)
-    import ctypes as C
-    from gimmvfi_b200._lib import default_lib, view_of
-    lib = default_lib()
     out = torch.empty(n, H, W, cout, device=dev)
-    bb = torch.zeros((cout + 31) // 32 * 32 + 256, device=dev); bb[:cout] = b
+    bb = torch.zeros((cout + 31) // 32 * 32 + 256, device=dev)
     s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
     def call():
-        lib.check(lib.dll.gimmvfi_op_conv2d_tc(C.byref(view_of(x)), None, C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()), cin, cout, k, k, 0, None, None, 0, None, None, None, None, 0, C.byref(view_of(out)), s))
-    call(); torch.cuda.synchronize()
-    e0.record()
-    for _ in range(5):
+        lib.check(lib.dll.gimmvfi_op_conv2d_tc(C.byref(view_of(x)), None, C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()), cin, cout, kh, kw,
+                                               0, None, None, 0, None, None, None, None, int(split), C.byref(view_of(out)), s))
+
+    for _ in range(3):
         call()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    fl = 2.0 * n * H * W * cout * cin * k * k
-    byt = 4.0 * n * H * W * (cin + cout)
-    print("conv_tc c%d>%d k%d @%dx%dx%d: %.3f ms  %.1f TFLOP/s  %.0f GB/s(algorithmic act bytes)" % (cin, cout, k, n, H, W, ms, fl / ms / 1e9, byt / ms / 1e6), flush=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    fl = 2.0 * n * H * W * cout * cin * kh * kw
+    print("conv_tc%s c%d>%d k%dx%d @%dx%dx%d: %.3f ms  %.1f TFLOP/s" % (" 3xTF32" if split else "", cin, cout, kh, kw, n, H, W, ms, fl / ms / 1e9), flush=True)
