@@ -205,7 +205,7 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1 /*optional 2nd channel segment
 // conv_tc.cu (sm_100a tcgen05 / TMA path; not part of the host simulation)
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
-void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale);
+void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split);
 // corr.cu
 void split_planes(Ctx& cx, const TV& src, float* planes);  // [2][n*h*w][c]: rn_tf32(x) and rn_tf32(x - rn_tf32(x))
 void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale);   // vol[n][i][j] = <fa[n,i], fb[n,j]> * scale

@@ -579,15 +579,17 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
 // All-pairs correlation vol[i][j] = scale * <fa[i,:], fb[j,:]> (raft/corr.py:167-175) as a 3xTF32 GEMM on the
 // same kernel: A = fa pixels (M), "weights" = the other frame's features, K-major as they lie in NHWC memory.
 // fb_planes = [2][N][C]: plane 0 = rn_tf32(x), plane 1 = rn_tf32(x - plane 0)  (split_planes in corr.cu).
-void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale) {
+void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split) {
   using namespace tc;
   if (fa.n != 1) throw std::runtime_error("corr_volume_tc: one sample per launch");
   const int N = fa.h * fa.w, C = fa.c;
   CUtensorMap mA, mB;
   encode_act(&mA, fa);
-  const int BN = 128, tiles_n = (N + BN - 1) / BN;   // SPLIT mode: BN <= 128 (register-promoted accumulation)
+  // split: BN <= 128 (register-promoted accumulation), fb_planes = [2][N][C].  plain TF32: BN = 256, fb_planes = the
+  // raw K-major features [N][C] of the other frame (the tensor core truncates them).
+  const int BN = split ? 128 : 256, tiles_n = (N + BN - 1) / BN;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, 2};
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)(split ? 2 : 1)};
     cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
     cuuint32_t box[3] = {BK, (cuuint32_t)BN, 1};
     encode(&mB, fb_planes, 3, dims, str, box);
@@ -602,20 +604,23 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   p.spin_limit = spin;
   p.bias = zero_bias; p.act1 = ACT_NONE; p.slope1 = nullptr; p.act2 = ACT_NONE; p.slope2 = nullptr;
   p.out = make_tv(vol, 1, fa.h, fa.w, N, N);
-  const int stage_bytes = 2 * (A_BYTES + BN * BK * 4);
+  const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
   p.stages = (227 * 1024 - 1024 - STG_BYTES - BAR_BYTES) / stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int smem = p.stages * stage_bytes + STG_BYTES + BAR_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t er = cudaFuncSetAttribute(conv2d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (er == cudaSuccess) er = cudaFuncSetAttribute(conv2d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (er != cudaSuccess) throw std::runtime_error(std::string("corr_volume_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
     attr_set = true;
   }
   const int num_tiles = p.tiles_y * p.tiles_x * tiles_n;
   const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
   cx.launches++;
-  if (cx.prof) cx.prof->begin(cx.stream, "corr_gemm_tc_3xtf32", 2.0 * (double)N * N * C);
-  conv2d_tc_kernel<true><<<grid, 320, smem, cx.stream>>>(mA, mA, mB, p);
+  if (cx.prof) cx.prof->begin(cx.stream, split ? "corr_gemm_tc_3xtf32" : "corr_gemm_tc_tf32", 2.0 * (double)N * N * C);
+  if (split) conv2d_tc_kernel<true><<<grid, 320, smem, cx.stream>>>(mA, mA, mB, p);
+  else conv2d_tc_kernel<false><<<grid, 192, smem, cx.stream>>>(mA, mA, mB, p);
   gv_check_launch("corr_volume_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }

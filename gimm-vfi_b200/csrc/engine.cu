@@ -392,15 +392,17 @@ struct Pyramid {
 // Volumes for both directions stacked on the batch axis: samples [0,B) hold
 // <F[s], F[s+B]>, samples [B,2B) hold <F[s], F[s-B]> (= the transposed volume,
 // raft/corr.py:32).  Level l is (2B*N) x (h_l*w_l).
-static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, bool tensor_cores) {
+// tc: 0 = fp32 CUDA-core GEMM, 1 = tcgen05 plain TF32, 2 = tcgen05 3xTF32 (promoted accumulation)
+static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, int tensor_cores) {
   Arena& A = cx.arena;
   Pyramid P; P.N = (int64_t)F.h * F.w;
   int h = F.h, w = F.w;
   for (int l = 0; l < 4; ++l) { P.h[l] = h; P.w[l] = w; P.lvl[l] = A.alloc_f((size_t)2 * B * P.N * h * w); h /= 2; w /= 2; }
   const float scale = 1.0f / std::sqrt((float)F.c);
 #ifndef GV_HOSTSIM
-  if (tensor_cores && F.c % 32 == 0 && F.ld % 4 == 0) {
-    // 3xTF32 tcgen05 GEMM; the other frame's features act as the K-major "weights"
+  if (tensor_cores && F.c % 32 == 0 && F.ld % 4 == 0 && F.ld == F.c) {
+    // tcgen05 GEMM; the other frame's features act as the K-major "weights"
+    const bool split = tensor_cores >= 2;
     const size_t mk = A.mark();
     const int64_t plane = (int64_t)P.N * F.c;
     float* planes = A.alloc_f((size_t)2 * plane);
@@ -409,8 +411,8 @@ static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, bool te
     if (!cx.dry) dev_memset(zeros, 0, (size_t)nz * sizeof(float), cx.stream);
     for (int s = 0; s < 2 * B; ++s) {
       const int other = s < B ? s + B : s - B;
-      split_planes(cx, F.batch(other, 1), planes);
-      if (!cx.dry) corr_volume_tc(cx, F.batch(s, 1), planes, zeros, P.lvl[0] + (int64_t)s * P.N * P.N, scale);
+      if (split) split_planes(cx, F.batch(other, 1), planes);
+      if (!cx.dry) corr_volume_tc(cx, F.batch(s, 1), split ? planes : F.batch(other, 1).p, zeros, P.lvl[0] + (int64_t)s * P.N * P.N, scale, split);
     }
     A.release(mk);
   } else
@@ -552,7 +554,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     N.conv("amt_second_last_cproj", c4, feat4);
     N.conv("amt_last_cproj", c8, feat8);
 
-    Pyramid pyr = build_pyramid(cx, fmap, B, tc_mode_ >= 2);
+    Pyramid pyr = build_pyramid(cx, fmap, B, tc_mode_ >= 2 ? 2 : 0);   // RAFT's volume: fp32-class only
     const std::string u = "flow_estimator.update_block";
     TV coords1 = A.tensor(2 * B, h, w, 2);
     TV flow = A.tensor(2 * B, h, w, 2, 4);   // ld 4: 16-byte pixel stride so the 7x7 2->128 conv can use TMA
@@ -607,7 +609,8 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   // ------------------------------------------------------------ bidirectional volume on projected features
   TV fproj = A.tensor(2 * B, h, w, 256);
   N.conv("amt_fproj", fmap, fproj);
-  Pyramid bpyr = build_pyramid(cx, fproj, B, tc_mode_ >= 2);   // gimmvfi_r.py:133, raft/corr.py:23-44
+  // the bidirectional volume only feeds TF32 layers (AMT update blocks) -> plain TF32 is at their input precision
+  Pyramid bpyr = build_pyramid(cx, fproj, B, tc_mode_ >= 1 ? 1 : 0);   // gimmvfi_r.py:133, raft/corr.py:23-44
 
   // ------------------------------------------------------------ hoisted (t-independent) decoder feature upsampling
   TV fup4 = A.tensor(2 * B, H4, W4, 128);   // NewInitDecoder.upsample   fi_components.py:234-244
