@@ -101,6 +101,7 @@ struct ConvGeom {
   int stride = 1;
   int ph = 0, pw = 0;
   int reflect = 0;  // 0: zero padding, 1: reflect padding (padding_mode="reflect")
+  int loose_w = 0;  // skip the output-width check (x-taps packed into the channel axis, see Engine::pack_stem)
 };
 
 // ---------------------------------------------------------------------------
@@ -216,6 +217,7 @@ void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords /*n,h,w,2 (x,y)*/
 void nchw_to_nhwc(Ctx& cx, const float* src, int64_t src_sn, int64_t src_sc, const TV& dst, float scale, float shift);
 void nhwc_to_nchw(Ctx& cx, const TV& src, float* dst, int64_t dst_sn, int64_t dst_sc, float scale, float shift, int clamp01);  // (v + shift) * scale
 void copy_channels(Ctx& cx, const TV& src, const TV& dst);
+void pad_image4(Ctx& cx, const TV& src /*c=3, ld=4*/, const TV& dst /*h+2p, w+2p, ld 4*/, int pad);
 void fill(Ctx& cx, const TV& dst, float v);
 void axpby(Ctx& cx, const TV& a, float alpha, const TV& b, float beta, const TV& out);  // out = alpha*a + beta*b (b optional)
 void resize_bilinear(Ctx& cx, const TV& src, const TV& dst, float scale_y, float scale_x, float mult, int accumulate, int act);

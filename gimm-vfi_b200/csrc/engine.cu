@@ -193,6 +193,34 @@ void Engine::pack_tc(ConvW& c, const std::vector<float>& pw) {
   c.w_tc = upload(t); c.cout_pad = cout_pad; c.cin_pad = cin_pad; c.has_lo = true;
 }
 
+// RAFT stem (7x7, stride 2, cin 3) with the x-taps packed into the channel axis: on a zero-padded image with
+// 4-float pixels, the 7 x-taps of one kernel row are 28 contiguous floats, so the conv becomes a (7 x 1) kernel
+// over 28 "channels" (K = 7 x 28 instead of 49 taps x 3-of-16 used lanes: 3.5x fewer K chunks).
+void Engine::pack_stem(const std::string& name, const std::string& bn) {
+  const HostTensor& W = raw(name + ".weight");
+  const HostTensor& Bv = raw(name + ".bias");
+  const int cout = (int)W.shape[0], cin = (int)W.shape[1], kh = (int)W.shape[2], kw = (int)W.shape[3];
+  if (cin != 3 || kh != 7 || kw != 7) throw std::runtime_error("pack_stem: expected a 7x7 conv on 3 channels");
+  std::vector<float> s(cout, 1.f), sh(cout, 0.f);
+  if (!bn.empty()) {
+    const auto& g = raw(bn + ".weight").data; const auto& be = raw(bn + ".bias").data;
+    const auto& mu = raw(bn + ".running_mean").data; const auto& var = raw(bn + ".running_var").data;
+    for (int co = 0; co < cout; ++co) { float k = g[co] / std::sqrt(var[co] + 1e-5f); s[co] = k; sh[co] = be[co] - mu[co] * k; }
+  }
+  const int cout_ld = (cout + 3) & ~3, K = 28;
+  std::vector<float> pw((size_t)kh * K * cout_ld, 0.f), pb(((tc_cout_pad(cout) + 31) & ~31) + 128, 0.f);
+  for (int co = 0; co < cout; ++co) {
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx)
+        for (int c = 0; c < 3; ++c)
+          pw[((size_t)ky * K + kx * 4 + c) * cout_ld + co] = W.data[(((size_t)co * cin + c) * kh + ky) * kw + kx] * s[co];
+    pb[co] = Bv.data[co] * s[co] + sh[co];
+  }
+  ConvW c;
+  c.w = upload(pw); c.b = upload(pb); c.cin = K; c.cout = cout; c.kh = kh; c.kw = 1; c.cout_ld = cout_ld;
+  conv_[name + "#xpacked"] = c;
+}
+
 void Engine::finalize_weights() {
   for (void* p : dev_allocs_) dev_free(p);
   dev_allocs_.clear(); conv_.clear(); vec_.clear();
@@ -201,6 +229,7 @@ void Engine::finalize_weights() {
     const std::string p = e == 0 ? "flow_estimator.fnet" : "flow_estimator.cnet";
     const bool bn = e == 1;
     pack_conv(p + ".conv1", bn ? p + ".norm1" : "");
+    pack_stem(p + ".conv1", bn ? p + ".norm1" : "");
     for (int li = 1; li <= 3; ++li)
       for (int bi = 0; bi < 2; ++bi) {
         const std::string q = p + ".layer" + std::to_string(li) + "." + std::to_string(bi);
@@ -309,7 +338,8 @@ static ConvW slice_cout(const ConvW& w, int co0, int cnt) {
 }
 
 // raft/extractor.py:173-220.  x: (n,H,W,3) -> fmap (n,H/8,W/8,256) [+ layer2/layer3 outputs]
-static void raft_encoder(Net& N, const std::string& p, bool instance, const TV& x, const TV& out256, TV* feat4, TV* feat8,
+static void raft_encoder(Net& N, const std::string& p, bool instance, const TV& x, const TV& xpad /*zero-padded by 3, 4-float pixels*/,
+                         const TV& out256, TV* feat4, TV* feat8,
                          const ConvW* split_tanh_relu_out /*cnet: tanh/relu halves*/, const TV& net_out, const TV& inp_out) {
   Ctx& cx = N.cx; Arena& A = cx.arena;
   const int n = x.n, H2 = x.h / 2, W2 = x.w / 2;
@@ -325,12 +355,20 @@ static void raft_encoder(Net& N, const std::string& p, bool instance, const TV& 
   };
   // stem
   TV a = A.tensor(n, H2, W2, 64);
+  auto stem = [&](const TV& dst, int act) {   // 7x7 stride-2 stem through the x-packed weights (pack_stem)
+    TV in = xpad; in.c = 28;
+    ConvGeom g; g.stride = 2; g.ph = 0; g.pw = 0; g.loose_w = 1;
+    ConvEpi e; e.act1 = act;
+    const bool tc = cx.tc; cx.tc = false;    // stride 2: CUDA-core kernel
+    conv2d(cx, in, TV(), N.W(p + ".conv1#xpacked"), g, e, dst);
+    cx.tc = tc;
+  };
   if (instance) {
     TV r = A.tensor(n, H2, W2, 64);
-    N.conv(p + ".conv1", x, r, ACT_NONE, nullptr, 2);
+    stem(r, ACT_NONE);
     norm_act(r, ACT_RELU, TV(), ACT_NONE, a);
   } else {
-    N.conv(p + ".conv1", x, a, ACT_RELU, nullptr, 2);
+    stem(a, ACT_RELU);
   }
   TV cur = a;
   int cin = 64;
@@ -544,10 +582,12 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     TV hx = A.tensor(2 * B, h, w, 384);              // [h | inp | motion]
     TV c4, c8;
     {
-      raft_encoder(N, "flow_estimator.fnet", true, raft_in, fmap, nullptr, nullptr, nullptr, TV(), TV());
+      TV raft_pad = A.tensor(2 * B, H + 6, W + 6, 3, 4);
+      pad_image4(cx, raft_in, raft_pad, 3);
+      raft_encoder(N, "flow_estimator.fnet", true, raft_in, raft_pad, fmap, nullptr, nullptr, nullptr, TV(), TV());
       // the encoder's temporaries stay allocated until `mk` is released (bump allocator)
       const ConvW& wc = N.W("flow_estimator.cnet.conv2");
-      raft_encoder(N, "flow_estimator.cnet", false, raft_in, TV(), &c4, &c8, &wc, hx.slice(0, 128), hx.slice(128, 128));
+      raft_encoder(N, "flow_estimator.cnet", false, raft_in, raft_pad, TV(), &c4, &c8, &wc, hx.slice(0, 128), hx.slice(128, 128));
     }
     tap("raft.fmap", fmap);
     // context features for the synthesis net (gimmvfi_r.py:134-141)

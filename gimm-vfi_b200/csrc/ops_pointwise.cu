@@ -101,6 +101,21 @@ void copy_channels(Ctx& cx, const TV& src, const TV& dst) {
   parallel_for(cx, dst.pixels() * dst.c, CopyK{src, dst}, "copy_channels");
 }
 
+// zero-padded copy of a 3-channel image stored with 4-float pixels (4th lane forced to 0)
+struct PadImage4K {
+  TV src, dst; int pad;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, 4);
+    int y = q.y - pad, x = q.x - pad;
+    float v = 0.f;
+    if (q.c < 3 && y >= 0 && y < src.h && x >= 0 && x < src.w) v = src.p[src.off(q.n, y, x) + q.c];
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = v;
+  }
+};
+void pad_image4(Ctx& cx, const TV& src, const TV& dst, int pad) {
+  parallel_for(cx, dst.pixels() * 4, PadImage4K{src, dst, pad}, "pad_image4");
+}
+
 struct FillK {
   TV dst; float v;
   GV_HD void operator()(int64_t i) const {
