@@ -96,6 +96,23 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// multicast variants: the box lands at the same CTA-relative smem offset (and signals the mbarrier at the same
+// offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -188,7 +205,11 @@ __device__ __forceinline__ void load4(const float* p, int c, int cout, float* r)
   }
 }
 
-template <bool SPLIT>
+// CL = thread-block-cluster size (1 or 2).  CL == 2: the two CTAs of a cluster work on neighbouring pixel tiles
+// with the same weights; each loads HALF of every weight box and multicasts it to both, halving the weight
+// traffic out of L2 (the limiter at N = 256).  A stage may be refilled only when BOTH CTAs' MMAs retired it,
+// so the MMA commit is multicast to both CTAs' empty barriers (count 2).
+template <bool SPLIT, int CL>
 __global__ void __launch_bounds__(SPLIT ? 320 : 192, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
                  const Params p) {
@@ -209,7 +230,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.n_img * p.tiles_y * p.tiles_x * p.tiles_n;
+  // tile index -> (pixel tile, N tile): consecutive indices 2k, 2k+1 (one cluster) share the N tile (same weights)
+  // and take neighbouring pixel tiles; the pixel-tile count is padded to CL so both CTAs run the same K-step count.
+  const int pix_tiles = (p.n_img * p.tiles_y * p.tiles_x + CL - 1) / CL * CL;
+  const int num_tiles = pix_tiles * p.tiles_n;
   const int ksteps = p.taps * p.kblocks;
   const int SPIN = p.spin_limit;
 
@@ -220,7 +244,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&xf_bar[s], 4); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); mbar_init(&xf_bar[s], 4); }
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -230,16 +254,18 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // barriers initialised cluster-wide before any remote arrive
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  uint32_t cta_rank = 0;
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n; int r = tile / p.tiles_n;
+        const int nt = (tile / CL) % p.tiles_n; int r = (tile / CL) / p.tiles_n * CL + tile % CL;
         const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int ky = tap / p.kw, kx = tap % p.kw;
@@ -251,8 +277,15 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + (SPLIT ? 2 * b_bytes : b_bytes)));
             if (kb < p.c0_blocks) tma_load_4d(a_dst, &tmA0, &full_bar[stage], kb * BK, x0, y0, n);
             else tma_load_4d(a_dst, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * BK, x0, y0, n);
-            tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * BK, nt * p.BN, tap);
-            if (SPLIT) tma_load_3d(b_dst + b_bytes, &tmB, &full_bar[stage], kb * BK, nt * p.BN, tap + p.taps);
+            if (CL == 1) {
+              tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * BK, nt * p.BN, tap);
+              if (SPLIT) tma_load_3d(b_dst + b_bytes, &tmB, &full_bar[stage], kb * BK, nt * p.BN, tap + p.taps);
+            } else {  // tmB's box is BN/CL rows: my slice of the weight tile, delivered to every CTA of the cluster
+              const int rows = p.BN / CL, roff = (int)cta_rank * rows;
+              tma_load_3d_mc(b_dst + roff * 128, &tmB, &full_bar[stage], kb * BK, nt * p.BN + roff, tap, (uint16_t)((1u << CL) - 1));
+              if (SPLIT)
+                tma_load_3d_mc(b_dst + b_bytes + roff * 128, &tmB, &full_bar[stage], kb * BK, nt * p.BN + roff, tap + p.taps, (uint16_t)((1u << CL) - 1));
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -296,7 +329,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
             }
           }
-          mma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+          if (CL == 1) mma_commit(&empty_bar[stage]);    // frees the smem slot when these MMAs retire
+          else mma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // ... in every CTA that shares the weight tile
           if (seg_end) mma_commit(&tfull_bar[acc]);      // accumulator (segment) complete
         }
         __syncwarp();
@@ -313,7 +347,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q8 = lane & 7, rsub = lane >> 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n; int r = tile / p.tiles_n;
+      const int nt = (tile / CL) % p.tiles_n; int r = (tile / CL) / p.tiles_n * CL + tile % CL;
       const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
       float racc[SPLIT ? 128 : 1];   // SPLIT: fp32 register accumulators (BN <= 128), summed across K segments
       if (SPLIT) {
@@ -376,7 +410,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int it = 0; it < 8; ++it) {
             const int rr = quarter * 32 + it * 4 + rsub;
             const int y = ty * TILE_H + rr / TILE_W, x = tx * TILE_W + rr % TILE_W;
-            if (y >= p.H || x >= p.W) continue;
+            if (y >= p.H || x >= p.W || n >= p.n_img) continue;
             const float4 sv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * STG_PITCH + q8 * 4);
             float o[4] = {sv.x, sv.y, sv.z, sv.w};
             if (p.res.p) {
@@ -455,7 +489,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   }
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while its peer may still write to it
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -495,6 +529,31 @@ static void encode_act(CUtensorMap* m, const TV& t) {
 
 }  // namespace tc
 
+// launch with an optional (2,1,1) thread-block cluster
+template <bool SPLIT, int CL>
+static void launch_tc(int grid, int threads, int smem, gvStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                      const tc::Params& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t er = cudaFuncSetAttribute(tc::conv2d_tc_kernel<SPLIT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t er = cudaLaunchKernelEx(&cfg, tc::conv2d_tc_kernel<SPLIT, CL>, a0, a1, b, p);
+  if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: launch failed: ") + cudaGetErrorString(er));
+}
+
+static int tc_cluster() {   // GIMMVFI_TC_CLUSTER=1 disables the 2-CTA weight multicast
+  static int c = -1;
+  if (c < 0) { const char* s = getenv("GIMMVFI_TC_CLUSTER"); c = s ? atoi(s) : 2; if (c != 1 && c != 2) c = 2; }
+  return c;
+}
+
 static int tc_seg() {
   static int seg = -1;
   if (seg < 0) { const char* s = getenv("GIMMVFI_TC_SEG"); seg = s ? atoi(s) : 2; if (seg < 1) seg = 1; }
@@ -519,6 +578,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   encode_act(&mA0, in0);
   if (in1.p) encode_act(&mA1, in1); else mA1 = mA0;
   int BN, tiles_n;
+  const int pix_tiles_host = out.n * ((out.h + TILE_H - 1) / TILE_H) * ((out.w + TILE_W - 1) / TILE_W);
   if (split) {  // register-promoted accumulation holds BN fp32 accumulators per thread -> BN <= 128
     const int c16 = (w.cout + 15) & ~15;
     tiles_n = (c16 + 127) / 128;
@@ -527,11 +587,13 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
     tc_tile_n(w.cout, &BN, &tiles_n);
     if (BN * tiles_n != w.cout_pad) throw std::runtime_error("conv_tc: weight padding does not match the N tiling");
   }
+  // 2-CTA clusters pay off when there are at least two pixel tiles per SM; BN/2 must keep the 8-row swizzle atom
+  const int CL = (tc_cluster() == 2 && pix_tiles_host >= 2 * cx.sm_count && BN % 16 == 0) ? 2 : 1;
   const int taps = w.kh * w.kw;
   {
     cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)(taps * (w.has_lo ? 2 : 1))};
     cuuint64_t str[2] = {(cuuint64_t)w.cin_pad * 4, (cuuint64_t)w.cin_pad * w.cout_pad * 4};
-    cuuint32_t box[3] = {BK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {BK, (cuuint32_t)(BN / CL), 1};   // CL == 2: each CTA fetches half of the weight rows
     encode(&mB, w.w_tc, 3, dims, str, box);
   }
   Params p;
@@ -548,29 +610,23 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.spin_limit = spin;
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2;
   p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
-  const int num_tiles = p.n_img * p.tiles_y * p.tiles_x * tiles_n;
   const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
   const int budget = 227 * 1024 - 1024 /*align*/ - STG_BYTES - BAR_BYTES;
   p.stages = budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.stages < 2) throw std::runtime_error("conv_tc: not enough shared memory for 2 pipeline stages");
   const int smem = p.stages * stage_bytes + STG_BYTES + BAR_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(conv2d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (er == cudaSuccess) er = cudaFuncSetAttribute(conv2d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
-    attr_set = true;
-  }
-  const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
+  const int padded_tiles = (pix_tiles_host + CL - 1) / CL * CL * tiles_n;
+  int grid = padded_tiles < cx.sm_count ? padded_tiles : cx.sm_count;
+  grid -= grid % CL;
   cx.launches++;
   if (cx.prof) {
     char nm[128];
     snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? "3xtf32" : "tf32", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
   }
-  if (split) conv2d_tc_kernel<true><<<grid, 320, smem, cx.stream>>>(mA0, mA1, mB, p);
-  else conv2d_tc_kernel<false><<<grid, 192, smem, cx.stream>>>(mA0, mA1, mB, p);
+  if (split) { if (CL == 2) launch_tc<true, 2>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
+  else { if (CL == 2) launch_tc<false, 2>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<false, 1>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); }
   gv_check_launch("conv2d_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }
@@ -608,19 +664,12 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   p.stages = (227 * 1024 - 1024 - STG_BYTES - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int smem = p.stages * stage_bytes + STG_BYTES + BAR_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(conv2d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (er == cudaSuccess) er = cudaFuncSetAttribute(conv2d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (er != cudaSuccess) throw std::runtime_error(std::string("corr_volume_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
-    attr_set = true;
-  }
   const int num_tiles = p.tiles_y * p.tiles_x * tiles_n;
   const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
   cx.launches++;
   if (cx.prof) cx.prof->begin(cx.stream, split ? "corr_gemm_tc_3xtf32" : "corr_gemm_tc_tf32", 2.0 * (double)N * N * C);
-  if (split) conv2d_tc_kernel<true><<<grid, 320, smem, cx.stream>>>(mA, mA, mB, p);
-  else conv2d_tc_kernel<false><<<grid, 192, smem, cx.stream>>>(mA, mA, mB, p);
+  if (split) launch_tc<true, 1>(grid, 320, smem, cx.stream, mA, mA, mB, p);
+  else launch_tc<false, 1>(grid, 192, smem, cx.stream, mA, mA, mB, p);
   gv_check_launch("corr_volume_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }

@@ -149,3 +149,34 @@ def test_conv2d_tc_gru_epilogues():
     q = torch.tanh(F.conv2d(torch.cat([rh_ref, hx[:, 128:]], 1).double(), wq.double(), bq.double(), padding=(0, 2))).float()
     ref = (1 - z) * hx[:, :128] + z * q
     assert (K.nchw(got) - ref).abs().max().item() <= 1e-4
+
+
+CLUSTER_CASES = [
+    # >= 2 pixel tiles per SM -> the 2-CTA weight-multicast path; 168x240 = 21x15 = 315 tiles (odd: exercises padding)
+    (64, 64, 3, 3, 168, 240, 1, 0, False),
+    (256, 256, 3, 3, 168, 240, 1, 3, False),
+    (96, 192, 3, 3, 160, 256, 1, 1, False),
+    (384, 128, 1, 5, 168, 240, 1, 4, True),
+    (128, 256, 3, 3, 168, 240, 1, 1, True),     # split, 2 N tiles: both CTAs of a cluster must share the N tile
+    (64, 64, 3, 3, 160, 256, 2, 0, True),
+]
+
+
+@pytest.mark.parametrize("case", CLUSTER_CASES)
+def test_conv2d_tc_cluster_multicast(case):
+    cin, cout, kh, kw, H, W, n, act1, split = case
+    x = rnd(n, cin, H, W, seed=1)
+    w = rnd(cout, cin, kh, kw, seed=2, scale=1.0 / (cin * kh * kw) ** 0.5)
+    b = rnd(cout, seed=3, scale=0.1)
+    slope = (0.25 + 0.1 * rnd(cout, seed=4)) if act1 == 3 else None
+    got = K.nchw(K.conv2d_tc(K.nhwc(x), w, b, act1, slope, split=split))
+    f = {0: lambda v: v, 1: F.relu, 3: lambda v: F.prelu(v, slope.double()), 4: torch.sigmoid}[act1]
+    if split:
+        ref = f(F.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))).float()
+        tol = 1e-4
+    else:
+        ref = f(F.conv2d(K.tf32_trunc(x).double(), K.tf32_rn(w).double(), b.double(), padding=(kh // 2, kw // 2))).float()
+        tol = 5e-5 + 2.0 ** -11 * ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    print("cluster case", case, "err %.3e" % err)
+    assert err <= tol
