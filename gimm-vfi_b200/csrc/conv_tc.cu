@@ -166,16 +166,26 @@ __device__ __forceinline__ float rn_tf32(float x) {  // round-to-nearest-even to
   return __uint_as_float(u & 0xffffe000u);
 }
 
-// Rare activations (sigmoid / tanh / sin) go through ONE out-of-line copy: inlining the accurate sinf/tanhf/expf
-// paths at every element site made the epilogue ~25k SASS instructions (instruction-cache bound, ~10 us per
-// 32-column chunk measured).
-__device__ __noinline__ float act_slow(float v, int act) {
-  switch (act) {
-    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-    case ACT_TANH: return tanhf(v);
-    case ACT_SIN: return sinf(v);
-    default: return v;
-  }
+// Lean, branch-free fp32 activations (the libm versions drag a slow path to every call site: inlined at 64 sites
+// they made the first version of this epilogue 25k SASS instructions and instruction-cache bound).
+__device__ __forceinline__ float sin_f32(float x) {
+  // Cody-Waite reduction by pi (3 terms) + odd degree-9 minimax polynomial on [-pi/2, pi/2]; |err| < 2e-7 for |x| < 1e3
+  const float k = rintf(x * 0.318309886183790672f);
+  float r = fmaf(-k, 3.140625f, x);
+  r = fmaf(-k, 9.67502593994140625e-4f, r);
+  r = fmaf(-k, 1.509957990978376432e-7f, r);
+  const float r2 = r * r;
+  float p = fmaf(r2, 2.60831598e-6f, -1.98106907e-4f);
+  p = fmaf(p, r2, 8.33307858e-3f);
+  p = fmaf(p, r2, -1.66666597e-1f);
+  p = fmaf(p * r2, r, r);
+  return (((int)k) & 1) ? -p : p;
+}
+__device__ __forceinline__ float sigmoid_f32(float v) { return 1.f / (1.f + expf(-v)); }
+__device__ __forceinline__ float tanh_f32(float v) {
+  // 1 - 2/(exp(2v)+1): absolute error ~1e-7 (the GRU candidate lives in (-1,1)); saturates cleanly for large |v|
+  const float e = expf(2.f * v);
+  return 1.f - 2.f / (e + 1.f);
 }
 // 4 consecutive channels starting at c (c % 4 == 0)
 __device__ __forceinline__ void act4(float* o, int act, const float* slope, int c, int cout) {
@@ -189,9 +199,15 @@ __device__ __forceinline__ void act4(float* o, int act, const float* slope, int 
   } else if (act == ACT_PRELU) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) { const float sl = (c + u < cout) ? slope[c + u] : 0.f; o[u] = o[u] > 0.f ? o[u] : sl * o[u]; }
+  } else if (act == ACT_SIN) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o[u] = sin_f32(o[u]);
+  } else if (act == ACT_SIGMOID) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o[u] = sigmoid_f32(o[u]);
   } else {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = act_slow(o[u], act);
+    for (int u = 0; u < 4; ++u) o[u] = tanh_f32(o[u]);
   }
 }
 // 4 channels of an optional side tensor at (pixel, channel c): float4 when in range and 16B aligned
@@ -392,17 +408,16 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_ld32(taddr + (uint32_t)c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
-        // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to tiles_n*BN on the host.
+        // phase 1 (thread = pixel row): scale + bias, stage to smem.  bias is padded past tiles_n*BN on the host.
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cbase + j);
           float o[4] = {__uint_as_float(v[j]) * p.out_scale + b4.x, __uint_as_float(v[j + 1]) * p.out_scale + b4.y,
                         __uint_as_float(v[j + 2]) * p.out_scale + b4.z, __uint_as_float(v[j + 3]) * p.out_scale + b4.w};
-          act4(o, p.act1, p.slope1, cbase + j, p.cout);
           *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
         __syncwarp();
-        // phase 2 (8 lanes = one 128-byte row, 4 rows per instruction): + residual, act2, gate multiply,
+        // phase 2 (8 lanes = one 128-byte row, 4 rows per instruction): act1, + residual, act2, gate multiply,
         // ConvGRU blend, optional TF32 rounding, coalesced store
         const int c = cbase + q8 * 4;
         if (c < p.cout) {
@@ -413,6 +428,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (y >= p.H || x >= p.W || n >= p.n_img) continue;
             const float4 sv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * STG_PITCH + q8 * 4);
             float o[4] = {sv.x, sv.y, sv.z, sv.w};
+            act4(o, p.act1, p.slope1, c, p.cout);
             if (p.res.p) {
               float t[4]; load4(p.res.p + p.res.off(n, y, x) + c, c, p.cout, t);
 #pragma unroll
