@@ -207,7 +207,7 @@ static int in_chunks(const TV& x) {  // ~64 pixels per thread, enough threads to
   int64_t hw = (int64_t)x.h * x.w; int64_t c = hw / 64;
   return (int)(c < 1 ? 1 : (c > IN_CHUNKS_MAX ? IN_CHUNKS_MAX : c));
 }
-int64_t instnorm_scratch_floats(const TV& x) { return (int64_t)x.n * IN_CHUNKS_MAX * x.c * 4; }
+int64_t instnorm_scratch_floats(const TV& x) { return (int64_t)x.n * (IN_CHUNKS_MAX + 32) * x.c * 4; }
 
 struct InPartialK {
   TV x; double* part; int chunks;
@@ -223,12 +223,22 @@ struct InPartialK {
     part[i * 2] = s; part[i * 2 + 1] = s2;
   }
 };
+// two-level tree over the chunk partials (a single thread per (n,c) looping over 1024 chunks was latency bound)
+struct InFoldK {   // part[n][chunks][c] -> fold[n][32][c]
+  const double* part; double* fold; int c, chunks;
+  GV_HD void operator()(int64_t i) const {
+    int ch = (int)(i % c); int64_t r = i / c; int g = (int)(r % 32); int n = (int)(r / 32);
+    double s = 0.0, s2 = 0.0;
+    for (int k = g; k < chunks; k += 32) { int64_t j = ((int64_t)n * chunks + k) * c + ch; s += part[j * 2]; s2 += part[j * 2 + 1]; }
+    fold[i * 2] = s; fold[i * 2 + 1] = s2;
+  }
+};
 struct InFinalK {
-  const double* part; float* mr; int c, chunks; double inv_hw;
+  const double* fold; float* mr; int c; double inv_hw;
   GV_HD void operator()(int64_t i) const {
     int ch = (int)(i % c); int n = (int)(i / c);
     double s = 0.0, s2 = 0.0;
-    for (int k = 0; k < chunks; ++k) { int64_t j = ((int64_t)n * chunks + k) * c + ch; s += part[j * 2]; s2 += part[j * 2 + 1]; }
+    for (int g = 0; g < 32; ++g) { int64_t j = ((int64_t)n * 32 + g) * c + ch; s += fold[j * 2]; s2 += fold[j * 2 + 1]; }
     double m = s * inv_hw; double var = s2 * inv_hw - m * m; if (var < 0.0) var = 0.0;
     mr[i * 2] = (float)m; mr[i * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
   }
@@ -236,8 +246,10 @@ struct InFinalK {
 void instnorm_stats(Ctx& cx, const TV& x, float* mean_rstd, float* scratch, int64_t) {
   double* part = reinterpret_cast<double*>(scratch);
   const int chunks = in_chunks(x);
+  double* fold = part + (int64_t)x.n * IN_CHUNKS_MAX * x.c * 2;
   parallel_for(cx, (int64_t)x.n * chunks * x.c, InPartialK{x, part, chunks}, "instnorm_partial");
-  parallel_for(cx, (int64_t)x.n * x.c, InFinalK{part, mean_rstd, x.c, chunks, 1.0 / ((double)x.h * x.w)}, "instnorm_final");
+  parallel_for(cx, (int64_t)x.n * 32 * x.c, InFoldK{part, fold, x.c, chunks}, "instnorm_fold");
+  parallel_for(cx, (int64_t)x.n * x.c, InFinalK{fold, mean_rstd, x.c, 1.0 / ((double)x.h * x.w)}, "instnorm_final");
 }
 struct InApplyK {
   TV x, res, out; const float* mr; int act1, act2;
