@@ -17,7 +17,7 @@
 //   SPLIT=false  plain TF32 operands (the tensor core ignores the low 13 mantissa bits of A;
 //                weights are rounded RN at pack time; outputs are stored TF32-rounded so the
 //                next layer's truncation is exact).  Used after RAFT (DESIGN.md precision plan).
-//   SPLIT=true   "3xTF32": D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with Ahi = trunc_tf32(a) (what the MMA reads), Alo = rn_tf32(a - Ahi) computed
+//   SPLIT=true   "3xTF32": D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with Ahi = rn_tf32(a), Alo = rn_tf32(a - Ahi) computed
 //                in shared memory by the splitter warps and Bhi/Blo pre-split at pack time:
 //                ~2^-21 relative error, i.e. fp32-class accuracy at 3 MMAs per K step.  Used
 //                for the RAFT recurrence, which amplifies operand rounding.
@@ -166,10 +166,12 @@ __device__ __forceinline__ float rn_tf32(float x) {  // round-to-nearest-even to
   return __uint_as_float(u & 0xffffe000u);
 }
 
-// Lean, branch-free fp32 activations (the libm versions drag a slow path to every call site: inlined at 64 sites
-// they made the first version of this epilogue 25k SASS instructions and instruction-cache bound).
+// Rare activations (sigmoid / tanh / sin) go through ONE out-of-line copy: inlining the accurate sinf/tanhf/expf
+// paths at every element site made the epilogue ~25k SASS instructions (instruction-cache bound, ~10 us per
+// 32-column chunk measured).
 __device__ __forceinline__ float sin_f32(float x) {
   // Cody-Waite reduction by pi (3 terms) + odd degree-9 minimax polynomial on [-pi/2, pi/2]; |err| < 2e-7 for |x| < 1e3
+  // (libm's sinf carries a Payne-Hanek slow path with a local-memory table: ~3x slower as a call)
   const float k = rintf(x * 0.318309886183790672f);
   float r = fmaf(-k, 3.140625f, x);
   r = fmaf(-k, 9.67502593994140625e-4f, r);
@@ -181,24 +183,12 @@ __device__ __forceinline__ float sin_f32(float x) {
   p = fmaf(p * r2, r, r);
   return (((int)k) & 1) ? -p : p;
 }
-__device__ __forceinline__ float sigmoid_f32(float v) { return 1.f / (1.f + expf(-v)); }
-__device__ __forceinline__ float tanh_f32(float v) {
-  // 1 - 2/(exp(2v)+1): absolute error ~1e-7 (the GRU candidate lives in (-1,1)); saturates cleanly for large |v|
-  const float e = expf(2.f * v);
-  return 1.f - 2.f / (e + 1.f);
-}
-// sin / sigmoid / tanh: ONE out-of-line copy (keeps the hot epilogue loops small; inlining them at every site cost
-// ~10 % on the PReLU/identity layers through code size alone)
-__device__ __noinline__ void act4_slow(float* o, int act) {
-  if (act == ACT_SIN) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = sin_f32(o[u]);
-  } else if (act == ACT_SIGMOID) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = sigmoid_f32(o[u]);
-  } else if (act == ACT_TANH) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = tanh_f32(o[u]);
+__device__ __noinline__ float act_slow(float v, int act) {
+  switch (act) {
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case ACT_TANH: return tanhf(v);
+    case ACT_SIN: return sin_f32(v);
+    default: return v;
   }
 }
 // 4 consecutive channels starting at c (c % 4 == 0)
@@ -214,7 +204,8 @@ __device__ __forceinline__ void act4(float* o, int act, const float* slope, int 
 #pragma unroll
     for (int u = 0; u < 4; ++u) { const float sl = (c + u < cout) ? slope[c + u] : 0.f; o[u] = o[u] > 0.f ? o[u] : sl * o[u]; }
   } else {
-    act4_slow(o, act);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o[u] = act_slow(o[u], act);
   }
 }
 // 4 channels of an optional side tensor at (pixel, channel c): float4 when in range and 16B aligned
@@ -333,37 +324,24 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-        mbar_wait(&full_bar[stage], phase, SPIN);
+        mbar_wait(SPLIT ? &xf_bar[stage] : &full_bar[stage], phase, SPIN);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-        const uint64_t adesc = make_smem_desc(a_addr);
-        const uint64_t bdesc = make_smem_desc(a_addr + a_all);
-        const uint64_t alo = make_smem_desc(a_addr + A_BYTES);
-        const uint64_t blo = make_smem_desc(a_addr + a_all + b_bytes);
-        const bool leader = elect_one();
-        if (leader) {
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + a_all);
+          const uint64_t alo = make_smem_desc(a_addr + A_BYTES);
+          const uint64_t blo = make_smem_desc(a_addr + a_all + b_bytes);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 B -> +2 in the (addr >> 4) field
             const uint64_t ko = (uint64_t)(k * 2);
-            if (SPLIT) {
-              // the raw A tile is read as A_hi = trunc_tf32(a) by the tensor core: these two terms need no splitter
+            if (SPLIT) {   // small terms first
               mma_tf32(d_tmem, adesc + ko, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);   // A_hi * B_lo
+              mma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
               mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, 1u);                               // A_hi * B_hi
             } else {
               mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
             }
-          }
-        }
-        __syncwarp();
-        if (SPLIT) {
-          // ... while they run, the splitter warps finish A_lo = rn(a - trunc(a)); only this last term waits for it
-          mbar_wait(&xf_bar[stage], phase, SPIN);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        if (leader) {
-          if (SPLIT) {
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) mma_tf32(d_tmem, alo + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);   // A_lo * B_hi
           }
           if (CL == 1) mma_commit(&empty_bar[stage]);    // frees the smem slot when these MMAs retire
           else mma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // ... in every CTA that shares the weight tile
@@ -428,7 +406,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_ld32(taddr + (uint32_t)c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
-        // phase 1 (thread = pixel row): scale + bias + act1, stage to smem.  bias is padded past tiles_n*BN on the host.
+        // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to tiles_n*BN on the host.
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cbase + j);
@@ -497,26 +475,25 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (SPLIT) {
     // ===================================================== operand splitter (warps 6..9)
-    // A_lo = rn_tf32(a - trunc_tf32(a)) goes to the second buffer at the same (swizzled) offsets as A, so one
-    // descriptor shape serves both.
+    // A is rewritten in place as A_hi = rn_tf32(a) and A_lo = rn_tf32(a - A_hi) goes to the second buffer at the
+    // same (swizzled) offsets, so one descriptor shape serves both.  Round-to-nearest on both terms keeps the
+    // split unbiased (truncation left a coherent ~2^-20 relative error per product, i.e. ~1e-6*sqrt(K)).
     const int t = threadIdx.x - 192;  // 0..127
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase, SPIN);
-        const float4* a = reinterpret_cast<const float4*>(smem + stage * stage_bytes);
+        float4* a = reinterpret_cast<float4*>(smem + stage * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + stage * stage_bytes + A_BYTES);
 #pragma unroll
         for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
           const float4 v = a[t + i * 128];
-          // A_hi is what the tensor core sees when it reads the raw tile: trunc_tf32(a).  a - A_hi is exact in
-          // fp32; rounding it to nearest keeps the split unbiased (2^-21 relative), and A itself stays untouched
-          // so the A_hi terms can be issued without waiting for this warp.
-          float4 ll;
-          ll.x = rn_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
-          ll.y = rn_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
-          ll.z = rn_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
-          ll.w = rn_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+          float4 hh, ll;
+          hh.x = rn_tf32(v.x); ll.x = rn_tf32(v.x - hh.x);
+          hh.y = rn_tf32(v.y); ll.y = rn_tf32(v.y - hh.y);
+          hh.z = rn_tf32(v.z); ll.z = rn_tf32(v.z - hh.z);
+          hh.w = rn_tf32(v.w); ll.w = rn_tf32(v.w - hh.w);
+          a[t + i * 128] = hh;
           lo[t + i * 128] = ll;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)

@@ -102,8 +102,8 @@ struct SplitPlanesK {
     int c = (int)(i % src.c); int64_t px = i / src.c;
     int x = (int)(px % src.w); int64_t r = px / src.w; int y = (int)(r % src.h); int n = (int)(r / src.h);
     float v = src.p[src.off(n, y, x) + c];
-    uint32_t u; memcpy(&u, &v, 4); u &= 0xffffe000u; float hi; memcpy(&hi, &u, 4);   // trunc_tf32: what the MMA reads of plane 0
-    planes[i] = v; planes[plane + i] = rn(v - hi);
+    float hi = rn(v);
+    planes[i] = hi; planes[plane + i] = rn(v - hi);
   }
 };
 void split_planes(Ctx& cx, const TV& src, float* planes) {
