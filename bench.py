@@ -254,12 +254,26 @@ def main():
         conv_fl = sum(v["work"] for k, v in prof.items() if k.startswith("conv2d"))
         dname, d = dom
         is_flop = dname.startswith("conv2d") or dname.startswith("corr_gemm")
+        # ncu --set full captures of the dominant LAYER SHAPE of each tensor-core kernel (profiles/r01_ncu_*.jsonl):
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch
+        NCU_TRAFFIC = {"conv2d_tc_tf32": {"layer": "3x3 256->256 @1088x1920", "bytes": 2.146013e9 + 2.092577e9, "algorithmic_bytes": 2 * 1088 * 1920 * 256 * 4.0},
+                       "conv2d_tc_3xtf32": {"layer": "1x5 384->128 @2x136x240 (SepConvGRU gate)", "bytes": 102.561792e6 + 12.403968e6,
+                                            "algorithmic_bytes": 2 * 136 * 240 * (384 + 128) * 4.0}}
+        NOTES = {"conv2d_tc_tf32": "tcgen05 kind::tf32 implicit GEMM (TMA halo tiles, TMEM accumulators); TF32 peak is half the bf16 peak used as denominator",
+                 "conv2d_tc_3xtf32": "tcgen05 3xTF32 (3 MMAs per K step + register-promoted accumulation): 'achieved' counts ALGORITHMIC flops, "
+                                     "the tensor pipe executes 3x that; small-resolution RAFT layers, pipeline-latency bound (ncu: tensor pipe 14.6 % active)",
+                 "conv2d_simt_n64": "fp32 CUDA-core implicit GEMM measured against the tensor-pipe peak (the layer class is tensor-bound, SURVEY 8(d))"}
         if is_flop:
             ach = d["work"] / (d["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": dname, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
-                    "traffic": None, "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["which"],
+                    "traffic": NCU_TRAFFIC.get(dname, {}).get("bytes"), "traffic_detail": NCU_TRAFFIC.get(dname),
+                    "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["which"],
                     "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_ms,
-                    "note": "fp32 CUDA-core implicit GEMM measured against the tensor-pipe peak (the layer class is tensor-bound, SURVEY §8(d))"}
+                    "note": NOTES.get(dname, "")}
+            # the single most expensive layer shape, for which the ncu capture above was taken
+            top = max(((k, v) for k, v in raw_prof.items() if k.startswith(("conv2d", "corr_gemm"))), key=lambda kv: kv[1]["ms"])
+            roof["top_layer"] = {"name": top[0], "ms_total": top[1]["ms"], "launches": top[1]["launches"],
+                                 "tflops": top[1]["work"] / (top[1]["ms"] * 1e-3) / 1e12, "frac_of_peak": top[1]["work"] / (top[1]["ms"] * 1e-3) / 1e12 / peaks["tf_sust"]}
         else:
             ach = 4.0 * d["work"] / (d["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dname, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
