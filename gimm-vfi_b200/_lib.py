@@ -47,7 +47,7 @@ EXPORTS = [
     "gimmvfi_create", "gimmvfi_destroy", "gimmvfi_load_weight", "gimmvfi_finalize_weights", "gimmvfi_plan",
     "gimmvfi_forward", "gimmvfi_last_error", "gimmvfi_last_launches", "gimmvfi_set_raft_iters", "gimmvfi_set_debug",
     "gimmvfi_get_tap", "gimmvfi_build_info", "gimmvfi_set_profile", "gimmvfi_profile_json",
-    "gimmvfi_set_tensor_cores", "gimmvfi_op_conv2d_tc", "gimmvfi_op_softsplat", "gimmvfi_op_backwarp", "gimmvfi_op_resize",
+    "gimmvfi_set_tensor_cores", "gimmvfi_op_conv2d_tc", "gimmvfi_op_frames_u8_to_padded_f32", "gimmvfi_op_pred_to_u8", "gimmvfi_op_softsplat", "gimmvfi_op_backwarp", "gimmvfi_op_resize",
     "gimmvfi_op_corr_volume", "gimmvfi_op_corr_pool", "gimmvfi_op_corr_lookup", "gimmvfi_op_conv2d",
     "gimmvfi_instnorm_scratch_floats", "gimmvfi_op_instnorm", "gimmvfi_op_convex_upsample", "gimmvfi_op_pixel_shuffle",
 ]
@@ -102,6 +102,8 @@ class Lib:
         d.gimmvfi_op_instnorm.argtypes = [PV, i32, vp, PV, vp]
         d.gimmvfi_op_convex_upsample.argtypes = [PV, PV, PV, vp]
         d.gimmvfi_op_pixel_shuffle.argtypes = [PV, PV, i32, vp]
+        d.gimmvfi_op_frames_u8_to_padded_f32.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i32, vp]
+        d.gimmvfi_op_pred_to_u8.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, vp]
 
     def build_info(self) -> str:
         return self.dll.gimmvfi_build_info().decode()

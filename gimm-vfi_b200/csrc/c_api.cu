@@ -185,6 +185,22 @@ int gimmvfi_op_convex_upsample(const gimmvfi_view* flow, const gimmvfi_view* mas
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, { Ctx cx = op_ctx(stream); convex_upsample(cx, to_tv(flow), to_tv(mask), to_tv(out)); })
 }
+int gimmvfi_op_frames_u8_to_padded_f32(const uint8_t* frames, int n, int h, int w, float* dst_nchw, int H, int W, int pad_top, int pad_left,
+                                       void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    if (H < h || W < w || pad_top < 0 || pad_left < 0 || pad_top + h > H || pad_left + w > W) throw std::runtime_error("bad padding geometry");
+    Ctx cx = op_ctx(stream); frames_u8_to_padded_f32(cx, frames, n, h, w, dst_nchw, H, W, pad_top, pad_left);
+  })
+}
+int gimmvfi_op_pred_to_u8(const float* pred_nchw, int n, int H, int W, uint8_t* dst, int h, int w, int pad_top, int pad_left, int bgr,
+                          void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    if (H < h || W < w || pad_top < 0 || pad_left < 0 || pad_top + h > H || pad_left + w > W) throw std::runtime_error("bad padding geometry");
+    Ctx cx = op_ctx(stream); pred_to_u8(cx, pred_nchw, n, H, W, dst, h, w, pad_top, pad_left, bgr);
+  })
+}
 int gimmvfi_op_pixel_shuffle(const gimmvfi_view* src, const gimmvfi_view* dst, int times, void* stream) {
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, { Ctx cx = op_ctx(stream); pixel_shuffle(cx, to_tv(src), to_tv(dst), times); })

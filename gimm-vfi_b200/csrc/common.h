@@ -217,6 +217,8 @@ void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords /*n,h,w,2 (x,y)*/
 void nchw_to_nhwc(Ctx& cx, const float* src, int64_t src_sn, int64_t src_sc, const TV& dst, float scale, float shift);
 void nhwc_to_nchw(Ctx& cx, const TV& src, float* dst, int64_t dst_sn, int64_t dst_sc, float scale, float shift, int clamp01);  // (v + shift) * scale
 void copy_channels(Ctx& cx, const TV& src, const TV& dst);
+void frames_u8_to_padded_f32(Ctx& cx, const uint8_t* src, int n, int h, int w, float* dst_nchw, int H, int W, int pad_top, int pad_left);
+void pred_to_u8(Ctx& cx, const float* src_nchw, int n, int H, int W, uint8_t* dst, int h, int w, int pad_top, int pad_left, int bgr);
 void pad_image4(Ctx& cx, const TV& src /*c=3, ld=4*/, const TV& dst /*h+2p, w+2p, ld 4*/, int pad);
 void fill(Ctx& cx, const TV& dst, float v);
 void axpby(Ctx& cx, const TV& a, float alpha, const TV& b, float beta, const TV& out);  // out = alpha*a + beta*b (b optional)

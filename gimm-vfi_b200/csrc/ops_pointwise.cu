@@ -101,6 +101,35 @@ void copy_channels(Ctx& cx, const TV& src, const TV& dst) {
   parallel_for(cx, dst.pixels() * dst.c, CopyK{src, dst}, "copy_channels");
 }
 
+// ---- driver-side pre/post-processing (src/video_Nx.py:40-50,152-153,182-202; src/utils/utils.py:156-185) ----
+// uint8 HWC RGB frame -> float32 CHW in [0,1] (x / 255.0) replicate-padded to (H, W): InputPadder.pad
+struct FramesU8ToF32K {
+  const uint8_t* src; float* dst; int h, w, H, W, pt, pl;
+  GV_HD void operator()(int64_t i) const {
+    int X = (int)(i % W); int64_t r = i / W; int Y = (int)(r % H); r /= H; int c = (int)(r % 3); int n = (int)(r / 3);
+    int y = Y - pt, x = X - pl;
+    y = y < 0 ? 0 : (y >= h ? h - 1 : y); x = x < 0 ? 0 : (x >= w ? w - 1 : x);
+    dst[i] = (float)src[(((int64_t)n * h + y) * w + x) * 3 + c] / 255.0f;
+  }
+};
+void frames_u8_to_padded_f32(Ctx& cx, const uint8_t* src, int n, int h, int w, float* dst_nchw, int H, int W, int pad_top, int pad_left) {
+  parallel_for(cx, (int64_t)n * 3 * H * W, FramesU8ToF32K{src, dst_nchw, h, w, H, W, pad_top, pad_left}, "frames_u8_to_f32");
+}
+// float32 CHW prediction -> unpadded uint8 HWC, (x * 255.0) truncated like numpy's astype(uint8); optional BGR
+struct PredToU8K {
+  const float* src; uint8_t* dst; int H, W, h, w, pt, pl, bgr;
+  GV_HD void operator()(int64_t i) const {
+    int c = (int)(i % 3); int64_t r = i / 3; int x = (int)(r % w); r /= w; int y = (int)(r % h); int n = (int)(r / h);
+    int cs = bgr ? 2 - c : c;
+    float v = src[(((int64_t)n * 3 + cs) * H + (y + pt)) * W + (x + pl)] * 255.0f;
+    v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+    dst[i] = (uint8_t)v;
+  }
+};
+void pred_to_u8(Ctx& cx, const float* src_nchw, int n, int H, int W, uint8_t* dst, int h, int w, int pad_top, int pad_left, int bgr) {
+  parallel_for(cx, (int64_t)n * h * w * 3, PredToU8K{src_nchw, dst, H, W, h, w, pad_top, pad_left, bgr}, "pred_to_u8");
+}
+
 // zero-padded copy of a 3-channel image stored with 4-float pixels (4th lane forced to 0)
 struct PadImage4K {
   TV src, dst; int pad;

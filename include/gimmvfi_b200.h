@@ -124,6 +124,15 @@ int64_t gimmvfi_instnorm_scratch_floats(int n, int c);
 int gimmvfi_op_instnorm(const gimmvfi_view* x, int relu, float* scratch, const gimmvfi_view* out, void* stream);
 /* convex x8 upsampling raft/raft.py:86-97: flow (n,h,w,2), mask (n,h,w,576), out (n,8h,8w,2) */
 int gimmvfi_op_convex_upsample(const gimmvfi_view* flow, const gimmvfi_view* mask, const gimmvfi_view* out, void* stream);
+/* Driver-side pre/post-processing on the GPU (reference src/video_Nx.py:40-50,152-153,182-202):
+ * uint8 HWC RGB frames (n,h,w,3) -> float32 (n,3,H,W) = x/255.0, replicate-padded like InputPadder(shape, 32).pad
+ * (src/utils/utils.py:156-174: pad_left = pad_w//2, pad_top = pad_h//2) */
+int gimmvfi_op_frames_u8_to_padded_f32(const uint8_t* frames, int n, int h, int w, float* dst_nchw, int H, int W, int pad_top,
+                                       int pad_left, void* stream);
+/* float32 (n,3,H,W) prediction -> unpadded uint8 (n,h,w,3): (x*255.0).astype(uint8) with optional RGB->BGR flip
+ * (InputPadder.unpad + video_Nx.py:190-196) */
+int gimmvfi_op_pred_to_u8(const float* pred_nchw, int n, int H, int W, uint8_t* dst, int h, int w, int pad_top, int pad_left, int bgr,
+                          void* stream);
 /* nn.PixelShuffle(2) applied `times` times */
 int gimmvfi_op_pixel_shuffle(const gimmvfi_view* src, const gimmvfi_view* dst, int times, void* stream);
 
