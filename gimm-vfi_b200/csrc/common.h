@@ -101,7 +101,8 @@ struct ConvGeom {
   int stride = 1;
   int ph = 0, pw = 0;
   int reflect = 0;  // 0: zero padding, 1: reflect padding (padding_mode="reflect")
-  int loose_w = 0;  // skip the output-width check (x-taps packed into the channel axis, see Engine::pack_stem)
+  int loose_w = 0;  // x-taps packed into the channel axis of a zero-padded input (Engine::pack_xpacked): the input is
+                    // larger than the output and carries its own padding, so the size / padding checks are skipped
 };
 
 // ---------------------------------------------------------------------------
@@ -220,6 +221,7 @@ void copy_channels(Ctx& cx, const TV& src, const TV& dst);
 void frames_u8_to_padded_f32(Ctx& cx, const uint8_t* src, int n, int h, int w, float* dst_nchw, int H, int W, int pad_top, int pad_left);
 void pred_to_u8(Ctx& cx, const float* src_nchw, int n, int H, int W, uint8_t* dst, int h, int w, int pad_top, int pad_left, int bgr);
 void pad_image4(Ctx& cx, const TV& src /*c=3, ld=4*/, const TV& dst /*h+2p, w+2p, ld 4*/, int pad);
+void pad_zero(Ctx& cx, const TV& src, const TV& dst /*h+2p, w+2p, all dst.ld lanes written*/, int pad);
 void fill(Ctx& cx, const TV& dst, float v);
 void axpby(Ctx& cx, const TV& a, float alpha, const TV& b, float beta, const TV& out);  // out = alpha*a + beta*b (b optional)
 void resize_bilinear(Ctx& cx, const TV& src, const TV& dst, float scale_y, float scale_x, float mult, int accumulate, int act);

@@ -579,10 +579,11 @@ bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const Con
   (void)e;
   if (!w.w_tc || g.stride != 1 || g.reflect) return false;
   if (split && !w.has_lo) return false;
-  if (g.ph != w.kh / 2 || g.pw != w.kw / 2) return false;
+  if (!g.loose_w && (g.ph != w.kh / 2 || g.pw != w.kw / 2)) return false;
+  if (g.loose_w && (g.ph != 0 || g.pw != 0 || w.kw != 1)) return false;
   if (!al16(in0.p) || in0.ld % 4 || in0.sn % 4) return false;
   if (in1.p && (!al16(in1.p) || in1.ld % 4 || in1.sn % 4 || in0.c % 32)) return false;
-  if (in0.h != out.h || in0.w != out.w) return false;
+  if (!g.loose_w && (in0.h != out.h || in0.w != out.w)) return false;
   return true;
 }
 

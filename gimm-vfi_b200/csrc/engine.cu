@@ -221,6 +221,28 @@ void Engine::pack_stem(const std::string& name, const std::string& bn) {
   conv_[name + "#xpacked"] = c;
 }
 
+// 7x7 convolutions on few channels with the x-taps packed into the channel axis (see pack_stem): the input is a
+// zero-padded copy with `ldp` floats per pixel, the kernel becomes (7 x 1) over K = 7*ldp "channels".
+void Engine::pack_xpacked(const std::string& name, int ldp) {
+  const HostTensor& W = raw(name + ".weight");
+  const HostTensor& Bv = raw(name + ".bias");
+  const int cout = (int)W.shape[0], cin = (int)W.shape[1], kh = (int)W.shape[2], kw = (int)W.shape[3];
+  if (kh != 7 || kw != 7 || cin > ldp) throw std::runtime_error("pack_xpacked: expected a 7x7 conv with cin <= ldp");
+  const int cout_ld = (cout + 3) & ~3, K = 7 * ldp;
+  std::vector<float> pw((size_t)kh * K * cout_ld, 0.f), pb(((tc_cout_pad(cout) + 31) & ~31) + 128, 0.f);
+  for (int co = 0; co < cout; ++co) {
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx)
+        for (int c = 0; c < cin; ++c)
+          pw[((size_t)ky * K + kx * ldp + c) * cout_ld + co] = W.data[(((size_t)co * cin + c) * kh + ky) * kw + kx];
+    pb[co] = Bv.data[co];
+  }
+  ConvW c;
+  c.w = upload(pw); c.b = upload(pb); c.cin = K; c.cout = cout; c.kh = kh; c.kw = 1; c.cout_ld = cout_ld;
+  pack_tc(c, pw);
+  conv_[name + "#xp"] = c;
+}
+
 void Engine::finalize_weights() {
   for (void* p : dev_allocs_) dev_free(p);
   dev_allocs_.clear(); conv_.clear(); vec_.clear();
@@ -246,6 +268,7 @@ void Engine::finalize_weights() {
                         ".flow_head.conv1", ".flow_head.conv2", ".mask.0"})
     pack_conv(u + n);
   pack_conv(u + ".mask.2", "", 0.25f);  // "scale mask to balance gradients" raft/update.py:153
+  pack_xpacked(u + ".encoder.convf1", 4);
   // --- feature projections (gimmvfi_r.py:51-53)
   pack_conv("amt_last_cproj"); pack_conv("amt_second_last_cproj"); pack_conv("amt_fproj");
   // --- decoders (fi_components.py:229-305)
@@ -277,6 +300,8 @@ void Engine::finalize_weights() {
     for (const char* n : {".convc1", ".convc2", ".convf1", ".convf2", ".conv", ".gru.0", ".gru.2", ".feat_head.0", ".feat_head.2", ".flow_head.0", ".flow_head.2"})
       pack_conv(std::string(d) + n);
   pack_conv("amt_comb_block.0"); vec("amt_comb_block.1.weight"); pack_conv("amt_comb_block.2");
+  pack_xpacked("amt_comb_block.0", 12); pack_xpacked("amt_comb_block.2", 20);
+  pack_xpacked("amt_update4_low.convf1", 4); pack_xpacked("amt_update4_high.convf1", 4);
   // --- GIMM encoders (gimmvfi_r.py:86-109)
   for (const char* n : {"cnn_encoder.0", "cnn_encoder.1", "cnn_encoder.3.layers.0", "cnn_encoder.3.layers.2", "cnn_encoder.4.layers.0",
                         "cnn_encoder.4.layers.2", "cnn_encoder.5.layers.0", "cnn_encoder.5.layers.2", "cnn_encoder.7", "res_conv.0",
@@ -327,6 +352,20 @@ struct Net {
   void conv_e(const std::string& name, const TV& in0, const TV& in1, const TV& out, const ConvEpi& e, int stride = 1, bool reflect = false) {
     const ConvW& w = W(name);
     conv2d(cx, in0, in1, w, geom(w, stride, reflect), e, out);
+  }
+  // 7x7 conv on few channels through the x-packed weights: zero-padded copy of `in`, then a (7 x 1) conv over 7*ldp lanes
+  void conv7x(const std::string& name, const TV& in, const TV& out, int act = ACT_NONE, const float* slope = nullptr) {
+    const ConvW& w = W(name + "#xp");
+    const int ldp = w.cin / 7;
+    Arena& A = cx.arena;
+    const size_t mk = A.mark();
+    TV pad = A.tensor(in.n, in.h + 6, in.w + 6, ldp, ldp);
+    pad_zero(cx, in, pad, 3);
+    TV v = pad; v.c = w.cin;
+    ConvGeom g; g.stride = 1; g.ph = 0; g.pw = 0; g.loose_w = 1;
+    ConvEpi e; e.act1 = act; e.slope1 = slope;
+    conv2d(cx, v, TV(), w, g, e, out);
+    A.release(mk);
   }
   // Sequential(Conv2d, PReLU)  (fi_components.py:32-54)
   void convrelu(const std::string& name, const TV& in, const TV& out) { conv(name + ".0", in, out, ACT_PRELU, V(name + ".1.weight")); }
@@ -477,7 +516,7 @@ static void amt_update(Net& N, const std::string& p, bool low, const TV& ft, con
   TV cor = A.tensor(n, h, w, 256), cf = A.tensor(n, h, w, 256), flo = A.tensor(n, h, w, 128);
   N.conv(p + ".convc1", corr648, cor, ACT_LRELU);
   N.conv(p + ".convc2", cor, cf.slice(0, 192), ACT_LRELU);
-  N.conv(p + ".convf1", flow_in, flo, ACT_LRELU);
+  N.conv7x(p + ".convf1", flow_in, flo, ACT_LRELU);
   N.conv(p + ".convf2", flo, cf.slice(192, 64), ACT_LRELU);
   N.conv(p + ".conv", cf, inp.slice(0, 188), ACT_LRELU);
   TV g1 = A.tensor(n, h, w, 192), g2 = A.tensor(n, h, w, 192), hd = A.tensor(n, h, w, 192);
@@ -610,7 +649,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       // BasicMotionEncoder raft/update.py:94-112
       N.conv(u + ".encoder.convc1", corr, cor1, ACT_RELU);
       N.conv(u + ".encoder.convc2", cor1, corflo.slice(0, 192), ACT_RELU);
-      N.conv(u + ".encoder.convf1", flow, flo1, ACT_RELU);
+      N.conv7x(u + ".encoder.convf1", flow, flo1, ACT_RELU);
       N.conv(u + ".encoder.convf2", flo1, corflo.slice(192, 64), ACT_RELU);
       N.conv(u + ".encoder.conv", corflo, hx.slice(256, 126), ACT_RELU);
       // SepConvGRU raft/update.py:35-73 (horizontal 1x5 then vertical 5x1)
@@ -846,8 +885,8 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     {
       TV w9 = A.tensor(B, Hf, Wf, 9, 12), mean3 = A.tensor(B, Hf, Wf, 3, 4), c18 = A.tensor(B, Hf, Wf, 18, 20), c3 = A.tensor(B, Hf, Wf, 3, 4);
       multi_flow_blend(cx, synf.batch(0, B), synf.batch(B, B), F0f, F1f, Mkf, Rsf, w9, mean3);
-      N.conv("amt_comb_block.0", w9, c18, ACT_PRELU, N.V("amt_comb_block.1.weight"));
-      N.conv("amt_comb_block.2", c18, c3);
+      N.conv7x("amt_comb_block.0", w9, c18, ACT_PRELU, N.V("amt_comb_block.1.weight"));
+      N.conv7x("amt_comb_block.2", c18, c3);
       combine_output(cx, mean3, c3, io.imgt_pred + (int64_t)ti * B * 3 * Hf * Wf);
     }
   }

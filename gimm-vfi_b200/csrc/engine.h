@@ -76,6 +76,7 @@ class Engine {
   int tc_mode_ = 0;
   void pack_tc(ConvW& c, const std::vector<float>& packed);
   void pack_stem(const std::string& name, const std::string& bn);
+  void pack_xpacked(const std::string& name, int ldp);
   Profiler prof_;
   int64_t launches_ = 0;
   int sm_count_ = 148;

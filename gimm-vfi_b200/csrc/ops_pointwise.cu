@@ -145,6 +145,21 @@ void pad_image4(Ctx& cx, const TV& src, const TV& dst, int pad) {
   parallel_for(cx, dst.pixels() * 4, PadImage4K{src, dst, pad}, "pad_image4");
 }
 
+// zero-padded copy: dst (n, h+2p, w+2p) gets src's channels in its interior, zeros elsewhere (all dst.ld lanes)
+struct PadZeroK {
+  TV src, dst; int pad;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.ld);
+    int y = q.y - pad, x = q.x - pad;
+    float v = 0.f;
+    if (q.c < src.c && y >= 0 && y < src.h && x >= 0 && x < src.w) v = src.p[src.off(q.n, y, x) + q.c];
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = v;
+  }
+};
+void pad_zero(Ctx& cx, const TV& src, const TV& dst, int pad) {
+  parallel_for(cx, dst.pixels() * dst.ld, PadZeroK{src, dst, pad}, "pad_zero");
+}
+
 struct FillK {
   TV dst; float v;
   GV_HD void operator()(int64_t i) const {
