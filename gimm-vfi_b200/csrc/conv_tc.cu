@@ -33,7 +33,7 @@ namespace tc {
 constexpr int TILE_H = 8, TILE_W = 16, BM = 128, BK = 32, MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 4;                // 16 KB
 constexpr int STG_PITCH = 36;                       // floats per staged row (32 + 4: keeps float4 alignment)
-constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;   // 4 epilogue warps x 32 rows
+constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;  // staging area of one epilogue warp (32 rows)
 constexpr int BAR_BYTES = 512;
 
 struct Params {
@@ -223,8 +223,11 @@ __device__ __forceinline__ void load4(const float* p, int c, int cout, float* r)
 // with the same weights; each loads HALF of every weight box and multicasts it to both, halving the weight
 // traffic out of L2 (the limiter at N = 256).  A stage may be refilled only when BOTH CTAs' MMAs retired it,
 // so the MMA commit is multicast to both CTAs' empty barriers (count 2).
-template <bool SPLIT, int CL>
-__global__ void __launch_bounds__(SPLIT ? 320 : 192, 1)
+// EW = epilogue warps (4 or 8).  With K-poor layers (1x1 convs, correlation, 32/64 channels) the epilogue, not the
+// MMA, is the critical path and one warp per SM sub-partition is instruction-latency bound: EW == 8 puts two warps
+// on every TMEM lane quarter, alternating over the 32-column chunks.
+template <bool SPLIT, int CL, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW + (SPLIT ? 128 : 0), 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
                  const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -235,7 +238,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int stage_bytes = a_all + (SPLIT ? 2 * b_bytes : b_bytes);
   const int STAGES = p.stages;
   float* stg_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + STG_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + EW * STG_WARP_BYTES);
   uint64_t* full_bar = bars;                          // [MAX_STAGES]  TMA bytes landed
   uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]  MMAs reading the stage retired
   uint64_t* xf_bar = bars + 2 * MAX_STAGES;           // [MAX_STAGES]  (SPLIT) A_lo written
@@ -259,7 +262,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); mbar_init(&xf_bar[s], 4); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -352,12 +355,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (seg_end) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + EW) {
     // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
     // TMEM gives each thread one pixel (row) x 32 consecutive channels; the 32x32 chunk is transposed
     // through shared memory so global reads/writes are full 128-byte rows (8 lanes x float4).
     const int quarter = warp & 3;
     float* stg = stg_base + (warp - 2) * 32 * STG_PITCH;
+    const int chunk0 = (warp - 2) / 4, chunk_step = EW / 4;   // EW == 8: the two warps of a quarter interleave chunks
     const int q8 = lane & 7, rsub = lane >> 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -393,7 +397,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll (SPLIT ? 4 : 1)
-      for (int chq = 0; chq < (SPLIT ? 4 : 8); ++chq) {
+      for (int chq = (SPLIT ? 0 : chunk0); chq < (SPLIT ? 4 : 8); chq += (SPLIT ? 1 : chunk_step)) {
         const int c0 = chq * 32;
         if (c0 >= p.BN) break;
         const int cbase = nt * p.BN + c0;
@@ -478,7 +482,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // A is rewritten in place as A_hi = rn_tf32(a) and A_lo = rn_tf32(a - A_hi) goes to the second buffer at the
     // same (swizzled) offsets, so one descriptor shape serves both.  Round-to-nearest on both terms keeps the
     // split unbiased (truncation left a coherent ~2^-20 relative error per product, i.e. ~1e-6*sqrt(K)).
-    const int t = threadIdx.x - 192;  // 0..127
+    const int t = threadIdx.x - 32 * (2 + EW);  // 0..127
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int ks = 0; ks < ksteps; ++ks) {
@@ -544,12 +548,12 @@ static void encode_act(CUtensorMap* m, const TV& t) {
 }  // namespace tc
 
 // launch with an optional (2,1,1) thread-block cluster
-template <bool SPLIT, int CL>
+template <bool SPLIT, int CL, int EW>
 static void launch_tc(int grid, int threads, int smem, gvStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                       const tc::Params& p) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(tc::conv2d_tc_kernel<SPLIT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t er = cudaFuncSetAttribute(tc::conv2d_tc_kernel<SPLIT, CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
     attr_set = true;
   }
@@ -558,7 +562,7 @@ static void launch_tc(int grid, int threads, int smem, gvStream_t stream, const 
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t er = cudaLaunchKernelEx(&cfg, tc::conv2d_tc_kernel<SPLIT, CL>, a0, a1, b, p);
+  cudaError_t er = cudaLaunchKernelEx(&cfg, tc::conv2d_tc_kernel<SPLIT, CL, EW>, a0, a1, b, p);
   if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: launch failed: ") + cudaGetErrorString(er));
 }
 
@@ -566,6 +570,12 @@ static int tc_cluster() {   // GIMMVFI_TC_CLUSTER=1 disables the 2-CTA weight mu
   static int c = -1;
   if (c < 0) { const char* s = getenv("GIMMVFI_TC_CLUSTER"); c = s ? atoi(s) : 2; if (c != 1 && c != 2) c = 2; }
   return c;
+}
+
+static bool tc_epi8() {   // GIMMVFI_TC_EPI8=0 keeps 4 epilogue warps everywhere
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_EPI8"); v = s ? atoi(s) : 1; }
+  return v != 0;
 }
 
 static int tc_seg() {
@@ -626,11 +636,13 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2;
   p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
   const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
-  const int budget = 227 * 1024 - 1024 /*align*/ - STG_BYTES - BAR_BYTES;
+  const bool ew8 = !split && BN <= 128 && tc_epi8();   // K-poor plain layers are epilogue bound: 8 epilogue warps
+  const int stg_bytes = (ew8 ? 8 : 4) * STG_WARP_BYTES;
+  const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES;
   p.stages = budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.stages < 2) throw std::runtime_error("conv_tc: not enough shared memory for 2 pipeline stages");
-  const int smem = p.stages * stage_bytes + STG_BYTES + BAR_BYTES + 1024;
+  const int smem = p.stages * stage_bytes + stg_bytes + BAR_BYTES + 1024;
   const int padded_tiles = (pix_tiles_host + CL - 1) / CL * CL * tiles_n;
   int grid = padded_tiles < cx.sm_count ? padded_tiles : cx.sm_count;
   grid -= grid % CL;
@@ -640,8 +652,9 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
     snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? "3xtf32" : "tf32", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
   }
-  if (split) { if (CL == 2) launch_tc<true, 2>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
-  else { if (CL == 2) launch_tc<false, 2>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<false, 1>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); }
+  if (split) { if (CL == 2) launch_tc<true, 2, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
+  else if (ew8) { if (CL == 2) launch_tc<false, 2, 8>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<false, 1, 8>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
+  else { if (CL == 2) launch_tc<false, 2, 4>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<false, 1, 4>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); }
   gv_check_launch("conv2d_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }
@@ -656,9 +669,9 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   const int N = fa.h * fa.w, C = fa.c;
   CUtensorMap mA, mB;
   encode_act(&mA, fa);
-  // split: BN <= 128 (register-promoted accumulation), fb_planes = [2][N][C].  plain TF32: BN = 256, fb_planes = the
-  // raw K-major features [N][C] of the other frame (the tensor core truncates them).
-  const int BN = split ? 128 : 256, tiles_n = (N + BN - 1) / BN;
+  // split: fb_planes = [2][N][C] (rn / residual planes).  plain TF32: fb_planes = the raw K-major features [N][C] of the
+  // other frame (the tensor core truncates them).  BN = 128 in both (register accumulators / 8 epilogue warps).
+  const int BN = 128, tiles_n = (N + BN - 1) / BN;
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)(split ? 2 : 1)};
     cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
@@ -676,15 +689,17 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   p.bias = zero_bias; p.act1 = ACT_NONE; p.slope1 = nullptr; p.act2 = ACT_NONE; p.slope2 = nullptr;
   p.out = make_tv(vol, 1, fa.h, fa.w, N, N);
   const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
-  p.stages = (227 * 1024 - 1024 - STG_BYTES - BAR_BYTES) / stage_bytes;
+  const int stg_bytes = ((!split && tc_epi8()) ? 8 : 4) * STG_WARP_BYTES;
+  p.stages = (227 * 1024 - 1024 - stg_bytes - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  const int smem = p.stages * stage_bytes + STG_BYTES + BAR_BYTES + 1024;
+  const int smem = p.stages * stage_bytes + stg_bytes + BAR_BYTES + 1024;
   const int num_tiles = p.tiles_y * p.tiles_x * tiles_n;
   const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
   cx.launches++;
   if (cx.prof) cx.prof->begin(cx.stream, split ? "corr_gemm_tc_3xtf32" : "corr_gemm_tc_tf32", 2.0 * (double)N * N * C);
-  if (split) launch_tc<true, 1>(grid, 320, smem, cx.stream, mA, mA, mB, p);
-  else launch_tc<false, 1>(grid, 192, smem, cx.stream, mA, mA, mB, p);
+  if (split) launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA, mA, mB, p);
+  else if (tc_epi8()) launch_tc<false, 1, 8>(grid, 320, smem, cx.stream, mA, mA, mB, p);
+  else launch_tc<false, 1, 4>(grid, 192, smem, cx.stream, mA, mA, mB, p);
   gv_check_launch("corr_volume_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }
