@@ -367,23 +367,25 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = (tile / CL) % p.tiles_n; int r = (tile / CL) / p.tiles_n * CL + tile % CL;
       const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
-      float racc[SPLIT ? 128 : 1];   // SPLIT: fp32 register accumulators (BN <= 128), summed across K segments
+      constexpr int NLC = SPLIT ? 4 / (EW / 4) : 1;   // 32-column chunks owned by this warp in SPLIT mode (4, or 2 with EW == 8)
+      float racc[SPLIT ? 32 * NLC : 1];   // SPLIT: fp32 register accumulators (BN <= 128), summed across K segments
       if (SPLIT) {
 #pragma unroll
-        for (int i = 0; i < (SPLIT ? 128 : 1); ++i) racc[i] = 0.f;
+        for (int i = 0; i < (SPLIT ? 32 * NLC : 1); ++i) racc[i] = 0.f;
         const int nseg = (ksteps + p.seg - 1) / p.seg;
         for (int sg = 0; sg < nseg; ++sg) {
           mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int lc = 0; lc < NLC; ++lc) {
+            const int ch = chunk0 + lc * chunk_step;
             if (ch * 32 < p.BN) {
               uint32_t t[32];
               tmem_ld32(ta + (uint32_t)(ch * 32), t);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-              for (int j = 0; j < 32; ++j) racc[(SPLIT ? ch * 32 : 0) + (SPLIT ? j : 0)] += __uint_as_float(t[j]);
+              for (int j = 0; j < 32; ++j) racc[(SPLIT ? lc * 32 : 0) + (SPLIT ? j : 0)] += __uint_as_float(t[j]);
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -396,8 +398,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-#pragma unroll (SPLIT ? 4 : 1)
-      for (int chq = (SPLIT ? 0 : chunk0); chq < (SPLIT ? 4 : 8); chq += (SPLIT ? 1 : chunk_step)) {
+#pragma unroll (SPLIT ? NLC : 1)
+      for (int lcq = 0; lcq < (SPLIT ? NLC : 8); ++lcq) {
+        const int chq = chunk0 + lcq * chunk_step;   // SPLIT: static register index lcq; plain: TMEM column chunk
         const int c0 = chq * 32;
         if (c0 >= p.BN) break;
         const int cbase = nt * p.BN + c0;
@@ -405,7 +408,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         uint32_t v[32];
         if (SPLIT) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(racc[(SPLIT ? chq * 32 : 0) + (SPLIT ? j : 0)]);
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(racc[(SPLIT ? lcq * 32 : 0) + (SPLIT ? j : 0)]);
         } else {
           tmem_ld32(taddr + (uint32_t)c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -578,6 +581,12 @@ static bool tc_epi8() {   // GIMMVFI_TC_EPI8=0 keeps 4 epilogue warps everywhere
   return v != 0;
 }
 
+static bool tc_split_epi8() {   // GIMMVFI_TC_SPLIT_EPI8=0: 4 epilogue/drain warps in the 3xTF32 kernel
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_EPI8"); v = s ? atoi(s) : 1; }
+  return v != 0;
+}
+
 static int tc_seg() {
   static int seg = -1;
   if (seg < 0) { const char* s = getenv("GIMMVFI_TC_SEG"); seg = s ? atoi(s) : 2; if (seg < 1) seg = 1; }
@@ -637,7 +646,8 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
   const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
   const bool ew8 = !split && BN <= 128 && tc_epi8();   // K-poor plain layers are epilogue bound: 8 epilogue warps
-  const int stg_bytes = (ew8 ? 8 : 4) * STG_WARP_BYTES;
+  const bool sew8 = split && tc_epi8() && tc_split_epi8();
+  const int stg_bytes = ((ew8 || sew8) ? 8 : 4) * STG_WARP_BYTES;
   const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES;
   p.stages = budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
@@ -652,7 +662,8 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
     snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? "3xtf32" : "tf32", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
   }
-  if (split) { if (CL == 2) launch_tc<true, 2, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
+  if (split && sew8) { if (CL == 2) launch_tc<true, 2, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p); }
+  else if (split) { if (CL == 2) launch_tc<true, 2, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
   else if (ew8) { if (CL == 2) launch_tc<false, 2, 8>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<false, 1, 8>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
   else { if (CL == 2) launch_tc<false, 2, 4>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<false, 1, 4>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); }
   gv_check_launch("conv2d_tc");
@@ -689,7 +700,8 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   p.bias = zero_bias; p.act1 = ACT_NONE; p.slope1 = nullptr; p.act2 = ACT_NONE; p.slope2 = nullptr;
   p.out = make_tv(vol, 1, fa.h, fa.w, N, N);
   const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
-  const int stg_bytes = ((!split && tc_epi8()) ? 8 : 4) * STG_WARP_BYTES;
+  const bool e8 = tc_epi8() && (!split || tc_split_epi8());
+  const int stg_bytes = (e8 ? 8 : 4) * STG_WARP_BYTES;
   p.stages = (227 * 1024 - 1024 - stg_bytes - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int smem = p.stages * stage_bytes + stg_bytes + BAR_BYTES + 1024;
@@ -697,8 +709,9 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
   cx.launches++;
   if (cx.prof) cx.prof->begin(cx.stream, split ? "corr_gemm_tc_3xtf32" : "corr_gemm_tc_tf32", 2.0 * (double)N * N * C);
-  if (split) launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA, mA, mB, p);
-  else if (tc_epi8()) launch_tc<false, 1, 8>(grid, 320, smem, cx.stream, mA, mA, mB, p);
+  if (split && e8) launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA, mA, mB, p);
+  else if (split) launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA, mA, mB, p);
+  else if (e8) launch_tc<false, 1, 8>(grid, 320, smem, cx.stream, mA, mA, mB, p);
   else launch_tc<false, 1, 4>(grid, 192, smem, cx.stream, mA, mA, mB, p);
   gv_check_launch("corr_volume_tc");
   if (cx.prof) cx.prof->end(cx.stream);
