@@ -646,7 +646,9 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
   const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
   const bool ew8 = !split && BN <= 128 && tc_epi8();   // K-poor plain layers are epilogue bound: 8 epilogue warps
-  const bool sew8 = split && tc_epi8() && tc_split_epi8();
+  // 3xTF32: 8 drain/epilogue warps help K-poor layers (+20-30 %) but steal issue slots from the splitter warps on
+  // K-rich full-width tiles (SepConvGRU gates: -15 %): measured in profiles/r01_tc_microbench_split_epi8.log
+  const bool sew8 = split && tc_epi8() && tc_split_epi8() && !(BN == 128 && taps * (w.cin_pad / 32) >= 48);
   const int stg_bytes = ((ew8 || sew8) ? 8 : 4) * STG_WARP_BYTES;
   const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES;
   p.stages = budget / stage_bytes;
