@@ -48,7 +48,7 @@ EXPORTS = [
     "gimmvfi_forward", "gimmvfi_last_error", "gimmvfi_last_launches", "gimmvfi_set_raft_iters", "gimmvfi_set_debug",
     "gimmvfi_get_tap", "gimmvfi_build_info", "gimmvfi_set_profile", "gimmvfi_profile_json",
     "gimmvfi_set_tensor_cores", "gimmvfi_op_conv2d_tc", "gimmvfi_op_frames_u8_to_padded_f32", "gimmvfi_op_pred_to_u8", "gimmvfi_op_softsplat", "gimmvfi_op_backwarp", "gimmvfi_op_resize",
-    "gimmvfi_op_corr_volume", "gimmvfi_op_corr_pool", "gimmvfi_op_corr_lookup", "gimmvfi_op_conv2d",
+    "gimmvfi_op_corr_volume", "gimmvfi_op_corr_pool", "gimmvfi_op_corr_pool_pyramid", "gimmvfi_op_corr_lookup", "gimmvfi_op_conv2d",
     "gimmvfi_instnorm_scratch_floats", "gimmvfi_op_instnorm", "gimmvfi_op_convex_upsample", "gimmvfi_op_pixel_shuffle",
 ]
 
@@ -95,6 +95,7 @@ class Lib:
         d.gimmvfi_op_resize.argtypes = [PV, PV, f32, f32, vp]
         d.gimmvfi_op_corr_volume.argtypes = [PV, PV, vp, vp]
         d.gimmvfi_op_corr_pool.argtypes = [vp, vp, i64, i32, i32, vp]
+        d.gimmvfi_op_corr_pool_pyramid.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
         d.gimmvfi_op_corr_lookup.argtypes = [C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32), PV, PV, vp]
         d.gimmvfi_op_conv2d.argtypes = [PV, PV, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, PV, PV, vp]
         d.gimmvfi_instnorm_scratch_floats.argtypes = [i32, i32]

@@ -123,6 +123,10 @@ int gimmvfi_op_corr_pool(const float* src, float* dst, int64_t rows, int h, int 
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, { Ctx cx = op_ctx(stream); corr_pool(cx, src, dst, rows, h, w); })
 }
+int gimmvfi_op_corr_pool_pyramid(const float* l0, float* l1, float* l2, float* l3, int64_t rows, int h, int w, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); corr_pool_pyramid(cx, l0, l1, l2, l3, rows, h, w); })
+}
 int gimmvfi_op_corr_lookup(const float* const lvl[4], const int32_t lvl_h[4], const int32_t lvl_w[4], const gimmvfi_view* coords,
                            const gimmvfi_view* out, void* stream) {
   gimmvfi_engine* e = nullptr;

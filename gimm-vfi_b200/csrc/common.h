@@ -212,6 +212,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
 void split_planes(Ctx& cx, const TV& src, float* planes);  // [2][n*h*w][c]: rn_tf32(x) and rn_tf32(x - rn_tf32(x))
 void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale);   // vol[n][i][j] = <fa[n,i], fb[n,j]> * scale
 void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w); // rows x (h*w) -> rows x (h/2*w/2)
+void corr_pool_pyramid(Ctx& cx, const float* l0, float* l1, float* l2, float* l3, int64_t rows, int h, int w);
 struct CorrPyr { const float* lvl[4]; int h[4], w[4]; int64_t rows_per_sample; };
 void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords /*n,h,w,2 (x,y)*/, const TV& out /*324 ch*/);
 // ops_pointwise.cu
@@ -221,6 +222,7 @@ void copy_channels(Ctx& cx, const TV& src, const TV& dst);
 void frames_u8_to_padded_f32(Ctx& cx, const uint8_t* src, int n, int h, int w, float* dst_nchw, int H, int W, int pad_top, int pad_left);
 void pred_to_u8(Ctx& cx, const float* src_nchw, int n, int H, int W, uint8_t* dst, int h, int w, int pad_top, int pad_left, int bgr);
 void pad_image4(Ctx& cx, const TV& src /*c=3, ld=4*/, const TV& dst /*h+2p, w+2p, ld 4*/, int pad);
+void pad_reflect(Ctx& cx, const TV& src, const TV& dst /*h+2p, w+2p*/, int pad);
 void pad_zero(Ctx& cx, const TV& src, const TV& dst /*h+2p, w+2p, all dst.ld lanes written*/, int pad);
 void fill(Ctx& cx, const TV& dst, float v);
 void axpby(Ctx& cx, const TV& a, float alpha, const TV& b, float beta, const TV& out);  // out = alpha*a + beta*b (b optional)

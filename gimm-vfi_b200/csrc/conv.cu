@@ -158,7 +158,7 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
   if (out.c != w.cout) throw std::runtime_error("conv2d: cout mismatch");
   {
     int eh = (in0.h + 2 * g.ph - w.kh) / g.stride + 1, ew = (in0.w + 2 * g.pw - w.kw) / g.stride + 1;
-    if (eh != out.h || (ew != out.w && !g.loose_w) || in0.n != out.n) throw std::runtime_error("conv2d: output geometry mismatch");
+    if (((eh != out.h || ew != out.w) && !g.loose_w) || in0.n != out.n) throw std::runtime_error("conv2d: output geometry mismatch");
   }
 #ifndef GV_HOSTSIM
   if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out, cx.tc_split)) { conv2d_tc(cx, in0, in1, w, g, e, out, cx.tc_split); return; }

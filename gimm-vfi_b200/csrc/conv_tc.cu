@@ -46,6 +46,9 @@ struct Params {
   int cout;
   int round_out;                   // store TF32-rounded (RN) values
   int spin_limit;                  // mbarrier try_wait attempts before trapping (0 = wait forever)
+  int dbg;                         // timing experiments only (GIMMVFI_TC_DEBUG): 1 = splitter idles, 2 = segment drain skips its TMEM loads
+  unsigned long long* stall;       // stall profiling (GIMMVFI_TC_STALL_BUF): 16 counters per CTA, else nullptr
+  int atmem;                       // SPLIT: A_hi / A_lo live in tensor memory (written by the splitter warps), not in smem
   int seg;                         // SPLIT: K steps accumulated in TMEM before promotion to fp32 registers
   float out_scale;                 // accumulator scale applied before the bias (all-pairs correlation: 1/sqrt(C))
   const float* bias;               // padded to tiles_n * BN
@@ -124,6 +127,16 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// mbar_wait that charges the cycles it blocked to a per-role counter (stall profiling only: p.stall != nullptr)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int spin_limit, long long* acc_cycles) {
+  if (acc_cycles) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity, spin_limit);
+    *acc_cycles += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity, spin_limit);
+  }
+}
 // K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -142,6 +155,25 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// A operand read from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -191,23 +223,6 @@ __device__ __noinline__ float act_slow(float v, int act) {
     default: return v;
   }
 }
-// 4 consecutive channels starting at c (c % 4 == 0)
-__device__ __forceinline__ void act4(float* o, int act, const float* slope, int c, int cout) {
-  if (act == ACT_NONE) return;
-  if (act == ACT_RELU) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = fmaxf(o[u], 0.f);
-  } else if (act == ACT_LRELU) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = o[u] > 0.f ? o[u] : 0.1f * o[u];
-  } else if (act == ACT_PRELU) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const float sl = (c + u < cout) ? slope[c + u] : 0.f; o[u] = o[u] > 0.f ? o[u] : sl * o[u]; }
-  } else {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = act_slow(o[u], act);
-  }
-}
 // 4 channels of an optional side tensor at (pixel, channel c): float4 when in range and 16B aligned
 __device__ __forceinline__ void load4(const float* p, int c, int cout, float* r) {
   if (c + 3 < cout && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
@@ -217,6 +232,152 @@ __device__ __forceinline__ void load4(const float* p, int c, int cout, float* r)
 #pragma unroll
     for (int u = 0; u < 4; ++u) r[u] = (c + u < cout) ? p[u] : 0.f;
   }
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// activation over N values whose first channel is c (the dispatch is hoisted out of the element loops: one warp's
+// epilogue is a dependent-instruction chain, so every instruction removed from it is ~5 cycles of critical path)
+template <int N>
+__device__ __forceinline__ void act_n(float* o, int act, const float* slope, int c, int cout) {
+  if (act == ACT_NONE) return;
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) o[u] = fmaxf(o[u], 0.f);
+  } else if (act == ACT_LRELU) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) o[u] = o[u] > 0.f ? o[u] : 0.1f * o[u];
+  } else if (act == ACT_PRELU) {
+    if (c + N <= cout && ((reinterpret_cast<uintptr_t>(slope + c) & 15) == 0)) {
+#pragma unroll
+      for (int u = 0; u < N; u += 4) {
+        const float4 sl = __ldg(reinterpret_cast<const float4*>(slope + c + u));
+        o[u] = o[u] > 0.f ? o[u] : sl.x * o[u]; o[u + 1] = o[u + 1] > 0.f ? o[u + 1] : sl.y * o[u + 1];
+        o[u + 2] = o[u + 2] > 0.f ? o[u + 2] : sl.z * o[u + 2]; o[u + 3] = o[u + 3] > 0.f ? o[u + 3] : sl.w * o[u + 3];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < N; ++u) { const float sl = (c + u < cout) ? slope[c + u] : 0.f; o[u] = o[u] > 0.f ? o[u] : sl * o[u]; }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < N; ++u) o[u] = act_slow(o[u], act);
+  }
+}
+// One 32-row x 32-column chunk of the output tile: v[j] = accumulator of (this thread's pixel row, column c0 + j).
+// stg_s = shared-window address of this warp's 32 x STG_PITCH staging area; cbase = first output channel of the chunk.
+__device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, uint32_t stg_s, int cbase, int quarter, int lane, int tx, int ty,
+                                          int n, long long* tprof /* stall profiling: [0] phase 1, [1] phase 2, [2] chunks */) {
+  const int q8 = lane & 7, rsub = lane >> 3;
+  const long long tp0 = tprof ? clock64() : 0;
+  // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to tiles_n*BN (+slack) on the host.
+  {
+    float o[32];
+    const float4* b4p = reinterpret_cast<const float4*>(p.bias + cbase);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = __ldg(b4p + j);
+      o[4 * j] = fmaf(__uint_as_float(v[4 * j]), p.out_scale, b4.x); o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), p.out_scale, b4.y);
+      o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), p.out_scale, b4.z); o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), p.out_scale, b4.w);
+    }
+    act_n<32>(o, p.act1, p.slope1, cbase, p.cout);
+    const uint32_t srow = stg_s + (uint32_t)(lane * STG_PITCH * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(srow + j * 16, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+  __syncwarp();
+  const long long tp1 = tprof ? clock64() : 0;
+  // phase 2 (8 lanes = one 128-byte row, 4 rows per instruction): + residual, act2, gate multiply,
+  // ConvGRU blend, optional TF32 rounding, coalesced store.  Row `it` of this lane is tile pixel
+  // (yy, xx) = (quarter * 2 + it / 4, (it % 4) * 4 + rsub).
+  const int c = cbase + q8 * 4;
+  if (c < p.cout && n < p.n_img) {
+    const bool full4 = c + 3 < p.cout;
+    const int y0 = ty * TILE_H + quarter * 2, x0 = tx * TILE_W + rsub;
+    const bool interior = y0 + 1 < p.H && tx * TILE_W + TILE_W <= p.W;
+    const uint32_t sbase = stg_s + (uint32_t)((rsub * STG_PITCH + q8 * 4) * 4);
+    const bool lean = !p.res.p && !p.mul.p && !p.gru_z.p;
+    const int64_t opix0 = (int64_t)y0 * p.W + x0;
+    float* const obase = p.out.p + (int64_t)n * p.out.sn + opix0 * p.out.ld + c;
+    const int64_t o_row = (int64_t)p.W * p.out.ld, o_x = (int64_t)4 * p.out.ld;
+    const bool ovec = full4 && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0) && (p.out.ld % 4 == 0);
+    if (lean) {
+      float o[32];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const float4 sv = lds128(sbase + (uint32_t)(it * 4 * STG_PITCH * 4));
+        o[4 * it] = sv.x; o[4 * it + 1] = sv.y; o[4 * it + 2] = sv.z; o[4 * it + 3] = sv.w;
+      }
+      if (p.act2 != ACT_NONE) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) act_n<4>(o + 4 * it, p.act2, p.slope2, c, p.cout);
+      }
+      if (p.round_out) {
+        // store TF32-representable values (round-to-nearest-even): the next TF32 layer then truncates
+        // nothing, i.e. its operands are RN- instead of toward-zero-rounded (unbiased)
+#pragma unroll
+        for (int u = 0; u < 32; ++u) o[u] = rn_tf32(o[u]);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int yy = it >> 2, xx = (it & 3) * 4;
+        if (!interior && (y0 + yy >= p.H || x0 + xx >= p.W)) continue;
+        float* optr = obase + yy * o_row + (it & 3) * o_x;
+        if (ovec) {
+          *reinterpret_cast<float4*>(optr) = make_float4(o[4 * it], o[4 * it + 1], o[4 * it + 2], o[4 * it + 3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (c + u < p.cout) optr[u] = o[4 * it + u];
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int yy = it >> 2, xx = (it & 3) * 4;
+        const int y = y0 + yy, x = x0 + xx;
+        if (!interior && (y >= p.H || x >= p.W)) continue;
+        const float4 sv = lds128(sbase + (uint32_t)(it * 4 * STG_PITCH * 4));
+        float o[4] = {sv.x, sv.y, sv.z, sv.w};
+        if (p.res.p) {
+          float t[4]; load4(p.res.p + p.res.off(n, y, x) + c, c, p.cout, t);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) o[u] += t[u];
+        }
+        act_n<4>(o, p.act2, p.slope2, c, p.cout);
+        if (p.mul.p) {
+          float t[4]; load4(p.mul.p + p.mul.off(n, y, x) + c, c, p.cout, t);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) o[u] *= t[u];
+        }
+        if (p.gru_z.p) {  // h = (1 - z) * h + z * q   (raft/update.py:58,66)
+          float z[4], h[4];
+          load4(p.gru_z.p + p.gru_z.off(n, y, x) + c, c, p.cout, z);
+          load4(p.gru_h.p + p.gru_h.off(n, y, x) + c, c, p.cout, h);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) o[u] = (1.f - z[u]) * h[u] + z[u] * o[u];
+        }
+        if (p.round_out) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) o[u] = rn_tf32(o[u]);
+        }
+        float* optr = obase + yy * o_row + (it & 3) * o_x;
+        if (ovec) {
+          *reinterpret_cast<float4*>(optr) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (c + u < p.cout) optr[u] = o[u];
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (tprof) { const long long tp2 = clock64(); tprof[0] += tp1 - tp0; tprof[1] += tp2 - tp1; tprof[2] += 1; }
 }
 
 // CL = thread-block-cluster size (1 or 2).  CL == 2: the two CTAs of a cluster work on neighbouring pixel tiles
@@ -229,12 +390,14 @@ __device__ __forceinline__ void load4(const float* p, int c, int cout, float* r)
 template <bool SPLIT, int CL, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW + (SPLIT ? 128 : 0), 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
-                 const Params p) {
+                 const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: per stage [A 16 KB | (A_lo 16 KB) | B BN*128 B | (B_lo)], then the epilogue staging area, then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.BN * BK * 4;
-  const int a_all = SPLIT ? 2 * A_BYTES : A_BYTES;
+  const bool ATM = SPLIT && p.atmem;   // TMEM columns: accumulators at 0 / 128, A ring (64 columns per stage) from 256
+  const int a_all = (SPLIT && !ATM) ? 2 * A_BYTES : A_BYTES;
+  const uint32_t acc_stride = ATM ? 128u : 256u;
   const int stage_bytes = a_all + (SPLIT ? 2 * b_bytes : b_bytes);
   const int STAGES = p.stages;
   float* stg_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
@@ -253,6 +416,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int num_tiles = pix_tiles * p.tiles_n;
   const int ksteps = p.taps * p.kblocks;
   const int SPIN = p.spin_limit;
+  long long st_a = 0, st_b = 0;           // stall-profile accumulators of this thread's role
+  long long st_c[3] = {0, 0, 0};
+  long long* const ST_A = p.stall ? &st_a : nullptr;
+  long long* const ST_B = p.stall ? &st_b : nullptr;
+  const long long t_start = p.stall ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0)) : "memory");
@@ -288,7 +456,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const int ky = tap / p.kw, kx = tap % p.kw;
           const int x0 = tx * TILE_W + kx - p.pw, y0 = ty * TILE_H + ky - p.ph;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1, SPIN);
+            mbar_wait_t(&empty_bar[stage], phase ^ 1, SPIN, ST_A);
             uint8_t* a_dst = smem + stage * stage_bytes;
             uint8_t* b_dst = a_dst + a_all;
             mbar_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + (SPLIT ? 2 * b_bytes : b_bytes)));
@@ -307,6 +475,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
       }
+      if (p.stall) p.stall[(size_t)blockIdx.x * 16] = (unsigned long long)st_a;
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
@@ -323,11 +492,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const bool seg_start = SPLIT ? (ks % p.seg == 0) : (ks == 0);
         const bool seg_end = SPLIT ? (ks % p.seg == p.seg - 1 || ks == ksteps - 1) : (ks == ksteps - 1);
         if (seg_start) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1, SPIN);
+          mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, SPIN, ST_B);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-        mbar_wait(SPLIT ? &xf_bar[stage] : &full_bar[stage], phase, SPIN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+        mbar_wait_t(SPLIT ? &xf_bar[stage] : &full_bar[stage], phase, SPIN, ST_A);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
@@ -338,7 +507,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 B -> +2 in the (addr >> 4) field
             const uint64_t ko = (uint64_t)(k * 2);
-            if (SPLIT) {   // small terms first
+            if (ATM) {
+              const uint32_t ahi_t = tmem_base + 256u + (uint32_t)(stage * 64 + k * 8), alo_t = ahi_t + 32u;
+              mma_tf32_ts(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);     // A_hi * B_lo
+              mma_tf32_ts(d_tmem, alo_t, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
+              mma_tf32_ts(d_tmem, ahi_t, bdesc + ko, idesc, 1u);                                 // A_hi * B_hi
+            } else if (SPLIT) {   // small terms first
               mma_tf32(d_tmem, adesc + ko, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);   // A_hi * B_lo
               mma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
               mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, 1u);                               // A_hi * B_hi
@@ -360,7 +534,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // TMEM gives each thread one pixel (row) x 32 consecutive channels; the 32x32 chunk is transposed
     // through shared memory so global reads/writes are full 128-byte rows (8 lanes x float4).
     const int quarter = warp & 3;
-    float* stg = stg_base + (warp - 2) * 32 * STG_PITCH;
+    const uint32_t stg_s = smem_u32(stg_base + (warp - 2) * 32 * STG_PITCH);
     const int chunk0 = (warp - 2) / 4, chunk_step = EW / 4;   // EW == 8: the two warps of a quarter interleave chunks
     const int q8 = lane & 7, rsub = lane >> 3;
     int acc = 0; uint32_t acc_phase = 0;
@@ -374,13 +548,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int i = 0; i < (SPLIT ? 32 * NLC : 1); ++i) racc[i] = 0.f;
         const int nseg = (ksteps + p.seg - 1) / p.seg;
         for (int sg = 0; sg < nseg; ++sg) {
-          mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
+          mbar_wait_t(&tfull_bar[acc], acc_phase, SPIN, ST_A);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_stride;
 #pragma unroll
           for (int lc = 0; lc < NLC; ++lc) {
             const int ch = chunk0 + lc * chunk_step;
-            if (ch * 32 < p.BN) {
+            if (ch * 32 < p.BN && !(p.dbg & 2)) {
               uint32_t t[32];
               tmem_ld32(ta + (uint32_t)(ch * 32), t);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -394,10 +568,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       } else {
-        mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
+        mbar_wait_t(&tfull_bar[acc], acc_phase, SPIN, ST_A);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * acc_stride;
+      const long long t_out0 = p.stall ? clock64() : 0;
 #pragma unroll (SPLIT ? NLC : 1)
       for (int lcq = 0; lcq < (SPLIT ? NLC : 8); ++lcq) {
         const int chq = chunk0 + lcq * chunk_step;   // SPLIT: static register index lcq; plain: TMEM column chunk
@@ -413,66 +588,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_ld32(taddr + (uint32_t)c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
-        // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to tiles_n*BN on the host.
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cbase + j);
-          float o[4] = {__uint_as_float(v[j]) * p.out_scale + b4.x, __uint_as_float(v[j + 1]) * p.out_scale + b4.y,
-                        __uint_as_float(v[j + 2]) * p.out_scale + b4.z, __uint_as_float(v[j + 3]) * p.out_scale + b4.w};
-          act4(o, p.act1, p.slope1, cbase + j, p.cout);
-          *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-        __syncwarp();
-        // phase 2 (8 lanes = one 128-byte row, 4 rows per instruction): + residual, act2, gate multiply,
-        // ConvGRU blend, optional TF32 rounding, coalesced store
-        const int c = cbase + q8 * 4;
-        if (c < p.cout) {
-#pragma unroll 2
-          for (int it = 0; it < 8; ++it) {
-            const int rr = quarter * 32 + it * 4 + rsub;
-            const int y = ty * TILE_H + rr / TILE_W, x = tx * TILE_W + rr % TILE_W;
-            if (y >= p.H || x >= p.W || n >= p.n_img) continue;
-            const float4 sv = *reinterpret_cast<const float4*>(stg + (it * 4 + rsub) * STG_PITCH + q8 * 4);
-            float o[4] = {sv.x, sv.y, sv.z, sv.w};
-            if (p.res.p) {
-              float t[4]; load4(p.res.p + p.res.off(n, y, x) + c, c, p.cout, t);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) o[u] += t[u];
-            }
-            act4(o, p.act2, p.slope2, c, p.cout);
-            if (p.mul.p) {
-              float t[4]; load4(p.mul.p + p.mul.off(n, y, x) + c, c, p.cout, t);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) o[u] *= t[u];
-            }
-            if (p.gru_z.p) {  // h = (1 - z) * h + z * q   (raft/update.py:58,66)
-              float z[4], h[4];
-              load4(p.gru_z.p + p.gru_z.off(n, y, x) + c, c, p.cout, z);
-              load4(p.gru_h.p + p.gru_h.off(n, y, x) + c, c, p.cout, h);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) o[u] = (1.f - z[u]) * h[u] + z[u] * o[u];
-            }
-            if (p.round_out) {
-              // store TF32-representable values (round-to-nearest-even): the next TF32 layer then truncates
-              // nothing, i.e. its operands are RN- instead of toward-zero-rounded (unbiased)
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                uint32_t bits = __float_as_uint(o[u]);
-                bits += 0xfffu + ((bits >> 13) & 1u);
-                o[u] = __uint_as_float(bits & 0xffffe000u);
-              }
-            }
-            float* optr = p.out.p + p.out.off(n, y, x) + c;
-            if (c + 3 < p.cout && ((reinterpret_cast<uintptr_t>(optr) & 15) == 0)) {
-              *reinterpret_cast<float4*>(optr) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) if (c + u < p.cout) optr[u] = o[u];
-            }
-          }
-        }
-        __syncwarp();
+        epi_chunk(p, v, stg_s, cbase, quarter, lane, tx, ty, n, p.stall ? st_c : nullptr);
       }
+      if (p.stall) st_b += clock64() - t_out0;
       if (!SPLIT) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -487,11 +605,47 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // split unbiased (truncation left a coherent ~2^-20 relative error per product, i.e. ~1e-6*sqrt(K)).
     const int t = threadIdx.x - 32 * (2 + EW);  // 0..127
     int stage = 0; uint32_t phase = 0;
+    if (ATM) {
+      // tensor-memory variant: thread = pixel row of its warp's TMEM lane quarter; hi / lo go to TMEM columns
+      // [256 + 64 * stage, +32) / (+32, +64) and the MMAs take A from there, so the shared-memory port only carries
+      // the TMA fill, one read of A and the weight reads (it is the limiter: 128 B/clk vs 3 MMAs per K step).
+      const int quarter = warp & 3, r = quarter * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256u;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait_t(&full_bar[stage], phase, SPIN, ST_A);
+          const uint8_t* arow = smem + stage * stage_bytes + r * 128;
+          if (!(p.dbg & 1)) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {   // 16-byte chunk (half * 4 + c) of row r sits at chunk ^ (r & 7)  (SWIZZLE_128B)
+                const float4 v = *reinterpret_cast<const float4*>(arow + (((half * 4 + c) ^ (r & 7)) << 4));
+                const float h0 = rn_tf32(v.x), h1 = rn_tf32(v.y), h2 = rn_tf32(v.z), h3 = rn_tf32(v.w);
+                hi[c * 4 + 0] = __float_as_uint(h0); lo[c * 4 + 0] = __float_as_uint(rn_tf32(v.x - h0));
+                hi[c * 4 + 1] = __float_as_uint(h1); lo[c * 4 + 1] = __float_as_uint(rn_tf32(v.y - h1));
+                hi[c * 4 + 2] = __float_as_uint(h2); lo[c * 4 + 2] = __float_as_uint(rn_tf32(v.z - h2));
+                hi[c * 4 + 3] = __float_as_uint(h3); lo[c * 4 + 3] = __float_as_uint(rn_tf32(v.w - h3));
+              }
+              tmem_st16(trow + (uint32_t)(stage * 64 + half * 16), hi);
+              tmem_st16(trow + (uint32_t)(stage * 64 + 32 + half * 16), lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xf_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase, SPIN);
         float4* a = reinterpret_cast<float4*>(smem + stage * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + stage * stage_bytes + A_BYTES);
+        if (!(p.dbg & 1))
 #pragma unroll
         for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
           const float4 v = a[t + i * 128];
@@ -509,6 +663,14 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+  }
+  if (p.stall && lane == 0) {
+    // [0] producer: empty waits  [1] MMA: operand waits  [2] MMA: accumulator waits  [3] epilogue warp 2: tfull waits
+    // [4] epilogue warp 2: output phase  [5] splitter warp: full waits  [6] CTA cycles (MMA warp)
+    unsigned long long* o = p.stall + (size_t)blockIdx.x * 16;
+    if (warp == 1) { o[1] = (unsigned long long)st_a; o[2] = (unsigned long long)st_b; o[6] = (unsigned long long)(clock64() - t_start); }
+    if (warp == 2) { o[3] = (unsigned long long)st_a; o[4] = (unsigned long long)st_b; o[8] = (unsigned long long)st_c[0]; o[9] = (unsigned long long)st_c[1]; o[10] = (unsigned long long)st_c[2]; }
+    if (warp == 2 + EW) o[5] = (unsigned long long)st_a;
   }
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while its peer may still write to it
   if (warp == 1) {
@@ -569,6 +731,20 @@ static void launch_tc(int grid, int threads, int smem, gvStream_t stream, const 
   if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: launch failed: ") + cudaGetErrorString(er));
 }
 
+static int tc_debug() {   // GIMMVFI_TC_DEBUG: timing experiments that break the numerics (never set in production)
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_DEBUG"); v = s ? atoi(s) : 0; }
+  return v;
+}
+static unsigned long long* tc_stall_buf() {   // GIMMVFI_TC_STALL_BUF=<device address of >= 148*16 u64>: scripts/tc_split_probe.py
+  const char* s = getenv("GIMMVFI_TC_STALL_BUF");
+  return s ? reinterpret_cast<unsigned long long*>(strtoull(s, nullptr, 0)) : nullptr;
+}
+static int tc_atmem() {   // GIMMVFI_TC_ATMEM=0: keep the split A operand in shared memory (the first implementation)
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_ATMEM"); v = s ? atoi(s) : 1; }
+  return v;
+}
 static int tc_cluster() {   // GIMMVFI_TC_CLUSTER=1 disables the 2-CTA weight multicast
   static int c = -1;
   if (c < 0) { const char* s = getenv("GIMMVFI_TC_CLUSTER"); c = s ? atoi(s) : 2; if (c != 1 && c != 2) c = 2; }
@@ -581,10 +757,10 @@ static bool tc_epi8() {   // GIMMVFI_TC_EPI8=0 keeps 4 epilogue warps everywhere
   return v != 0;
 }
 
-static bool tc_split_epi8() {   // GIMMVFI_TC_SPLIT_EPI8=0: 4 epilogue/drain warps in the 3xTF32 kernel
+static int tc_split_epi8() {   // GIMMVFI_TC_SPLIT_EPI8: 0 = 4 drain warps in the 3xTF32 kernel, 1 = 4 for K-rich full-width tiles, 2 (default) = always 8
   static int v = -1;
-  if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_EPI8"); v = s ? atoi(s) : 1; }
-  return v != 0;
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_EPI8"); v = s ? atoi(s) : 2; }
+  return v;
 }
 
 static int tc_seg() {
@@ -599,7 +775,7 @@ bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const Con
   if (!w.w_tc || g.stride != 1 || g.reflect) return false;
   if (split && !w.has_lo) return false;
   if (!g.loose_w && (g.ph != w.kh / 2 || g.pw != w.kw / 2)) return false;
-  if (g.loose_w && (g.ph != 0 || g.pw != 0 || w.kw != 1)) return false;
+  if (g.loose_w && (g.ph != 0 || g.pw != 0)) return false;   // pre-padded input: taps index it directly
   if (!al16(in0.p) || in0.ld % 4 || in0.sn % 4) return false;
   if (in1.p && (!al16(in1.p) || in1.ld % 4 || in1.sn % 4 || in0.c % 32)) return false;
   if (!g.loose_w && (in0.h != out.h || in0.w != out.w)) return false;
@@ -641,18 +817,19 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.seg = tc_seg();
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
-  p.spin_limit = spin;
+  p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = split ? tc_atmem() : 0; p.stall = tc_stall_buf();
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2;
   p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
-  const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
+  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * BN * BK * 4) : (A_BYTES + BN * BK * 4);
   const bool ew8 = !split && BN <= 128 && tc_epi8();   // K-poor plain layers are epilogue bound: 8 epilogue warps
   // 3xTF32: 8 drain/epilogue warps help K-poor layers (+20-30 %) but steal issue slots from the splitter warps on
   // K-rich full-width tiles (SepConvGRU gates: -15 %): measured in profiles/r01_tc_microbench_split_epi8.log
-  const bool sew8 = split && tc_epi8() && tc_split_epi8() && !(BN == 128 && taps * (w.cin_pad / 32) >= 48);
+  const bool sew8 = split && tc_epi8() && tc_split_epi8() && (tc_split_epi8() == 2 || !(BN == 128 && taps * (w.cin_pad / 32) >= 48));
   const int stg_bytes = ((ew8 || sew8) ? 8 : 4) * STG_WARP_BYTES;
   const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES;
   p.stages = budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (p.atmem && p.stages > 4) p.stages = 4;   // the TMEM A ring has 4 slots of 64 columns
   if (p.stages < 2) throw std::runtime_error("conv_tc: not enough shared memory for 2 pipeline stages");
   const int smem = p.stages * stage_bytes + stg_bytes + BAR_BYTES + 1024;
   const int padded_tiles = (pix_tiles_host + CL - 1) / CL * CL * tiles_n;
@@ -698,14 +875,15 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale; p.seg = tc_seg();
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
-  p.spin_limit = spin;
+  p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = split ? tc_atmem() : 0; p.stall = tc_stall_buf();
   p.bias = zero_bias; p.act1 = ACT_NONE; p.slope1 = nullptr; p.act2 = ACT_NONE; p.slope2 = nullptr;
   p.out = make_tv(vol, 1, fa.h, fa.w, N, N);
-  const int stage_bytes = (split ? 2 : 1) * (A_BYTES + BN * BK * 4);
+  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * BN * BK * 4) : (A_BYTES + BN * BK * 4);
   const bool e8 = tc_epi8() && (!split || tc_split_epi8());
   const int stg_bytes = (e8 ? 8 : 4) * STG_WARP_BYTES;
   p.stages = (227 * 1024 - 1024 - stg_bytes - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (p.atmem && p.stages > 4) p.stages = 4;
   const int smem = p.stages * stage_bytes + stg_bytes + BAR_BYTES + 1024;
   const int num_tiles = p.tiles_y * p.tiles_x * tiles_n;
   const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;

@@ -126,6 +126,69 @@ void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w
   parallel_for(cx, rows * ho * wo, CorrPoolK{src, dst, h, w, ho, wo}, "corr_pool");
 }
 
+#ifndef GV_HOSTSIM
+// All three pooled levels of one correlation row in one pass: level 0 is read from HBM once, levels 1 and 2 stay in
+// shared memory for their successors (the per-level kernels re-read 1.3x the bytes).  One CTA per row (n, pixel).
+__global__ void __launch_bounds__(256) corr_pyramid_kernel(const float* __restrict__ l0, float* __restrict__ l1, float* __restrict__ l2,
+                                                            float* __restrict__ l3, int64_t rows, int h, int w) {
+  extern __shared__ float sm[];
+  const int h1 = h / 2, w1 = w / 2, h2 = h1 / 2, w2 = w1 / 2, h3 = h2 / 2, w3 = w2 / 2;
+  float* s1 = sm; float* s2 = sm + h1 * w1;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* src = l0 + row * ((int64_t)h * w);
+    float* d1 = l1 + row * ((int64_t)h1 * w1);
+    for (int i = threadIdx.x; i < h1 * w1; i += blockDim.x) {
+      const int y = i / w1, x = i - y * w1;
+      const float* s = src + (int64_t)(2 * y) * w + 2 * x;
+      float2 a, b;
+      if ((w & 1) == 0) { a = __ldcs(reinterpret_cast<const float2*>(s)); b = __ldcs(reinterpret_cast<const float2*>(s + w)); }
+      else { a = make_float2(s[0], s[1]); b = make_float2(s[w], s[w + 1]); }
+      const float v = (a.x + a.y + b.x + b.y) * 0.25f;
+      s1[i] = v; d1[i] = v;
+    }
+    __syncthreads();
+    float* d2 = l2 + row * ((int64_t)h2 * w2);
+    for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) {
+      const int y = i / w2, x = i - y * w2;
+      const float* s = s1 + (2 * y) * w1 + 2 * x;
+      const float v = (s[0] + s[1] + s[w1] + s[w1 + 1]) * 0.25f;
+      s2[i] = v; d2[i] = v;
+    }
+    __syncthreads();
+    float* d3 = l3 + row * ((int64_t)h3 * w3);
+    for (int i = threadIdx.x; i < h3 * w3; i += blockDim.x) {
+      const int y = i / w3, x = i - y * w3;
+      const float* s = s2 + (2 * y) * w2 + 2 * x;
+      d3[i] = (s[0] + s[1] + s[w2] + s[w2 + 1]) * 0.25f;
+    }
+    __syncthreads();   // s1/s2 are rewritten by the next row
+  }
+}
+#endif
+
+// levels 1..3 of the pyramid from level 0 (raft/corr.py:139-142: three successive avg_pool2d(2, 2))
+void corr_pool_pyramid(Ctx& cx, const float* l0, float* l1, float* l2, float* l3, int64_t rows, int h, int w) {
+#ifndef GV_HOSTSIM
+  const int h1 = h / 2, w1 = w / 2, h2 = h1 / 2, w2 = w1 / 2;
+  const size_t smem = ((size_t)h1 * w1 + (size_t)h2 * w2) * sizeof(float);
+  if (smem <= 96 * 1024 && h2 / 2 > 0 && w2 / 2 > 0) {
+    if (cx.dry) return;
+    cx.launches++;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(corr_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    if (cx.prof) cx.prof->begin(cx.stream, "corr_pool_pyramid", (double)rows * h * w);
+    const int64_t grid = rows < (int64_t)cx.sm_count * 8 ? rows : (int64_t)cx.sm_count * 8;
+    corr_pyramid_kernel<<<(unsigned)grid, 256, smem, cx.stream>>>(l0, l1, l2, l3, rows, h, w);
+    gv_check_launch("corr_pool_pyramid");
+    if (cx.prof) cx.prof->end(cx.stream);
+    return;
+  }
+#endif
+  corr_pool(cx, l0, l1, rows, h, w);
+  corr_pool(cx, l1, l2, rows, h / 2, w / 2);
+  corr_pool(cx, l2, l3, rows, h / 4, w / 4);
+}
+
 // ----------------------------------------------------------------- lookup
 // raft/corr.py:144-165.  out channel = lvl*81 + a*9 + b samples level `lvl` of row
 // (n, pixel) at (x/2^lvl + (a-4), y/2^lvl + (b-4)) — the "transposed window" of the

@@ -346,11 +346,22 @@ struct Net {
   // plain conv + activation
   void conv(const std::string& name, const TV& in, const TV& out, int act = ACT_NONE, const float* slope = nullptr, int stride = 1,
             bool reflect = false) {
-    const ConvW& w = W(name); ConvEpi e; e.act1 = act; e.slope1 = slope;
-    conv2d(cx, in, TV(), w, geom(w, stride, reflect), e, out);
+    ConvEpi e; e.act1 = act; e.slope1 = slope;
+    conv_e(name, in, TV(), out, e, stride, reflect);
   }
   void conv_e(const std::string& name, const TV& in0, const TV& in1, const TV& out, const ConvEpi& e, int stride = 1, bool reflect = false) {
     const ConvW& w = W(name);
+    if (reflect && cx.tc && !in1.p && stride == 1 && w.w_tc && in0.ld % 4 == 0) {
+      // the TMA path can only zero-fill: materialise the reflect padding once, then a "valid" conv on the padded buffer
+      Arena& A = cx.arena;
+      const size_t mk = A.mark();
+      TV pad = A.tensor(in0.n, in0.h + 2 * (w.kh / 2), in0.w + 2 * (w.kw / 2), in0.c, (in0.c + 3) & ~3);
+      pad_reflect(cx, in0, pad, w.kh / 2);
+      ConvGeom g; g.stride = 1; g.ph = 0; g.pw = 0; g.loose_w = 1;
+      conv2d(cx, pad, TV(), w, g, e, out);
+      A.release(mk);
+      return;
+    }
     conv2d(cx, in0, in1, w, geom(w, stride, reflect), e, out);
   }
   // 7x7 conv on few channels through the x-packed weights: zero-padded copy of `in`, then a (7 x 1) conv over 7*ldp lanes
@@ -499,7 +510,7 @@ static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, int ten
     corr_volume(cx, F.batch(0, B), F.batch(B, B), P.lvl[0], scale);
     corr_volume(cx, F.batch(B, B), F.batch(0, B), P.lvl[0] + (int64_t)B * P.N * P.N, scale);
   }
-  for (int l = 1; l < 4; ++l) corr_pool(cx, P.lvl[l - 1], P.lvl[l], (int64_t)2 * B * P.N, P.h[l - 1], P.w[l - 1]);
+  corr_pool_pyramid(cx, P.lvl[0], P.lvl[1], P.lvl[2], P.lvl[3], (int64_t)2 * B * P.N, P.h[0], P.w[0]);
   return P;
 }
 

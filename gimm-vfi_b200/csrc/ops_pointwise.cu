@@ -145,6 +145,21 @@ void pad_image4(Ctx& cx, const TV& src, const TV& dst, int pad) {
   parallel_for(cx, dst.pixels() * 4, PadImage4K{src, dst, pad}, "pad_image4");
 }
 
+// reflect-padded copy (padding_mode="reflect"): lets the tensor-core conv, whose TMA can only zero-fill, run the
+// reflect-padded layers (gimmvfi_r.py:94-96,106-108) as a "valid" conv on the padded buffer
+struct PadReflectK {
+  TV src, dst; int pad;
+  GV_HD int refl(int v, int n) const { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    int y = refl(q.y - pad, src.h), x = refl(q.x - pad, src.w);
+    dst.p[dst.off(q.n, q.y, q.x) + q.c] = src.p[src.off(q.n, y, x) + q.c];
+  }
+};
+void pad_reflect(Ctx& cx, const TV& src, const TV& dst, int pad) {
+  parallel_for(cx, dst.pixels() * dst.c, PadReflectK{src, dst, pad}, "pad_reflect");
+}
+
 // zero-padded copy: dst (n, h+2p, w+2p) gets src's channels in its interior, zeros elsewhere (all dst.ld lanes)
 struct PadZeroK {
   TV src, dst; int pad;

@@ -105,6 +105,8 @@ int gimmvfi_op_resize(const gimmvfi_view* src, const gimmvfi_view* dst, float sc
 int gimmvfi_op_corr_volume(const gimmvfi_view* fa, const gimmvfi_view* fb, float* vol, void* stream);
 /* 2x2 average pooling of every row's (h,w) image: raft/corr.py:139-142 */
 int gimmvfi_op_corr_pool(const float* src, float* dst, int64_t rows, int h, int w, void* stream);
+/* levels 1..3 from level 0 in one pass (three successive corr_pool's, raft/corr.py:139-142) */
+int gimmvfi_op_corr_pool_pyramid(const float* l0, float* l1, float* l2, float* l3, int64_t rows, int h, int w, void* stream);
 /* 4-level 9x9 lookup raft/corr.py:144-165: lvl[k] = (n*h*w) x (h_k*w_k) pyramids; out (n,h,w,324) */
 int gimmvfi_op_corr_lookup(const float* const lvl[4], const int32_t lvl_h[4], const int32_t lvl_w[4], const gimmvfi_view* coords,
                            const gimmvfi_view* out, void* stream);

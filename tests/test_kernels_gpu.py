@@ -145,3 +145,24 @@ def test_pixel_shuffle(times):
     for _ in range(times):
         ref = F.pixel_shuffle(ref, 2)
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("h,w", [(16, 20), (34, 60), (17, 31)])
+def test_corr_pool_pyramid_matches_levelwise(h, w):
+    """the fused three-level pooling is bit-identical to three corr_pool passes (raft/corr.py:139-142)"""
+    import ctypes as C
+    lib = K.default_lib()
+    rows = 300
+    l0 = torch.randn(rows, h, w, device="cuda")
+    ref = [l0]
+    hh, ww = h, w
+    for _ in range(3):
+        nxt = torch.empty(rows, hh // 2, ww // 2, device="cuda")
+        lib.check(lib.dll.gimmvfi_op_corr_pool(C.c_void_p(ref[-1].data_ptr()), C.c_void_p(nxt.data_ptr()), rows, hh, ww, K._stream(l0)))
+        ref.append(nxt); hh, ww = hh // 2, ww // 2
+    got = [torch.empty_like(r) for r in ref[1:]]
+    lib.check(lib.dll.gimmvfi_op_corr_pool_pyramid(C.c_void_p(l0.data_ptr()), *[C.c_void_p(g.data_ptr()) for g in got], rows, h, w, K._stream(l0)))
+    torch.cuda.synchronize()
+    for g, r in zip(got, ref[1:]):
+        assert torch.equal(g, r)
+    assert torch.allclose(got[0], torch.nn.functional.avg_pool2d(l0[:, None], 2, 2)[:, 0], atol=1e-6)
