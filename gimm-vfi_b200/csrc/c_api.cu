@@ -171,6 +171,26 @@ int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1, const
 #endif
   })
 }
+int gimmvfi_op_conv2d_tc_f16(const gimmvfi_view* in0, const gimmvfi_view* in1, const void* w_tc_h, const float* w_tc, const float* bias, int cin,
+                             int cout, int kh, int kw, int act1, const float* slope1, const gimmvfi_view* residual, int act2,
+                             const float* slope2, int half_mask, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+#ifdef GV_HOSTSIM
+    throw std::runtime_error("conv2d_tc is a tcgen05 kernel; not available in the host simulation");
+#else
+    Ctx cx = op_ctx(stream);
+    ConvW w; w.b = bias; w.cin = cin; w.cout = cout; w.kh = kh; w.kw = kw; w.w_tc = w_tc; w.has_lo = true;
+    w.cout_pad = tc_cout_pad(cout); w.cin_pad = (cin + 31) & ~31; w.w_tc_h = w_tc_h; w.cin_pad_h = (cin + 63) & ~63;
+    ConvGeom g; g.stride = 1; g.ph = kh / 2; g.pw = kw / 2;
+    TV a0 = to_tv(in0); TV a1 = to_tv(in1); TV r = to_tv(residual); TV o = to_tv(out);
+    a0.f16 = half_mask & 1; if (a1.p) a1.f16 = half_mask & 1; o.f16 = (half_mask >> 1) & 1; if (r.p) r.f16 = (half_mask >> 2) & 1;
+    ConvEpi ep; ep.act1 = act1; ep.slope1 = slope1; ep.res = r; ep.act2 = act2; ep.slope2 = slope2;
+    if (!conv2d_tc_supported(a0, a1, w, g, ep, o, false)) throw std::runtime_error("conv2d_tc_f16: unsupported configuration");
+    conv2d_tc(cx, a0, a1, w, g, ep, o, false);
+#endif
+  })
+}
 int64_t gimmvfi_instnorm_scratch_floats(int n, int c) {
   TV t; t.n = n; t.c = c;
   return instnorm_scratch_floats(t) + (int64_t)n * c * 2;

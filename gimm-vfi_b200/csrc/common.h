@@ -41,9 +41,11 @@ struct TV {
   int n = 0, h = 0, w = 0, c = 0;
   int ld = 0;
   int64_t sn = 0;
+  int f16 = 0;   // 1: elements are IEEE half (p is reinterpreted); only the tensor-core conv reads / writes such tensors
   GV_HD int64_t off(int in, int y, int x) const { return (int64_t)in * sn + ((int64_t)y * w + x) * ld; }
-  TV slice(int c0, int cnt) const { TV t = *this; t.p = p + c0; t.c = cnt; return t; }
-  TV batch(int n0, int cnt) const { TV t = *this; t.p = p + (int64_t)n0 * sn; t.n = cnt; return t; }
+  float* at(int64_t elem) const { return f16 ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(p) + elem) : p + elem; }
+  TV slice(int c0, int cnt) const { TV t = *this; t.p = at(c0); t.c = cnt; return t; }
+  TV batch(int n0, int cnt) const { TV t = *this; t.p = at((int64_t)n0 * sn); t.n = cnt; return t; }
   int64_t pixels() const { return (int64_t)n * h * w; }
 };
 
@@ -76,6 +78,9 @@ struct ConvW {
   const float* w_tc = nullptr;
   int cout_pad = 0, cin_pad = 0;
   bool has_lo = false;
+  // fp16 copy for layers fed with half-precision activations: w_tc_h[tap][cout_pad][cin_pad_h] (cin padded to 64)
+  const void* w_tc_h = nullptr;
+  int cin_pad_h = 0;
 };
 
 // N tiling of the tensor-core path: cout padded to 16, split into <= 256-wide tiles of equal width.
@@ -122,6 +127,11 @@ struct Arena {
     return reinterpret_cast<float*>(base + o);
   }
   TV tensor(int n, int h, int w, int c, int ld = 0) { if (!ld) ld = c; return make_tv(alloc_f((size_t)n * h * w * ld), n, h, w, c, ld); }
+  TV tensor_h(int n, int h, int w, int c, int ld = 0) {   // half-precision storage (ld % 8 == 0: 16-byte TMA strides)
+    if (!ld) ld = (c + 7) & ~7;
+    TV t = make_tv(alloc_f(((size_t)n * h * w * ld + 1) / 2), n, h, w, c, ld); t.f16 = 1; return t;
+  }
+  TV tensor_like(const TV& x, int c) { return x.f16 ? tensor_h(x.n, x.h, x.w, c) : tensor(x.n, x.h, x.w, c); }
   size_t mark() const { return top; }
   void release(size_t m) { top = m; }
 };

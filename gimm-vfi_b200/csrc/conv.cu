@@ -161,7 +161,9 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
     if (((eh != out.h || ew != out.w) && !g.loose_w) || in0.n != out.n) throw std::runtime_error("conv2d: output geometry mismatch");
   }
 #ifndef GV_HOSTSIM
-  if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out, cx.tc_split)) { conv2d_tc(cx, in0, in1, w, g, e, out, cx.tc_split); return; }
+  const bool any_f16 = in0.f16 || in1.f16 || out.f16 || e.res.f16;
+  if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out, cx.tc_split && !any_f16)) { conv2d_tc(cx, in0, in1, w, g, e, out, cx.tc_split && !any_f16); return; }
+  if (any_f16) throw std::runtime_error("conv2d: half-precision tensors are only handled by the tensor-core path (layer not eligible)");
 #endif
   cx.launches++;
 #ifdef GV_HOSTSIM

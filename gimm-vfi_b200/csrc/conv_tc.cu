@@ -25,6 +25,7 @@
 
 #ifndef GV_HOSTSIM
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace gv {
 
@@ -48,6 +49,8 @@ struct Params {
   int spin_limit;                  // mbarrier try_wait attempts before trapping (0 = wait forever)
   int dbg;                         // timing experiments only (GIMMVFI_TC_DEBUG): 1 = splitter idles, 2 = segment drain skips its TMEM loads
   unsigned long long* stall;       // stall profiling (GIMMVFI_TC_STALL_BUF): 16 counters per CTA, else nullptr
+  int f16_in;                      // A / B operands are IEEE half (kind::f16, 64-element K blocks); else fp32 read as TF32
+  int bk;                          // K elements per 128-byte smem row: 32 (tf32) or 64 (f16)
   int atmem;                       // SPLIT: A_hi / A_lo live in tensor memory (written by the splitter warps), not in smem
   int seg;                         // SPLIT: K steps accumulated in TMEM before promotion to fp32 registers
   float out_scale;                 // accumulator scale applied before the bias (all-pairs correlation: 1/sqrt(C))
@@ -157,6 +160,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
 // A operand read from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -233,6 +246,48 @@ __device__ __forceinline__ void load4(const float* p, int c, int cout, float* r)
     for (int u = 0; u < 4; ++u) r[u] = (c + u < cout) ? p[u] : 0.f;
   }
 }
+// 4 consecutive values -> 4 halves (round-to-nearest-even, saturating at +-65504 so a stray large activation cannot become inf)
+__device__ __forceinline__ uint2 pack_h4(const float* o) {
+  const float lim = 65504.f;
+  const __half2 a = __floats2half2_rn(fminf(fmaxf(o[0], -lim), lim), fminf(fmaxf(o[1], -lim), lim));
+  const __half2 b = __floats2half2_rn(fminf(fmaxf(o[2], -lim), lim), fminf(fmaxf(o[3], -lim), lim));
+  uint2 r; r.x = *reinterpret_cast<const uint32_t*>(&a); r.y = *reinterpret_cast<const uint32_t*>(&b);
+  return r;
+}
+// store 4 channels (first channel c) of an fp32 or half tensor at element offset eoff
+__device__ __forceinline__ void store4(const TV& t, int64_t eoff, const float* o, int c, int cout, bool vec) {
+  if (t.f16) {
+    __half* q = reinterpret_cast<__half*>(t.p) + eoff;
+    if (vec) { *reinterpret_cast<uint2*>(q) = pack_h4(o); }
+    else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (c + u < cout) q[u] = __float2half_rn(fminf(fmaxf(o[u], -65504.f), 65504.f));
+    }
+  } else {
+    float* q = t.p + eoff;
+    if (vec) { *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]); }
+    else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (c + u < cout) q[u] = o[u];
+    }
+  }
+}
+// 4 channels of an fp32 or half side tensor (residual) at element offset eoff
+__device__ __forceinline__ void load4_any(const TV& t, int64_t eoff, int c, int cout, float* r) {
+  if (t.f16) {
+    const __half* q = reinterpret_cast<const __half*>(t.p) + eoff;
+    if (c + 3 < cout && ((reinterpret_cast<uintptr_t>(q) & 7) == 0)) {
+      const uint2 v = *reinterpret_cast<const uint2*>(q);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+      r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = (c + u < cout) ? __half2float(q[u]) : 0.f;
+    }
+  } else {
+    load4(t.p + eoff, c, cout, r);
+  }
+}
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
@@ -304,9 +359,10 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
     const uint32_t sbase = stg_s + (uint32_t)((rsub * STG_PITCH + q8 * 4) * 4);
     const bool lean = !p.res.p && !p.mul.p && !p.gru_z.p;
     const int64_t opix0 = (int64_t)y0 * p.W + x0;
-    float* const obase = p.out.p + (int64_t)n * p.out.sn + opix0 * p.out.ld + c;
+    const int64_t obase = (int64_t)n * p.out.sn + opix0 * p.out.ld + c;    // element offset of (row 0 of this lane, channel c)
     const int64_t o_row = (int64_t)p.W * p.out.ld, o_x = (int64_t)4 * p.out.ld;
-    const bool ovec = full4 && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0) && (p.out.ld % 4 == 0);
+    const uintptr_t oaddr = reinterpret_cast<uintptr_t>(p.out.p) + (uintptr_t)obase * (p.out.f16 ? 2 : 4);
+    const bool ovec = full4 && ((oaddr & (p.out.f16 ? 7 : 15)) == 0) && (p.out.ld % 4 == 0);
     if (lean) {
       float o[32];
 #pragma unroll
@@ -328,13 +384,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
       for (int it = 0; it < 8; ++it) {
         const int yy = it >> 2, xx = (it & 3) * 4;
         if (!interior && (y0 + yy >= p.H || x0 + xx >= p.W)) continue;
-        float* optr = obase + yy * o_row + (it & 3) * o_x;
-        if (ovec) {
-          *reinterpret_cast<float4*>(optr) = make_float4(o[4 * it], o[4 * it + 1], o[4 * it + 2], o[4 * it + 3]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) if (c + u < p.cout) optr[u] = o[4 * it + u];
-        }
+        store4(p.out, obase + yy * o_row + (it & 3) * o_x, o + 4 * it, c, p.cout, ovec);
       }
     } else {
 #pragma unroll 2
@@ -345,7 +395,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
         const float4 sv = lds128(sbase + (uint32_t)(it * 4 * STG_PITCH * 4));
         float o[4] = {sv.x, sv.y, sv.z, sv.w};
         if (p.res.p) {
-          float t[4]; load4(p.res.p + p.res.off(n, y, x) + c, c, p.cout, t);
+          float t[4]; load4_any(p.res, p.res.off(n, y, x) + c, c, p.cout, t);
 #pragma unroll
           for (int u = 0; u < 4; ++u) o[u] += t[u];
         }
@@ -366,13 +416,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
 #pragma unroll
           for (int u = 0; u < 4; ++u) o[u] = rn_tf32(o[u]);
         }
-        float* optr = obase + yy * o_row + (it & 3) * o_x;
-        if (ovec) {
-          *reinterpret_cast<float4*>(optr) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) if (c + u < p.cout) optr[u] = o[u];
-        }
+        store4(p.out, obase + yy * o_row + (it & 3) * o_x, o, c, p.cout, ovec);
       }
     }
   }
@@ -460,16 +504,16 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint8_t* a_dst = smem + stage * stage_bytes;
             uint8_t* b_dst = a_dst + a_all;
             mbar_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + (SPLIT ? 2 * b_bytes : b_bytes)));
-            if (kb < p.c0_blocks) tma_load_4d(a_dst, &tmA0, &full_bar[stage], kb * BK, x0, y0, n);
-            else tma_load_4d(a_dst, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * BK, x0, y0, n);
+            if (kb < p.c0_blocks) tma_load_4d(a_dst, &tmA0, &full_bar[stage], kb * p.bk, x0, y0, n);
+            else tma_load_4d(a_dst, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * p.bk, x0, y0, n);
             if (CL == 1) {
-              tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * BK, nt * p.BN, tap);
-              if (SPLIT) tma_load_3d(b_dst + b_bytes, &tmB, &full_bar[stage], kb * BK, nt * p.BN, tap + p.taps);
+              tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * p.bk, nt * p.BN, tap);
+              if (SPLIT) tma_load_3d(b_dst + b_bytes, &tmB, &full_bar[stage], kb * p.bk, nt * p.BN, tap + p.taps);
             } else {  // tmB's box is BN/CL rows: my slice of the weight tile, delivered to every CTA of the cluster
               const int rows = p.BN / CL, roff = (int)cta_rank * rows;
-              tma_load_3d_mc(b_dst + roff * 128, &tmB, &full_bar[stage], kb * BK, nt * p.BN + roff, tap, (uint16_t)((1u << CL) - 1));
+              tma_load_3d_mc(b_dst + roff * 128, &tmB, &full_bar[stage], kb * p.bk, nt * p.BN + roff, tap, (uint16_t)((1u << CL) - 1));
               if (SPLIT)
-                tma_load_3d_mc(b_dst + b_bytes + roff * 128, &tmB, &full_bar[stage], kb * BK, nt * p.BN + roff, tap + p.taps, (uint16_t)((1u << CL) - 1));
+                tma_load_3d_mc(b_dst + b_bytes + roff * 128, &tmB, &full_bar[stage], kb * p.bk, nt * p.BN + roff, tap + p.taps, (uint16_t)((1u << CL) - 1));
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -480,7 +524,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3, M>>4
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // (kind::f16: a/b format 0 = F16, K = 16 per instruction = the same 32 bytes of every smem row)
+    const uint32_t idesc = (1u << 4) | ((p.f16_in ? 0u : 2u) << 7) | ((p.f16_in ? 0u : 2u) << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -516,6 +561,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               mma_tf32(d_tmem, adesc + ko, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);   // A_hi * B_lo
               mma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
               mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, 1u);                               // A_hi * B_hi
+            } else if (p.f16_in) {
+              mma_f16(d_tmem, adesc + ko, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
             } else {
               mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
             }
@@ -695,9 +742,10 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+static void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                   bool f16 = false) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  CUresult r = encode_fn()(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("conv_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
@@ -705,9 +753,10 @@ static void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
 
 static void encode_act(CUtensorMap* m, const TV& t) {
   cuuint64_t dims[4] = {(cuuint64_t)t.c, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
-  cuuint64_t str[3] = {(cuuint64_t)t.ld * 4, (cuuint64_t)t.w * t.ld * 4, (cuuint64_t)t.sn * 4};
-  cuuint32_t box[4] = {BK, TILE_W, TILE_H, 1};
-  encode(m, t.p, 4, dims, str, box);
+  const cuuint64_t es = t.f16 ? 2 : 4;
+  cuuint64_t str[3] = {(cuuint64_t)t.ld * es, (cuuint64_t)t.w * t.ld * es, (cuuint64_t)t.sn * es};
+  cuuint32_t box[4] = {(cuuint32_t)(t.f16 ? 2 * BK : BK), TILE_W, TILE_H, 1};   // 128-byte rows either way
+  encode(m, t.p, 4, dims, str, box, t.f16 != 0);
 }
 
 }  // namespace tc
@@ -771,13 +820,17 @@ static int tc_seg() {
 
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  (void)e;
   if (!w.w_tc || g.stride != 1 || g.reflect) return false;
   if (split && !w.has_lo) return false;
   if (!g.loose_w && (g.ph != w.kh / 2 || g.pw != w.kw / 2)) return false;
   if (g.loose_w && (g.ph != 0 || g.pw != 0)) return false;   // pre-padded input: taps index it directly
-  if (!al16(in0.p) || in0.ld % 4 || in0.sn % 4) return false;
-  if (in1.p && (!al16(in1.p) || in1.ld % 4 || in1.sn % 4 || in0.c % 32)) return false;
+  const bool h = in0.f16 != 0;                                 // half activations: kind::f16, 64-channel K blocks
+  const int amul = h ? 8 : 4, kblk = h ? 64 : 32;              // 16-byte TMA strides
+  if (h && (split || !w.w_tc_h)) return false;
+  if (in1.p && (in1.f16 != 0) != h) return false;
+  if (e.mul.f16 || e.gru_z.f16 || e.gru_h.f16) return false;   // only the residual may be half
+  if (!al16(in0.p) || in0.ld % amul || in0.sn % amul) return false;
+  if (in1.p && (!al16(in1.p) || in1.ld % amul || in1.sn % amul || in0.c % kblk)) return false;
   if (!g.loose_w && (in0.h != out.h || in0.w != out.w)) return false;
   return true;
 }
@@ -800,7 +853,14 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   // 2-CTA clusters pay off when there are at least two pixel tiles per SM; BN/2 must keep the 8-row swizzle atom
   const int CL = (tc_cluster() == 2 && pix_tiles_host >= 2 * cx.sm_count && BN % 16 == 0) ? 2 : 1;
   const int taps = w.kh * w.kw;
-  {
+  const bool f16 = in0.f16 != 0;
+  const int bk = f16 ? 2 * BK : BK, cin_pad = f16 ? w.cin_pad_h : w.cin_pad;
+  if (f16) {
+    cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)taps};
+    cuuint64_t str[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * w.cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(BN / CL), 1};
+    encode(&mB, w.w_tc_h, 3, dims, str, box, true);
+  } else {
     cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)(taps * (w.has_lo ? 2 : 1))};
     cuuint64_t str[2] = {(cuuint64_t)w.cin_pad * 4, (cuuint64_t)w.cin_pad * w.cout_pad * 4};
     cuuint32_t box[3] = {BK, (cuuint32_t)(BN / CL), 1};   // CL == 2: each CTA fetches half of the weight rows
@@ -808,11 +868,12 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   }
   Params p;
   p.taps = taps; p.kw = w.kw; p.ph = g.ph; p.pw = g.pw;
-  p.c0_blocks = in1.p ? in0.c / 32 : (in0.c + 31) / 32;
-  p.kblocks = w.cin_pad / 32;
+  p.f16_in = f16 ? 1 : 0; p.bk = bk;
+  p.c0_blocks = in1.p ? in0.c / bk : (in0.c + bk - 1) / bk;
+  p.kblocks = cin_pad / bk;
   p.tiles_x = (out.w + TILE_W - 1) / TILE_W; p.tiles_y = (out.h + TILE_H - 1) / TILE_H; p.n_img = out.n; p.tiles_n = tiles_n;
   p.H = out.h; p.W = out.w; p.BN = BN; p.cout = w.cout;
-  p.round_out = split ? 0 : 1;
+  p.round_out = (split || out.f16) ? 0 : 1;   // (a half store already rounds to 10 mantissa bits)
   p.out_scale = 1.f;
   p.seg = tc_seg();
   static int spin = -1;
@@ -838,7 +899,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   cx.launches++;
   if (cx.prof) {
     char nm[128];
-    snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? "3xtf32" : "tf32", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
+    snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? "3xtf32" : (f16 ? "f16" : "tf32"), w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
   }
   if (split && sew8) { if (CL == 2) launch_tc<true, 2, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p); }
@@ -870,7 +931,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   }
   Params p;
   p.taps = 1; p.kw = 1; p.ph = 0; p.pw = 0;
-  p.kblocks = C / 32; p.c0_blocks = p.kblocks;
+  p.kblocks = C / 32; p.c0_blocks = p.kblocks; p.f16_in = 0; p.bk = BK;
   p.tiles_x = (fa.w + TILE_W - 1) / TILE_W; p.tiles_y = (fa.h + TILE_H - 1) / TILE_H; p.n_img = 1; p.tiles_n = tiles_n;
   p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale; p.seg = tc_seg();
   static int spin = -1;

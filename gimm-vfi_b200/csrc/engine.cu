@@ -162,6 +162,8 @@ ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float ou
   ConvW c;
   c.w = upload(pw); c.b = upload(pb); c.cin = cin; c.cout = cout; c.kh = kh; c.kw = kw; c.cout_ld = cout_ld;
   pack_tc(c, pw);
+  // layers of the final decoder's residual trunk read half-precision activations in precision mode 3 (run())
+  if (name.rfind("amt_final_decoder.convblock.", 0) == 0 && name.rfind("amt_final_decoder.convblock.0", 0) != 0) pack_tc_f16(c, pw);
   conv_[name] = c;
   return c;
 }
@@ -191,6 +193,43 @@ void Engine::pack_tc(ConvW& c, const std::vector<float>& pw) {
         t[o] = hi; t[plane + o] = tf32_rn(w - hi);
       }
   c.w_tc = upload(t); c.cout_pad = cout_pad; c.cin_pad = cin_pad; c.has_lo = true;
+}
+
+// IEEE binary16 with round-to-nearest-even and saturation to +-65504 (host side, bit exact with cvt.rn.satfinite.f16.f32)
+static uint16_t f32_to_f16_rn(float f) {
+  uint32_t u; std::memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  u &= 0x7fffffffu;
+  if (u > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);                 // NaN
+  if (u >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);                // >= 65520 (or inf): saturate
+  if (u < 0x33000001u) return sign;                                       // < 2^-25: rounds to zero
+  if (u < 0x38800000u) {                                                  // subnormal half
+    const int shift = 113 - (int)(u >> 23);                               // 1..24
+    uint32_t m = (u & 0x7fffffu) | 0x800000u;
+    const uint32_t lsb = 1u << (shift + 13), half = lsb >> 1;
+    uint32_t q = m >> (shift + 13);
+    const uint32_t rem = m & (lsb - 1);
+    if (rem > half || (rem == half && (q & 1u))) ++q;
+    return (uint16_t)(sign | q);
+  }
+  uint32_t e = (u >> 23) - 112, m = u & 0x7fffffu;
+  uint32_t h = (e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return (uint16_t)(sign | h);
+}
+
+// [tap][cin][cout_ld] fp32 -> [tap][cout_pad][cin_pad_h] fp16 (K-major rows of 64-element / 128-byte K blocks): the
+// B operand of the kind::f16 tensor-core path for layers whose activations are stored in half precision
+void Engine::pack_tc_f16(ConvW& c, const std::vector<float>& pw) {
+  const int cout_pad = tc_cout_pad(c.cout), cin_pad = (c.cin + 63) & ~63, taps = c.kh * c.kw;
+  std::vector<float> t(((size_t)taps * cout_pad * cin_pad + 1) / 2, 0.f);
+  uint16_t* h = reinterpret_cast<uint16_t*>(t.data());
+  for (int tp = 0; tp < taps; ++tp)
+    for (int ci = 0; ci < c.cin; ++ci)
+      for (int co = 0; co < c.cout; ++co)
+        h[((size_t)tp * cout_pad + co) * cin_pad + ci] = f32_to_f16_rn(pw[((size_t)tp * c.cin + ci) * c.cout_ld + co]);
+  c.w_tc_h = upload(t); c.cin_pad_h = cin_pad;
 }
 
 // RAFT stem (7x7, stride 2, cin 3) with the x-taps packed into the channel axis: on a zero-padded image with
@@ -552,7 +591,7 @@ static void amt_update(Net& N, const std::string& p, bool low, const TV& ft, con
 static void resblock(Net& N, const std::string& q, const TV& x, int C, int S) {
   Ctx& cx = N.cx; Arena& A = cx.arena;
   const size_t mk = A.mark();
-  TV a = A.tensor(x.n, x.h, x.w, C), b = A.tensor(x.n, x.h, x.w, C), s1 = A.tensor(x.n, x.h, x.w, S), s2 = A.tensor(x.n, x.h, x.w, S);
+  TV a = A.tensor_like(x, C), b = A.tensor_like(x, C), s1 = A.tensor_like(x, S), s2 = A.tensor_like(x, S);
   N.convrelu(q + ".conv1", x, a);
   N.convrelu(q + ".conv2", a.slice(C - S, S), s1);
   { ConvEpi e; e.act1 = ACT_PRELU; e.slope1 = N.V(q + ".conv3.1.weight"); N.conv_e(q + ".conv3.0", a.slice(0, C - S), s1, b, e); }
@@ -874,7 +913,9 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       copy_channels(cx, s1, fin1.slice(264, 3));
       backwarp(cx, s0, fl0, fin1.slice(267, 3));
       backwarp(cx, s1, fl1, fin1.slice(270, 3));
-      TV x1 = A.tensor(B, H, W, 256);
+      // precision mode 3: the 256-channel residual trunk (9 of the 10 heaviest launches) is stored in fp16 and runs on the
+      // kind::f16 tensor-core path (same 10-bit mantissa as TF32, half the bytes per operand, twice the MMA rate)
+      TV x1 = (cx.tc && tc_mode_ >= 3) ? A.tensor_h(B, H, W, 256) : A.tensor(B, H, W, 256);
       N.convrelu("amt_final_decoder.convblock.0", fin1, x1);
       for (int k = 1; k <= 3; ++k) resblock(N, "amt_final_decoder.convblock." + std::to_string(k), x1, 256, 64);
       TV o24 = A.tensor(B, H, W, 24);

@@ -75,6 +75,7 @@ class Engine {
   bool finalized_ = false, debug_ = false, profile_ = false;
   int tc_mode_ = 0;
   void pack_tc(ConvW& c, const std::vector<float>& packed);
+  void pack_tc_f16(ConvW& c, const std::vector<float>& packed);
   void pack_stem(const std::string& name, const std::string& bn);
   void pack_xpacked(const std::string& name, int ldp);
   Profiler prof_;

@@ -63,9 +63,10 @@ class GIMMVFI_R(nn.Module):
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_weights_dirty", True))
         self.aux_outputs = True  # False: skip the auxiliary outputs (only imgt_pred is produced)
         # 0: fp32 CUDA cores everywhere; 1: post-RAFT convolutions on tcgen05 TF32 (RAFT on CUDA cores);
-        # 2 (default): additionally RAFT + correlation on tcgen05 with 3xTF32 operand splitting and register-promoted
-        # accumulation (fp32-class accuracy).  All three meet max|d imgt_pred| <= 1e-3 vs the reference.
-        self.tensor_cores = 2
+        # 2: additionally RAFT + correlation on tcgen05 with 3xTF32 operand splitting and register-promoted accumulation
+        # (fp32-class accuracy); 3 (default): additionally the final decoder's 256-channel residual trunk stored in fp16
+        # and run on kind::f16 MMAs (same 10-bit mantissa as TF32).  All modes meet max|d imgt_pred| <= 1e-3 vs the reference.
+        self.tensor_cores = 3
 
     def _container(self, key: str):
         parts = key.split(".")

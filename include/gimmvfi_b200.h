@@ -121,6 +121,14 @@ int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1_or_nul
                          int cout, int kh, int kw, int act1, const float* slope1, const gimmvfi_view* residual_or_null, int act2,
                          const float* slope2, const gimmvfi_view* mul_or_null, const gimmvfi_view* gru_z_or_null,
                          const gimmvfi_view* gru_h_or_null, int split, const gimmvfi_view* out, void* stream);
+/* the same kernel with half-precision storage (precision mode 3: the final decoder's residual trunk, fi_components.py:97-154,
+ * 299-305).  half_mask: bit 0 = in0/in1 hold IEEE half (kind::f16 MMAs; weights = w_tc_h [kh*kw][cout_pad][cin_pad64] half),
+ * bit 1 = out is half, bit 2 = residual is half; views of half tensors give strides in ELEMENTS.  With bit 0 clear the operands are
+ * fp32/TF32 (w_tc as above) and only the store / residual formats change. */
+int gimmvfi_op_conv2d_tc_f16(const gimmvfi_view* in0, const gimmvfi_view* in1_or_null, const void* w_tc_h, const float* w_tc,
+                             const float* bias, int cin, int cout, int kh, int kw, int act1, const float* slope1,
+                             const gimmvfi_view* residual_or_null, int act2, const float* slope2, int half_mask,
+                             const gimmvfi_view* out, void* stream);
 /* nn.InstanceNorm2d + optional relu: raft/extractor.py:133-134; scratch >= gimmvfi_instnorm_scratch_floats */
 int64_t gimmvfi_instnorm_scratch_floats(int n, int c);
 int gimmvfi_op_instnorm(const gimmvfi_view* x, int relu, float* scratch, const gimmvfi_view* out, void* stream);

@@ -23,7 +23,7 @@ with torch.no_grad():
     ref = O.gimmvfi_r_forward(sd, xs, [(O.sample_coord_input(1, (H, W), [0.5]), None)], [0.5 * torch.ones(1)])
 print("oracle %dx%d on %d threads: %.1f s" % (H, W, torch.get_num_threads(), time.time() - t0), flush=True)
 coord = [(model.sample_coord_input(1, (H, W), [0.5], device=dev), None)]
-for mode in (0, 1, 2):
+for mode in [int(m) for m in os.environ.get("PARITY_MODES", "0,1,2,3").split(",")]:
     model.tensor_cores = mode
     out = model(xs.to(dev), coord, t=[0.5 * torch.ones(1, device=dev)])
     torch.cuda.synchronize()

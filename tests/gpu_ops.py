@@ -171,3 +171,30 @@ def conv2d_tc(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2=N
                                       V(mul), V(gru_z), V(gru_h), int(split), C.byref(view_of(out)), _stream(out))
     lib.check(rc)
     return out
+
+
+def pack_weight_tc_f16(w):  # (cout,cin,kh,kw) -> [kh*kw][cout_pad][cin_pad64] half (RN)
+    cout, cin, kh, kw = w.shape
+    cp, kp = tc_cout_pad(cout), (cin + 63) // 64 * 64
+    p = torch.zeros(kh * kw, cp, kp, device=w.device, dtype=torch.float16)
+    p[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).half()
+    return p.contiguous()
+
+
+def conv2d_tc_f16(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2=None, x1_nhwc=None, out_half=True, lib=None):
+    """x (and x1, residual) may be torch.float16 NHWC tensors: half operands run on kind::f16; fp32 x on TF32"""
+    lib = lib or default_lib()
+    cout, cin, kh, kw = w.shape
+    in_half = x_nhwc.dtype == torch.float16
+    pw_h = pack_weight_tc_f16(w)
+    pw = pack_weight_tc(w)
+    bb = torch.zeros((tc_cout_pad(cout) + 31) // 32 * 32 + 128, device=w.device)
+    bb[:cout] = b
+    n, h, wd, _ = x_nhwc.shape
+    out = torch.empty(n, h, wd, cout, device=w.device, dtype=torch.float16 if out_half else torch.float32)
+    mask = (1 if in_half else 0) | (2 if out_half else 0) | (4 if (residual is not None and residual.dtype == torch.float16) else 0)
+    V = lambda t: C.byref(view_of(t)) if t is not None else None
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    lib.check(lib.dll.gimmvfi_op_conv2d_tc_f16(V(x_nhwc), V(x1_nhwc), P(pw_h), P(pw), P(bb), cin, cout, kh, kw, act1, P(slope1), V(residual), act2,
+                                               P(slope2), mask, V(out), _stream(out)))
+    return out

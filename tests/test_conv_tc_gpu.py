@@ -180,3 +180,69 @@ def test_conv2d_tc_cluster_multicast(case):
     err = (got - ref).abs().max().item()
     print("cluster case", case, "err %.3e" % err)
     assert err <= tol
+
+
+F16_CASES = [
+    # cin, cout, k, H, W, n
+    (64, 64, 1, 8, 16, 1),        # one tile, one 64-channel K block
+    (256, 256, 3, 24, 40, 1),     # the residual trunk's dominant shape (N = 256)
+    (64, 64, 3, 20, 28, 2),       # side conv, ragged tiles
+    (256, 24, 3, 16, 32, 1),      # trunk -> 24 output channels (fp32 out in the network)
+]
+
+
+@pytest.mark.parametrize("case", F16_CASES)
+@pytest.mark.parametrize("out_half", [True, False])
+def test_conv2d_tc_f16_operands(case, out_half):
+    """kind::f16 path (precision mode 3): half activations and weights, fp32 accumulation.  Strict reference = fp64
+    convolution of the SAME half-rounded operands; the only differences are accumulation order and the output rounding."""
+    cin, cout, k, H, W, n = case
+    x = rnd(n, cin, H, W, seed=1)
+    w = rnd(cout, cin, k, k, seed=2, scale=1.0 / (cin * k * k) ** 0.5)
+    b = rnd(cout, seed=3, scale=0.1)
+    slope = 0.25 + 0.1 * rnd(cout, seed=4)
+    xh = K.nhwc(x).half()
+    got = K.conv2d_tc_f16(xh, w, b, 3, slope, out_half=out_half)
+    assert got.dtype == (torch.float16 if out_half else torch.float32)
+    ref = F.prelu(F.conv2d(x.half().double(), w.half().double(), b.double(), padding=k // 2), slope.double()).float()
+    err = (K.nchw(got.float()) - ref).abs().max().item()
+    tol = 1e-3 * max(1.0, ref.abs().max().item())   # half store, or fp32 store rounded to TF32 for the next layer: 2^-11 relative
+    print("f16 case", case, out_half, "err %.3e" % err, "ref absmax %.3e" % ref.abs().max().item())
+    assert err <= tol
+
+
+def test_conv2d_tc_f16_resblock_tail():
+    """two half input segments (192 + 64 channels), half residual, PReLU after the add, half output: conv5 of
+    ResBlock(256, 64) (fi_components.py:139-154) as the engine runs it in precision mode 3"""
+    n, H, W = 1, 24, 40
+    a = rnd(n, 192, H, W, seed=1); s2 = rnd(n, 64, H, W, seed=2); res = rnd(n, 256, H, W, seed=3)
+    w = rnd(256, 256, 3, 3, seed=4, scale=1.0 / (256 * 9) ** 0.5)
+    b = rnd(256, seed=5, scale=0.1)
+    slope = 0.25 + 0.1 * rnd(256, seed=6)
+    ah, sh, rh = K.nhwc(a).half(), K.nhwc(s2).half(), K.nhwc(res).half()
+    got = K.conv2d_tc_f16(ah, w, b, 0, None, residual=rh, act2=3, slope2=slope, x1_nhwc=sh, out_half=True)
+    xin = torch.cat([a.half().double(), s2.half().double()], 1)
+    ref = F.prelu(F.conv2d(xin, w.half().double(), b.double(), padding=1) + res.half().double(), slope.double()).float()
+    err = (K.nchw(got.float()) - ref).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_conv2d_tc_tf32_in_half_out():
+    """fp32 / TF32 operands with a half-precision store: convblock.0 (273 -> 256) feeding the half trunk"""
+    n, cin, cout, H, W = 1, 273, 256, 16, 24
+    x = rnd(n, cin, H, W, seed=1)
+    w = rnd(cout, cin, 3, 3, seed=2, scale=1.0 / (cin * 9) ** 0.5)
+    b = rnd(cout, seed=3, scale=0.1)
+    slope = 0.25 + 0.1 * rnd(cout, seed=4)
+    pad = torch.zeros(n, H, W, 276, device=DEV); pad[..., :cin] = K.nhwc(x)
+    lib = K.default_lib()
+    import ctypes as C
+    pw, pwh = K.pack_weight_tc(w), K.pack_weight_tc_f16(w)
+    bb = torch.zeros(512, device=DEV); bb[:cout] = b
+    out = torch.empty(n, H, W, cout, device=DEV, dtype=torch.float16)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    lib.check(lib.dll.gimmvfi_op_conv2d_tc_f16(C.byref(K.view_of(pad, channels=cin)), None, P(pwh), P(pw), P(bb), cin, cout, 3, 3, 3, P(slope), None, 0,
+                                               None, 2, C.byref(K.view_of(out)), K._stream(out)))
+    ref = F.prelu(F.conv2d(K.tf32_trunc(x).double(), K.tf32_rn(w).double(), b.double(), padding=1), slope.double()).float()
+    err = (K.nchw(out.float()) - ref).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item())
