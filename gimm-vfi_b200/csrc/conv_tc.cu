@@ -115,6 +115,58 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: one MMA of M = 256 spans the two SMs of a cluster; operands and barriers of the
+// peer CTA are addressed through the shared::cluster window
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of one CTA of the pair that signal the LEADER's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool f16) {
+  if (f16)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -320,6 +372,12 @@ __device__ __forceinline__ void act_n(float* o, int act, const float* slope, int
 #pragma unroll
       for (int u = 0; u < N; ++u) { const float sl = (c + u < cout) ? slope[c + u] : 0.f; o[u] = o[u] > 0.f ? o[u] : sl * o[u]; }
     }
+  } else if (act == ACT_SIGMOID) {   // 1 / (1 + 2^(-x log2 e)): MUFU.EX2 + MUFU.RCP, ~2 ulp (inline: the SepConvGRU gates)
+#pragma unroll
+    for (int u = 0; u < N; ++u) o[u] = __fdividef(1.f, 1.f + exp2f(-1.4426950408889634f * o[u]));
+  } else if (act == ACT_TANH) {      // 1 - 2 / (1 + e^(2x)); absolute error ~1e-7 (saturates correctly at +-1)
+#pragma unroll
+    for (int u = 0; u < N; ++u) o[u] = 1.f - __fdividef(2.f, 1.f + exp2f(2.8853900817779268f * o[u]));
   } else {
 #pragma unroll
     for (int u = 0; u < N; ++u) o[u] = act_slow(o[u], act);
@@ -431,14 +489,19 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
 // EW = epilogue warps (4 or 8).  With K-poor layers (1x1 convs, correlation, 32/64 channels) the epilogue, not the
 // MMA, is the critical path and one warp per SM sub-partition is instruction-latency bound: EW == 8 puts two warps
 // on every TMEM lane quarter, alternating over the 32-column chunks.
-template <bool SPLIT, int CL, int EW>
+// PAIR (CL == 2, !SPLIT): the two CTAs of the cluster issue ONE tcgen05.mma.cta_group::2 of M = 256 (rows 0-127 = the
+// leader's pixel tile, 128-255 = the peer's); each CTA holds its own A tile and HALF of the weight tile, so every SM's
+// shared memory carries 2/3 of the bytes per MMA of the single-CTA form (whose limiter it is: 128 B/clk).  Only the
+// leader (cluster rank 0) issues MMAs; both CTAs' TMA loads signal the leader's full barrier, the MMA commits are
+// multicast to both CTAs' empty / accumulator-full barriers, and the peer's epilogue releases accumulators remotely.
+template <bool SPLIT, int CL, int EW, bool PAIR = false>
 __global__ void __launch_bounds__(64 + 32 * EW + (SPLIT ? 128 : 0), 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: per stage [A 16 KB | (A_lo 16 KB) | B BN*128 B | (B_lo)], then the epilogue staging area, then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.BN * BK * 4;
+  const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * BK * 4;   // PAIR: this CTA's half of the weight rows
   const bool ATM = SPLIT && p.atmem;   // TMEM columns: accumulators at 0 / 128, A ring (64 columns per stage) from 256
   const int a_all = (SPLIT && !ATM) ? 2 * A_BYTES : A_BYTES;
   const uint32_t acc_stride = ATM ? 128u : 256u;
@@ -473,14 +536,19 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); mbar_init(&xf_bar[s], 4); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EW); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PAIR ? 2 : 1); mbar_init(&empty_bar[s], PAIR ? 1 : CL); mbar_init(&xf_bar[s], 4); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * EW : EW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     // 512 columns: two 256-column fp32 accumulators (1 CTA / SM, so the whole TMEM is ours)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // barriers initialised cluster-wide before any remote arrive
@@ -503,6 +571,15 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait_t(&empty_bar[stage], phase ^ 1, SPIN, ST_A);
             uint8_t* a_dst = smem + stage * stage_bytes;
             uint8_t* b_dst = a_dst + a_all;
+            if (PAIR) {   // both CTAs' bytes are counted by the leader's barrier (2 arrivals + 2 x (A + B/2) bytes)
+              const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0u);
+              mbar_expect_tx_cluster(lead_full, (uint32_t)(A_BYTES + b_bytes));
+              if (kb < p.c0_blocks) tma_load_4d_2sm(a_dst, &tmA0, lead_full, kb * p.bk, x0, y0, n);
+              else tma_load_4d_2sm(a_dst, &tmA1, lead_full, (kb - p.c0_blocks) * p.bk, x0, y0, n);
+              tma_load_3d_2sm(b_dst, &tmB, lead_full, kb * p.bk, nt * p.BN + (int)cta_rank * (p.BN / 2), tap);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + (SPLIT ? 2 * b_bytes : b_bytes)));
             if (kb < p.c0_blocks) tma_load_4d(a_dst, &tmA0, &full_bar[stage], kb * p.bk, x0, y0, n);
             else tma_load_4d(a_dst, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * p.bk, x0, y0, n);
@@ -525,10 +602,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ===================================================== MMA issuer
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3, M>>4
     // (kind::f16: a/b format 0 = F16, K = 16 per instruction = the same 32 bytes of every smem row)
-    const uint32_t idesc = (1u << 4) | ((p.f16_in ? 0u : 2u) << 7) | ((p.f16_in ? 0u : 2u) << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((p.f16_in ? 0u : 2u) << 7) | ((p.f16_in ? 0u : 2u) << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                           ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < ((PAIR && cta_rank != 0) ? 0 : num_tiles); tile += gridDim.x) {
       // plain: one TMEM accumulator per tile.  SPLIT: the K loop is cut into segments; every segment
       // (p.seg K steps) starts a fresh accumulator (alternating buffers) that the epilogue warps drain into fp32 registers.
       // The tensor core's accumulator add truncates; short chains + a true fp32 sum across segments keep the
@@ -561,15 +639,22 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               mma_tf32(d_tmem, adesc + ko, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);   // A_hi * B_lo
               mma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
               mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, 1u);                               // A_hi * B_hi
+            } else if (PAIR) {
+              mma_2sm(d_tmem, adesc + ko, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u, p.f16_in != 0);
             } else if (p.f16_in) {
               mma_f16(d_tmem, adesc + ko, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
             } else {
               mma_tf32(d_tmem, adesc + ko, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
             }
           }
-          if (CL == 1) mma_commit(&empty_bar[stage]);    // frees the smem slot when these MMAs retire
-          else mma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // ... in every CTA that shares the weight tile
-          if (seg_end) mma_commit(&tfull_bar[acc]);      // accumulator (segment) complete
+          if (PAIR) {
+            mma_commit_2sm(&empty_bar[stage], (uint16_t)3);                      // both CTAs' producers
+            if (seg_end) mma_commit_2sm(&tfull_bar[acc], (uint16_t)3);           // both CTAs' epilogues
+          } else {
+            if (CL == 1) mma_commit(&empty_bar[stage]);    // frees the smem slot when these MMAs retire
+            else mma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // ... in every CTA that shares the weight tile
+            if (seg_end) mma_commit(&tfull_bar[acc]);      // accumulator (segment) complete
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -641,7 +726,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (!SPLIT) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0u));   // the leader's MMA warp waits for both epilogues
+          else mbar_arrive(&tempty_bar[acc]);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -721,7 +809,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while its peer may still write to it
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -762,12 +851,12 @@ static void encode_act(CUtensorMap* m, const TV& t) {
 }  // namespace tc
 
 // launch with an optional (2,1,1) thread-block cluster
-template <bool SPLIT, int CL, int EW>
+template <bool SPLIT, int CL, int EW, bool PAIR = false>
 static void launch_tc(int grid, int threads, int smem, gvStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                       const tc::Params& p) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(tc::conv2d_tc_kernel<SPLIT, CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t er = cudaFuncSetAttribute(tc::conv2d_tc_kernel<SPLIT, CL, EW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
     attr_set = true;
   }
@@ -776,7 +865,7 @@ static void launch_tc(int grid, int threads, int smem, gvStream_t stream, const 
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t er = cudaLaunchKernelEx(&cfg, tc::conv2d_tc_kernel<SPLIT, CL, EW>, a0, a1, b, p);
+  cudaError_t er = cudaLaunchKernelEx(&cfg, tc::conv2d_tc_kernel<SPLIT, CL, EW, PAIR>, a0, a1, b, p);
   if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: launch failed: ") + cudaGetErrorString(er));
 }
 
@@ -792,6 +881,11 @@ static unsigned long long* tc_stall_buf() {   // GIMMVFI_TC_STALL_BUF=<device ad
 static int tc_atmem() {   // GIMMVFI_TC_ATMEM=0: keep the split A operand in shared memory (the first implementation)
   static int v = -1;
   if (v < 0) { const char* s = getenv("GIMMVFI_TC_ATMEM"); v = s ? atoi(s) : 1; }
+  return v;
+}
+static int tc_pair() {   // GIMMVFI_TC_PAIR=0: keep single-CTA MMAs (+ weight multicast) instead of cta_group::2 CTA pairs
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_PAIR"); v = s ? atoi(s) : 1; }
   return v;
 }
 static int tc_cluster() {   // GIMMVFI_TC_CLUSTER=1 disables the 2-CTA weight multicast
@@ -881,7 +975,8 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = split ? tc_atmem() : 0; p.stall = tc_stall_buf();
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2;
   p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
-  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * BN * BK * 4) : (A_BYTES + BN * BK * 4);
+  const bool pair = !split && CL == 2 && tc_pair() && BN % 32 == 0;   // N/2 rows per CTA must keep the 8-row swizzle atom (and N % 16)
+  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * BN * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4);
   const bool ew8 = !split && BN <= 128 && tc_epi8();   // K-poor plain layers are epilogue bound: 8 epilogue warps
   // 3xTF32: 8 drain/epilogue warps help K-poor layers (+20-30 %) but steal issue slots from the splitter warps on
   // K-rich full-width tiles (SepConvGRU gates: -15 %): measured in profiles/r01_tc_microbench_split_epi8.log
@@ -904,8 +999,15 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   }
   if (split && sew8) { if (CL == 2) launch_tc<true, 2, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p); }
   else if (split) { if (CL == 2) launch_tc<true, 2, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
-  else if (ew8) { if (CL == 2) launch_tc<false, 2, 8>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<false, 1, 8>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
-  else { if (CL == 2) launch_tc<false, 2, 4>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<false, 1, 4>(grid, 192, smem, cx.stream, mA0, mA1, mB, p); }
+  else if (ew8) {
+    if (pair) launch_tc<false, 2, 8, true>(grid, 320, smem, cx.stream, mA0, mA1, mB, p);
+    else if (CL == 2) launch_tc<false, 2, 8>(grid, 320, smem, cx.stream, mA0, mA1, mB, p);
+    else launch_tc<false, 1, 8>(grid, 320, smem, cx.stream, mA0, mA1, mB, p);
+  } else {
+    if (pair) launch_tc<false, 2, 4, true>(grid, 192, smem, cx.stream, mA0, mA1, mB, p);
+    else if (CL == 2) launch_tc<false, 2, 4>(grid, 192, smem, cx.stream, mA0, mA1, mB, p);
+    else launch_tc<false, 1, 4>(grid, 192, smem, cx.stream, mA0, mA1, mB, p);
+  }
   gv_check_launch("conv2d_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }

@@ -5,7 +5,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SHAPES = [(384, 128, 1, 5, 136, 240, 2), (256, 192, 3, 3, 136, 240, 2), (128, 256, 3, 3, 136, 240, 2), (64, 64, 3, 3, 544, 960, 2)]
+BIG = [(256, 256, 3, 3, 1088, 1920, 1), (32, 32, 3, 3, 1088, 1920, 2)]
+SHAPES = ([] if os.environ.get("PROBE_BIG") else [(384, 128, 1, 5, 136, 240, 2), (256, 192, 3, 3, 136, 240, 2), (128, 256, 3, 3, 136, 240, 2), (64, 64, 3, 3, 544, 960, 2)]) + (BIG if os.environ.get("PROBE_BIG") else [])
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import ctypes as C
@@ -20,7 +21,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     if stall is not None:
         os.environ["GIMMVFI_TC_STALL_BUF"] = str(stall.data_ptr())
     for (cin, cout, kh, kw, H, W, n) in SHAPES:
-        for split in (0, 1):
+        for split in ((0,) if os.environ.get("PROBE_BIG") else (0, 1)):
             x = torch.randn(n, H, W, cin, device="cuda")
             w = torch.randn(cout, cin, kh, kw, device="cuda") / (cin * kh * kw) ** 0.5
             pw = K.pack_weight_tc(w)
@@ -49,7 +50,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(" | ".join(res), flush=True)
     sys.exit(0)
 
-KNOBS = [{}, {"PROBE_STALL": "1"}, {"PROBE_STALL": "1", "GIMMVFI_TC_SPLIT_EPI8": "1"}] + [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[1:]]
+KNOBS = [{"PROBE_BIG": "1", "PROBE_STALL": "1"}, {"PROBE_BIG": "1", "PROBE_STALL": "1", "GIMMVFI_TC_PAIR": "0"}] + [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[1:]]
 for kn in KNOBS:
     env = dict(os.environ); env.update(kn)
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
