@@ -445,36 +445,66 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
         store4(p.out, obase + yy * o_row + (it & 3) * o_x, o + 4 * it, c, p.cout, ovec);
       }
     } else {
-#pragma unroll 2
-      for (int it = 0; it < 8; ++it) {
-        const int yy = it >> 2, xx = (it & 3) * 4;
-        const int y = y0 + yy, x = x0 + xx;
-        if (!interior && (y >= p.H || x >= p.W)) continue;
-        const float4 sv = lds128(sbase + (uint32_t)(it * 4 * STG_PITCH * 4));
-        float o[4] = {sv.x, sv.y, sv.z, sv.w};
-        if (p.res.p) {
-          float t[4]; load4_any(p.res, p.res.off(n, y, x) + c, c, p.cout, t);
+      // side tensors (residual / gate / GRU state): two groups of 4 rows, every global load of a group issued before its
+      // first use (one warp's epilogue is latency bound: the 2-row loop this replaces took 2x the main loop at N = 256)
+      const int64_t rbase = p.res.p ? p.res.off(n, y0, x0) + c : 0, mbase = p.mul.p ? p.mul.off(n, y0, x0) + c : 0;
+      const int64_t zbase = p.gru_z.p ? p.gru_z.off(n, y0, x0) + c : 0, hbase = p.gru_z.p ? p.gru_h.off(n, y0, x0) + c : 0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) o[u] += t[u];
+      for (int g = 0; g < 2; ++g) {
+        float o[16];
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ok[j] = interior || (y0 + g < p.H && x0 + j * 4 < p.W);
+          const float4 sv = lds128(sbase + (uint32_t)((g * 4 + j) * 4 * STG_PITCH * 4));
+          o[4 * j] = sv.x; o[4 * j + 1] = sv.y; o[4 * j + 2] = sv.z; o[4 * j + 3] = sv.w;
         }
-        act_n<4>(o, p.act2, p.slope2, c, p.cout);
-        if (p.mul.p) {
-          float t[4]; load4(p.mul.p + p.mul.off(n, y, x) + c, c, p.cout, t);
+        if (p.res.p) {
+          float t[16];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) o[u] *= t[u];
+          for (int j = 0; j < 4; ++j) {
+            if (ok[j]) load4_any(p.res, rbase + (int64_t)g * p.res.w * p.res.ld + (int64_t)j * 4 * p.res.ld, c, p.cout, t + 4 * j);
+            else { t[4 * j] = t[4 * j + 1] = t[4 * j + 2] = t[4 * j + 3] = 0.f; }
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) o[u] += t[u];
+        }
+        if (p.act2 != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) act_n<4>(o + 4 * j, p.act2, p.slope2, c, p.cout);
+        }
+        if (p.mul.p) {
+          float t[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (ok[j]) load4(p.mul.p + mbase + (int64_t)g * p.mul.w * p.mul.ld + (int64_t)j * 4 * p.mul.ld, c, p.cout, t + 4 * j);
+            else { t[4 * j] = t[4 * j + 1] = t[4 * j + 2] = t[4 * j + 3] = 0.f; }
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) o[u] *= t[u];
         }
         if (p.gru_z.p) {  // h = (1 - z) * h + z * q   (raft/update.py:58,66)
-          float z[4], h[4];
-          load4(p.gru_z.p + p.gru_z.off(n, y, x) + c, c, p.cout, z);
-          load4(p.gru_h.p + p.gru_h.off(n, y, x) + c, c, p.cout, h);
+          float z[16], hh[16];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) o[u] = (1.f - z[u]) * h[u] + z[u] * o[u];
+          for (int j = 0; j < 4; ++j) {
+            if (ok[j]) {
+              load4(p.gru_z.p + zbase + (int64_t)g * p.gru_z.w * p.gru_z.ld + (int64_t)j * 4 * p.gru_z.ld, c, p.cout, z + 4 * j);
+              load4(p.gru_h.p + hbase + (int64_t)g * p.gru_h.w * p.gru_h.ld + (int64_t)j * 4 * p.gru_h.ld, c, p.cout, hh + 4 * j);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { z[4 * j + u] = 0.f; hh[4 * j + u] = 0.f; }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) o[u] = (1.f - z[u]) * hh[u] + z[u] * o[u];
         }
         if (p.round_out) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) o[u] = rn_tf32(o[u]);
+          for (int u = 0; u < 16; ++u) o[u] = rn_tf32(o[u]);
         }
-        store4(p.out, obase + yy * o_row + (it & 3) * o_x, o, c, p.cout, ovec);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ok[j]) store4(p.out, obase + g * o_row + j * o_x, o + 4 * j, c, p.cout, ovec);
       }
     }
   }
@@ -977,7 +1007,11 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
   const bool pair = !split && CL == 2 && tc_pair() && BN % 32 == 0;   // N/2 rows per CTA must keep the 8-row swizzle atom (and N % 16)
   const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * BN * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4);
-  const bool ew8 = !split && BN <= 128 && tc_epi8();   // K-poor plain layers are epilogue bound: 8 epilogue warps
+  static int ew8_wide = -1;   // GIMMVFI_TC_EPI8_WIDE=0: 4 epilogue warps for N > 128 tiles of CTA pairs
+  if (ew8_wide < 0) { const char* q = getenv("GIMMVFI_TC_EPI8_WIDE"); ew8_wide = q ? atoi(q) : 1; }
+  // K-poor plain layers are epilogue bound: 8 epilogue warps.  CTA pairs halve the per-stage smem footprint, which leaves room
+  // for the 8-warp staging area next to >= 5 stages even at N = 256 (where the f16 trunk's epilogue is as long as its main loop)
+  const bool ew8 = !split && (BN <= 128 || (pair && ew8_wide)) && tc_epi8();
   // 3xTF32: 8 drain/epilogue warps help K-poor layers (+20-30 %) but steal issue slots from the splitter warps on
   // K-rich full-width tiles (SepConvGRU gates: -15 %): measured in profiles/r01_tc_microbench_split_epi8.log
   const bool sew8 = split && tc_epi8() && tc_split_epi8() && (tc_split_epi8() == 2 || !(BN == 128 && taps * (w.cin_pad / 32) >= 48));

@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIG = [(256, 256, 3, 3, 1088, 1920, 1), (32, 32, 3, 3, 1088, 1920, 2)]
+BIG = [(256, 256, 3, 3, 1088, 1920, 1), (64, 64, 3, 3, 1088, 1920, 1)]
 SHAPES = ([] if os.environ.get("PROBE_BIG") else [(384, 128, 1, 5, 136, 240, 2), (256, 192, 3, 3, 136, 240, 2), (128, 256, 3, 3, 136, 240, 2), (64, 64, 3, 3, 544, 960, 2)]) + (BIG if os.environ.get("PROBE_BIG") else [])
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -22,14 +22,21 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         os.environ["GIMMVFI_TC_STALL_BUF"] = str(stall.data_ptr())
     for (cin, cout, kh, kw, H, W, n) in SHAPES:
         for split in ((0,) if os.environ.get("PROBE_BIG") else (0, 1)):
+            f16 = bool(os.environ.get("PROBE_F16"))
             x = torch.randn(n, H, W, cin, device="cuda")
             w = torch.randn(cout, cin, kh, kw, device="cuda") / (cin * kh * kw) ** 0.5
             pw = K.pack_weight_tc(w)
             out = torch.empty(n, H, W, cout, device="cuda")
+            if f16:
+                x = x.half(); out = out.half(); pwh = K.pack_weight_tc_f16(w)
             bb = torch.zeros((cout + 31) // 32 * 32 + 256, device="cuda")
             s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
             def call():
+                if f16:
+                    lib.check(lib.dll.gimmvfi_op_conv2d_tc_f16(C.byref(view_of(x)), None, C.c_void_p(pwh.data_ptr()), C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()),
+                                                               cin, cout, kh, kw, 0, None, None, 0, None, 3, C.byref(view_of(out)), s))
+                    return
                 lib.check(lib.dll.gimmvfi_op_conv2d_tc(C.byref(view_of(x)), None, C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()), cin, cout, kh, kw,
                                                        0, None, None, 0, None, None, None, None, split, C.byref(view_of(out)), s))
             for _ in range(3):
@@ -50,7 +57,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(" | ".join(res), flush=True)
     sys.exit(0)
 
-KNOBS = [{"PROBE_BIG": "1", "PROBE_STALL": "1"}, {"PROBE_BIG": "1", "PROBE_STALL": "1", "GIMMVFI_TC_PAIR": "0"}] + [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[1:]]
+KNOBS = [{"PROBE_BIG": "1", "PROBE_STALL": "1", "PROBE_F16": "1"}, {"PROBE_BIG": "1", "PROBE_STALL": "1", "PROBE_F16": "1", "GIMMVFI_TC_EPI8_WIDE": "0"},
+         {"PROBE_BIG": "1", "PROBE_STALL": "1", "PROBE_F16": "1", "GIMMVFI_TC_PAIR": "0"}, {"PROBE_BIG": "1", "PROBE_STALL": "1"}] + [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[1:]]
 for kn in KNOBS:
     env = dict(os.environ); env.update(kn)
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
