@@ -383,10 +383,58 @@ __device__ __forceinline__ void act_n(float* o, int act, const float* slope, int
     for (int u = 0; u < N; ++u) o[u] = act_slow(o[u], act);
   }
 }
+// the same activation on R rows of 4 channels that all start at channel c (phase 2 of the epilogue): per-channel slopes
+// are fetched once, not once per row
+template <int R>
+__device__ __forceinline__ void act_rows(float* o, int act, const float* slope, int c, int cout) {
+  if (act == ACT_PRELU) {
+    float sl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sl[u] = (c + u < cout) ? __ldg(slope + c + u) : 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) o[4 * r + u] = o[4 * r + u] > 0.f ? o[4 * r + u] : sl[u] * o[4 * r + u];
+  } else {
+    act_n<4 * R>(o, act, slope, c, cout);   // (channel-independent activations)
+  }
+}
+// Residual values of one chunk, fetched one chunk ahead of their use (8 rows x 4 channels per lane, raw bits: 16 B per row
+// for fp32, 8 B for half).  A lane whose 4 channels are ragged or misaligned reports false and loads in place later.
+__device__ __forceinline__ bool res_prefetch(const Params& p, int cbase, int quarter, int lane, int tx, int ty, int n, uint4* rp) {
+  const int q8 = lane & 7, rsub = lane >> 3;
+  const int c = cbase + q8 * 4;
+  if (!p.res.p || c + 3 >= p.cout || n >= p.n_img || (p.res.ld & 3)) return false;
+  const int y0 = ty * TILE_H + quarter * 2, x0 = tx * TILE_W + rsub;
+  const int64_t base = p.res.off(n, y0, x0) + c;
+  const char* q = reinterpret_cast<const char*>(p.res.p) + base * (p.res.f16 ? 2 : 4);
+  if (reinterpret_cast<uintptr_t>(q) & (p.res.f16 ? 7 : 15)) return false;
+  const int64_t rowb = (int64_t)p.res.w * p.res.ld * (p.res.f16 ? 2 : 4), xb = (int64_t)4 * p.res.ld * (p.res.f16 ? 2 : 4);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int yy = it >> 2, xx = (it & 3) * 4;
+    rp[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (y0 + yy < p.H && x0 + xx < p.W) {
+      const char* a = q + yy * rowb + (it & 3) * xb;
+      if (p.res.f16) { const uint2 t = *reinterpret_cast<const uint2*>(a); rp[it].x = t.x; rp[it].y = t.y; }
+      else rp[it] = *reinterpret_cast<const uint4*>(a);
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void res_unpack(const Params& p, const uint4& r, float* t) {
+  if (p.res.f16) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    t[0] = a.x; t[1] = a.y; t[2] = b.x; t[3] = b.y;
+  } else {
+    t[0] = __uint_as_float(r.x); t[1] = __uint_as_float(r.y); t[2] = __uint_as_float(r.z); t[3] = __uint_as_float(r.w);
+  }
+}
 // One 32-row x 32-column chunk of the output tile: v[j] = accumulator of (this thread's pixel row, column c0 + j).
 // stg_s = shared-window address of this warp's 32 x STG_PITCH staging area; cbase = first output channel of the chunk.
 __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, uint32_t stg_s, int cbase, int quarter, int lane, int tx, int ty,
-                                          int n, long long* tprof /* stall profiling: [0] phase 1, [1] phase 2, [2] chunks */) {
+                                          int n, long long* tprof /* stall profiling: [0] phase 1, [1] phase 2, [2] chunks */,
+                                          const uint4* rp = nullptr /* res_prefetch() of this chunk */, bool rp_valid = false) {
   const int q8 = lane & 7, rsub = lane >> 3;
   const long long tp0 = tprof ? clock64() : 0;
   // phase 1 (thread = pixel row): bias + act1, stage to smem.  bias is padded to tiles_n*BN (+slack) on the host.
@@ -428,10 +476,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
         const float4 sv = lds128(sbase + (uint32_t)(it * 4 * STG_PITCH * 4));
         o[4 * it] = sv.x; o[4 * it + 1] = sv.y; o[4 * it + 2] = sv.z; o[4 * it + 3] = sv.w;
       }
-      if (p.act2 != ACT_NONE) {
-#pragma unroll
-        for (int it = 0; it < 8; ++it) act_n<4>(o + 4 * it, p.act2, p.slope2, c, p.cout);
-      }
+      if (p.act2 != ACT_NONE) act_rows<8>(o, p.act2, p.slope2, c, p.cout);
       if (p.round_out) {
         // store TF32-representable values (round-to-nearest-even): the next TF32 layer then truncates
         // nothing, i.e. its operands are RN- instead of toward-zero-rounded (unbiased)
@@ -463,16 +508,14 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
           float t[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (ok[j]) load4_any(p.res, rbase + (int64_t)g * p.res.w * p.res.ld + (int64_t)j * 4 * p.res.ld, c, p.cout, t + 4 * j);
+            if (rp_valid) res_unpack(p, rp[g * 4 + j], t + 4 * j);
+            else if (ok[j]) load4_any(p.res, rbase + (int64_t)g * p.res.w * p.res.ld + (int64_t)j * 4 * p.res.ld, c, p.cout, t + 4 * j);
             else { t[4 * j] = t[4 * j + 1] = t[4 * j + 2] = t[4 * j + 3] = 0.f; }
           }
 #pragma unroll
           for (int u = 0; u < 16; ++u) o[u] += t[u];
         }
-        if (p.act2 != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) act_n<4>(o + 4 * j, p.act2, p.slope2, c, p.cout);
-        }
+        if (p.act2 != ACT_NONE) act_rows<4>(o, p.act2, p.slope2, c, p.cout);
         if (p.mul.p) {
           float t[16];
 #pragma unroll
@@ -705,6 +748,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
       constexpr int NLC = SPLIT ? 4 / (EW / 4) : 1;   // 32-column chunks owned by this warp in SPLIT mode (4, or 2 with EW == 8)
       float racc[SPLIT ? 32 * NLC : 1];   // SPLIT: fp32 register accumulators (BN <= 128), summed across K segments
+      uint4 rp_cur[SPLIT ? 1 : 8], rp_nxt[SPLIT ? 1 : 8];   // plain: residual of the current / next chunk (res_prefetch)
+      bool rp_ok = false, rp_ok_nxt = false;
       if (SPLIT) {
 #pragma unroll
         for (int i = 0; i < (SPLIT ? 32 * NLC : 1); ++i) racc[i] = 0.f;
@@ -730,6 +775,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       } else {
+        // the residual of this warp's first chunk is requested before the accumulator is even complete
+        if (p.res.p) rp_ok = res_prefetch(p, nt * p.BN + chunk0 * 32, quarter, lane, tx, ty, n, rp_cur);
         mbar_wait_t(&tfull_bar[acc], acc_phase, SPIN, ST_A);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
@@ -748,9 +795,18 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(racc[(SPLIT ? lcq * 32 : 0) + (SPLIT ? j : 0)]);
         } else {
           tmem_ld32(taddr + (uint32_t)c0, v);
+          if (p.res.p) {   // next chunk's residual: in flight during this chunk's phases
+            const int c0n = (chq + chunk_step) * 32;
+            rp_ok_nxt = (c0n < p.BN && nt * p.BN + c0n < p.cout) ? res_prefetch(p, nt * p.BN + c0n, quarter, lane, tx, ty, n, rp_nxt) : false;
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
-        epi_chunk(p, v, stg_s, cbase, quarter, lane, tx, ty, n, p.stall ? st_c : nullptr);
+        epi_chunk(p, v, stg_s, cbase, quarter, lane, tx, ty, n, p.stall ? st_c : nullptr, SPLIT ? nullptr : rp_cur, SPLIT ? false : rp_ok);
+        if (!SPLIT && p.res.p) {
+#pragma unroll
+          for (int i = 0; i < (SPLIT ? 1 : 8); ++i) rp_cur[i] = rp_nxt[i];
+          rp_ok = rp_ok_nxt;
+        }
       }
       if (p.stall) st_b += clock64() - t_out0;
       if (!SPLIT) {
