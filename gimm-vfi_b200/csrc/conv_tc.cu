@@ -233,6 +233,16 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
+__device__ __forceinline__ void mma_tf32_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -609,7 +619,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PAIR ? 2 : 1); mbar_init(&empty_bar[s], PAIR ? 1 : CL); mbar_init(&xf_bar[s], 4); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], (PAIR && !SPLIT) ? 2 : 1); mbar_init(&empty_bar[s], PAIR ? 1 : CL); mbar_init(&xf_bar[s], (PAIR && SPLIT) ? 10 : 4); }
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * EW : EW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -644,12 +654,26 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait_t(&empty_bar[stage], phase ^ 1, SPIN, ST_A);
             uint8_t* a_dst = smem + stage * stage_bytes;
             uint8_t* b_dst = a_dst + a_all;
-            if (PAIR) {   // both CTAs' bytes are counted by the leader's barrier (2 arrivals + 2 x (A + B/2) bytes)
+            if (PAIR && !SPLIT) {   // both CTAs' bytes are counted by the leader's barrier (2 arrivals + 2 x (A + B/2) bytes)
               const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0u);
               mbar_expect_tx_cluster(lead_full, (uint32_t)(A_BYTES + b_bytes));
               if (kb < p.c0_blocks) tma_load_4d_2sm(a_dst, &tmA0, lead_full, kb * p.bk, x0, y0, n);
               else tma_load_4d_2sm(a_dst, &tmA1, lead_full, (kb - p.c0_blocks) * p.bk, x0, y0, n);
               tma_load_3d_2sm(b_dst, &tmB, lead_full, kb * p.bk, nt * p.BN + (int)cta_rank * (p.BN / 2), tap);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
+            if (PAIR && SPLIT) {
+              // A feeds this CTA's own splitter warps (local barrier); the two weight-plane halves are operands of the leader's
+              // MMAs: their bytes are counted by the LEADER's xf barrier, next to the 8 splitter-warp arrivals of both CTAs
+              mbar_expect_tx(&full_bar[stage], (uint32_t)A_BYTES);
+              if (kb < p.c0_blocks) tma_load_4d(a_dst, &tmA0, &full_bar[stage], kb * p.bk, x0, y0, n);
+              else tma_load_4d(a_dst, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * p.bk, x0, y0, n);
+              const uint32_t lead_xf = mapa_shared(smem_u32(&xf_bar[stage]), 0u);
+              mbar_expect_tx_cluster(lead_xf, (uint32_t)(2 * b_bytes));
+              const int row0 = nt * p.BN + (int)cta_rank * (p.BN / 2);
+              tma_load_3d_2sm(b_dst, &tmB, lead_xf, kb * p.bk, row0, tap);
+              tma_load_3d_2sm(b_dst + b_bytes, &tmB, lead_xf, kb * p.bk, row0, tap + p.taps);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
               continue;
             }
@@ -703,7 +727,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 B -> +2 in the (addr >> 4) field
             const uint64_t ko = (uint64_t)(k * 2);
-            if (ATM) {
+            if (ATM && PAIR) {
+              const uint32_t ahi_t = tmem_base + 256u + (uint32_t)(stage * 64 + k * 8), alo_t = ahi_t + 32u;
+              mma_tf32_ts_2sm(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
+              mma_tf32_ts_2sm(d_tmem, alo_t, bdesc + ko, idesc, 1u);
+              mma_tf32_ts_2sm(d_tmem, ahi_t, bdesc + ko, idesc, 1u);
+            } else if (ATM) {
               const uint32_t ahi_t = tmem_base + 256u + (uint32_t)(stage * 64 + k * 8), alo_t = ahi_t + 32u;
               mma_tf32_ts(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);     // A_hi * B_lo
               mma_tf32_ts(d_tmem, alo_t, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
@@ -771,7 +800,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0u));
+            else mbar_arrive(&tempty_bar[acc]);
+          }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       } else {
@@ -856,7 +888,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&xf_bar[stage]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&xf_bar[stage]), 0u));   // the leader's MMA consumes both CTAs' A rows
+            else mbar_arrive(&xf_bar[stage]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -969,9 +1004,10 @@ static int tc_atmem() {   // GIMMVFI_TC_ATMEM=0: keep the split A operand in sha
   if (v < 0) { const char* s = getenv("GIMMVFI_TC_ATMEM"); v = s ? atoi(s) : 1; }
   return v;
 }
-static int tc_pair() {   // GIMMVFI_TC_PAIR=0: keep single-CTA MMAs (+ weight multicast) instead of cta_group::2 CTA pairs
+static int tc_pair() {   // GIMMVFI_TC_PAIR: 0 = single-CTA MMAs (+ weight multicast) everywhere; 1 = cta_group::2 CTA pairs in the plain / f16 kernel;
+                         // 2 (default) = also in the 3xTF32 kernel
   static int v = -1;
-  if (v < 0) { const char* s = getenv("GIMMVFI_TC_PAIR"); v = s ? atoi(s) : 1; }
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_PAIR"); v = s ? atoi(s) : 2; }
   return v;
 }
 static int tc_cluster() {   // GIMMVFI_TC_CLUSTER=1 disables the 2-CTA weight multicast
@@ -1061,16 +1097,17 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = split ? tc_atmem() : 0; p.stall = tc_stall_buf();
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2;
   p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
-  const bool pair = !split && CL == 2 && tc_pair() && BN % 32 == 0;   // N/2 rows per CTA must keep the 8-row swizzle atom (and N % 16)
-  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * BN * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4);
+  // 3xTF32: 8 drain/epilogue warps help K-poor layers (+20-30 %) but steal issue slots from the splitter warps on
+  // K-rich full-width tiles (SepConvGRU gates: -15 %): measured in profiles/r01_tc_microbench_split_epi8.log
+  const bool sew8 = split && tc_epi8() && tc_split_epi8() && (tc_split_epi8() == 2 || !(BN == 128 && taps * (w.cin_pad / 32) >= 48));
+  // CTA pairs: N/2 rows per CTA must keep the 8-row swizzle atom (and N % 16); the 3xTF32 kernel pairs only in its TMEM-A, 8-drain-warp form
+  const bool pair = CL == 2 && BN % 32 == 0 && (split ? (tc_pair() >= 2 && p.atmem && sew8) : (tc_pair() != 0));
+  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * (pair ? BN / 2 : BN) * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4);
   static int ew8_wide = -1;   // GIMMVFI_TC_EPI8_WIDE=0: 4 epilogue warps for N > 128 tiles of CTA pairs
   if (ew8_wide < 0) { const char* q = getenv("GIMMVFI_TC_EPI8_WIDE"); ew8_wide = q ? atoi(q) : 1; }
   // K-poor plain layers are epilogue bound: 8 epilogue warps.  CTA pairs halve the per-stage smem footprint, which leaves room
   // for the 8-warp staging area next to >= 5 stages even at N = 256 (where the f16 trunk's epilogue is as long as its main loop)
   const bool ew8 = !split && (BN <= 128 || (pair && ew8_wide)) && tc_epi8();
-  // 3xTF32: 8 drain/epilogue warps help K-poor layers (+20-30 %) but steal issue slots from the splitter warps on
-  // K-rich full-width tiles (SepConvGRU gates: -15 %): measured in profiles/r01_tc_microbench_split_epi8.log
-  const bool sew8 = split && tc_epi8() && tc_split_epi8() && (tc_split_epi8() == 2 || !(BN == 128 && taps * (w.cin_pad / 32) >= 48));
   const int stg_bytes = ((ew8 || sew8) ? 8 : 4) * STG_WARP_BYTES;
   const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES;
   p.stages = budget / stage_bytes;
@@ -1087,7 +1124,11 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
     snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? "3xtf32" : (f16 ? "f16" : "tf32"), w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
   }
-  if (split && sew8) { if (CL == 2) launch_tc<true, 2, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p); }
+  if (split && sew8) {
+    if (pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
+    else if (CL == 2) launch_tc<true, 2, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
+    else launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
+  }
   else if (split) { if (CL == 2) launch_tc<true, 2, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); else launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA0, mA1, mB, p); }
   else if (ew8) {
     if (pair) launch_tc<false, 2, 8, true>(grid, 320, smem, cx.stream, mA0, mA1, mB, p);

@@ -57,8 +57,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(" | ".join(res), flush=True)
     sys.exit(0)
 
-KNOBS = [{"PROBE_BIG": "1", "PROBE_STALL": "1", "PROBE_F16": "1"}, {"PROBE_BIG": "1", "PROBE_STALL": "1", "PROBE_F16": "1", "GIMMVFI_TC_EPI8_WIDE": "0"},
-         {"PROBE_BIG": "1", "PROBE_STALL": "1", "PROBE_F16": "1", "GIMMVFI_TC_PAIR": "0"}, {"PROBE_BIG": "1", "PROBE_STALL": "1"}] + [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[1:]]
+KNOBS = [{"PROBE_STALL": "1"}, {"PROBE_STALL": "1", "GIMMVFI_TC_PAIR": "1"}] + [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[1:]]
 for kn in KNOBS:
     env = dict(os.environ); env.update(kn)
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
