@@ -171,6 +171,23 @@ int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1, const
 #endif
   })
 }
+int gimmvfi_op_conv2d_tc_strided(const gimmvfi_view* in0, const float* w_tc, const float* bias, int cin, int cout, int kh, int kw, int stride,
+                                 int act1, int split, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+#ifdef GV_HOSTSIM
+    throw std::runtime_error("conv2d_tc is a tcgen05 kernel; not available in the host simulation");
+#else
+    Ctx cx = op_ctx(stream);
+    ConvW w; w.b = bias; w.cin = cin; w.cout = cout; w.kh = kh; w.kw = kw; w.w_tc = w_tc; w.has_lo = true;
+    w.cout_pad = tc_cout_pad(cout); w.cin_pad = (cin + 31) & ~31;
+    ConvGeom g; g.stride = stride; g.ph = kh / 2; g.pw = kw / 2;
+    ConvEpi ep; ep.act1 = act1;
+    if (!conv2d_tc_supported(to_tv(in0), TV(), w, g, ep, to_tv(out), split != 0)) throw std::runtime_error("conv2d_tc_strided: unsupported configuration");
+    conv2d_tc(cx, to_tv(in0), TV(), w, g, ep, to_tv(out), split != 0);
+#endif
+  })
+}
 int gimmvfi_op_conv2d_tc_f16(const gimmvfi_view* in0, const gimmvfi_view* in1, const void* w_tc_h, const float* w_tc, const float* bias, int cin,
                              int cout, int kh, int kw, int act1, const float* slope1, const gimmvfi_view* residual, int act2,
                              const float* slope2, int half_mask, const gimmvfi_view* out, void* stream) {

@@ -39,6 +39,7 @@ constexpr int BAR_BYTES = 512;
 
 struct Params {
   int taps, kw, ph, pw;
+  int stride;                      // 1 or 2: output pixel (y, x) reads input (y * stride + ky - ph, ...) through TMA element strides
   int kblocks, c0_blocks;          // 32-channel K blocks in total / from segment 0
   int tiles_x, tiles_y, n_img, tiles_n;
   int H, W;
@@ -649,7 +650,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int ky = tap / p.kw, kx = tap % p.kw;
-          const int x0 = tx * TILE_W + kx - p.pw, y0 = ty * TILE_H + ky - p.ph;
+          const int x0 = tx * TILE_W * p.stride + kx - p.pw, y0 = ty * TILE_H * p.stride + ky - p.ph;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait_t(&empty_bar[stage], phase ^ 1, SPIN, ST_A);
             uint8_t* a_dst = smem + stage * stage_bytes;
@@ -953,20 +954,22 @@ static EncodeTiledFn encode_fn() {
 }
 
 static void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
-                   bool f16 = false) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+                   bool f16 = false, int pixel_stride = 1) {
+  cuuint32_t estr[5] = {1, (cuuint32_t)pixel_stride, (cuuint32_t)pixel_stride, 1, 1};   // (activation maps: dims 1, 2 = x, y)
   CUresult r = encode_fn()(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("conv_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
 }
 
-static void encode_act(CUtensorMap* m, const TV& t) {
+// stride 2: the box spans 2x the tile in x and y and TMA keeps every second element (elementStrides), so shared memory
+// receives the same dense 16 x 8 pixel tile as at stride 1
+static void encode_act(CUtensorMap* m, const TV& t, int stride = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)t.c, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
   const cuuint64_t es = t.f16 ? 2 : 4;
   cuuint64_t str[3] = {(cuuint64_t)t.ld * es, (cuuint64_t)t.w * t.ld * es, (cuuint64_t)t.sn * es};
-  cuuint32_t box[4] = {(cuuint32_t)(t.f16 ? 2 * BK : BK), TILE_W, TILE_H, 1};   // 128-byte rows either way
-  encode(m, t.p, 4, dims, str, box, t.f16 != 0);
+  cuuint32_t box[4] = {(cuuint32_t)(t.f16 ? 2 * BK : BK), (cuuint32_t)(TILE_W * stride), (cuuint32_t)(TILE_H * stride), 1};   // 128-byte rows either way
+  encode(m, t.p, 4, dims, str, box, t.f16 != 0, stride);
 }
 
 }  // namespace tc
@@ -1036,7 +1039,7 @@ static int tc_seg() {
 
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!w.w_tc || g.stride != 1 || g.reflect) return false;
+  if (!w.w_tc || (g.stride != 1 && g.stride != 2) || g.reflect) return false;
   if (split && !w.has_lo) return false;
   if (!g.loose_w && (g.ph != w.kh / 2 || g.pw != w.kw / 2)) return false;
   if (g.loose_w && (g.ph != 0 || g.pw != 0)) return false;   // pre-padded input: taps index it directly
@@ -1047,15 +1050,15 @@ bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const Con
   if (e.mul.f16 || e.gru_z.f16 || e.gru_h.f16) return false;   // only the residual may be half
   if (!al16(in0.p) || in0.ld % amul || in0.sn % amul) return false;
   if (in1.p && (!al16(in1.p) || in1.ld % amul || in1.sn % amul || in0.c % kblk)) return false;
-  if (!g.loose_w && (in0.h != out.h || in0.w != out.w)) return false;
+  if (!g.loose_w && ((in0.h + 2 * g.ph - w.kh) / g.stride + 1 != out.h || (in0.w + 2 * g.pw - w.kw) / g.stride + 1 != out.w)) return false;
   return true;
 }
 
 void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
   using namespace tc;
   CUtensorMap mA0, mA1, mB;
-  encode_act(&mA0, in0);
-  if (in1.p) encode_act(&mA1, in1); else mA1 = mA0;
+  encode_act(&mA0, in0, g.stride);
+  if (in1.p) encode_act(&mA1, in1, g.stride); else mA1 = mA0;
   int BN, tiles_n;
   const int pix_tiles_host = out.n * ((out.h + TILE_H - 1) / TILE_H) * ((out.w + TILE_W - 1) / TILE_W);
   if (split) {  // register-promoted accumulation holds BN fp32 accumulators per thread -> BN <= 128
@@ -1083,7 +1086,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
     encode(&mB, w.w_tc, 3, dims, str, box);
   }
   Params p;
-  p.taps = taps; p.kw = w.kw; p.ph = g.ph; p.pw = g.pw;
+  p.taps = taps; p.kw = w.kw; p.ph = g.ph; p.pw = g.pw; p.stride = g.stride;
   p.f16_in = f16 ? 1 : 0; p.bk = bk;
   p.c0_blocks = in1.p ? in0.c / bk : (in0.c + bk - 1) / bk;
   p.kblocks = cin_pad / bk;
@@ -1163,7 +1166,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
     encode(&mB, fb_planes, 3, dims, str, box);
   }
   Params p;
-  p.taps = 1; p.kw = 1; p.ph = 0; p.pw = 0;
+  p.taps = 1; p.kw = 1; p.ph = 0; p.pw = 0; p.stride = 1;
   p.kblocks = C / 32; p.c0_blocks = p.kblocks; p.f16_in = 0; p.bk = BK;
   p.tiles_x = (fa.w + TILE_W - 1) / TILE_W; p.tiles_y = (fa.h + TILE_H - 1) / TILE_H; p.n_img = 1; p.tiles_n = tiles_n;
   p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale; p.seg = tc_seg();

@@ -448,9 +448,7 @@ static void raft_encoder(Net& N, const std::string& p, bool instance, const TV& 
     TV in = xpad; in.c = 28;
     ConvGeom g; g.stride = 2; g.ph = 0; g.pw = 0; g.loose_w = 1;
     ConvEpi e; e.act1 = act;
-    const bool tc = cx.tc; cx.tc = false;    // stride 2: CUDA-core kernel
-    conv2d(cx, in, TV(), N.W(p + ".conv1#xpacked"), g, e, dst);
-    cx.tc = tc;
+    conv2d(cx, in, TV(), N.W(p + ".conv1#xpacked"), g, e, dst);   // (tensor-core path: TMA element strides take every 2nd pixel)
   };
   if (instance) {
     TV r = A.tensor(n, H2, W2, 64);

@@ -121,6 +121,10 @@ int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1_or_nul
                          int cout, int kh, int kw, int act1, const float* slope1, const gimmvfi_view* residual_or_null, int act2,
                          const float* slope2, const gimmvfi_view* mul_or_null, const gimmvfi_view* gru_z_or_null,
                          const gimmvfi_view* gru_h_or_null, int split, const gimmvfi_view* out, void* stream);
+/* the same kernel at stride 1 or 2 with "same"-style padding k/2 (RAFT encoder down-sampling convs, raft/extractor.py:42-48,140):
+ * out is (n, (h + 2*(kh/2) - kh)/stride + 1, ...); TMA element strides pick every stride-th input pixel */
+int gimmvfi_op_conv2d_tc_strided(const gimmvfi_view* in0, const float* w_tc, const float* bias, int cin, int cout, int kh, int kw,
+                                 int stride, int act1, int split, const gimmvfi_view* out, void* stream);
 /* the same kernel with half-precision storage (precision mode 3: the final decoder's residual trunk, fi_components.py:97-154,
  * 299-305).  half_mask: bit 0 = in0/in1 hold IEEE half (kind::f16 MMAs; weights = w_tc_h [kh*kw][cout_pad][cin_pad64] half),
  * bit 1 = out is half, bit 2 = residual is half; views of half tensors give strides in ELEMENTS.  With bit 0 clear the operands are

@@ -246,3 +246,28 @@ def test_conv2d_tc_tf32_in_half_out():
     ref = F.prelu(F.conv2d(K.tf32_trunc(x).double(), K.tf32_rn(w).double(), b.double(), padding=1), slope.double()).float()
     err = (K.nchw(out.float()) - ref).abs().max().item()
     assert err <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [(64, 96, 3, 32, 48, 2), (64, 96, 1, 32, 48, 1), (96, 128, 3, 40, 56, 2), (64, 64, 3, 34, 62, 1)])
+@pytest.mark.parametrize("split", [False, True])
+def test_conv2d_tc_stride2(case, split):
+    """stride-2 convolutions of the RAFT encoder (raft/extractor.py:42-48): TMA element strides gather every 2nd pixel"""
+    import ctypes as C
+    cin, cout, k, H, W, n = case
+    x = rnd(n, cin, H, W, seed=1)
+    w = rnd(cout, cin, k, k, seed=2, scale=1.0 / (cin * k * k) ** 0.5)
+    b = rnd(cout, seed=3, scale=0.1)
+    xn = K.nhwc(x)
+    Ho, Wo = (H + 2 * (k // 2) - k) // 2 + 1, (W + 2 * (k // 2) - k) // 2 + 1
+    out = torch.empty(n, Ho, Wo, cout, device=DEV)
+    pw = K.pack_weight_tc(w)
+    bb = torch.zeros(512, device=DEV); bb[:cout] = b
+    lib = K.default_lib()
+    lib.check(lib.dll.gimmvfi_op_conv2d_tc_strided(C.byref(K.view_of(xn)), C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()), cin, cout, k, k, 2, 1,
+                                                   int(split), C.byref(K.view_of(out)), K._stream(out)))
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=k // 2)).float()
+    assert ref.shape[2:] == (Ho, Wo)
+    err = (K.nchw(out) - ref).abs().max().item()
+    tol = (2e-5 if split else 3e-3) * max(1.0, ref.abs().max().item())
+    print("stride-2 case", case, "split", split, "err %.3e" % err)
+    assert err <= tol
