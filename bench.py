@@ -285,13 +285,15 @@ def main():
         is_flop = dname.startswith("conv2d") or dname.startswith("corr_gemm")
         # ncu --set full captures of the dominant LAYER SHAPE of each tensor-core kernel (profiles/r01_ncu_*.jsonl):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch
-        NCU_TRAFFIC = {"conv2d_tc_tf32": {"layer": "3x3 256->256 @1088x1920", "bytes": 2.146013e9 + 2.092577e9, "algorithmic_bytes": 2 * 1088 * 1920 * 256 * 4.0},
-                       "conv2d_tc_3xtf32": {"layer": "1x5 384->128 @2x136x240 (SepConvGRU gate)", "bytes": 102.561792e6 + 12.403968e6,
+        NCU_TRAFFIC = {"conv2d_tc_f16": {"layer": "3x3 256->256 @1088x1920, fp16 storage (profiles/r01_ncu_conv2d_tc_f16_256x256_1080p.jsonl)",
+                                         "bytes": 1.072938e9 + 1.031320e9, "algorithmic_bytes": 2 * 1088 * 1920 * 256 * 2.0},
+                       "conv2d_tc_tf32": {"layer": "3x3 256->256 @1088x1920", "bytes": 2.146013e9 + 2.092577e9, "algorithmic_bytes": 2 * 1088 * 1920 * 256 * 4.0},
+                       "conv2d_tc_3xtf32": {"layer": "1x5 384->128 @2x136x240 (SepConvGRU gate; profiles/r01_ncu_conv2d_tc_3xtf32_gru_384x128_pair.jsonl)", "bytes": 102.902784e6 + 12.797184e6,
                                             "algorithmic_bytes": 2 * 136 * 240 * (384 + 128) * 4.0}}
         NOTES = {"conv2d_tc_f16": "tcgen05 kind::f16 implicit GEMM on the fp16-stored residual trunk (TMA halo tiles, TMEM fp32 accumulators)",
                  "conv2d_tc_tf32": "tcgen05 kind::tf32 implicit GEMM (TMA halo tiles, TMEM accumulators); TF32 peak is half the bf16 peak used as denominator",
                  "conv2d_tc_3xtf32": "tcgen05 3xTF32 (3 MMAs per K step + register-promoted accumulation): 'achieved' counts ALGORITHMIC flops, "
-                                     "the tensor pipe executes 3x that; small-resolution RAFT layers, pipeline-latency bound (ncu: tensor pipe 14.6 % active)",
+                                     "the tensor pipe executes 3x that at the TF32 rate (= bf16 peak / 2), so the ceiling of this ratio is 1/6; small-resolution RAFT layers on CTA pairs with TMEM-resident split operands (ncu: tensor pipe 58.8 % active)",
                  "conv2d_simt_n64": "fp32 CUDA-core implicit GEMM measured against the tensor-pipe peak (the layer class is tensor-bound, SURVEY 8(d))"}
         if is_flop:
             ach = d["work"] / (d["ms"] * 1e-3) / 1e12
