@@ -147,6 +147,89 @@ __global__ void __launch_bounds__(256) conv2d_simt_kernel(ConvArgs a) {
 }
 #endif
 
+
+#ifndef GV_HOSTSIM
+// Convolutions with 1-2 output channels over a wide input (RAFT FlowHead.conv2: 3x3, 256 -> 2, raft/update.py:6-14).
+// A GEMM tile would be all padding (N = 16 of which 2 are real) and still pay the whole A-operand pipeline; here one warp
+// owns one output pixel: lanes split the input channels (float4 each), the weights sit in shared memory as (co0, co1) pairs,
+// two fp32 accumulators per lane, one shuffle reduction.  Exact fp32 arithmetic; reads every input byte ~once from L2
+// (the 9-fold tap reuse is served by L1).  y = res + conv + bias (the only epilogue its callers need).
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_narrow_kernel(ConvArgs a, int warps_total) {
+  extern __shared__ float2 wsm[];   // [tap * cin + ci] -> (w[co 0], w[co 1])
+  const int cin = a.w.cin, taps = a.w.kh * a.w.kw;
+  for (int i = threadIdx.x; i < taps * cin; i += blockDim.x) {
+    const float* wp = a.w.w + (size_t)i * a.w.cout_ld;
+    wsm[i] = make_float2(wp[0], COUT > 1 ? wp[1] : 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int OW = a.out.w, OH = a.out.h;
+  for (int m = blockIdx.x * wpb + wib; m < warps_total; m += gridDim.x * wpb) {
+    const int ox = m % OW; int r = m / OW; const int oy = r % OH; const int n = r / OH;
+    float acc0 = 0.f, acc1 = 0.f;
+    if (a.w.kh == 3 && a.w.kw == 3 && cin == 256) {
+      // FlowHead.conv2: all 18 activation loads of the lane are issued before the first use (predicated zero outside the image)
+      float4 v[18];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int iy = oy + t / 3 - a.g.ph, ix = ox + t % 3 - a.g.pw;
+        const bool in = iy >= 0 && iy < a.in0.h && ix >= 0 && ix < a.in0.w;
+        const float* src = a.in0.p + a.in0.off(n, in ? iy : 0, in ? ix : 0) + lane * 4;
+        v[2 * t] = in ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[2 * t + 1] = in ? *reinterpret_cast<const float4*>(src + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const float2* wt = wsm + t * 256 + hf * 128 + lane * 4;
+          const float4 w01 = *reinterpret_cast<const float4*>(wt), w23 = *reinterpret_cast<const float4*>(wt + 2);
+          const float4 x = v[2 * t + hf];
+          acc0 = fmaf(x.x, w01.x, acc0); acc1 = fmaf(x.x, w01.y, acc1);
+          acc0 = fmaf(x.y, w01.z, acc0); acc1 = fmaf(x.y, w01.w, acc1);
+          acc0 = fmaf(x.z, w23.x, acc0); acc1 = fmaf(x.z, w23.y, acc1);
+          acc0 = fmaf(x.w, w23.z, acc0); acc1 = fmaf(x.w, w23.w, acc1);
+        }
+      }
+    } else
+    for (int ky = 0; ky < a.w.kh; ++ky) {
+      const int iy = oy + ky - a.g.ph;
+      if (iy < 0 || iy >= a.in0.h) continue;
+      for (int kx = 0; kx < a.w.kw; ++kx) {
+        const int ix = ox + kx - a.g.pw;
+        if (ix < 0 || ix >= a.in0.w) continue;
+        const float* src = a.in0.p + a.in0.off(n, iy, ix);
+        const float2* wt = wsm + (ky * a.w.kw + kx) * cin;
+        for (int c = lane * 4; c < cin; c += 128) {
+          const float4 v = *reinterpret_cast<const float4*>(src + c);
+          const float4 w01 = *reinterpret_cast<const float4*>(wt + c), w23 = *reinterpret_cast<const float4*>(wt + c + 2);
+          acc0 = fmaf(v.x, w01.x, acc0); acc1 = fmaf(v.x, w01.y, acc1);
+          acc0 = fmaf(v.y, w01.z, acc0); acc1 = fmaf(v.y, w01.w, acc1);
+          acc0 = fmaf(v.z, w23.x, acc0); acc1 = fmaf(v.z, w23.y, acc1);
+          acc0 = fmaf(v.w, w23.z, acc0); acc1 = fmaf(v.w, w23.w, acc1);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, o); acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); }
+    if (lane < COUT) {
+      float v = (lane == 0 ? acc0 : acc1) + a.w.b[lane];
+      if (a.e.res.p) v += a.e.res.p[a.e.res.off(n, oy, ox) + lane];
+      a.out.p[a.out.off(n, oy, ox) + lane] = v;
+    }
+  }
+}
+
+static bool conv_narrow_ok(const ConvArgs& a) {
+  const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return a.w.cout <= 2 && !a.in1.p && a.g.stride == 1 && !a.g.reflect && !a.g.loose_w && a.w.cin % 128 == 0 && a.in0.ld % 4 == 0 && a.in0.sn % 4 == 0 &&
+         al16(a.in0.p) && a.e.act1 == ACT_NONE && a.e.act2 == ACT_NONE && !a.e.mul.p && !a.e.gru_z.p && !a.in0.f16 && !a.out.f16 && !a.e.res.f16 &&
+         (size_t)a.w.kh * a.w.kw * a.w.cin * sizeof(float2) <= 96 * 1024 &&
+         a.w.kh * a.w.kw * a.w.cin >= 1024;   // (a full-resolution 1x1 with few channels is better off as one MMA tile per 128 pixels)
+}
+#endif
+
 void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out) {
   if (cx.dry) return;
   ConvArgs a;
@@ -161,6 +244,27 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
     if (((eh != out.h || ew != out.w) && !g.loose_w) || in0.n != out.n) throw std::runtime_error("conv2d: output geometry mismatch");
   }
 #ifndef GV_HOSTSIM
+  if (conv_narrow_ok(a)) {   // before the tensor-core dispatch: exact fp32 and ~10x faster than a 16-wide MMA tile of padding
+    cx.launches++;
+    const size_t smem = (size_t)w.kh * w.kw * w.cin * sizeof(float2);
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(conv_narrow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(conv_narrow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    if (cx.prof) {
+      char nm[128];
+      snprintf(nm, sizeof nm, "conv_narrow k%dx%d c%d>%d @%dx%dx%d", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
+      cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)a.M * w.cout * (double)w.cin * w.kh * w.kw);
+    }
+    const int blocks = std::min((a.M + 7) / 8, cx.sm_count * 8);
+    if (w.cout == 1) conv_narrow_kernel<1><<<blocks, 256, smem, cx.stream>>>(a, a.M);
+    else conv_narrow_kernel<2><<<blocks, 256, smem, cx.stream>>>(a, a.M);
+    gv_check_launch("conv_narrow");
+    if (cx.prof) cx.prof->end(cx.stream);
+    return;
+  }
   const bool any_f16 = in0.f16 || in1.f16 || out.f16 || e.res.f16;
   if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out, cx.tc_split && !any_f16)) { conv2d_tc(cx, in0, in1, w, g, e, out, cx.tc_split && !any_f16); return; }
   if (any_f16) throw std::runtime_error("conv2d: half-precision tensors are only handled by the tensor-core path (layer not eligible)");

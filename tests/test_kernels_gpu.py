@@ -166,3 +166,19 @@ def test_corr_pool_pyramid_matches_levelwise(h, w):
     for g, r in zip(got, ref[1:]):
         assert torch.equal(g, r)
     assert torch.allclose(got[0], torch.nn.functional.avg_pool2d(l0[:, None], 2, 2)[:, 0], atol=1e-6)
+
+
+@pytest.mark.parametrize("case", [(256, 2, 3, 24, 40, 2, True), (128, 1, 3, 17, 23, 1, False), (256, 2, 5, 16, 20, 1, True)])
+def test_conv_narrow_cout(case):
+    """1-2 output channels over a wide input (RAFT FlowHead.conv2, raft/update.py:6-14): warp-per-pixel fp32 kernel, + residual"""
+    cin, cout, k, H, W, n, use_res = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    b = (0.1 * torch.randn(cout, generator=g)).cuda()
+    res = torch.randn(n, cout, H, W, generator=g).cuda() if use_res else None
+    got = K.nchw(K.conv2d(K.nhwc(x), w, b, pad=(k // 2, k // 2), residual=K.nhwc(res) if use_res else None))
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2)
+    if use_res:
+        ref = ref + res.double()
+    assert (got.double() - ref).abs().max().item() <= 2e-5
