@@ -76,6 +76,10 @@ int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out) {
     out->data = t.p; out->n = t.n; out->h = t.h; out->w = t.w; out->c = t.c; out->pixel_stride = t.ld; out->batch_stride = t.sn;
   })
 }
+size_t gimmvfi_frame_cache_bytes(const gimmvfi_problem* p) { return Engine::frame_cache_bytes(to_problem(p)); }
+int gimmvfi_set_frame_cache(gimmvfi_engine* e, void* cache, size_t bytes, int load, int store) {
+  GV_TRY(e, { e->eng.set_frame_cache(static_cast<float*>(cache), bytes, load != 0, store != 0); })
+}
 int gimmvfi_set_tensor_cores(gimmvfi_engine* e, int mode) { GV_TRY(e, { e->eng.set_tensor_cores(mode); }) }
 int gimmvfi_set_profile(gimmvfi_engine* e, int on) { GV_TRY(e, { e->eng.set_profile(on != 0); }) }
 const char* gimmvfi_profile_json(gimmvfi_engine* e, void* stream) {
@@ -118,6 +122,23 @@ int gimmvfi_op_resize(const gimmvfi_view* src, const gimmvfi_view* dst, float sc
 int gimmvfi_op_corr_volume(const gimmvfi_view* fa, const gimmvfi_view* fb, float* vol, void* stream) {
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, { Ctx cx = op_ctx(stream); TV a = to_tv(fa); corr_volume(cx, a, to_tv(fb), vol, 1.0f / std::sqrt((float)a.c)); })
+}
+int gimmvfi_op_corr_volume_tc(const gimmvfi_view* fa, const gimmvfi_view* fb, float* scratch, float* vol, int split, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+#ifdef GV_HOSTSIM
+    throw std::runtime_error("corr_volume_tc is a tcgen05 kernel; not available in the host simulation");
+#else
+    Ctx cx = op_ctx(stream);
+    TV a = to_tv(fa); TV b = to_tv(fb);
+    if (a.n != 1 || b.n != 1 || a.c % 32 || a.ld != a.c || b.ld != b.c) throw std::runtime_error("corr_volume_tc: one dense sample with C % 32 == 0");
+    const int64_t N = (int64_t)a.h * a.w;
+    float* planes = scratch; float* zeros = scratch + 2 * N * a.c;
+    dev_memset(zeros, 0, (size_t)(((N + 255) / 256) * 256 + 512) * sizeof(float), cx.stream);
+    if (split) split_planes(cx, b, planes);
+    corr_volume_tc(cx, a, split ? planes : b.p, zeros, vol, 1.0f / std::sqrt((float)a.c), split != 0);
+#endif
+  })
 }
 int gimmvfi_op_corr_pool(const float* src, float* dst, int64_t rows, int h, int w, void* stream) {
   gimmvfi_engine* e = nullptr;

@@ -1159,10 +1159,16 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   // split: fb_planes = [2][N][C] (rn / residual planes).  plain TF32: fb_planes = the raw K-major features [N][C] of the
   // other frame (the tensor core truncates them).  BN = 128 in both (register accumulators / 8 epilogue warps).
   const int BN = 128, tiles_n = (N + BN - 1) / BN;
+  const int pix_tiles_host = ((fa.h + TILE_H - 1) / TILE_H) * ((fa.w + TILE_W - 1) / TILE_W);
+  const bool e8 = tc_epi8() && (!split || tc_split_epi8());
+  // CTA pairs as in conv2d_tc: two neighbouring source-pixel tiles share the target-pixel ("weight") tile, half of it per CTA
+  const bool atm = split && tc_atmem();
+  const bool pair = e8 && pix_tiles_host >= 2 && (split ? (tc_pair() >= 2 && atm) : (tc_pair() != 0)) && pix_tiles_host * tiles_n >= 2 * cx.sm_count;
+  const int CL = pair ? 2 : 1;
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)(split ? 2 : 1)};
     cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
-    cuuint32_t box[3] = {BK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {BK, (cuuint32_t)(BN / CL), 1};
     encode(&mB, fb_planes, 3, dims, str, box);
   }
   Params p;
@@ -1172,22 +1178,25 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale; p.seg = tc_seg();
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
-  p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = split ? tc_atmem() : 0; p.stall = tc_stall_buf();
+  p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = atm ? 1 : 0; p.stall = tc_stall_buf();
   p.bias = zero_bias; p.act1 = ACT_NONE; p.slope1 = nullptr; p.act2 = ACT_NONE; p.slope2 = nullptr;
   p.out = make_tv(vol, 1, fa.h, fa.w, N, N);
-  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * BN * BK * 4) : (A_BYTES + BN * BK * 4);
-  const bool e8 = tc_epi8() && (!split || tc_split_epi8());
+  const int bn_cta = pair ? BN / 2 : BN;
+  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * bn_cta * BK * 4) : (A_BYTES + bn_cta * BK * 4);
   const int stg_bytes = (e8 ? 8 : 4) * STG_WARP_BYTES;
   p.stages = (227 * 1024 - 1024 - stg_bytes - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.atmem && p.stages > 4) p.stages = 4;
   const int smem = p.stages * stage_bytes + stg_bytes + BAR_BYTES + 1024;
-  const int num_tiles = p.tiles_y * p.tiles_x * tiles_n;
-  const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
+  const int num_tiles = (pix_tiles_host + CL - 1) / CL * CL * tiles_n;
+  int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
+  grid -= grid % CL;
   cx.launches++;
   if (cx.prof) cx.prof->begin(cx.stream, split ? "corr_gemm_tc_3xtf32" : "corr_gemm_tc_tf32", 2.0 * (double)N * N * C);
-  if (split && e8) launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA, mA, mB, p);
+  if (split && pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA, mA, mB, p);
+  else if (split && e8) launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA, mA, mB, p);
   else if (split) launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA, mA, mB, p);
+  else if (pair) launch_tc<false, 2, 8, true>(grid, 320, smem, cx.stream, mA, mA, mB, p);
   else if (e8) launch_tc<false, 1, 8>(grid, 320, smem, cx.stream, mA, mA, mB, p);
   else launch_tc<false, 1, 4>(grid, 192, smem, cx.stream, mA, mA, mB, p);
   gv_check_launch("corr_volume_tc");

@@ -668,18 +668,39 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     const size_t mk = A.mark();
     TV hx = A.tensor(2 * B, h, w, 384);              // [h | inp | motion]
     TV c4, c8;
+    // frame cache (set_frame_cache): with `load` the encoders only see the second frames, samples [B, 2B)
+    const bool fc_on = fc_ != nullptr && !cx.dry;
+    if (fc_on && fc_bytes_ < frame_cache_bytes(P)) throw std::runtime_error("gimmvfi: frame cache smaller than frame_cache_bytes()");
+    const bool fload = fc_on && fc_load_, fstore = fc_on && fc_store_;
+    const int e0 = fload ? B : 0, en = fload ? B : 2 * B;
     {
-      TV raft_pad = A.tensor(2 * B, H + 6, W + 6, 3, 4);
-      pad_image4(cx, raft_in, raft_pad, 3);
-      raft_encoder(N, "flow_estimator.fnet", true, raft_in, raft_pad, fmap, nullptr, nullptr, nullptr, TV(), TV());
+      TV rin = raft_in.batch(e0, en);
+      TV raft_pad = A.tensor(en, H + 6, W + 6, 3, 4);
+      pad_image4(cx, rin, raft_pad, 3);
+      raft_encoder(N, "flow_estimator.fnet", true, rin, raft_pad, fmap.batch(e0, en), nullptr, nullptr, nullptr, TV(), TV());
       // the encoder's temporaries stay allocated until `mk` is released (bump allocator)
       const ConvW& wc = N.W("flow_estimator.cnet.conv2");
-      raft_encoder(N, "flow_estimator.cnet", false, raft_in, raft_pad, TV(), &c4, &c8, &wc, hx.slice(0, 128), hx.slice(128, 128));
+      raft_encoder(N, "flow_estimator.cnet", false, rin, raft_pad, TV(), &c4, &c8, &wc, hx.batch(e0, en).slice(0, 128), hx.batch(e0, en).slice(128, 128));
+    }
+    // context features for the synthesis net (gimmvfi_r.py:134-141)
+    N.conv("amt_second_last_cproj", c4, feat4.batch(e0, en));
+    N.conv("amt_last_cproj", c8, feat8.batch(e0, en));
+    if (fc_on) {
+      float* q = fc_;
+      TV c_fmap = make_tv(q, B, h, w, 256); q += (size_t)B * h * w * 256;
+      TV c_ni = make_tv(q, B, h, w, 256); q += (size_t)B * h * w * 256;
+      TV c_f4 = make_tv(q, B, H4, W4, 128); q += (size_t)B * H4 * W4 * 128;
+      TV c_f8 = make_tv(q, B, h, w, 256);
+      if (fload) {
+        copy_channels(cx, c_fmap, fmap.batch(0, B)); copy_channels(cx, c_ni, hx.batch(0, B).slice(0, 256));
+        copy_channels(cx, c_f4, feat4.batch(0, B)); copy_channels(cx, c_f8, feat8.batch(0, B));
+      }
+      if (fstore) {   // (before the GRU overwrites `net` in place)
+        copy_channels(cx, fmap.batch(B, B), c_fmap); copy_channels(cx, hx.batch(B, B).slice(0, 256), c_ni);
+        copy_channels(cx, feat4.batch(B, B), c_f4); copy_channels(cx, feat8.batch(B, B), c_f8);
+      }
     }
     tap("raft.fmap", fmap);
-    // context features for the synthesis net (gimmvfi_r.py:134-141)
-    N.conv("amt_second_last_cproj", c4, feat4);
-    N.conv("amt_last_cproj", c8, feat8);
 
     Pyramid pyr = build_pyramid(cx, fmap, B, tc_mode_ >= 2 ? 2 : 0);   // RAFT's volume: fp32-class only
     const std::string u = "flow_estimator.update_block";
@@ -940,6 +961,11 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       combine_output(cx, mean3, c3, io.imgt_pred + (int64_t)ti * B * 3 * Hf * Wf);
     }
   }
+}
+
+size_t Engine::frame_cache_bytes(const Problem& p) {
+  const size_t h = (size_t)p.H() / 8, w = (size_t)p.W() / 8, H4 = (size_t)p.H() / 4, W4 = (size_t)p.W() / 4;
+  return ((size_t)p.B * h * w * 256 * 3 + (size_t)p.B * H4 * W4 * 128) * sizeof(float);
 }
 
 size_t Engine::plan(const Problem& p) {

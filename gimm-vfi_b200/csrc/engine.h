@@ -56,6 +56,12 @@ class Engine {
   // 0: fp32 CUDA cores everywhere; 1: post-RAFT convs on TF32 tensor cores; 2: + RAFT convs on 3xTF32 tensor cores
   void set_tensor_cores(int mode) { tc_mode_ = mode; }
   std::string profile_json(gvStream_t stream);
+  // Video callers (src/video_Nx.py:134-216) walk consecutive pairs (j, j+1), (j+1, j+2), ...: the RAFT encoder products of a
+  // call's SECOND frame (fnet map, cnet net/inp, projected context features) can be kept in a caller-owned device buffer and
+  // re-used as the next call's FIRST frame.  load: frame 0 comes from the cache (the caller guarantees it
+  // is the frame the cache was stored from); store: frame 1's products are written to it.  Results are bit-identical.
+  static size_t frame_cache_bytes(const Problem& p);
+  void set_frame_cache(float* cache, size_t bytes, bool load, bool store) { fc_ = cache; fc_bytes_ = bytes; fc_load_ = load; fc_store_ = store; }
   const std::map<std::string, TV>& taps() const { return taps_; }
   std::string last_error;
   int raft_iters = 20;  // GIMMVFI_R hard-codes iters=20 (gimmvfi_r.py:126-132)
@@ -74,6 +80,7 @@ class Engine {
   int device_ = 0;
   bool finalized_ = false, debug_ = false, profile_ = false;
   int tc_mode_ = 0;
+  float* fc_ = nullptr; size_t fc_bytes_ = 0; bool fc_load_ = false, fc_store_ = false;
   void pack_tc(ConvW& c, const std::vector<float>& packed);
   void pack_tc_f16(ConvW& c, const std::vector<float>& packed);
   void pack_stem(const std::string& name, const std::string& bn);

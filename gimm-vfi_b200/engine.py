@@ -89,9 +89,14 @@ class EngineHandle:
             self._plans[key] = int(n.value)
         return self._plans[key]
 
+    def frame_cache_bytes(self, B, Hf, Wf, T, ds, Hc, Wc) -> int:
+        p = self._problem(B, Hf, Wf, T, ds, Hc, Wc)
+        return int(self.lib.dll.gimmvfi_frame_cache_bytes(C.byref(p)))
+
     def forward(self, img_xs: torch.Tensor, coords: torch.Tensor, t: torch.Tensor, ds: Optional[float] = None,
-                aux_outputs: bool = True) -> Dict[str, torch.Tensor]:
-        """img_xs (B,3,2,Hf,Wf), coords (T,B,1,Hc,Wc,3), t (T,B): contiguous fp32 on self.device."""
+                aux_outputs: bool = True, frame_cache=None) -> Dict[str, torch.Tensor]:
+        """img_xs (B,3,2,Hf,Wf), coords (T,B,1,Hc,Wc,3), t (T,B): contiguous fp32 on self.device.
+        frame_cache = (uint8 device tensor of frame_cache_bytes(), load, store): see gimmvfi_set_frame_cache."""
         for x in (img_xs, coords, t):
             assert x.dtype == torch.float32 and x.is_contiguous() and x.device.type == self.device.type
         B, _, _, Hf, Wf = img_xs.shape
@@ -114,8 +119,16 @@ class EngineHandle:
             setattr(io, k, v.data_ptr())
         p = self._problem(B, Hf, Wf, T, ds, Hc, Wc)
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
-        self.lib.check(self.lib.dll.gimmvfi_forward(self._h, C.byref(p), C.byref(io), C.c_void_p(self._ws.data_ptr()),
-                                                    self._ws.numel(), C.c_void_p(stream)), self._h)
+        if frame_cache is not None:
+            buf, load, store = frame_cache
+            assert buf.dtype == torch.uint8 and buf.is_contiguous() and buf.device.type == self.device.type
+            self.lib.check(self.lib.dll.gimmvfi_set_frame_cache(self._h, C.c_void_p(buf.data_ptr()), buf.numel(), int(load), int(store)), self._h)
+        try:
+            self.lib.check(self.lib.dll.gimmvfi_forward(self._h, C.byref(p), C.byref(io), C.c_void_p(self._ws.data_ptr()),
+                                                        self._ws.numel(), C.c_void_p(stream)), self._h)
+        finally:
+            if frame_cache is not None:
+                self.lib.check(self.lib.dll.gimmvfi_set_frame_cache(self._h, None, 0, 0, 0), self._h)
         return out
 
     def tap(self, name: str) -> torch.Tensor:

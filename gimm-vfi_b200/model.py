@@ -128,7 +128,7 @@ class GIMMVFI_R(nn.Module):
         xs = img_xs.to(torch.float32).contiguous()
         coords = torch.stack([c[0].to(torch.float32) for c in coord], 0).contiguous()  # (T,B,1,Hc,Wc,3)
         tt = torch.stack([x.reshape(-1).to(torch.float32).expand(B) for x in t], 0).contiguous()  # (T,B)
-        o = eng.forward(xs, coords, tt, ds_factor, aux_outputs=self.aux_outputs)
+        o = eng.forward(xs, coords, tt, ds_factor, aux_outputs=self.aux_outputs, frame_cache=getattr(self, "_frame_cache", None))
         T = len(t)
         out = {"imgt_pred": [o["imgt_pred"][i] for i in range(T)]}
         if self.aux_outputs:

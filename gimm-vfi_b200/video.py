@@ -69,3 +69,55 @@ def interpolate_pair_u8(model, frame0_u8: torch.Tensor, frame1_u8: torch.Tensor,
     finally:
         model.aux_outputs = aux
     return [padder.unpad_u8(im, bgr)[0] for im in out["imgt_pred"]]
+
+
+class VideoInterpolator:
+    """video_Nx.py's frame loop (src/video_Nx.py:134-216) as a streaming object: push() the frames of a clip one by one and
+    get the N-1 interpolated frames between the previous frame and the new one.  Consecutive pairs share a frame, so the
+    RAFT encoder products of each pair's second frame (fnet map, cnet net/inp, projected context features) stay in a device
+    cache and are not recomputed when that frame becomes the next pair's first frame; the outputs
+    are bit-identical to independent per-pair calls."""
+
+    def __init__(self, model, N: int = 2, ds_factor: Optional[float] = None, bgr: bool = True):
+        self.model, self.N, self.ds, self.bgr = model, int(N), ds_factor, bgr
+        self._prev = None      # padded float frame (3,H,W) of the last push
+        self._padder = None
+        self._cache = None     # uint8 device buffer holding the previous frame's encoder products
+        self._cache_valid = False
+
+    def reset(self):
+        self._prev, self._cache_valid = None, False
+
+    @torch.no_grad()
+    def push(self, frame_u8: torch.Tensor) -> List[torch.Tensor]:
+        dev = frame_u8.device
+        if self._padder is None or (self._padder.ht, self._padder.wd) != tuple(frame_u8.shape[:2]):
+            self._padder = InputPadder(frame_u8.shape[:2], 32)
+            self.reset()
+        cur = self._padder.pad_u8(frame_u8.unsqueeze(0))[0]              # (3,H,W)
+        if self._prev is None:
+            self._prev = cur
+            return []
+        m = self.model
+        xs = torch.stack([self._prev, cur], 1).unsqueeze(0).contiguous()  # (1,3,2,H,W)
+        H, W = xs.shape[-2:]
+        ratio = 1.0 if self.ds is None else self.ds
+        N = self.N
+        coords = [(m.sample_coord_input(1, (H, W), [i / N], device=dev, upsample_ratio=ratio), None) for i in range(1, N)]
+        ts = [i / N * torch.ones(1, device=dev) for i in range(1, N)]
+        Hc, Wc = coords[0][0].shape[2:4]
+        need = m.engine.frame_cache_bytes(1, H, W, N - 1, self.ds, Hc, Wc)
+        if self._cache is None or self._cache.numel() < need or self._cache.device != dev:
+            self._cache, self._cache_valid = torch.empty(need, dtype=torch.uint8, device=dev), False
+        aux, m.aux_outputs = m.aux_outputs, False
+        m._frame_cache = (self._cache, self._cache_valid, True)
+        try:
+            out = m(xs, coords, t=ts, ds_factor=self.ds)
+            self._cache_valid = True
+        except Exception:
+            self._cache_valid = False
+            raise
+        finally:
+            m.aux_outputs, m._frame_cache = aux, None
+        self._prev = cur
+        return [self._padder.unpad_u8(im, self.bgr)[0] for im in out["imgt_pred"]]

@@ -82,6 +82,13 @@ int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters);
 /* debug taps: intermediate tensors of the last forward (views into the workspace) */
 int gimmvfi_set_debug(gimmvfi_engine* e, int on);
 int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out);
+/* Video callers (src/video_Nx.py:134-216) walk consecutive pairs (j, j+1), (j+1, j+2), ...  A caller-owned device buffer of
+ * gimmvfi_frame_cache_bytes() keeps the RAFT encoder products of a call's SECOND frame (raft/raft.py:118-136 fnet map and cnet
+ * net/inp, gimmvfi_r.py:134-141 projected context features); with load != 0 the next forward takes its FIRST frame's products
+ * from it instead of recomputing them (the caller guarantees it is the same frame, same problem), with store != 0 it writes the
+ * second frame's products.  cache == NULL switches the mechanism off.  Results are bit-identical to an uncached forward. */
+size_t gimmvfi_frame_cache_bytes(const gimmvfi_problem* p);
+int gimmvfi_set_frame_cache(gimmvfi_engine* e, void* cache, size_t bytes, int load, int store);
 /* 0: fp32 CUDA cores everywhere; 1: post-RAFT convolutions on the tcgen05 TF32 path (fp32 accumulate);
  * 2: additionally the RAFT convolutions on tcgen05 with 3xTF32 operand splitting (fp32-class accuracy) */
 int gimmvfi_set_tensor_cores(gimmvfi_engine* e, int mode);
@@ -103,6 +110,9 @@ int gimmvfi_op_backwarp(const gimmvfi_view* src, const gimmvfi_view* flow, const
 int gimmvfi_op_resize(const gimmvfi_view* src, const gimmvfi_view* dst, float scale_factor, float mult, void* stream);
 /* all-pairs correlation raft/corr.py:167-175: vol[n][i][j] = <fa[n,i,:], fb[n,j,:]> / sqrt(C) */
 int gimmvfi_op_corr_volume(const gimmvfi_view* fa, const gimmvfi_view* fb, float* vol, void* stream);
+/* the same volume for ONE sample (n == 1, dense views, C % 32 == 0) as a tcgen05 GEMM: split != 0 -> 3xTF32 (RAFT's volume),
+ * else TF32 (the bidirectional volume).  scratch >= 2*h*w*C + h*w + 1024 floats */
+int gimmvfi_op_corr_volume_tc(const gimmvfi_view* fa, const gimmvfi_view* fb, float* scratch, float* vol, int split, void* stream);
 /* 2x2 average pooling of every row's (h,w) image: raft/corr.py:139-142 */
 int gimmvfi_op_corr_pool(const float* src, float* dst, int64_t rows, int h, int w, void* stream);
 /* levels 1..3 from level 0 in one pass (three successive corr_pool's, raft/corr.py:139-142) */

@@ -271,3 +271,28 @@ def test_conv2d_tc_stride2(case, split):
     tol = (2e-5 if split else 3e-3) * max(1.0, ref.abs().max().item())
     print("stride-2 case", case, "split", split, "err %.3e" % err)
     assert err <= tol
+
+
+@pytest.mark.parametrize("hw", [(16, 24), (72, 96)])   # 72x96: 54 source tiles x 54 target tiles -> CTA pairs (>= 2 x 148 tiles)
+@pytest.mark.parametrize("split", [True, False])
+def test_corr_volume_tc(hw, split):
+    """all-pairs correlation (raft/corr.py:167-175) on the tcgen05 kernel: 3xTF32 for RAFT, TF32 for the bidirectional volume"""
+    import ctypes as C
+    h, w = hw
+    Cc = 256
+    g = torch.Generator().manual_seed(3)
+    fa = torch.randn(1, h, w, Cc, generator=g).to(DEV)
+    fb = torch.randn(1, h, w, Cc, generator=g).to(DEV)
+    N = h * w
+    vol = torch.empty(N, N, device=DEV)
+    scratch = torch.empty(2 * N * Cc + N + 2048, device=DEV)
+    lib = K.default_lib()
+    lib.check(lib.dll.gimmvfi_op_corr_volume_tc(C.byref(K.view_of(fa)), C.byref(K.view_of(fb)), C.c_void_p(scratch.data_ptr()), C.c_void_p(vol.data_ptr()),
+                                                int(split), K._stream(vol)))
+    a = fa.view(N, Cc).double(); b = fb.view(N, Cc).double()
+    if not split:
+        a, b = K.tf32_trunc(fa).view(N, Cc).double(), K.tf32_trunc(fb).view(N, Cc).double()
+    ref = (a @ b.t() / 16.0).float()
+    err = (vol - ref).abs().max().item()
+    print("corr_volume_tc", hw, "split", split, "err %.3e" % err, "absmax %.2f" % ref.abs().max().item())
+    assert err <= (3e-5 if split else 2e-4)

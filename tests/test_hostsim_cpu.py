@@ -52,3 +52,27 @@ def test_planner_is_exact_and_rejects_bad_shapes(eng):
         eng.workspace_bytes(1, 100, 160, 1, None, 100, 160)    # not a multiple of 8
     with pytest.raises(GimmvfiError):
         eng.workspace_bytes(1, 128, 160, 1, None, 64, 80)      # coord grid != network resolution
+
+
+def test_frame_cache_reuses_second_frame_bit_exactly(eng):
+    """pairs (A,B), (B,C) of a clip — the second call takes frame B's RAFT encoder products from the cache
+    written by the first; every output must equal the uncached forward (same arithmetic, only skipped)."""
+    torch.set_grad_enabled(False)
+    H, W = 128, 160
+    fr = synth_batch(2, H, W, seed=11)                       # (2,3,2,H,W): two pairs -> frames A,B and (reused) B,C
+    A, Bf, Cf = fr[0, :, 0], fr[0, :, 1], fr[1, :, 1]
+    pair = lambda a, b: torch.stack([a, b], 1).unsqueeze(0).contiguous()
+    coords = O.sample_coord_input(1, (H, W), [0.5], 1.0).unsqueeze(0).contiguous()
+    tt = 0.5 * torch.ones(1, 1)
+    ref_ab = eng.forward(pair(A, Bf), coords, tt, None)
+    ref_bc = eng.forward(pair(Bf, Cf), coords, tt, None)
+    cache = torch.zeros(eng.frame_cache_bytes(1, H, W, 1, None, H, W), dtype=torch.uint8)
+    got_ab = eng.forward(pair(A, Bf), coords, tt, None, frame_cache=(cache, False, True))
+    got_bc = eng.forward(pair(Bf, Cf), coords, tt, None, frame_cache=(cache, True, True))
+    for ref, got in ((ref_ab, got_ab), (ref_bc, got_bc)):
+        assert torch.equal(ref["raft_flow"], got["raft_flow"])
+        assert (ref["imgt_pred"] - got["imgt_pred"]).abs().max() <= 1e-6   # (splat atomics: summation order only)
+    # a stale cache must change the result (the mechanism is really in the path)
+    cache.zero_()
+    bad = eng.forward(pair(Bf, Cf), coords, tt, None, frame_cache=(cache, True, False))
+    assert not torch.equal(ref_bc["raft_flow"], bad["raft_flow"])

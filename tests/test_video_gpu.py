@@ -70,3 +70,52 @@ def test_interpolate_pair_u8_end_to_end():
     d0 = (outs[0].float() - f0.float()).abs().mean().item()
     d2 = (outs[2].float() - f0.float()).abs().mean().item()
     assert np.isfinite(d0) and np.isfinite(d2)
+
+
+def test_frame_cache_is_bit_exact_on_gpu(weights0):
+    """engine level, default precision: pair (B,C) with frame B's encoder products taken from the cache written by pair (A,B)
+    gives the same RAFT flow bit for bit (only the splat atomics' summation order may move imgt_pred, as between any two runs)"""
+    from gimmvfi_b200 import GIMMVFI_R
+    from gimmvfi_b200.synth import synth_batch
+
+    m = GIMMVFI_R(seed=0).to(DEV).eval()
+    m.load_state_dict(weights0, strict=True)
+    H, W = 256, 320
+    fr = synth_batch(2, H, W, seed=11).to(DEV)
+    A, Bf, Cf = fr[0, :, 0], fr[0, :, 1], fr[1, :, 1]
+    pair = lambda a, b: torch.stack([a, b], 1).unsqueeze(0).contiguous()
+    coord = [(m.sample_coord_input(1, (H, W), [0.5], device=DEV), None)]
+    t = [0.5 * torch.ones(1, device=DEV)]
+    ref_bc = m(pair(Bf, Cf), coord, t=t)
+    cache = torch.zeros(m.engine.frame_cache_bytes(1, H, W, 1, None, H, W), dtype=torch.uint8, device=DEV)
+    m._frame_cache = (cache, False, True)
+    m(pair(A, Bf), coord, t=t)
+    m._frame_cache = (cache, True, True)
+    got_bc = m(pair(Bf, Cf), coord, t=t)
+    m._frame_cache = None
+    assert torch.equal(ref_bc["raft_flow"], got_bc["raft_flow"])
+    assert (ref_bc["imgt_pred"][0] - got_bc["imgt_pred"][0]).abs().max().item() <= 6e-4
+
+
+def test_video_interpolator_matches_per_pair_calls(weights0):
+    """streaming clip API with the RAFT-encoder frame cache == independent interpolate_pair_u8 calls"""
+    from gimmvfi_b200 import GIMMVFI_R
+    from gimmvfi_b200.synth import synth_batch
+    from gimmvfi_b200.video import VideoInterpolator, interpolate_pair_u8
+
+    m = GIMMVFI_R(seed=0).to("cuda").eval()
+    m.load_state_dict(weights0, strict=True)
+    m.tensor_cores = 0   # fp32 CUDA cores: run-to-run jitter (splat atomics) stays ~1e-7, so uint8 outputs can be compared tightly
+    h, w = 150, 200                                   # not a multiple of 32: exercises the padder too
+    base = synth_batch(2, 160, 224, seed=21)
+    frames = [(base[0, :, 0, :h, :w].permute(1, 2, 0) * 255).round().to(torch.uint8).cuda(),
+              (base[0, :, 1, :h, :w].permute(1, 2, 0) * 255).round().to(torch.uint8).cuda(),
+              (base[1, :, 1, :h, :w].permute(1, 2, 0) * 255).round().to(torch.uint8).cuda()]
+    vi = VideoInterpolator(m, N=2)
+    assert vi.push(frames[0]) == []
+    got = [vi.push(frames[1])[0], vi.push(frames[2])[0]]
+    ref = [interpolate_pair_u8(m, frames[0], frames[1], N=2)[0], interpolate_pair_u8(m, frames[1], frames[2], N=2)[0]]
+    for a, b in zip(got, ref):
+        assert a.shape == (h, w, 3) and a.dtype == torch.uint8
+        d = (a.int() - b.int()).abs()
+        assert d.max().item() <= 1 and (d > 0).float().mean().item() < 1e-4   # at most an LSB flip on a handful of values
