@@ -100,6 +100,9 @@ struct ConvEpi {
   TV res;   // optional residual (same n,h,w as output; res.p == nullptr -> none)
   TV mul;   // optional elementwise multiplier
   TV gru_z, gru_h;  // optional GRU blend
+  // two convolutions over the same input merged along cout (SepConvGRU z | r gates): output channels >= split_c go to out2
+  // (as its channels 0..), and `mul` applies to them only.  Tensor-core path only.
+  TV out2; int split_c = 0;
 };
 
 struct ConvGeom {

@@ -238,7 +238,7 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
   a.M = out.n * out.h * out.w;
   const int cin_total = in0.c + (in1.p ? in1.c : 0);
   if (cin_total != w.cin) throw std::runtime_error("conv2d: cin mismatch (" + std::to_string(cin_total) + " vs " + std::to_string(w.cin) + ")");
-  if (out.c != w.cout) throw std::runtime_error("conv2d: cout mismatch");
+  if (e.split_c ? (out.c != e.split_c || e.out2.c != w.cout - e.split_c) : (out.c != w.cout)) throw std::runtime_error("conv2d: cout mismatch");
   {
     int eh = (in0.h + 2 * g.ph - w.kh) / g.stride + 1, ew = (in0.w + 2 * g.pw - w.kw) / g.stride + 1;
     if (((eh != out.h || ew != out.w) && !g.loose_w) || in0.n != out.n) throw std::runtime_error("conv2d: output geometry mismatch");
@@ -269,6 +269,7 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
   if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out, cx.tc_split && !any_f16)) { conv2d_tc(cx, in0, in1, w, g, e, out, cx.tc_split && !any_f16); return; }
   if (any_f16) throw std::runtime_error("conv2d: half-precision tensors are only handled by the tensor-core path (layer not eligible)");
 #endif
+  if (e.split_c) throw std::runtime_error("conv2d: merged two-output convolutions exist on the tensor-core path only");
   cx.launches++;
 #ifdef GV_HOSTSIM
   const int OH = out.h, OW = out.w, IH = in0.h, IW = in0.w;

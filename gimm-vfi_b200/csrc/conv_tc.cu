@@ -59,6 +59,7 @@ struct Params {
   int act1; const float* slope1;
   int act2; const float* slope2;
   TV res, mul, gru_z, gru_h, out;
+  TV out2; int split_c;            // channels >= split_c go to out2 (and only they see `mul`): merged z | r gate convolution
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -474,12 +475,16 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
     const int y0 = ty * TILE_H + quarter * 2, x0 = tx * TILE_W + rsub;
     const bool interior = y0 + 1 < p.H && tx * TILE_W + TILE_W <= p.W;
     const uint32_t sbase = stg_s + (uint32_t)((rsub * STG_PITCH + q8 * 4) * 4);
-    const bool lean = !p.res.p && !p.mul.p && !p.gru_z.p;
+    const bool second = p.split_c > 0 && cbase >= p.split_c;          // merged z | r convolution: this chunk belongs to out2
+    const TV& O = second ? p.out2 : p.out;
+    const int c_loc = c - (second ? p.split_c : 0);
+    const bool use_mul = p.mul.p && (p.split_c == 0 || second);
+    const bool lean = !p.res.p && !use_mul && !p.gru_z.p;
     const int64_t opix0 = (int64_t)y0 * p.W + x0;
-    const int64_t obase = (int64_t)n * p.out.sn + opix0 * p.out.ld + c;    // element offset of (row 0 of this lane, channel c)
-    const int64_t o_row = (int64_t)p.W * p.out.ld, o_x = (int64_t)4 * p.out.ld;
-    const uintptr_t oaddr = reinterpret_cast<uintptr_t>(p.out.p) + (uintptr_t)obase * (p.out.f16 ? 2 : 4);
-    const bool ovec = full4 && ((oaddr & (p.out.f16 ? 7 : 15)) == 0) && (p.out.ld % 4 == 0);
+    const int64_t obase = (int64_t)n * O.sn + opix0 * O.ld + c_loc;    // element offset of (row 0 of this lane, its first channel)
+    const int64_t o_row = (int64_t)p.W * O.ld, o_x = (int64_t)4 * O.ld;
+    const uintptr_t oaddr = reinterpret_cast<uintptr_t>(O.p) + (uintptr_t)obase * (O.f16 ? 2 : 4);
+    const bool ovec = full4 && ((oaddr & (O.f16 ? 7 : 15)) == 0) && (O.ld % 4 == 0);
     if (lean) {
       float o[32];
 #pragma unroll
@@ -498,12 +503,12 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
       for (int it = 0; it < 8; ++it) {
         const int yy = it >> 2, xx = (it & 3) * 4;
         if (!interior && (y0 + yy >= p.H || x0 + xx >= p.W)) continue;
-        store4(p.out, obase + yy * o_row + (it & 3) * o_x, o + 4 * it, c, p.cout, ovec);
+        store4(O, obase + yy * o_row + (it & 3) * o_x, o + 4 * it, c, p.cout, ovec);
       }
     } else {
       // side tensors (residual / gate / GRU state): two groups of 4 rows, every global load of a group issued before its
       // first use (one warp's epilogue is latency bound: the 2-row loop this replaces took 2x the main loop at N = 256)
-      const int64_t rbase = p.res.p ? p.res.off(n, y0, x0) + c : 0, mbase = p.mul.p ? p.mul.off(n, y0, x0) + c : 0;
+      const int64_t rbase = p.res.p ? p.res.off(n, y0, x0) + c : 0, mbase = use_mul ? p.mul.off(n, y0, x0) + c_loc : 0;
       const int64_t zbase = p.gru_z.p ? p.gru_z.off(n, y0, x0) + c : 0, hbase = p.gru_z.p ? p.gru_h.off(n, y0, x0) + c : 0;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -527,7 +532,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
           for (int u = 0; u < 16; ++u) o[u] += t[u];
         }
         if (p.act2 != ACT_NONE) act_rows<4>(o, p.act2, p.slope2, c, p.cout);
-        if (p.mul.p) {
+        if (use_mul) {
           float t[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -558,7 +563,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (ok[j]) store4(p.out, obase + g * o_row + j * o_x, o + 4 * j, c, p.cout, ovec);
+          if (ok[j]) store4(O, obase + g * o_row + j * o_x, o + 4 * j, c, p.cout, ovec);
       }
     }
   }
@@ -1048,6 +1053,7 @@ bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const Con
   if (h && (split || !w.w_tc_h)) return false;
   if (in1.p && (in1.f16 != 0) != h) return false;
   if (e.mul.f16 || e.gru_z.f16 || e.gru_h.f16) return false;   // only the residual may be half
+  if (e.split_c && (e.split_c % 32 || !e.out2.p || e.out2.f16 || e.res.p || e.gru_z.p)) return false;
   if (!al16(in0.p) || in0.ld % amul || in0.sn % amul) return false;
   if (in1.p && (!al16(in1.p) || in1.ld % amul || in1.sn % amul || in0.c % kblk)) return false;
   if (!g.loose_w && ((in0.h + 2 * g.ph - w.kh) / g.stride + 1 != out.h || (in0.w + 2 * g.pw - w.kw) / g.stride + 1 != out.w)) return false;
@@ -1099,7 +1105,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = split ? tc_atmem() : 0; p.stall = tc_stall_buf();
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2;
-  p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out;
+  p.res = e.res; p.mul = e.mul; p.gru_z = e.gru_z; p.gru_h = e.gru_h; p.out = out; p.out2 = e.out2; p.split_c = e.split_c;
   // 3xTF32: 8 drain/epilogue warps help K-poor layers (+20-30 %) but steal issue slots from the splitter warps on
   // K-rich full-width tiles (SepConvGRU gates: -15 %): measured in profiles/r01_tc_microbench_split_epi8.log
   const bool sew8 = split && tc_epi8() && tc_split_epi8() && (tc_split_epi8() == 2 || !(BN == 128 && taps * (w.cin_pad / 32) >= 48));
@@ -1180,7 +1186,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = atm ? 1 : 0; p.stall = tc_stall_buf();
   p.bias = zero_bias; p.act1 = ACT_NONE; p.slope1 = nullptr; p.act2 = ACT_NONE; p.slope2 = nullptr;
-  p.out = make_tv(vol, 1, fa.h, fa.w, N, N);
+  p.out = make_tv(vol, 1, fa.h, fa.w, N, N); p.out2 = TV(); p.split_c = 0;
   const int bn_cta = pair ? BN / 2 : BN;
   const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * bn_cta * BK * 4) : (A_BYTES + bn_cta * BK * 4);
   const int stg_bytes = (e8 ? 8 : 4) * STG_WARP_BYTES;
