@@ -257,6 +257,7 @@ void Engine::pack_stem(const std::string& name, const std::string& bn) {
   }
   ConvW c;
   c.w = upload(pw); c.b = upload(pb); c.cin = K; c.cout = cout; c.kh = kh; c.kw = 1; c.cout_ld = cout_ld;
+  pack_tc(c, pw);   // stride 2 runs on the tensor-core path too (TMA element strides)
   conv_[name + "#xpacked"] = c;
 }
 
