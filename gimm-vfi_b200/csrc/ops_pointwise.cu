@@ -97,7 +97,16 @@ struct CopyK {
     dst.p[dst.off(q.n, q.y, q.x) + q.c] = src.p[src.off(q.n, q.y, q.x) + q.c];
   }
 };
+struct CopyK4 {
+  TV src, dst;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c / 4);
+    st4(dst.p + dst.off(q.n, q.y, q.x) + q.c * 4, ld4(src.p + src.off(q.n, q.y, q.x) + q.c * 4));
+  }
+};
 void copy_channels(Ctx& cx, const TV& src, const TV& dst) {
+  TV s4 = src; s4.c = dst.c;
+  if (vec4_ok(s4) && vec4_ok(dst)) { parallel_for(cx, dst.pixels() * (dst.c / 4), CopyK4{src, dst}, "copy_channels"); return; }
   parallel_for(cx, dst.pixels() * dst.c, CopyK{src, dst}, "copy_channels");
 }
 
@@ -156,7 +165,17 @@ struct PadReflectK {
     dst.p[dst.off(q.n, q.y, q.x) + q.c] = src.p[src.off(q.n, y, x) + q.c];
   }
 };
+struct PadReflectK4 {
+  TV src, dst; int pad;
+  GV_HD int refl(int v, int n) const { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c / 4);
+    int y = refl(q.y - pad, src.h), x = refl(q.x - pad, src.w);
+    st4(dst.p + dst.off(q.n, q.y, q.x) + q.c * 4, ld4(src.p + src.off(q.n, y, x) + q.c * 4));
+  }
+};
 void pad_reflect(Ctx& cx, const TV& src, const TV& dst, int pad) {
+  if (vec4_ok(src) && vec4_ok(dst)) { parallel_for(cx, dst.pixels() * (dst.c / 4), PadReflectK4{src, dst, pad}, "pad_reflect"); return; }
   parallel_for(cx, dst.pixels() * dst.c, PadReflectK{src, dst, pad}, "pad_reflect");
 }
 
@@ -222,7 +241,44 @@ struct ResizeK {
     *o = accumulate ? (*o + v) : v;
   }
 };
+struct ResizeK4 {   // 4 channels per thread, the per-component arithmetic of ResizeK unchanged
+  TV src, dst; float rsy, rsx, mult; int accumulate, act;
+  GV_HD float fin(float v00, float v01, float v10, float v11, float lx0, float lx1, float ly0, float ly1, float old) const {
+    float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    v *= mult;
+    if (act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+    return accumulate ? (old + v) : v;
+  }
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c / 4);
+    float sy = rsy * ((float)q.y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+    float sx = rsx * ((float)q.x + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+    int y0 = (int)sy, x0 = (int)sx;
+    if (y0 > src.h - 1) y0 = src.h - 1;
+    if (x0 > src.w - 1) x0 = src.w - 1;
+    int y1 = y0 + (y0 < src.h - 1 ? 1 : 0), x1 = x0 + (x0 < src.w - 1 ? 1 : 0);
+    float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+    float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* b = src.p + (int64_t)q.n * src.sn + q.c * 4;
+    const F4 a00 = ld4(b + ((int64_t)y0 * src.w + x0) * src.ld), a01 = ld4(b + ((int64_t)y0 * src.w + x1) * src.ld);
+    const F4 a10 = ld4(b + ((int64_t)y1 * src.w + x0) * src.ld), a11 = ld4(b + ((int64_t)y1 * src.w + x1) * src.ld);
+    float* o = dst.p + dst.off(q.n, q.y, q.x) + q.c * 4;
+    F4 old = {0.f, 0.f, 0.f, 0.f};
+    if (accumulate) old = ld4(o);
+    F4 r;
+    r.x = fin(a00.x, a01.x, a10.x, a11.x, lx0, lx1, ly0, ly1, old.x); r.y = fin(a00.y, a01.y, a10.y, a11.y, lx0, lx1, ly0, ly1, old.y);
+    r.z = fin(a00.z, a01.z, a10.z, a11.z, lx0, lx1, ly0, ly1, old.z); r.w = fin(a00.w, a01.w, a10.w, a11.w, lx0, lx1, ly0, ly1, old.w);
+    st4(o, r);
+  }
+};
 void resize_bilinear(Ctx& cx, const TV& src, const TV& dst, float rscale_y, float rscale_x, float mult, int accumulate, int act) {
+  {
+    TV s4 = src; s4.c = dst.c;
+    if (vec4_ok(s4) && vec4_ok(dst)) {
+      parallel_for(cx, dst.pixels() * (dst.c / 4), ResizeK4{src, dst, rscale_y, rscale_x, mult, accumulate, act}, "resize_bilinear");
+      return;
+    }
+  }
   parallel_for(cx, dst.pixels() * dst.c, ResizeK{src, dst, rscale_y, rscale_x, mult, accumulate, act}, "resize_bilinear");
 }
 
@@ -237,7 +293,27 @@ struct BackwarpK {
     dst.p[dst.off(q.n, q.y, q.x) + q.c] = tap_fetch(src, q.n, t, q.c);
   }
 };
+struct BackwarpK4 {   // 4 channels per thread; same tap order / products as tap_fetch
+  TV src, flow, dst;
+  GV_HD void acc(F4& v, const float* p, float w) const { const F4 a = ld4(p); v.x += a.x * w; v.y += a.y * w; v.z += a.z * w; v.w += a.w * w; }
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c / 4);
+    const float* f = flow.p + flow.off(q.n, q.y, q.x);
+    const BilinearTap t = border_tap(q.x, q.y, f[0], f[1], flow.w, flow.h, src.w, src.h);
+    const float* b = src.p + (int64_t)q.n * src.sn + q.c * 4;
+    F4 v = {0.f, 0.f, 0.f, 0.f};
+    if (t.vy0 && t.vx0) acc(v, b + ((int64_t)t.y0 * src.w + t.x0) * src.ld, t.wx0 * t.wy0);
+    if (t.vy0 && t.vx1) acc(v, b + ((int64_t)t.y0 * src.w + t.x1) * src.ld, t.wx1 * t.wy0);
+    if (t.vy1 && t.vx0) acc(v, b + ((int64_t)t.y1 * src.w + t.x0) * src.ld, t.wx0 * t.wy1);
+    if (t.vy1 && t.vx1) acc(v, b + ((int64_t)t.y1 * src.w + t.x1) * src.ld, t.wx1 * t.wy1);
+    st4(dst.p + dst.off(q.n, q.y, q.x) + q.c * 4, v);
+  }
+};
 void backwarp(Ctx& cx, const TV& src, const TV& flow, const TV& dst) {
+  {
+    TV s4 = src; s4.c = dst.c;
+    if (vec4_ok(s4) && vec4_ok(dst)) { parallel_for(cx, dst.pixels() * (dst.c / 4), BackwarpK4{src, flow, dst}, "backwarp"); return; }
+  }
   parallel_for(cx, dst.pixels() * dst.c, BackwarpK{src, flow, dst}, "backwarp");
 }
 
@@ -322,7 +398,33 @@ struct InApplyK {
     out.p[out.off(q.n, q.y, q.x) + q.c] = v;
   }
 };
+struct InApplyK4 {
+  TV x, res, out; const float* mr; int act1, act2;
+  GV_HD float one(float xv, float m, float r, float rv) const {
+    float v = (xv - m) * r;
+    v = apply_act(v, act1, nullptr, 0);
+    if (res.p) v += rv;
+    return apply_act(v, act2, nullptr, 0);
+  }
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, out.h, out.w, out.c / 4);
+    const int c = q.c * 4;
+    const float* s = mr + ((int64_t)q.n * x.c + c) * 2;   // (mean, rstd) pairs of 4 consecutive channels
+    const F4 s01 = ld4(s), s23 = ld4(s + 4);
+    const F4 a = ld4(x.p + x.off(q.n, q.y, q.x) + c);
+    F4 rv = {0.f, 0.f, 0.f, 0.f};
+    if (res.p) rv = ld4(res.p + res.off(q.n, q.y, q.x) + c);
+    F4 o;
+    o.x = one(a.x, s01.x, s01.y, rv.x); o.y = one(a.y, s01.z, s01.w, rv.y);
+    o.z = one(a.z, s23.x, s23.y, rv.z); o.w = one(a.w, s23.z, s23.w, rv.w);
+    st4(out.p + out.off(q.n, q.y, q.x) + c, o);
+  }
+};
 void instnorm_apply(Ctx& cx, const TV& x, const float* mean_rstd, int act1, const TV& res, int act2, const TV& out) {
+  if (vec4_ok(x) && vec4_ok(out) && (!res.p || vec4_ok(res)) && (reinterpret_cast<uintptr_t>(mean_rstd) & 15) == 0 && x.c == out.c) {
+    parallel_for(cx, out.pixels() * (out.c / 4), InApplyK4{x, res, out, mean_rstd, act1, act2}, "instnorm_apply");
+    return;
+  }
   parallel_for(cx, out.pixels() * out.c, InApplyK{x, res, out, mean_rstd, act1, act2}, "instnorm_apply");
 }
 
