@@ -318,7 +318,7 @@ def main():
         line = {
             "metric": METRIC, "value": world * B * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "3xtf32": "tf32", "mixed": "tf32+f16 operands, f32 accumulate"}[args.precision], "data": "synthetic",
-            "config": {"precision": {"tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.4e-4 at this size (profiles/r01_parity_1080p.log)", "fp32": "fp32 everywhere", "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere; parity vs CPU reference in profiles/r01_parity_1080p_modes.log", "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.5e-4 at this size, PSNR 81.7 dB (profiles/r01_parity_1080p_modes.log)"}[args.precision], "workload": "%d x 1920x1080 pair per GPU (padded %dx%d), t=0.5, T=1, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
+            "config": {"precision": {"tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.4e-4 at this size (profiles/r01_parity_1080p.log)", "fp32": "fp32 everywhere", "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere; max|d imgt_pred| vs CPU reference 5.9e-4 at this size, PSNR 81.2 dB (profiles/r01_parity_1080p_mode3_final.log)", "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.5e-4 at this size, PSNR 81.7 dB (profiles/r01_parity_1080p_modes.log)"}[args.precision], "workload": "%d x 1920x1080 pair per GPU (padded %dx%d), t=0.5, T=1, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
                                    % (B, H, W), "parallelism": "pairs sharded, 1 all-gather of output frames" if world > 1 else "single GPU",
                        "l2": "256 MiB L2 flush between timed steps; per-step working set ~30 GB >> L2",
                        "algorithmic_tflop_per_frame": fl / 1e12, "achieved_tflops_end_to_end": world * fl / (ms * 1e-3) / 1e12},

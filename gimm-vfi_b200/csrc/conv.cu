@@ -168,31 +168,6 @@ __global__ void __launch_bounds__(256) conv_narrow_kernel(ConvArgs a, int warps_
   for (int m = blockIdx.x * wpb + wib; m < warps_total; m += gridDim.x * wpb) {
     const int ox = m % OW; int r = m / OW; const int oy = r % OH; const int n = r / OH;
     float acc0 = 0.f, acc1 = 0.f;
-    if (a.w.kh == 3 && a.w.kw == 3 && cin == 256) {
-      // FlowHead.conv2: all 18 activation loads of the lane are issued before the first use (predicated zero outside the image)
-      float4 v[18];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int iy = oy + t / 3 - a.g.ph, ix = ox + t % 3 - a.g.pw;
-        const bool in = iy >= 0 && iy < a.in0.h && ix >= 0 && ix < a.in0.w;
-        const float* src = a.in0.p + a.in0.off(n, in ? iy : 0, in ? ix : 0) + lane * 4;
-        v[2 * t] = in ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[2 * t + 1] = in ? *reinterpret_cast<const float4*>(src + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const float2* wt = wsm + t * 256 + hf * 128 + lane * 4;
-          const float4 w01 = *reinterpret_cast<const float4*>(wt), w23 = *reinterpret_cast<const float4*>(wt + 2);
-          const float4 x = v[2 * t + hf];
-          acc0 = fmaf(x.x, w01.x, acc0); acc1 = fmaf(x.x, w01.y, acc1);
-          acc0 = fmaf(x.y, w01.z, acc0); acc1 = fmaf(x.y, w01.w, acc1);
-          acc0 = fmaf(x.z, w23.x, acc0); acc1 = fmaf(x.z, w23.y, acc1);
-          acc0 = fmaf(x.w, w23.z, acc0); acc1 = fmaf(x.w, w23.w, acc1);
-        }
-      }
-    } else
     for (int ky = 0; ky < a.w.kh; ++ky) {
       const int iy = oy + ky - a.g.ph;
       if (iy < 0 || iy >= a.in0.h) continue;
@@ -221,12 +196,127 @@ __global__ void __launch_bounds__(256) conv_narrow_kernel(ConvArgs a, int warps_
   }
 }
 
+
+// FlowHead.conv2 shape (3x3, 256 -> 2): one warp computes FOUR horizontally adjacent output pixels, so the 3 x 6 input pixels
+// and the lane's 18 x 8 weights are fetched once for four outputs (3x fewer load instructions than one pixel per warp).
+__global__ void __launch_bounds__(256, 2) conv_narrow3x3_c256_kernel(ConvArgs a, int quads_per_row, int quads_total) {
+  extern __shared__ float2 wsm[];   // [tap * 256 + ci] -> (w[co 0], w[co 1])
+  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) {
+    const float* wp = a.w.w + (size_t)i * a.w.cout_ld;
+    wsm[i] = make_float2(wp[0], a.w.cout > 1 ? wp[1] : 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int OW = a.out.w, OH = a.out.h;
+  for (int qd = blockIdx.x * wpb + wib; qd < quads_total; qd += gridDim.x * wpb) {
+    const int qx = qd % quads_per_row; int r = qd / quads_per_row; const int oy = r % OH; const int n = r / OH;
+    const int ox0 = qx * 4;
+    float acc[4][2];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { acc[p][0] = 0.f; acc[p][1] = 0.f; }
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {          // the lane's channels: hf * 128 + lane * 4 .. + 3
+      float4 v[3][6];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int iy = oy + dy - 1;
+#pragma unroll
+        for (int dx = 0; dx < 6; ++dx) {
+          const int ix = ox0 + dx - 1;
+          const bool in = iy >= 0 && iy < a.in0.h && ix >= 0 && ix < a.in0.w;
+          v[dy][dx] = in ? *reinterpret_cast<const float4*>(a.in0.p + a.in0.off(n, iy, ix) + hf * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float2* wt = wsm + t * 256 + hf * 128 + lane * 4;
+        const float4 w01 = *reinterpret_cast<const float4*>(wt), w23 = *reinterpret_cast<const float4*>(wt + 2);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float4 x = v[t / 3][p + t % 3];
+          acc[p][0] = fmaf(x.x, w01.x, acc[p][0]); acc[p][1] = fmaf(x.x, w01.y, acc[p][1]);
+          acc[p][0] = fmaf(x.y, w01.z, acc[p][0]); acc[p][1] = fmaf(x.y, w01.w, acc[p][1]);
+          acc[p][0] = fmaf(x.z, w23.x, acc[p][0]); acc[p][1] = fmaf(x.z, w23.y, acc[p][1]);
+          acc[p][0] = fmaf(x.w, w23.z, acc[p][0]); acc[p][1] = fmaf(x.w, w23.w, acc[p][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { acc[p][0] += __shfl_xor_sync(0xffffffffu, acc[p][0], o); acc[p][1] += __shfl_xor_sync(0xffffffffu, acc[p][1], o); }
+    if (lane < 4 * a.w.cout) {     // lane = pixel * cout + channel
+      const int p = lane / a.w.cout, co = lane % a.w.cout, ox = ox0 + p;
+      if (ox < OW) {
+        float val = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) if (pp == p) val = co == 0 ? acc[pp][0] : acc[pp][1];
+        val += a.w.b[co];
+        if (a.e.res.p) val += a.e.res.p[a.e.res.off(n, oy, ox) + co];
+        a.out.p[a.out.off(n, oy, ox) + co] = val;
+      }
+    }
+  }
+}
+
 static bool conv_narrow_ok(const ConvArgs& a) {
   const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   return a.w.cout <= 2 && !a.in1.p && a.g.stride == 1 && !a.g.reflect && !a.g.loose_w && a.w.cin % 128 == 0 && a.in0.ld % 4 == 0 && a.in0.sn % 4 == 0 &&
          al16(a.in0.p) && a.e.act1 == ACT_NONE && a.e.act2 == ACT_NONE && !a.e.mul.p && !a.e.gru_z.p && !a.in0.f16 && !a.out.f16 && !a.e.res.f16 &&
          (size_t)a.w.kh * a.w.kw * a.w.cin * sizeof(float2) <= 96 * 1024 &&
          a.w.kh * a.w.kw * a.w.cin >= 1024;   // (a full-resolution 1x1 with few channels is better off as one MMA tile per 128 pixels)
+}
+#endif
+
+
+#ifndef GV_HOSTSIM
+// Convolutions with very few input channels (GIMM cnn_encoder.0: 3x3, 2 -> 16 at full resolution, gimmvfi_r.py:86-88): the
+// layer is pure memory traffic (18 MACs per output value), so one thread owns one output pixel: taps are scalar loads that
+// hit L1 (neighbouring threads share them), weights + bias live in shared memory, the COUT results leave as float4 stores.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_thin_kernel(ConvArgs a) {
+  extern __shared__ float wth[];   // [tap * cin + ci][COUT] then bias[COUT]
+  const int cin = a.w.cin, taps = a.w.kh * a.w.kw;
+  for (int i = threadIdx.x; i < taps * cin * COUT; i += blockDim.x) wth[i] = a.w.w[(size_t)(i / COUT) * a.w.cout_ld + (i % COUT)];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) wth[taps * cin * COUT + i] = a.w.b[i];
+  __syncthreads();
+  const int OW = a.out.w, OH = a.out.h;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += gridDim.x * blockDim.x) {
+    const int ox = m % OW; int r = m / OW; const int oy = r % OH; const int n = r / OH;
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < a.w.kh; ++ky) {
+      const int iy = oy + ky - a.g.ph;
+      if (iy < 0 || iy >= a.in0.h) continue;
+      for (int kx = 0; kx < a.w.kw; ++kx) {
+        const int ix = ox + kx - a.g.pw;
+        if (ix < 0 || ix >= a.in0.w) continue;
+        const float* src = a.in0.p + a.in0.off(n, iy, ix);
+        const float* wt = wth + (ky * a.w.kw + kx) * cin * COUT;
+        for (int c = 0; c < cin; ++c) {
+          const float v = src[c];
+#pragma unroll
+          for (int j = 0; j < COUT; ++j) acc[j] = fmaf(v, wt[c * COUT + j], acc[j]);
+        }
+      }
+    }
+    float* o = a.out.p + a.out.off(n, oy, ox);
+#pragma unroll
+    for (int j = 0; j < COUT; j += 4) {
+      F4 v;
+      v.x = apply_act(acc[j] + wth[taps * cin * COUT + j], a.e.act1, a.e.slope1, j);
+      v.y = apply_act(acc[j + 1] + wth[taps * cin * COUT + j + 1], a.e.act1, a.e.slope1, j + 1);
+      v.z = apply_act(acc[j + 2] + wth[taps * cin * COUT + j + 2], a.e.act1, a.e.slope1, j + 2);
+      v.w = apply_act(acc[j + 3] + wth[taps * cin * COUT + j + 3], a.e.act1, a.e.slope1, j + 3);
+      st4(o + j, v);
+    }
+  }
+}
+static bool conv_thin_ok(const ConvArgs& a) {
+  return a.w.cout == 16 && a.w.cin <= 4 && !a.in1.p && a.g.stride == 1 && !a.g.reflect && !a.g.loose_w && !a.e.res.p && !a.e.mul.p && !a.e.gru_z.p &&
+         a.e.act2 == ACT_NONE && a.e.act1 != ACT_SIGMOID && a.e.act1 != ACT_TANH && a.e.act1 != ACT_SIN && !a.in0.f16 && !a.out.f16 &&
+         (reinterpret_cast<uintptr_t>(a.out.p) & 15) == 0 && a.out.ld % 4 == 0 && a.out.sn % 4 == 0;
 }
 #endif
 
@@ -259,9 +349,28 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
       cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)a.M * w.cout * (double)w.cin * w.kh * w.kw);
     }
     const int blocks = std::min((a.M + 7) / 8, cx.sm_count * 8);
-    if (w.cout == 1) conv_narrow_kernel<1><<<blocks, 256, smem, cx.stream>>>(a, a.M);
+    if (w.kh == 3 && w.kw == 3 && w.cin == 256 && g.ph == 1 && g.pw == 1) {
+      const int qpr = (out.w + 3) / 4, quads = out.n * out.h * qpr;
+      static bool attr4 = false;
+      if (!attr4) { cudaFuncSetAttribute(conv_narrow3x3_c256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr4 = true; }
+      conv_narrow3x3_c256_kernel<<<std::min((quads + 7) / 8, cx.sm_count * 8), 256, smem, cx.stream>>>(a, qpr, quads);
+    } else if (w.cout == 1) conv_narrow_kernel<1><<<blocks, 256, smem, cx.stream>>>(a, a.M);
     else conv_narrow_kernel<2><<<blocks, 256, smem, cx.stream>>>(a, a.M);
     gv_check_launch("conv_narrow");
+    if (cx.prof) cx.prof->end(cx.stream);
+    return;
+  }
+  if (conv_thin_ok(a)) {
+    cx.launches++;
+    const size_t smem = ((size_t)w.kh * w.kw * w.cin + 1) * 16 * sizeof(float);
+    if (cx.prof) {
+      char nm[128];
+      snprintf(nm, sizeof nm, "conv_thin k%dx%d c%d>%d @%dx%dx%d", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
+      cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)a.M * w.cout * (double)w.cin * w.kh * w.kw);
+    }
+    const int blocks = std::min((a.M + 255) / 256, cx.sm_count * 16);
+    conv_thin_kernel<16><<<blocks, 256, smem, cx.stream>>>(a);
+    gv_check_launch("conv_thin");
     if (cx.prof) cx.prof->end(cx.stream);
     return;
   }

@@ -182,3 +182,17 @@ def test_conv_narrow_cout(case):
     if use_res:
         ref = ref + res.double()
     assert (got.double() - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("case", [(2, 16, 3, 40, 56, 2, 0), (3, 16, 3, 17, 23, 1, 2), (4, 16, 5, 16, 20, 1, 1)])
+def test_conv_thin_cin(case):
+    """very few input channels, 16 outputs (GIMM cnn_encoder.0: 3x3 2 -> 16, gimmvfi_r.py:86-88): thread-per-pixel fp32 kernel"""
+    cin, cout, k, H, W, n, act = case
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(n, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    b = (0.1 * torch.randn(cout, generator=g)).cuda()
+    got = K.nchw(K.conv2d(K.nhwc(x), w, b, pad=(k // 2, k // 2), act=act))
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2)
+    ref = {0: lambda v: v, 1: F.relu, 2: lambda v: F.leaky_relu(v, 0.1)}[act](ref)
+    assert (got.double() - ref).abs().max().item() <= 2e-5
