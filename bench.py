@@ -150,6 +150,9 @@ def main():
                          "tcgen05 kind::f16; 3xtf32: the trunk in TF32 too; tf32: RAFT on fp32 CUDA cores instead; fp32: everything on "
                          "fp32 CUDA cores.  All meet max|d imgt_pred| <= 1e-3 vs the reference (profiles/).")
     ap.add_argument("--profile-json", default="", help="write the per-kernel CUDA-event breakdown here")
+    ap.add_argument("--timesteps", type=int, default=1,
+                    help="T interpolated frames per pair at t = i/(T+1): 1 = the headline metric (t=0.5); 7 = the reference's N=8 video setting "
+                         "(flow estimation amortised over 7 frames; secondary figure, profiles/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -169,19 +172,20 @@ def main():
     from gimmvfi_b200 import GIMMVFI_R
     from gimmvfi_b200.synth import synth_pair
 
-    H, W, B, T, tval = args.height, args.width, 1, 1, 0.5
+    H, W, B, T, tval = args.height, args.width, 1, max(1, args.timesteps), 0.5
+    tvals = [0.5] if T == 1 else [i / (T + 1) for i in range(1, T + 1)]
     model = GIMMVFI_R(seed=0).to(dev).eval()
     model.tensor_cores = {"fp32": 0, "tf32": 1, "3xtf32": 2, "mixed": 3}[args.precision]
     xs_host = synth_pair(H, W, seed=100 + rank).pin_memory()
     xs = xs_host.to(dev, non_blocking=True)
-    coord = [(model.sample_coord_input(B, (H, W), [tval], device=dev), None)]
-    tt = [tval * torch.ones(B, device=dev)]
-    gathered = torch.empty(world * B, 3, H, W, device=dev) if world > 1 else None
+    coord = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
+    tt = [tv * torch.ones(B, device=dev) for tv in tvals]
+    gathered = torch.empty(world * B * T, 3, H, W, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step():
         out = model(xs, coord, t=tt)
-        img = out["imgt_pred"][0]
+        img = torch.stack(out["imgt_pred"], 0).reshape(-1, 3, H, W) if T > 1 else out["imgt_pred"][0]
         if world > 1:
             dist.all_gather_into_tensor(gathered, img.contiguous())   # the single output collective
         return img
@@ -216,7 +220,7 @@ def main():
     # The loop is what a video caller runs (src/video_Nx.py:134-216 of the reference walks consecutive pairs): the copies of
     # step i+1 / i-1 travel on a second stream while step i computes; nothing is reused across steps and the whole K-step
     # region (all copies included) is timed by the wall clock between two full synchronisations.
-    out_host = [torch.empty(B, 3, H, W).pin_memory() for _ in range(2)]
+    out_host = [torch.empty(B * T, 3, H, W).pin_memory() for _ in range(2)]
     x_dev = [torch.empty_like(xs) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
@@ -241,9 +245,9 @@ def main():
         main_stream.wait_event(ev_in[i % 2])
         if i + 1 < args.steps:
             h2d(i + 1)
-        c = [(model.sample_coord_input(B, (H, W), [tval], device=dev), None)]
-        o = model(x_dev[i % 2], c, t=[tval * torch.ones(B, device=dev)])
-        img = o["imgt_pred"][0]
+        c = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
+        o = model(x_dev[i % 2], c, t=[tv * torch.ones(B, device=dev) for tv in tvals])
+        img = torch.stack(o["imgt_pred"], 0).reshape(-1, 3, H, W) if T > 1 else o["imgt_pred"][0]
         if world > 1:
             dist.all_gather_into_tensor(gathered, img.contiguous())
         ev_free[i % 2].record(main_stream)
@@ -318,8 +322,8 @@ def main():
         line = {
             "metric": METRIC, "value": world * B * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "3xtf32": "tf32", "mixed": "tf32+f16 operands, f32 accumulate"}[args.precision], "data": "synthetic",
-            "config": {"precision": {"tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.4e-4 at this size (profiles/r01_parity_1080p.log)", "fp32": "fp32 everywhere", "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere; max|d imgt_pred| vs CPU reference 5.9e-4 at this size, PSNR 81.2 dB (profiles/r01_parity_1080p_mode3_final.log)", "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.5e-4 at this size, PSNR 81.7 dB (profiles/r01_parity_1080p_modes.log)"}[args.precision], "workload": "%d x 1920x1080 pair per GPU (padded %dx%d), t=0.5, T=1, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
-                                   % (B, H, W), "parallelism": "pairs sharded, 1 all-gather of output frames" if world > 1 else "single GPU",
+            "config": {"precision": {"tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.4e-4 at this size (profiles/r01_parity_1080p.log)", "fp32": "fp32 everywhere", "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere; max|d imgt_pred| vs CPU reference 5.9e-4 at this size, PSNR 81.2 dB (profiles/r01_parity_1080p_mode3_final.log)", "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.5e-4 at this size, PSNR 81.7 dB (profiles/r01_parity_1080p_modes.log)"}[args.precision], "workload": "%d x 1920x1080 pair per GPU (padded %dx%d), %s, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
+                                   % (B, H, W, "t=0.5, T=1" if T == 1 else "T=%d frames per pair at t=i/%d" % (T, T + 1)), "parallelism": "pairs sharded, 1 all-gather of output frames" if world > 1 else "single GPU",
                        "l2": "256 MiB L2 flush between timed steps; per-step working set ~30 GB >> L2",
                        "algorithmic_tflop_per_frame": fl / 1e12, "achieved_tflops_end_to_end": world * fl / (ms * 1e-3) / 1e12},
             "e2e": {"value": world * B * T / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": xs_host.numel() * 4,
