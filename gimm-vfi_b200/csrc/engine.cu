@@ -682,6 +682,9 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     const bool fc_on = fc_ != nullptr && !cx.dry;
     if (fc_on && fc_bytes_ < frame_cache_bytes(P)) throw std::runtime_error("gimmvfi: frame cache smaller than frame_cache_bytes()");
     const bool fload = fc_on && fc_load_, fstore = fc_on && fc_store_;
+    if (fload && (fc_valid_ptr_ != fc_ || fc_valid_dims_[0] != B || fc_valid_dims_[1] != H || fc_valid_dims_[2] != W || fc_valid_dims_[3] != tc_mode_))
+      throw std::runtime_error("gimmvfi: frame cache load requested, but this buffer does not hold a frame stored by a forward of the same "
+                               "problem size and precision mode");
     const int e0 = fload ? B : 0, en = fload ? B : 2 * B;
     {
       TV rin = raft_in.batch(e0, en);
@@ -705,6 +708,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
         copy_channels(cx, c_fmap, fmap.batch(0, B)); copy_channels(cx, c_ni, hx.batch(0, B).slice(0, 256));
         copy_channels(cx, c_f4, feat4.batch(0, B)); copy_channels(cx, c_f8, feat8.batch(0, B));
       }
+      if (fstore) { fc_valid_ptr_ = fc_; fc_valid_dims_[0] = B; fc_valid_dims_[1] = H; fc_valid_dims_[2] = W; fc_valid_dims_[3] = tc_mode_; }
       if (fstore) {   // (before the GRU overwrites `net` in place)
         copy_channels(cx, fmap.batch(B, B), c_fmap); copy_channels(cx, hx.batch(B, B).slice(0, 256), c_ni);
         copy_channels(cx, feat4.batch(B, B), c_f4); copy_channels(cx, feat8.batch(B, B), c_f8);

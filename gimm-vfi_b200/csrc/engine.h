@@ -81,6 +81,8 @@ class Engine {
   bool finalized_ = false, debug_ = false, profile_ = false;
   int tc_mode_ = 0;
   float* fc_ = nullptr; size_t fc_bytes_ = 0; bool fc_load_ = false, fc_store_ = false;
+  // what the cache holds (host-side bookkeeping of the last store): a load with a different buffer / problem is refused
+  const float* fc_valid_ptr_ = nullptr; int fc_valid_dims_[4] = {0, 0, 0, 0};
   void pack_tc(ConvW& c, const std::vector<float>& packed);
   void pack_tc_f16(ConvW& c, const std::vector<float>& packed);
   void pack_stem(const std::string& name, const std::string& bn);

@@ -110,10 +110,14 @@ class VideoInterpolator:
         if self._cache is None or self._cache.numel() < need or self._cache.device != dev:
             self._cache, self._cache_valid = torch.empty(need, dtype=torch.uint8, device=dev), False
         aux, m.aux_outputs = m.aux_outputs, False
-        m._frame_cache = (self._cache, self._cache_valid, True)
+        # (the engine keeps its own record of what the buffer holds: a model whose engine was rebuilt, or whose precision mode
+        # changed, refuses the load -> fall back to a full forward once)
+        sig = (id(m.engine), int(m.tensor_cores))
+        load = self._cache_valid and getattr(self, "_cache_sig", None) == sig
+        m._frame_cache = (self._cache, load, True)
         try:
             out = m(xs, coords, t=ts, ds_factor=self.ds)
-            self._cache_valid = True
+            self._cache_valid, self._cache_sig = True, sig
         except Exception:
             self._cache_valid = False
             raise

@@ -72,7 +72,12 @@ def test_frame_cache_reuses_second_frame_bit_exactly(eng):
     for ref, got in ((ref_ab, got_ab), (ref_bc, got_bc)):
         assert torch.equal(ref["raft_flow"], got["raft_flow"])
         assert (ref["imgt_pred"] - got["imgt_pred"]).abs().max() <= 1e-6   # (splat atomics: summation order only)
-    # a stale cache must change the result (the mechanism is really in the path)
+    # a cache with other content must change the result (the mechanism is really in the path)
     cache.zero_()
     bad = eng.forward(pair(Bf, Cf), coords, tt, None, frame_cache=(cache, True, False))
     assert not torch.equal(ref_bc["raft_flow"], bad["raft_flow"])
+    # a buffer no forward has stored into is refused
+    from gimmvfi_b200._lib import GimmvfiError
+    other = torch.zeros_like(cache)
+    with pytest.raises(GimmvfiError):
+        eng.forward(pair(Bf, Cf), coords, tt, None, frame_cache=(other, True, False))
