@@ -10,6 +10,10 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         from . import model
 
         return getattr(model, name)
+    if name == "GIMM":
+        from .gimm import GIMM
+
+        return GIMM
     if name == "EngineHandle":
         from .engine import EngineHandle
 

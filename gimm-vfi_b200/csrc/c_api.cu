@@ -64,6 +64,18 @@ int gimmvfi_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_i
   })
 }
 
+int gimmvfi_finalize_weights_gimm(gimmvfi_engine* e) { GV_TRY(e, { e->eng.finalize_weights_gimm(); }) }
+int gimmvfi_gimm_plan(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes) {
+  GV_TRY(e, { *workspace_bytes = e->eng.plan_gimm(to_problem(p)); })
+}
+int gimmvfi_gimm_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const float* xs, const float* ori_flow, const float* coords, const float* t,
+                         float* out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  GV_TRY(e, {
+    GimmIO q; q.xs = xs; q.ori_flow = ori_flow; q.coords = coords; q.t = t; q.out = out;
+    e->eng.forward_gimm(to_problem(p), q, workspace, workspace_bytes, (gvStream_t)cuda_stream);
+  })
+}
+
 const char* gimmvfi_last_error(gimmvfi_engine* e) { return e ? e->err.c_str() : g_static_err.c_str(); }
 int64_t gimmvfi_last_launches(gimmvfi_engine* e) { return e->eng.last_launches(); }
 int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters) { GV_TRY(e, { if (iters < 1) throw std::runtime_error("iters must be >= 1"); e->eng.raft_iters = iters; }) }

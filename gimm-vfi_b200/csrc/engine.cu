@@ -351,6 +351,12 @@ void Engine::finalize_weights() {
   pack_conv("amt_comb_block.0"); vec("amt_comb_block.1.weight"); pack_conv("amt_comb_block.2");
   pack_xpacked("amt_comb_block.0", 12); pack_xpacked("amt_comb_block.2", 20);
   pack_xpacked("amt_update4_low.convf1", 4); pack_xpacked("amt_update4_high.convf1", 4);
+  finalize_gimm_part();
+  finalized_ = true; gimm_only_ = false;
+}
+
+// GIMM's own parameters (gimm.py:36-80 == gimmvfi_r.py:86-111): motion encoder, latent refiner, HypoNet, splat-metric scalars
+void Engine::finalize_gimm_part() {
   // --- GIMM encoders (gimmvfi_r.py:86-109)
   for (const char* n : {"cnn_encoder.0", "cnn_encoder.1", "cnn_encoder.3.layers.0", "cnn_encoder.3.layers.2", "cnn_encoder.4.layers.0",
                         "cnn_encoder.4.layers.2", "cnn_encoder.5.layers.0", "cnn_encoder.5.layers.2", "cnn_encoder.7", "res_conv.0",
@@ -375,8 +381,16 @@ void Engine::finalize_weights() {
     conv_[key] = c;
   }
   g9_ = vec("g_filter"); alpha_fe_ = vec("alpha_fe"); alpha_v_ = vec("alpha_v");
-  finalized_ = true;
 }
+
+// standalone GIMM checkpoint: only the keys of gimm.py's module tree are present
+void Engine::finalize_weights_gimm() {
+  for (void* p : dev_allocs_) dev_free(p);
+  dev_allocs_.clear(); conv_.clear(); vec_.clear();
+  finalize_gimm_part();
+  finalized_ = true; gimm_only_ = true;
+}
+
 
 // ---------------------------------------------------------------------------
 // forward
@@ -815,27 +829,8 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     for (int j = 0; j < 2; ++j)
       nhwc_to_nchw(cx, nf.batch(j * B, B), io.nflow + (int64_t)j * H * W, (int64_t)4 * H * W, (int64_t)2 * H * W, 1.f, 0.f, 0);
   TV wts = A.tensor(2 * B, H, W, 1);
-  splat_weights(cx, f01, f10, g9_, alpha_fe_, alpha_v_, wts.batch(0, B));
-  splat_weights(cx, f10, f01, g9_, alpha_fe_, alpha_v_, wts.batch(B, B));
-  tap("gimm.splat_w", wts);
   TV X64 = A.tensor(B, H, W, 64);   // [lat0 | lat1 | splat0 | splat1]
-  {
-    const size_t mk = A.mark();
-    TV a = A.tensor(2 * B, H, W, 16), x = A.tensor(2 * B, H, W, 32), y = A.tensor(2 * B, H, W, 32), m = A.tensor(2 * B, H, W, 32);
-    N.conv("cnn_encoder.0", nf, a);
-    N.conv("cnn_encoder.1", a, x, ACT_LRELU);
-    for (int i = 3; i <= 5; ++i) {  // LateralBlock fi_components.py:17-29 (+ the LeakyReLU after the last one)
-      const std::string q = "cnn_encoder." + std::to_string(i);
-      N.conv(q + ".layers.0", x, m, ACT_LRELU);
-      ConvEpi e; e.res = x; e.act2 = (i == 5) ? ACT_LRELU : ACT_NONE;
-      N.conv_e(q + ".layers.2", m, TV(), y, e);
-      std::swap(x, y);
-    }
-    N.conv("cnn_encoder.7", x.batch(0, B), X64.slice(0, 16), ACT_NONE, nullptr, 1, true);
-    N.conv("cnn_encoder.7", x.batch(B, B), X64.slice(16, 16), ACT_NONE, nullptr, 1, true);
-    A.release(mk);
-  }
-  tap("gimm.lat0", X64.slice(0, 16));
+  gimm_encode(N, nf, f01, f10, wts, X64);
 
   // ------------------------------------------------------------ per-timestep: GIMM decode + frame synthesis
   TV grid_flow = A.tensor(B, h, w, 4);   // flow_4_lr = cat(fl0, fl1)
@@ -843,38 +838,8 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   for (int ti = 0; ti < T; ++ti) {
     A.release(t_mark);
     const float* tdev = io.t + (int64_t)ti * B;
-    // ---- forward splat of both latents to time t (gimmvfi_r.py:171-193)
-    TV acc = A.tensor(2 * B, H, W, 17, 20);
-    if (!cx.dry) dev_memset(acc.p, 0, (size_t)2 * B * H * W * 20 * sizeof(float), cx.stream);
-    softsplat_accumulate(cx, X64.slice(0, 16), f01, wts.batch(0, B), tdev, 0, acc.batch(0, B));
-    softsplat_accumulate(cx, X64.slice(16, 16), f10, wts.batch(B, B), tdev, 1, acc.batch(B, B));
-    softsplat_normalize(cx, acc.batch(0, B), X64.slice(32, 16));
-    softsplat_normalize(cx, acc.batch(B, B), X64.slice(48, 16));
-    if (ti == 0) tap("gimm.splat0", X64.slice(32, 16));
-    TV hin = A.tensor(B, H, W, 35, 36);  // HypoNet input [latent32 | t,y,x]
-    {
-      const size_t mk = A.mark();
-      TV a = A.tensor(B, H, W, 32), x = A.tensor(B, H, W, 64), m = A.tensor(B, H, W, 64), y = A.tensor(B, H, W, 64);
-      N.conv("res_conv.0", X64, a);
-      N.conv("res_conv.1", a, x, ACT_LRELU);
-      N.conv("res_conv.3.layers.0", x, m, ACT_LRELU);
-      { ConvEpi e; e.res = x; e.act2 = ACT_LRELU; N.conv_e("res_conv.3.layers.2", m, TV(), y, e); }
-      { ConvEpi e; e.res = X64.slice(32, 32); N.conv_e("res_conv.5", y, TV(), hin.slice(0, 32), e, 1, true); }
-      A.release(mk);
-    }
-    if (ti == 0) tap("gimm.latent", hin.slice(0, 32));
-    hypo_pack_input(cx, io.coords + (int64_t)ti * B * P.Hc * P.Wc * 3, hin.slice(32, 3));
     TV ninr = A.tensor(B, H, W, 2);
-    {
-      const size_t mk = A.mark();
-      TV a = A.tensor(B, H, W, 128), b = A.tensor(B, H, W, 128);
-      N.conv("hyponet.params_dict.linear_wb0", hin, a, ACT_SIN);
-      N.conv("hyponet.params_dict.linear_wb1", a, b, ACT_SIN);
-      N.conv("hyponet.params_dict.linear_wb2", b, a, ACT_SIN);
-      N.conv("hyponet.params_dict.linear_wb3", a, b, ACT_SIN);
-      N.conv("hyponet.params_dict.linear_wb4", b, ninr);
-      A.release(mk);
-    }
+    gimm_decode(N, X64, f01, f10, wts, tdev, io.coords + (int64_t)ti * B * P.Hc * P.Wc * 3, ninr, ti == 0);
     if (io.ninrflow) nhwc_to_nchw(cx, ninr, io.ninrflow + (int64_t)ti * B * 2 * H * W, (int64_t)2 * H * W, (int64_t)H * W, 1.f, 0.f, 0);
     TV flow_t = A.tensor(B, H, W, 2);
     unnormalize_flow(cx, ninr, scaler, flow_t);
@@ -982,6 +947,137 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// GIMM stages (gimm.py:129-214 == gimmvfi_r.py:158-211), shared by run() and run_gimm()
+// ---------------------------------------------------------------------------
+// t-independent part: splatting metrics (gimm.py:82-127) and the motion encoder on both normalised flows -> X64[0:32]
+void Engine::gimm_encode(Net& N, const TV& nf /*2B: [nf01; nf10]*/, const TV& f01, const TV& f10, const TV& wts /*2B,1*/, const TV& X64) {
+  Ctx& cx = N.cx; Arena& A = cx.arena;
+  const int B = f01.n, H = f01.h, W = f01.w;
+  splat_weights(cx, f01, f10, g9_, alpha_fe_, alpha_v_, wts.batch(0, B));
+  splat_weights(cx, f10, f01, g9_, alpha_fe_, alpha_v_, wts.batch(B, B));
+  tap("gimm.splat_w", wts);
+  {
+    const size_t mk = A.mark();
+    TV a = A.tensor(2 * B, H, W, 16), x = A.tensor(2 * B, H, W, 32), y = A.tensor(2 * B, H, W, 32), m = A.tensor(2 * B, H, W, 32);
+    N.conv("cnn_encoder.0", nf, a);
+    N.conv("cnn_encoder.1", a, x, ACT_LRELU);
+    for (int i = 3; i <= 5; ++i) {  // LateralBlock fi_components.py:17-29 (+ the LeakyReLU after the last one)
+      const std::string q = "cnn_encoder." + std::to_string(i);
+      N.conv(q + ".layers.0", x, m, ACT_LRELU);
+      ConvEpi e; e.res = x; e.act2 = (i == 5) ? ACT_LRELU : ACT_NONE;
+      N.conv_e(q + ".layers.2", m, TV(), y, e);
+      std::swap(x, y);
+    }
+    N.conv("cnn_encoder.7", x.batch(0, B), X64.slice(0, 16), ACT_NONE, nullptr, 1, true);
+    N.conv("cnn_encoder.7", x.batch(B, B), X64.slice(16, 16), ACT_NONE, nullptr, 1, true);
+    A.release(mk);
+  }
+  tap("gimm.lat0", X64.slice(0, 16));
+}
+
+// one timestep: forward splat of both latents to time t, latent refiner, HypoNet -> normalised flow (B,H,W,2)
+void Engine::gimm_decode(Net& N, const TV& X64, const TV& f01, const TV& f10, const TV& wts, const float* tdev, const float* coords_t,
+                         const TV& ninr, bool tap_it) {
+  Ctx& cx = N.cx; Arena& A = cx.arena;
+  const int B = f01.n, H = f01.h, W = f01.w;
+  const size_t mk0 = A.mark();
+  // ---- forward splat of both latents to time t (gimmvfi_r.py:171-193)
+  TV acc = A.tensor(2 * B, H, W, 17, 20);
+  if (!cx.dry) dev_memset(acc.p, 0, (size_t)2 * B * H * W * 20 * sizeof(float), cx.stream);
+  softsplat_accumulate(cx, X64.slice(0, 16), f01, wts.batch(0, B), tdev, 0, acc.batch(0, B));
+  softsplat_accumulate(cx, X64.slice(16, 16), f10, wts.batch(B, B), tdev, 1, acc.batch(B, B));
+  softsplat_normalize(cx, acc.batch(0, B), X64.slice(32, 16));
+  softsplat_normalize(cx, acc.batch(B, B), X64.slice(48, 16));
+  if (tap_it) tap("gimm.splat0", X64.slice(32, 16));
+  TV hin = A.tensor(B, H, W, 35, 36);  // HypoNet input [latent32 | t,y,x]
+  {
+    const size_t mk = A.mark();
+    TV a = A.tensor(B, H, W, 32), x = A.tensor(B, H, W, 64), m = A.tensor(B, H, W, 64), y = A.tensor(B, H, W, 64);
+    N.conv("res_conv.0", X64, a);
+    N.conv("res_conv.1", a, x, ACT_LRELU);
+    N.conv("res_conv.3.layers.0", x, m, ACT_LRELU);
+    { ConvEpi e; e.res = x; e.act2 = ACT_LRELU; N.conv_e("res_conv.3.layers.2", m, TV(), y, e); }
+    { ConvEpi e; e.res = X64.slice(32, 32); N.conv_e("res_conv.5", y, TV(), hin.slice(0, 32), e, 1, true); }
+    A.release(mk);
+  }
+  if (tap_it) tap("gimm.latent", hin.slice(0, 32));
+  hypo_pack_input(cx, coords_t, hin.slice(32, 3));
+  {
+    const size_t mk = A.mark();
+    TV a = A.tensor(B, H, W, 128), b = A.tensor(B, H, W, 128);
+    N.conv("hyponet.params_dict.linear_wb0", hin, a, ACT_SIN);
+    N.conv("hyponet.params_dict.linear_wb1", a, b, ACT_SIN);
+    N.conv("hyponet.params_dict.linear_wb2", b, a, ACT_SIN);
+    N.conv("hyponet.params_dict.linear_wb3", a, b, ACT_SIN);
+    N.conv("hyponet.params_dict.linear_wb4", b, ninr);
+    A.release(mk);
+  }
+  if (!debug_) A.release(mk0);   // (debug taps keep pointing into this region)
+}
+
+// (B,2,2,H,W) flow pair, reference layout [b][c][j][y][x] -> NHWC (2B,H,W,2), sample j*B+b
+struct FlowPairLoadK {
+  const float* src; TV dst; int B;
+  GV_HD void operator()(int64_t i) const {
+    const int c = (int)(i & 1); int64_t r = i >> 1;
+    const int x = (int)(r % dst.w); r /= dst.w; const int y = (int)(r % dst.h); const int n = (int)(r / dst.h);
+    const int j = n / B, b = n - j * B;
+    const int64_t hw = (int64_t)dst.h * dst.w;
+    dst.p[dst.off(n, y, x) + c] = src[(((int64_t)b * 2 + c) * 2 + j) * hw + (int64_t)y * dst.w + x];
+  }
+};
+
+// GIMM.forward (gimm.py:129-214): normalised flows xs + raw flows ori_flow + timesteps + coords -> normalised flows at t
+void Engine::run_gimm(Ctx& cx, const Problem& P, const GimmIO& io) {
+  if (P.B < 1 || P.T < 1) throw std::runtime_error("gimmvfi: B and T must be >= 1");
+  const int B = P.B, H = P.Hf, W = P.Wf, T = P.T;
+  if (P.ds > 0.f) throw std::runtime_error("gimm: ds_factor does not exist on this path");
+  if (H < 8 || W < 8) throw std::runtime_error("gimm: H and W must be >= 8");
+  if (P.Hc != H || P.Wc != W) throw std::runtime_error("gimm: the coordinate grid must match the flow resolution");
+  Net N{*this, cx};
+  Arena& A = cx.arena;
+  cx.tc = tc_mode_ >= 1; cx.tc_split = false;   // downstream-of-RAFT arithmetic (DESIGN.md precision plan)
+  TV nf = A.tensor(2 * B, H, W, 2), fl = A.tensor(2 * B, H, W, 2);
+  parallel_for(cx, nf.pixels() * 2, FlowPairLoadK{io.xs, nf, B}, "flow_pair_load");
+  parallel_for(cx, fl.pixels() * 2, FlowPairLoadK{io.ori_flow, fl, B}, "flow_pair_load");
+  TV f01 = fl.batch(0, B), f10 = fl.batch(B, B);
+  TV wts = A.tensor(2 * B, H, W, 1);
+  TV X64 = A.tensor(B, H, W, 64);
+  gimm_encode(N, nf, f01, f10, wts, X64);
+  TV ninr = A.tensor(B, H, W, 2);
+  for (int ti = 0; ti < T; ++ti) {
+    gimm_decode(N, X64, f01, f10, wts, io.t + (int64_t)ti * B, io.coords + (int64_t)ti * B * P.Hc * P.Wc * 3, ninr, ti == 0);
+    nhwc_to_nchw(cx, ninr, io.out + (int64_t)ti * B * 2 * H * W, (int64_t)2 * H * W, (int64_t)H * W, 1.f, 0.f, 0);
+  }
+}
+
+size_t Engine::plan_gimm(const Problem& p) {
+  if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
+  Ctx cx; cx.dry = true; cx.arena.dry = true; cx.sm_count = sm_count_;
+  GimmIO io; float* fake = reinterpret_cast<float*>(size_t(64));
+  io.xs = io.ori_flow = io.coords = io.t = fake; io.out = fake;
+  const bool dbg = debug_; debug_ = false;
+  run_gimm(cx, p, io);
+  debug_ = dbg; taps_.clear();
+  return cx.arena.peak + 256;
+}
+
+void Engine::forward_gimm(const Problem& p, const GimmIO& io, void* workspace, size_t workspace_bytes, gvStream_t stream) {
+  if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
+  if (!io.xs || !io.ori_flow || !io.coords || !io.t || !io.out) throw std::runtime_error("gimm: xs, ori_flow, coords, t and out are required");
+  Ctx cx; cx.stream = stream; cx.sm_count = sm_count_;
+  prof_.reset();
+  cx.prof = profile_ ? &prof_ : nullptr;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  cx.arena.base = reinterpret_cast<char*>(base);
+  cx.arena.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
+  taps_.clear();
+  run_gimm(cx, p, io);
+  launches_ = cx.launches;
+}
+
 size_t Engine::frame_cache_bytes(const Problem& p) {
   const size_t h = (size_t)p.H() / 8, w = (size_t)p.W() / 8, H4 = (size_t)p.H() / 4, W4 = (size_t)p.W() / 4;
   return ((size_t)p.B * h * w * 256 * 3 + (size_t)p.B * H4 * W4 * 128) * sizeof(float);
@@ -1003,6 +1099,7 @@ size_t Engine::plan(const Problem& p) {
 
 void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t workspace_bytes, gvStream_t stream) {
   if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
+  if (gimm_only_) throw std::runtime_error("gimmvfi: only GIMM's weights were loaded (finalize_weights_gimm); use gimm_forward");
   if (!io.img_xs || !io.coords || !io.t || !io.imgt_pred) throw std::runtime_error("gimmvfi: img_xs, coords, t and imgt_pred are required");
   Ctx cx; cx.stream = stream; cx.sm_count = sm_count_;
   prof_.reset();

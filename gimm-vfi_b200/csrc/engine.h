@@ -40,12 +40,26 @@ struct IO {
 
 struct DebugTap { TV tv; };
 
+// GIMM.forward (gimm.py:129-214) device pointers, reference layouts
+struct GimmIO {
+  const float* xs = nullptr;        // (B,2,2,H,W) normalised flows [f01 | f10] on dim 2
+  const float* ori_flow = nullptr;  // (B,2,2,H,W) raw flows
+  const float* coords = nullptr;    // (T,B,1,H,W,3)
+  const float* t = nullptr;         // (T,B)
+  float* out = nullptr;             // (T,B,2,1,H,W) normalised flow at t (keep_xs_shape=True)
+};
+
+struct Net;
+
 class Engine {
  public:
   explicit Engine(int device);
   ~Engine();
   void load_weight(const std::string& key, const float* host, const int64_t* shape, int ndim);
   void finalize_weights();
+  void finalize_weights_gimm();                        // a standalone GIMM checkpoint (gimm.py's module tree only)
+  size_t plan_gimm(const Problem& p);
+  void forward_gimm(const Problem& p, const GimmIO& io, void* workspace, size_t workspace_bytes, gvStream_t stream);
   size_t plan(const Problem& p);                       // dry run -> workspace bytes
   void forward(const Problem& p, const IO& io, void* workspace, size_t workspace_bytes, gvStream_t stream);
   int64_t last_launches() const { return launches_; }
@@ -71,6 +85,11 @@ class Engine {
  private:
   struct Impl;
   void run(Ctx& cx, const Problem& p, const IO& io);
+  void run_gimm(Ctx& cx, const Problem& p, const GimmIO& io);
+  void finalize_gimm_part();
+  void gimm_encode(Net& N, const TV& nf, const TV& f01, const TV& f10, const TV& wts, const TV& X64);
+  void gimm_decode(Net& N, const TV& X64, const TV& f01, const TV& f10, const TV& wts, const float* tdev, const float* coords_t, const TV& ninr,
+                   bool tap_it);
   ConvW pack_conv(const std::string& name, const std::string& bn = "", float out_scale = 1.f, const std::vector<int>* perm = nullptr);
   const float* upload(const std::vector<float>& v);
   const float* vec(const std::string& key);
@@ -78,7 +97,7 @@ class Engine {
   void tap(const std::string& name, const TV& tv) { if (debug_) taps_[name] = tv; }
 
   int device_ = 0;
-  bool finalized_ = false, debug_ = false, profile_ = false;
+  bool finalized_ = false, debug_ = false, profile_ = false, gimm_only_ = false;
   int tc_mode_ = 0;
   float* fc_ = nullptr; size_t fc_bytes_ = 0; bool fc_load_ = false, fc_store_ = false;
   // what the cache holds (host-side bookkeeping of the last store): a load with a different buffer / problem is refused

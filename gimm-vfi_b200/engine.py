@@ -38,14 +38,16 @@ class EngineHandle:
             pass
 
     # ------------------------------------------------------------------ weights
-    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], gimm_only: bool = False):
+        """gimm_only: `sd` is a standalone GIMM checkpoint (gimm.py's module tree), only gimm_forward() is available"""
         for k, v in sd.items():
             if not v.dtype.is_floating_point:
                 continue  # num_batches_tracked
             t = v.detach().to("cpu", torch.float32).contiguous()
             shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
             self.lib.check(self.lib.dll.gimmvfi_load_weight(self._h, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()), self._h)
-        self.lib.check(self.lib.dll.gimmvfi_finalize_weights(self._h), self._h)
+        fin = self.lib.dll.gimmvfi_finalize_weights_gimm if gimm_only else self.lib.dll.gimmvfi_finalize_weights
+        self.lib.check(fin(self._h), self._h)
         self.weights_loaded = True
 
     def set_debug(self, on: bool):
@@ -129,6 +131,30 @@ class EngineHandle:
         finally:
             if frame_cache is not None:
                 self.lib.check(self.lib.dll.gimmvfi_set_frame_cache(self._h, None, 0, 0, 0), self._h)
+        return out
+
+    def gimm_forward(self, xs: torch.Tensor, ori_flow: torch.Tensor, coords: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """GIMM.forward (gimm.py:129-214): xs, ori_flow (B,2,2,H,W), coords (T,B,1,H,W,3), t (T,B) -> (T,B,2,1,H,W)."""
+        for x in (xs, ori_flow, coords, t):
+            assert x.dtype == torch.float32 and x.is_contiguous() and x.device.type == self.device.type
+        B, _, _, H, W = xs.shape
+        T = coords.shape[0]
+        assert tuple(ori_flow.shape) == (B, 2, 2, H, W) and tuple(coords.shape) == (T, B, 1, H, W, 3) and tuple(t.shape) == (T, B)
+        p = self._problem(B, H, W, T, None, H, W)
+        key = ("gimm", B, H, W, T)
+        if key not in self._plans:
+            n = C.c_size_t()
+            self.lib.check(self.lib.dll.gimmvfi_gimm_plan(self._h, C.byref(p), C.byref(n)), self._h)
+            self._plans[key] = int(n.value)
+        nbytes = self._plans[key]
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        out = torch.empty(T, B, 2, 1, H, W, dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+        P = lambda x: C.c_void_p(x.data_ptr())
+        self.lib.check(self.lib.dll.gimmvfi_gimm_forward(self._h, C.byref(p), P(xs), P(ori_flow), P(coords), P(t), P(out), P(self._ws),
+                                                         self._ws.numel(), C.c_void_p(stream)), self._h)
         return out
 
     def tap(self, name: str) -> torch.Tensor:

@@ -39,3 +39,16 @@ def synth_pair(H: int, W: int, seed: int = 0, max_disp: float = 8.0) -> torch.Te
 
 def synth_batch(B: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
     return torch.cat([synth_pair(H, W, seed + i) for i in range(B)], 0)
+
+
+def synth_flow_pair(B: int, H: int, W: int, seed: int = 0, max_disp: float = 6.0) -> torch.Tensor:
+    """Seeded bidirectional flow fields for the GIMM-standalone path: (B,2,2,H,W), [:, :, 0] = f01 (smooth low-frequency
+    field + a global translation), [:, :, 1] = f10 ~ -f01 plus a small inconsistency (so the forward/backward-consistency term
+    of the splatting metric, gimm.py:106-121, is exercised)."""
+    g = torch.Generator().manual_seed(seed)
+    hs, ws = max(2, H // 16), max(2, W // 16)
+    lo = torch.randn(B, 2, hs, ws, generator=g) * (max_disp / 2)
+    f01 = F.interpolate(lo, size=(H, W), mode="bicubic", align_corners=False) + torch.tensor([2.5, -1.25]).view(1, 2, 1, 1)
+    dev = torch.randn(B, 2, hs, ws, generator=g) * 0.35
+    f10 = -f01 + F.interpolate(dev, size=(H, W), mode="bicubic", align_corners=False)
+    return torch.stack([f01, f10], 2).contiguous()

@@ -76,6 +76,17 @@ int gimmvfi_finalize_weights(gimmvfi_engine* e);
 int gimmvfi_plan(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes);
 int gimmvfi_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_io* io, void* workspace, size_t workspace_bytes,
                     void* cuda_stream);
+/* ---- GIMM standalone: GIMM.forward (gimm.py:129-214), the motion-modelling network alone ----
+ * Weights: either the full GIMM-VFI-R state_dict (gimmvfi_finalize_weights) or a GIMM checkpoint holding only gimm.py's module
+ * tree (cnn_encoder.*, res_conv.*, hyponet.*, g_filter, alpha_v, alpha_fe) followed by gimmvfi_finalize_weights_gimm.
+ * problem: batch, height, width = flow resolution (any size >= 8), timesteps = T, ds_factor = 0, coord grid = height x width.
+ * xs (B,2,2,H,W): flows normalised as in fi_utils.py:52-60, [f01 | f10] on dim 2; ori_flow (B,2,2,H,W): the raw flows;
+ * coords (T,B,1,H,W,3); t (T,B); out (T,B,2,1,H,W) = the list of keep_xs_shape=True outputs. */
+int gimmvfi_finalize_weights_gimm(gimmvfi_engine* e);
+int gimmvfi_gimm_plan(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes);
+int gimmvfi_gimm_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const float* xs, const float* ori_flow, const float* coords,
+                         const float* t, float* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 const char* gimmvfi_last_error(gimmvfi_engine* e);
 int64_t gimmvfi_last_launches(gimmvfi_engine* e);
 int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters);

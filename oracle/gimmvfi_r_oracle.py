@@ -388,6 +388,20 @@ def predict_flow(sd: SD, nflow: Tensor, coords: List[Tensor], ts: List[Tensor], 
     return outs
 
 
+def gimm_forward(sd: SD, xs: Tensor, coord, ori_flow: Tensor, timesteps, keep_xs_shape: bool = True):
+    """gimm.py:129-214 — GIMM.forward, the motion-modelling network alone (cal_splatting_weights :82-127, cnn_encoder,
+    softsplat "linear-zeroeps", res_conv, HypoNet).  xs (B,2,2,H,W): normalised flows [f01 | f10] on dim 2; ori_flow: the raw
+    flows.  List form: timesteps = [ (B,) ... ], coord = [ (B,1,Hc,Wc,3) ... ] -> list of outputs; tensor form -> one output.
+    Output (B,2,1,Hc,Wc) with keep_xs_shape (the reference's `permute(0, -1, 1, 2, 3)`), else (B,1,Hc,Wc,2)."""
+    is_list = isinstance(timesteps, list)
+    if is_list:
+        assert isinstance(coord, list) and len(coord) == len(timesteps)
+    outs = predict_flow(sd, xs, coord if is_list else [coord], timesteps if is_list else [timesteps], ori_flow)
+    if not keep_xs_shape:
+        outs = [o.permute(0, 2, 3, 4, 1) for o in outs]
+    return outs if is_list else outs[0]
+
+
 # --------------------------------------------------------------------------
 # AMT-style synthesis (modules/fi_components.py)
 # --------------------------------------------------------------------------

@@ -35,6 +35,10 @@ CASES = [
 ]
 
 
+# GIMM standalone: name, B, H, W, timesteps, flow seed
+GIMM_CASES = [("gimm_64x96_t0.25_0.75", 1, 64, 96, [0.25, 0.75], 1), ("gimm_b2_72x80_t0.5", 2, 72, 80, [0.5], 2)]
+
+
 def sub(t, s):
     return t[..., ::s, ::s].contiguous().numpy()
 
@@ -44,7 +48,11 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     manifest = {}
     models = {}
-    for name, B, H, W, ts, ds, iseed, wseed, stride in CASES:
+    only_gimm = "--only-gimm" in sys.argv      # keep the GIMM-VFI-R fixtures, (re)generate the GIMM-standalone ones
+    if only_gimm:
+        with open(os.path.join(out_dir, "manifest.json")) as f:
+            manifest = json.load(f)
+    for name, B, H, W, ts, ds, iseed, wseed, stride in ([] if only_gimm else CASES):
         if wseed not in models:
             sd = random_state_dict(wseed)
             models[wseed] = (ref_shim.build_reference_model(sd), sd)
@@ -72,6 +80,25 @@ def main():
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrays)
         manifest[name] = dict(B=B, H=H, W=W, timesteps=ts, ds_factor=ds, input_seed=iseed, weight_seed=wseed,
                               stride=stride, oracle_vs_reference_max_abs=pin)
+        print(name, "oracle-vs-reference max|Δ| =", pin, flush=True)
+    # ---- GIMM standalone (gimm.py:129-214): the unmodified reference GIMM on seeded flows
+    from gimmvfi_b200.synth import synth_flow_pair  # noqa: E402
+    sd = random_state_dict(0)
+    gimm = ref_shim.build_reference_gimm(sd)
+    spec = [[k, list(v.shape)] for k, v in gimm.state_dict().items()]
+    with open(os.path.join(out_dir, "state_dict_spec_gimm.json"), "w") as f:
+        json.dump(spec, f)
+    for name, B, H, W, ts, fseed in GIMM_CASES:
+        ori = synth_flow_pair(B, H, W, seed=fseed)
+        xs, _ = O.normalize_flow(ori)
+        coord = [O.sample_coord_input(B, (H, W), [t], 1.0) for t in ts]
+        tt = [t * torch.ones(B) for t in ts]
+        ref = gimm(xs, coord, True, ori, tt)
+        ora = O.gimm_forward(sd, xs, coord, ori, tt)
+        pin = max((a - b).abs().max().item() for a, b in zip(ref, ora))
+        arrays = {"out_%d" % i: ref[i].numpy() for i in range(len(ts))}
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrays)
+        manifest[name] = dict(kind="gimm", B=B, H=H, W=W, timesteps=ts, flow_seed=fseed, weight_seed=0, oracle_vs_reference_max_abs=pin)
         print(name, "oracle-vs-reference max|Δ| =", pin, flush=True)
     with open(os.path.join(out_dir, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)

@@ -223,3 +223,20 @@ def build_reference_model(state_dict=None, seed=0):
         model.load_state_dict(state_dict, strict=True)
     model.eval()
     return model
+
+
+GIMM_KEY_PREFIXES = ("cnn_encoder.", "res_conv.", "hyponet.", "g_filter", "alpha_v", "alpha_fe")
+
+
+def build_reference_gimm(state_dict=None, seed=0):
+    """Constructs the reference GIMM (gimm.py:25, the motion-modelling network alone) on CPU in eval mode.  `state_dict` may be
+    a full GIMM-VFI-R state_dict: only gimm.py's keys are taken (same names, gimmvfi_r.py:86-111)."""
+    mods = load_reference_modules()
+    gimm = importlib.import_module("gimmvfi_reference.generalizable_INR.gimm")
+    torch.manual_seed(seed)
+    model = gimm.GIMM(default_arch_config())
+    if state_dict is not None:
+        sub = {k: v for k, v in state_dict.items() if k.startswith(GIMM_KEY_PREFIXES)}
+        model.load_state_dict(sub, strict=True)
+    model.eval()
+    return model

@@ -28,3 +28,18 @@ def test_random_state_dict_deterministic():
     assert all(torch.equal(a[k], b[k]) for k in a)
     k = "flow_estimator.cnet.layer2.0."
     assert torch.equal(a[k + "norm3.weight"], a[k + "downsample.1.weight"])
+
+
+def test_gimm_state_dict_matches_reference_dump():
+    """GIMM standalone (gimm.py:25-80): same 36 keys, order and shapes as the reference module's state_dict"""
+    import json, os
+    from conftest import GOLDEN_DIR
+    from gimmvfi_b200.gimm import GIMM, param_spec_gimm
+
+    spec = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_spec_gimm.json")))
+    assert [[k, list(s)] for k, s, _ in param_spec_gimm()] == spec
+    m = GIMM()
+    sd = m.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    assert all(list(sd[k].shape) == s for k, s in spec)
+    m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)

@@ -81,3 +81,32 @@ def test_frame_cache_reuses_second_frame_bit_exactly(eng):
     other = torch.zeros_like(cache)
     with pytest.raises(GimmvfiError):
         eng.forward(pair(Bf, Cf), coords, tt, None, frame_cache=(other, True, False))
+
+
+@pytest.mark.parametrize("gimm_only", [False, True])
+def test_hostsim_gimm_forward_matches_oracle(weights0, gimm_only):
+    """GIMM standalone through the engine (run_gimm): full GIMM-VFI-R weights, and a GIMM-only checkpoint"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    from harness import hostsim_engine
+    from gimmvfi_b200.gimm import GIMM_KEY_PREFIXES
+    from gimmvfi_b200.synth import synth_flow_pair
+    from gimmvfi_b200._lib import GimmvfiError
+
+    torch.set_grad_enabled(False)
+    e = hostsim_engine()
+    sd = {k: v for k, v in weights0.items() if k.startswith(GIMM_KEY_PREFIXES)} if gimm_only else weights0
+    e.load_state_dict(sd, gimm_only=gimm_only)
+    B, H, W, ts = 2, 40, 56, [0.25, 0.75]
+    ori = synth_flow_pair(B, H, W, seed=4)
+    xs, _ = O.normalize_flow(ori)
+    coords = torch.stack([O.sample_coord_input(B, (H, W), [t], 1.0) for t in ts], 0).contiguous()
+    tt = torch.stack([t * torch.ones(B) for t in ts], 0).contiguous()
+    got = e.gimm_forward(xs.contiguous(), ori, coords, tt)
+    ref = O.gimm_forward(weights0, xs, [coords[i] for i in range(len(ts))], ori, [tt[i] for i in range(len(ts))])
+    for i in range(len(ts)):
+        assert (got[i] - ref[i]).abs().max() <= 2e-5
+    if gimm_only:   # the interpolation path needs the whole GIMM-VFI-R state_dict
+        c1 = O.sample_coord_input(1, (128, 160), [0.5], 1.0).unsqueeze(0).contiguous()
+        with pytest.raises(GimmvfiError):
+            e.forward(synth_batch(1, 128, 160, seed=1), c1, 0.5 * torch.ones(1, 1), None)

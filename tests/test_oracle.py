@@ -90,3 +90,24 @@ def test_zeroeps_holes():
     flow = torch.full((1, 2, 4, 4), 10.0)  # everything leaves the frame
     out = O.softsplat_linear_zeroeps(inp, flow, torch.ones(1, 1, 4, 4))
     assert torch.count_nonzero(out) == 0
+
+
+@pytest.mark.parametrize("name", ["gimm_64x96_t0.25_0.75", "gimm_b2_72x80_t0.5"])
+def test_oracle_gimm_matches_reference_golden(name, golden_manifest, weights0):
+    """GIMM standalone (gimm.py:129-214): the oracle's gimm_forward vs outputs of the unmodified reference GIMM"""
+    from gimmvfi_b200.synth import synth_flow_pair
+
+    torch.set_grad_enabled(False)
+    meta = golden_manifest[name]
+    assert meta["kind"] == "gimm" and meta["oracle_vs_reference_max_abs"] <= 2e-6
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    B, H, W, ts = meta["B"], meta["H"], meta["W"], meta["timesteps"]
+    ori = synth_flow_pair(B, H, W, seed=meta["flow_seed"])
+    xs, _ = O.normalize_flow(ori)
+    coord = [O.sample_coord_input(B, (H, W), [t], 1.0) for t in ts]
+    out = O.gimm_forward(weights0, xs, coord, ori, [t * torch.ones(B) for t in ts])
+    for i in range(len(ts)):
+        assert out[i].shape == (B, 2, 1, H, W)
+        assert np.abs(out[i].numpy() - g["out_%d" % i]).max() <= TOL
+    one = O.gimm_forward(weights0, xs, coord[0], ori, ts[0] * torch.ones(B), keep_xs_shape=False)   # tensor form
+    assert one.shape == (B, 1, H, W, 2) and torch.equal(one.permute(0, 4, 1, 2, 3), out[0])
