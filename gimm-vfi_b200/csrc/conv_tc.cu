@@ -8,19 +8,28 @@
 //                   TMA box {32 ch, 16 x, 8 y, 1 n} of the NHWC activation at the
 //                   tap-shifted coordinate (out-of-bounds -> zero fill = zero padding,
 //                   no im2col, no halo staging code) plus one {32 k, BN} weight box.
-//   roles       warp 0: TMA producer | warp 1: MMA issuer (+TMEM alloc) | warps 2-5: epilogue
-//               | warps 6-9 (SPLIT only): operand splitter
+//   roles       warp 0: TMA producer | warp 1: MMA issuer (+TMEM alloc) | 4 or 8 epilogue warps
+//               | 4 operand-splitter warps (SPLIT only)
 //   pipelines   smem full/empty ring, 2 TMEM accumulators (full/empty) so the epilogue of
 //               tile i overlaps the MMAs of tile i+1; persistent over tiles.
+//   CTA pairs   PAIR: the two CTAs of a cluster issue ONE cta_group::2 MMA of M = 256 (two pixel tiles), each holding
+//               half of the weight tile; TMA loads of both signal the leader's barrier, commits are multicast.
+//               (Without PAIR, CL = 2 only multicasts the weight tile.)
+//   stride 2    TMA element strides {1, 2, 2, 1}: the box spans 32 x 16 pixels, every second one is delivered.
 //
-// Two precisions:
-//   SPLIT=false  plain TF32 operands (the tensor core ignores the low 13 mantissa bits of A;
-//                weights are rounded RN at pack time; outputs are stored TF32-rounded so the
-//                next layer's truncation is exact).  Used after RAFT (DESIGN.md precision plan).
-//   SPLIT=true   "3xTF32": D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with Ahi = rn_tf32(a), Alo = rn_tf32(a - Ahi) computed
-//                in shared memory by the splitter warps and Bhi/Blo pre-split at pack time:
-//                ~2^-21 relative error, i.e. fp32-class accuracy at 3 MMAs per K step.  Used
-//                for the RAFT recurrence, which amplifies operand rounding.
+// Three operand formats:
+//   TF32         (SPLIT=false) the tensor core ignores the low 13 mantissa bits of A; weights are rounded RN at
+//                pack time; outputs are stored TF32-rounded so the next layer's truncation is exact.  Post-RAFT layers.
+//   FP16 storage (SPLIT=false, Params::f16_in) activations and weights in IEEE half, kind::f16 MMAs with K = 64 per
+//                128-byte smem row, fp32 accumulation; half outputs / residuals as flagged per tensor (TV::f16).  The final
+//                decoder's 256-channel residual trunk in precision mode 3.
+//   3xTF32       (SPLIT=true) D += Ahi*Blo + Alo*Bhi + Ahi*Bhi with Ahi = rn_tf32(a), Alo = rn_tf32(a - Ahi).  The splitter
+//                warps read the fp32 A tile from shared memory once and write Ahi / Alo into TENSOR MEMORY (tcgen05.st,
+//                64 columns per stage); the MMAs take A from there (tcgen05.mma [d], [a_tmem], b_desc), Bhi / Blo are
+//                pre-split at pack time.  The K loop is cut into segments of Params::seg K steps whose accumulators are
+//                drained into fp32 registers (the tensor core's accumulate add truncates): ~2^-21 relative error, i.e.
+//                fp32-class accuracy at 3 MMAs per K step.  Used for the RAFT recurrence, which amplifies operand rounding.
+//                (GIMMVFI_TC_ATMEM=0 keeps the first version, which rewrote Ahi / Alo in shared memory.)
 #include "common.h"
 
 #ifndef GV_HOSTSIM
