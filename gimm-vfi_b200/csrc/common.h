@@ -60,6 +60,42 @@ GV_HD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
 GV_HD void st4(float* p, const F4& v) { *reinterpret_cast<F4*>(p) = v; }
 inline bool vec4_ok(const TV& t) { return (reinterpret_cast<uintptr_t>(t.p) & 15) == 0 && t.c % 4 == 0 && t.ld % 4 == 0 && t.sn % 4 == 0 && !t.f16; }
 
+// IEEE binary16 with round-to-nearest-even and saturation to +-65504 (host side, bit exact with cvt.rn.satfinite.f16.f32)
+inline uint16_t gv_f32_to_f16(float f) {
+  uint32_t u; std::memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  u &= 0x7fffffffu;
+  if (u > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);                 // NaN
+  if (u >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);                // >= 65520 (or inf): saturate
+  if (u < 0x33000001u) return sign;                                       // < 2^-25: rounds to zero
+  if (u < 0x38800000u) {                                                  // subnormal half
+    const int shift = 113 - (int)(u >> 23);                               // 1..24
+    uint32_t m = (u & 0x7fffffu) | 0x800000u;
+    const uint32_t lsb = 1u << (shift + 13), half = lsb >> 1;
+    uint32_t q = m >> (shift + 13);
+    const uint32_t rem = m & (lsb - 1);
+    if (rem > half || (rem == half && (q & 1u))) ++q;
+    return (uint16_t)(sign | q);
+  }
+  uint32_t e = (u >> 23) - 112, m = u & 0x7fffffu;
+  uint32_t h = (e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return (uint16_t)(sign | h);
+}
+
+inline float gv_f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  uint32_t u;
+  if (e == 0) {
+    if (m == 0) u = sign;
+    else { int sh = 0; uint32_t mm = m; while (!(mm & 0x400u)) { mm <<= 1; ++sh; } u = sign | ((uint32_t)(113 - sh) << 23) | ((mm & 0x3ffu) << 13); }
+  } else if (e == 31) u = sign | 0x7f800000u | (m << 13);
+  else u = sign | ((e + 112) << 23) | (m << 13);
+  float f; std::memcpy(&f, &u, 4);
+  return f;
+}
+
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_PRELU = 3, ACT_SIGMOID = 4, ACT_TANH = 5, ACT_SIN = 6 };
 
 GV_HD float apply_act(float v, int act, const float* slope, int ch) {

@@ -320,6 +320,25 @@ static bool conv_thin_ok(const ConvArgs& a) {
 }
 #endif
 
+// Eligibility of a layer for the tensor-core path (conv_tc.cu; its arithmetic is emulated on the host in tests/hostsim)
+bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!w.w_tc || (g.stride != 1 && g.stride != 2) || g.reflect) return false;
+  if (split && !w.has_lo) return false;
+  if (!g.loose_w && (g.ph != w.kh / 2 || g.pw != w.kw / 2)) return false;
+  if (g.loose_w && (g.ph != 0 || g.pw != 0)) return false;   // pre-padded input: taps index it directly
+  const bool h = in0.f16 != 0;                                 // half activations: kind::f16, 64-channel K blocks
+  const int amul = h ? 8 : 4, kblk = h ? 64 : 32;              // 16-byte TMA strides
+  if (h && (split || !w.w_tc_h)) return false;
+  if (in1.p && (in1.f16 != 0) != h) return false;
+  if (e.mul.f16 || e.gru_z.f16 || e.gru_h.f16) return false;   // only the residual may be half
+  if (e.split_c && (e.split_c % 32 || !e.out2.p || e.out2.f16 || e.res.p || e.gru_z.p)) return false;
+  if (!al16(in0.p) || in0.ld % amul || in0.sn % amul) return false;
+  if (in1.p && (!al16(in1.p) || in1.ld % amul || in1.sn % amul || in0.c % kblk)) return false;
+  if (!g.loose_w && ((in0.h + 2 * g.ph - w.kh) / g.stride + 1 != out.h || (in0.w + 2 * g.pw - w.kw) / g.stride + 1 != out.w)) return false;
+  return true;
+}
+
 void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out) {
   if (cx.dry) return;
   ConvArgs a;
@@ -374,10 +393,10 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
     if (cx.prof) cx.prof->end(cx.stream);
     return;
   }
+#endif
   const bool any_f16 = in0.f16 || in1.f16 || out.f16 || e.res.f16;
   if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out, cx.tc_split && !any_f16)) { conv2d_tc(cx, in0, in1, w, g, e, out, cx.tc_split && !any_f16); return; }
   if (any_f16) throw std::runtime_error("conv2d: half-precision tensors are only handled by the tensor-core path (layer not eligible)");
-#endif
   if (e.split_c) throw std::runtime_error("conv2d: merged two-output convolutions exist on the tensor-core path only");
   cx.launches++;
 #ifdef GV_HOSTSIM

@@ -1051,24 +1051,6 @@ static int tc_seg() {
   return seg;
 }
 
-bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
-  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!w.w_tc || (g.stride != 1 && g.stride != 2) || g.reflect) return false;
-  if (split && !w.has_lo) return false;
-  if (!g.loose_w && (g.ph != w.kh / 2 || g.pw != w.kw / 2)) return false;
-  if (g.loose_w && (g.ph != 0 || g.pw != 0)) return false;   // pre-padded input: taps index it directly
-  const bool h = in0.f16 != 0;                                 // half activations: kind::f16, 64-channel K blocks
-  const int amul = h ? 8 : 4, kblk = h ? 64 : 32;              // 16-byte TMA strides
-  if (h && (split || !w.w_tc_h)) return false;
-  if (in1.p && (in1.f16 != 0) != h) return false;
-  if (e.mul.f16 || e.gru_z.f16 || e.gru_h.f16) return false;   // only the residual may be half
-  if (e.split_c && (e.split_c % 32 || !e.out2.p || e.out2.f16 || e.res.p || e.gru_z.p)) return false;
-  if (!al16(in0.p) || in0.ld % amul || in0.sn % amul) return false;
-  if (in1.p && (!al16(in1.p) || in1.ld % amul || in1.sn % amul || in0.c % kblk)) return false;
-  if (!g.loose_w && ((in0.h + 2 * g.ph - w.kh) / g.stride + 1 != out.h || (in0.w + 2 * g.pw - w.kw) / g.stride + 1 != out.w)) return false;
-  return true;
-}
-
 void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
   using namespace tc;
   CUtensorMap mA0, mA1, mB;

@@ -195,30 +195,6 @@ void Engine::pack_tc(ConvW& c, const std::vector<float>& pw) {
   c.w_tc = upload(t); c.cout_pad = cout_pad; c.cin_pad = cin_pad; c.has_lo = true;
 }
 
-// IEEE binary16 with round-to-nearest-even and saturation to +-65504 (host side, bit exact with cvt.rn.satfinite.f16.f32)
-static uint16_t f32_to_f16_rn(float f) {
-  uint32_t u; std::memcpy(&u, &f, 4);
-  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
-  u &= 0x7fffffffu;
-  if (u > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);                 // NaN
-  if (u >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);                // >= 65520 (or inf): saturate
-  if (u < 0x33000001u) return sign;                                       // < 2^-25: rounds to zero
-  if (u < 0x38800000u) {                                                  // subnormal half
-    const int shift = 113 - (int)(u >> 23);                               // 1..24
-    uint32_t m = (u & 0x7fffffu) | 0x800000u;
-    const uint32_t lsb = 1u << (shift + 13), half = lsb >> 1;
-    uint32_t q = m >> (shift + 13);
-    const uint32_t rem = m & (lsb - 1);
-    if (rem > half || (rem == half && (q & 1u))) ++q;
-    return (uint16_t)(sign | q);
-  }
-  uint32_t e = (u >> 23) - 112, m = u & 0x7fffffu;
-  uint32_t h = (e << 10) | (m >> 13);
-  const uint32_t rem = m & 0x1fffu;
-  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
-  return (uint16_t)(sign | h);
-}
-
 // [tap][cin][cout_ld] fp32 -> [tap][cout_pad][cin_pad_h] fp16 (K-major rows of 64-element / 128-byte K blocks): the
 // B operand of the kind::f16 tensor-core path for layers whose activations are stored in half precision
 void Engine::pack_tc_f16(ConvW& c, const std::vector<float>& pw) {
@@ -228,7 +204,7 @@ void Engine::pack_tc_f16(ConvW& c, const std::vector<float>& pw) {
   for (int tp = 0; tp < taps; ++tp)
     for (int ci = 0; ci < c.cin; ++ci)
       for (int co = 0; co < c.cout; ++co)
-        h[((size_t)tp * cout_pad + co) * cin_pad + ci] = f32_to_f16_rn(pw[((size_t)tp * c.cin + ci) * c.cout_ld + co]);
+        h[((size_t)tp * cout_pad + co) * cin_pad + ci] = gv_f32_to_f16(pw[((size_t)tp * c.cin + ci) * c.cout_ld + co]);
   c.w_tc_h = upload(t); c.cin_pad_h = cin_pad;
 }
 
@@ -548,7 +524,6 @@ static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, int ten
   int h = F.h, w = F.w;
   for (int l = 0; l < 4; ++l) { P.h[l] = h; P.w[l] = w; P.lvl[l] = A.alloc_f((size_t)2 * B * P.N * h * w); h /= 2; w /= 2; }
   const float scale = 1.0f / std::sqrt((float)F.c);
-#ifndef GV_HOSTSIM
   if (tensor_cores && F.c % 32 == 0 && F.ld % 4 == 0 && F.ld == F.c) {
     // tcgen05 GEMM; the other frame's features act as the K-major "weights"
     const bool split = tensor_cores >= 2;
@@ -565,9 +540,7 @@ static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, int ten
     }
     A.release(mk);
   } else
-#endif
   {
-    (void)tensor_cores;
     corr_volume(cx, F.batch(0, B), F.batch(B, B), P.lvl[0], scale);
     corr_volume(cx, F.batch(B, B), F.batch(0, B), P.lvl[0] + (int64_t)B * P.N * P.N, scale);
   }

@@ -1,6 +1,6 @@
 """TEST-ONLY: builds the sources of gimm-vfi_b200/csrc with g++ -DGV_HOSTSIM
 (every thread-per-element kernel body runs as an OpenMP loop; conv / corr GEMM use
-naive host loops) so the host orchestration and kernel arithmetic can be checked
+naive host loops; the tensor-core convolution's operand rounding is emulated by csrc/conv_tc_hostsim.cu) so the host orchestration and kernel arithmetic can be checked
 against the oracle in the GPU-less build container.  Never loaded by the product."""
 import os
 import subprocess
@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "gimm-vfi_b200", "csrc")
-SOURCES = ["ops_pointwise.cu", "corr.cu", "conv.cu", "engine.cu", "c_api.cu"]
+SOURCES = ["ops_pointwise.cu", "corr.cu", "conv.cu", "conv_tc_hostsim.cu", "engine.cu", "c_api.cu"]
 OUT = os.path.join(HERE, "libgimmvfi_hostsim.so")
 
 

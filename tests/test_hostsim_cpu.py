@@ -110,3 +110,29 @@ def test_hostsim_gimm_forward_matches_oracle(weights0, gimm_only):
         c1 = O.sample_coord_input(1, (128, 160), [0.5], 1.0).unsqueeze(0).contiguous()
         with pytest.raises(GimmvfiError):
             e.forward(synth_batch(1, 128, 160, seed=1), c1, 0.5 * torch.ones(1, 1), None)
+
+
+import os as _os
+
+
+@pytest.mark.parametrize("mode", [3, 2, 1] if _os.environ.get("GIMMVFI_HOSTSIM_ALL_MODES") else [3])   # (72 s per mode on 8 cores)
+def test_hostsim_tensor_core_modes_match_oracle(eng, weights0, mode):
+    """The engine's tensor-core ORCHESTRATION on the CPU: precision modes 1-3 with the tensor-core convolution's operand rounding
+    emulated on the host (csrc/conv_tc_hostsim.cu) — half-precision trunk tensors, merged GRU gates, stride-2 and pre-padded
+    layers, tensor-core correlation — against the oracle within the product's tolerance (max|d imgt_pred| <= 1e-3)."""
+    torch.set_grad_enabled(False)
+    B, H, W, ts = 1, 128, 160, [0.5]
+    xs = synth_batch(B, H, W, seed=3)
+    coords = torch.stack([O.sample_coord_input(B, (H, W), [t], 1.0) for t in ts], 0).contiguous()
+    tt = torch.stack([t * torch.ones(B) for t in ts], 0).contiguous()
+    eng.set_tensor_cores(mode)
+    try:
+        out = eng.forward(xs, coords, tt, None)
+    finally:
+        eng.set_tensor_cores(0)
+    ref = O.gimmvfi_r_forward(weights0, xs, [(coords[0], None)], [tt[0]])
+    d_img = (out["imgt_pred"][0] - ref["imgt_pred"][0]).abs().max().item()
+    d_raft = (out["raft_flow"] - ref["raft_flow"]).abs().max().item()
+    print("hostsim mode", mode, "imgt_pred max %.3e raft_flow max %.3e" % (d_img, d_raft))
+    assert d_img <= 1e-3
+    assert d_raft <= (2e-3 if mode >= 2 else 5e-4)
