@@ -164,6 +164,12 @@ ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float ou
   pack_tc(c, pw);
   // layers of the final decoder's residual trunk read half-precision activations in precision mode 3 (run())
   if (name.rfind("amt_final_decoder.convblock.", 0) == 0 && name.rfind("amt_final_decoder.convblock.0", 0) != 0) pack_tc_f16(c, pw);
+  // precision mode 4 (experimental): the 32/64-channel full-resolution chains are stored in half as well -> their consumers
+  static const char* const kHalfFed[] = {"cnn_encoder.3.", "cnn_encoder.4.", "cnn_encoder.5.", "cnn_encoder.7", "res_conv.1", "res_conv.3.", "res_conv.5",
+                                         "amt_final_decoder.upsample.3.", "amt_final_decoder.upsample.4.", "amt_final_decoder.upsample.5.",
+                                         "amt_final_decoder.upsample.6.", "amt_final_decoder.upsample.7"};
+  for (const char* pre : kHalfFed)
+    if (name.rfind(pre, 0) == 0) { pack_tc_f16(c, pw); break; }
   conv_[name] = c;
   return c;
 }
@@ -390,11 +396,12 @@ struct Net {
   }
   void conv_e(const std::string& name, const TV& in0, const TV& in1, const TV& out, const ConvEpi& e, int stride = 1, bool reflect = false) {
     const ConvW& w = W(name);
-    if (reflect && cx.tc && !in1.p && stride == 1 && w.w_tc && in0.ld % 4 == 0) {
+    if (reflect && cx.tc && !in1.p && stride == 1 && w.w_tc && in0.ld % (in0.f16 ? 8 : 4) == 0 && (!in0.f16 || w.w_tc_h)) {
       // the TMA path can only zero-fill: materialise the reflect padding once, then a "valid" conv on the padded buffer
       Arena& A = cx.arena;
       const size_t mk = A.mark();
-      TV pad = A.tensor(in0.n, in0.h + 2 * (w.kh / 2), in0.w + 2 * (w.kw / 2), in0.c, (in0.c + 3) & ~3);
+      TV pad = in0.f16 ? A.tensor_h(in0.n, in0.h + 2 * (w.kh / 2), in0.w + 2 * (w.kw / 2), in0.c)
+                       : A.tensor(in0.n, in0.h + 2 * (w.kh / 2), in0.w + 2 * (w.kw / 2), in0.c, (in0.c + 3) & ~3);
       pad_reflect(cx, in0, pad, w.kh / 2);
       ConvGeom g; g.stride = 1; g.ph = 0; g.pw = 0; g.loose_w = 1;
       conv2d(cx, pad, TV(), w, g, e, out);
@@ -782,7 +789,9 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   {
     const size_t mk = A.mark();
     const std::string p = "amt_final_decoder.upsample.";
-    TV a = A.tensor(2 * B, H, W, 8), b = A.tensor(2 * B, H, W, 32), c = A.tensor(2 * B, H, W, 32), d = A.tensor(2 * B, H, W, 64);
+    const bool hs = half_chains(cx);
+    TV a = A.tensor(2 * B, H, W, 8);
+    TV b = hs ? A.tensor_h(2 * B, H, W, 32) : A.tensor(2 * B, H, W, 32), c = A.tensor_like(b, 32), d = A.tensor_like(b, 64);
     pixel_shuffle(cx, feat4, a, 2);
     N.convrelu(p + "2", a, b); N.convrelu(p + "3", b, c); N.convrelu(p + "4", c, b); N.convrelu(p + "5", b, c);
     N.convrelu(p + "6", c, d);
@@ -933,7 +942,9 @@ void Engine::gimm_encode(Net& N, const TV& nf /*2B: [nf01; nf10]*/, const TV& f0
   tap("gimm.splat_w", wts);
   {
     const size_t mk = A.mark();
-    TV a = A.tensor(2 * B, H, W, 16), x = A.tensor(2 * B, H, W, 32), y = A.tensor(2 * B, H, W, 32), m = A.tensor(2 * B, H, W, 32);
+    const bool hs = half_chains(cx);   // precision mode 4: the 32-channel full-resolution chain lives in half precision
+    TV a = A.tensor(2 * B, H, W, 16);
+    TV x = hs ? A.tensor_h(2 * B, H, W, 32) : A.tensor(2 * B, H, W, 32), y = A.tensor_like(x, 32), m = A.tensor_like(x, 32);
     N.conv("cnn_encoder.0", nf, a);
     N.conv("cnn_encoder.1", a, x, ACT_LRELU);
     for (int i = 3; i <= 5; ++i) {  // LateralBlock fi_components.py:17-29 (+ the LeakyReLU after the last one)
@@ -967,7 +978,9 @@ void Engine::gimm_decode(Net& N, const TV& X64, const TV& f01, const TV& f10, co
   TV hin = A.tensor(B, H, W, 35, 36);  // HypoNet input [latent32 | t,y,x]
   {
     const size_t mk = A.mark();
-    TV a = A.tensor(B, H, W, 32), x = A.tensor(B, H, W, 64), m = A.tensor(B, H, W, 64), y = A.tensor(B, H, W, 64);
+    const bool hs = half_chains(cx);
+    TV a = hs ? A.tensor_h(B, H, W, 32) : A.tensor(B, H, W, 32);
+    TV x = A.tensor_like(a, 64), m = A.tensor_like(a, 64), y = A.tensor_like(a, 64);
     N.conv("res_conv.0", X64, a);
     N.conv("res_conv.1", a, x, ACT_LRELU);
     N.conv("res_conv.3.layers.0", x, m, ACT_LRELU);

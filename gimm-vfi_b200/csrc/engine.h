@@ -67,8 +67,12 @@ class Engine {
   void set_debug(bool on) { debug_ = on; }
   // per-kernel CUDA-event timing of the next forward(s): {"name": {"ms", "work", "launches"}}
   void set_profile(bool on) { profile_ = on; }
-  // 0: fp32 CUDA cores everywhere; 1: post-RAFT convs on TF32 tensor cores; 2: + RAFT convs on 3xTF32 tensor cores
+  // 0: fp32 CUDA cores everywhere; 1: post-RAFT convs on TF32 tensor cores; 2: + RAFT convs on 3xTF32 tensor cores;
+  // 3: + final-decoder residual trunk in fp16; 4: + the 32/64-channel full-resolution chains in fp16 (experimental)
   void set_tensor_cores(int mode) { tc_mode_ = mode; }
+  // precision mode 4 (experimental): the 32/64-channel full-resolution chains (motion encoder laterals, latent
+  // refiner, final-decoder upsample branch) are stored in half precision like the residual trunk of mode 3
+  bool half_chains(const Ctx& cx) const { return cx.tc && tc_mode_ >= 4; }
   std::string profile_json(gvStream_t stream);
   // Video callers (src/video_Nx.py:134-216) walk consecutive pairs (j, j+1), (j+1, j+2), ...: the RAFT encoder products of a
   // call's SECOND frame (fnet map, cnet net/inp, projected context features) can be kept in a caller-owned device buffer and

@@ -174,7 +174,18 @@ struct PadReflectK4 {
     st4(dst.p + dst.off(q.n, q.y, q.x) + q.c * 4, ld4(src.p + src.off(q.n, y, x) + q.c * 4));
   }
 };
+struct PadReflectK16 {   // half-precision tensors (2-byte elements)
+  TV src, dst; int pad;
+  GV_HD int refl(int v, int n) const { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    int y = refl(q.y - pad, src.h), x = refl(q.x - pad, src.w);
+    reinterpret_cast<uint16_t*>(dst.p)[dst.off(q.n, q.y, q.x) + q.c] = reinterpret_cast<const uint16_t*>(src.p)[src.off(q.n, y, x) + q.c];
+  }
+};
 void pad_reflect(Ctx& cx, const TV& src, const TV& dst, int pad) {
+  if (src.f16 != dst.f16) throw std::runtime_error("pad_reflect: source and destination must have the same storage type");
+  if (src.f16) { parallel_for(cx, dst.pixels() * dst.c, PadReflectK16{src, dst, pad}, "pad_reflect"); return; }
   if (vec4_ok(src) && vec4_ok(dst)) { parallel_for(cx, dst.pixels() * (dst.c / 4), PadReflectK4{src, dst, pad}, "pad_reflect"); return; }
   parallel_for(cx, dst.pixels() * dst.c, PadReflectK{src, dst, pad}, "pad_reflect");
 }

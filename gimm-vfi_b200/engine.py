@@ -56,7 +56,8 @@ class EngineHandle:
 
     def set_tensor_cores(self, mode: int):
         """0: fp32 CUDA cores; 1: post-RAFT convs on tcgen05 TF32; 2: + RAFT convs on tcgen05 3xTF32; 3: + the final decoder's
-        residual trunk stored in fp16 on tcgen05 kind::f16 (conv_tc.cu).  The workspace plan depends on the mode."""
+        residual trunk stored in fp16 on tcgen05 kind::f16 (conv_tc.cu); 4 (experimental): + the 32/64-channel full-resolution chains in
+        fp16.  The workspace plan depends on the mode."""
         self.lib.check(self.lib.dll.gimmvfi_set_tensor_cores(self._h, int(mode)), self._h)
         self.tensor_cores = int(mode)
         self._plans.clear()

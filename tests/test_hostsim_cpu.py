@@ -115,7 +115,7 @@ def test_hostsim_gimm_forward_matches_oracle(weights0, gimm_only):
 import os as _os
 
 
-@pytest.mark.parametrize("mode", [3, 2, 1] if _os.environ.get("GIMMVFI_HOSTSIM_ALL_MODES") else [3])   # (72 s per mode on 8 cores)
+@pytest.mark.parametrize("mode", [4, 3, 2, 1] if _os.environ.get("GIMMVFI_HOSTSIM_ALL_MODES") else [3])   # (72 s per mode on 8 cores)
 def test_hostsim_tensor_core_modes_match_oracle(eng, weights0, mode):
     """The engine's tensor-core ORCHESTRATION on the CPU: precision modes 1-3 with the tensor-core convolution's operand rounding
     emulated on the host (csrc/conv_tc_hostsim.cu) — half-precision trunk tensors, merged GRU gates, stride-2 and pre-padded
