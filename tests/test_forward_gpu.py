@@ -23,6 +23,8 @@ TOL_IMG = 1e-3
 
 
 MODES = {"tc_mixed_f16_trunk": 3, "tc_3xtf32_raft+tf32": 2, "tc_tf32_post_raft": 1, "fp32": 0}
+if os.environ.get("GIMMVFI_TEST_MODE4"):   # experimental mode 4 (fp16 storage of the 32/64-channel chains): opt-in until validated on hardware
+    MODES = {"tc_mixed_f16_chains": 4, **MODES}
 
 
 @pytest.fixture(scope="module", params=list(MODES))
