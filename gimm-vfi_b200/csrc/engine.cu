@@ -360,6 +360,7 @@ void Engine::finalize_gimm_part() {
     }
     ConvW c; c.w = upload(pw); c.b = upload(pb); c.cin = fin; c.cout = fout; c.kh = c.kw = 1; c.cout_ld = ld;
     pack_tc(c, pw);
+    if (l >= 1) pack_tc_f16(c, pw);   // precision mode 4: the sin() activations between the layers (|x| <= 1) are stored in half
     conv_[key] = c;
   }
   g9_ = vec("g_filter"); alpha_fe_ = vec("alpha_fe"); alpha_v_ = vec("alpha_v");
@@ -992,7 +993,7 @@ void Engine::gimm_decode(Net& N, const TV& X64, const TV& f01, const TV& f10, co
   hypo_pack_input(cx, coords_t, hin.slice(32, 3));
   {
     const size_t mk = A.mark();
-    TV a = A.tensor(B, H, W, 128), b = A.tensor(B, H, W, 128);
+    TV a = half_chains(cx) ? A.tensor_h(B, H, W, 128) : A.tensor(B, H, W, 128), b = A.tensor_like(a, 128);
     N.conv("hyponet.params_dict.linear_wb0", hin, a, ACT_SIN);
     N.conv("hyponet.params_dict.linear_wb1", a, b, ACT_SIN);
     N.conv("hyponet.params_dict.linear_wb2", b, a, ACT_SIN);
