@@ -167,7 +167,8 @@ ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float ou
   // precision mode 4 (experimental): the 32/64-channel full-resolution chains are stored in half as well -> their consumers
   static const char* const kHalfFed[] = {"cnn_encoder.3.", "cnn_encoder.4.", "cnn_encoder.5.", "cnn_encoder.7", "res_conv.1", "res_conv.3.", "res_conv.5",
                                          "amt_final_decoder.upsample.3.", "amt_final_decoder.upsample.4.", "amt_final_decoder.upsample.5.",
-                                         "amt_final_decoder.upsample.6.", "amt_final_decoder.upsample.7"};
+                                         "amt_final_decoder.upsample.6.", "amt_final_decoder.upsample.7", "amt_init_decoder.convblock.1.",
+                                         "amt_init_decoder.convblock.2.", "amt_init_decoder.convblock.3.", "amt_init_decoder.convblock.4"};
   for (const char* pre : kHalfFed)
     if (name.rfind(pre, 0) == 0) { pack_tc_f16(c, pw); break; }
   conv_[name] = c;
@@ -843,7 +844,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     resize_bilinear(cx, s1, fin.slice(263, 3), 4.f, 4.f, 1.f, 0, ACT_NONE);
     backwarp(cx, fin.slice(260, 3), f0in, fin.slice(266, 3));
     backwarp(cx, fin.slice(263, 3), f1in, fin.slice(269, 3));
-    TV x4 = A.tensor(B, H4, W4, 128);
+    TV x4 = half_chains(cx) ? A.tensor_h(B, H4, W4, 128) : A.tensor(B, H4, W4, 128);   // (mode 4: the H/4 residual trunk in half too)
     N.convrelu("amt_init_decoder.convblock.0", fin, x4);
     for (int k = 1; k <= 3; ++k) resblock(N, "amt_init_decoder.convblock." + std::to_string(k), x4, 128, 64);
     TV o136 = A.tensor(B, H4, W4, 133, 136);
