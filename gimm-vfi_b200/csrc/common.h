@@ -24,6 +24,7 @@
 typedef void* gvStream_t;
 #else
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #define GV_HD __host__ __device__ __forceinline__
 #define GV_DEV __device__ __forceinline__
 typedef cudaStream_t gvStream_t;
@@ -96,6 +97,36 @@ inline float gv_f16_to_f32(uint16_t h) {
   return f;
 }
 
+// half-aware element access for the pointwise kernels that write / read the half-precision tensors of precision mode 4
+GV_HD uint16_t gv_f2h(float v) {
+#if defined(__CUDA_ARCH__)
+  return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+#else
+  return gv_f32_to_f16(v);
+#endif
+}
+GV_HD float gv_h2f(uint16_t h) {
+#if defined(__CUDA_ARCH__)
+  return __half2float(__ushort_as_half(h));
+#else
+  return gv_f16_to_f32(h);
+#endif
+}
+GV_HD float ld1(const TV& t, int64_t eoff) { return t.f16 ? gv_h2f(reinterpret_cast<const uint16_t*>(t.p)[eoff]) : t.p[eoff]; }
+GV_HD void st1(const TV& t, int64_t eoff, float v) { if (t.f16) reinterpret_cast<uint16_t*>(t.p)[eoff] = gv_f2h(v); else t.p[eoff] = v; }
+struct alignas(8) H4 { uint16_t x, y, z, w; };
+GV_HD F4 ld4v(const TV& t, int64_t eoff) {   // 4 consecutive channels: one 16-byte (fp32) or 8-byte (half) access
+  if (t.f16) { const H4 h = *reinterpret_cast<const H4*>(reinterpret_cast<const uint16_t*>(t.p) + eoff); F4 r = {gv_h2f(h.x), gv_h2f(h.y), gv_h2f(h.z), gv_h2f(h.w)}; return r; }
+  return ld4(t.p + eoff);
+}
+GV_HD void st4v(const TV& t, int64_t eoff, const F4& v) {
+  if (t.f16) { H4 h = {gv_f2h(v.x), gv_f2h(v.y), gv_f2h(v.z), gv_f2h(v.w)}; *reinterpret_cast<H4*>(reinterpret_cast<uint16_t*>(t.p) + eoff) = h; }
+  else st4(t.p + eoff, v);
+}
+// like vec4_ok, half tensors allowed (8-byte alignment suffices for them)
+inline bool vec4_ok_any(const TV& t) {
+  return (reinterpret_cast<uintptr_t>(t.p) & (t.f16 ? 7 : 15)) == 0 && t.c % 4 == 0 && t.ld % 4 == 0 && t.sn % 4 == 0;
+}
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_PRELU = 3, ACT_SIGMOID = 4, ACT_TANH = 5, ACT_SIN = 6 };
 
 GV_HD float apply_act(float v, int act, const float* slope, int ch) {

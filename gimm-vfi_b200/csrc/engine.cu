@@ -168,7 +168,8 @@ ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float ou
   static const char* const kHalfFed[] = {"cnn_encoder.3.", "cnn_encoder.4.", "cnn_encoder.5.", "cnn_encoder.7", "res_conv.1", "res_conv.3.", "res_conv.5",
                                          "amt_final_decoder.upsample.3.", "amt_final_decoder.upsample.4.", "amt_final_decoder.upsample.5.",
                                          "amt_final_decoder.upsample.6.", "amt_final_decoder.upsample.7", "amt_init_decoder.convblock.1.",
-                                         "amt_init_decoder.convblock.2.", "amt_init_decoder.convblock.3.", "amt_init_decoder.convblock.4"};
+                                         "amt_init_decoder.convblock.2.", "amt_init_decoder.convblock.3.", "amt_init_decoder.convblock.4",
+                                         "amt_final_decoder.convblock.0."};
   for (const char* pre : kHalfFed)
     if (name.rfind(pre, 0) == 0) { pack_tc_f16(c, pw); break; }
   conv_[name] = c;
@@ -777,7 +778,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
 
   // ------------------------------------------------------------ hoisted (t-independent) decoder feature upsampling
   TV fup4 = A.tensor(2 * B, H4, W4, 128);   // NewInitDecoder.upsample   fi_components.py:234-244
-  TV fup1 = A.tensor(2 * B, H, W, 64);      // NewMultiFlowDecoder.upsample fi_components.py:284-295
+  TV fup1 = half_chains(cx) ? A.tensor_h(2 * B, H, W, 64) : A.tensor(2 * B, H, W, 64);      // NewMultiFlowDecoder.upsample fi_components.py:284-295
   {
     const size_t mk = A.mark();
     const std::string p = "amt_init_decoder.upsample.";
@@ -888,12 +889,17 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     TV F0 = A.tensor(B, H, W, 6, 8), F1 = A.tensor(B, H, W, 6, 8), Mk = A.tensor(B, H, W, 3, 4), Rs = A.tensor(B, H, W, 9, 12);
     {
       const size_t mk = A.mark();
-      TV fin1 = A.tensor(B, H, W, 273, 276);
-      TV fl0 = fin1.slice(256, 2), fl1 = fin1.slice(258, 2), mk1 = fin1.slice(260, 1);
+      // precision mode 4: the 273-channel concat buffer itself is half precision (written by the half-aware resize / backwarp /
+      // copy kernels); the up-sampled flows and mask are additionally kept in fp32 (they drive the warps and the output heads)
+      const bool hs = half_chains(cx);
+      TV fin1 = hs ? A.tensor_h(B, H, W, 273, 280) : A.tensor(B, H, W, 273, 276);
+      TV aux5 = hs ? A.tensor(B, H, W, 5, 8) : TV();
+      TV fl0 = hs ? aux5.slice(0, 2) : fin1.slice(256, 2), fl1 = hs ? aux5.slice(2, 2) : fin1.slice(258, 2), mk1 = hs ? aux5.slice(4, 1) : fin1.slice(260, 1);
       resize_bilinear(cx, fl4.slice(0, 2), fl0, 0.25f, 0.25f, 4.f, 0, ACT_NONE);
       resize_bilinear(cx, fl4.slice(2, 2), fl1, 0.25f, 0.25f, 4.f, 0, ACT_NONE);
       resize_bilinear(cx, ft_4, fin1.slice(0, 128), 0.25f, 0.25f, 1.f, 0, ACT_NONE);
       resize_bilinear(cx, mask4, mk1, 0.25f, 0.25f, 1.f, 0, ACT_NONE);
+      if (hs) copy_channels(cx, aux5.slice(0, 5), fin1.slice(256, 5));
       backwarp(cx, fup1.batch(0, B), fl0, fin1.slice(128, 64));
       backwarp(cx, fup1.batch(B, B), fl1, fin1.slice(192, 64));
       copy_channels(cx, s0, fin1.slice(261, 3));

@@ -104,7 +104,15 @@ struct CopyK4 {
     st4(dst.p + dst.off(q.n, q.y, q.x) + q.c * 4, ld4(src.p + src.off(q.n, q.y, q.x) + q.c * 4));
   }
 };
+struct CopyAnyK {   // either side may be half precision (precision mode 4 concat buffers)
+  TV src, dst;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    st1(dst, dst.off(q.n, q.y, q.x) + q.c, ld1(src, src.off(q.n, q.y, q.x) + q.c));
+  }
+};
 void copy_channels(Ctx& cx, const TV& src, const TV& dst) {
+  if (src.f16 || dst.f16) { parallel_for(cx, dst.pixels() * dst.c, CopyAnyK{src, dst}, "copy_channels"); return; }
   TV s4 = src; s4.c = dst.c;
   if (vec4_ok(s4) && vec4_ok(dst)) { parallel_for(cx, dst.pixels() * (dst.c / 4), CopyK4{src, dst}, "copy_channels"); return; }
   parallel_for(cx, dst.pixels() * dst.c, CopyK{src, dst}, "copy_channels");
@@ -282,7 +290,40 @@ struct ResizeK4 {   // 4 channels per thread, the per-component arithmetic of Re
     st4(o, r);
   }
 };
+struct ResizeAnyK4 {   // ResizeK4 with half-aware loads / stores (no accumulate mode)
+  TV src, dst; float rsy, rsx, mult; int act;
+  GV_HD float fin(float v00, float v01, float v10, float v11, float lx0, float lx1, float ly0, float ly1) const {
+    float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    v *= mult;
+    if (act == ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+    return v;
+  }
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c / 4);
+    float sy = rsy * ((float)q.y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+    float sx = rsx * ((float)q.x + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+    int y0 = (int)sy, x0 = (int)sx;
+    if (y0 > src.h - 1) y0 = src.h - 1;
+    if (x0 > src.w - 1) x0 = src.w - 1;
+    int y1 = y0 + (y0 < src.h - 1 ? 1 : 0), x1 = x0 + (x0 < src.w - 1 ? 1 : 0);
+    float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+    float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const int64_t b = (int64_t)q.n * src.sn + q.c * 4;
+    const F4 a00 = ld4v(src, b + ((int64_t)y0 * src.w + x0) * src.ld), a01 = ld4v(src, b + ((int64_t)y0 * src.w + x1) * src.ld);
+    const F4 a10 = ld4v(src, b + ((int64_t)y1 * src.w + x0) * src.ld), a11 = ld4v(src, b + ((int64_t)y1 * src.w + x1) * src.ld);
+    F4 r;
+    r.x = fin(a00.x, a01.x, a10.x, a11.x, lx0, lx1, ly0, ly1); r.y = fin(a00.y, a01.y, a10.y, a11.y, lx0, lx1, ly0, ly1);
+    r.z = fin(a00.z, a01.z, a10.z, a11.z, lx0, lx1, ly0, ly1); r.w = fin(a00.w, a01.w, a10.w, a11.w, lx0, lx1, ly0, ly1);
+    st4v(dst, dst.off(q.n, q.y, q.x) + q.c * 4, r);
+  }
+};
 void resize_bilinear(Ctx& cx, const TV& src, const TV& dst, float rscale_y, float rscale_x, float mult, int accumulate, int act) {
+  if (src.f16 || dst.f16) {
+    TV s4 = src; s4.c = dst.c;
+    if (accumulate || !vec4_ok_any(s4) || !vec4_ok_any(dst)) throw std::runtime_error("resize_bilinear: half-precision tensors need 4-channel-aligned views and no accumulation");
+    parallel_for(cx, dst.pixels() * (dst.c / 4), ResizeAnyK4{src, dst, rscale_y, rscale_x, mult, act}, "resize_bilinear");
+    return;
+  }
   {
     TV s4 = src; s4.c = dst.c;
     if (vec4_ok(s4) && vec4_ok(dst)) {
@@ -320,7 +361,45 @@ struct BackwarpK4 {   // 4 channels per thread; same tap order / products as tap
     st4(dst.p + dst.off(q.n, q.y, q.x) + q.c * 4, v);
   }
 };
+struct BackwarpAnyK4 {   // BackwarpK4 with half-aware loads / stores
+  TV src, flow, dst;
+  GV_HD void acc(F4& v, int64_t eoff, float w) const { const F4 a = ld4v(src, eoff); v.x += a.x * w; v.y += a.y * w; v.z += a.z * w; v.w += a.w * w; }
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c / 4);
+    const float* f = flow.p + flow.off(q.n, q.y, q.x);
+    const BilinearTap t = border_tap(q.x, q.y, f[0], f[1], flow.w, flow.h, src.w, src.h);
+    const int64_t b = (int64_t)q.n * src.sn + q.c * 4;
+    F4 v = {0.f, 0.f, 0.f, 0.f};
+    if (t.vy0 && t.vx0) acc(v, b + ((int64_t)t.y0 * src.w + t.x0) * src.ld, t.wx0 * t.wy0);
+    if (t.vy0 && t.vx1) acc(v, b + ((int64_t)t.y0 * src.w + t.x1) * src.ld, t.wx1 * t.wy0);
+    if (t.vy1 && t.vx0) acc(v, b + ((int64_t)t.y1 * src.w + t.x0) * src.ld, t.wx0 * t.wy1);
+    if (t.vy1 && t.vx1) acc(v, b + ((int64_t)t.y1 * src.w + t.x1) * src.ld, t.wx1 * t.wy1);
+    st4v(dst, dst.off(q.n, q.y, q.x) + q.c * 4, v);
+  }
+};
+struct BackwarpAnyK {   // scalar: 3-channel image warps into a half-precision concat buffer
+  TV src, flow, dst;
+  GV_HD void operator()(int64_t i) const {
+    Idx4 q = decode4(i, dst.h, dst.w, dst.c);
+    const float* f = flow.p + flow.off(q.n, q.y, q.x);
+    const BilinearTap t = border_tap(q.x, q.y, f[0], f[1], flow.w, flow.h, src.w, src.h);
+    const int64_t b = (int64_t)q.n * src.sn + q.c;
+    float v = 0.f;
+    if (t.vy0 && t.vx0) v += ld1(src, b + ((int64_t)t.y0 * src.w + t.x0) * src.ld) * (t.wx0 * t.wy0);
+    if (t.vy0 && t.vx1) v += ld1(src, b + ((int64_t)t.y0 * src.w + t.x1) * src.ld) * (t.wx1 * t.wy0);
+    if (t.vy1 && t.vx0) v += ld1(src, b + ((int64_t)t.y1 * src.w + t.x0) * src.ld) * (t.wx0 * t.wy1);
+    if (t.vy1 && t.vx1) v += ld1(src, b + ((int64_t)t.y1 * src.w + t.x1) * src.ld) * (t.wx1 * t.wy1);
+    st1(dst, dst.off(q.n, q.y, q.x) + q.c, v);
+  }
+};
 void backwarp(Ctx& cx, const TV& src, const TV& flow, const TV& dst) {
+  if (flow.f16) throw std::runtime_error("backwarp: the flow field must be fp32");
+  if (src.f16 || dst.f16) {
+    TV s4 = src; s4.c = dst.c;
+    if (vec4_ok_any(s4) && vec4_ok_any(dst)) parallel_for(cx, dst.pixels() * (dst.c / 4), BackwarpAnyK4{src, flow, dst}, "backwarp");
+    else parallel_for(cx, dst.pixels() * dst.c, BackwarpAnyK{src, flow, dst}, "backwarp");
+    return;
+  }
   {
     TV s4 = src; s4.c = dst.c;
     if (vec4_ok(s4) && vec4_ok(dst)) { parallel_for(cx, dst.pixels() * (dst.c / 4), BackwarpK4{src, flow, dst}, "backwarp"); return; }
