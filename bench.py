@@ -144,11 +144,11 @@ def main():
     ap.add_argument("--height", type=int, default=H_PAD)
     ap.add_argument("--width", type=int, default=W_PAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="mixed", choices=["mixed", "3xtf32", "tf32", "fp32"],
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "mixed4", "3xtf32", "tf32", "fp32"],
                     help="mixed (default): RAFT + correlation on tcgen05 with 3xTF32 operand splitting and register-promoted "
                          "accumulation, post-RAFT convs on tcgen05 TF32, the final decoder's 256-channel residual trunk stored in fp16 on "
                          "tcgen05 kind::f16; 3xtf32: the trunk in TF32 too; tf32: RAFT on fp32 CUDA cores instead; fp32: everything on "
-                         "fp32 CUDA cores.  All meet max|d imgt_pred| <= 1e-3 vs the reference (profiles/).")
+                         "fp32 CUDA cores.  All meet max|d imgt_pred| <= 1e-3 vs the reference (profiles/).  mixed4: experimental mode 4, see DESIGN.md.")
     ap.add_argument("--profile-json", default="", help="write the per-kernel CUDA-event breakdown here")
     ap.add_argument("--timesteps", type=int, default=1,
                     help="T interpolated frames per pair at t = i/(T+1): 1 = the headline metric (t=0.5); 7 = the reference's N=8 video setting "
@@ -175,7 +175,7 @@ def main():
     H, W, B, T, tval = args.height, args.width, 1, max(1, args.timesteps), 0.5
     tvals = [0.5] if T == 1 else [i / (T + 1) for i in range(1, T + 1)]
     model = GIMMVFI_R(seed=0).to(dev).eval()
-    model.tensor_cores = {"fp32": 0, "tf32": 1, "3xtf32": 2, "mixed": 3}[args.precision]
+    model.tensor_cores = {"fp32": 0, "tf32": 1, "3xtf32": 2, "mixed": 3, "mixed4": 4}[args.precision]
     xs_host = synth_pair(H, W, seed=100 + rank).pin_memory()
     xs = xs_host.to(dev, non_blocking=True)
     coord = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
@@ -321,8 +321,8 @@ def main():
         fl = flops_per_frame(P, T)
         line = {
             "metric": METRIC, "value": world * B * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "3xtf32": "tf32", "mixed": "tf32+f16 operands, f32 accumulate"}[args.precision], "data": "synthetic",
-            "config": {"precision": {"tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.4e-4 at this size (profiles/r01_parity_1080p.log)", "fp32": "fp32 everywhere", "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere; max|d imgt_pred| vs CPU reference 5.9e-4 at this size, PSNR 81.2 dB (profiles/r01_parity_1080p_mode3_final.log)", "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.5e-4 at this size, PSNR 81.7 dB (profiles/r01_parity_1080p_modes.log)"}[args.precision], "workload": "%d x 1920x1080 pair per GPU (padded %dx%d), %s, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "3xtf32": "tf32", "mixed": "tf32+f16 operands, f32 accumulate", "mixed4": "tf32+f16 operands, f32 accumulate"}[args.precision], "data": "synthetic",
+            "config": {"precision": {"tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.4e-4 at this size (profiles/r01_parity_1080p.log)", "fp32": "fp32 everywhere", "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere; max|d imgt_pred| vs CPU reference 5.9e-4 at this size, PSNR 81.2 dB (profiles/r01_parity_1080p_mode3_final.log)", "mixed4": "EXPERIMENTAL precision mode 4 (mixed + fp16 storage of the 32/64-channel full-resolution chains, HypoNet activations, init-decoder trunk and the decoder concat); parity validated on the CPU emulation only (DESIGN.md)", "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.5e-4 at this size, PSNR 81.7 dB (profiles/r01_parity_1080p_modes.log)"}[args.precision], "workload": "%d x 1920x1080 pair per GPU (padded %dx%d), %s, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
                                    % (B, H, W, "t=0.5, T=1" if T == 1 else "T=%d frames per pair at t=i/%d" % (T, T + 1)), "parallelism": "pairs sharded, 1 all-gather of output frames" if world > 1 else "single GPU",
                        "l2": "256 MiB L2 flush between timed steps; per-step working set ~30 GB >> L2",
                        "algorithmic_tflop_per_frame": fl / 1e12, "achieved_tflops_end_to_end": world * fl / (ms * 1e-3) / 1e12},
