@@ -33,6 +33,8 @@ METRIC = "interpolated frames/sec @1080p t=0.5"
 UNIT = "frames/s"
 H_PAD, W_PAD = 1088, 1920          # InputPadder(1080x1920, 32)  src/utils/utils.py:156-185
 SAMPLE_H, SAMPLE_W = 256, 448      # bounded CPU sample (BASELINE config 1 size)
+if os.environ.get("GIMMVFI_CPU_SAMPLE"):   # tests shrink the sample (e.g. "128x160"); the scaling to 1080p is by pixel count either way
+    SAMPLE_H, SAMPLE_W = (int(v) for v in os.environ["GIMMVFI_CPU_SAMPLE"].lower().split("x"))
 
 
 def flops_per_frame(P, T=1, P_full=None):
