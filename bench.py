@@ -86,15 +86,22 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_threads():
-    """Threads for the CPU arm: all host cores up to 32 (the reference's small convolutions stop scaling —
-    and oversubscribe oneDNN — beyond that on the 128-core GPU boxes)."""
-    return max(1, min(os.cpu_count() or 1, int(os.environ.get("GIMMVFI_CPU_THREADS", "32"))))
+    """Threads for the CPU arm: all host cores up to GIMMVFI_CPU_THREADS (default 64: the builder's 1080p run, 104.5 s per frame,
+    used 64 of the GPU box's 128 cores; the reference's small RAFT convolutions oversubscribe oneDNN beyond that)."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("GIMMVFI_CPU_THREADS", "64"))))
 
 
-def cpu_reference_fps(steps, warmup):
-    """The reference's own PyTorch path on the host cores, via the oracle port (bit-identical
-    to the reference in the build container, tests/golden/manifest.json).  Bounded sample:
-    one 256x448 pair per step; frames/s scaled by the pixel ratio to the 1088x1920 workload."""
+def workload_config(H, W, T, B=1, precision=None, world=1):
+    """`config` of the JSON line — IDENTICAL in both arms (the driver compares them: same workload, same metric)."""
+    return {"workload": "%d x 1920x1080 pair per GPU (padded %dx%d), %s, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
+                        % (B, H, W, "t=0.5, T=1" if T == 1 else "T=%d frames per pair at t=i/%d" % (T, T + 1)),
+            "height": H, "width": W, "timesteps": T, "pairs_per_step_per_gpu": B}
+
+
+def cpu_reference_fps(steps, warmup, H=H_PAD, W=W_PAD, T=1):
+    """The reference's own PyTorch path (fp32, torch.no_grad) on the host cores via the oracle port (bit-identical to the unmodified
+    reference in the build container at every fixture size incl. 736x1280: tests/golden/manifest*.json).  One step = one full
+    forward of ONE HxW pair — the same workload the GPU arm times, no extrapolation."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gimmvfi_r_oracle as O
     from gimmvfi_b200.synth import synth_batch
@@ -102,9 +109,10 @@ def cpu_reference_fps(steps, warmup):
 
     torch.set_num_threads(cpu_threads())
     sd = random_state_dict(0)
-    xs = synth_batch(1, SAMPLE_H, SAMPLE_W, seed=6)
-    coord = [(O.sample_coord_input(1, (SAMPLE_H, SAMPLE_W), [0.5]), None)]
-    t = [0.5 * torch.ones(1)]
+    xs = synth_batch(1, H, W, seed=100)
+    tvals = [0.5] if T == 1 else [i / (T + 1) for i in range(1, T + 1)]
+    coord = [(O.sample_coord_input(1, (H, W), [tv]), None) for tv in tvals]
+    t = [tv * torch.ones(1) for tv in tvals]
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -114,27 +122,136 @@ def cpu_reference_fps(steps, warmup):
             if i >= warmup:
                 times.append(dt)
     sec = sum(times) / len(times)
-    ratio = (SAMPLE_H * SAMPLE_W) / float(H_PAD * W_PAD)
-    return dict(sample_sec_per_frame=sec, fps_sample=1.0 / sec, fps_scaled=ratio / sec, cores=torch.get_num_threads(),
-                sample="oracle port (== reference PyTorch fp32 path) on one %dx%d pair, %d warm-up + %d timed; frames/s scaled by the pixel ratio "
-                       "%d/%d to the 1088x1920 workload (all-pairs corr term grows faster, so this flatters the CPU)"
-                       % (SAMPLE_H, SAMPLE_W, warmup, steps, SAMPLE_H * SAMPLE_W, H_PAD * W_PAD))
+    return dict(sec_per_step=sec, fps=T / sec, cores=torch.get_num_threads(), times=times)
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the SAME config (one 1088x1920 pair per step).  A forward takes
+    ~100 s on the box's host cores, so the number of forwards actually run is bounded (GIMMVFI_REF_MAX_STEPS timed, default 2, after
+    at most one warm-up) — `steps`/`warmup` echo the request, `steps_timed`/`warmup_run` say what ran."""
     if rank != 0:
         return
-    r = cpu_reference_fps(max(1, args.steps), max(1, args.warmup))
+    H, W = args.height, args.width
+    scaled = None
+    if os.environ.get("GIMMVFI_CPU_SAMPLE"):   # contract tests only: a small frame instead of the workload (NOT the same config; flagged)
+        H, W = (int(v) for v in os.environ["GIMMVFI_CPU_SAMPLE"].lower().split("x"))
+        scaled = (H * W) / float(args.height * args.width)
+    T = max(1, args.timesteps)
+    timed = max(1, min(args.steps, int(os.environ.get("GIMMVFI_REF_MAX_STEPS", "2"))))
+    warm = min(max(0, args.warmup), int(os.environ.get("GIMMVFI_REF_MAX_WARMUP", "1")))
+    r = cpu_reference_fps(timed, warm, H, W, T)
+    fps = r["fps"] * (scaled if scaled else 1.0)
+    sample = ("oracle port (== reference PyTorch fp32 path, bit-identical to it on the golden fixtures) on the full %dx%d pair, "
+              "%d warm-up + %d timed forwards of %d requested (bounded: ~100 s each)" % (H, W, warm, timed, args.steps))
+    if scaled:
+        sample = "TEST SAMPLE %dx%d pixel-scaled to %dx%d — not the benchmark config" % (H, W, args.height, args.width)
+    cfg = workload_config(args.height, args.width, T)
+    if scaled:
+        cfg["timed_sample"] = "%dx%d" % (H, W)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["fps_scaled"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * r["sample_sec_per_frame"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1 x 1920x1080 pair (padded 1088x1920), t=0.5, GIMM-VFI-R, random-init weights", "timed_sample": "%dx%d" % (SAMPLE_H, SAMPLE_W)},
-        "cpu_baseline": {"value": r["fps_scaled"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
-        "e2e": {"value": r["fps_scaled"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "steps_timed": timed, "warmup_run": warm, "ms_per_step": 1000.0 * r["sec_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_torch_baseline(H, W, T, dev, steps=3, warmup=1):
+    """The 'stock PyTorch on the same B200' bar of SURVEY 2a / 8(d): the oracle port (== the reference's own torch ops: cuDNN / cuBLAS
+    convolutions, grid_sample, index_add_ splat) in fp32 with TF32 disabled, eager, same input, CUDA-event timed.  Test
+    infrastructure used as a measured baseline only; nothing of it is on the product path."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gimmvfi_r_oracle as O
+    from gimmvfi_b200.synth import synth_batch
+    from gimmvfi_b200.weights import random_state_dict
+
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    try:
+        sd = {k: v.to(dev) for k, v in random_state_dict(0).items()}
+        xs = synth_batch(1, H, W, seed=100).to(dev)
+        tvals = [0.5] if T == 1 else [i / (T + 1) for i in range(1, T + 1)]
+        ms = []
+        with torch.no_grad(), torch.device(dev):   # the oracle's factory calls (linspace / arange / zeros) follow the default device
+            coord = [(O.sample_coord_input(1, (H, W), [tv]), None) for tv in tvals]
+            t = [tv * torch.ones(1) for tv in tvals]
+            out = None
+            for i in range(warmup + steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = O.gimmvfi_r_forward(sd, xs, coord, t)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                if i >= warmup:
+                    ms.append(e0.elapsed_time(e1))
+        peak = torch.cuda.max_memory_allocated(dev)
+        img = out["imgt_pred"][0]
+        del out
+        torch.cuda.empty_cache()
+        m = sum(ms) / len(ms)
+        return {"value": T / (m * 1e-3), "unit": UNIT, "ms_per_step": m, "steps": steps, "warmup": warmup, "peak_mem_gb": peak / 2 ** 30,
+                "what": "oracle port == the reference's own torch ops (cuDNN/cuBLAS eager, fp32, allow_tf32=False, cudnn.benchmark=True, "
+                        "splat via index_add_) on the same B200 and the same 1x%dx%d input; CUDA-event timed" % (H, W)}, img
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant layer shape of each kernel, written by
+    scripts/summarize_ncu.py from the committed `ncu --set full` captures (profiles/ncu_traffic.json); absent -> traffic null."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        return json.load(f)
+
+
+PRECISIONS = {"fp32": 0, "tf32": 1, "3xtf32": 2, "mixed": 3, "mixed4": 4}
+PRECISION_NOTES = {
+    "fp32": "fp32 CUDA cores everywhere",
+    "tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate",
+    "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate",
+    "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder "
+             "residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere.  Parity at this exact workload: "
+             "tests/test_bench_parity_gpu.py::big_r_1088x1920_t0.5 (reference-generated fixture, max|d imgt_pred| <= 1e-3)",
+    "mixed4": "mixed + fp16 storage of the 32/64-channel full-resolution chains, HypoNet activations, init-decoder trunk and the decoder concat",
+}
+DTYPES = {"fp32": "f32", "tf32": "tf32", "3xtf32": "tf32", "mixed": "tf32+f16 operands, f32 accumulate", "mixed4": "tf32+f16 operands, f32 accumulate"}
+NOTES = {"conv2d_tc_f16": "tcgen05 kind::f16 implicit GEMM on fp16-stored activations (TMA halo tiles, TMEM fp32 accumulators)",
+         "conv2d_tc_tf32": "tcgen05 kind::tf32 implicit GEMM (TMA halo tiles, TMEM accumulators); the TF32 tensor peak is half the bf16 peak used as denominator (ceiling 0.5)",
+         "conv2d_tc_3xtf32": "tcgen05 3xTF32 (3 MMAs per K step + register-promoted accumulation): 'achieved' counts ALGORITHMIC flops, the tensor pipe "
+                             "executes 3x that at the TF32 rate (= bf16 peak / 2), so the ceiling of this ratio is 1/6",
+         "conv2d_tc_3xf16": "tcgen05 3-term fp16 hi/lo split (3 kind::f16 MMAs per K step + register-promoted accumulation): 'achieved' counts ALGORITHMIC "
+                            "flops, the tensor pipe executes 3x that at the f16 rate, so the ceiling of this ratio is 1/3",
+         "conv2d_simt_n64": "fp32 CUDA-core implicit GEMM measured against the tensor-pipe peak (the layer class is tensor-bound, SURVEY 8(d))"}
+CEILING = {"conv2d_tc_tf32": 0.5, "conv2d_tc_3xtf32": 1.0 / 6.0, "conv2d_tc_3xf16": 1.0 / 3.0, "conv2d_tc_f16": 1.0}
+
+
+def build_roofline(prof, raw_prof, peaks):
+    """The dominant kernel of the profiled step: algorithmic work / CUDA-event time of its launches."""
+    total_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    dname, d = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    traffic = load_ncu_traffic()
+    if dname.startswith(("conv2d", "corr_gemm", "hyponet")):
+        ach = d["work"] / (d["ms"] * 1e-3) / 1e12
+        tr = traffic.get(dname, {})
+        roof = {"bound": "tensor", "kernel": dname, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
+                "traffic": tr.get("bytes"), "traffic_detail": tr or None,
+                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["which"], "format_ceiling_frac": CEILING.get(dname),
+                "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_ms, "note": NOTES.get(dname, "")}
+        top = max(((k, v) for k, v in raw_prof.items() if k.startswith(("conv2d", "corr_gemm", "hyponet"))), key=lambda kv: kv[1]["ms"])
+        roof["top_layer"] = {"name": top[0], "ms_total": top[1]["ms"], "launches": top[1]["launches"],
+                             "tflops": top[1]["work"] / (top[1]["ms"] * 1e-3) / 1e12, "frac_of_peak": top[1]["work"] / (top[1]["ms"] * 1e-3) / 1e12 / peaks["tf_sust"]}
+    else:   # pointwise / gather kernels report `work` in fp32 elements touched
+        ach = 4.0 * d["work"] / (d["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dname, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                "traffic": traffic.get(dname, {}).get("bytes"), "launches": d["launches"], "share_of_step": d["ms"] / total_ms}
+    return roof, total_ms
 
 
 def main():
@@ -143,22 +260,27 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--height", type=int, default=H_PAD)
-    ap.add_argument("--width", type=int, default=W_PAD)
+    ap.add_argument("--config", default="pair1080", choices=["pair1080", "batch720"],
+                    help="pair1080 (default, BASELINE configs[1], the headline metric): one 1920x1080 pair per GPU per step, weak scaling.  "
+                         "batch720 (BASELINE configs[4]): 256 1280x720 pairs (padded 736x1280) sharded across the ranks, a step = the whole "
+                         "batch in micro-batches of --micro-batch pairs per forward, ONE all-gather of the output frames, strong scaling")
+    ap.add_argument("--pairs", type=int, default=256)
+    ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="mixed", choices=["mixed", "mixed4", "3xtf32", "tf32", "fp32"],
-                    help="mixed (default): RAFT + correlation on tcgen05 with 3xTF32 operand splitting and register-promoted "
-                         "accumulation, post-RAFT convs on tcgen05 TF32, the final decoder's 256-channel residual trunk stored in fp16 on "
-                         "tcgen05 kind::f16; 3xtf32: the trunk in TF32 too; tf32: RAFT on fp32 CUDA cores instead; fp32: everything on "
-                         "fp32 CUDA cores.  All meet max|d imgt_pred| <= 1e-3 vs the reference (profiles/).  mixed4: experimental mode 4, see DESIGN.md.")
+    ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--precision", default="mixed", choices=list(PRECISIONS))
     ap.add_argument("--profile-json", default="", help="write the per-kernel CUDA-event breakdown here")
     ap.add_argument("--timesteps", type=int, default=1,
-                    help="T interpolated frames per pair at t = i/(T+1): 1 = the headline metric (t=0.5); 7 = the reference's N=8 video setting "
-                         "(flow estimation amortised over 7 frames; secondary figure, profiles/)")
+                    help="T interpolated frames per pair at t = i/(T+1): 1 = the headline metric (t=0.5); 7 = the reference's N=8 video setting")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    batch_mode = args.config == "batch720"
+    if not args.height:
+        args.height, args.width = (736, 1280) if batch_mode else (H_PAD, W_PAD)
+    args.warmup = max(args.warmup, 3 if not batch_mode else 1) if args.impl == "ours" else args.warmup
 
-    from gimmvfi_b200.parallel import init_from_env
+    from gimmvfi_b200.parallel import init_from_env, shard_range
 
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
@@ -172,31 +294,62 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     from gimmvfi_b200 import GIMMVFI_R
-    from gimmvfi_b200.synth import synth_pair
+    from gimmvfi_b200.synth import synth_batch
 
-    H, W, B, T, tval = args.height, args.width, 1, max(1, args.timesteps), 0.5
+    H, W, T = args.height, args.width, max(1, args.timesteps)
     tvals = [0.5] if T == 1 else [i / (T + 1) for i in range(1, T + 1)]
     model = GIMMVFI_R(seed=0).to(dev).eval()
-    model.tensor_cores = {"fp32": 0, "tf32": 1, "3xtf32": 2, "mixed": 3, "mixed4": 4}[args.precision]
-    xs_host = synth_pair(H, W, seed=100 + rank).pin_memory()
+    model.tensor_cores = PRECISIONS[args.precision]
+    if batch_mode:
+        mine = shard_range(args.pairs, rank, world)
+        MB = max(1, args.micro_batch)
+        nmb = (len(mine) + MB - 1) // MB
+        B = MB
+        distinct = synth_batch(min(4, MB), H, W, seed=100 + 7 * rank)              # a few distinct pairs, tiled to the micro-batch
+        xs_host = distinct.repeat((MB + distinct.shape[0] - 1) // distinct.shape[0], 1, 1, 1, 1)[:MB].contiguous().pin_memory()
+        per_rank_max = len(shard_range(args.pairs, 0, world))
+    else:
+        B, nmb, MB = 1, 1, 1
+        xs_host = synth_batch(1, H, W, seed=100 + rank).pin_memory()
     xs = xs_host.to(dev, non_blocking=True)
     coord = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
     tt = [tv * torch.ones(B, device=dev) for tv in tvals]
-    gathered = torch.empty(world * B * T, 3, H, W, device=dev) if world > 1 else None
+    frames_per_step_rank = (len(mine) if batch_mode else B) * T
+    if batch_mode:
+        outbuf = torch.empty(per_rank_max * T, 3, H, W, device=dev)
+        gathered = torch.empty(world * per_rank_max * T, 3, H, W, device=dev) if world > 1 else None
+    else:
+        outbuf = None
+        gathered = torch.empty(world * B * T, 3, H, W, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step():
-        out = model(xs, coord, t=tt)
-        img = torch.stack(out["imgt_pred"], 0).reshape(-1, 3, H, W) if T > 1 else out["imgt_pred"][0]
+    def frames_of(out, b):
+        return (torch.stack(out["imgt_pred"], 1).reshape(-1, 3, H, W) if T > 1 else out["imgt_pred"][0])[: b * T]
+
+    def step(x=None):
+        """one step on device-resident inputs: pair1080 = one forward; batch720 = this rank's shard in micro-batches + ONE all-gather"""
+        if not batch_mode:
+            img = frames_of(model(xs if x is None else x, coord, t=tt), B)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, img.contiguous())   # the single output collective
+            return img
+        done = 0
+        for m in range(nmb):
+            b = min(MB, len(mine) - done)
+            outbuf[done * T:(done + b) * T].copy_(frames_of(model(xs, coord, t=tt), b))   # (a ragged last micro-batch computes MB pairs, keeps b)
+            done += b
         if world > 1:
-            dist.all_gather_into_tensor(gathered, img.contiguous())   # the single output collective
-        return img
+            dist.all_gather_into_tensor(gathered, outbuf)
+        return outbuf
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    aux = model.aux_outputs
+    if batch_mode:
+        model.aux_outputs = False   # config 5 collects frames only (SURVEY 8(e)); pair1080 produces every reference output
     for _ in range(args.warmup):
         step()
     barrier()
@@ -217,11 +370,11 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
-    launches = model.engine.last_launches
-    # ---- end-to-end through the public API: pinned host input -> H2D -> forward -> D2H of the frame, every step.
-    # The loop is what a video caller runs (src/video_Nx.py:134-216 of the reference walks consecutive pairs): the copies of
-    # step i+1 / i-1 travel on a second stream while step i computes; nothing is reused across steps and the whole K-step
-    # region (all copies included) is timed by the wall clock between two full synchronisations.
+    launches = model.engine.last_launches * nmb
+    # ---- end-to-end through the public API: pinned host input -> H2D -> forward -> D2H of the frames, every forward.
+    # The loop is what a video / batch caller runs (src/video_Nx.py:134-216 walks consecutive pairs): the copies of forward i+1 / i-1
+    # travel on a second stream while forward i computes; nothing is reused across forwards and the whole region (all copies
+    # included) is timed by the wall clock between two full synchronisations.
     out_host = [torch.empty(B * T, 3, H, W).pin_memory() for _ in range(2)]
     x_dev = [torch.empty_like(xs) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -230,6 +383,7 @@ def main():
     ev_free = [torch.cuda.Event() for _ in range(2)]   # forward that read the buffer finished
     ev_out = [torch.cuda.Event() for _ in range(2)]    # D2H of the result buffer finished
     keep = [None, None]
+    n_fwd = args.steps * nmb
 
     def h2d(i):
         with torch.cuda.stream(copy_stream):
@@ -243,14 +397,14 @@ def main():
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     h2d(0)
-    for i in range(args.steps):
+    for i in range(n_fwd):
         main_stream.wait_event(ev_in[i % 2])
-        if i + 1 < args.steps:
+        if i + 1 < n_fwd:
             h2d(i + 1)
         c = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
         o = model(x_dev[i % 2], c, t=[tv * torch.ones(B, device=dev) for tv in tvals])
-        img = torch.stack(o["imgt_pred"], 0).reshape(-1, 3, H, W) if T > 1 else o["imgt_pred"][0]
-        if world > 1:
+        img = frames_of(o, B)
+        if world > 1 and not batch_mode:
             dist.all_gather_into_tensor(gathered, img.contiguous())
         ev_free[i % 2].record(main_stream)
         keep[i % 2] = img
@@ -260,16 +414,18 @@ def main():
             img.record_stream(copy_stream)
             out_host[i % 2].copy_(img, non_blocking=True)
             ev_out[i % 2].record(copy_stream)
+        if batch_mode and world > 1 and (i + 1) % nmb == 0:
+            dist.all_gather_into_tensor(gathered, outbuf)
     torch.cuda.synchronize(dev)
-    e2e_t = [(time.perf_counter() - t0) / args.steps]
+    e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
     barrier()
     clocks = sampler.stop() if sampler else None
-    e2e_ms = 1000.0 * sum(e2e_t) / len(e2e_t)
-    # ---- per-kernel breakdown (CUDA events around every launch of one extra step)
+    # ---- per-kernel breakdown (CUDA events around every launch of one extra forward)
     model.engine.set_profile(True)
-    step()
+    model(xs, coord, t=tt)
     prof = model.engine.profile()
     model.engine.set_profile(False)
+    model.aux_outputs = aux
     # max over ranks
     if world > 1:
         tm = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -283,54 +439,33 @@ def main():
             a = agg.setdefault(k.split(" ")[0], {"ms": 0.0, "work": 0.0, "launches": 0})
             a["ms"] += v["ms"]; a["work"] += v["work"]; a["launches"] += v["launches"]
         prof = agg
-        total_ms = sum(v["ms"] for v in prof.values()) or 1.0
-        dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        roof, total_ms = build_roofline(prof, raw_prof, peaks)
         conv_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("conv2d"))
         conv_fl = sum(v["work"] for k, v in prof.items() if k.startswith("conv2d"))
-        dname, d = dom
-        is_flop = dname.startswith("conv2d") or dname.startswith("corr_gemm")
-        # ncu --set full captures of the dominant LAYER SHAPE of each tensor-core kernel (profiles/r01_ncu_*.jsonl):
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch
-        NCU_TRAFFIC = {"conv2d_tc_f16": {"layer": "3x3 256->256 @1088x1920, fp16 storage (profiles/r01_ncu_conv2d_tc_f16_256x256_1080p.jsonl)",
-                                         "bytes": 1.072938e9 + 1.031320e9, "algorithmic_bytes": 2 * 1088 * 1920 * 256 * 2.0},
-                       "conv2d_tc_tf32": {"layer": "3x3 256->256 @1088x1920", "bytes": 2.146013e9 + 2.092577e9, "algorithmic_bytes": 2 * 1088 * 1920 * 256 * 4.0},
-                       "conv2d_tc_3xtf32": {"layer": "1x5 384->128 @2x136x240 (SepConvGRU gate; profiles/r01_ncu_conv2d_tc_3xtf32_gru_384x128_pair.jsonl)", "bytes": 102.902784e6 + 12.797184e6,
-                                            "algorithmic_bytes": 2 * 136 * 240 * (384 + 128) * 4.0}}
-        NOTES = {"conv2d_tc_f16": "tcgen05 kind::f16 implicit GEMM on the fp16-stored residual trunk (TMA halo tiles, TMEM fp32 accumulators)",
-                 "conv2d_tc_tf32": "tcgen05 kind::tf32 implicit GEMM (TMA halo tiles, TMEM accumulators); TF32 peak is half the bf16 peak used as denominator",
-                 "conv2d_tc_3xtf32": "tcgen05 3xTF32 (3 MMAs per K step + register-promoted accumulation): 'achieved' counts ALGORITHMIC flops, "
-                                     "the tensor pipe executes 3x that at the TF32 rate (= bf16 peak / 2), so the ceiling of this ratio is 1/6; small-resolution RAFT layers on CTA pairs with TMEM-resident split operands (ncu: tensor pipe 58.8 % active)",
-                 "conv2d_simt_n64": "fp32 CUDA-core implicit GEMM measured against the tensor-pipe peak (the layer class is tensor-bound, SURVEY 8(d))"}
-        if is_flop:
-            ach = d["work"] / (d["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": dname, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
-                    "traffic": NCU_TRAFFIC.get(dname, {}).get("bytes"), "traffic_detail": NCU_TRAFFIC.get(dname),
-                    "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["which"],
-                    "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_ms,
-                    "note": NOTES.get(dname, "")}
-            # the single most expensive layer shape, for which the ncu capture above was taken
-            top = max(((k, v) for k, v in raw_prof.items() if k.startswith(("conv2d", "corr_gemm"))), key=lambda kv: kv[1]["ms"])
-            roof["top_layer"] = {"name": top[0], "ms_total": top[1]["ms"], "launches": top[1]["launches"],
-                                 "tflops": top[1]["work"] / (top[1]["ms"] * 1e-3) / 1e12, "frac_of_peak": top[1]["work"] / (top[1]["ms"] * 1e-3) / 1e12 / peaks["tf_sust"]}
-        else:
-            ach = 4.0 * d["work"] / (d["ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": dname, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
-                    "launches": d["launches"], "share_of_step": d["ms"] / total_ms}
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump({"per_kernel": prof, "per_layer": raw_prof, "sum_ms": total_ms, "step_ms": ms}, f, indent=1)
-        P = H * W
-        fl = flops_per_frame(P, T)
+        total_frames = (args.pairs if batch_mode else world * B) * T
+        fl = flops_per_frame(H * W, T)
+        n_pairs_total = args.pairs if batch_mode else world * B
+        cfg = workload_config(H, W, T, B)
+        if batch_mode:
+            cfg["workload"] = ("%d x 1280x720 pairs (padded %dx%d), t=0.5, GIMM-VFI-R (RAFT 20 iters), random-init weights, sharded over %d GPU(s), "
+                               "micro-batch %d pairs per forward, frames only" % (args.pairs, H, W, world, MB))
+            cfg["pairs"] = args.pairs
+            cfg["micro_batch"] = MB
+        cfg.update({"precision": PRECISION_NOTES[args.precision],
+                    "parallelism": ("pairs sharded rank::world, ONE all-gather of the output frames per step" if world > 1 else "single GPU"),
+                    "l2": "256 MiB L2 flush between timed steps; per-step working set ~30 GB >> L2",
+                    "algorithmic_tflop_per_frame": fl / T / 1e12, "achieved_tflops_end_to_end": n_pairs_total * fl / (ms * 1e-3) / 1e12})
         line = {
-            "metric": METRIC, "value": world * B * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "3xtf32": "tf32", "mixed": "tf32+f16 operands, f32 accumulate", "mixed4": "tf32+f16 operands, f32 accumulate"}[args.precision], "data": "synthetic",
-            "config": {"precision": {"tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.4e-4 at this size (profiles/r01_parity_1080p.log)", "fp32": "fp32 everywhere", "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere; max|d imgt_pred| vs CPU reference 5.9e-4 at this size, PSNR 81.2 dB (profiles/r01_parity_1080p_mode3_final.log)", "mixed4": "EXPERIMENTAL precision mode 4 (mixed + fp16 storage of the 32/64-channel full-resolution chains, HypoNet activations, init-decoder trunk and the decoder concat); parity validated on the CPU emulation only (DESIGN.md)", "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate; max|d imgt_pred| vs CPU reference 5.5e-4 at this size, PSNR 81.7 dB (profiles/r01_parity_1080p_modes.log)"}[args.precision], "workload": "%d x 1920x1080 pair per GPU (padded %dx%d), %s, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
-                                   % (B, H, W, "t=0.5, T=1" if T == 1 else "T=%d frames per pair at t=i/%d" % (T, T + 1)), "parallelism": "pairs sharded, 1 all-gather of output frames" if world > 1 else "single GPU",
-                       "l2": "256 MiB L2 flush between timed steps; per-step working set ~30 GB >> L2",
-                       "algorithmic_tflop_per_frame": fl / 1e12, "achieved_tflops_end_to_end": world * fl / (ms * 1e-3) / 1e12},
-            "e2e": {"value": world * B * T / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": xs_host.numel() * 4,
-                    "d2h_bytes_per_step": out_host[0].numel() * 4,
-                    "how": "K-step loop, wall clock between full syncs; per-step H2D/D2H on a copy stream overlapped with the previous/next forward"},
+            "metric": METRIC if not batch_mode else "interpolated frames/sec, batch of 256 1280x720 pairs, t=0.5", "value": total_frames / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if batch_mode else "weak", "vs_baseline": None, "dtype": DTYPES[args.precision], "data": "synthetic",
+            "config": cfg,
+            "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": xs_host.numel() * 4 * nmb,
+                    "d2h_bytes_per_step": out_host[0].numel() * 4 * nmb,
+                    "how": "K-step loop, wall clock between full syncs; per-forward H2D/D2H on a copy stream overlapped with the previous/next forward"},
             "gpu_launches": int(launches) * args.steps,
             "launches_per_step": int(launches),
             "roofline": roof,
@@ -339,13 +474,28 @@ def main():
             "clocks": clocks,
             "wall_s_timed_region": wall,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            # bounded: the CPU arm runs in a child process with a hard time limit
+        if world == 1 and not args.no_torch_baseline and not batch_mode:
             try:
+                del flush
+                torch.cuda.empty_cache()
+                tb, ref_img = gpu_torch_baseline(H, W, T, dev)
+                mine_img = frames_of(model(xs, coord, t=tt), B)[:1]
+                tb["max_abs_diff_imgt_pred_vs_this_arm"] = (ref_img - mine_img).abs().max().item()
+                tb["speedup_of_this_arm"] = line["value"] / tb["value"]
+                line["gpu_torch_baseline"] = tb
+            except Exception as ex:  # noqa: BLE001
+                line["gpu_torch_baseline"] = {"value": None, "error": repr(ex)[:300]}
+        if world == 1 and not args.no_cpu_baseline and not batch_mode:
+            # bounded sample (~10-30 s of CPU work): ONE 256x448 pair per step (BASELINE config 1 size), frames/s EXTRAPOLATED to the
+            # workload by the pixel ratio — the same-config CPU measurement is the `--impl reference` arm (~100 s per forward)
+            try:
+                env = dict(os.environ, GIMMVFI_CPU_SAMPLE="%dx%d" % (SAMPLE_H, SAMPLE_W), GIMMVFI_CPU_THREADS=os.environ.get("GIMMVFI_CPU_THREADS", "32"))
                 o = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
-                                   capture_output=True, text=True, timeout=240).stdout.strip().splitlines()
+                                   capture_output=True, text=True, timeout=240, env=env).stdout.strip().splitlines()
                 cb = json.loads([l for l in o if l.startswith("{")][-1])["cpu_baseline"]
-                cb["sample_sec_per_frame"] = 1.0 / (cb["value"] * (H_PAD * W_PAD) / float(SAMPLE_H * SAMPLE_W))
+                cb["sample"] = ("EXTRAPOLATED: oracle port (== reference PyTorch fp32 path) on one %dx%d pair, 1 warm-up + 2 timed, frames/s scaled by the "
+                                "pixel ratio to %dx%d (the all-pairs correlation grows faster, so this flatters the CPU; the measured same-config "
+                                "figure is the --impl reference arm)" % (SAMPLE_H, SAMPLE_W, H, W))
                 line["cpu_baseline"] = cb
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": "CPU arm did not finish within 240 s: %r" % (ex,)}

@@ -45,7 +45,7 @@ class View(C.Structure):
 
 EXPORTS = [
     "gimmvfi_create", "gimmvfi_destroy", "gimmvfi_load_weight", "gimmvfi_finalize_weights", "gimmvfi_plan",
-    "gimmvfi_forward", "gimmvfi_last_error", "gimmvfi_last_launches", "gimmvfi_set_raft_iters", "gimmvfi_set_debug",
+    "gimmvfi_forward", "gimmvfi_last_error", "gimmvfi_last_launches", "gimmvfi_weights_version", "gimmvfi_set_raft_iters", "gimmvfi_set_debug",
     "gimmvfi_get_tap", "gimmvfi_build_info", "gimmvfi_set_profile", "gimmvfi_profile_json",
     "gimmvfi_set_tensor_cores", "gimmvfi_finalize_weights_gimm", "gimmvfi_gimm_plan", "gimmvfi_gimm_forward", "gimmvfi_frame_cache_bytes", "gimmvfi_set_frame_cache", "gimmvfi_op_conv2d_tc", "gimmvfi_op_conv2d_tc_f16", "gimmvfi_op_conv2d_tc_strided", "gimmvfi_op_frames_u8_to_padded_f32", "gimmvfi_op_pred_to_u8", "gimmvfi_op_softsplat", "gimmvfi_op_backwarp", "gimmvfi_op_resize",
     "gimmvfi_op_corr_volume", "gimmvfi_op_corr_volume_tc", "gimmvfi_op_corr_pool", "gimmvfi_op_corr_pool_pyramid", "gimmvfi_op_corr_lookup", "gimmvfi_op_conv2d",
@@ -81,6 +81,8 @@ class Lib:
         d.gimmvfi_last_error.restype = C.c_char_p
         d.gimmvfi_last_launches.argtypes = [vp]
         d.gimmvfi_last_launches.restype = i64
+        d.gimmvfi_weights_version.argtypes = [vp]
+        d.gimmvfi_weights_version.restype = i64
         d.gimmvfi_set_raft_iters.argtypes = [vp, i32]
         d.gimmvfi_set_debug.argtypes = [vp, i32]
         d.gimmvfi_get_tap.argtypes = [vp, C.c_char_p, PV]

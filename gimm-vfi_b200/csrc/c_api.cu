@@ -78,6 +78,7 @@ int gimmvfi_gimm_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const floa
 
 const char* gimmvfi_last_error(gimmvfi_engine* e) { return e ? e->err.c_str() : g_static_err.c_str(); }
 int64_t gimmvfi_last_launches(gimmvfi_engine* e) { return e->eng.last_launches(); }
+int64_t gimmvfi_weights_version(gimmvfi_engine* e) { return e->eng.weights_version(); }
 int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters) { GV_TRY(e, { if (iters < 1) throw std::runtime_error("iters must be >= 1"); e->eng.raft_iters = iters; }) }
 int gimmvfi_set_debug(gimmvfi_engine* e, int on) { GV_TRY(e, { e->eng.set_debug(on != 0); }) }
 int gimmvfi_get_tap(gimmvfi_engine* e, const char* name, gimmvfi_view* out) {

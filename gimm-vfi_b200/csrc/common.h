@@ -239,6 +239,20 @@ struct Ctx {
 
 void gv_check_launch(const char* what);
 
+#ifndef GV_HOSTSIM
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE function attribute: remember it per (call site, device).
+// `flags` is a zero-initialised static array of 64 bytes owned by the call site; a benign race sets the attribute twice.
+template <class K>
+inline void gv_set_max_smem(K kernel, int bytes, volatile unsigned char* flags) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && flags[dev]) return;
+  cudaError_t er = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (er != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(er));
+  if (dev >= 0 && dev < 64) flags[dev] = 1;
+}
+#endif
+
 // ---------------------------------------------------------------------------
 // thread-per-element launcher
 // ---------------------------------------------------------------------------

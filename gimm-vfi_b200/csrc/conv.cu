@@ -356,12 +356,9 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
   if (conv_narrow_ok(a)) {   // before the tensor-core dispatch: exact fp32 and ~10x faster than a 16-wide MMA tile of padding
     cx.launches++;
     const size_t smem = (size_t)w.kh * w.kw * w.cin * sizeof(float2);
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(conv_narrow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(conv_narrow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr = true;
-    }
+    static volatile unsigned char attr1[64], attr2[64], attr4[64];
+    gv_set_max_smem(conv_narrow_kernel<1>, 96 * 1024, attr1);
+    gv_set_max_smem(conv_narrow_kernel<2>, 96 * 1024, attr2);
     if (cx.prof) {
       char nm[128];
       snprintf(nm, sizeof nm, "conv_narrow k%dx%d c%d>%d @%dx%dx%d", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
@@ -370,8 +367,7 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
     const int blocks = std::min((a.M + 7) / 8, cx.sm_count * 8);
     if (w.kh == 3 && w.kw == 3 && w.cin == 256 && g.ph == 1 && g.pw == 1) {
       const int qpr = (out.w + 3) / 4, quads = out.n * out.h * qpr;
-      static bool attr4 = false;
-      if (!attr4) { cudaFuncSetAttribute(conv_narrow3x3_c256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr4 = true; }
+      gv_set_max_smem(conv_narrow3x3_c256_kernel, 96 * 1024, attr4);
       conv_narrow3x3_c256_kernel<<<std::min((quads + 7) / 8, cx.sm_count * 8), 256, smem, cx.stream>>>(a, qpr, quads);
     } else if (w.cout == 1) conv_narrow_kernel<1><<<blocks, 256, smem, cx.stream>>>(a, a.M);
     else conv_narrow_kernel<2><<<blocks, 256, smem, cx.stream>>>(a, a.M);

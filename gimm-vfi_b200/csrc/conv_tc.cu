@@ -76,11 +76,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-// try_wait suspends the thread up to ~10 ms per attempt; a pipeline that makes no progress for
-// spin_limit attempts (default ~4 s) is a bug -> trap, so a would-be hang becomes a launch failure.
+// A pipeline that makes no progress for spin_limit x 10 ms of WALL time (%globaltimer; default 400 -> 4 s) is a bug -> trap,
+// so a would-be hang becomes a launch failure.  The bound is on elapsed time, not on try_wait attempts: the suspend hint is
+// only an upper bound and a healthy pipeline under a debugger / sanitizer / time-slicing may need many attempts.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int spin_limit) {
   const uint32_t addr = smem_u32(bar);
-  for (int spin = 0; spin_limit == 0 || spin < spin_limit; ++spin) {
+  unsigned long long t0 = 0;
+  for (;;) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
@@ -92,8 +94,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int sp
         : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return;
+    if (spin_limit > 0) {   // slow path only: the clock is not read while the barrier completes within one attempt
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > (unsigned long long)spin_limit * 10000000ull) __trap();
+    }
   }
-  __trap();
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -992,12 +999,8 @@ static void encode_act(CUtensorMap* m, const TV& t, int stride = 1) {
 template <bool SPLIT, int CL, int EW, bool PAIR = false>
 static void launch_tc(int grid, int threads, int smem, gvStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                       const tc::Params& p) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(tc::conv2d_tc_kernel<SPLIT, CL, EW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(er));
-    attr_set = true;
-  }
+  static volatile unsigned char attr_set[64];   // per (instantiation, device)
+  gv_set_max_smem(tc::conv2d_tc_kernel<SPLIT, CL, EW, PAIR>, 227 * 1024, attr_set);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
   cudaLaunchAttribute at[1];

@@ -186,8 +186,8 @@ void corr_pool_pyramid(Ctx& cx, const float* l0, float* l1, float* l2, float* l3
   if (smem <= 96 * 1024 && h2 / 2 > 0 && w2 / 2 > 0) {
     if (cx.dry) return;
     cx.launches++;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(corr_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    static volatile unsigned char attr[64];
+    gv_set_max_smem(corr_pyramid_kernel, 96 * 1024, attr);
     if (cx.prof) cx.prof->begin(cx.stream, "corr_pool_pyramid", (double)rows * h * w);
     const int64_t grid = rows < (int64_t)cx.sm_count * 8 ? rows : (int64_t)cx.sm_count * 8;
     corr_pyramid_kernel<<<(unsigned)grid, 256, smem, cx.stream>>>(l0, l1, l2, l3, rows, h, w);

@@ -36,6 +36,22 @@ void dev_copy(void* dst, const void* src, size_t bytes, gvStream_t s) { cuda_ok(
 void dev_sync(gvStream_t s) { cuda_ok(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
 #endif
 
+// RAII: make the engine's device current for the duration of a call and restore the caller's (an engine on cuda:1 must
+// not change torch's current device, and its uploads / launches must not land on whatever device happens to be current)
+struct DeviceGuard {
+#ifndef GV_HOSTSIM
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    cuda_ok(cudaGetDevice(&prev), "cudaGetDevice");
+    if (prev != dev) { cuda_ok(cudaSetDevice(dev), "cudaSetDevice"); switched = true; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+#else
+  explicit DeviceGuard(int) {}
+#endif
+  DeviceGuard(const DeviceGuard&) = delete; DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ---------------------------------------------------------------------------
 // Profiler (CUDA events around every launch; off by default)
 // ---------------------------------------------------------------------------
@@ -66,6 +82,7 @@ Profiler::~Profiler() { for (void* e : pool) cudaEventDestroy((cudaEvent_t)e); }
 
 std::string Engine::profile_json(gvStream_t stream) {
   std::string out = "{";
+  DeviceGuard dg(device_);
 #ifndef GV_HOSTSIM
   cuda_ok(cudaStreamSynchronize(stream), "sync");
   struct Acc { double ms = 0, work = 0; int64_t n = 0; };
@@ -93,14 +110,17 @@ std::string Engine::profile_json(gvStream_t stream) {
 // ---------------------------------------------------------------------------
 Engine::Engine(int device) : device_(device) {
 #ifndef GV_HOSTSIM
-  cuda_ok(cudaSetDevice(device), "cudaSetDevice");
-  cudaDeviceProp prop;
-  cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
-  sm_count_ = prop.multiProcessorCount;
+  int count = 0;
+  cuda_ok(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
+  if (device < 0 || device >= count) throw std::runtime_error("gimmvfi: no CUDA device " + std::to_string(device));
+  int sms = 148;
+  cuda_ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");   // (no cudaSetDevice: the caller's current device stays)
+  sm_count_ = sms;
 #endif
 }
 
 Engine::~Engine() {
+  DeviceGuard dg(device_);
   for (void* p : dev_allocs_) dev_free(p);
 }
 
@@ -268,8 +288,10 @@ void Engine::pack_xpacked(const std::string& name, int ldp) {
 }
 
 void Engine::finalize_weights() {
+  DeviceGuard dg(device_);
   for (void* p : dev_allocs_) dev_free(p);
   dev_allocs_.clear(); conv_.clear(); vec_.clear();
+  fc_valid_.clear(); ++weights_version_;   // a frame cache stored under the old weights must not be loaded again
   // --- RAFT encoders (raft/extractor.py:122-171); cnet's BatchNorm is folded
   for (int e = 0; e < 2; ++e) {
     const std::string p = e == 0 ? "flow_estimator.fnet" : "flow_estimator.cnet";
@@ -370,8 +392,10 @@ void Engine::finalize_gimm_part() {
 
 // standalone GIMM checkpoint: only the keys of gimm.py's module tree are present
 void Engine::finalize_weights_gimm() {
+  DeviceGuard dg(device_);
   for (void* p : dev_allocs_) dev_free(p);
   dev_allocs_.clear(); conv_.clear(); vec_.clear();
+  fc_valid_.clear(); ++weights_version_;
   finalize_gimm_part();
   finalized_ = true; gimm_only_ = true;
 }
@@ -679,7 +703,8 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     const bool fc_on = fc_ != nullptr && !cx.dry;
     if (fc_on && fc_bytes_ < frame_cache_bytes(P)) throw std::runtime_error("gimmvfi: frame cache smaller than frame_cache_bytes()");
     const bool fload = fc_on && fc_load_, fstore = fc_on && fc_store_;
-    if (fload && (fc_valid_ptr_ != fc_ || fc_valid_dims_[0] != B || fc_valid_dims_[1] != H || fc_valid_dims_[2] != W || fc_valid_dims_[3] != tc_mode_))
+    const auto fc_it = fc_valid_.find(fc_);
+    if (fload && (fc_it == fc_valid_.end() || fc_it->second.B != B || fc_it->second.H != H || fc_it->second.W != W || fc_it->second.mode != tc_mode_))
       throw std::runtime_error("gimmvfi: frame cache load requested, but this buffer does not hold a frame stored by a forward of the same "
                                "problem size and precision mode");
     const int e0 = fload ? B : 0, en = fload ? B : 2 * B;
@@ -705,7 +730,8 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
         copy_channels(cx, c_fmap, fmap.batch(0, B)); copy_channels(cx, c_ni, hx.batch(0, B).slice(0, 256));
         copy_channels(cx, c_f4, feat4.batch(0, B)); copy_channels(cx, c_f8, feat8.batch(0, B));
       }
-      if (fstore) { fc_valid_ptr_ = fc_; fc_valid_dims_[0] = B; fc_valid_dims_[1] = H; fc_valid_dims_[2] = W; fc_valid_dims_[3] = tc_mode_; }
+      if (fstore) fc_valid_[fc_] = FcRec{B, H, W, tc_mode_};
+      else if (!fload) fc_valid_.erase(fc_);
       if (fstore) {   // (before the GRU overwrites `net` in place)
         copy_channels(cx, fmap.batch(B, B), c_fmap); copy_channels(cx, hx.batch(B, B).slice(0, 256), c_ni);
         copy_channels(cx, feat4.batch(B, B), c_f4); copy_channels(cx, feat8.batch(B, B), c_f8);
@@ -1061,6 +1087,7 @@ size_t Engine::plan_gimm(const Problem& p) {
 void Engine::forward_gimm(const Problem& p, const GimmIO& io, void* workspace, size_t workspace_bytes, gvStream_t stream) {
   if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
   if (!io.xs || !io.ori_flow || !io.coords || !io.t || !io.out) throw std::runtime_error("gimm: xs, ori_flow, coords, t and out are required");
+  DeviceGuard dg(device_);
   Ctx cx; cx.stream = stream; cx.sm_count = sm_count_;
   prof_.reset();
   cx.prof = profile_ ? &prof_ : nullptr;
@@ -1095,6 +1122,7 @@ void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t wor
   if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
   if (gimm_only_) throw std::runtime_error("gimmvfi: only GIMM's weights were loaded (finalize_weights_gimm); use gimm_forward");
   if (!io.img_xs || !io.coords || !io.t || !io.imgt_pred) throw std::runtime_error("gimmvfi: img_xs, coords, t and imgt_pred are required");
+  DeviceGuard dg(device_);
   Ctx cx; cx.stream = stream; cx.sm_count = sm_count_;
   prof_.reset();
   cx.prof = profile_ ? &prof_ : nullptr;

@@ -84,6 +84,7 @@ class Engine {
   std::string last_error;
   int raft_iters = 20;  // GIMMVFI_R hard-codes iters=20 (gimmvfi_r.py:126-132)
   int device() const { return device_; }
+  int64_t weights_version() const { return weights_version_; }   // bumped by every finalize_weights*: callers key caches on it
   bool finalized() const { return finalized_; }
 
  private:
@@ -103,9 +104,12 @@ class Engine {
   int device_ = 0;
   bool finalized_ = false, debug_ = false, profile_ = false, gimm_only_ = false;
   int tc_mode_ = 0;
+  int64_t weights_version_ = 0;
   float* fc_ = nullptr; size_t fc_bytes_ = 0; bool fc_load_ = false, fc_store_ = false;
   // what the cache holds (host-side bookkeeping of the last store): a load with a different buffer / problem is refused
-  const float* fc_valid_ptr_ = nullptr; int fc_valid_dims_[4] = {0, 0, 0, 0};
+  // (one record per cache buffer, so several video streams can share an engine; cleared when the weights change)
+  struct FcRec { int B, H, W, mode; };
+  std::map<const float*, FcRec> fc_valid_;
   void pack_tc(ConvW& c, const std::vector<float>& packed);
   void pack_tc_f16(ConvW& c, const std::vector<float>& packed);
   void pack_stem(const std::string& name, const std::string& bn);

@@ -1,6 +1,7 @@
 """EngineHandle: owns one native engine (one per GPU / host thread), the packed
 weights and a cached workspace; turns torch tensors into the raw pointers of the
 C ABI (include/gimmvfi_b200.h).  PyTorch is used for device memory and streams only."""
+import contextlib
 import ctypes as C
 from typing import Dict, Optional
 
@@ -25,6 +26,9 @@ class EngineHandle:
             idx = torch.cuda.current_device() if self.device.index is None else self.device.index
         self.lib.check(self.lib.dll.gimmvfi_create(idx, C.byref(h)))
         self._h = h
+        self._index = idx
+        if self.device.type == "cuda":
+            self.device = torch.device("cuda", idx)
         self._ws = None
         self._plans: Dict[tuple, int] = {}
         self.weights_loaded = False
@@ -79,6 +83,22 @@ class EngineHandle:
     def last_launches(self) -> int:
         return int(self.lib.dll.gimmvfi_last_launches(self._h))
 
+    @property
+    def weights_version(self) -> int:
+        return int(self.lib.dll.gimmvfi_weights_version(self._h))
+
+    def _check_inputs(self, *tensors):
+        """contiguous fp32 on THIS engine's device (a tensor of another GPU would hand the kernels a foreign pointer)"""
+        for x in tensors:
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                raise RuntimeError("gimmvfi_b200: inputs must be contiguous float32 tensors")
+            if x.device.type != self.device.type or (self.device.type == "cuda" and x.device.index != self._index):
+                raise RuntimeError("gimmvfi_b200: input on %s, engine on %s:%d" % (x.device, self.device.type, self._index))
+
+    def _guard(self):
+        """torch's current device = the engine's for the duration of a call (stream lookup, torch.empty)"""
+        return torch.cuda.device(self._index) if self.device.type == "cuda" else contextlib.nullcontext()
+
     # ------------------------------------------------------------------ forward
     def _problem(self, B, Hf, Wf, T, ds, Hc, Wc) -> Problem:
         return Problem(B, Hf, Wf, T, float(ds) if ds else 0.0, Hc, Wc)
@@ -100,8 +120,11 @@ class EngineHandle:
                 aux_outputs: bool = True, frame_cache=None) -> Dict[str, torch.Tensor]:
         """img_xs (B,3,2,Hf,Wf), coords (T,B,1,Hc,Wc,3), t (T,B): contiguous fp32 on self.device.
         frame_cache = (uint8 device tensor of frame_cache_bytes(), load, store): see gimmvfi_set_frame_cache."""
-        for x in (img_xs, coords, t):
-            assert x.dtype == torch.float32 and x.is_contiguous() and x.device.type == self.device.type
+        self._check_inputs(img_xs, coords, t)
+        with self._guard():
+            return self._forward(img_xs, coords, t, ds, aux_outputs, frame_cache)
+
+    def _forward(self, img_xs, coords, t, ds, aux_outputs, frame_cache):
         B, _, _, Hf, Wf = img_xs.shape
         T, _, _, Hc, Wc, _ = coords.shape
         H, W = (Hf, Wf) if not ds else (int(Hf * ds), int(Wf * ds))
@@ -124,7 +147,7 @@ class EngineHandle:
         stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
         if frame_cache is not None:
             buf, load, store = frame_cache
-            assert buf.dtype == torch.uint8 and buf.is_contiguous() and buf.device.type == self.device.type
+            assert buf.dtype == torch.uint8 and buf.is_contiguous() and buf.device == self.device
             self.lib.check(self.lib.dll.gimmvfi_set_frame_cache(self._h, C.c_void_p(buf.data_ptr()), buf.numel(), int(load), int(store)), self._h)
         try:
             self.lib.check(self.lib.dll.gimmvfi_forward(self._h, C.byref(p), C.byref(io), C.c_void_p(self._ws.data_ptr()),
@@ -136,8 +159,11 @@ class EngineHandle:
 
     def gimm_forward(self, xs: torch.Tensor, ori_flow: torch.Tensor, coords: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """GIMM.forward (gimm.py:129-214): xs, ori_flow (B,2,2,H,W), coords (T,B,1,H,W,3), t (T,B) -> (T,B,2,1,H,W)."""
-        for x in (xs, ori_flow, coords, t):
-            assert x.dtype == torch.float32 and x.is_contiguous() and x.device.type == self.device.type
+        self._check_inputs(xs, ori_flow, coords, t)
+        with self._guard():
+            return self._gimm_forward(xs, ori_flow, coords, t)
+
+    def _gimm_forward(self, xs, ori_flow, coords, t):
         B, _, _, H, W = xs.shape
         T = coords.shape[0]
         assert tuple(ori_flow.shape) == (B, 2, 2, H, W) and tuple(coords.shape) == (T, B, 1, H, W, 3) and tuple(t.shape) == (T, B)

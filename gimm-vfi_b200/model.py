@@ -167,11 +167,33 @@ class GIMMVFI_R(nn.Module):
         return psnr.mean() if reduction == "mean" else (psnr.sum() if reduction == "sum" else psnr)
 
 
+def _check_engine_config(config):
+    """The engine is specialised to the shipped HypoNet / warp settings (configs/gimmvfi/*.yaml, module_config.py:28-41): a config
+    that asks for anything else must fail here, not be silently ignored."""
+    hy = config.hyponet
+    want = dict(type="mlp", n_layer=5, input_dim=3, output_dim=2, use_bias=True, normalize_weight=True, output_bias=0.5)
+    for k, v in want.items():
+        if getattr(hy, k, v) != v:
+            raise NotImplementedError("hyponet.%s=%r: the sm_100a engine is built for the shipped value %r" % (k, getattr(hy, k), v))
+    if list(getattr(hy, "hidden_dim", [128])) != [128]:
+        raise NotImplementedError("hyponet.hidden_dim=%r: the engine is built for [128]" % (list(hy.hidden_dim),))
+    act = getattr(hy, "activation", None)
+    if act is not None and (getattr(act, "type", "siren") != "siren" or float(getattr(act, "siren_w0", 1.0)) != 1.0):
+        raise NotImplementedError("hyponet.activation: the engine is built for siren with w0 = 1")
+    if getattr(config, "modulated_layer_idxs", None) not in (None, [], [1]):
+        raise NotImplementedError("modulated_layer_idxs: weight modulation is unused by the shipped models (hyponet.py:101-117 is a no-op)")
+
+
 def create_model(config, ema: bool = False):
-    """src/models/__init__.py:15-37 for the built model types."""
+    """src/models/__init__.py:15-37 for the built model types (gimmvfi_r, gimm)."""
     model_type = config.type.lower()
-    if model_type != "gimmvfi_r":
-        raise ValueError("%s is not built in gimmvfi_b200 (GIMM-VFI-R only; see DESIGN.md scope)" % model_type)
     if ema:
         raise NotImplementedError("EMA wrappers are training-only (src/models/ema.py) and out of scope")
-    return GIMMVFI_R(config), None
+    _check_engine_config(config)
+    if model_type == "gimmvfi_r":
+        return GIMMVFI_R(config), None
+    if model_type == "gimm":
+        from .gimm import GIMM
+
+        return GIMM(config), None
+    raise ValueError("%s is not built in gimmvfi_b200 (gimmvfi_r and gimm; see DESIGN.md scope)" % model_type)

@@ -7,7 +7,7 @@ from typing import List, Optional
 
 import torch
 
-from ._lib import default_lib
+from ._lib import GimmvfiError, default_lib
 
 
 class InputPadder:
@@ -110,13 +110,19 @@ class VideoInterpolator:
         if self._cache is None or self._cache.numel() < need or self._cache.device != dev:
             self._cache, self._cache_valid = torch.empty(need, dtype=torch.uint8, device=dev), False
         aux, m.aux_outputs = m.aux_outputs, False
-        # (the engine keeps its own record of what the buffer holds: a model whose engine was rebuilt, or whose precision mode
-        # changed, refuses the load -> fall back to a full forward once)
-        sig = (id(m.engine), int(m.tensor_cores))
+        # The engine keeps its own record of what each cache buffer holds (problem size, precision mode; cleared when the weights
+        # change): a refused load -> one full forward with load=False.  The signature adds what only the caller can know.
+        sig = (id(m.engine), int(m.tensor_cores), m.engine.weights_version)
         load = self._cache_valid and getattr(self, "_cache_sig", None) == sig
-        m._frame_cache = (self._cache, load, True)
         try:
-            out = m(xs, coords, t=ts, ds_factor=self.ds)
+            try:
+                m._frame_cache = (self._cache, load, True)
+                out = m(xs, coords, t=ts, ds_factor=self.ds)
+            except GimmvfiError as ex:
+                if not (load and "frame cache" in str(ex)):
+                    raise
+                m._frame_cache = (self._cache, False, True)
+                out = m(xs, coords, t=ts, ds_factor=self.ds)
             self._cache_valid, self._cache_sig = True, sig
         except Exception:
             self._cache_valid = False

@@ -89,6 +89,8 @@ int gimmvfi_gimm_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const floa
 
 const char* gimmvfi_last_error(gimmvfi_engine* e);
 int64_t gimmvfi_last_launches(gimmvfi_engine* e);
+/* bumped by every gimmvfi_finalize_weights*: callers that keep derived state (the frame cache below) key it on this */
+int64_t gimmvfi_weights_version(gimmvfi_engine* e);
 int gimmvfi_set_raft_iters(gimmvfi_engine* e, int iters);
 /* debug taps: intermediate tensors of the last forward (views into the workspace) */
 int gimmvfi_set_debug(gimmvfi_engine* e, int on);

@@ -111,3 +111,28 @@ def test_oracle_gimm_matches_reference_golden(name, golden_manifest, weights0):
         assert np.abs(out[i].numpy() - g["out_%d" % i]).max() <= TOL
     one = O.gimm_forward(weights0, xs, coord[0], ori, ts[0] * torch.ones(B), keep_xs_shape=False)   # tensor form
     assert one.shape == (B, 1, H, W, 2) and torch.equal(one.permute(0, 4, 1, 2, 3), out[0])
+
+
+def test_oracle_matches_reference_on_demo_frames(weights0):
+    """The reference's own demo frames (demo/input_frames, 720x844 -> InputPadder 736x864): the fixture holds the uint8 frames and
+    the UNMODIFIED reference's output at this size (oracle/make_golden_big.py) — the oracle restatement must reproduce it."""
+    import json
+
+    import torch.nn.functional as F
+
+    name = "big_r_demo_736x864_t0.5"
+    with open(os.path.join(GOLDEN_DIR, "manifest_big.json")) as f:
+        meta = json.load(f)[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    torch.set_grad_enabled(False)
+    x = torch.from_numpy(g["frames_u8"].copy()).permute(0, 3, 1, 2).float() / 255.0
+    ht, wd = x.shape[-2:]
+    ph, pw = (((ht // 32) + 1) * 32 - ht) % 32, (((wd // 32) + 1) * 32 - wd) % 32
+    x = F.pad(x, [pw // 2, pw - pw // 2, ph // 2, ph - ph // 2], mode="replicate")
+    xs = torch.stack([x[0], x[1]], 1).unsqueeze(0).contiguous()
+    H, W = meta["H"], meta["W"]
+    assert tuple(xs.shape) == (1, 3, 2, H, W)
+    out = O.gimmvfi_r_forward(weights0, xs, [(O.sample_coord_input(1, (H, W), [0.5]), None)], [0.5 * torch.ones(1)])
+    s = int(g["stride"])
+    assert np.abs(out["imgt_pred"][0][..., ::s, ::s].numpy() - g["imgt_pred_0"]).max() <= TOL
+    assert np.abs(out["raft_flow"][..., ::s, ::s].numpy() - g["raft_flow"]).max() <= 50 * TOL
