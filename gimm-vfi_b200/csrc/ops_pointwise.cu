@@ -694,7 +694,117 @@ struct SplatAccK {
     if (x1 >= 0 && x1 < W && y1 >= 0 && y1 < H) atomic_add_f(base + ((int64_t)y1 * W + x1) * acc.ld, v * wse);
   }
 };
+#ifndef GV_HOSTSIM
+// The B200 form of the scatter (the functor above is the reference kernel's thread-per-(pixel, channel) decomposition, kept for the
+// host simulation and for ragged layouts).  ONE thread per source pixel:
+//   * flow, metric, target cell and the four bilinear weights are computed once (the reference does it 17 times per pixel);
+//   * the 16 latent channels arrive as four 16-byte loads; with the metric they form five float4 groups = the 80-byte accumulator
+//     pixel [16 x sum(in*m*w) | sum(m*w) | 3 pad lanes];
+//   * lanes of a warp hold x-consecutive source pixels.  Under a smooth flow lane l's EAST column of target cells is lane l+1's
+//     WEST column: the west contributions travel one lane down by warp shuffle and are summed in registers, so an interior
+//     lane issues 2 instead of 4 corner updates;
+//   * every update is one red.global.add.v4.f32 (16 bytes per atomic): 10-20 vector reductions per pixel instead of 68 scalar ones.
+// Summation order differs from the reference's (whose atomics are unordered anyway): fp32 re-association, ~1e-7 relative.
+__device__ __forceinline__ void red_add_v4(float* addr, const F4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__global__ void __launch_bounds__(256) softsplat_acc_v4_kernel(TV lat, TV flow, TV metric, TV acc, const float* __restrict__ t, int t_mode,
+                                                              int64_t npix) {
+  const int lane = threadIdx.x & 31;
+  const int W = acc.w, H = acc.h;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t npad = (npix + 31) & ~(int64_t)31;   // whole warps take part in the shuffles
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += step) {
+    bool act = i < npix;
+    int x = 0, y = 0, n = 0, x0 = 0, y0 = 0;
+    float wnw = 0.f, wne = 0.f, wsw = 0.f, wse = 0.f, m = 0.f;
+    F4 v[5];
+#pragma unroll
+    for (int g = 0; g < 5; ++g) v[g] = F4{0.f, 0.f, 0.f, 0.f};
+    if (act) {
+      x = (int)(i % W); const int64_t r = i / W; y = (int)(r % H); n = (int)(r / H);
+      const float tt = __ldg(t + n), sc = t_mode ? (1.f - tt) : tt;
+      const float2 f = *reinterpret_cast<const float2*>(flow.p + flow.off(n, y, x));
+      const float fx = (float)x + f.x * sc, fy = (float)y + f.y * sc;
+      act = gv_isfinite(fx) && gv_isfinite(fy);
+      if (act) {
+        const float x0f = floorf(fx), y0f = floorf(fy);
+        x0 = (int)x0f; y0 = (int)y0f;
+        const float x1f = (float)(x0 + 1), y1f = (float)(y0 + 1);
+        wnw = (x1f - fx) * (y1f - fy); wne = (fx - (float)x0) * (y1f - fy);
+        wsw = (x1f - fx) * (fy - (float)y0); wse = (fx - (float)x0) * (fy - (float)y0);
+        m = metric.p[metric.off(n, y, x)];
+        const float* lp = lat.p + lat.off(n, y, x);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { const F4 a = ld4(lp + 4 * g); v[g] = F4{a.x * m, a.y * m, a.z * m, a.w * m}; }
+        v[4] = F4{m, 0.f, 0.f, 0.f};
+      }
+    }
+    // x-neighbour merge: lane l+1 is pixel x+1 of the same row (rows never straddle a merge: x + 1 < W is required)
+    const int px0 = __shfl_down_sync(0xffffffffu, x0, 1), py0 = __shfl_down_sync(0xffffffffu, y0, 1);
+    const int pact = __shfl_down_sync(0xffffffffu, (int)act, 1);
+    const float pwnw = __shfl_down_sync(0xffffffffu, wnw, 1), pwsw = __shfl_down_sync(0xffffffffu, wsw, 1);
+    const bool take = lane < 31 && act && pact && x + 1 < W && px0 == x0 + 1 && py0 == y0;   // my east column == its west column
+    const bool taken = __shfl_up_sync(0xffffffffu, (int)take, 1) != 0 && lane > 0;          // lane l-1 carries my west column
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const bool in_y0 = y0 >= 0 && y0 < H, in_y1 = y1 >= 0 && y1 < H, in_x0 = x0 >= 0 && x0 < W, in_x1 = x1 >= 0 && x1 < W;
+    float* base = acc.p + (int64_t)n * acc.sn;
+    float* a_nw = base + ((int64_t)y0 * W + x0) * acc.ld;
+    float* a_sw = a_nw + (int64_t)W * acc.ld;
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+      // the neighbour's west-column VALUES (its own v * its own west weights), fetched by every lane (shuffles are warp collective)
+      F4 pv;
+      pv.x = __shfl_down_sync(0xffffffffu, v[g].x, 1); pv.y = __shfl_down_sync(0xffffffffu, v[g].y, 1);
+      pv.z = __shfl_down_sync(0xffffffffu, v[g].z, 1); pv.w = __shfl_down_sync(0xffffffffu, v[g].w, 1);
+      if (!act) continue;
+      F4 ne = F4{v[g].x * wne, v[g].y * wne, v[g].z * wne, v[g].w * wne};
+      F4 se = F4{v[g].x * wse, v[g].y * wse, v[g].z * wse, v[g].w * wse};
+      if (take) {
+        ne.x += pv.x * pwnw; ne.y += pv.y * pwnw; ne.z += pv.z * pwnw; ne.w += pv.w * pwnw;
+        se.x += pv.x * pwsw; se.y += pv.y * pwsw; se.z += pv.z * pwsw; se.w += pv.w * pwsw;
+      }
+      if (!taken) {
+        if (in_x0 && in_y0) red_add_v4(a_nw + 4 * g, F4{v[g].x * wnw, v[g].y * wnw, v[g].z * wnw, v[g].w * wnw});
+        if (in_x0 && in_y1) red_add_v4(a_sw + 4 * g, F4{v[g].x * wsw, v[g].y * wsw, v[g].z * wsw, v[g].w * wsw});
+      }
+      if (in_x1 && in_y0) red_add_v4(a_nw + acc.ld + 4 * g, ne);
+      if (in_x1 && in_y1) red_add_v4(a_sw + acc.ld + 4 * g, se);
+    }
+  }
+}
+// "zeroeps" normalisation, 4 channels per thread
+struct SplatNormK4 {
+  TV acc, out;
+  GV_HD void operator()(int64_t i) const {
+    const int g = (int)(i & 3); int64_t r = i >> 2;
+    const int x = (int)(r % out.w); r /= out.w; const int y = (int)(r % out.h); const int n = (int)(r / out.h);
+    const float* a = acc.p + acc.off(n, y, x);
+    float d = a[16]; if (d == 0.f) d = 1.f;
+    const F4 v = ld4(a + 4 * g);
+    st4(out.p + out.off(n, y, x) + 4 * g, F4{v.x / d, v.y / d, v.z / d, v.w / d});
+  }
+};
+#endif
+
 void softsplat_accumulate(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const TV& acc) {
+#ifndef GV_HOSTSIM
+  // vector form: 16-byte aligned latent / accumulator pixels (acc.ld % 4: the pad lanes receive +0)
+  const bool v4 = lat.c == 16 && vec4_ok(lat) && (reinterpret_cast<uintptr_t>(acc.p) & 15) == 0 && acc.ld % 4 == 0 && acc.ld >= 20 && acc.sn % 4 == 0 &&
+                  (reinterpret_cast<uintptr_t>(flow.p) & 7) == 0 && flow.ld % 2 == 0 && flow.sn % 2 == 0 && !acc.f16 && !flow.f16 && !metric.f16;
+  if (v4) {
+    if (cx.dry) return;
+    cx.launches++;
+    const int64_t npix = lat.pixels();
+    if (cx.prof) cx.prof->begin(cx.stream, "softsplat_accumulate", (double)npix * 35.0);   // 140 B per pixel: 16+1+2 read, 16 written
+    int64_t blocks = (npix + 255) / 256, cap = (int64_t)cx.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    softsplat_acc_v4_kernel<<<(unsigned)blocks, 256, 0, cx.stream>>>(lat, flow, metric, acc, t_per_sample, t_mode, npix);
+    gv_check_launch("softsplat_accumulate");
+    if (cx.prof) cx.prof->end(cx.stream);
+    return;
+  }
+#endif
   parallel_for(cx, lat.pixels() * 17, SplatAccK{lat, flow, metric, acc, t_per_sample, t_mode}, "softsplat_accumulate");
 }
 // "zeroeps" normalisation, modules/softsplat.py:330-344.
@@ -708,6 +818,12 @@ struct SplatNormK {
   }
 };
 void softsplat_normalize(Ctx& cx, const TV& acc, const TV& out) {
+#ifndef GV_HOSTSIM
+  if (out.c == 16 && vec4_ok(out) && (reinterpret_cast<uintptr_t>(acc.p) & 15) == 0 && acc.ld % 4 == 0 && acc.sn % 4 == 0) {
+    parallel_for(cx, out.pixels() * 4, SplatNormK4{acc, out}, "softsplat_normalize");
+    return;
+  }
+#endif
   parallel_for(cx, out.pixels() * 16, SplatNormK{acc, out}, "softsplat_normalize");
 }
 
