@@ -391,33 +391,38 @@ def main():
             x_dev[i % 2].copy_(xs_host, non_blocking=True)
             ev_in[i % 2].record(copy_stream)
 
-    barrier()
-    for e in ev_free + ev_out:
-        e.record(main_stream)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    h2d(0)
-    for i in range(n_fwd):
-        main_stream.wait_event(ev_in[i % 2])
-        if i + 1 < n_fwd:
-            h2d(i + 1)
-        c = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
-        o = model(x_dev[i % 2], c, t=[tv * torch.ones(B, device=dev) for tv in tvals])
-        img = frames_of(o, B)
-        if world > 1 and not batch_mode:
-            dist.all_gather_into_tensor(gathered, img.contiguous())
-        ev_free[i % 2].record(main_stream)
-        keep[i % 2] = img
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_free[i % 2])
-            copy_stream.wait_event(ev_out[i % 2])
-            img.record_stream(copy_stream)
-            out_host[i % 2].copy_(img, non_blocking=True)
-            ev_out[i % 2].record(copy_stream)
-        if batch_mode and world > 1 and (i + 1) % nmb == 0:
-            dist.all_gather_into_tensor(gathered, outbuf)
-    torch.cuda.synchronize(dev)
-    e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
+    def e2e_loop(n):
+        """n pipelined forwards; returns wall seconds between two full synchronisations"""
+        barrier()
+        for e in ev_free + ev_out:
+            e.record(main_stream)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        h2d(0)
+        for i in range(n):
+            main_stream.wait_event(ev_in[i % 2])
+            if i + 1 < n:
+                h2d(i + 1)
+            c = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
+            o = model(x_dev[i % 2], c, t=[tv * torch.ones(B, device=dev) for tv in tvals])
+            img = frames_of(o, B)
+            if world > 1 and not batch_mode:
+                dist.all_gather_into_tensor(gathered, img.contiguous())
+            ev_free[i % 2].record(main_stream)
+            keep[i % 2] = img
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[i % 2])
+                copy_stream.wait_event(ev_out[i % 2])
+                img.record_stream(copy_stream)
+                out_host[i % 2].copy_(img, non_blocking=True)
+                ev_out[i % 2].record(copy_stream)
+            if batch_mode and world > 1 and (i + 1) % nmb == 0:
+                dist.all_gather_into_tensor(gathered, outbuf)
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0
+
+    e2e_loop(2 * nmb if not batch_mode else nmb)   # untimed warm-up of the copy stream / pinned buffers / pipelined path (first-touch costs)
+    e2e_ms = 1000.0 * e2e_loop(n_fwd) / args.steps
     barrier()
     clocks = sampler.stop() if sampler else None
     # ---- per-kernel breakdown (CUDA events around every launch of one extra forward)

@@ -188,7 +188,7 @@ int gimmvfi_op_conv2d(const gimmvfi_view* in0, const gimmvfi_view* in1, const fl
 int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1, const float* w_tc, const float* bias, int cin, int cout, int kh,
                          int kw, int act1, const float* slope1, const gimmvfi_view* residual, int act2, const float* slope2,
                          const gimmvfi_view* mul, const gimmvfi_view* gru_z, const gimmvfi_view* gru_h, int split,
-                         const gimmvfi_view* out, void* stream) {
+                         const gimmvfi_view* out, const void* w_tc_s, float w_scale, void* stream) {
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, {
 #ifdef GV_HOSTSIM
@@ -197,6 +197,7 @@ int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1, const
     Ctx cx = op_ctx(stream);
     ConvW w; w.b = bias; w.cin = cin; w.cout = cout; w.kh = kh; w.kw = kw; w.w_tc = w_tc; w.has_lo = true;
     w.cout_pad = tc_cout_pad(cout); w.cin_pad = (cin + 31) & ~31;
+    if (w_tc_s) { w.w_tc_s = w_tc_s; w.cin_pad_s = (cin + 63) & ~63; w.w_scale = w_scale; }   // 3xF16 form of the split kernel
     ConvGeom g; g.stride = 1; g.ph = kh / 2; g.pw = kw / 2;
     ConvEpi ep; ep.act1 = act1; ep.slope1 = slope1; ep.res = to_tv(residual); ep.act2 = act2; ep.slope2 = slope2;
     ep.mul = to_tv(mul); ep.gru_z = to_tv(gru_z); ep.gru_h = to_tv(gru_h);
@@ -240,6 +241,15 @@ int gimmvfi_op_conv2d_tc_f16(const gimmvfi_view* in0, const gimmvfi_view* in1, c
     if (!conv2d_tc_supported(a0, a1, w, g, ep, o, false)) throw std::runtime_error("conv2d_tc_f16: unsupported configuration");
     conv2d_tc(cx, a0, a1, w, g, ep, o, false);
 #endif
+  })
+}
+int gimmvfi_op_hyponet(gimmvfi_engine* e, const gimmvfi_view* latent, const float* coords, const gimmvfi_view* out, int fp32_class, void* stream) {
+  GV_TRY(e, {
+    if (!e->eng.finalized() || !e->eng.hyponet_blob(fp32_class != 0)) throw std::runtime_error("hyponet: finalize_weights() first");
+    Ctx cx = op_ctx(stream);
+    if (!hyponet_fused_supported(to_tv(latent), to_tv(out))) throw std::runtime_error("hyponet: latent (n,h,w,32) dense fp32, out (n,h,w,2)");
+    if (fp32_class) hyponet_fused3(cx, to_tv(latent), coords, e->eng.hyponet_blob(true), to_tv(out));
+    else hyponet_fused(cx, to_tv(latent), coords, e->eng.hyponet_blob(false), to_tv(out));
   })
 }
 int64_t gimmvfi_instnorm_scratch_floats(int n, int c) {

@@ -155,6 +155,11 @@ struct ConvW {
   // fp16 copy for layers fed with half-precision activations: w_tc_h[tap][cout_pad][cin_pad_h] (cin padded to 64)
   const void* w_tc_h = nullptr;
   int cin_pad_h = 0;
+  // fp16 hi / lo planes of w * w_scale for the 3-term kind::f16 split (conv_tc.cu "3xF16"): w_tc_s[2][tap][cout_pad][cin_pad_s]
+  // (cin padded to 64); w_scale = a power of two that lifts max|w| to [2^13, 2^14) so the lo parts stay normal halves
+  const void* w_tc_s = nullptr;
+  int cin_pad_s = 0;
+  float w_scale = 1.f;
 };
 
 // N tiling of the tensor-core path: cout padded to 16, split into <= 256-wide tiles of equal width.
@@ -186,6 +191,24 @@ struct ConvGeom {
   int loose_w = 0;  // x-taps packed into the channel axis of a zero-padded input (Engine::pack_xpacked): the input is
                     // larger than the output and carries its own padding, so the size / padding checks are skipped
 };
+
+// ---------------------------------------------------------------------------
+// Fused HypoNet (hyponet.cu): byte layout of the packed parameter blob, exactly as it sits in shared memory.  Weight tiles are
+// K-major [out row][128-byte K block] in the SWIZZLE_128B pattern of the UMMA descriptors (16-byte chunk c of row r at c ^ (r & 7)).
+//   W0  [128][32] fp32 (TF32-rounded)  latent part of layer 0        | W1..W3 [2 K blocks][128][64] half | W4 [2][16][64] half (2 rows used)
+//   AFF [4][128] fp32: layer-0 rows of t, y, x and the bias          | B1..B3 [128] fp32 | B4 [16] fp32 (output_bias folded in)
+namespace hypo {
+constexpr int W0 = 0, W1 = 16384, W4 = 16384 + 3 * 32768, AFF = W4 + 4096, B1 = AFF + 2048, B4 = B1 + 3 * 512, BLOB = B4 + 64;
+inline size_t swz(int row, int byte_in_row) { return (size_t)row * 128 + (size_t)((((byte_in_row >> 4) ^ (row & 7)) << 4) | (byte_in_row & 15)); }
+}  // namespace hypo
+// fp32-class variant (hyponet.cu, hyponet_fused3): layers 1-3 as three kind::f16 MMAs on fp16 hi / lo pairs (weights pre-scaled by
+// 2^6 and pre-split; activations split by the epilogue and kept in TENSOR memory), layers 0 and 4 on the CUDA cores in fp32.
+//   W13 [3 layers][hi, lo][2 K blocks][128][64] half, swizzled as above | W0A [36][128] fp32: rows 0..31 latent, 32..34 (t, y, x), 35 bias
+//   B13 [3][128] fp32 | W4 [128][2] fp32 | B4 [2] fp32 (output_bias folded in)
+namespace hypo3 {
+constexpr int W13 = 0, W0A = 3 * 2 * 2 * 16384, B13 = W0A + 36 * 128 * 4, W4 = B13 + 3 * 512, B4 = W4 + 1024, BLOB = B4 + 16;
+constexpr float W_SCALE = 64.f;
+}  // namespace hypo3
 
 // ---------------------------------------------------------------------------
 // Execution context
@@ -309,6 +332,10 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1 /*optional 2nd channel segment
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split);
+// hyponet.cu (sm_100a; the host simulation emulates its arithmetic): the whole HypoNet MLP in one kernel
+bool hyponet_fused_supported(const TV& lat, const TV& out);
+void hyponet_fused(Ctx& cx, const TV& lat /*n,h,w,32*/, const float* coords /*n*h*w x (t,y,x)*/, const void* blob /*hypo:: layout*/, const TV& out /*2 ch*/);
+void hyponet_fused3(Ctx& cx, const TV& lat, const float* coords, const void* blob3 /*hypo3:: layout*/, const TV& out);   // fp32-class arithmetic
 // corr.cu
 void split_planes(Ctx& cx, const TV& src, float* planes);  // [2][n*h*w][c]: rn_tf32(x) and rn_tf32(x - rn_tf32(x))
 void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale);   // vol[n][i][j] = <fa[n,i], fb[n,j]> * scale

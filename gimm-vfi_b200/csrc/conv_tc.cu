@@ -63,6 +63,8 @@ struct Params {
   int bk;                          // K elements per 128-byte smem row: 32 (tf32) or 64 (f16)
   int atmem;                       // SPLIT: A_hi / A_lo live in tensor memory (written by the splitter warps), not in smem
   int seg;                         // SPLIT: K steps accumulated in TMEM before promotion to fp32 registers
+  int split_f16;                   // SPLIT: the three MMAs run on kind::f16 with fp16 hi / lo operand pairs (K step = 64 elements = two
+                                   // 32-channel fp32 A boxes; weights pre-split and pre-scaled at pack time): twice the MMA rate of 3xTF32
   float out_scale;                 // accumulator scale applied before the bias (all-pairs correlation: 1/sqrt(C))
   const float* bias;               // padded to tiles_n * BN
   int act1; const float* slope1;
@@ -71,219 +73,7 @@ struct Params {
   TV out2; int split_c;            // channels >= split_c go to out2 (and only they see `mul`): merged z | r gate convolution
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-// A pipeline that makes no progress for spin_limit x 10 ms of WALL time (%globaltimer; default 400 -> 4 s) is a bug -> trap,
-// so a would-be hang becomes a launch failure.  The bound is on elapsed time, not on try_wait attempts: the suspend hint is
-// only an upper bound and a healthy pipeline under a debugger / sanitizer / time-slicing may need many attempts.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int spin_limit) {
-  const uint32_t addr = smem_u32(bar);
-  unsigned long long t0 = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(0x989680u)
-        : "memory");
-    if (ok) return;
-    if (spin_limit > 0) {   // slow path only: the clock is not read while the barrier completes within one attempt
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > (unsigned long long)spin_limit * 10000000ull) __trap();
-    }
-  }
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-// multicast variants: the box lands at the same CTA-relative smem offset (and signals the mbarrier at the same
-// offset) in every CTA of `mask`
-__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-// ---- CTA-pair (cta_group::2) helpers: one MMA of M = 256 spans the two SMs of a cluster; operands and barriers of the
-// peer CTA are addressed through the shared::cluster window
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA loads of one CTA of the pair that signal the LEADER's mbarrier (cluster address)
-__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_2sm(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool f16) {
-  if (f16)
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-// mbar_wait that charges the cycles it blocked to a per-role counter (stall profiling only: p.stall != nullptr)
-__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int spin_limit, long long* acc_cycles) {
-  if (acc_cycles) {
-    const long long t0 = clock64();
-    mbar_wait(bar, parity, spin_limit);
-    *acc_cycles += clock64() - t0;
-  } else {
-    mbar_wait(bar, parity, spin_limit);
-  }
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), version 1 (sm_100).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address  [0,14)
-  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows x 128 B [32,46)
-  d |= (uint64_t)1 << 46;                            // descriptor version [46,48)
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B [61,64)
-  return d;
-}
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-// A operand read from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void mma_tf32_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
+#include "tc_ptx.cuh"
 
 __device__ __forceinline__ float rn_tf32(float x) {  // round-to-nearest-even to 10 mantissa bits
   uint32_t u = __float_as_uint(x);
@@ -608,7 +398,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * BK * 4;   // PAIR: this CTA's half of the weight rows
   const bool ATM = SPLIT && p.atmem;   // TMEM columns: accumulators at 0 / 128, A ring (64 columns per stage) from 256
-  const int a_all = (SPLIT && !ATM) ? 2 * A_BYTES : A_BYTES;
+  const bool SF16 = SPLIT && p.split_f16;   // (implies ATM)
+  const int a_all = (SPLIT && (!ATM || SF16)) ? 2 * A_BYTES : A_BYTES;   // SF16: two 32-channel fp32 sub-tiles per 64-element K step
   const uint32_t acc_stride = ATM ? 128u : 256u;
   const int stage_bytes = a_all + (SPLIT ? 2 * b_bytes : b_bytes);
   const int STAGES = p.stages;
@@ -688,9 +479,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (PAIR && SPLIT) {
               // A feeds this CTA's own splitter warps (local barrier); the two weight-plane halves are operands of the leader's
               // MMAs: their bytes are counted by the LEADER's xf barrier, next to the 8 splitter-warp arrivals of both CTAs
-              mbar_expect_tx(&full_bar[stage], (uint32_t)A_BYTES);
+              mbar_expect_tx(&full_bar[stage], (uint32_t)(SF16 ? 2 * A_BYTES : A_BYTES));
               if (kb < p.c0_blocks) tma_load_4d(a_dst, &tmA0, &full_bar[stage], kb * p.bk, x0, y0, n);
               else tma_load_4d(a_dst, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * p.bk, x0, y0, n);
+              if (SF16) {   // channels [32, 64) of the K block (beyond the tensor: zero fill)
+                if (kb < p.c0_blocks) tma_load_4d(a_dst + A_BYTES, &tmA0, &full_bar[stage], kb * p.bk + 32, x0, y0, n);
+                else tma_load_4d(a_dst + A_BYTES, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * p.bk + 32, x0, y0, n);
+              }
               const uint32_t lead_xf = mapa_shared(smem_u32(&xf_bar[stage]), 0u);
               mbar_expect_tx_cluster(lead_xf, (uint32_t)(2 * b_bytes));
               const int row0 = nt * p.BN + (int)cta_rank * (p.BN / 2);
@@ -699,9 +494,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
               continue;
             }
-            mbar_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + (SPLIT ? 2 * b_bytes : b_bytes)));
+            mbar_expect_tx(&full_bar[stage], (uint32_t)((SF16 ? 2 * A_BYTES : A_BYTES) + (SPLIT ? 2 * b_bytes : b_bytes)));
             if (kb < p.c0_blocks) tma_load_4d(a_dst, &tmA0, &full_bar[stage], kb * p.bk, x0, y0, n);
             else tma_load_4d(a_dst, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * p.bk, x0, y0, n);
+            if (SF16) {
+              if (kb < p.c0_blocks) tma_load_4d(a_dst + A_BYTES, &tmA0, &full_bar[stage], kb * p.bk + 32, x0, y0, n);
+              else tma_load_4d(a_dst + A_BYTES, &tmA1, &full_bar[stage], (kb - p.c0_blocks) * p.bk + 32, x0, y0, n);
+            }
             if (CL == 1) {
               tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * p.bk, nt * p.BN, tap);
               if (SPLIT) tma_load_3d(b_dst + b_bytes, &tmB, &full_bar[stage], kb * p.bk, nt * p.BN, tap + p.taps);
@@ -721,7 +520,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ===================================================== MMA issuer
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3, M>>4
     // (kind::f16: a/b format 0 = F16, K = 16 per instruction = the same 32 bytes of every smem row)
-    const uint32_t idesc = (1u << 4) | ((p.f16_in ? 0u : 2u) << 7) | ((p.f16_in ? 0u : 2u) << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+    const uint32_t fmt = (p.f16_in || (SPLIT && p.split_f16)) ? 0u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                            ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -751,14 +551,26 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint64_t ko = (uint64_t)(k * 2);
             if (ATM && PAIR) {
               const uint32_t ahi_t = tmem_base + 256u + (uint32_t)(stage * 64 + k * 8), alo_t = ahi_t + 32u;
-              mma_tf32_ts_2sm(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
-              mma_tf32_ts_2sm(d_tmem, alo_t, bdesc + ko, idesc, 1u);
-              mma_tf32_ts_2sm(d_tmem, ahi_t, bdesc + ko, idesc, 1u);
+              if (SF16) {   // 8 TMEM columns = 16 packed halves = one K = 16 instruction
+                mma_f16_ts_2sm(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
+                mma_f16_ts_2sm(d_tmem, alo_t, bdesc + ko, idesc, 1u);
+                mma_f16_ts_2sm(d_tmem, ahi_t, bdesc + ko, idesc, 1u);
+              } else {
+                mma_tf32_ts_2sm(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
+                mma_tf32_ts_2sm(d_tmem, alo_t, bdesc + ko, idesc, 1u);
+                mma_tf32_ts_2sm(d_tmem, ahi_t, bdesc + ko, idesc, 1u);
+              }
             } else if (ATM) {
               const uint32_t ahi_t = tmem_base + 256u + (uint32_t)(stage * 64 + k * 8), alo_t = ahi_t + 32u;
-              mma_tf32_ts(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);     // A_hi * B_lo
-              mma_tf32_ts(d_tmem, alo_t, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
-              mma_tf32_ts(d_tmem, ahi_t, bdesc + ko, idesc, 1u);                                 // A_hi * B_hi
+              if (SF16) {
+                mma_f16_ts(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
+                mma_f16_ts(d_tmem, alo_t, bdesc + ko, idesc, 1u);
+                mma_f16_ts(d_tmem, ahi_t, bdesc + ko, idesc, 1u);
+              } else {
+                mma_tf32_ts(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);     // A_hi * B_lo
+                mma_tf32_ts(d_tmem, alo_t, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
+                mma_tf32_ts(d_tmem, ahi_t, bdesc + ko, idesc, 1u);                                 // A_hi * B_hi
+              }
             } else if (SPLIT) {   // small terms first
               mma_tf32(d_tmem, adesc + ko, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);   // A_hi * B_lo
               mma_tf32(d_tmem, alo + ko, bdesc + ko, idesc, 1u);                                 // A_lo * B_hi
@@ -890,7 +702,27 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait_t(&full_bar[stage], phase, SPIN, ST_A);
           const uint8_t* arow = smem + stage * stage_bytes + r * 128;
-          if (!(p.dbg & 1)) {
+          if (SF16 && !(p.dbg & 1)) {
+            // fp16 hi / lo pairs: a = hi + lo with hi = rn_f16(a), lo = rn_f16(a - hi) (both exact-product operands of kind::f16
+            // MMAs: 11 x 11 significand bits fit the fp32 accumulator); two K elements per 32-bit TMEM column.
+            // K elements [32 s, 32 s + 32) of the block come from sub-tile s -> hi columns [16 s, 16 s + 16), lo columns 32 + the same.
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {   // 16-byte chunk c of row r sits at chunk ^ (r & 7)  (SWIZZLE_128B)
+                const float4 v = *reinterpret_cast<const float4*>(arow + sub * A_BYTES + ((c ^ (r & 7)) << 4));
+                const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+                hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h0); hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                lo[2 * c] = *reinterpret_cast<const uint32_t*>(&l0); lo[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+              }
+              tmem_st16(trow + (uint32_t)(stage * 64 + sub * 16), hi);
+              tmem_st16(trow + (uint32_t)(stage * 64 + 32 + sub * 16), lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          } else if (!(p.dbg & 1)) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               uint32_t hi[16], lo[16];
@@ -974,8 +806,8 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
-                   bool f16 = false, int pixel_stride = 1) {
+void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+            bool f16, int pixel_stride) {
   cuuint32_t estr[5] = {1, (cuuint32_t)pixel_stride, (cuuint32_t)pixel_stride, 1, 1};   // (activation maps: dims 1, 2 = x, y)
   CUresult r = encode_fn()(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1048,6 +880,16 @@ static int tc_split_epi8() {   // GIMMVFI_TC_SPLIT_EPI8: 0 = 4 drain warps in th
   return v;
 }
 
+static int tc_split_f16() {   // GIMMVFI_TC_SPLIT_F16=0: keep the 3xTF32 form of the split kernel
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_F16"); v = s ? atoi(s) : 1; }
+  return v;
+}
+static int tc_seg_f16() {   // K steps (of 64 elements) per TMEM accumulation segment of the 3xF16 form
+  static int seg = -1;
+  if (seg < 0) { const char* s = getenv("GIMMVFI_TC_SEG_F16"); seg = s ? atoi(s) : 1; if (seg < 1) seg = 1; }
+  return seg;
+}
 static int tc_seg() {
   static int seg = -1;
   if (seg < 0) { const char* s = getenv("GIMMVFI_TC_SEG"); seg = s ? atoi(s) : 2; if (seg < 1) seg = 1; }
@@ -1065,6 +907,9 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
     const int c16 = (w.cout + 15) & ~15;
     tiles_n = (c16 + 127) / 128;
     BN = (((c16 + tiles_n - 1) / tiles_n) + 15) & ~15;   // weight rows beyond cout_pad are TMA zero-fill
+    // several N tiles: a tile's last 32-column epilogue chunk must not reach into the next tile's channels (it would store columns
+    // the MMA never wrote) -> tile width = whole chunks
+    if (tiles_n > 1) BN = (BN + 31) & ~31;
   } else {
     tc_tile_n(w.cout, &BN, &tiles_n);
     if (BN * tiles_n != w.cout_pad) throw std::runtime_error("conv_tc: weight padding does not match the N tiling");
@@ -1073,8 +918,16 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   const int CL = (tc_cluster() == 2 && pix_tiles_host >= 2 * cx.sm_count && BN % 16 == 0) ? 2 : 1;
   const int taps = w.kh * w.kw;
   const bool f16 = in0.f16 != 0;
-  const int bk = f16 ? 2 * BK : BK, cin_pad = f16 ? w.cin_pad_h : w.cin_pad;
-  if (f16) {
+  // 3xF16: the split kernel on kind::f16 with fp16 hi / lo operand pairs (two 32-channel activation boxes per 64-element K step);
+  // needs the TMEM-resident A operand, pre-split weights, and a first segment of whole K blocks
+  const bool sf16 = split && tc_split_f16() && tc_atmem() && w.w_tc_s != nullptr && (!in1.p || in0.c % 64 == 0);
+  const int bk = (f16 || sf16) ? 2 * BK : BK, cin_pad = f16 ? w.cin_pad_h : (sf16 ? w.cin_pad_s : w.cin_pad);
+  if (sf16) {
+    cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)(taps * 2)};
+    cuuint64_t str[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * w.cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(BN / CL), 1};
+    encode(&mB, w.w_tc_s, 3, dims, str, box, true);
+  } else if (f16) {
     cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)taps};
     cuuint64_t str[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * w.cout_pad * 2};
     cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(BN / CL), 1};
@@ -1087,14 +940,14 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   }
   Params p;
   p.taps = taps; p.kw = w.kw; p.ph = g.ph; p.pw = g.pw; p.stride = g.stride;
-  p.f16_in = f16 ? 1 : 0; p.bk = bk;
+  p.f16_in = f16 ? 1 : 0; p.bk = bk; p.split_f16 = sf16 ? 1 : 0;
   p.c0_blocks = in1.p ? in0.c / bk : (in0.c + bk - 1) / bk;
   p.kblocks = cin_pad / bk;
   p.tiles_x = (out.w + TILE_W - 1) / TILE_W; p.tiles_y = (out.h + TILE_H - 1) / TILE_H; p.n_img = out.n; p.tiles_n = tiles_n;
   p.H = out.h; p.W = out.w; p.BN = BN; p.cout = w.cout;
   p.round_out = (split || out.f16) ? 0 : 1;   // (a half store already rounds to 10 mantissa bits)
-  p.out_scale = 1.f;
-  p.seg = tc_seg();
+  p.out_scale = sf16 ? 1.f / w.w_scale : 1.f;
+  p.seg = sf16 ? tc_seg_f16() : tc_seg();
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = split ? tc_atmem() : 0; p.stall = tc_stall_buf();
@@ -1105,7 +958,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   const bool sew8 = split && tc_epi8() && tc_split_epi8() && (tc_split_epi8() == 2 || !(BN == 128 && taps * (w.cin_pad / 32) >= 48));
   // CTA pairs: N/2 rows per CTA must keep the 8-row swizzle atom (and N % 16); the 3xTF32 kernel pairs only in its TMEM-A, 8-drain-warp form
   const bool pair = CL == 2 && BN % 32 == 0 && (split ? (tc_pair() >= 2 && p.atmem && sew8) : (tc_pair() != 0));
-  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * (pair ? BN / 2 : BN) * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4);
+  const int stage_bytes = split ? (((p.atmem && !sf16) ? 1 : 2) * A_BYTES + 2 * (pair ? BN / 2 : BN) * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4);
   static int ew8_wide = -1;   // GIMMVFI_TC_EPI8_WIDE=0: 4 epilogue warps for N > 128 tiles of CTA pairs
   if (ew8_wide < 0) { const char* q = getenv("GIMMVFI_TC_EPI8_WIDE"); ew8_wide = q ? atoi(q) : 1; }
   // K-poor plain layers are epilogue bound: 8 epilogue warps.  CTA pairs halve the per-stage smem footprint, which leaves room
@@ -1124,7 +977,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   cx.launches++;
   if (cx.prof) {
     char nm[128];
-    snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? "3xtf32" : (f16 ? "f16" : "tf32"), w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
+    snprintf(nm, sizeof nm, "conv2d_tc_%s k%dx%d c%d>%d @%dx%dx%d", split ? (sf16 ? "3xf16" : "3xtf32") : (f16 ? "f16" : "tf32"), w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
   }
   if (split && sew8) {
@@ -1173,7 +1026,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   }
   Params p;
   p.taps = 1; p.kw = 1; p.ph = 0; p.pw = 0; p.stride = 1;
-  p.kblocks = C / 32; p.c0_blocks = p.kblocks; p.f16_in = 0; p.bk = BK;
+  p.kblocks = C / 32; p.c0_blocks = p.kblocks; p.f16_in = 0; p.bk = BK; p.split_f16 = 0;
   p.tiles_x = (fa.w + TILE_W - 1) / TILE_W; p.tiles_y = (fa.h + TILE_H - 1) / TILE_H; p.n_img = 1; p.tiles_n = tiles_n;
   p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale; p.seg = tc_seg();
   static int spin = -1;

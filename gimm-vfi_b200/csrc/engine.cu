@@ -109,6 +109,8 @@ std::string Engine::profile_json(gvStream_t stream) {
 // Engine: weights
 // ---------------------------------------------------------------------------
 Engine::Engine(int device) : device_(device) {
+  if (const char* kn = getenv("GIMMVFI_PRECISE")) precise_ = atoi(kn);   // builder experiments: override the 3xTF32 stage mask
+  if (const char* kn = getenv("GIMMVFI_HYPO_FAST")) hypo_fast_ = atoi(kn) != 0;
 #ifndef GV_HOSTSIM
   int count = 0;
   cuda_ok(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
@@ -221,6 +223,29 @@ void Engine::pack_tc(ConvW& c, const std::vector<float>& pw) {
         t[o] = hi; t[plane + o] = tf32_rn(w - hi);
       }
   c.w_tc = upload(t); c.cout_pad = cout_pad; c.cin_pad = cin_pad; c.has_lo = true;
+  // fp16 hi / lo planes of w * 2^e for the 3xF16 split: 64-element K blocks (two 32-channel fp32 activation boxes per K step)
+  {
+    float mx = 0.f;
+    for (float v : pw) mx = std::max(mx, std::fabs(v));
+    int e = 0;
+    if (mx > 0.f) { int ex; std::frexp(mx, &ex); e = 14 - ex; }   // mx * 2^e in [2^13, 2^14)
+    if (e > 24) e = 24;
+    if (e < -24) e = -24;
+    const float sc = std::ldexp(1.f, e);
+    const int cps = (c.cin + 63) & ~63;
+    const size_t pl = (size_t)taps * cout_pad * cps;
+    std::vector<float> hs((2 * pl + 1) / 2, 0.f);
+    uint16_t* h = reinterpret_cast<uint16_t*>(hs.data());
+    for (int tp = 0; tp < taps; ++tp)
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int co = 0; co < c.cout; ++co) {
+          const float w = pw[((size_t)tp * c.cin + ci) * c.cout_ld + co] * sc;
+          const uint16_t hi = gv_f32_to_f16(w), lo = gv_f32_to_f16(w - gv_f16_to_f32(hi));
+          const size_t o = ((size_t)tp * cout_pad + co) * cps + ci;
+          h[o] = hi; h[pl + o] = lo;
+        }
+    c.w_tc_s = upload(hs); c.cin_pad_s = cps; c.w_scale = sc;
+  }
 }
 
 // [tap][cin][cout_ld] fp32 -> [tap][cout_pad][cin_pad_h] fp16 (K-major rows of 64-element / 128-byte K blocks): the
@@ -386,6 +411,75 @@ void Engine::finalize_gimm_part() {
     pack_tc(c, pw);
     if (l >= 1) pack_tc_f16(c, pw);   // precision mode 4: the sin() activations between the layers (|x| <= 1) are stored in half
     conv_[key] = c;
+  }
+  // --- the same five matrices packed for the fused kernel (hyponet.cu): pre-swizzled K-major tiles, fp32 affine rows for (t, y, x)
+  {
+    std::vector<float> blobf((hypo::BLOB + 3) / 4, 0.f);
+    uint8_t* blob = reinterpret_cast<uint8_t*>(blobf.data());
+    auto norm_col = [&](const HostTensor& wb, int fin, int fout, int co) {
+      double nrm = 0.0;
+      for (int ci = 0; ci < fin; ++ci) { double v = wb.data[(size_t)ci * fout + co]; nrm += v * v; }
+      return std::max((float)std::sqrt(nrm), 1e-12f);
+    };
+    const HostTensor& w0 = raw("hyponet.params_dict.linear_wb0");
+    if (w0.shape[0] != 36 || w0.shape[1] != 128) throw std::runtime_error("hyponet: expected linear_wb0 of shape (36, 128)");
+    float* aff = reinterpret_cast<float*>(blob + hypo::AFF);
+    for (int n = 0; n < 128; ++n) {
+      const float d = norm_col(w0, 35, 128, n);
+      for (int k = 0; k < 32; ++k) { const float v = tf32_rn(w0.data[(size_t)k * 128 + n] / d); std::memcpy(blob + hypo::W0 + hypo::swz(n, k * 4), &v, 4); }
+      for (int j = 0; j < 3; ++j) aff[j * 128 + n] = w0.data[(size_t)(32 + j) * 128 + n] / d;
+      aff[3 * 128 + n] = w0.data[(size_t)35 * 128 + n];
+    }
+    for (int l = 1; l <= 4; ++l) {
+      const HostTensor& wb = raw("hyponet.params_dict.linear_wb" + std::to_string(l));
+      const int fout = (int)wb.shape[1];
+      if (wb.shape[0] != 129 || fout != (l < 4 ? 128 : 2)) throw std::runtime_error("hyponet: unexpected hidden / output layer shape");
+      const int rows = l < 4 ? 128 : 16, base = l < 4 ? hypo::W1 + (l - 1) * 32768 : hypo::W4, kb_bytes = rows * 128;
+      float* bias = reinterpret_cast<float*>(blob + (l < 4 ? hypo::B1 + (l - 1) * 512 : hypo::B4));
+      for (int n = 0; n < fout; ++n) {
+        const float d = norm_col(wb, 128, fout, n);
+        for (int k = 0; k < 128; ++k) {
+          const uint16_t h = gv_f32_to_f16(wb.data[(size_t)k * fout + n] / d);
+          std::memcpy(blob + base + (k / 64) * kb_bytes + hypo::swz(n, (k % 64) * 2), &h, 2);
+        }
+        bias[n] = wb.data[(size_t)128 * fout + n] + (l == 4 ? 0.5f : 0.f);
+      }
+    }
+    hypo_blob_ = upload(blobf);
+    // fp32-class variant (hyponet_fused3): scaled fp16 hi / lo planes of layers 1-3, fp32 rows of layers 0 and 4
+    std::vector<float> b3f((hypo3::BLOB + 3) / 4, 0.f);
+    uint8_t* b3 = reinterpret_cast<uint8_t*>(b3f.data());
+    float* w0a = reinterpret_cast<float*>(b3 + hypo3::W0A);
+    for (int n = 0; n < 128; ++n) {
+      const float d = norm_col(w0, 35, 128, n);
+      for (int k = 0; k < 35; ++k) w0a[k * 128 + n] = w0.data[(size_t)k * 128 + n] / d;
+      w0a[35 * 128 + n] = w0.data[(size_t)35 * 128 + n];
+    }
+    for (int l = 1; l <= 3; ++l) {
+      const HostTensor& wb = raw("hyponet.params_dict.linear_wb" + std::to_string(l));
+      float* bias = reinterpret_cast<float*>(b3 + hypo3::B13 + (l - 1) * 512);
+      for (int n = 0; n < 128; ++n) {
+        const float d = norm_col(wb, 128, 128, n);
+        for (int k = 0; k < 128; ++k) {
+          const float v = wb.data[(size_t)k * 128 + n] / d * hypo3::W_SCALE;
+          const uint16_t hi = gv_f32_to_f16(v), lo = gv_f32_to_f16(v - gv_f16_to_f32(hi));
+          std::memcpy(b3 + hypo3::W13 + (((l - 1) * 2 + 0) * 2 + k / 64) * 16384 + hypo::swz(n, (k % 64) * 2), &hi, 2);
+          std::memcpy(b3 + hypo3::W13 + (((l - 1) * 2 + 1) * 2 + k / 64) * 16384 + hypo::swz(n, (k % 64) * 2), &lo, 2);
+        }
+        bias[n] = wb.data[(size_t)128 * 128 + n];
+      }
+    }
+    {
+      const HostTensor& wb = raw("hyponet.params_dict.linear_wb4");
+      float* w4 = reinterpret_cast<float*>(b3 + hypo3::W4);
+      float* b4 = reinterpret_cast<float*>(b3 + hypo3::B4);
+      for (int n = 0; n < 2; ++n) {
+        const float d = norm_col(wb, 128, 2, n);
+        for (int k = 0; k < 128; ++k) w4[k * 2 + n] = wb.data[(size_t)k * 2 + n] / d;
+        b4[n] = wb.data[(size_t)128 * 2 + n] + 0.5f;
+      }
+    }
+    hypo_blob3_ = upload(b3f);
   }
   g9_ = vec("g_filter"); alpha_fe_ = vec("alpha_fe"); alpha_v_ = vec("alpha_v");
 }
@@ -654,6 +748,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   check_problem(P);
   Net N{*this, cx};
   Arena& A = cx.arena;
+  const int knobs = precise_;   // which post-RAFT stages run in 3xTF32 (fp32-class) arithmetic: see set_precise()
   const int B = P.B, Hf = P.Hf, Wf = P.Wf, H = P.H(), W = P.W(), T = P.T;
   const int h = H / 8, w = W / 8, H4 = H / 4, W4 = W / 4;
   const bool ds = P.ds > 0.f;
@@ -841,7 +936,9 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       nhwc_to_nchw(cx, nf.batch(j * B, B), io.nflow + (int64_t)j * H * W, (int64_t)4 * H * W, (int64_t)2 * H * W, 1.f, 0.f, 0);
   TV wts = A.tensor(2 * B, H, W, 1);
   TV X64 = A.tensor(B, H, W, 64);   // [lat0 | lat1 | splat0 | splat1]
+  cx.tc_split = (knobs & 1) != 0;
   gimm_encode(N, nf, f01, f10, wts, X64);
+  cx.tc_split = false;
 
   // ------------------------------------------------------------ per-timestep: GIMM decode + frame synthesis
   TV grid_flow = A.tensor(B, h, w, 4);   // flow_4_lr = cat(fl0, fl1)
@@ -850,7 +947,9 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     A.release(t_mark);
     const float* tdev = io.t + (int64_t)ti * B;
     TV ninr = A.tensor(B, H, W, 2);
+    cx.tc_split = (knobs & 1) != 0;
     gimm_decode(N, X64, f01, f10, wts, tdev, io.coords + (int64_t)ti * B * P.Hc * P.Wc * 3, ninr, ti == 0);
+    cx.tc_split = (knobs & 4) != 0;   // init decoder + update blocks
     if (io.ninrflow) nhwc_to_nchw(cx, ninr, io.ninrflow + (int64_t)ti * B * 2 * H * W, (int64_t)2 * H * W, (int64_t)H * W, 1.f, 0.f, 0);
     TV flow_t = A.tensor(B, H, W, 2);
     unnormalize_flow(cx, ninr, scaler, flow_t);
@@ -912,6 +1011,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
     if (io.flowt1_4) nhwc_to_nchw(cx, fl4.slice(2, 2), io.flowt1_4 + (int64_t)ti * B * 2 * H4 * W4, (int64_t)2 * H4 * W4, (int64_t)H4 * W4, 1.f, 0.f, 0);
 
     // NewMultiFlowDecoder (fi_components.py:307-340)
+    cx.tc_split = (knobs & 8) != 0;
     TV F0 = A.tensor(B, H, W, 6, 8), F1 = A.tensor(B, H, W, 6, 8), Mk = A.tensor(B, H, W, 3, 4), Rs = A.tensor(B, H, W, 9, 12);
     {
       const size_t mk = A.mark();
@@ -934,7 +1034,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       backwarp(cx, s1, fl1, fin1.slice(270, 3));
       // precision mode 3: the 256-channel residual trunk (9 of the 10 heaviest launches) is stored in fp16 and runs on the
       // kind::f16 tensor-core path (same 10-bit mantissa as TF32, half the bytes per operand, twice the MMA rate)
-      TV x1 = (cx.tc && tc_mode_ >= 3) ? A.tensor_h(B, H, W, 256) : A.tensor(B, H, W, 256);
+      TV x1 = (cx.tc && tc_mode_ >= 3 && !(knobs & 8)) ? A.tensor_h(B, H, W, 256) : A.tensor(B, H, W, 256);
       N.convrelu("amt_final_decoder.convblock.0", fin1, x1);
       for (int k = 1; k <= 3; ++k) resblock(N, "amt_final_decoder.convblock." + std::to_string(k), x1, 256, 64);
       TV o24 = A.tensor(B, H, W, 24);
@@ -942,6 +1042,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       final_heads(cx, o24, fl0, fl1, mk1, F0, F1, Mk, Rs);
       A.release(mk);
     }
+    cx.tc_split = (knobs & 16) != 0;   // comb block
     TV F0f = F0, F1f = F1, Mkf = Mk, Rsf = Rs;
     if (ds) {  // gimmvfi_r.py:294-303
       F0f = A.tensor(B, Hf, Wf, 6, 8); F1f = A.tensor(B, Hf, Wf, 6, 8); Mkf = A.tensor(B, Hf, Wf, 3, 4); Rsf = A.tensor(B, Hf, Wf, 9, 12);
@@ -960,6 +1061,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       N.conv7x("amt_comb_block.2", c18, c3);
       combine_output(cx, mean3, c3, io.imgt_pred + (int64_t)ti * B * 3 * Hf * Wf);
     }
+    cx.tc_split = false;
   }
 }
 
@@ -1009,7 +1111,11 @@ void Engine::gimm_decode(Net& N, const TV& X64, const TV& f01, const TV& f10, co
   softsplat_normalize(cx, acc.batch(0, B), X64.slice(32, 16));
   softsplat_normalize(cx, acc.batch(B, B), X64.slice(48, 16));
   if (tap_it) tap("gimm.splat0", X64.slice(32, 16));
-  TV hin = A.tensor(B, H, W, 35, 36);  // HypoNet input [latent32 | t,y,x]
+  // HypoNet (hyponet.py:71-146).  Tensor-core modes: ONE fused kernel (hyponet.cu) that takes the refined latent and the caller's
+  // coordinate tensor directly; fp32 mode: five 1x1 convolutions on a packed [latent32 | t,y,x] input.
+  const bool fused = cx.tc && hypo_blob_ != nullptr && !(precise_ & 2);
+  const bool split_saved = cx.tc_split;
+  TV hin = fused ? A.tensor(B, H, W, 32) : A.tensor(B, H, W, 35, 36);
   {
     const size_t mk = A.mark();
     const bool hs = half_chains(cx);
@@ -1023,16 +1129,23 @@ void Engine::gimm_decode(Net& N, const TV& X64, const TV& f01, const TV& f10, co
     A.release(mk);
   }
   if (tap_it) tap("gimm.latent", hin.slice(0, 32));
-  hypo_pack_input(cx, coords_t, hin.slice(32, 3));
-  {
+  if (fused) {
+    // fp32-class by default: the flow is (2 o - 1) * max|flow|, so operand rounding at 2^-11 becomes ~1e-2 px at 40 px motion and
+    // moves real frames by > 1e-3 (tests/test_bench_parity_gpu.py, demo frames); hypo_fast_ selects the TF32 / half-operand kernel
+    if (hypo_fast_) hyponet_fused(cx, hin, coords_t, hypo_blob_, ninr);
+    else hyponet_fused3(cx, hin, coords_t, hypo_blob3_, ninr);
+  } else {
+    cx.tc_split = (precise_ & 2) != 0;
+    hypo_pack_input(cx, coords_t, hin.slice(32, 3));
     const size_t mk = A.mark();
-    TV a = half_chains(cx) ? A.tensor_h(B, H, W, 128) : A.tensor(B, H, W, 128), b = A.tensor_like(a, 128);
+    TV a = A.tensor(B, H, W, 128), b = A.tensor(B, H, W, 128);
     N.conv("hyponet.params_dict.linear_wb0", hin, a, ACT_SIN);
     N.conv("hyponet.params_dict.linear_wb1", a, b, ACT_SIN);
     N.conv("hyponet.params_dict.linear_wb2", b, a, ACT_SIN);
     N.conv("hyponet.params_dict.linear_wb3", a, b, ACT_SIN);
     N.conv("hyponet.params_dict.linear_wb4", b, ninr);
     A.release(mk);
+    cx.tc_split = split_saved;
   }
   if (!debug_) A.release(mk0);   // (debug taps keep pointing into this region)
 }

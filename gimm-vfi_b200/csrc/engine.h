@@ -84,7 +84,8 @@ class Engine {
   std::string last_error;
   int raft_iters = 20;  // GIMMVFI_R hard-codes iters=20 (gimmvfi_r.py:126-132)
   int device() const { return device_; }
-  int64_t weights_version() const { return weights_version_; }   // bumped by every finalize_weights*: callers key caches on it
+  int64_t weights_version() const { return weights_version_; }
+  const void* hyponet_blob(bool fp32_class) const { return fp32_class ? hypo_blob3_ : hypo_blob_; }   // bumped by every finalize_weights*: callers key caches on it
   bool finalized() const { return finalized_; }
 
  private:
@@ -105,6 +106,7 @@ class Engine {
   bool finalized_ = false, debug_ = false, profile_ = false, gimm_only_ = false;
   int tc_mode_ = 0;
   int64_t weights_version_ = 0;
+  int precise_ = 0;   // bit mask of post-RAFT stages in 3xTF32: 1 GIMM encoders / latent refiner, 2 HypoNet, 4 init decoder + update blocks, 8 final decoder, 16 combine
   float* fc_ = nullptr; size_t fc_bytes_ = 0; bool fc_load_ = false, fc_store_ = false;
   // what the cache holds (host-side bookkeeping of the last store): a load with a different buffer / problem is refused
   // (one record per cache buffer, so several video streams can share an engine; cleared when the weights change)
@@ -122,6 +124,9 @@ class Engine {
   std::map<std::string, const float*> vec_;
   std::vector<void*> dev_allocs_;
   std::map<std::string, TV> taps_;
+  const void* hypo_blob_ = nullptr;   // packed parameters of the fused HypoNet kernel (common.h hypo::)
+  const void* hypo_blob3_ = nullptr;  // ... of its fp32-class variant (common.h hypo3::), the default
+  bool hypo_fast_ = false;            // true: TF32 / half-operand HypoNet kernel (0.56 ms vs the fp32-class one; fails the 1e-3 bound on real frames)
   const float* g9_ = nullptr; const float* alpha_fe_ = nullptr; const float* alpha_v_ = nullptr;
 
   // op helpers used by run()

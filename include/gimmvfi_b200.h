@@ -139,11 +139,14 @@ int gimmvfi_op_conv2d(const gimmvfi_view* in0, const gimmvfi_view* in1_or_null, 
                       const float* slope, const gimmvfi_view* residual_or_null, const gimmvfi_view* out, void* stream);
 /* tcgen05/TMA implicit-GEMM conv (stride 1, "same" zero padding).  w_tc packed [2][kh*kw][cout_pad][cin_pad32]
  * (plane 0 = TF32(w), plane 1 = TF32(w - plane 0); cout_pad = N tiling of cout, see tc_tile_n); bias padded to cout_pad.
- * y = gru( act2(residual + act1(conv + bias)) * mul );  split != 0 -> 3xTF32 (fp32-class accuracy, unrounded output) */
+ * y = gru( act2(residual + act1(conv + bias)) * mul );  split != 0 -> three-term operand split (fp32-class accuracy, unrounded
+ * output): 3xTF32, or — when w_tc_s is given — 3xF16: w_tc_s = half [2][kh*kw][cout_pad][cin_pad64] holding the fp16 hi / lo planes of
+ * w * w_scale (w_scale a power of two), activations split on the fly, kind::f16 MMAs at twice the TF32 rate */
 int gimmvfi_op_conv2d_tc(const gimmvfi_view* in0, const gimmvfi_view* in1_or_null, const float* w_tc, const float* bias, int cin,
                          int cout, int kh, int kw, int act1, const float* slope1, const gimmvfi_view* residual_or_null, int act2,
                          const float* slope2, const gimmvfi_view* mul_or_null, const gimmvfi_view* gru_z_or_null,
-                         const gimmvfi_view* gru_h_or_null, int split, const gimmvfi_view* out, void* stream);
+                         const gimmvfi_view* gru_h_or_null, int split, const gimmvfi_view* out, const void* w_tc_s_or_null, float w_scale,
+                         void* stream);
 /* the same kernel at stride 1 or 2 with "same"-style padding k/2 (RAFT encoder down-sampling convs, raft/extractor.py:42-48,140):
  * out is (n, (h + 2*(kh/2) - kh)/stride + 1, ...); TMA element strides pick every stride-th input pixel */
 int gimmvfi_op_conv2d_tc_strided(const gimmvfi_view* in0, const float* w_tc, const float* bias, int cin, int cout, int kh, int kw,
@@ -157,6 +160,11 @@ int gimmvfi_op_conv2d_tc_f16(const gimmvfi_view* in0, const gimmvfi_view* in1_or
                              const gimmvfi_view* residual_or_null, int act2, const float* slope2, int half_mask,
                              const gimmvfi_view* out, void* stream);
 /* nn.InstanceNorm2d + optional relu: raft/extractor.py:133-134; scratch >= gimmvfi_instnorm_scratch_floats */
+/* HypoNet.forward (modules/hyponet.py:71-146) as ONE fused tcgen05 kernel with the engine's loaded weights: latent (n,h,w,32),
+ * coords n*h*w x (t,y,x) as the caller's coordinate tensor holds them -> out (n,h,w,2) = normalised flow (output_bias included).
+ * fp32_class != 0: the default kernel of the forward pass (fp16 hi/lo operand pairs, fp32-class result); 0: TF32 / half operands */
+int gimmvfi_op_hyponet(gimmvfi_engine* e, const gimmvfi_view* latent, const float* coords, const gimmvfi_view* out, int fp32_class,
+                       void* cuda_stream);
 int64_t gimmvfi_instnorm_scratch_floats(int n, int c);
 int gimmvfi_op_instnorm(const gimmvfi_view* x, int relu, float* scratch, const gimmvfi_view* out, void* stream);
 /* convex x8 upsampling raft/raft.py:86-97: flow (n,h,w,2), mask (n,h,w,576), out (n,8h,8w,2) */

@@ -154,11 +154,29 @@ def pack_weight_tc(w):  # (cout,cin,kh,kw) -> [2][kh*kw][cout_pad][cin_pad32]: T
     return p.contiguous()
 
 
+def pack_weight_tc_split_f16(w):
+    """(cout,cin,kh,kw) -> (half [2][kh*kw][cout_pad][cin_pad64], scale): fp16 hi / lo planes of w * 2^e, max|w| * 2^e in [2^13, 2^14)"""
+    import math
+
+    cout, cin, kh, kw = w.shape
+    cp, kp = tc_cout_pad(cout), (cin + 63) // 64 * 64
+    mx = w.abs().max().item()
+    e = 0 if mx == 0 else max(-24, min(24, 14 - math.frexp(mx)[1]))
+    ws = (w * (2.0 ** e)).permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    p = torch.zeros(2, kh * kw, cp, kp, device=w.device, dtype=torch.float16)
+    p[0, :, :cout, :cin] = hi
+    p[1, :, :cout, :cin] = lo
+    return p.contiguous(), float(2.0 ** e)
+
+
 def conv2d_tc(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2=None, x1_nhwc=None, in_view=None, lib=None,
-              mul=None, gru_z=None, gru_h=None, split=False, out=None):
+              mul=None, gru_z=None, gru_h=None, split=False, out=None, split_f16=False):
     lib = lib or default_lib()
     cout, cin, kh, kw = w.shape
     pw = pack_weight_tc(w)
+    pws, wsc = pack_weight_tc_split_f16(w) if (split and split_f16) else (None, 1.0)
     bb = torch.zeros((tc_cout_pad(cout) + 31) // 32 * 32 + 128, device=w.device)
     bb[:cout] = b
     n, h, wd, _ = x_nhwc.shape
@@ -168,7 +186,7 @@ def conv2d_tc(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2=N
     V = lambda t: C.byref(view_of(t)) if t is not None else None
     P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
     rc = lib.dll.gimmvfi_op_conv2d_tc(C.byref(v0), V(x1_nhwc), P(pw), P(bb), cin, cout, kh, kw, act1, P(slope1), V(residual), act2, P(slope2),
-                                      V(mul), V(gru_z), V(gru_h), int(split), C.byref(view_of(out)), _stream(out))
+                                      V(mul), V(gru_z), V(gru_h), int(split), C.byref(view_of(out)), P(pws), wsc, _stream(out))
     lib.check(rc)
     return out
 

@@ -90,5 +90,98 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   }
 }
 
+
+// hyponet.cu's arithmetic: TF32 layer 0 on the latent + exact fp32 affine term for (t, y, x); half-precision activations and
+// weights in the hidden layers; fp32 accumulation; fp32 output.  (The device kernel uses MUFU sin: |error| ~1e-6, not emulated.)
+bool hyponet_fused_supported(const TV& lat, const TV& out) {
+  return lat.c == 32 && !lat.f16 && !out.f16 && out.c == 2 && out.n == lat.n && out.h == lat.h && out.w == lat.w;
+}
+void hyponet_fused(Ctx& cx, const TV& lat, const float* coords, const void* blob_v, const TV& out) {
+  if (cx.dry) return;
+  cx.launches++;
+  const uint8_t* blob = static_cast<const uint8_t*>(blob_v);
+  const float* aff = reinterpret_cast<const float*>(blob + hypo::AFF);
+  const int64_t P = lat.pixels();
+#pragma omp parallel for schedule(static)
+  for (int64_t pix = 0; pix < P; ++pix) {
+    const int x = (int)(pix % lat.w); int64_t r = pix / lat.w; const int y = (int)(r % lat.h); const int n = (int)(r / lat.h);
+    const float* lp = lat.p + lat.off(n, y, x);
+    const float* c = coords + pix * 3;
+    float a[128], b[128];
+    for (int o = 0; o < 128; ++o) {
+      float acc = 0.f;
+      for (int k = 0; k < 32; ++k) { float w; std::memcpy(&w, blob + hypo::W0 + hypo::swz(o, k * 4), 4); acc += tf32_trunc(lp[k]) * w; }
+      const float z = std::fmaf(c[0], aff[o], std::fmaf(c[1], aff[128 + o], std::fmaf(c[2], aff[256 + o], acc + aff[384 + o])));
+      a[o] = gv_f16_to_f32(gv_f32_to_f16(sinf(z)));
+    }
+    for (int l = 1; l <= 3; ++l) {
+      const float* bias = reinterpret_cast<const float*>(blob + hypo::B1 + (l - 1) * 512);
+      for (int o = 0; o < 128; ++o) {
+        float acc = 0.f;
+        for (int k = 0; k < 128; ++k) {
+          uint16_t h; std::memcpy(&h, blob + hypo::W1 + (l - 1) * 32768 + (k / 64) * 16384 + hypo::swz(o, (k % 64) * 2), 2);
+          acc += a[k] * gv_f16_to_f32(h);
+        }
+        b[o] = gv_f16_to_f32(gv_f32_to_f16(sinf(acc + bias[o])));
+      }
+      std::memcpy(a, b, sizeof a);
+    }
+    const float* b4 = reinterpret_cast<const float*>(blob + hypo::B4);
+    for (int o = 0; o < 2; ++o) {
+      float acc = 0.f;
+      for (int k = 0; k < 128; ++k) {
+        uint16_t h; std::memcpy(&h, blob + hypo::W4 + (k / 64) * 2048 + hypo::swz(o, (k % 64) * 2), 2);
+        acc += a[k] * gv_f16_to_f32(h);
+      }
+      out.p[out.off(n, y, x) + o] = acc + b4[o];
+    }
+  }
+}
+
+
+// hyponet_fused3: fp32 layers 0 and 4; layers 1-3 with the weights' and activations' fp16 hi + lo pairs (= their 22-bit values)
+void hyponet_fused3(Ctx& cx, const TV& lat, const float* coords, const void* blob_v, const TV& out) {
+  if (cx.dry) return;
+  cx.launches++;
+  const uint8_t* blob = static_cast<const uint8_t*>(blob_v);
+  const float* W0 = reinterpret_cast<const float*>(blob + hypo3::W0A);
+  const float* W4 = reinterpret_cast<const float*>(blob + hypo3::W4);
+  const float* b4 = reinterpret_cast<const float*>(blob + hypo3::B4);
+  auto pair = [](float v) { const float hi = gv_f16_to_f32(gv_f32_to_f16(v)); return hi + gv_f16_to_f32(gv_f32_to_f16(v - hi)); };
+  const int64_t P = lat.pixels();
+#pragma omp parallel for schedule(static)
+  for (int64_t pix = 0; pix < P; ++pix) {
+    const int x = (int)(pix % lat.w); int64_t r = pix / lat.w; const int y = (int)(r % lat.h); const int n = (int)(r / lat.h);
+    const float* lp = lat.p + lat.off(n, y, x);
+    const float* c = coords + pix * 3;
+    float a[128], b[128];
+    for (int o = 0; o < 128; ++o) {
+      float z = W0[35 * 128 + o];
+      for (int k = 0; k < 35; ++k) z = std::fmaf(k < 32 ? lp[k] : c[k - 32], W0[k * 128 + o], z);
+      a[o] = pair(sinf(z));
+    }
+    for (int l = 0; l < 3; ++l) {
+      const float* bias = reinterpret_cast<const float*>(blob + hypo3::B13 + l * 512);
+      for (int o = 0; o < 128; ++o) {
+        float acc = 0.f;
+        for (int k = 0; k < 128; ++k) {
+          uint16_t hi, lo;
+          std::memcpy(&hi, blob + hypo3::W13 + ((l * 2 + 0) * 2 + k / 64) * 16384 + hypo::swz(o, (k % 64) * 2), 2);
+          std::memcpy(&lo, blob + hypo3::W13 + ((l * 2 + 1) * 2 + k / 64) * 16384 + hypo::swz(o, (k % 64) * 2), 2);
+          acc += a[k] * (gv_f16_to_f32(hi) + gv_f16_to_f32(lo));
+        }
+        const float s = sinf(acc / hypo3::W_SCALE + bias[o]);
+        b[o] = l < 2 ? pair(s) : s;
+      }
+      std::memcpy(a, b, sizeof a);
+    }
+    for (int o = 0; o < 2; ++o) {
+      float acc = 0.f;
+      for (int k = 0; k < 128; ++k) acc = std::fmaf(a[k], W4[k * 2 + o], acc);
+      out.p[out.off(n, y, x) + o] = acc + b4[o];
+    }
+  }
+}
+
 }  // namespace gv
 #endif  // GV_HOSTSIM

@@ -103,12 +103,17 @@ SPLIT_CASES = [
     (256, 576, 1, 1, 16, 20, 1, 0),     # mask head: cout 576 -> 3 N tiles of 192
     (256, 2, 3, 3, 16, 20, 2, 0),       # flow head: cout 2
     (128, 256, 3, 3, 24, 40, 1, 1),
+    (128, 133, 3, 3, 24, 40, 1, 0),     # 2 N tiles whose width is not a multiple of the 32-column epilogue chunk (init-decoder head)
+    (96, 96, 3, 3, 24, 40, 2, 1),       # cin not a multiple of the 64-element K block of the 3xF16 form
+    (272, 128, 1, 1, 24, 40, 1, 0),
 ]
 
 
+@pytest.mark.parametrize("f16", [False, True], ids=["3xtf32", "3xf16"])
 @pytest.mark.parametrize("case", SPLIT_CASES)
-def test_conv2d_tc_3xtf32(case):
-    """3xTF32 operand splitting: fp32-class accuracy (vs an fp64 convolution of the UNROUNDED operands)."""
+def test_conv2d_tc_3xtf32(case, f16):
+    """Three-term operand splitting (3xTF32, and 3xF16: fp16 hi / lo pairs on kind::f16): fp32-class accuracy (vs an fp64
+    convolution of the UNROUNDED operands)."""
     cin, cout, kh, kw, H, W, n, act1 = case
     x = rnd(n, cin, H, W, seed=1)
     w = rnd(cout, cin, kh, kw, seed=2, scale=1.0 / (cin * kh * kw) ** 0.5)
@@ -117,18 +122,19 @@ def test_conv2d_tc_3xtf32(case):
     if cin % 4:
         pad = torch.full((n, H, W, (cin + 3) // 4 * 4), 7.0, device=DEV)
         pad[..., :cin] = xn
-        got = K.nchw(K.conv2d_tc(pad, w, b, act1, in_view=K.view_of(pad, channels=cin), split=True))
+        got = K.nchw(K.conv2d_tc(pad, w, b, act1, in_view=K.view_of(pad, channels=cin), split=True, split_f16=f16))
     else:
-        got = K.nchw(K.conv2d_tc(xn, w, b, act1, split=True))
+        got = K.nchw(K.conv2d_tc(xn, w, b, act1, split=True, split_f16=f16))
     f = {0: lambda v: v, 1: F.relu, 4: torch.sigmoid, 5: torch.tanh}[act1]
     ref = f(F.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))).float()
     err = (got - ref).abs().max().item()
-    print("split case", case, "err %.3e ref absmax %.3e" % (err, ref.abs().max().item()))
+    print("split case", case, "3xf16" if f16 else "3xtf32", "err %.3e ref absmax %.3e" % (err, ref.abs().max().item()))
     # operands are exact to ~2^-22; what remains is the tensor core's fp32 accumulation (long chains, truncating adder)
     assert err <= 1e-4
 
 
-def test_conv2d_tc_gru_epilogues():
+@pytest.mark.parametrize("f16", [False, True], ids=["3xtf32", "3xf16"])
+def test_conv2d_tc_gru_epilogues(f16):
     """r-gate: sigmoid(conv) * h;  q-gate: h' = (1-z) h + z tanh(conv(cat[r*h, x]))  (raft/update.py:52-59)."""
     n, H, W = 2, 16, 20
     hx = rnd(n, 384, H, W, seed=1)
@@ -140,12 +146,12 @@ def test_conv2d_tc_gru_epilogues():
     h_view = K.view_of(hxn, channels=128)
     # r * h
     hbuf = K.nhwc(hx[:, :128])
-    rh = K.conv2d_tc(hxn, wr, br, 4, mul=hbuf, split=True)
+    rh = K.conv2d_tc(hxn, wr, br, 4, mul=hbuf, split=True, split_f16=f16)
     rh_ref = torch.sigmoid(F.conv2d(hx.double(), wr.double(), br.double(), padding=(0, 2))).float() * hx[:, :128]
     assert (K.nchw(rh) - rh_ref).abs().max().item() <= 1e-4
     # q with two input segments and the GRU blend
     xin = K.nhwc(hx[:, 128:])
-    got = K.conv2d_tc(rh, wq, bq, 5, x1_nhwc=xin, gru_z=K.nhwc(z), gru_h=hbuf, split=True)
+    got = K.conv2d_tc(rh, wq, bq, 5, x1_nhwc=xin, gru_z=K.nhwc(z), gru_h=hbuf, split=True, split_f16=f16)
     q = torch.tanh(F.conv2d(torch.cat([rh_ref, hx[:, 128:]], 1).double(), wq.double(), bq.double(), padding=(0, 2))).float()
     ref = (1 - z) * hx[:, :128] + z * q
     assert (K.nchw(got) - ref).abs().max().item() <= 1e-4
@@ -162,14 +168,17 @@ CLUSTER_CASES = [
 ]
 
 
+@pytest.mark.parametrize("f16", [False, True], ids=["3xtf32", "3xf16"])
 @pytest.mark.parametrize("case", CLUSTER_CASES)
-def test_conv2d_tc_cluster_multicast(case):
+def test_conv2d_tc_cluster_multicast(case, f16):
     cin, cout, kh, kw, H, W, n, act1, split = case
+    if f16 and not split:
+        pytest.skip("3xF16 is a form of the split kernel")
     x = rnd(n, cin, H, W, seed=1)
     w = rnd(cout, cin, kh, kw, seed=2, scale=1.0 / (cin * kh * kw) ** 0.5)
     b = rnd(cout, seed=3, scale=0.1)
     slope = (0.25 + 0.1 * rnd(cout, seed=4)) if act1 == 3 else None
-    got = K.nchw(K.conv2d_tc(K.nhwc(x), w, b, act1, slope, split=split))
+    got = K.nchw(K.conv2d_tc(K.nhwc(x), w, b, act1, slope, split=split, split_f16=f16))
     f = {0: lambda v: v, 1: F.relu, 3: lambda v: F.prelu(v, slope.double()), 4: torch.sigmoid}[act1]
     if split:
         ref = f(F.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))).float()

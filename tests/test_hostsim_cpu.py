@@ -118,7 +118,7 @@ import os as _os
 @pytest.mark.parametrize("mode", [4, 3, 2, 1] if _os.environ.get("GIMMVFI_HOSTSIM_ALL_MODES") else [3])   # (72 s per mode on 8 cores)
 def test_hostsim_tensor_core_modes_match_oracle(eng, weights0, mode):
     """The engine's tensor-core ORCHESTRATION on the CPU: precision modes 1-3 with the tensor-core convolution's operand rounding
-    emulated on the host (csrc/conv_tc_hostsim.cu) — half-precision trunk tensors, merged GRU gates, stride-2 and pre-padded
+    emulated on the host (tests/hostsim/tc_hostsim.cu) — half-precision trunk tensors, merged GRU gates, stride-2 and pre-padded
     layers, tensor-core correlation — against the oracle within the product's tolerance (max|d imgt_pred| <= 1e-3)."""
     torch.set_grad_enabled(False)
     B, H, W, ts = 1, 128, 160, [0.5]

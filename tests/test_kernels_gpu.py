@@ -196,3 +196,38 @@ def test_conv_thin_cin(case):
     ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2)
     ref = {0: lambda v: v, 1: F.relu, 2: lambda v: F.leaky_relu(v, 0.1)}[act](ref)
     assert (got.double() - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("fp32_class", [1, 0])
+@pytest.mark.parametrize("shape", [(1, 24, 40), (2, 50, 37), (1, 128, 160)])   # incl. pixel counts that are not a multiple of the 128-pixel tile
+def test_hyponet_fused_vs_oracle(shape, fp32_class, weights0):
+    """The fused tcgen05 HypoNet kernels (csrc/hyponet.cu) against the oracle's hyponet_forward (modules/hyponet.py:71-146) in fp32.
+    fp32_class = 1 (the forward pass's default): fp16 hi/lo operand pairs in layers 1-3, CUDA-core fp32 layers 0 and 4 -> fp32-level
+    agreement (the output feeds (2 o - 1) * max|flow|: 1e-5 here is 1e-3 px at 40 px motion).  fp32_class = 0: TF32 layer 0 + half
+    hidden activations -> operand rounding at 2^-11."""
+    import ctypes as C
+
+    from gimmvfi_b200 import EngineHandle
+    from gimmvfi_b200._lib import view_of
+
+    n, h, w = shape
+    eng = EngineHandle(DEV)
+    eng.load_state_dict(weights0)
+    g = torch.Generator().manual_seed(5)
+    lat = (torch.randn(n, h, w, 32, generator=g) * 0.7)
+    coord = torch.cat([O.sample_coord_input(1, (h, w), [0.25 + 0.5 * i]) for i in range(n)], 0)   # (n,1,h,w,3), a different t per sample
+    lat = K.tf32_rn(lat)   # the producing conv stores TF32-representable values (conv_tc.cu round_out): both kernels see them exactly
+    ref = O.hyponet_forward({k: v.double() for k, v in weights0.items() if k.startswith("hyponet.")}, coord.double(), lat.double()).float()   # (n,1,h,w,2)
+    lat_d = lat.to(DEV)
+    out = torch.empty(n, h, w, 2, device=DEV)
+    cd = coord.to(DEV).contiguous()
+    eng.lib.check(eng.lib.dll.gimmvfi_op_hyponet(eng._h, C.byref(view_of(lat_d)), C.c_void_p(cd.data_ptr()), C.byref(view_of(out)), fp32_class,
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), eng._h)
+    torch.cuda.synchronize()
+    d = (out.cpu() - ref[:, 0]).abs()
+    print("hyponet fused", shape, "fp32_class", fp32_class, "max %.3e mean %.3e" % (d.max().item(), d.mean().item()))
+    assert torch.isfinite(out).all()
+    if fp32_class:
+        assert d.max().item() <= 2e-5 and d.mean().item() <= 2e-6   # MUFU sin (~1e-6 per activation) is the largest term
+    else:
+        assert d.max().item() <= 4e-3 and d.mean().item() <= 5e-4
