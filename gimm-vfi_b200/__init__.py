@@ -14,6 +14,10 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         from .gimm import GIMM
 
         return GIMM
+    if name == "GIMMVFI_F":
+        from .model_f import GIMMVFI_F
+
+        return GIMMVFI_F
     if name == "EngineHandle":
         from .engine import EngineHandle
 

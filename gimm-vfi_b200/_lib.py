@@ -31,6 +31,10 @@ class IO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _IO_FIELDS]
 
 
+class FlowInputs(C.Structure):
+    _fields_ = [("flows", C.c_void_p), ("feat4", C.c_void_p * 2), ("feat8", C.c_void_p * 2), ("fnet", C.c_void_p * 2)]
+
+
 class View(C.Structure):
     _fields_ = [
         ("data", C.c_void_p),
@@ -47,7 +51,7 @@ EXPORTS = [
     "gimmvfi_create", "gimmvfi_destroy", "gimmvfi_load_weight", "gimmvfi_finalize_weights", "gimmvfi_plan",
     "gimmvfi_forward", "gimmvfi_last_error", "gimmvfi_last_launches", "gimmvfi_weights_version", "gimmvfi_set_raft_iters", "gimmvfi_set_debug",
     "gimmvfi_get_tap", "gimmvfi_build_info", "gimmvfi_set_profile", "gimmvfi_profile_json",
-    "gimmvfi_set_tensor_cores", "gimmvfi_finalize_weights_gimm", "gimmvfi_gimm_plan", "gimmvfi_gimm_forward", "gimmvfi_frame_cache_bytes", "gimmvfi_set_frame_cache", "gimmvfi_op_conv2d_tc", "gimmvfi_op_conv2d_tc_f16", "gimmvfi_op_conv2d_tc_strided", "gimmvfi_op_frames_u8_to_padded_f32", "gimmvfi_op_pred_to_u8", "gimmvfi_op_softsplat", "gimmvfi_op_backwarp", "gimmvfi_op_resize",
+    "gimmvfi_set_tensor_cores", "gimmvfi_finalize_weights_gimm", "gimmvfi_finalize_weights_synthesis", "gimmvfi_plan_from_flow", "gimmvfi_forward_from_flow", "gimmvfi_gimm_plan", "gimmvfi_gimm_forward", "gimmvfi_frame_cache_bytes", "gimmvfi_set_frame_cache", "gimmvfi_op_conv2d_tc", "gimmvfi_op_conv2d_tc_f16", "gimmvfi_op_conv2d_tc_strided", "gimmvfi_op_frames_u8_to_padded_f32", "gimmvfi_op_pred_to_u8", "gimmvfi_op_softsplat", "gimmvfi_op_backwarp", "gimmvfi_op_resize",
     "gimmvfi_op_corr_volume", "gimmvfi_op_corr_volume_tc", "gimmvfi_op_corr_pool", "gimmvfi_op_corr_pool_pyramid", "gimmvfi_op_corr_lookup", "gimmvfi_op_conv2d",
     "gimmvfi_instnorm_scratch_floats", "gimmvfi_op_hyponet", "gimmvfi_op_instnorm", "gimmvfi_op_convex_upsample", "gimmvfi_op_pixel_shuffle",
 ]
@@ -90,6 +94,9 @@ class Lib:
         d.gimmvfi_set_profile.argtypes = [vp, i32]
         d.gimmvfi_set_tensor_cores.argtypes = [vp, i32]
         d.gimmvfi_finalize_weights_gimm.argtypes = [vp]
+        d.gimmvfi_finalize_weights_synthesis.argtypes = [vp]
+        d.gimmvfi_plan_from_flow.argtypes = [vp, C.POINTER(Problem), C.POINTER(C.c_size_t)]
+        d.gimmvfi_forward_from_flow.argtypes = [vp, C.POINTER(Problem), C.POINTER(IO), C.POINTER(FlowInputs), vp, C.c_size_t, vp]
         d.gimmvfi_gimm_plan.argtypes = [vp, C.POINTER(Problem), C.POINTER(C.c_size_t)]
         d.gimmvfi_gimm_forward.argtypes = [vp, C.POINTER(Problem), vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
         d.gimmvfi_frame_cache_bytes.argtypes = [C.POINTER(Problem)]

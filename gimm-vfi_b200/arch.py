@@ -155,3 +155,26 @@ def param_spec_r() -> Spec:
         s.append(("hyponet.params_dict.linear_wb%d" % i, (129, 128), "float32"))
     s.append(("hyponet.params_dict.linear_wb4", (129, 2), "float32"))
     return s
+
+
+R_ONLY_PREFIXES = ("flow_estimator.", "amt_last_cproj.", "amt_second_last_cproj.", "amt_fproj.")
+
+
+def param_spec_f() -> Spec:
+    """GIMM-VFI-F (gimmvfi_f.py:27-111): 639 tensors = FlowFormer (`flow_estimator.*`: Twins-SVT-L stages 1-2 x2, cost-perceiver
+    encoder, GMA memory decoder — flowformer/core/**) + the same decoder / GIMM parameter tree as GIMM-VFI-R without its three feature
+    projections.  The FlowFormer part (410 keys, the layout of its published `flowformer_sintel.pth` checkpoint) is kept as a
+    schema table (specs/state_dict_spec_f.json, dumped from the reference module; tests/test_arch.py compares it with the dump
+    under tests/golden/); the rest is generated exactly like param_spec_r."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "specs", "state_dict_spec_f.json")) as f:
+        table = json.load(f)
+    spec = [(k, tuple(shape), dt) for k, shape, dt in table]
+    shared = {k: (shape, dt) for k, shape, dt in param_spec_r() if not k.startswith(R_ONLY_PREFIXES)}
+    for k, shape, dt in spec:   # the synthesis half must be the R layout, key for key
+        if not k.startswith("flow_estimator."):
+            assert k in shared and tuple(shared[k][0]) == tuple(shape) and shared[k][1] == dt, k
+    assert sum(1 for k, _, _ in spec if not k.startswith("flow_estimator.")) == len(shared)
+    return spec

@@ -64,6 +64,26 @@ int gimmvfi_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_i
   })
 }
 
+static IO to_io(const gimmvfi_io* io) {
+  IO q;
+  q.img_xs = io->img_xs; q.coords = io->coords; q.t = io->t; q.imgt_pred = io->imgt_pred; q.img_warp_4 = io->img_warp_4;
+  q.flowt0_1 = io->flowt0_1; q.flowt1_1 = io->flowt1_1; q.flowt0_4 = io->flowt0_4; q.flowt1_4 = io->flowt1_4;
+  q.raft_flow = io->raft_flow; q.nflow = io->nflow; q.ninrflow = io->ninrflow; q.flowt = io->flowt;
+  return q;
+}
+int gimmvfi_finalize_weights_synthesis(gimmvfi_engine* e) { GV_TRY(e, { e->eng.finalize_weights_synthesis(); }) }
+int gimmvfi_plan_from_flow(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes) {
+  GV_TRY(e, { *workspace_bytes = e->eng.plan_from_flow(to_problem(p)); })
+}
+int gimmvfi_forward_from_flow(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_io* io, const gimmvfi_flow_inputs* fin,
+                              void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  GV_TRY(e, {
+    if (!io || !fin) throw std::runtime_error("gimmvfi_forward_from_flow: io and fin are required");
+    FlowInputs f; f.flows = fin->flows;
+    for (int j = 0; j < 2; ++j) { f.feat4[j] = fin->feat4[j]; f.feat8[j] = fin->feat8[j]; f.fnet[j] = fin->fnet[j]; }
+    e->eng.forward_from_flow(to_problem(p), to_io(io), f, workspace, workspace_bytes, (gvStream_t)cuda_stream);
+  })
+}
 int gimmvfi_finalize_weights_gimm(gimmvfi_engine* e) { GV_TRY(e, { e->eng.finalize_weights_gimm(); }) }
 int gimmvfi_gimm_plan(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes) {
   GV_TRY(e, { *workspace_bytes = e->eng.plan_gimm(to_problem(p)); })
@@ -148,7 +168,8 @@ int gimmvfi_op_corr_volume_tc(const gimmvfi_view* fa, const gimmvfi_view* fb, fl
     const int64_t N = (int64_t)a.h * a.w;
     float* planes = scratch; float* zeros = scratch + 2 * N * a.c;
     dev_memset(zeros, 0, (size_t)(((N + 255) / 256) * 256 + 512) * sizeof(float), cx.stream);
-    if (split) split_planes(cx, b, planes);
+    if (split && corr_volume_tc_wants_f16_planes()) split_planes_f16(cx, b, planes);
+    else if (split) split_planes(cx, b, planes);
     corr_volume_tc(cx, a, split ? planes : b.p, zeros, vol, 1.0f / std::sqrt((float)a.c), split != 0);
 #endif
   })

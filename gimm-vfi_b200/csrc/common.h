@@ -332,12 +332,14 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1 /*optional 2nd channel segment
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split);
+bool corr_volume_tc_wants_f16_planes();   // split mode: true -> fb_planes must come from split_planes_f16 (3xF16 form), else split_planes
 // hyponet.cu (sm_100a; the host simulation emulates its arithmetic): the whole HypoNet MLP in one kernel
 bool hyponet_fused_supported(const TV& lat, const TV& out);
 void hyponet_fused(Ctx& cx, const TV& lat /*n,h,w,32*/, const float* coords /*n*h*w x (t,y,x)*/, const void* blob /*hypo:: layout*/, const TV& out /*2 ch*/);
 void hyponet_fused3(Ctx& cx, const TV& lat, const float* coords, const void* blob3 /*hypo3:: layout*/, const TV& out);   // fp32-class arithmetic
 // corr.cu
 void split_planes(Ctx& cx, const TV& src, float* planes);  // [2][n*h*w][c]: rn_tf32(x) and rn_tf32(x - rn_tf32(x))
+void split_planes_f16(Ctx& cx, const TV& src, void* planes);  // half [2][n*h*w][c]: rn_f16(x) and rn_f16(x - rn_f16(x))
 void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale);   // vol[n][i][j] = <fa[n,i], fb[n,j]> * scale
 void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w); // rows x (h*w) -> rows x (h/2*w/2)
 void corr_pool_pyramid(Ctx& cx, const float* l0, float* l1, float* l2, float* l3, int64_t rows, int h, int w);

@@ -1016,9 +1016,15 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   const bool e8 = tc_epi8() && (!split || tc_split_epi8());
   // CTA pairs as in conv2d_tc: two neighbouring source-pixel tiles share the target-pixel ("weight") tile, half of it per CTA
   const bool atm = split && tc_atmem();
+  const bool sf16 = split && corr_volume_tc_wants_f16_planes() && C % 64 == 0;
   const bool pair = e8 && pix_tiles_host >= 2 && (split ? (tc_pair() >= 2 && atm) : (tc_pair() != 0)) && pix_tiles_host * tiles_n >= 2 * cx.sm_count;
   const int CL = pair ? 2 : 1;
-  {
+  if (sf16) {   // half planes, 64-element K blocks (128-byte rows)
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, 2};
+    cuuint64_t str[2] = {(cuuint64_t)C * 2, (cuuint64_t)N * C * 2};
+    cuuint32_t box[3] = {2 * BK, (cuuint32_t)(BN / CL), 1};
+    encode(&mB, fb_planes, 3, dims, str, box, true);
+  } else {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)(split ? 2 : 1)};
     cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
     cuuint32_t box[3] = {BK, (cuuint32_t)(BN / CL), 1};
@@ -1026,16 +1032,16 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   }
   Params p;
   p.taps = 1; p.kw = 1; p.ph = 0; p.pw = 0; p.stride = 1;
-  p.kblocks = C / 32; p.c0_blocks = p.kblocks; p.f16_in = 0; p.bk = BK; p.split_f16 = 0;
+  p.kblocks = sf16 ? C / 64 : C / 32; p.c0_blocks = p.kblocks; p.f16_in = 0; p.bk = sf16 ? 2 * BK : BK; p.split_f16 = sf16 ? 1 : 0;
   p.tiles_x = (fa.w + TILE_W - 1) / TILE_W; p.tiles_y = (fa.h + TILE_H - 1) / TILE_H; p.n_img = 1; p.tiles_n = tiles_n;
-  p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale; p.seg = tc_seg();
+  p.H = fa.h; p.W = fa.w; p.BN = BN; p.cout = N; p.round_out = 0; p.out_scale = scale; p.seg = sf16 ? tc_seg_f16() : tc_seg();
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin; p.dbg = tc_debug(); p.atmem = atm ? 1 : 0; p.stall = tc_stall_buf();
   p.bias = zero_bias; p.act1 = ACT_NONE; p.slope1 = nullptr; p.act2 = ACT_NONE; p.slope2 = nullptr;
   p.out = make_tv(vol, 1, fa.h, fa.w, N, N); p.out2 = TV(); p.split_c = 0;
   const int bn_cta = pair ? BN / 2 : BN;
-  const int stage_bytes = split ? ((p.atmem ? 1 : 2) * A_BYTES + 2 * bn_cta * BK * 4) : (A_BYTES + bn_cta * BK * 4);
+  const int stage_bytes = split ? (((p.atmem && !sf16) ? 1 : 2) * A_BYTES + 2 * bn_cta * BK * 4) : (A_BYTES + bn_cta * BK * 4);
   const int stg_bytes = (e8 ? 8 : 4) * STG_WARP_BYTES;
   p.stages = (227 * 1024 - 1024 - stg_bytes - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
@@ -1045,7 +1051,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
   grid -= grid % CL;
   cx.launches++;
-  if (cx.prof) cx.prof->begin(cx.stream, split ? "corr_gemm_tc_3xtf32" : "corr_gemm_tc_tf32", 2.0 * (double)N * N * C);
+  if (cx.prof) cx.prof->begin(cx.stream, split ? (sf16 ? "corr_gemm_tc_3xf16" : "corr_gemm_tc_3xtf32") : "corr_gemm_tc_tf32", 2.0 * (double)N * N * C);
   if (split && pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA, mA, mB, p);
   else if (split && e8) launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA, mA, mB, p);
   else if (split) launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA, mA, mB, p);
@@ -1055,6 +1061,8 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   gv_check_launch("corr_volume_tc");
   if (cx.prof) cx.prof->end(cx.stream);
 }
+
+bool corr_volume_tc_wants_f16_planes() { return tc_split_f16() != 0 && tc_atmem() != 0; }
 
 }  // namespace gv
 #endif  // GV_HOSTSIM

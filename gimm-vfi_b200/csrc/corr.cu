@@ -110,6 +110,21 @@ void split_planes(Ctx& cx, const TV& src, float* planes) {
   int64_t n = src.pixels() * src.c;
   parallel_for(cx, n, SplitPlanesK{src, planes, n}, "split_planes");
 }
+// half [2][pixels][c] planes for the 3xF16 correlation GEMM: hi = rn_f16(x), lo = rn_f16(x - hi)  (feature maps are O(1): no scaling)
+struct SplitPlanesF16K {
+  TV src; uint16_t* planes; int64_t plane;
+  GV_HD void operator()(int64_t i) const {
+    int c = (int)(i % src.c); int64_t px = i / src.c;
+    int x = (int)(px % src.w); int64_t r = px / src.w; int y = (int)(r % src.h); int n = (int)(r / src.h);
+    const float v = src.p[src.off(n, y, x) + c];
+    const uint16_t hi = gv_f2h(v);
+    planes[i] = hi; planes[plane + i] = gv_f2h(v - gv_h2f(hi));
+  }
+};
+void split_planes_f16(Ctx& cx, const TV& src, void* planes) {
+  int64_t n = src.pixels() * src.c;
+  parallel_for(cx, n, SplitPlanesF16K{src, static_cast<uint16_t*>(planes), n}, "split_planes");
+}
 
 // ------------------------------------------------------------------- pool
 // F.avg_pool2d(corr, 2, stride=2) over the trailing (h, w) image of every row (raft/corr.py:139-142).

@@ -351,6 +351,13 @@ void Engine::finalize_weights() {
   pack_xpacked(u + ".encoder.convf1", 4);
   // --- feature projections (gimmvfi_r.py:51-53)
   pack_conv("amt_last_cproj"); pack_conv("amt_second_last_cproj"); pack_conv("amt_fproj");
+  finalize_decoders();
+  finalize_gimm_part();
+  finalized_ = true; gimm_only_ = false; synth_only_ = false;
+}
+
+// AMT decoders / update blocks / combine block (fi_components.py:229-305): shared by GIMM-VFI-R and -F
+void Engine::finalize_decoders() {
   // --- decoders (fi_components.py:229-305)
   {
     const std::string p = "amt_init_decoder";
@@ -382,8 +389,18 @@ void Engine::finalize_weights() {
   pack_conv("amt_comb_block.0"); vec("amt_comb_block.1.weight"); pack_conv("amt_comb_block.2");
   pack_xpacked("amt_comb_block.0", 12); pack_xpacked("amt_comb_block.2", 20);
   pack_xpacked("amt_update4_low.convf1", 4); pack_xpacked("amt_update4_high.convf1", 4);
+}
+
+// GIMM-VFI-F's parameter tree minus flow_estimator.* (gimmvfi_f.py:37-111): the synthesis half runs natively on the outputs of an
+// external flow estimator (forward_from_flow); there are no feature projections in F (twins features are used as they are)
+void Engine::finalize_weights_synthesis() {
+  DeviceGuard dg(device_);
+  for (void* p : dev_allocs_) dev_free(p);
+  dev_allocs_.clear(); conv_.clear(); vec_.clear();
+  fc_valid_.clear(); ++weights_version_;
+  finalize_decoders();
   finalize_gimm_part();
-  finalized_ = true; gimm_only_ = false;
+  finalized_ = true; gimm_only_ = false; synth_only_ = true;
 }
 
 // GIMM's own parameters (gimm.py:36-80 == gimmvfi_r.py:86-111): motion encoder, latent refiner, HypoNet, splat-metric scalars
@@ -663,7 +680,8 @@ static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, int ten
     if (!cx.dry) dev_memset(zeros, 0, (size_t)nz * sizeof(float), cx.stream);
     for (int s = 0; s < 2 * B; ++s) {
       const int other = s < B ? s + B : s - B;
-      if (split) split_planes(cx, F.batch(other, 1), planes);
+      if (split && corr_volume_tc_wants_f16_planes()) split_planes_f16(cx, F.batch(other, 1), planes);
+      else if (split) split_planes(cx, F.batch(other, 1), planes);
       if (!cx.dry) corr_volume_tc(cx, F.batch(s, 1), split ? planes : F.batch(other, 1).p, zeros, P.lvl[0] + (int64_t)s * P.N * P.N, scale, split);
     }
     A.release(mk);
@@ -744,7 +762,7 @@ static void check_problem(const Problem& p) {
     throw std::runtime_error("gimmvfi: coordinate grid must match the network resolution (frame_synthesize consumes flow_t at that size)");
 }
 
-void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
+void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin) {
   check_problem(P);
   Net N{*this, cx};
   Arena& A = cx.arena;
@@ -790,7 +808,16 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   // ------------------------------------------------------------ RAFT (both directions batched)
   // The recurrence amplifies operand rounding -> fp32-class arithmetic only: 3xTF32 tensor cores or CUDA cores.
   cx.tc = tc_mode_ >= 2; cx.tc_split = true;
-  {
+  TV fproj = A.tensor(2 * B, h, w, 256);            // the maps BidirCorrBlock correlates (R: amt_fproj(fnet map); F: the estimator's own)
+  if (fin) {
+    // external flow estimator (GIMM-VFI-F): NCHW -> the engine's NHWC buffers, samples [frame-0 batch ; frame-1 batch]
+    for (int j = 0; j < 2; ++j) {
+      nchw_to_nhwc(cx, fin->flows + (int64_t)j * H * W, (int64_t)4 * H * W, (int64_t)2 * H * W, flow_up.batch(j * B, B), 1.f, 0.f);
+      nchw_to_nhwc(cx, fin->feat4[j], (int64_t)128 * H4 * W4, (int64_t)H4 * W4, feat4.batch(j * B, B), 1.f, 0.f);
+      nchw_to_nhwc(cx, fin->feat8[j], (int64_t)256 * h * w, (int64_t)h * w, feat8.batch(j * B, B), 1.f, 0.f);
+      nchw_to_nhwc(cx, fin->fnet[j], (int64_t)256 * h * w, (int64_t)h * w, fproj.batch(j * B, B), 1.f, 0.f);
+    }
+  } else {
     const size_t mk = A.mark();
     TV hx = A.tensor(2 * B, h, w, 384);              // [h | inp | motion]
     TV c4, c8;
@@ -807,11 +834,13 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
       TV rin = raft_in.batch(e0, en);
       TV raft_pad = A.tensor(en, H + 6, W + 6, 3, 4);
       pad_image4(cx, rin, raft_pad, 3);
+      if (precise_ & 32) cx.tc_split = false;   // experiment: RAFT encoders on plain TF32
       raft_encoder(N, "flow_estimator.fnet", true, rin, raft_pad, fmap.batch(e0, en), nullptr, nullptr, nullptr, TV(), TV());
       // the encoder's temporaries stay allocated until `mk` is released (bump allocator)
       const ConvW& wc = N.W("flow_estimator.cnet.conv2");
       raft_encoder(N, "flow_estimator.cnet", false, rin, raft_pad, TV(), &c4, &c8, &wc, hx.batch(e0, en).slice(0, 128), hx.batch(e0, en).slice(128, 128));
     }
+    cx.tc_split = true;
     // context features for the synthesis net (gimmvfi_r.py:134-141)
     N.conv("amt_second_last_cproj", c4, feat4.batch(e0, en));
     N.conv("amt_last_cproj", c8, feat8.batch(e0, en));
@@ -892,8 +921,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io) {
   // Everything downstream of RAFT tolerates TF32 operands (DESIGN.md precision plan).
   cx.tc = tc_mode_ >= 1; cx.tc_split = false;
   // ------------------------------------------------------------ bidirectional volume on projected features
-  TV fproj = A.tensor(2 * B, h, w, 256);
-  N.conv("amt_fproj", fmap, fproj);
+  if (!fin) N.conv("amt_fproj", fmap, fproj);
   // the bidirectional volume only feeds TF32 layers (AMT update blocks) -> plain TF32 is at their input precision
   Pyramid bpyr = build_pyramid(cx, fproj, B, tc_mode_ >= 1 ? 1 : 0);   // gimmvfi_r.py:133, raft/corr.py:23-44
 
@@ -1217,8 +1245,41 @@ size_t Engine::frame_cache_bytes(const Problem& p) {
   return ((size_t)p.B * h * w * 256 * 3 + (size_t)p.B * H4 * W4 * 128) * sizeof(float);
 }
 
+size_t Engine::plan_from_flow(const Problem& p) {
+  if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights*() has not been called");
+  if (gimm_only_) throw std::runtime_error("gimmvfi: only GIMM's weights were loaded");
+  Ctx cx; cx.dry = true; cx.arena.dry = true; cx.sm_count = sm_count_;
+  IO io; float* fake = reinterpret_cast<float*>(size_t(64));
+  io.img_xs = io.coords = io.t = fake;
+  io.imgt_pred = io.img_warp_4 = io.flowt0_1 = io.flowt1_1 = io.flowt0_4 = io.flowt1_4 = io.raft_flow = io.nflow = io.ninrflow = io.flowt = fake;
+  FlowInputs fin; fin.flows = fake;
+  for (int j = 0; j < 2; ++j) fin.feat4[j] = fin.feat8[j] = fin.fnet[j] = fake;
+  run(cx, p, io, &fin);
+  taps_.clear();
+  return cx.arena.peak + 256;
+}
+
+void Engine::forward_from_flow(const Problem& p, const IO& io, const FlowInputs& fin, void* workspace, size_t workspace_bytes, gvStream_t stream) {
+  if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights*() has not been called");
+  if (gimm_only_) throw std::runtime_error("gimmvfi: only GIMM's weights were loaded (finalize_weights_gimm)");
+  if (!io.img_xs || !io.coords || !io.t || !io.imgt_pred) throw std::runtime_error("gimmvfi: img_xs, coords, t and imgt_pred are required");
+  if (!fin.flows || !fin.feat4[0] || !fin.feat4[1] || !fin.feat8[0] || !fin.feat8[1] || !fin.fnet[0] || !fin.fnet[1])
+    throw std::runtime_error("gimmvfi: forward_from_flow needs flows, feat4[2], feat8[2] and fnet[2]");
+  DeviceGuard dg(device_);
+  Ctx cx; cx.stream = stream; cx.sm_count = sm_count_;
+  prof_.reset();
+  cx.prof = profile_ ? &prof_ : nullptr;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  cx.arena.base = reinterpret_cast<char*>(base);
+  cx.arena.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
+  taps_.clear();
+  run(cx, p, io, &fin);
+  launches_ = cx.launches;
+}
+
 size_t Engine::plan(const Problem& p) {
   if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
+  if (synth_only_) throw std::runtime_error("gimmvfi: no flow estimator weights were loaded (finalize_weights_synthesis); use plan_from_flow");
   Ctx cx; cx.dry = true; cx.arena.dry = true; cx.sm_count = sm_count_;
   IO io;  // null pointers; dry run never dereferences them, but optional outputs must be "present"
   float* fake = reinterpret_cast<float*>(size_t(64));
@@ -1234,6 +1295,7 @@ size_t Engine::plan(const Problem& p) {
 void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t workspace_bytes, gvStream_t stream) {
   if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
   if (gimm_only_) throw std::runtime_error("gimmvfi: only GIMM's weights were loaded (finalize_weights_gimm); use gimm_forward");
+  if (synth_only_) throw std::runtime_error("gimmvfi: no flow estimator weights were loaded (finalize_weights_synthesis); use forward_from_flow");
   if (!io.img_xs || !io.coords || !io.t || !io.imgt_pred) throw std::runtime_error("gimmvfi: img_xs, coords, t and imgt_pred are required");
   DeviceGuard dg(device_);
   Ctx cx; cx.stream = stream; cx.sm_count = sm_count_;

@@ -38,6 +38,15 @@ struct IO {
   float* flowt = nullptr;          // (T,B,2,Hc,Wc)
 };
 
+// Outputs of an EXTERNAL bidirectional flow estimator at the network resolution (GIMM-VFI-F: FlowFormer, gimmvfi_f.py:114-138) in the
+// reference's NCHW layouts; with these the engine runs everything downstream of cal_bidirection_flow (forward_from_flow)
+struct FlowInputs {
+  const float* flows = nullptr;                  // (B,2,2,H,W): [f01 | f10] on dim 2
+  const float* feat4[2] = {nullptr, nullptr};    // (B,128,H/4,W/4): features0[0], features1[0]
+  const float* feat8[2] = {nullptr, nullptr};    // (B,256,H/8,W/8): features0[1], features1[1]
+  const float* fnet[2] = {nullptr, nullptr};     // (B,256,H/8,W/8): the maps BidirCorrBlock correlates
+};
+
 struct DebugTap { TV tv; };
 
 // GIMM.forward (gimm.py:129-214) device pointers, reference layouts
@@ -58,6 +67,9 @@ class Engine {
   void load_weight(const std::string& key, const float* host, const int64_t* shape, int ndim);
   void finalize_weights();
   void finalize_weights_gimm();                        // a standalone GIMM checkpoint (gimm.py's module tree only)
+  void finalize_weights_synthesis();                   // everything downstream of the flow estimator (GIMM-VFI-F's tree minus flow_estimator.*)
+  size_t plan_from_flow(const Problem& p);
+  void forward_from_flow(const Problem& p, const IO& io, const FlowInputs& fin, void* workspace, size_t workspace_bytes, gvStream_t stream);
   size_t plan_gimm(const Problem& p);
   void forward_gimm(const Problem& p, const GimmIO& io, void* workspace, size_t workspace_bytes, gvStream_t stream);
   size_t plan(const Problem& p);                       // dry run -> workspace bytes
@@ -90,7 +102,8 @@ class Engine {
 
  private:
   struct Impl;
-  void run(Ctx& cx, const Problem& p, const IO& io);
+  void run(Ctx& cx, const Problem& p, const IO& io, const FlowInputs* fin = nullptr);
+  void finalize_decoders();
   void run_gimm(Ctx& cx, const Problem& p, const GimmIO& io);
   void finalize_gimm_part();
   void gimm_encode(Net& N, const TV& nf, const TV& f01, const TV& f10, const TV& wts, const TV& X64);
@@ -103,7 +116,7 @@ class Engine {
   void tap(const std::string& name, const TV& tv) { if (debug_) taps_[name] = tv; }
 
   int device_ = 0;
-  bool finalized_ = false, debug_ = false, profile_ = false, gimm_only_ = false;
+  bool finalized_ = false, debug_ = false, profile_ = false, gimm_only_ = false, synth_only_ = false;
   int tc_mode_ = 0;
   int64_t weights_version_ = 0;
   int precise_ = 0;   // bit mask of post-RAFT stages in 3xTF32: 1 GIMM encoders / latent refiner, 2 HypoNet, 4 init decoder + update blocks, 8 final decoder, 16 combine

@@ -7,7 +7,7 @@ from typing import Dict, Optional
 
 import torch
 
-from ._lib import IO, Lib, Problem, View, default_lib
+from ._lib import IO, FlowInputs, Lib, Problem, View, default_lib
 
 
 class EngineHandle:
@@ -42,15 +42,21 @@ class EngineHandle:
             pass
 
     # ------------------------------------------------------------------ weights
-    def load_state_dict(self, sd: Dict[str, torch.Tensor], gimm_only: bool = False):
-        """gimm_only: `sd` is a standalone GIMM checkpoint (gimm.py's module tree), only gimm_forward() is available"""
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], gimm_only: bool = False, synthesis_only: bool = False):
+        """gimm_only: `sd` is a standalone GIMM checkpoint (gimm.py's module tree), only gimm_forward() is available.
+        synthesis_only: `sd` is a GIMM-VFI-F state_dict; its `flow_estimator.*` (FlowFormer) entries are skipped and only
+        forward_from_flow() is available."""
         for k, v in sd.items():
             if not v.dtype.is_floating_point:
                 continue  # num_batches_tracked
+            if synthesis_only and k.startswith("flow_estimator."):
+                continue
             t = v.detach().to("cpu", torch.float32).contiguous()
             shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
             self.lib.check(self.lib.dll.gimmvfi_load_weight(self._h, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()), self._h)
-        fin = self.lib.dll.gimmvfi_finalize_weights_gimm if gimm_only else self.lib.dll.gimmvfi_finalize_weights
+        fin = self.lib.dll.gimmvfi_finalize_weights_gimm if gimm_only else (
+            self.lib.dll.gimmvfi_finalize_weights_synthesis if synthesis_only else self.lib.dll.gimmvfi_finalize_weights)
+        self.synthesis_only = synthesis_only
         self.lib.check(fin(self._h), self._h)
         self.weights_loaded = True
 
@@ -103,37 +109,51 @@ class EngineHandle:
     def _problem(self, B, Hf, Wf, T, ds, Hc, Wc) -> Problem:
         return Problem(B, Hf, Wf, T, float(ds) if ds else 0.0, Hc, Wc)
 
-    def workspace_bytes(self, B, Hf, Wf, T, ds, Hc, Wc) -> int:
+    def workspace_bytes(self, B, Hf, Wf, T, ds, Hc, Wc, from_flow: bool = False) -> int:
         key = (B, Hf, Wf, T, float(ds) if ds else 0.0, Hc, Wc)
-        if key not in self._plans:
+        pkey = key + (bool(from_flow),)
+        if pkey not in self._plans:
             p = self._problem(*key)
             n = C.c_size_t()
-            self.lib.check(self.lib.dll.gimmvfi_plan(self._h, C.byref(p), C.byref(n)), self._h)
-            self._plans[key] = int(n.value)
-        return self._plans[key]
+            plan = self.lib.dll.gimmvfi_plan_from_flow if from_flow else self.lib.dll.gimmvfi_plan
+            self.lib.check(plan(self._h, C.byref(p), C.byref(n)), self._h)
+            self._plans[pkey] = int(n.value)
+        return self._plans[pkey]
 
     def frame_cache_bytes(self, B, Hf, Wf, T, ds, Hc, Wc) -> int:
         p = self._problem(B, Hf, Wf, T, ds, Hc, Wc)
         return int(self.lib.dll.gimmvfi_frame_cache_bytes(C.byref(p)))
 
     def forward(self, img_xs: torch.Tensor, coords: torch.Tensor, t: torch.Tensor, ds: Optional[float] = None,
-                aux_outputs: bool = True, frame_cache=None) -> Dict[str, torch.Tensor]:
+                aux_outputs: bool = True, frame_cache=None, flow_inputs=None) -> Dict[str, torch.Tensor]:
         """img_xs (B,3,2,Hf,Wf), coords (T,B,1,Hc,Wc,3), t (T,B): contiguous fp32 on self.device.
-        frame_cache = (uint8 device tensor of frame_cache_bytes(), load, store): see gimmvfi_set_frame_cache."""
+        frame_cache = (uint8 device tensor of frame_cache_bytes(), load, store): see gimmvfi_set_frame_cache.
+        flow_inputs = dict(flows (B,2,2,H,W), feat4 [2 x (B,128,H/4,W/4)], feat8 [2 x (B,256,H/8,W/8)], fnet [2 x (B,256,H/8,W/8)]):
+        the outputs of an external flow estimator at the network resolution -> gimmvfi_forward_from_flow (GIMM-VFI-F)."""
         self._check_inputs(img_xs, coords, t)
+        if flow_inputs is not None:
+            flow_inputs = {k: (v.to(torch.float32).contiguous() if torch.is_tensor(v) else [u.to(torch.float32).contiguous() for u in v])
+                           for k, v in flow_inputs.items()}
+            self._check_inputs(flow_inputs["flows"], *flow_inputs["feat4"], *flow_inputs["feat8"], *flow_inputs["fnet"])
         with self._guard():
-            return self._forward(img_xs, coords, t, ds, aux_outputs, frame_cache)
+            return self._forward(img_xs, coords, t, ds, aux_outputs, frame_cache, flow_inputs)
 
-    def _forward(self, img_xs, coords, t, ds, aux_outputs, frame_cache):
+    def _forward(self, img_xs, coords, t, ds, aux_outputs, frame_cache, flow_inputs=None):
         B, _, _, Hf, Wf = img_xs.shape
         T, _, _, Hc, Wc, _ = coords.shape
         H, W = (Hf, Wf) if not ds else (int(Hf * ds), int(Wf * ds))
-        nbytes = self.workspace_bytes(B, Hf, Wf, T, ds, Hc, Wc)
+        nbytes = self.workspace_bytes(B, Hf, Wf, T, ds, Hc, Wc, from_flow=flow_inputs is not None)
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         E = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
         out = {"imgt_pred": E(T, B, 3, Hf, Wf)}
+        if flow_inputs is not None:
+            fi = flow_inputs
+            assert tuple(fi["flows"].shape) == (B, 2, 2, H, W), (tuple(fi["flows"].shape), (B, 2, 2, H, W))
+            for j in range(2):
+                assert tuple(fi["feat4"][j].shape) == (B, 128, H // 4, W // 4) and tuple(fi["feat8"][j].shape) == (B, 256, H // 8, W // 8)
+                assert tuple(fi["fnet"][j].shape) == (B, 256, H // 8, W // 8)
         if aux_outputs:
             out.update(
                 img_warp_4=E(T, B, 3, H, W), flowt0_1=E(T, B, 3, 2, Hf, Wf), flowt1_1=E(T, B, 3, 2, Hf, Wf),
@@ -150,8 +170,16 @@ class EngineHandle:
             assert buf.dtype == torch.uint8 and buf.is_contiguous() and buf.device == self.device
             self.lib.check(self.lib.dll.gimmvfi_set_frame_cache(self._h, C.c_void_p(buf.data_ptr()), buf.numel(), int(load), int(store)), self._h)
         try:
-            self.lib.check(self.lib.dll.gimmvfi_forward(self._h, C.byref(p), C.byref(io), C.c_void_p(self._ws.data_ptr()),
-                                                        self._ws.numel(), C.c_void_p(stream)), self._h)
+            if flow_inputs is not None:
+                f = FlowInputs()
+                f.flows = flow_inputs["flows"].data_ptr()
+                for j in range(2):
+                    f.feat4[j], f.feat8[j], f.fnet[j] = (flow_inputs[k][j].data_ptr() for k in ("feat4", "feat8", "fnet"))
+                self.lib.check(self.lib.dll.gimmvfi_forward_from_flow(self._h, C.byref(p), C.byref(io), C.byref(f), C.c_void_p(self._ws.data_ptr()),
+                                                                      self._ws.numel(), C.c_void_p(stream)), self._h)
+            else:
+                self.lib.check(self.lib.dll.gimmvfi_forward(self._h, C.byref(p), C.byref(io), C.c_void_p(self._ws.data_ptr()),
+                                                            self._ws.numel(), C.c_void_p(stream)), self._h)
         finally:
             if frame_cache is not None:
                 self.lib.check(self.lib.dll.gimmvfi_set_frame_cache(self._h, None, 0, 0, 0), self._h)

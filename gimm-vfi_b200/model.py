@@ -196,4 +196,8 @@ def create_model(config, ema: bool = False):
         from .gimm import GIMM
 
         return GIMM(config), None
-    raise ValueError("%s is not built in gimmvfi_b200 (gimmvfi_r and gimm; see DESIGN.md scope)" % model_type)
+    if model_type == "gimmvfi_f":   # boundary + native synthesis half; the FlowFormer estimator is external (model_f.py)
+        from .model_f import GIMMVFI_F
+
+        return GIMMVFI_F(config), None
+    raise ValueError("%s is not built in gimmvfi_b200 (gimmvfi_r, gimmvfi_f, gimm; see DESIGN.md scope)" % model_type)

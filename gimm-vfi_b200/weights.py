@@ -9,7 +9,7 @@ import math
 
 import torch
 
-from .arch import param_spec_r
+from .arch import param_spec_f, param_spec_r
 
 
 def random_state_dict(seed: int = 0) -> dict:
@@ -61,4 +61,26 @@ def random_state_dict(seed: int = 0) -> dict:
     for key in list(sd):
         if ".norm3." in key:
             sd[key.replace(".norm3.", ".downsample.1.")] = sd[key]
+    return sd
+
+
+def random_state_dict_f(seed: int = 0, flow_estimator: dict = None) -> dict:
+    """Seeded GIMM-VFI-F state_dict: the decoder / GIMM half takes the SAME tensors as random_state_dict(seed) (identical layout,
+    arch.param_spec_f), `flow_estimator.*` (FlowFormer) comes from the caller (e.g. a reference module's own init) or a small seeded
+    normal init — the native engine does not consume those (the flow estimator is external, model_f.py)."""
+    r = random_state_dict(seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    sd = {}
+    for key, shape, dt in param_spec_f():
+        if key.startswith("flow_estimator."):
+            if flow_estimator is not None:
+                t = flow_estimator[key].detach().clone()
+            elif dt == "int64":
+                t = torch.zeros(shape, dtype=torch.int64)
+            else:
+                t = 0.02 * torch.randn(shape, generator=g)
+            assert tuple(t.shape) == tuple(shape), key
+            sd[key] = t
+        else:
+            sd[key] = r[key]
     return sd

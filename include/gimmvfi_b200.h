@@ -76,6 +76,24 @@ int gimmvfi_finalize_weights(gimmvfi_engine* e);
 int gimmvfi_plan(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes);
 int gimmvfi_forward(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_io* io, void* workspace, size_t workspace_bytes,
                     void* cuda_stream);
+/* ---- GIMM-VFI-F (gimmvfi_f.py): everything downstream of the flow estimator ----
+ * GIMMVFI_F.forward = FlowFormer (cal_bidirection_flow, gimmvfi_f.py:114-138) + exactly the GIMM / synthesis stages of GIMM-VFI-R
+ * without the feature projections.  Those stages run natively on the outputs of an EXTERNAL estimator, given in the reference's
+ * NCHW layouts at the network resolution H x W (= Hf x Wf, or floor(Hf*ds) x floor(Wf*ds)):                                      */
+typedef struct gimmvfi_flow_inputs {
+  const float* flows;      /* (B,2,2,H,W)       [f01 | f10] on dim 2 = `ori_flows` of cal_bidirection_flow        gimmvfi_f.py:127 */
+  const float* feat4[2];   /* (B,128,H/4,W/4)   features0[0], features1[0]  (context-encoder stage 1)       encoders.py:22-48 */
+  const float* feat8[2];   /* (B,256,H/8,W/8)   features0[1], features1[1]  (context-encoder stage 2)                         */
+  const float* fnet[2];    /* (B,256,H/8,W/8)   fnet0, fnet1 -> BidirCorrBlock                               gimmvfi_f.py:121 */
+} gimmvfi_flow_inputs;
+/* Weights: the GIMM-VFI-F state_dict minus flow_estimator.* (gimmvfi_load_weight each, then this instead of gimmvfi_finalize_weights).
+ * A full GIMM-VFI-R engine (gimmvfi_finalize_weights) accepts gimmvfi_forward_from_flow as well (its RAFT is then skipped). */
+int gimmvfi_finalize_weights_synthesis(gimmvfi_engine* e);
+int gimmvfi_plan_from_flow(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes);
+/* io->raft_flow (optional) receives a copy of `flows` (the reference returns them as "raft_flow", gimmvfi_f.py:382). */
+int gimmvfi_forward_from_flow(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_io* io, const gimmvfi_flow_inputs* fin,
+                              void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* ---- GIMM standalone: GIMM.forward (gimm.py:129-214), the motion-modelling network alone ----
  * Weights: either the full GIMM-VFI-R state_dict (gimmvfi_finalize_weights) or a GIMM checkpoint holding only gimm.py's module
  * tree (cnn_encoder.*, res_conv.*, hyponet.*, g_filter, alpha_v, alpha_fe) followed by gimmvfi_finalize_weights_gimm.

@@ -73,6 +73,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   }
 }
 
+bool corr_volume_tc_wants_f16_planes() { return false; }   // the emulation takes the TF32 hi / lo planes (same 22-bit values)
 void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split) {
   (void)zero_bias;
   if (cx.dry) return;

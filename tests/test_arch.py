@@ -43,3 +43,18 @@ def test_gimm_state_dict_matches_reference_dump():
     assert list(sd.keys()) == [k for k, _ in spec]
     assert all(list(sd[k].shape) == s for k, s in spec)
     m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+
+
+def test_param_spec_f_matches_reference_dump():
+    """GIMM-VFI-F: the packaged 639-key table == the dump of the reference GIMMVFI_F module (oracle/make_golden_f.py); the
+    synthesis half is the GIMM-VFI-R layout without the three feature projections."""
+    import json, os
+    from conftest import GOLDEN_DIR
+    from gimmvfi_b200.arch import R_ONLY_PREFIXES, param_spec_f, param_spec_r
+
+    ref = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_spec_f.json")))
+    mine = param_spec_f()
+    assert len(mine) == len(ref) == 639
+    assert [[k, list(s), d] for k, s, d in mine] == ref
+    shared = [k for k, _, _ in param_spec_r() if not k.startswith(R_ONLY_PREFIXES)]
+    assert sorted(k for k, _, _ in mine if not k.startswith("flow_estimator.")) == sorted(shared)

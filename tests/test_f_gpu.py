@@ -1,0 +1,87 @@
+"""GIMM-VFI-F (gimmvfi_f.py): the boundary class and the natively-run half — everything downstream of the flow estimator — against
+fixtures produced by the UNMODIFIED reference GIMMVFI_F (oracle/make_golden_f.py).  The fixtures carry the reference FlowFormer's
+outputs (flows, context features, fnet maps); `forward_from_flow` consumes them exactly where the reference's forward does."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from gimmvfi_b200.model_f import GIMMVFI_F
+from gimmvfi_b200.synth import synth_batch
+from gimmvfi_b200.weights import random_state_dict_f
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+with open(os.path.join(GOLDEN_DIR, "manifest_f.json")) as _f:
+    MANIFEST = json.load(_f)
+
+
+def flow_inputs_of(g, dev):
+    T = lambda k: torch.from_numpy(g[k]).to(dev)
+    return dict(flows=T("flows"), feat4=[T("feat4_0"), T("feat4_1")], feat8=[T("feat8_0"), T("feat8_1")], fnet=[T("fnet_0"), T("fnet_1")])
+
+
+@pytest.fixture(scope="module")
+def model():
+    m = GIMMVFI_F(seed=0).to(DEV).eval()
+    m.load_state_dict(random_state_dict_f(0), strict=True)
+    return m
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST))
+@pytest.mark.parametrize("mode", [3, 0], ids=["default", "fp32"])
+def test_f_synthesis_matches_reference(name, mode, model):
+    meta = MANIFEST[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    B, H, W, ts, ds = meta["B"], meta["H"], meta["W"], meta["timesteps"], meta["ds_factor"]
+    xs = synth_batch(B, H, W, seed=meta["input_seed"]).to(DEV)
+    ratio = 1.0 if ds is None else ds
+    coord = [(model.sample_coord_input(B, (H, W), [t], device=DEV, upsample_ratio=ratio), None) for t in ts]
+    tt = [t * torch.ones(B, device=DEV) for t in ts]
+    model.tensor_cores = mode
+    out = model(xs, coord, t=tt, ds_factor=ds, flow_inputs=flow_inputs_of(g, DEV))
+    torch.cuda.synchronize()
+    tol = 1e-3 if mode else 2e-5
+    assert torch.equal(out["raft_flow"].cpu(), torch.from_numpy(g["raft_flow"]))   # the estimator's flows are passed through
+    for i in range(len(ts)):
+        d = (out["imgt_pred"][i].cpu() - torch.from_numpy(g["imgt_pred_%d" % i])).abs()
+        print(name, "mode", mode, "imgt_pred[%d] max %.3e rmse %.3e" % (i, d.max().item(), d.pow(2).mean().sqrt().item()))
+        assert d.max().item() <= tol
+        w4 = (out["other_pred"][i][0].cpu() - torch.from_numpy(g["img_warp_4_%d" % i])).abs().max().item()
+        assert w4 <= tol
+        nin = (out["ninrflow"][i].cpu() - torch.from_numpy(g["ninrflow_%d" % i])).abs().max().item()
+        assert nin <= (2e-5 if mode else 2e-6), nin   # HypoNet output: fp32-class in every mode
+
+
+def test_f_boundary(model):
+    """639-key state_dict (strict), honest failure without a flow backend, and the backend hook with the reference's signature."""
+    sd = model.state_dict()
+    with open(os.path.join(GOLDEN_DIR, "state_dict_spec_f.json")) as f:
+        spec = json.load(f)
+    assert list(sd.keys()) == [k for k, _, _ in spec] and all(list(sd[k].shape) == s for k, s, _ in spec)
+    name = "f_128x160_t0.5"
+    meta, g = MANIFEST[name], np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    xs = synth_batch(1, meta["H"], meta["W"], seed=meta["input_seed"]).to(DEV)
+    coord = [(model.sample_coord_input(1, (meta["H"], meta["W"]), [0.5], device=DEV), None)]
+    tt = [0.5 * torch.ones(1, device=DEV)]
+    model.flow_backend = None
+    with pytest.raises(NotImplementedError):
+        model(xs, coord, t=tt)
+    fi = flow_inputs_of(g, DEV)
+    calls = []
+
+    def backend(im0, im1):   # FlowFormer.forward(im0, im1, return_feat=True) -> (flow_predictions, cfeat, ffeat)
+        j = len(calls)
+        calls.append((float(im0.max()), float(im1.max())))
+        return [fi["flows"][:, :, j]], [fi["feat4"][j], fi["feat8"][j]], fi["fnet"][j]
+
+    model.flow_backend = backend
+    model.tensor_cores = 3
+    out = model(xs, coord, t=tt)
+    model.flow_backend = None
+    assert len(calls) == 2 and calls[0][0] > 1.5   # the backend sees 0..255 frames (gimmvfi_f.py:320-328)
+    assert (out["imgt_pred"][0].cpu() - torch.from_numpy(g["imgt_pred_0"])).abs().max().item() <= 1e-3

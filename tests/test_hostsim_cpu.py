@@ -136,3 +136,34 @@ def test_hostsim_tensor_core_modes_match_oracle(eng, weights0, mode):
     print("hostsim mode", mode, "imgt_pred max %.3e raft_flow max %.3e" % (d_img, d_raft))
     assert d_img <= 1e-3
     assert d_raft <= (2e-3 if mode >= 2 else 5e-4)
+
+
+def test_hostsim_f_synthesis_from_flow_matches_reference():
+    """GIMM-VFI-F: the engine's forward_from_flow (everything downstream of the flow estimator) on the CPU build of the kernels,
+    fed with the reference FlowFormer's outputs from the fixture, against the UNMODIFIED reference GIMMVFI_F's frame."""
+    import json, os, sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import harness
+    from conftest import GOLDEN_DIR
+    from gimmvfi_b200._lib import GimmvfiError
+    from gimmvfi_b200.weights import random_state_dict_f
+
+    torch.set_grad_enabled(False)
+    name = "f_128x160_t0.5"
+    meta = json.load(open(os.path.join(GOLDEN_DIR, "manifest_f.json")))[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    e = harness.hostsim_engine()
+    e.load_state_dict(random_state_dict_f(0), synthesis_only=True)
+    B, H, W = meta["B"], meta["H"], meta["W"]
+    xs = synth_batch(B, H, W, seed=meta["input_seed"])
+    coords = torch.stack([O.sample_coord_input(B, (H, W), [t], 1.0) for t in meta["timesteps"]], 0).contiguous()
+    tt = torch.stack([t * torch.ones(B) for t in meta["timesteps"]], 0).contiguous()
+    T = lambda k: torch.from_numpy(g[k])
+    fi = dict(flows=T("flows"), feat4=[T("feat4_0"), T("feat4_1")], feat8=[T("feat8_0"), T("feat8_1")], fnet=[T("fnet_0"), T("fnet_1")])
+    out = e.forward(xs, coords, tt, None, flow_inputs=fi)
+    d = (out["imgt_pred"][0] - T("imgt_pred_0")).abs().max().item()
+    print("hostsim F synthesis: imgt_pred max %.3e" % d)
+    assert d <= 2e-5
+    with pytest.raises(GimmvfiError):   # no flow estimator weights in this engine
+        e.forward(xs, coords, tt, None)
