@@ -53,7 +53,7 @@ EXPORTS = [
     "gimmvfi_get_tap", "gimmvfi_build_info", "gimmvfi_set_profile", "gimmvfi_profile_json",
     "gimmvfi_set_tensor_cores", "gimmvfi_finalize_weights_gimm", "gimmvfi_finalize_weights_synthesis", "gimmvfi_plan_from_flow", "gimmvfi_forward_from_flow", "gimmvfi_gimm_plan", "gimmvfi_gimm_forward", "gimmvfi_frame_cache_bytes", "gimmvfi_set_frame_cache", "gimmvfi_op_conv2d_tc", "gimmvfi_op_conv2d_tc_f16", "gimmvfi_op_conv2d_tc_strided", "gimmvfi_op_frames_u8_to_padded_f32", "gimmvfi_op_pred_to_u8", "gimmvfi_op_softsplat", "gimmvfi_op_backwarp", "gimmvfi_op_resize",
     "gimmvfi_op_corr_volume", "gimmvfi_op_corr_volume_tc", "gimmvfi_op_corr_pool", "gimmvfi_op_corr_pool_pyramid", "gimmvfi_op_corr_lookup", "gimmvfi_op_conv2d",
-    "gimmvfi_instnorm_scratch_floats", "gimmvfi_op_hyponet", "gimmvfi_op_instnorm", "gimmvfi_op_convex_upsample", "gimmvfi_op_pixel_shuffle",
+    "gimmvfi_instnorm_scratch_floats", "gimmvfi_op_hyponet", "gimmvfi_op_conv2d_halo", "gimmvfi_op_instnorm", "gimmvfi_op_convex_upsample", "gimmvfi_op_pixel_shuffle",
 ]
 
 
@@ -116,6 +116,7 @@ class Lib:
         d.gimmvfi_op_corr_pool_pyramid.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
         d.gimmvfi_op_corr_lookup.argtypes = [C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32), PV, PV, vp]
         d.gimmvfi_op_conv2d.argtypes = [PV, PV, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, PV, PV, vp]
+        d.gimmvfi_op_conv2d_halo.argtypes = [PV, vp, vp, vp, i32, i32, i32, vp, PV, i32, vp, i32, i32, PV, vp]
         d.gimmvfi_op_hyponet.argtypes = [vp, PV, vp, PV, i32, vp]
         d.gimmvfi_instnorm_scratch_floats.argtypes = [i32, i32]
         d.gimmvfi_instnorm_scratch_floats.restype = i64

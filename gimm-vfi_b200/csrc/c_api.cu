@@ -264,6 +264,26 @@ int gimmvfi_op_conv2d_tc_f16(const gimmvfi_view* in0, const gimmvfi_view* in1, c
 #endif
   })
 }
+int gimmvfi_op_conv2d_halo(const gimmvfi_view* in0, const void* w_tc_h, const float* w_tc, const float* bias, int cin, int cout, int act1,
+                           const float* slope1, const gimmvfi_view* residual, int act2, const float* slope2, int half_mask, int prepadded,
+                           const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+#ifdef GV_HOSTSIM
+    throw std::runtime_error("conv2d_halo is a tcgen05 kernel; not available in the host simulation");
+#else
+    Ctx cx = op_ctx(stream);
+    ConvW w; w.b = bias; w.cin = cin; w.cout = cout; w.kh = 3; w.kw = 3; w.w_tc = w_tc; w.has_lo = true;
+    w.cout_pad = tc_cout_pad(cout); w.cin_pad = (cin + 31) & ~31; w.w_tc_h = w_tc_h; w.cin_pad_h = (cin + 63) & ~63;
+    ConvGeom g; g.stride = 1; g.ph = prepadded ? 0 : 1; g.pw = prepadded ? 0 : 1; g.loose_w = prepadded ? 1 : 0;
+    TV a0 = to_tv(in0); TV r = to_tv(residual); TV o = to_tv(out);
+    a0.f16 = half_mask & 1; o.f16 = (half_mask >> 1) & 1; if (r.p) r.f16 = (half_mask >> 2) & 1;
+    ConvEpi ep; ep.act1 = act1; ep.slope1 = slope1; ep.res = r; ep.act2 = act2; ep.slope2 = slope2;
+    if (!conv2d_halo_supported(a0, TV(), w, g, ep, o)) throw std::runtime_error("conv2d_halo: unsupported configuration");
+    conv2d_halo(cx, a0, w, g, ep, o);
+#endif
+  })
+}
 int gimmvfi_op_hyponet(gimmvfi_engine* e, const gimmvfi_view* latent, const float* coords, const gimmvfi_view* out, int fp32_class, void* stream) {
   GV_TRY(e, {
     if (!e->eng.finalized() || !e->eng.hyponet_blob(fp32_class != 0)) throw std::runtime_error("hyponet: finalize_weights() first");

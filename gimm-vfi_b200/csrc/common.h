@@ -333,6 +333,10 @@ bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const Con
 void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split);
 bool corr_volume_tc_wants_f16_planes();   // split mode: true -> fb_planes must come from split_planes_f16 (3xF16 form), else split_planes
+// conv_halo.cu (sm_100a): 3x3 stride-1 convolutions of K-poor layers (cin <= 32 fp32 / 64 half, cout <= 64) with the activation tile
+// + halo loaded once and the 9 taps as shifted UMMA views of it
+bool conv2d_halo_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out);
+void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out);
 // hyponet.cu (sm_100a; the host simulation emulates its arithmetic): the whole HypoNet MLP in one kernel
 bool hyponet_fused_supported(const TV& lat, const TV& out);
 void hyponet_fused(Ctx& cx, const TV& lat /*n,h,w,32*/, const float* coords /*n*h*w x (t,y,x)*/, const void* blob /*hypo:: layout*/, const TV& out /*2 ch*/);

@@ -391,6 +391,13 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeo
   }
 #endif
   const bool any_f16 = in0.f16 || in1.f16 || out.f16 || e.res.f16;
+#ifndef GV_HOSTSIM
+  // K-poor 3x3 layers: halo tile loaded once, taps as shifted operand views (same TF32 / half operand arithmetic as conv2d_tc)
+  if (cx.tc && !(cx.tc_split && !any_f16) && conv2d_halo_supported(in0, in1, w, g, e, out) && conv2d_tc_supported(in0, in1, w, g, e, out, false)) {
+    conv2d_halo(cx, in0, w, g, e, out);
+    return;
+  }
+#endif
   if (cx.tc && conv2d_tc_supported(in0, in1, w, g, e, out, cx.tc_split && !any_f16)) { conv2d_tc(cx, in0, in1, w, g, e, out, cx.tc_split && !any_f16); return; }
   if (any_f16) throw std::runtime_error("conv2d: half-precision tensors are only handled by the tensor-core path (layer not eligible)");
   if (e.split_c) throw std::runtime_error("conv2d: merged two-output convolutions exist on the tensor-core path only");

@@ -21,6 +21,12 @@ namespace gv {
 namespace tc {
 #include "tc_ptx.cuh"
 
+// constants live in SHARED memory: explicit ld.shared (a generic-pointer load goes through the global / local queue and throttles)
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
 
 struct HypoParams {
@@ -30,7 +36,7 @@ struct HypoParams {
 
 // one epilogue pass over the 128 accumulator columns of this thread's pixel row: z = acc + bias (+ affine) -> sin -> half -> smem
 template <bool FIRST>
-__device__ __forceinline__ void hypo_epilogue(uint32_t my_t, uint8_t* abuf, int row, const float* bias, const float* aff, float ct, float cy, float cx) {
+__device__ __forceinline__ void hypo_epilogue(uint32_t my_t, uint8_t* abuf, int row, uint32_t bias_s, uint32_t aff_s, float ct, float cy, float cx) {
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
     uint32_t v[32];
@@ -40,11 +46,10 @@ __device__ __forceinline__ void hypo_epilogue(uint32_t my_t, uint8_t* abuf, int 
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const int c = ch * 32 + j;
-      const float4 b = *reinterpret_cast<const float4*>(bias + c);
+      const float4 b = lds_f4(bias_s + 4u * c);
       float z0 = __uint_as_float(v[j]) + b.x, z1 = __uint_as_float(v[j + 1]) + b.y, z2 = __uint_as_float(v[j + 2]) + b.z, z3 = __uint_as_float(v[j + 3]) + b.w;
       if (FIRST) {   // (t, y, x) . W0[32..34, :] in fp32
-        const float4 wt = *reinterpret_cast<const float4*>(aff + c), wy = *reinterpret_cast<const float4*>(aff + 128 + c),
-                     wx = *reinterpret_cast<const float4*>(aff + 256 + c);
+        const float4 wt = lds_f4(aff_s + 4u * c), wy = lds_f4(aff_s + 4u * (128 + c)), wx = lds_f4(aff_s + 4u * (256 + c));
         z0 = fmaf(ct, wt.x, fmaf(cy, wy.x, fmaf(cx, wx.x, z0))); z1 = fmaf(ct, wt.y, fmaf(cy, wy.y, fmaf(cx, wx.y, z1)));
         z2 = fmaf(ct, wt.z, fmaf(cy, wy.z, fmaf(cx, wx.z, z2))); z3 = fmaf(ct, wt.w, fmaf(cy, wy.w, fmaf(cx, wx.w, z3)));
       }
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(128 * HN_GROUPS, 1) hyponet_fused_kernel(const
   const uint32_t id_f16 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t id_f16_n16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t a_s = smem_u32(abuf), w_s = smem_u32(wsm);
-  const float* aff = reinterpret_cast<const float*>(wsm + HN_AFF);
+  const uint32_t aff_s = w_s + HN_AFF;
 
   for (int tile = blockIdx.x * HN_GROUPS + g; tile < p.num_tiles; tile += gridDim.x * HN_GROUPS) {
     const long long pix = (long long)tile * 128 + row;
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(128 * HN_GROUPS, 1) hyponet_fused_kernel(const
     ph_in ^= 1;
     mbar_wait(bar_mma, ph_mma, SPIN); ph_mma ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    hypo_epilogue<true>(my_t, abuf, row, aff + 384, aff, ct, cy, cx);
+    hypo_epilogue<true>(my_t, abuf, row, aff_s + 4u * 384, aff_s, ct, cy, cx);
 #pragma unroll 1
     for (int l = 1; l <= 4; ++l) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // activations (generic proxy) -> visible to the MMAs
@@ -141,15 +146,15 @@ __global__ void __launch_bounds__(128 * HN_GROUPS, 1) hyponet_fused_kernel(const
       mbar_wait(bar_mma, ph_mma, SPIN); ph_mma ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (l < 4) {
-        hypo_epilogue<false>(my_t, abuf, row, reinterpret_cast<const float*>(wsm + HN_B1) + (l - 1) * 128, aff, 0.f, 0.f, 0.f);
+        hypo_epilogue<false>(my_t, abuf, row, w_s + HN_B1 + (l - 1) * 512, aff_s, 0.f, 0.f, 0.f);
       } else {
         uint32_t v[16];
         tmem_ld16(my_t, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float* b4 = reinterpret_cast<const float*>(wsm + HN_B4);
+        const float4 b4 = lds_f4(w_s + HN_B4);
         if (valid) {
           float* o = p.out + pix * p.out_ld;
-          o[0] = __uint_as_float(v[0]) + b4[0]; o[1] = __uint_as_float(v[1]) + b4[1];
+          o[0] = __uint_as_float(v[0]) + b4.x; o[1] = __uint_as_float(v[1]) + b4.y;
         }
       }
     }
@@ -217,9 +222,7 @@ __global__ void __launch_bounds__(128 * H3_GROUPS, 1) hyponet_fused3_kernel(cons
   const int SPIN = p.spin_limit;
   const uint32_t id_f16 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t w_s = smem_u32(smem);
-  const float* W0 = reinterpret_cast<const float*>(smem + hypo3::W0A);
-  const float* B13 = reinterpret_cast<const float*>(smem + hypo3::B13);
-  const float* W4 = reinterpret_cast<const float*>(smem + hypo3::W4);
+  const uint32_t W0s = w_s + hypo3::W0A, B13s = w_s + hypo3::B13, W4s = w_s + hypo3::W4;
   const float inv_scale = 1.0f / hypo3::W_SCALE;
 
   for (int tile = blockIdx.x * H3_GROUPS + g; tile < p.num_tiles; tile += gridDim.x * H3_GROUPS) {
@@ -241,14 +244,14 @@ __global__ void __launch_bounds__(128 * H3_GROUPS, 1) hyponet_fused3_kernel(cons
       float z[32];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(W0 + 35 * 128 + ch * 32 + j);
+        const float4 b = lds_f4(W0s + 4u * (35 * 128 + ch * 32 + j));
         z[j] = b.x; z[j + 1] = b.y; z[j + 2] = b.z; z[j + 3] = b.w;
       }
 #pragma unroll
       for (int k = 0; k < 35; ++k) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 w = *reinterpret_cast<const float4*>(W0 + k * 128 + ch * 32 + j);
+          const float4 w = lds_f4(W0s + 4u * (k * 128 + ch * 32 + j));
           z[j] = fmaf(x[k], w.x, z[j]); z[j + 1] = fmaf(x[k], w.y, z[j + 1]); z[j + 2] = fmaf(x[k], w.z, z[j + 2]); z[j + 3] = fmaf(x[k], w.w, z[j + 3]);
         }
       }
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(128 * H3_GROUPS, 1) hyponet_fused3_kernel(cons
         float z[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(B13 + l * 128 + ch * 32 + j);
+          const float4 b = lds_f4(B13s + 4u * (l * 128 + ch * 32 + j));
           z[j] = __sinf(fmaf(__uint_as_float(v[j]), inv_scale, b.x)); z[j + 1] = __sinf(fmaf(__uint_as_float(v[j + 1]), inv_scale, b.y));
           z[j + 2] = __sinf(fmaf(__uint_as_float(v[j + 2]), inv_scale, b.z)); z[j + 3] = __sinf(fmaf(__uint_as_float(v[j + 3]), inv_scale, b.w));
         }
@@ -296,16 +299,16 @@ __global__ void __launch_bounds__(128 * H3_GROUPS, 1) hyponet_fused3_kernel(cons
         } else {   // layer 4 on the fly: o += h3 . W4
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float4 w = *reinterpret_cast<const float4*>(W4 + (ch * 32 + j) * 2);
+            const float4 w = lds_f4(W4s + 4u * ((ch * 32 + j) * 2));
             o0 = fmaf(z[j], w.x, o0); o1 = fmaf(z[j], w.y, o1); o0 = fmaf(z[j + 1], w.z, o0); o1 = fmaf(z[j + 1], w.w, o1);
           }
         }
       }
     }
     if (valid) {
-      const float* b4 = reinterpret_cast<const float*>(smem + hypo3::B4);
+      const float4 b4 = lds_f4(w_s + hypo3::B4);
       float* o = p.out + pix * p.out_ld;
-      o[0] = o0 + b4[0]; o[1] = o1 + b4[1];
+      o[0] = o0 + b4.x; o[1] = o1 + b4.y;
     }
     // (the next tile's layer-0 stores into A_hi / A_lo are ordered after this tile's last MMAs: every thread waited on their commit)
   }

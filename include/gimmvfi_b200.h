@@ -178,6 +178,12 @@ int gimmvfi_op_conv2d_tc_f16(const gimmvfi_view* in0, const gimmvfi_view* in1_or
                              const gimmvfi_view* residual_or_null, int act2, const float* slope2, int half_mask,
                              const gimmvfi_view* out, void* stream);
 /* nn.InstanceNorm2d + optional relu: raft/extractor.py:133-134; scratch >= gimmvfi_instnorm_scratch_floats */
+/* 3x3 stride-1 convolution of a K-poor layer (cin <= 32 fp32 or <= 64 half, cout <= 64): halo tile loaded once, the 9 taps as shifted
+ * UMMA operand views (csrc/conv_halo.cu).  Weight packing as gimmvfi_op_conv2d_tc (plane 0) / gimmvfi_op_conv2d_tc_f16; half_mask bit 0:
+ * input half, bit 1: output half, bit 2: residual half; prepadded != 0: `in0` is (h+2, w+2) and carries its own padding (valid conv). */
+int gimmvfi_op_conv2d_halo(const gimmvfi_view* in0, const void* w_tc_h_or_null, const float* w_tc, const float* bias, int cin, int cout,
+                           int act1, const float* slope1, const gimmvfi_view* residual_or_null, int act2, const float* slope2,
+                           int half_mask, int prepadded, const gimmvfi_view* out, void* stream);
 /* HypoNet.forward (modules/hyponet.py:71-146) as ONE fused tcgen05 kernel with the engine's loaded weights: latent (n,h,w,32),
  * coords n*h*w x (t,y,x) as the caller's coordinate tensor holds them -> out (n,h,w,2) = normalised flow (output_bias included).
  * fp32_class != 0: the default kernel of the forward pass (fp16 hi/lo operand pairs, fp32-class result); 0: TF32 / half operands */

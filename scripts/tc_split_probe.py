@@ -21,11 +21,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     if stall is not None:
         os.environ["GIMMVFI_TC_STALL_BUF"] = str(stall.data_ptr())
     for (cin, cout, kh, kw, H, W, n) in SHAPES:
-        for split in ((0,) if os.environ.get("PROBE_BIG") else (0, 1)):
+        for split in ((0,) if os.environ.get("PROBE_BIG") else (0, 1, 2)):   # 0 plain TF32, 1 3xTF32, 2 3xF16
             f16 = bool(os.environ.get("PROBE_F16"))
             x = torch.randn(n, H, W, cin, device="cuda")
             w = torch.randn(cout, cin, kh, kw, device="cuda") / (cin * kh * kw) ** 0.5
             pw = K.pack_weight_tc(w)
+            pws, wsc = K.pack_weight_tc_split_f16(w) if split == 2 else (None, 1.0)
             out = torch.empty(n, H, W, cout, device="cuda")
             if f16:
                 x = x.half(); out = out.half(); pwh = K.pack_weight_tc_f16(w)
@@ -38,7 +39,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
                                                                cin, cout, kh, kw, 0, None, None, 0, None, 3, C.byref(view_of(out)), s))
                     return
                 lib.check(lib.dll.gimmvfi_op_conv2d_tc(C.byref(view_of(x)), None, C.c_void_p(pw.data_ptr()), C.c_void_p(bb.data_ptr()), cin, cout, kh, kw,
-                                                       0, None, None, 0, None, None, None, None, split, C.byref(view_of(out)), s))
+                                                       0, None, None, 0, None, None, None, None, int(split != 0), C.byref(view_of(out)),
+                                                       C.c_void_p(pws.data_ptr()) if pws is not None else None, wsc, s))
             for _ in range(3):
                 call()
             torch.cuda.synchronize()
@@ -48,7 +50,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
                 call()
             e1.record()
             torch.cuda.synchronize()
-            res.append("%s%d>%d k%dx%d: %.3f" % ("S " if split else "P ", cin, cout, kh, kw, e0.elapsed_time(e1) / 20))
+            res.append("%s%d>%d k%dx%d: %.3f" % (["P ", "S ", "S16 "][split], cin, cout, kh, kw, e0.elapsed_time(e1) / 20))
             if stall is not None:
                 stall.zero_(); call(); torch.cuda.synchronize()
                 m = stall.view(148, 16).double().mean(0).tolist()

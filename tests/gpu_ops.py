@@ -216,3 +216,24 @@ def conv2d_tc_f16(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slop
     lib.check(lib.dll.gimmvfi_op_conv2d_tc_f16(V(x_nhwc), V(x1_nhwc), P(pw_h), P(pw), P(bb), cin, cout, kh, kw, act1, P(slope1), V(residual), act2,
                                                P(slope2), mask, V(out), _stream(out)))
     return out
+
+
+def conv2d_halo(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2=None, out_half=False, prepadded=False, lib=None):
+    """3x3 K-poor conv through csrc/conv_halo.cu; x (and residual) may be torch.float16 NHWC tensors"""
+    lib = lib or default_lib()
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    in_half = x_nhwc.dtype == torch.float16
+    pw_h = pack_weight_tc_f16(w) if in_half else None
+    pw = pack_weight_tc(w)
+    bb = torch.zeros((tc_cout_pad(cout) + 31) // 32 * 32 + 128, device=w.device)
+    bb[:cout] = b
+    n, h, wd, _ = x_nhwc.shape
+    oh, ow = (h - 2, wd - 2) if prepadded else (h, wd)
+    out = torch.empty(n, oh, ow, cout, device=w.device, dtype=torch.float16 if out_half else torch.float32)
+    mask = (1 if in_half else 0) | (2 if out_half else 0) | (4 if (residual is not None and residual.dtype == torch.float16) else 0)
+    V = lambda t: C.byref(view_of(t)) if t is not None else None
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    lib.check(lib.dll.gimmvfi_op_conv2d_halo(V(x_nhwc), P(pw_h), P(pw), P(bb), cin, cout, act1, P(slope1), V(residual), act2, P(slope2), mask,
+                                             int(prepadded), V(out), _stream(out)))
+    return out

@@ -305,3 +305,55 @@ def test_corr_volume_tc(hw, split):
     err = (vol - ref).abs().max().item()
     print("corr_volume_tc", hw, "split", split, "err %.3e" % err, "absmax %.2f" % ref.abs().max().item())
     assert err <= (3e-5 if split else 2e-4)
+
+
+HALO_CASES = [
+    # cin, cout, H, W, n, act1, residual, half
+    (32, 32, 48, 40, 2, 2, False, False),     # the 32 -> 32 full-resolution layers (LeakyReLU)
+    (32, 32, 50, 37, 1, 0, True, False),      # ragged tiles (8 x 16), residual epilogue
+    (16, 32, 32, 24, 1, 2, False, False),     # cin 16: K block zero-filled by TMA
+    (32, 64, 32, 24, 2, 3, False, False),     # BN = 64, PReLU
+    (32, 16, 34, 26, 1, 0, False, False),     # cout 16
+    (64, 64, 32, 24, 1, 3, False, True),      # half-precision storage: 64 channels = one K block
+    (64, 64, 35, 20, 1, 0, True, True),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv2d_halo(case):
+    """csrc/conv_halo.cu: the tile + halo is loaded once and every tap is an MMA on a shifted view (UMMA base offset).  Strict
+    reference = fp64 convolution of the operands as the tensor core sees them (TF32-truncated activations / RN weights, or halves)."""
+    cin, cout, H, W, n, act1, use_res, half = case
+    x = rnd(n, cin, H, W, seed=1)
+    w = rnd(cout, cin, 3, 3, seed=2, scale=1.0 / (cin * 9) ** 0.5)
+    b = rnd(cout, seed=3, scale=0.1)
+    slope = (0.25 + 0.1 * rnd(cout, seed=4)) if act1 == 3 else None
+    res = rnd(n, cout, H, W, seed=5) if use_res else None
+    xn = K.nhwc(x)
+    if half:
+        got = K.conv2d_halo(xn.half(), w, b, act1, slope, residual=K.nhwc(res).half() if use_res else None, out_half=True)
+        ref = F.conv2d(x.half().double(), w.half().double(), b.double(), padding=1)
+    else:
+        got = K.conv2d_halo(xn, w, b, act1, slope, residual=K.nhwc(res) if use_res else None)
+        ref = F.conv2d(K.tf32_trunc(x).double(), K.tf32_rn(w).double(), b.double(), padding=1)
+    f = {0: lambda v: v, 2: lambda v: F.leaky_relu(v, 0.1), 3: lambda v: F.prelu(v, slope.double())}[act1]
+    ref = f(ref)
+    if use_res:
+        ref = ref + (res.half().double() if half else res.double())
+    ref = ref.float()
+    err = (K.nchw(got.float()) - ref).abs().max().item()
+    tol = (1e-3 if half else 5e-5 + 2.0 ** -11) * max(1.0, ref.abs().max().item())   # store rounding: half / RN to TF32
+    print("halo case", case, "err %.3e (tol %.1e)" % (err, tol))
+    assert err <= tol
+
+
+def test_conv2d_halo_prepadded_matches_reflect():
+    """reflect-padded layers (cnn_encoder.7): valid convolution on a pre-padded buffer, tile origin without the -1 shift"""
+    x = rnd(1, 32, 40, 32, seed=1)
+    w = rnd(16, 32, 3, 3, seed=2, scale=0.06)
+    b = rnd(16, seed=3, scale=0.1)
+    xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    got = K.nchw(K.conv2d_halo(K.nhwc(xp), w, b, prepadded=True))
+    ref = F.conv2d(K.tf32_trunc(xp).double(), K.tf32_rn(w).double(), b.double()).float()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 5e-5 + 2.0 ** -11 * ref.abs().max().item()
