@@ -114,6 +114,8 @@ int gimmvfi_set_frame_cache(gimmvfi_engine* e, void* cache, size_t bytes, int lo
   GV_TRY(e, { e->eng.set_frame_cache(static_cast<float*>(cache), bytes, load != 0, store != 0); })
 }
 int gimmvfi_set_tensor_cores(gimmvfi_engine* e, int mode) { GV_TRY(e, { e->eng.set_tensor_cores(mode); }) }
+int gimmvfi_set_cuda_graph(gimmvfi_engine* e, int on) { GV_TRY(e, { e->eng.set_cuda_graph(on != 0); }) }
+int64_t gimmvfi_graph_replays(gimmvfi_engine* e) { return e->eng.graph_replays(); }
 int gimmvfi_set_profile(gimmvfi_engine* e, int on) { GV_TRY(e, { e->eng.set_profile(on != 0); }) }
 const char* gimmvfi_profile_json(gimmvfi_engine* e, void* stream) {
   try { e->prof_json = e->eng.profile_json((gvStream_t)stream); } catch (const std::exception& ex) { e->err = ex.what(); e->prof_json = "{}"; }

@@ -331,7 +331,7 @@ void conv2d(Ctx& cx, const TV& in0, const TV& in1 /*optional 2nd channel segment
 // conv_tc.cu (sm_100a tcgen05 / TMA path; not part of the host simulation)
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
-void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split);
+void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split, int n_targets = 0);
 bool corr_volume_tc_wants_f16_planes();   // split mode: true -> fb_planes must come from split_planes_f16 (3xF16 form), else split_planes
 // conv_halo.cu (sm_100a): 3x3 stride-1 convolutions of K-poor layers (cin <= 32 fp32 / 64 half, cout <= 64) with the activation tile
 // + halo loaded once and the 9 taps as shifted UMMA views of it
@@ -346,6 +346,7 @@ void split_planes(Ctx& cx, const TV& src, float* planes);  // [2][n*h*w][c]: rn_
 void split_planes_f16(Ctx& cx, const TV& src, void* planes);  // half [2][n*h*w][c]: rn_f16(x) and rn_f16(x - rn_f16(x))
 void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale);   // vol[n][i][j] = <fa[n,i], fb[n,j]> * scale
 void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w); // rows x (h*w) -> rows x (h/2*w/2)
+void avgpool2_features(Ctx& cx, const TV& src, const TV& dst);   // NHWC 2x2 average, floor semantics (F.avg_pool2d(x, 2, 2))
 void corr_pool_pyramid(Ctx& cx, const float* l0, float* l1, float* l2, float* l3, int64_t rows, int h, int w);
 struct CorrPyr { const float* lvl[4]; int h[4], w[4]; int64_t rows_per_sample; };
 void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords /*n,h,w,2 (x,y)*/, const TV& out /*324 ch*/);

@@ -6,10 +6,12 @@
 // per launch and the measured limiter (0.80 ms = 6 TB/s; 96 TFLOP/s; HBM floor 0.17 ms).
 //
 // How: output tile = 8 (x) x 16 (y) pixels, so the 8-row groups of the M = 128 operand are image rows.  ONE TMA box
-// {32 ch, 16 x, 18 y} lands the tile plus halo 128B-swizzled in shared memory with a row pitch of 16 pixels = 2048 bytes; tap
-// (ky, kx) is the UMMA descriptor whose start address is advanced by (ky * 16 + kx) pixel rows, stride between 8-row groups 2048 B,
-// "matrix base offset" = the start row's phase inside the 1024-byte swizzle pattern (kx).  Out-of-bounds box elements are
-// zero-filled = the convolution's zero padding.  The 9 weight tiles (<= 72 KB) stay resident in shared memory for the whole
+// {32 ch, P x, 18 y} lands the tile plus halo 128B-swizzled in shared memory with a row pitch of P pixels (P = 16: 2048 bytes, or
+// P = 10: 1280 bytes); tap (ky, kx) is the UMMA descriptor whose start address is advanced by (ky * P + kx) pixel rows, with the
+// stride between 8-row groups = P * 128 bytes.  The 128B swizzle is a function of the ABSOLUTE shared-memory address bits on both
+// the TMA write and the MMA read (measured: profiles/r02_halo_diag.log - every tap exact with the descriptor's "matrix base offset"
+// field left 0, garbage when it is set to the start row's phase), so a row-shifted start needs no further treatment.
+// Out-of-bounds box elements are zero-filled = the convolution's zero padding.  The 9 weight tiles (<= 72 KB) stay resident in shared memory for the whole
 // persistent CTA.  Per tile: 36 KB of TMA traffic instead of 144 KB (+ weights), 36 MMAs, no other shared-memory writes.
 //
 // Roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), 8 epilogue warps (two per TMEM lane quarter, each BN/2 columns).
@@ -32,18 +34,21 @@ constexpr int HL_STG_WARP_BYTES = 32 * HL_STG_PITCH * 4;
 constexpr int HL_MAX_STAGES = 4;
 
 struct HaloParams {
-  int tiles_x, tiles_y, n_img, H, W, cout, BN, stages, origin, f16_in, round_out, spin_limit;
+  int tiles_x, tiles_y, n_img, H, W, cout, BN, stages, origin, f16_in, round_out, spin_limit, dbg;
+  int copies3;      // 1: three x-shifted copies {K, 8 x, 18 y} of the tile (aligned descriptors only); 0: one {K, P x, 18 y} halo tile + shifted views
+  int pitch;        // P: pixels per halo row (16 or 10)
+  int halo_bytes;   // bytes of one pipeline stage (multiple of 1024)
   const float* bias; int act1; const float* slope1; int act2; const float* slope2;
   TV res, out;
 };
 
-__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes, int dbg) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)((saddr >> 7) & 7) << 49;   // matrix base offset: phase of the start row inside the 1024-byte swizzle pattern
+  if (dbg & 1) d |= (uint64_t)((saddr >> 7) & 7) << 49;   // experiment only: "matrix base offset" = start row phase -> WRONG results on sm_100a
   d |= (uint64_t)2 << 61;
   return d;
 }
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
   const int w_region = (w_bytes + 1023) & ~1023;
   uint8_t* wsm = smem;
   uint8_t* halo = smem + w_region;
-  float* stg_base = reinterpret_cast<float*>(halo + p.stages * HL_HALO_BYTES);
+  float* stg_base = reinterpret_cast<float*>(halo + p.stages * p.halo_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg_base) + 8 * HL_STG_WARP_BYTES);
   uint64_t* w_bar = bars;                         // weights landed
   uint64_t* full_bar = bars + 1;                  // [HL_MAX_STAGES]
@@ -96,8 +101,14 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int r = tile; const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
         mbar_wait(&empty_bar[stage], phase ^ 1, SPIN);
-        mbar_expect_tx(&full_bar[stage], (uint32_t)HL_HALO_BYTES);
-        tma_load_4d(halo + stage * HL_HALO_BYTES, &tmA, &full_bar[stage], 0, tx * HL_TW + p.origin, ty * HL_TH + p.origin, n);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)p.halo_bytes);
+        if (p.copies3) {   // copy kx = the 8-pixel-wide column of the tile shifted by kx: every tap's operand starts 1024-byte aligned
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            tma_load_4d(halo + stage * p.halo_bytes + kx * (HL_TW * HL_BH * 128), &tmA, &full_bar[stage], 0, tx * HL_TW + p.origin + kx, ty * HL_TH + p.origin, n);
+        } else {
+          tma_load_4d(halo + stage * p.halo_bytes, &tmA, &full_bar[stage], 0, tx * HL_TW + p.origin, ty * HL_TH + p.origin, n);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -112,11 +123,12 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
-        const uint32_t h_s = smem_u32(halo + stage * HL_HALO_BYTES), w_s = smem_u32(wsm);
+        const uint32_t h_s = smem_u32(halo + stage * p.halo_bytes), w_s = smem_u32(wsm);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap % 3;
-          const uint64_t ad = make_desc_sbo(h_s + (uint32_t)((ky * HL_BW + kx) * 128), HL_BW * 128);   // shifted view of the halo tile
+          const uint64_t ad = p.copies3 ? make_smem_desc(h_s + (uint32_t)(kx * (HL_TW * HL_BH * 128) + ky * HL_TW * 128))          // copy kx, image row ky
+                                        : make_desc_sbo(h_s + (uint32_t)((ky * p.pitch + kx) * 128), (uint32_t)(p.pitch * 128), p.dbg);   // shifted view of the halo tile
           const uint64_t bd = make_smem_desc(w_s + (uint32_t)(tap * p.BN * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 32 bytes of K per instruction (8 tf32 / 16 half)
@@ -197,6 +209,12 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
 
 }  // namespace tc
 
+static int halo_mode() {   // GIMMVFI_HALO_MODE: 1 (default) = one 16-wide halo tile (36 KB) + row-shifted descriptor starts; 2 = 10-wide halo tile
+                           // (22.5 KB, 1280-byte group stride); 3 = three x-shifted 8-wide copies (54 KB, 1024-aligned starts only)
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GIMMVFI_HALO_MODE"); v = s ? atoi(s) : 1; }
+  return v;
+}
 static int tc_halo() {   // GIMMVFI_TC_HALO=0: K-poor 3x3 layers stay on the per-tap TMA path of conv_tc.cu
   static int v = -1;
   if (v < 0) { const char* s = getenv("GIMMVFI_TC_HALO"); v = s ? atoi(s) : 1; }
@@ -226,7 +244,7 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
     const cuuint64_t es = f16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)in0.c, (cuuint64_t)in0.w, (cuuint64_t)in0.h, (cuuint64_t)in0.n};
     cuuint64_t str[3] = {(cuuint64_t)in0.ld * es, (cuuint64_t)in0.w * in0.ld * es, (cuuint64_t)in0.sn * es};
-    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), HL_BW, HL_BH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)(halo_mode() == 3 ? HL_TW : (halo_mode() == 2 ? HL_TW + 2 : HL_BW)), HL_BH, 1};
     encode(&mA, in0.p, 4, dims, str, box, f16);
   }
   {   // weights [tap][cout_pad][K block]: rows beyond cout_pad are zero-filled by TMA
@@ -243,13 +261,17 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin;
+  { const char* d = getenv("GIMMVFI_HALO_DBG"); p.dbg = d ? atoi(d) : 0; }
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2; p.res = e.res; p.out = out;
+  p.copies3 = halo_mode() == 3 ? 1 : 0;
+  p.pitch = halo_mode() == 2 ? HL_TW + 2 : HL_BW;
+  p.halo_bytes = p.copies3 ? 3 * HL_TW * HL_BH * 128 : ((p.pitch * HL_BH * 128 + 1023) & ~1023);
   const int w_region = (9 * BN * 128 + 1023) & ~1023;
   const int fixed = w_region + 8 * HL_STG_WARP_BYTES + 256 + 1024;
-  p.stages = (227 * 1024 - fixed) / HL_HALO_BYTES;
+  p.stages = (227 * 1024 - fixed) / p.halo_bytes;
   if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
   if (p.stages < 2) throw std::runtime_error("conv2d_halo: not enough shared memory");
-  const int smem = fixed + p.stages * HL_HALO_BYTES;
+  const int smem = fixed + p.stages * p.halo_bytes;
   static volatile unsigned char attr[64];
   gv_set_max_smem(conv3x3_halo_kernel, smem, attr);
   const int num_tiles = p.n_img * p.tiles_y * p.tiles_x;

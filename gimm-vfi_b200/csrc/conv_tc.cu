@@ -863,10 +863,12 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
 // All-pairs correlation vol[i][j] = scale * <fa[i,:], fb[j,:]> (raft/corr.py:167-175) as a 3xTF32 GEMM on the
 // same kernel: A = fa pixels (M), "weights" = the other frame's features, K-major as they lie in NHWC memory.
 // fb_planes = [2][N][C]: plane 0 = rn_tf32(x), plane 1 = rn_tf32(x - plane 0)  (split_planes in corr.cu).
-void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split) {
+void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split, int n_targets) {
   using namespace tc;
   if (fa.n != 1) throw std::runtime_error("corr_volume_tc: one sample per launch");
-  const int N = fa.h * fa.w, C = fa.c;
+  // M = the source pixels of fa; N = n_targets rows of fb (0: as many as sources).  Pooled pyramid levels are GEMMs against the
+  // avg-pooled target features (pooling and the dot product commute), so the level-0 volume is never re-read.
+  const int Ms = fa.h * fa.w, N = n_targets > 0 ? n_targets : Ms, C = fa.c;
   CUtensorMap mA, mB;
   encode_act(&mA, fa);
   // split: fb_planes = [2][N][C] (rn / residual planes).  plain TF32: fb_planes = the raw K-major features [N][C] of the
@@ -911,7 +913,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
   grid -= grid % CL;
   cx.launches++;
-  if (cx.prof) cx.prof->begin(cx.stream, split ? (sf16 ? "corr_gemm_tc_3xf16" : "corr_gemm_tc_3xtf32") : "corr_gemm_tc_tf32", 2.0 * (double)N * N * C);
+  if (cx.prof) cx.prof->begin(cx.stream, split ? (sf16 ? "corr_gemm_tc_3xf16" : "corr_gemm_tc_3xtf32") : "corr_gemm_tc_tf32", 2.0 * (double)Ms * N * C);
   if (split && pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA, mA, mB, p);
   else if (split && e8) launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA, mA, mB, p);
   else if (split) launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA, mA, mB, p);

@@ -126,6 +126,21 @@ void split_planes_f16(Ctx& cx, const TV& src, void* planes) {
   parallel_for(cx, n, SplitPlanesF16K{src, static_cast<uint16_t*>(planes), n}, "split_planes");
 }
 
+// 2x2 average of an NHWC feature map (floor semantics): the targets of pyramid level l are the level-(l-1) features pooled
+struct PoolFeatK {
+  TV src, dst;
+  GV_HD void operator()(int64_t i) const {
+    const int c = (int)(i % dst.c); int64_t r = i / dst.c;
+    const int x = (int)(r % dst.w); r /= dst.w; const int y = (int)(r % dst.h); const int n = (int)(r / dst.h);
+    const float* s = src.p + src.off(n, 2 * y, 2 * x) + c;
+    const int64_t dx = src.ld, dy = (int64_t)src.w * src.ld;
+    dst.p[dst.off(n, y, x) + c] = (s[0] + s[dx] + s[dy] + s[dy + dx]) * 0.25f;
+  }
+};
+void avgpool2_features(Ctx& cx, const TV& src, const TV& dst) {
+  parallel_for(cx, dst.pixels() * dst.c, PoolFeatK{src, dst}, "avgpool2_features");
+}
+
 // ------------------------------------------------------------------- pool
 // F.avg_pool2d(corr, 2, stride=2) over the trailing (h, w) image of every row (raft/corr.py:139-142).
 struct CorrPoolK {
@@ -251,7 +266,71 @@ struct CorrLookupK {
     out.p[out.off(n, y, x) + ch] = v;
   }
 };
+#ifndef GV_HOSTSIM
+// One warp per (source pixel, level): the 9 x-offsets and 9 y-offsets of the window go through the grid_sample round trip ONCE
+// (lanes 0..8 / 9..17: 18 coordinate evaluations instead of 2 x 81), the 81 outputs take their (x0, wx) / (y0, wy) by shuffle and issue
+// their four taps back to back; a warp's stores are 32 consecutive channels.  Arithmetic and summation order are those of CorrLookupK
+// (bit-identical results); the thread-per-output form spent ~100 instructions per output on the coordinate transform.
+__global__ void __launch_bounds__(256) corr_lookup_warp_kernel(CorrPyr pyr, TV coords, TV out, int64_t n_items) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t it = warp0; it < n_items; it += nwarps) {
+    const int lvl = (int)(it & 3); int64_t r = it >> 2;
+    const int x = (int)(r % coords.w); r /= coords.w; const int y = (int)(r % coords.h); const int n = (int)(r / coords.h);
+    const float* c = coords.p + coords.off(n, y, x);
+    const float inv = 1.0f / (float)(1 << lvl);
+    const int H = pyr.h[lvl], W = pyr.w[lvl];
+    // lane l < 9: x offset a = l; lanes 9..17: y offset b = l - 9
+    const bool isx = lane < 9;
+    const int d = isx ? lane : lane - 9;
+    const int S = isx ? W : H;
+    const float pc = (isx ? c[0] : c[1]) * inv + (float)(d - 4);
+    const float g = 2.f * pc / (float)(S - 1) - 1.f;
+    const float ic = ((g + 1.f) / 2.f) * (float)(S - 1);
+    const float c0f = floorf(ic);
+    const int my0 = (int)c0f;
+    const float mw1 = ic - c0f, mw0 = (c0f + 1.f) - ic;
+    const int64_t row = (int64_t)n * pyr.rows_per_sample + (int64_t)y * coords.w + x;
+    const float* img = pyr.lvl[lvl] + row * ((int64_t)H * W);
+    float* o = out.p + out.off(n, y, x) + lvl * 81;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const int k = pass * 32 + lane, kk = k < 81 ? k : 80;
+      const int a = kk / 9, b = kk - a * 9;
+      const int x0 = __shfl_sync(0xffffffffu, my0, a), y0 = __shfl_sync(0xffffffffu, my0, 9 + b);
+      const float wx0 = __shfl_sync(0xffffffffu, mw0, a), wx1 = __shfl_sync(0xffffffffu, mw1, a);
+      const float wy0 = __shfl_sync(0xffffffffu, mw0, 9 + b), wy1 = __shfl_sync(0xffffffffu, mw1, 9 + b);
+      if (k < 81) {
+        const int x1 = x0 + 1, y1 = y0 + 1;
+        const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+        const float t00 = (vy0 && vx0) ? __ldg(img + (int64_t)y0 * W + x0) : 0.f, t01 = (vy0 && vx1) ? __ldg(img + (int64_t)y0 * W + x1) : 0.f;
+        const float t10 = (vy1 && vx0) ? __ldg(img + (int64_t)y1 * W + x0) : 0.f, t11 = (vy1 && vx1) ? __ldg(img + (int64_t)y1 * W + x1) : 0.f;
+        float v = 0.f;
+        if (vy0 && vx0) v += t00 * (wx0 * wy0);
+        if (vy0 && vx1) v += t01 * (wx1 * wy0);
+        if (vy1 && vx0) v += t10 * (wx0 * wy1);
+        if (vy1 && vx1) v += t11 * (wx1 * wy1);
+        o[k] = v;
+      }
+    }
+  }
+}
+#endif
 void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords, const TV& out) {
+#ifndef GV_HOSTSIM
+  if (!out.f16 && !coords.f16) {
+    if (cx.dry) return;
+    cx.launches++;
+    const int64_t items = coords.pixels() * 4;
+    if (cx.prof) cx.prof->begin(cx.stream, "corr_lookup", (double)coords.pixels() * 324);
+    int64_t blocks = (items + 7) / 8, cap = (int64_t)cx.sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    corr_lookup_warp_kernel<<<(unsigned)blocks, 256, 0, cx.stream>>>(pyr, coords, out, items);
+    gv_check_launch("corr_lookup");
+    if (cx.prof) cx.prof->end(cx.stream);
+    return;
+  }
+#endif
   parallel_for(cx, coords.pixels() * 324, CorrLookupK{pyr, coords, out}, "corr_lookup");
 }
 

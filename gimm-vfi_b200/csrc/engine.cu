@@ -122,6 +122,7 @@ Engine::Engine(int device) : device_(device) {
 }
 
 Engine::~Engine() {
+  clear_graphs();
   DeviceGuard dg(device_);
   for (void* p : dev_allocs_) dev_free(p);
 }
@@ -316,7 +317,7 @@ void Engine::finalize_weights() {
   DeviceGuard dg(device_);
   for (void* p : dev_allocs_) dev_free(p);
   dev_allocs_.clear(); conv_.clear(); vec_.clear();
-  fc_valid_.clear(); ++weights_version_;   // a frame cache stored under the old weights must not be loaded again
+  fc_valid_.clear(); ++weights_version_; clear_graphs();   // a frame cache stored under the old weights must not be loaded again
   // --- RAFT encoders (raft/extractor.py:122-171); cnet's BatchNorm is folded
   for (int e = 0; e < 2; ++e) {
     const std::string p = e == 0 ? "flow_estimator.fnet" : "flow_estimator.cnet";
@@ -397,7 +398,7 @@ void Engine::finalize_weights_synthesis() {
   DeviceGuard dg(device_);
   for (void* p : dev_allocs_) dev_free(p);
   dev_allocs_.clear(); conv_.clear(); vec_.clear();
-  fc_valid_.clear(); ++weights_version_;
+  fc_valid_.clear(); ++weights_version_; clear_graphs();
   finalize_decoders();
   finalize_gimm_part();
   finalized_ = true; gimm_only_ = false; synth_only_ = true;
@@ -506,7 +507,7 @@ void Engine::finalize_weights_gimm() {
   DeviceGuard dg(device_);
   for (void* p : dev_allocs_) dev_free(p);
   dev_allocs_.clear(); conv_.clear(); vec_.clear();
-  fc_valid_.clear(); ++weights_version_;
+  fc_valid_.clear(); ++weights_version_; clear_graphs();
   finalize_gimm_part();
   finalized_ = true; gimm_only_ = true;
 }
@@ -670,7 +671,10 @@ static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, int ten
   for (int l = 0; l < 4; ++l) { P.h[l] = h; P.w[l] = w; P.lvl[l] = A.alloc_f((size_t)2 * B * P.N * h * w); h /= 2; w /= 2; }
   const float scale = 1.0f / std::sqrt((float)F.c);
   if (tensor_cores && F.c % 32 == 0 && F.ld % 4 == 0 && F.ld == F.c) {
-    // tcgen05 GEMM; the other frame's features act as the K-major "weights"
+    // tcgen05 GEMMs; the other frame's features act as the K-major "weights".  Level l > 0 is the GEMM against the 2^l x 2^l
+    // AVERAGE-POOLED target features: avg_pool2d of the volume over the target axes (raft/corr.py:139-142) commutes with the dot
+    // product, so the pooled levels (1/4 + 1/16 + 1/64 of level 0) cost a third more GEMM work and the 8.5 GB level-0 volume
+    // (1088x1920) is never re-read (the pooling pass over it took as long as the GEMM that wrote it).
     const bool split = tensor_cores >= 2;
     const size_t mk = A.mark();
     const int64_t plane = (int64_t)P.N * F.c;
@@ -678,13 +682,20 @@ static Pyramid build_pyramid(Ctx& cx, const TV& F /*2B,h,w,256*/, int B, int ten
     const int64_t nz = ((P.N + 255) / 256) * 256 + 512;
     float* zeros = A.alloc_f((size_t)nz);
     if (!cx.dry) dev_memset(zeros, 0, (size_t)nz * sizeof(float), cx.stream);
+    TV Fl[4]; Fl[0] = F;
+    for (int l = 1; l < 4; ++l) { Fl[l] = A.tensor(2 * B, P.h[l], P.w[l], F.c); avgpool2_features(cx, Fl[l - 1], Fl[l]); }
     for (int s = 0; s < 2 * B; ++s) {
       const int other = s < B ? s + B : s - B;
-      if (split && corr_volume_tc_wants_f16_planes()) split_planes_f16(cx, F.batch(other, 1), planes);
-      else if (split) split_planes(cx, F.batch(other, 1), planes);
-      if (!cx.dry) corr_volume_tc(cx, F.batch(s, 1), split ? planes : F.batch(other, 1).p, zeros, P.lvl[0] + (int64_t)s * P.N * P.N, scale, split);
+      for (int l = 0; l < 4; ++l) {
+        const int nt = P.h[l] * P.w[l];
+        if (nt <= 0) continue;
+        if (split && corr_volume_tc_wants_f16_planes()) split_planes_f16(cx, Fl[l].batch(other, 1), planes);
+        else if (split) split_planes(cx, Fl[l].batch(other, 1), planes);
+        if (!cx.dry) corr_volume_tc(cx, F.batch(s, 1), split ? planes : Fl[l].batch(other, 1).p, zeros, P.lvl[l] + (int64_t)s * P.N * nt, scale, split, nt);
+      }
     }
     A.release(mk);
+    return P;
   } else
   {
     corr_volume(cx, F.batch(0, B), F.batch(B, B), P.lvl[0], scale);
@@ -1292,6 +1303,14 @@ size_t Engine::plan(const Problem& p) {
   return cx.arena.peak + 256;
 }
 
+void Engine::clear_graphs() {
+#ifndef GV_HOSTSIM
+  DeviceGuard dg(device_);
+  for (GraphEntry& g : graphs_) if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+#endif
+  graphs_.clear();
+}
+
 void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t workspace_bytes, gvStream_t stream) {
   if (!finalized_) throw std::runtime_error("gimmvfi: finalize_weights() has not been called");
   if (gimm_only_) throw std::runtime_error("gimmvfi: only GIMM's weights were loaded (finalize_weights_gimm); use gimm_forward");
@@ -1305,6 +1324,48 @@ void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t wor
   cx.arena.base = reinterpret_cast<char*>(base);
   cx.arena.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
   taps_.clear();
+#ifndef GV_HOSTSIM
+  // (the legacy default stream - handles 0 / 1 / 2 - cannot be captured: such callers run eagerly)
+  if (use_graph_ && !profile_ && !debug_ && fc_ == nullptr && reinterpret_cast<uintptr_t>(stream) > 2) {
+    // everything a recorded launch sequence depends on: problem, every caller pointer, the workspace, the arithmetic mode, the weights
+    std::vector<uint64_t> key = {(uint64_t)p.B, (uint64_t)p.Hf, (uint64_t)p.Wf, (uint64_t)p.T, (uint64_t)p.Hc, (uint64_t)p.Wc, 0, (uint64_t)tc_mode_, (uint64_t)precise_,
+                                 (uint64_t)hypo_fast_, (uint64_t)weights_version_, (uint64_t)raft_iters, (uint64_t)workspace, (uint64_t)workspace_bytes, (uint64_t)(uintptr_t)stream};
+    std::memcpy(&key[6], &p.ds, sizeof(float));
+    const void* ptrs[] = {io.img_xs, io.coords, io.t, io.imgt_pred, io.img_warp_4, io.flowt0_1, io.flowt1_1, io.flowt0_4, io.flowt1_4, io.raft_flow, io.nflow, io.ninrflow, io.flowt};
+    for (const void* q : ptrs) key.push_back((uint64_t)(uintptr_t)q);
+    GraphEntry* hit = nullptr;
+    for (GraphEntry& g : graphs_) if (g.key == key) { hit = &g; break; }
+    if (hit && hit->exec) {
+      cuda_ok(cudaGraphLaunch((cudaGraphExec_t)hit->exec, stream), "cudaGraphLaunch");
+      launches_ = hit->launches; ++graph_replays_;
+      return;
+    }
+    if (hit && hit->seen >= 1) {   // second sighting: record.  (The first call ran eagerly: lazy one-time host work - function attributes - is done.)
+      cudaGraph_t graph = nullptr;
+      cuda_ok(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+      try {
+        run(cx, p, io);
+      } catch (...) {
+        cudaStreamEndCapture(stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      cuda_ok(cudaStreamEndCapture(stream, &graph), "cudaStreamEndCapture");
+      cudaGraphExec_t exec = nullptr;
+      cuda_ok(cudaGraphInstantiate(&exec, graph, 0), "cudaGraphInstantiate");
+      cudaGraphDestroy(graph);
+      hit->exec = exec; hit->launches = cx.launches;
+      cuda_ok(cudaGraphLaunch(exec, stream), "cudaGraphLaunch");
+      launches_ = cx.launches; ++graph_replays_;
+      return;
+    }
+    if (!hit) {
+      if (graphs_.size() >= 8) { if (graphs_.front().exec) cudaGraphExecDestroy((cudaGraphExec_t)graphs_.front().exec); graphs_.erase(graphs_.begin()); }
+      GraphEntry g; g.key = key; g.seen = 1;
+      graphs_.push_back(g);
+    }
+  }
+#endif
   run(cx, p, io);
   launches_ = cx.launches;
 }

@@ -75,6 +75,12 @@ class Engine {
   size_t plan(const Problem& p);                       // dry run -> workspace bytes
   void forward(const Problem& p, const IO& io, void* workspace, size_t workspace_bytes, gvStream_t stream);
   int64_t last_launches() const { return launches_; }
+  // CUDA graphs: forward() records the launch sequence of a (problem, buffers, mode) combination the SECOND time it sees it and
+  // replays the instantiated graph afterwards - one cudaGraphLaunch instead of ~550 kernel launches and ~1000 host-side tensor-map
+  // encodes per forward.  The replay is exactly the recorded stream of kernels with the recorded parameters, so it is only used
+  // when every pointer the launches captured is unchanged (key below); profiling, debug taps and the frame cache bypass it.
+  void set_cuda_graph(bool on) { use_graph_ = on; if (!on) clear_graphs(); }
+  int64_t graph_replays() const { return graph_replays_; }
   // debug taps: name -> NHWC view inside the workspace of the last forward
   void set_debug(bool on) { debug_ = on; }
   // per-kernel CUDA-event timing of the next forward(s): {"name": {"ms", "work", "launches"}}
@@ -119,6 +125,11 @@ class Engine {
   bool finalized_ = false, debug_ = false, profile_ = false, gimm_only_ = false, synth_only_ = false;
   int tc_mode_ = 0;
   int64_t weights_version_ = 0;
+  bool use_graph_ = false;
+  int64_t graph_replays_ = 0;
+  struct GraphEntry { std::vector<uint64_t> key; void* exec = nullptr; int64_t launches = 0; int seen = 0; };
+  std::vector<GraphEntry> graphs_;
+  void clear_graphs();
   int precise_ = 0;   // bit mask of post-RAFT stages in 3xTF32: 1 GIMM encoders / latent refiner, 2 HypoNet, 4 init decoder + update blocks, 8 final decoder, 16 combine
   float* fc_ = nullptr; size_t fc_bytes_ = 0; bool fc_load_ = false, fc_store_ = false;
   // what the cache holds (host-side bookkeeping of the last store): a load with a different buffer / problem is refused

@@ -443,9 +443,15 @@ struct InPartialK {
     int64_t per = (hw + chunks - 1) / chunks;
     int64_t a = (int64_t)ch * per, b = a + per; if (b > hw) b = hw;
     const float* p = x.p + (int64_t)n * x.sn + c;
-    double s = 0.0, s2 = 0.0;
-    for (int64_t k = a; k < b; ++k) { double v = (double)p[k * x.ld]; s += v; s2 += v * v; }
-    part[i * 2] = s; part[i * 2 + 1] = s2;
+    // four independent accumulator pairs: four loads in flight per thread (the single dependent chain was latency bound)
+    double s = 0.0, s2 = 0.0, t = 0.0, t2 = 0.0, u = 0.0, u2 = 0.0, w = 0.0, w2 = 0.0;
+    int64_t k = a;
+    for (; k + 3 < b; k += 4) {
+      const double v0 = (double)p[k * x.ld], v1 = (double)p[(k + 1) * x.ld], v2 = (double)p[(k + 2) * x.ld], v3 = (double)p[(k + 3) * x.ld];
+      s += v0; s2 += v0 * v0; t += v1; t2 += v1 * v1; u += v2; u2 += v2 * v2; w += v3; w2 += v3 * v3;
+    }
+    for (; k < b; ++k) { const double v = (double)p[k * x.ld]; s += v; s2 += v * v; }
+    part[i * 2] = (s + t) + (u + w); part[i * 2 + 1] = (s2 + t2) + (u2 + w2);
   }
 };
 // two-level tree over the chunk partials (a single thread per (n,c) looping over 1024 chunks was latency bound)

@@ -32,6 +32,10 @@ class EngineHandle:
         self._ws = None
         self._plans: Dict[tuple, int] = {}
         self.weights_loaded = False
+        # static_outputs: forward() returns the same output tensors on every call of a problem shape (overwritten by the next call) -
+        # with set_cuda_graph(True) and caller-owned input tensors this makes every pointer repeat, i.e. every forward a graph replay
+        self.static_outputs = False
+        self._static = None
 
     def __del__(self):
         try:
@@ -71,6 +75,15 @@ class EngineHandle:
         self.lib.check(self.lib.dll.gimmvfi_set_tensor_cores(self._h, int(mode)), self._h)
         self.tensor_cores = int(mode)
         self._plans.clear()
+
+    def set_cuda_graph(self, on: bool):
+        """Replay forward() from a recorded CUDA graph whenever problem, tensors (same addresses), stream and mode repeat; see
+        include/gimmvfi_b200.h.  Callers that want replays keep their input / coordinate tensors alive and let outputs recycle."""
+        self.lib.check(self.lib.dll.gimmvfi_set_cuda_graph(self._h, int(on)), self._h)
+
+    @property
+    def graph_replays(self) -> int:
+        return int(self.lib.dll.gimmvfi_graph_replays(self._h))
 
     def set_profile(self, on: bool):
         self.lib.check(self.lib.dll.gimmvfi_set_profile(self._h, int(on)), self._h)
@@ -147,6 +160,10 @@ class EngineHandle:
             self._ws = None
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         E = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        okey = (B, Hf, Wf, T, float(ds) if ds else 0.0, Hc, Wc, bool(aux_outputs))
+        if self.static_outputs and self._static is not None and self._static[0] == okey:
+            out = self._static[1]   # the SAME tensors as the previous call (aliasing is the caller's choice: static_outputs = True)
+            return self._launch(out, img_xs, coords, t, B, Hf, Wf, T, ds, Hc, Wc, frame_cache, flow_inputs)
         out = {"imgt_pred": E(T, B, 3, Hf, Wf)}
         if flow_inputs is not None:
             fi = flow_inputs
@@ -159,6 +176,11 @@ class EngineHandle:
                 img_warp_4=E(T, B, 3, H, W), flowt0_1=E(T, B, 3, 2, Hf, Wf), flowt1_1=E(T, B, 3, 2, Hf, Wf),
                 flowt0_4=E(T, B, 2, H // 4, W // 4), flowt1_4=E(T, B, 2, H // 4, W // 4), raft_flow=E(B, 2, 2, H, W),
                 nflow=E(B, 2, 2, H, W), ninrflow=E(T, B, 2, 1, Hc, Wc), flowt=E(T, B, 2, Hc, Wc))
+        if self.static_outputs:
+            self._static = (okey, out)
+        return self._launch(out, img_xs, coords, t, B, Hf, Wf, T, ds, Hc, Wc, frame_cache, flow_inputs)
+
+    def _launch(self, out, img_xs, coords, t, B, Hf, Wf, T, ds, Hc, Wc, frame_cache, flow_inputs):
         io = IO()
         io.img_xs, io.coords, io.t = img_xs.data_ptr(), coords.data_ptr(), t.data_ptr()
         for k, v in out.items():

@@ -123,6 +123,12 @@ int gimmvfi_set_frame_cache(gimmvfi_engine* e, void* cache, size_t bytes, int lo
 /* 0: fp32 CUDA cores everywhere; 1: post-RAFT convolutions on the tcgen05 TF32 path (fp32 accumulate);
  * 2: additionally the RAFT convolutions on tcgen05 with 3xTF32 operand splitting (fp32-class accuracy) */
 int gimmvfi_set_tensor_cores(gimmvfi_engine* e, int mode);
+/* CUDA graphs (off by default): gimmvfi_forward records its launch sequence the second time it is called with the same problem, the
+ * same caller pointers (inputs, outputs, workspace), stream and mode, and replays the instantiated graph from then on - one graph
+ * launch instead of ~550 kernel launches + ~1000 host-side tensor-map encodes.  Calls with other pointers run eagerly (and start
+ * their own record; 8 graphs are kept).  gimmvfi_graph_replays: forwards served by a replay so far. */
+int gimmvfi_set_cuda_graph(gimmvfi_engine* e, int on);
+int64_t gimmvfi_graph_replays(gimmvfi_engine* e);
 /* per-kernel CUDA-event timing of subsequent forwards; profile_json() synchronises the stream and
  * returns {"kernel": {"ms": total, "work": flops-or-elements, "launches": n}, ...} for the LAST forward */
 int gimmvfi_set_profile(gimmvfi_engine* e, int on);

@@ -74,13 +74,13 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
 }
 
 bool corr_volume_tc_wants_f16_planes() { return false; }   // the emulation takes the TF32 hi / lo planes (same 22-bit values)
-void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split) {
+void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* zero_bias, float* vol, float scale, bool split, int n_targets) {
   (void)zero_bias;
   if (cx.dry) return;
   cx.launches++;
-  const int64_t N = (int64_t)fa.h * fa.w; const int C = fa.c;
+  const int64_t Ms = (int64_t)fa.h * fa.w, N = n_targets > 0 ? n_targets : Ms; const int C = fa.c;
 #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < N; ++i) {
+  for (int64_t i = 0; i < Ms; ++i) {
     const float* a = fa.p + i * fa.ld;
     for (int64_t j = 0; j < N; ++j) {
       float s = 0.f;
