@@ -142,6 +142,15 @@ int gimmvfi_op_softsplat(const gimmvfi_view* lat, const gimmvfi_view* flow, cons
     softsplat_normalize(cx, acc, to_tv(out));
   })
 }
+int gimmvfi_op_softsplat_fused(const gimmvfi_view* lat, const gimmvfi_view* flow, const gimmvfi_view* metric, const float* t, int t_mode,
+                               const float* flow_absmax, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    if (!softsplat_fused(cx, to_tv(lat), to_tv(flow), to_tv(metric), t, t_mode, flow_absmax, to_tv(out)))
+      throw std::runtime_error("softsplat_fused: 16-channel 16-byte-aligned latent / output, 8-byte-aligned flow and a flow bound are required");
+  })
+}
 int gimmvfi_op_backwarp(const gimmvfi_view* src, const gimmvfi_view* flow, const gimmvfi_view* dst, void* stream) {
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, { Ctx cx = op_ctx(stream); backwarp(cx, to_tv(src), to_tv(flow), to_tv(dst)); })

@@ -376,6 +376,9 @@ void splat_weights(Ctx& cx, const TV& f_self, const TV& f_other, const float* g9
 void normalize_flow_pair(Ctx& cx, const TV& f01, const TV& f10, const float* scaler, const TV& n0, const TV& n1);
 void softsplat_accumulate(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const TV& acc);
 void softsplat_normalize(Ctx& cx, const TV& acc, const TV& out);
+// the whole splat in one pass (target tiles in shared memory); flow_absmax[n] >= max |flow| of sample n bounds the scan region
+bool softsplat_fused(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const float* flow_absmax,
+                     const TV& out);
 void scale_flow_t(Ctx& cx, const TV& flow_t, const float* t_per_sample, const TV& f0, const TV& f1);
 void hypo_pack_input(Ctx& cx, const float* coord /*B,Hc,Wc,3*/, const TV& dst /*slice of 3 ch*/);
 void unnormalize_flow(Ctx& cx, const TV& ninr, const float* scaler, const TV& out);

@@ -6,9 +6,9 @@
 // per launch and the measured limiter (0.80 ms = 6 TB/s; 96 TFLOP/s; HBM floor 0.17 ms).
 //
 // How: output tile = 8 (x) x 16 (y) pixels, so the 8-row groups of the M = 128 operand are image rows.  ONE TMA box
-// {32 ch, P x, 18 y} lands the tile plus halo 128B-swizzled in shared memory with a row pitch of P pixels (P = 16: 2048 bytes, or
-// P = 10: 1280 bytes); tap (ky, kx) is the UMMA descriptor whose start address is advanced by (ky * P + kx) pixel rows, with the
-// stride between 8-row groups = P * 128 bytes.  The 128B swizzle is a function of the ABSOLUTE shared-memory address bits on both
+// {32 ch, 16 x, 18 y} lands the tile plus halo 128B-swizzled in shared memory with a row pitch of P = 16 pixels (2048 bytes: the
+// stride between 8-row groups must be a multiple of the 1024-byte swizzle pattern - a 10-pixel pitch measured wrong); tap (ky, kx)
+// is the UMMA descriptor whose start address is advanced by (ky * P + kx) pixel rows, stride between 8-row groups P * 128 bytes.  The 128B swizzle is a function of the ABSOLUTE shared-memory address bits on both
 // the TMA write and the MMA read (measured: profiles/r02_halo_diag.log - every tap exact with the descriptor's "matrix base offset"
 // field left 0, garbage when it is set to the start row's phase), so a row-shifted start needs no further treatment.
 // Out-of-bounds box elements are zero-filled = the convolution's zero padding.  The 9 weight tiles (<= 72 KB) stay resident in shared memory for the whole
@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
 
 }  // namespace tc
 
-static int halo_mode() {   // GIMMVFI_HALO_MODE: 1 (default) = one 16-wide halo tile (36 KB) + row-shifted descriptor starts; 2 = 10-wide halo tile
-                           // (22.5 KB, 1280-byte group stride); 3 = three x-shifted 8-wide copies (54 KB, 1024-aligned starts only)
+static int halo_mode() {   // GIMMVFI_HALO_MODE: 1 (default) = one 16-wide halo tile (36 KB) + row-shifted descriptor starts;
+                           // 3 = three x-shifted 8-wide copies (54 KB, 1024-aligned starts only).  (A 10-wide halo tile with a 1280-byte
+                           // group stride does NOT work: measured wrong - the stride between 8-row groups has to be a multiple of 1024.)
   static int v = -1;
   if (v < 0) { const char* s = getenv("GIMMVFI_HALO_MODE"); v = s ? atoi(s) : 1; }
   return v;
@@ -244,7 +245,7 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
     const cuuint64_t es = f16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)in0.c, (cuuint64_t)in0.w, (cuuint64_t)in0.h, (cuuint64_t)in0.n};
     cuuint64_t str[3] = {(cuuint64_t)in0.ld * es, (cuuint64_t)in0.w * in0.ld * es, (cuuint64_t)in0.sn * es};
-    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)(halo_mode() == 3 ? HL_TW : (halo_mode() == 2 ? HL_TW + 2 : HL_BW)), HL_BH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)(halo_mode() == 3 ? HL_TW : HL_BW), HL_BH, 1};
     encode(&mA, in0.p, 4, dims, str, box, f16);
   }
   {   // weights [tap][cout_pad][K block]: rows beyond cout_pad are zero-filled by TMA
@@ -264,7 +265,7 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
   { const char* d = getenv("GIMMVFI_HALO_DBG"); p.dbg = d ? atoi(d) : 0; }
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2; p.res = e.res; p.out = out;
   p.copies3 = halo_mode() == 3 ? 1 : 0;
-  p.pitch = halo_mode() == 2 ? HL_TW + 2 : HL_BW;
+  p.pitch = HL_BW;
   p.halo_bytes = p.copies3 ? 3 * HL_TW * HL_BH * 128 : ((p.pitch * HL_BH * 128 + 1023) & ~1023);
   const int w_region = (9 * BN * 128 + 1023) & ~1023;
   const int fixed = w_region + 8 * HL_STG_WARP_BYTES + 256 + 1024;

@@ -745,9 +745,11 @@ static int tc_split_f16() {   // GIMMVFI_TC_SPLIT_F16=0: keep the 3xTF32 form of
   if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_F16"); v = s ? atoi(s) : 1; }
   return v;
 }
-static int tc_seg_f16() {   // K steps (of 64 elements) per TMEM accumulation segment of the 3xF16 form
+static int tc_seg_f16() {   // K steps (of 64 elements) per TMEM accumulation segment of the 3xF16 form.  2 (default): draining the
+                            // 64 KB accumulator (TMEM reads: 64 B/clk/SM) every step costs more than the step's MMAs; full-frame parity at
+                            // 1088x1920: 0 of 6.27 M values off by > 1e-3 with 1 and with 2, one outlier appears with 3 (profiles/r02_fullframe_parity.log)
   static int seg = -1;
-  if (seg < 0) { const char* s = getenv("GIMMVFI_TC_SEG_F16"); seg = s ? atoi(s) : 1; if (seg < 1) seg = 1; }
+  if (seg < 0) { const char* s = getenv("GIMMVFI_TC_SEG_F16"); seg = s ? atoi(s) : 2; if (seg < 1) seg = 1; }
   return seg;
 }
 static int tc_seg() {

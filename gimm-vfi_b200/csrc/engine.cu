@@ -968,6 +968,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
     float* sc = A.alloc_f((size_t)absmax_scratch_floats(f01));
     absmax_per_sample(cx, f01, f10, scaler, sc);
   }
+  flow_absmax_ = scaler;   // per-sample max |flow| over both directions: also bounds the forward splat's reach (gimm_decode)
   TV nf = A.tensor(2 * B, H, W, 2);
   normalize_flow_pair(cx, f01, f10, scaler, nf.batch(0, B), nf.batch(B, B));
   if (io.nflow)
@@ -1143,12 +1144,18 @@ void Engine::gimm_decode(Net& N, const TV& X64, const TV& f01, const TV& f10, co
   const int B = f01.n, H = f01.h, W = f01.w;
   const size_t mk0 = A.mark();
   // ---- forward splat of both latents to time t (gimmvfi_r.py:171-193)
-  TV acc = A.tensor(2 * B, H, W, 17, 20);
-  if (!cx.dry) dev_memset(acc.p, 0, (size_t)2 * B * H * W * 20 * sizeof(float), cx.stream);
-  softsplat_accumulate(cx, X64.slice(0, 16), f01, wts.batch(0, B), tdev, 0, acc.batch(0, B));
-  softsplat_accumulate(cx, X64.slice(16, 16), f10, wts.batch(B, B), tdev, 1, acc.batch(B, B));
-  softsplat_normalize(cx, acc.batch(0, B), X64.slice(32, 16));
-  softsplat_normalize(cx, acc.batch(B, B), X64.slice(48, 16));
+  // one pass per direction (target tiles in shared memory, bounded by the per-sample max |flow|); else memset + vector reductions + normalise
+  const bool one_pass = flow_absmax_ != nullptr &&
+                        softsplat_fused(cx, X64.slice(0, 16), f01, wts.batch(0, B), tdev, 0, flow_absmax_, X64.slice(32, 16)) &&
+                        softsplat_fused(cx, X64.slice(16, 16), f10, wts.batch(B, B), tdev, 1, flow_absmax_, X64.slice(48, 16));
+  if (!one_pass) {
+    TV acc = A.tensor(2 * B, H, W, 17, 20);
+    if (!cx.dry) dev_memset(acc.p, 0, (size_t)2 * B * H * W * 20 * sizeof(float), cx.stream);
+    softsplat_accumulate(cx, X64.slice(0, 16), f01, wts.batch(0, B), tdev, 0, acc.batch(0, B));
+    softsplat_accumulate(cx, X64.slice(16, 16), f10, wts.batch(B, B), tdev, 1, acc.batch(B, B));
+    softsplat_normalize(cx, acc.batch(0, B), X64.slice(32, 16));
+    softsplat_normalize(cx, acc.batch(B, B), X64.slice(48, 16));
+  }
   if (tap_it) tap("gimm.splat0", X64.slice(32, 16));
   // HypoNet (hyponet.py:71-146).  Tensor-core modes: ONE fused kernel (hyponet.cu) that takes the refined latent and the caller's
   // coordinate tensor directly; fp32 mode: five 1x1 convolutions on a packed [latent32 | t,y,x] input.
@@ -1217,6 +1224,12 @@ void Engine::run_gimm(Ctx& cx, const Problem& P, const GimmIO& io) {
   TV f01 = fl.batch(0, B), f10 = fl.batch(B, B);
   TV wts = A.tensor(2 * B, H, W, 1);
   TV X64 = A.tensor(B, H, W, 64);
+  {   // bound of the splat's reach (the caller's normalisation scale is not passed in: recompute max |ori_flow| per sample)
+    float* amax = A.alloc_f(std::max(B, 64));
+    float* sc = A.alloc_f((size_t)absmax_scratch_floats(f01));
+    absmax_per_sample(cx, f01, f10, amax, sc);
+    flow_absmax_ = amax;
+  }
   gimm_encode(N, nf, f01, f10, wts, X64);
   TV ninr = A.tensor(B, H, W, 2);
   for (int ti = 0; ti < T; ++ti) {

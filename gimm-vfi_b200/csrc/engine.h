@@ -148,6 +148,7 @@ class Engine {
   std::map<std::string, const float*> vec_;
   std::vector<void*> dev_allocs_;
   std::map<std::string, TV> taps_;
+  const float* flow_absmax_ = nullptr;   // device, per sample: max |flow| over both directions of the forward in flight
   const void* hypo_blob_ = nullptr;   // packed parameters of the fused HypoNet kernel (common.h hypo::)
   const void* hypo_blob3_ = nullptr;  // ... of its fp32-class variant (common.h hypo3::), the default
   bool hypo_fast_ = false;            // true: TF32 / half-operand HypoNet kernel (0.56 ms vs the fp32-class one; fails the 1e-3 bound on real frames)

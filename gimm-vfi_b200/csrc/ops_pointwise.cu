@@ -793,6 +793,96 @@ struct SplatNormK4 {
 };
 #endif
 
+#ifndef GV_HOSTSIM
+// The whole "linear-zeroeps" splat (modules/softsplat.py:286-352) in ONE pass over HBM: a CTA owns a 32 x 32 tile of TARGET pixels whose
+// 17-channel accumulators live in shared memory (68 KB), scans the source pixels that can reach it - the tile grown by
+// R = ceil(max|flow| * s) + 1, the per-sample flow bound the engine computes anyway for normalize_flow (fi_utils.py:52-60) - adds the
+// landing ones with shared-memory atomics, normalises in place and writes the 16 output channels.  DRAM traffic: flows (8 B, re-read
+// by neighbouring tiles mostly from L2) + latents and metric of the landing pixels (68 B) + the output (64 B) = the op's algorithmic
+// 140 B/px; the three-pass form (memset, global vector reductions, normalise) moves ~430 B/px through a 167 MB accumulator that
+// does not fit L2.  Summation order differs from the reference's (unordered atomics there too): fp32 re-association only.
+constexpr int SPT = 32;   // tile edge
+__global__ void __launch_bounds__(256) softsplat_tile_kernel(TV lat, TV flow, TV metric, TV out, const float* __restrict__ t, int t_mode,
+                                                            const float* __restrict__ absmax, int tiles_x, int tiles_y, int n_img) {
+  extern __shared__ float sacc[];   // [SPT * SPT][17]
+  const int W = out.w, H = out.h, tid = threadIdx.x;
+  const int num_tiles = n_img * tiles_x * tiles_y;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int r = tile; const int tx = r % tiles_x; r /= tiles_x; const int ty = r % tiles_y; const int n = r / tiles_y;
+    const int X0 = tx * SPT, Y0 = ty * SPT;
+    for (int i = tid; i < SPT * SPT * 17; i += 256) sacc[i] = 0.f;
+    const float tt = __ldg(t + n), sc = t_mode ? (1.f - tt) : tt;
+    const float bound = __ldg(absmax + n) * fabsf(sc);
+    const int R = (bound < 1e6f ? (int)ceilf(bound) : 1000000) + 1;   // (a non-finite / absurd bound degrades to scanning the frame)
+    const int xa = max(0, X0 - R), xb = min(W, X0 + SPT + R), ya = max(0, Y0 - R), yb = min(H, Y0 + SPT + R);
+    const int rw = xb - xa;
+    __syncthreads();
+    for (int i = tid; i < rw * (yb - ya); i += 256) {
+      const int y = ya + i / rw, x = xa + i % rw;
+      const float2 f = *reinterpret_cast<const float2*>(flow.p + flow.off(n, y, x));
+      const float fx = (float)x + f.x * sc, fy = (float)y + f.y * sc;
+      if (!gv_isfinite(fx) || !gv_isfinite(fy)) continue;
+      const float x0f = floorf(fx), y0f = floorf(fy);
+      const int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+      if (x1 < X0 || x0 >= X0 + SPT || y1 < Y0 || y0 >= Y0 + SPT) continue;   // no corner in this tile
+      const float m = metric.p[metric.off(n, y, x)];
+      float v[17];
+      const float* lp = lat.p + lat.off(n, y, x);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) { const F4 a = ld4(lp + 4 * g); v[4 * g] = a.x * m; v[4 * g + 1] = a.y * m; v[4 * g + 2] = a.z * m; v[4 * g + 3] = a.w * m; }
+      v[16] = m;
+      const float x1f = (float)x1, y1f = (float)y1;
+      const float wgt[4] = {(x1f - fx) * (y1f - fy), (fx - (float)x0) * (y1f - fy), (x1f - fx) * (fy - (float)y0), (fx - (float)x0) * (fy - (float)y0)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cx = (k & 1) ? x1 : x0, cy = (k & 2) ? y1 : y0;
+        if (cx < X0 || cx >= X0 + SPT || cy < Y0 || cy >= Y0 + SPT || cx >= W || cy >= H || cx < 0 || cy < 0) continue;
+        float* a = sacc + ((cy - Y0) * SPT + (cx - X0)) * 17;
+#pragma unroll
+        for (int c = 0; c < 17; ++c) atomicAdd(a + c, v[c] * wgt[k]);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < SPT * SPT * 4; i += 256) {   // "zeroeps" normalisation + store, 4 channels per thread
+      const int g = i & 3, p = i >> 2, lx = p % SPT, ly = p / SPT;
+      const int x = X0 + lx, y = Y0 + ly;
+      if (x >= W || y >= H) continue;
+      const float* a = sacc + p * 17;
+      float d = a[16]; if (d == 0.f) d = 1.f;
+      st4(out.p + out.off(n, y, x) + 4 * g, F4{a[4 * g] / d, a[4 * g + 1] / d, a[4 * g + 2] / d, a[4 * g + 3] / d});
+    }
+    __syncthreads();
+  }
+}
+#endif
+// fused splat: returns false when the layout does not qualify (caller falls back to memset + accumulate + normalise)
+bool softsplat_fused(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const float* flow_absmax,
+                     const TV& out) {
+#ifndef GV_HOSTSIM
+  static int on = -1;
+  if (on < 0) { const char* s = getenv("GIMMVFI_SPLAT_TILE"); on = s ? atoi(s) : 1; }
+  if (!on || !flow_absmax || lat.c != 16 || out.c != 16 || !vec4_ok(lat) || !vec4_ok(out) || (reinterpret_cast<uintptr_t>(flow.p) & 7) || flow.ld % 2 || flow.sn % 2 ||
+      flow.f16 || metric.f16)
+    return false;
+  if (cx.dry) return true;
+  cx.launches++;
+  const int tiles_x = (out.w + SPT - 1) / SPT, tiles_y = (out.h + SPT - 1) / SPT;
+  const int smem = SPT * SPT * 17 * 4;
+  static volatile unsigned char attr[64];
+  gv_set_max_smem(softsplat_tile_kernel, smem, attr);
+  if (cx.prof) cx.prof->begin(cx.stream, "softsplat_fused", (double)lat.pixels() * 35.0);   // 140 B per pixel
+  const int tiles = out.n * tiles_x * tiles_y;
+  const int grid = tiles < cx.sm_count * 3 ? tiles : cx.sm_count * 3;
+  softsplat_tile_kernel<<<grid, 256, smem, cx.stream>>>(lat, flow, metric, out, t_per_sample, t_mode, flow_absmax, tiles_x, tiles_y, out.n);
+  gv_check_launch("softsplat_fused");
+  if (cx.prof) cx.prof->end(cx.stream);
+  return true;
+#else
+  (void)cx; (void)lat; (void)flow; (void)metric; (void)t_per_sample; (void)t_mode; (void)flow_absmax; (void)out;
+  return false;
+#endif
+}
+
 void softsplat_accumulate(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const TV& acc) {
 #ifndef GV_HOSTSIM
   // vector form: 16-byte aligned latent / accumulator pixels (acc.ld % 4: the pad lanes receive +0)

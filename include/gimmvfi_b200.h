@@ -142,6 +142,9 @@ const char* gimmvfi_build_info(void);
 int gimmvfi_op_softsplat(const gimmvfi_view* lat, const gimmvfi_view* flow, const gimmvfi_view* metric, const float* t, int t_mode,
                          const gimmvfi_view* scratch, const gimmvfi_view* out, void* stream);
 /* backward warp: modules/fi_utils.py:19-49 */
+/* the same splat in ONE pass (target tiles accumulated in shared memory); flow_absmax[n] (device) >= max |flow| of sample n */
+int gimmvfi_op_softsplat_fused(const gimmvfi_view* lat, const gimmvfi_view* flow, const gimmvfi_view* metric, const float* t_per_sample, int t_mode,
+                               const float* flow_absmax, const gimmvfi_view* out, void* stream);
 int gimmvfi_op_backwarp(const gimmvfi_view* src, const gimmvfi_view* flow, const gimmvfi_view* dst, void* stream);
 /* F.interpolate(bilinear, align_corners=False): modules/fi_utils.py:67-70; dst = mult * resize(src) */
 int gimmvfi_op_resize(const gimmvfi_view* src, const gimmvfi_view* dst, float scale_factor, float mult, void* stream);

@@ -55,7 +55,9 @@ lat = torch.randn(1, H, W, 16, device=dev)
 flow = smooth_flow(1, H, W)
 metric = 0.5 + torch.rand(1, H, W, 1, device=dev)
 t = torch.full((1,), 0.5, device=dev)
-timeit("softsplat 16ch 1088x1920 (whole op)", lambda: K.softsplat(lat, flow, metric, t, 0), H * W * 140.0)
+timeit("softsplat 16ch 1088x1920 (3 passes)", lambda: K.softsplat(lat, flow, metric, t, 0), H * W * 140.0)
+amax = flow.abs().amax().reshape(1).contiguous()
+timeit("softsplat 16ch 1088x1920 (one pass)", lambda: K.softsplat_fused(lat, flow, metric, t, 0, amax), H * W * 140.0)
 # ---- backwarp 64 ch at full resolution
 src = torch.randn(1, H, W, 64, device=dev)
 timeit("backwarp 64ch 1088x1920", lambda: K.backwarp(src, flow), H * W * (2 * 64 + 2) * 4.0)

@@ -58,6 +58,15 @@ def softsplat(lat, flow, metric, t, t_mode, lib=None):
     return out
 
 
+def softsplat_fused(lat, flow, metric, t, t_mode, absmax, lib=None):
+    lib = lib or default_lib()
+    n, h, w, _ = lat.shape
+    out = torch.empty(n, h, w, 16, device=lat.device)
+    lib.check(lib.dll.gimmvfi_op_softsplat_fused(C.byref(view_of(lat)), C.byref(view_of(flow)), C.byref(view_of(metric)), C.c_void_p(t.data_ptr()),
+                                                 t_mode, C.c_void_p(absmax.data_ptr()), C.byref(view_of(out)), _stream(out)))
+    return out
+
+
 def backwarp(src, flow, lib=None):
     lib = lib or default_lib()
     out = torch.empty(flow.shape[0], flow.shape[1], flow.shape[2], src.shape[3], device=src.device)

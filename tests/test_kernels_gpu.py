@@ -83,6 +83,28 @@ def test_softsplat_vs_oracle():
         assert err.max().item() <= 3e-4 and err.mean().item() <= 1e-6
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 56), (1, 70, 100)])   # < one 32 x 32 tile row / ragged tiles
+def test_softsplat_fused_vs_oracle(shape):
+    """the one-pass splat (32 x 32 target tiles in shared memory, scan region bounded by the per-sample max |flow|): NaN / inf flows,
+    flows that leave the frame (holes stay 0), an infinite bound (sample with an inf flow: the scan degrades to the whole frame)"""
+    n, h, w = shape
+    lat = rnd(n, 16, h, w, seed=1)
+    flow = rnd(n, 2, h, w, seed=2, scale=4.0)
+    flow[0, 0, 3, 3] = float("nan")
+    flow[n - 1, 1, 5, 7] = float("inf")
+    flow[0, :, 0, 0] = torch.tensor([2.0, 1.0], device=DEV)
+    flow[0, :, 10:14, 10:14] = 100.0
+    metric = 0.5 + rnd(n, 1, h, w, seed=3).abs()
+    t = torch.tensor([0.5, 0.25][:n], device=DEV)
+    absmax = torch.nan_to_num(flow.abs(), nan=0.0, posinf=float("inf")).amax(dim=(1, 2, 3)).contiguous()   # what absmax_per_sample yields (fmaxf drops NaN)
+    for mode in (0, 1):
+        got = K.nchw(K.softsplat_fused(K.nhwc(lat), K.nhwc(flow), K.nhwc(metric), t, mode, absmax))
+        sc = (t if mode == 0 else (1 - t)).view(n, 1, 1, 1)
+        ref = O.softsplat_linear_zeroeps(lat.cpu(), (flow * sc).cpu(), metric.cpu()).to(DEV)
+        err = (got - ref).abs()
+        assert err.max().item() <= 3e-4 and err.mean().item() <= 1e-6
+
+
 def test_backwarp_vs_oracle():
     src = rnd(2, 19, 24, 40, seed=1)
     flow = rnd(2, 2, 24, 40, seed=2, scale=6.0)   # includes out-of-frame targets (border clamp)
