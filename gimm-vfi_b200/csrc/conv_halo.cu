@@ -14,7 +14,8 @@
 // Out-of-bounds box elements are zero-filled = the convolution's zero padding.  The 9 weight tiles (<= 72 KB) stay resident in shared memory for the whole
 // persistent CTA.  Per tile: 36 KB of TMA traffic instead of 144 KB (+ weights), 36 MMAs, no other shared-memory writes.
 //
-// Roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), 8 epilogue warps (two per TMEM lane quarter, each BN/2 columns).
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), 8 epilogue warps (two per TMEM lane quarter, each BN/2 columns;
+// a thread stores its pixel's 16 / 32 channels straight from registers).
 #include "common.h"
 
 #ifndef GV_HOSTSIM
@@ -29,8 +30,6 @@ namespace tc {
 constexpr int HL_TW = 8, HL_TH = 16;                  // output tile (x, y)
 constexpr int HL_BW = 16, HL_BH = HL_TH + 2;          // halo box: 16 x 18 pixels (x extent padded to 16: 2048-byte row pitch)
 constexpr int HL_HALO_BYTES = HL_BW * HL_BH * 128;    // 36 KB
-constexpr int HL_STG_PITCH = 20;                      // floats per staged row (16 + 4)
-constexpr int HL_STG_WARP_BYTES = 32 * HL_STG_PITCH * 4;
 constexpr int HL_MAX_STAGES = 4;
 
 struct HaloParams {
@@ -61,8 +60,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
   const int w_region = (w_bytes + 1023) & ~1023;
   uint8_t* wsm = smem;
   uint8_t* halo = smem + w_region;
-  float* stg_base = reinterpret_cast<float*>(halo + p.stages * p.halo_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg_base) + 8 * HL_STG_WARP_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(halo + p.stages * p.halo_bytes);
   uint64_t* w_bar = bars;                         // weights landed
   uint64_t* full_bar = bars + 1;                  // [HL_MAX_STAGES]
   uint64_t* empty_bar = bars + 1 + HL_MAX_STAGES; // [HL_MAX_STAGES]
@@ -144,14 +142,19 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ---- epilogue: warp -> TMEM lane quarter (warp % 4) = image rows [4 q, 4 q + 4) of the tile; the two warps of a quarter split the columns
+    // ---- epilogue: warp -> TMEM lane quarter (warp % 4) = image rows [4 q, 4 q + 4) of the tile; the two warps of a quarter split the
+    // columns.  A thread owns ONE output pixel (TMEM lane = tile row m = y * 8 + x) and 16 consecutive channels = 64 contiguous bytes of
+    // the NHWC output: bias / activation / residual / rounding and four 16-byte stores straight from registers.  (The first version
+    // transposed through shared memory like conv_tc.cu's epilogue: 555 instructions per warp and tile, the kernel's limiter per ncu -
+    // tensor pipe 20 % active; a pixel's other 16-channel halves are written by the partner warp, so every 32-byte sector is still
+    // written in full.)
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int cpw = p.BN / 2;                                  // columns per warp: 16 or 32
-    const uint32_t stg_s = smem_u32(stg_base + (warp - 2) * 32 * HL_STG_PITCH);
-    const int rsub = lane >> 2, q4 = lane & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int r = tile; const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
+      const int y = ty * HL_TH + quarter * 4 + (lane >> 3), x = tx * HL_TW + (lane & 7);
+      const bool inside = y < p.H && x < p.W;
       mbar_wait(&tfull_bar[acc], acc_phase, SPIN);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 64 + half * cpw);
@@ -160,40 +163,33 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)(u * 16), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (cbase < p.cout) {
-          {   // phase 1 (thread = pixel row of the tile): bias + act1 -> staging
-            float o[16];
+        if (cbase < p.cout && inside) {
+          float o[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + j);
-              o[4 * j] = __uint_as_float(v[4 * j]) + b4.x; o[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-              o[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; o[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-            }
-            act_n<16>(o, p.act1, p.slope1, cbase, p.cout);
-            const uint32_t srow = stg_s + (uint32_t)(lane * HL_STG_PITCH * 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sts128(srow + j * 16, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + j);
+            o[4 * j] = __uint_as_float(v[4 * j]) + b4.x; o[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            o[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; o[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
           }
-          __syncwarp();
-          // phase 2 (4 lanes = the 16 channels of one pixel, 8 pixels = one image row of the tile per instruction)
-          const int c = cbase + q4 * 4;
-          if (c < p.cout) {
+          act_n<16>(o, p.act1, p.slope1, cbase, p.cout);
+          if (p.res.p) {
+            const int64_t rb = p.res.off(n, y, x) + cbase;
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int y = ty * HL_TH + quarter * 4 + it, x = tx * HL_TW + rsub;
-              const float4 sv = lds128(stg_s + (uint32_t)(((it * 8 + rsub) * HL_STG_PITCH + q4 * 4) * 4));
-              float o[4] = {sv.x, sv.y, sv.z, sv.w};
-              if (y < p.H && x < p.W) {
-                if (p.res.p) { float t[4]; load4_any(p.res, p.res.off(n, y, x) + c, c, p.cout, t); o[0] += t[0]; o[1] += t[1]; o[2] += t[2]; o[3] += t[3]; }
-                if (p.act2 != ACT_NONE) act_rows<1>(o, p.act2, p.slope2, c, p.cout);
-                if (p.round_out) { o[0] = rn_tf32(o[0]); o[1] = rn_tf32(o[1]); o[2] = rn_tf32(o[2]); o[3] = rn_tf32(o[3]); }
-                const int64_t eoff = p.out.off(n, y, x) + c;
-                const uintptr_t oaddr = reinterpret_cast<uintptr_t>(p.out.p) + (uintptr_t)eoff * (p.out.f16 ? 2 : 4);
-                store4(p.out, eoff, o, c, p.cout, c + 3 < p.cout && (oaddr & (p.out.f16 ? 7 : 15)) == 0);
-              }
-            }
+            for (int j = 0; j < 4; ++j) { float t[4]; load4_any(p.res, rb + 4 * j, cbase + 4 * j, p.cout, t); o[4 * j] += t[0]; o[4 * j + 1] += t[1]; o[4 * j + 2] += t[2]; o[4 * j + 3] += t[3]; }
           }
-          __syncwarp();
+          if (p.act2 != ACT_NONE) act_n<16>(o, p.act2, p.slope2, cbase, p.cout);
+          if (p.round_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = rn_tf32(o[j]);
+          }
+          const int64_t eoff = p.out.off(n, y, x) + cbase;
+          const uintptr_t oaddr = reinterpret_cast<uintptr_t>(p.out.p) + (uintptr_t)eoff * (p.out.f16 ? 2 : 4);
+          const bool al = (oaddr & (p.out.f16 ? 7 : 15)) == 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = cbase + 4 * j;
+            if (c < p.cout) store4(p.out, eoff + 4 * j, o + 4 * j, c, p.cout, al && c + 3 < p.cout);
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -268,7 +264,7 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
   p.pitch = HL_BW;
   p.halo_bytes = p.copies3 ? 3 * HL_TW * HL_BH * 128 : ((p.pitch * HL_BH * 128 + 1023) & ~1023);
   const int w_region = (9 * BN * 128 + 1023) & ~1023;
-  const int fixed = w_region + 8 * HL_STG_WARP_BYTES + 256 + 1024;
+  const int fixed = w_region + 256 + 1024;
   p.stages = (227 * 1024 - fixed) / p.halo_bytes;
   if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
   if (p.stages < 2) throw std::runtime_error("conv2d_halo: not enough shared memory");

@@ -291,14 +291,14 @@ void Engine::pack_stem(const std::string& name, const std::string& bn) {
   conv_[name + "#xpacked"] = c;
 }
 
-// 7x7 convolutions on few channels with the x-taps packed into the channel axis (see pack_stem): the input is a
-// zero-padded copy with `ldp` floats per pixel, the kernel becomes (7 x 1) over K = 7*ldp "channels".
+// k x k convolutions (k = 7, 5) on few channels with the x-taps packed into the channel axis (see pack_stem): the input is a
+// zero-padded copy with `ldp` floats per pixel, the kernel becomes (k x 1) over K = k*ldp "channels" - k K-step groups instead of k*k.
 void Engine::pack_xpacked(const std::string& name, int ldp) {
   const HostTensor& W = raw(name + ".weight");
   const HostTensor& Bv = raw(name + ".bias");
   const int cout = (int)W.shape[0], cin = (int)W.shape[1], kh = (int)W.shape[2], kw = (int)W.shape[3];
-  if (kh != 7 || kw != 7 || cin > ldp) throw std::runtime_error("pack_xpacked: expected a 7x7 conv with cin <= ldp");
-  const int cout_ld = (cout + 3) & ~3, K = 7 * ldp;
+  if (kh != kw || !(kh & 1) || cin > ldp) throw std::runtime_error("pack_xpacked: expected an odd k x k conv with cin <= ldp");
+  const int cout_ld = (cout + 3) & ~3, K = kw * ldp;
   std::vector<float> pw((size_t)kh * K * cout_ld, 0.f), pb(((tc_cout_pad(cout) + 31) & ~31) + 128, 0.f);
   for (int co = 0; co < cout; ++co) {
     for (int ky = 0; ky < kh; ++ky)
@@ -390,6 +390,7 @@ void Engine::finalize_decoders() {
   pack_conv("amt_comb_block.0"); vec("amt_comb_block.1.weight"); pack_conv("amt_comb_block.2");
   pack_xpacked("amt_comb_block.0", 12); pack_xpacked("amt_comb_block.2", 20);
   pack_xpacked("amt_update4_low.convf1", 4); pack_xpacked("amt_update4_high.convf1", 4);
+  pack_xpacked("amt_final_decoder.upsample.2.0", 8);   // 5x5 on 8 channels at full resolution: 5 x 40 lanes instead of 25 taps x 8-of-32 lanes
 }
 
 // GIMM-VFI-F's parameter tree minus flow_estimator.* (gimmvfi_f.py:37-111): the synthesis half runs natively on the outputs of an
@@ -552,11 +553,11 @@ struct Net {
   // 7x7 conv on few channels through the x-packed weights: zero-padded copy of `in`, then a (7 x 1) conv over 7*ldp lanes
   void conv7x(const std::string& name, const TV& in, const TV& out, int act = ACT_NONE, const float* slope = nullptr) {
     const ConvW& w = W(name + "#xp");
-    const int ldp = w.cin / 7;
+    const int k = w.kh, ldp = w.cin / k;   // (k x k kernel packed as k x 1 over k * ldp lanes)
     Arena& A = cx.arena;
     const size_t mk = A.mark();
-    TV pad = A.tensor(in.n, in.h + 6, in.w + 6, ldp, ldp);
-    pad_zero(cx, in, pad, 3);
+    TV pad = A.tensor(in.n, in.h + 2 * (k / 2), in.w + 2 * (k / 2), ldp, ldp);
+    pad_zero(cx, in, pad, k / 2);
     TV v = pad; v.c = w.cin;
     ConvGeom g; g.stride = 1; g.ph = 0; g.pw = 0; g.loose_w = 1;
     ConvEpi e; e.act1 = act; e.slope1 = slope;
@@ -956,7 +957,9 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
     TV a = A.tensor(2 * B, H, W, 8);
     TV b = hs ? A.tensor_h(2 * B, H, W, 32) : A.tensor(2 * B, H, W, 32), c = A.tensor_like(b, 32), d = A.tensor_like(b, 64);
     pixel_shuffle(cx, feat4, a, 2);
-    N.convrelu(p + "2", a, b); N.convrelu(p + "3", b, c); N.convrelu(p + "4", c, b); N.convrelu(p + "5", b, c);
+    if (cx.tc && !hs) N.conv7x(p + "2.0", a, b, ACT_PRELU, N.V(p + "2.1.weight"));   // x-packed 5x5 (pack_xpacked)
+    else N.convrelu(p + "2", a, b);
+    N.convrelu(p + "3", b, c); N.convrelu(p + "4", c, b); N.convrelu(p + "5", b, c);
     N.convrelu(p + "6", c, d);
     N.conv(p + "7", d, fup1, ACT_RELU);
     A.release(mk);

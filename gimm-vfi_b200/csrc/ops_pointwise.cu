@@ -860,7 +860,10 @@ bool softsplat_fused(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, c
                      const TV& out) {
 #ifndef GV_HOSTSIM
   static int on = -1;
-  if (on < 0) { const char* s = getenv("GIMMVFI_SPLAT_TILE"); on = s ? atoi(s) : 1; }
+  // off by default: DRAM traffic is 0.85x the op's algorithmic bytes (ncu), but fp32 (and 64-bit integer) atomic adds on SHARED memory are
+  // compare-and-swap loops on sm_100a (ATOMS.CAST.SPIN): 115 M warp instructions, 0.318 ms vs 0.249 ms for the three-pass form whose
+  // red.global.add.v4.f32 run in the L2 atomic units (profiles/r02_hbm_kernels_probe.log, r02_ncu_softsplat_tile.jsonl)
+  if (on < 0) { const char* s = getenv("GIMMVFI_SPLAT_TILE"); on = s ? atoi(s) : 0; }
   if (!on || !flow_absmax || lat.c != 16 || out.c != 16 || !vec4_ok(lat) || !vec4_ok(out) || (reinterpret_cast<uintptr_t>(flow.p) & 7) || flow.ld % 2 || flow.sn % 2 ||
       flow.f16 || metric.f16)
     return false;
