@@ -147,7 +147,7 @@ int gimmvfi_op_softsplat_fused(const gimmvfi_view* lat, const gimmvfi_view* flow
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, {
     Ctx cx = op_ctx(stream);
-    if (!softsplat_fused(cx, to_tv(lat), to_tv(flow), to_tv(metric), t, t_mode, flow_absmax, to_tv(out)))
+    if (!softsplat_fused(cx, to_tv(lat), to_tv(flow), to_tv(metric), t, t_mode, flow_absmax, to_tv(out), /*force=*/true))
       throw std::runtime_error("softsplat_fused: 16-channel 16-byte-aligned latent / output, 8-byte-aligned flow and a flow bound are required");
   })
 }
@@ -203,6 +203,18 @@ int gimmvfi_op_corr_lookup(const float* const lvl[4], const int32_t lvl_h[4], co
     for (int l = 0; l < 4; ++l) { p.lvl[l] = lvl[l]; p.h[l] = lvl_h[l]; p.w[l] = lvl_w[l]; }
     p.rows_per_sample = (int64_t)c.h * c.w;
     corr_lookup(cx, p, c, to_tv(out));
+  })
+}
+int gimmvfi_op_corr_lookup_direct(const gimmvfi_view* src, const void* const tgt_half[4], const int32_t lvl_h[4], const int32_t lvl_w[4], float scale,
+                                  const gimmvfi_view* coords, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    TV s = to_tv(src);
+    CorrFeat f;
+    for (int l = 0; l < 4; ++l) { f.lvl[l] = static_cast<const uint16_t*>(tgt_half[l]); f.h[l] = lvl_h[l]; f.w[l] = lvl_w[l]; }
+    f.c = s.c; f.scale = scale;
+    corr_lookup_direct(cx, s, f, to_tv(coords), to_tv(out));
   })
 }
 int gimmvfi_op_conv2d(const gimmvfi_view* in0, const gimmvfi_view* in1, const float* w_packed, const float* bias, int cin, int cout,

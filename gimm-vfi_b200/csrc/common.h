@@ -350,6 +350,11 @@ void avgpool2_features(Ctx& cx, const TV& src, const TV& dst);   // NHWC 2x2 ave
 void corr_pool_pyramid(Ctx& cx, const float* l0, float* l1, float* l2, float* l3, int64_t rows, int h, int w);
 struct CorrPyr { const float* lvl[4]; int h[4], w[4]; int64_t rows_per_sample; };
 void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords /*n,h,w,2 (x,y)*/, const TV& out /*324 ch*/);
+// volume-free lookup: the other frame's features (IEEE half, NHWC, c channels; level l = the 2^l x 2^l average-pooled map, sample-major)
+struct CorrFeat { const uint16_t* lvl[4]; int h[4], w[4]; int c; float scale; };
+void features_to_half(Ctx& cx, const TV& src, void* dst /*half, dense NHWC*/);
+bool corr_lookup_direct_supported(const TV& src, const CorrFeat& tgt, const TV& coords, const TV& out);
+void corr_lookup_direct(Ctx& cx, const TV& src /*n,h,w,256 fp32: the source frame's features*/, const CorrFeat& tgt, const TV& coords, const TV& out);
 // ops_pointwise.cu
 void nchw_to_nhwc(Ctx& cx, const float* src, int64_t src_sn, int64_t src_sc, const TV& dst, float scale, float shift);
 void nhwc_to_nchw(Ctx& cx, const TV& src, float* dst, int64_t dst_sn, int64_t dst_sc, float scale, float shift, int clamp01);  // (v + shift) * scale
@@ -378,7 +383,7 @@ void softsplat_accumulate(Ctx& cx, const TV& lat, const TV& flow, const TV& metr
 void softsplat_normalize(Ctx& cx, const TV& acc, const TV& out);
 // the whole splat in one pass (target tiles in shared memory); flow_absmax[n] >= max |flow| of sample n bounds the scan region
 bool softsplat_fused(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const float* flow_absmax,
-                     const TV& out);
+                     const TV& out, bool force = false);
 void scale_flow_t(Ctx& cx, const TV& flow_t, const float* t_per_sample, const TV& f0, const TV& f1);
 void hypo_pack_input(Ctx& cx, const float* coord /*B,Hc,Wc,3*/, const TV& dst /*slice of 3 ch*/);
 void unnormalize_flow(Ctx& cx, const TV& ninr, const float* scaler, const TV& out);

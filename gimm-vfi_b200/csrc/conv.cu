@@ -332,7 +332,7 @@ bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const Con
   if (h && (split || !w.w_tc_h)) return false;
   if (in1.p && (in1.f16 != 0) != h) return false;
   if (e.mul.f16 || e.gru_z.f16 || e.gru_h.f16) return false;   // only the residual may be half
-  if (e.split_c && (e.split_c % 32 || !e.out2.p || e.out2.f16 || e.res.p || e.gru_z.p)) return false;
+  if (e.split_c && (e.split_c % 32 || !e.out2.p || e.out2.f16 || e.gru_z.p)) return false;   // (a residual is indexed by the merged channel)
   if (!al16(in0.p) || in0.ld % amul || in0.sn % amul) return false;
   if (in1.p && (!al16(in1.p) || in1.ld % amul || in1.sn % amul || in0.c % kblk)) return false;
   if (!g.loose_w && ((in0.h + 2 * g.ph - w.kh) / g.stride + 1 != out.h || (in0.w + 2 * g.pw - w.kw) / g.stride + 1 != out.w)) return false;

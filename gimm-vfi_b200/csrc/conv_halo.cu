@@ -37,6 +37,7 @@ struct HaloParams {
   int copies3;      // 1: three x-shifted copies {K, 8 x, 18 y} of the tile (aligned descriptors only); 0: one {K, P x, 18 y} halo tile + shifted views
   int pitch;        // P: pixels per halo row (16 or 10)
   int halo_bytes;   // bytes of one pipeline stage (multiple of 1024)
+  int kinstr;       // MMAs per tap: ceil(cin bytes / 32) <= 4
   const float* bias; int act1; const float* slope1; int act2; const float* slope2;
   TV res, out;
 };
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
                                         : make_desc_sbo(h_s + (uint32_t)((ky * p.pitch + kx) * 128), (uint32_t)(p.pitch * 128), p.dbg);   // shifted view of the halo tile
           const uint64_t bd = make_smem_desc(w_s + (uint32_t)(tap * p.BN * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 32 bytes of K per instruction (8 tf32 / 16 half)
+          for (int k = 0; k < 4; ++k) {   // 32 bytes of K per instruction (8 tf32 / 16 half); channels beyond cin are zero fill: not issued
+            if (k >= p.kinstr) break;
             if (p.f16_in) mma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (tap | k) ? 1u : 0u);
             else mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (tap | k) ? 1u : 0u);
           }
@@ -261,6 +263,7 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
   { const char* d = getenv("GIMMVFI_HALO_DBG"); p.dbg = d ? atoi(d) : 0; }
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2; p.res = e.res; p.out = out;
   p.copies3 = halo_mode() == 3 ? 1 : 0;
+  p.kinstr = (in0.c * (f16 ? 2 : 4) + 31) / 32;
   p.pitch = HL_BW;
   p.halo_bytes = p.copies3 ? 3 * HL_TW * HL_BH * 128 : ((p.pitch * HL_BH * 128 + 1023) & ~1023);
   const int w_region = (9 * BN * 128 + 1023) & ~1023;
@@ -270,7 +273,7 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
   if (p.stages < 2) throw std::runtime_error("conv2d_halo: not enough shared memory");
   const int smem = fixed + p.stages * p.halo_bytes;
   static volatile unsigned char attr[64];
-  gv_set_max_smem(conv3x3_halo_kernel, smem, attr);
+  gv_set_max_smem(conv3x3_halo_kernel, 227 * 1024, attr);   // set once per device: the layer-dependent size below must always fit
   const int num_tiles = p.n_img * p.tiles_y * p.tiles_x;
   const int grid = num_tiles < cx.sm_count ? num_tiles : cx.sm_count;
   cx.launches++;

@@ -334,4 +334,182 @@ void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords, const TV& out) {
   parallel_for(cx, coords.pixels() * 324, CorrLookupK{pyr, coords, out}, "corr_lookup");
 }
 
+// -------------------------------------------------------- volume-free lookup
+// BidirCorrBlock (raft/corr.py:23-93) is looked up ONCE per interpolated frame: building the all-pairs volume pyramid for it writes
+// N^2 x 4/3 x 2 values (11 GB at 1088x1920) to read back 2 x N x 324.  Bilinear interpolation of the volume is linear in the volume,
+// and a level-l volume entry is the dot product with the 2^l x 2^l average-pooled target feature, so the 81 window samples of a level
+// only need the dot products with the (at most) 10 x 10 integer neighbours of the window: 100 dots of 256 channels per (pixel, level)
+// = 8.6 GFLOP per pair instead of the 1.45 TFLOP GEMM.  Target features are IEEE half (the same 11-bit significand the plain-TF32
+// volume GEMM gave them), the source feature and the accumulation are fp32.
+struct ToHalfK {
+  TV src; uint16_t* dst;
+  GV_HD void operator()(int64_t i) const {
+    const int c = (int)(i % src.c); int64_t r = i / src.c;
+    const int x = (int)(r % src.w); r /= src.w; const int y = (int)(r % src.h); const int n = (int)(r / src.h);
+    dst[i] = gv_f2h(src.p[src.off(n, y, x) + c]);
+  }
+};
+void features_to_half(Ctx& cx, const TV& src, void* dst) {
+  parallel_for(cx, src.pixels() * src.c, ToHalfK{src, static_cast<uint16_t*>(dst)}, "features_to_half");
+}
+
+// grid_sample(align_corners=True) round trip of one window coordinate (raft/utils/utils.py:66-80), as CorrLookupK evaluates it
+GV_HD void corr_axis(float c, float inv, int d, int S, int& i0, float& w0, float& w1) {
+  const float pc = c * inv + (float)(d - 4);
+  const float g = 2.f * pc / (float)(S - 1) - 1.f;
+  const float ic = ((g + 1.f) / 2.f) * (float)(S - 1);
+  const float c0f = floorf(ic);
+  i0 = (int)c0f; w1 = ic - c0f; w0 = (c0f + 1.f) - ic;
+}
+
+// thread-per-output form (host build of the engine; the reference for the warp kernel below): four taps, each a C-channel dot
+struct CorrLookupDirectK {
+  TV src; CorrFeat tgt; TV coords, out;
+  GV_HD float dot(const float* a, int n, int lvl, int ty, int tx) const {
+    const uint16_t* b = tgt.lvl[lvl] + ((int64_t)n * tgt.h[lvl] * tgt.w[lvl] + (int64_t)ty * tgt.w[lvl] + tx) * tgt.c;
+    float acc = 0.f;
+    for (int k = 0; k < tgt.c; ++k) acc = fmaf(a[k], gv_h2f(b[k]), acc);
+    return acc * tgt.scale;
+  }
+  GV_HD void operator()(int64_t i) const {
+    const int ch = (int)(i % 324); int64_t r = i / 324;
+    const int x = (int)(r % coords.w); r /= coords.w; const int y = (int)(r % coords.h); const int n = (int)(r / coords.h);
+    const int lvl = ch / 81, k = ch % 81, a = k / 9, b = k % 9;
+    const float* c = coords.p + coords.off(n, y, x);
+    const float inv = 1.0f / (float)(1 << lvl);
+    const int H = tgt.h[lvl], W = tgt.w[lvl];
+    int x0, y0; float wx0, wx1, wy0, wy1;
+    corr_axis(c[0], inv, a, W, x0, wx0, wx1);
+    corr_axis(c[1], inv, b, H, y0, wy0, wy1);
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const float* f = src.p + src.off(n, y, x);
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    float v = 0.f;
+    if (vy0 && vx0) v += dot(f, n, lvl, y0, x0) * (wx0 * wy0);
+    if (vy0 && vx1) v += dot(f, n, lvl, y0, x1) * (wx1 * wy0);
+    if (vy1 && vx0) v += dot(f, n, lvl, y1, x0) * (wx0 * wy1);
+    if (vy1 && vx1) v += dot(f, n, lvl, y1, x1) * (wx1 * wy1);
+    out.p[out.off(n, y, x) + ch] = v;
+  }
+};
+
+#ifndef GV_HOSTSIM
+// One warp per (source pixel, level); the 8 warps of a CTA take 8 x-adjacent pixels of one level, whose windows overlap by ~90 % and
+// stay in L1.  A lane owns 8 of the 256 channels: the source feature sits in registers, every neighbour costs one 16-byte load per
+// lane (512 contiguous bytes per warp), and 32 neighbours at a time are reduced across the warp with a transposing butterfly
+// (31 shuffles for 32 sums).  The 100 dots land in shared memory; the 81 outputs are then the four-tap blends of CorrLookupK.
+constexpr int CLD_WARPS = 8;
+__global__ void __launch_bounds__(256) corr_lookup_direct_kernel(TV src, CorrFeat tgt, TV coords, TV out, int xblocks, int64_t n_groups) {
+  __shared__ float dots_s[CLD_WARPS][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* dots = dots_s[warp];
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    int64_t r = grp;
+    const int xb = (int)(r % xblocks); r /= xblocks;
+    const int y = (int)(r % coords.h); r /= coords.h;
+    const int n = (int)(r % coords.n); const int lvl = (int)(r / coords.n);
+    const int x = xb * CLD_WARPS + warp;
+    if (x < coords.w) {   // (warp-uniform)
+      const float* c = coords.p + coords.off(n, y, x);
+      const float inv = 1.0f / (float)(1 << lvl);
+      const int H = tgt.h[lvl], W = tgt.w[lvl];
+      const bool isx = lane < 9;
+      int my0; float mw0, mw1;
+      corr_axis(isx ? c[0] : c[1], inv, isx ? lane : (lane < 18 ? lane - 9 : 0), isx ? W : H, my0, mw0, mw1);
+      const int bx = __shfl_sync(0xffffffffu, my0, 0), by = __shfl_sync(0xffffffffu, my0, 9);
+      float f[8];
+      {
+        const float4* fp = reinterpret_cast<const float4*>(src.p + src.off(n, y, x) + lane * 8);
+        const float4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+        f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
+      }
+      const uint16_t* tb = tgt.lvl[lvl] + (int64_t)n * H * W * 256 + lane * 8;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        float p[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int nb = g * 32 + j;           // neighbour (gy, gx) of the 10 x 10 grid based at (by, bx)
+          const int gy = nb / 10, gx = nb - gy * 10;
+          const int ty = by + gy, tx = bx + gx;
+          float acc = 0.f;
+          if (nb < 100 && ty >= 0 && ty < H && tx >= 0 && tx < W) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(tb + ((int64_t)ty * W + tx) * 256));
+            const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), a3 = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+            acc = fmaf(f[0], a0.x, acc); acc = fmaf(f[1], a0.y, acc); acc = fmaf(f[2], a1.x, acc); acc = fmaf(f[3], a1.y, acc);
+            acc = fmaf(f[4], a2.x, acc); acc = fmaf(f[5], a2.y, acc); acc = fmaf(f[6], a3.x, acc); acc = fmaf(f[7], a3.y, acc);
+          }
+          p[j] = acc;
+        }
+        // transposing reduction: after the step with stride s, a lane keeps the half of the neighbour indices whose bit s equals its own
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+          const bool up = (lane & s) != 0;
+#pragma unroll
+          for (int i = 0; i < s; ++i) {
+            const float send = up ? p[i] : p[i + s], keep = up ? p[i + s] : p[i];
+            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+          }
+        }
+        dots[g * 32 + lane] = p[0] * tgt.scale;
+      }
+      __syncwarp();
+      float* o = out.p + out.off(n, y, x) + lvl * 81;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const int k = pass * 32 + lane, kk = k < 81 ? k : 80;
+        const int a = kk / 9, b = kk - a * 9;
+        int x0 = __shfl_sync(0xffffffffu, my0, a), y0 = __shfl_sync(0xffffffffu, my0, 9 + b);
+        float wx0 = __shfl_sync(0xffffffffu, mw0, a), wx1 = __shfl_sync(0xffffffffu, mw1, a);
+        float wy0 = __shfl_sync(0xffffffffu, mw0, 9 + b), wy1 = __shfl_sync(0xffffffffu, mw1, 9 + b);
+        if (k < 81) {
+          // window column a normally starts at bx + a; a floor() that lands one off through rounding moves the (then ~zero-weight)
+          // far tap outside the 10-wide grid: fold it onto the grid edge
+          int ix = x0 - bx, iy = y0 - by;
+          if (ix < 0) { ix = 0; x0 = bx; wx0 = wx1; wx1 = 0.f; } else if (ix > 8) { ix = 8; x0 = bx + 8; wx1 = wx0; wx0 = 0.f; }
+          if (iy < 0) { iy = 0; y0 = by; wy0 = wy1; wy1 = 0.f; } else if (iy > 8) { iy = 8; y0 = by + 8; wy1 = wy0; wy0 = 0.f; }
+          const int x1 = x0 + 1, y1 = y0 + 1;
+          const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+          const float* d = dots + iy * 10 + ix;
+          float v = 0.f;
+          if (vy0 && vx0) v += d[0] * (wx0 * wy0);
+          if (vy0 && vx1) v += d[1] * (wx1 * wy0);
+          if (vy1 && vx0) v += d[10] * (wx0 * wy1);
+          if (vy1 && vx1) v += d[11] * (wx1 * wy1);
+          o[k] = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+#endif
+
+bool corr_lookup_direct_supported(const TV& src, const CorrFeat& tgt, const TV& coords, const TV& out) {
+  return !src.f16 && !coords.f16 && !out.f16 && src.c == 256 && tgt.c == 256 && src.ld % 4 == 0 && src.sn % 4 == 0 &&
+         (reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && src.h == coords.h && src.w == coords.w && src.n == coords.n && out.c >= 324;
+}
+
+void corr_lookup_direct(Ctx& cx, const TV& src, const CorrFeat& tgt, const TV& coords, const TV& out) {
+  if (!corr_lookup_direct_supported(src, tgt, coords, out)) throw std::runtime_error("corr_lookup_direct: unsupported tensor layout");
+#ifndef GV_HOSTSIM
+  if (cx.dry) return;
+  cx.launches++;
+  for (int l = 0; l < 4; ++l)
+    if ((reinterpret_cast<uintptr_t>(tgt.lvl[l]) & 15) != 0) throw std::runtime_error("corr_lookup_direct: target features must be 16-byte aligned");
+  const int xblocks = (coords.w + CLD_WARPS - 1) / CLD_WARPS;
+  const int64_t groups = (int64_t)4 * coords.n * coords.h * xblocks;
+  if (cx.prof) cx.prof->begin(cx.stream, "corr_lookup_direct", (double)coords.pixels() * 4 * 100 * 256 * 2);
+  int64_t blocks = groups, cap = (int64_t)cx.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  corr_lookup_direct_kernel<<<(unsigned)blocks, 256, 0, cx.stream>>>(src, tgt, coords, out, xblocks, groups);
+  gv_check_launch("corr_lookup_direct");
+  if (cx.prof) cx.prof->end(cx.stream);
+#else
+  parallel_for(cx, coords.pixels() * 324, CorrLookupDirectK{src, tgt, coords, out}, "corr_lookup_direct");
+#endif
+}
+
+
 }  // namespace gv

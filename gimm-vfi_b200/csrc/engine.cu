@@ -111,6 +111,8 @@ std::string Engine::profile_json(gvStream_t stream) {
 Engine::Engine(int device) : device_(device) {
   if (const char* kn = getenv("GIMMVFI_PRECISE")) precise_ = atoi(kn);   // builder experiments: override the 3xTF32 stage mask
   if (const char* kn = getenv("GIMMVFI_HYPO_FAST")) hypo_fast_ = atoi(kn) != 0;
+  if (const char* kn = getenv("GIMMVFI_CORR_DIRECT")) corr_direct_max_t_ = atoi(kn);
+  if (const char* kn = getenv("GIMMVFI_GRU_HOIST")) gru_hoist_ = atoi(kn) != 0;
 #ifndef GV_HOSTSIM
   int count = 0;
   cuda_ok(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
@@ -347,6 +349,26 @@ void Engine::finalize_weights() {
     b.shape[0] = bz.shape[0] + br.shape[0]; b.data.insert(b.data.end(), br.data.begin(), br.data.end());
     raw_[u + ".gru.convzr" + sfx + ".weight"] = w; raw_[u + ".gru.convzr" + sfx + ".bias"] = b;
     pack_conv(u + ".gru.convzr" + sfx);
+    // The GRU input is [h | inp | motion features] (raft/update.py:122-124) and `inp` (the context network's output) does not change
+    // over the iterations: its share of every gate convolution is computed once per pair ("_inp", carries the bias) and enters the
+    // per-iteration convolutions over [h | motion] ("_hm", K = 256 instead of 384) as a pre-activation term.
+    for (const char* gate : {"zr", "q"}) {
+      const std::string g = u + ".gru.conv" + gate + sfx;
+      const HostTensor& wf = raw(g + ".weight"); const HostTensor& bf = raw(g + ".bias");
+      const int64_t co = wf.shape[0], ci = wf.shape[1], kk = wf.shape[2] * wf.shape[3];
+      if (ci != 384) throw std::runtime_error("gimmvfi: SepConvGRU input width");
+      HostTensor w_hm, w_in, b0 = bf;
+      w_hm.shape = {co, 256, wf.shape[2], wf.shape[3]}; w_in.shape = {co, 128, wf.shape[2], wf.shape[3]};
+      for (int64_t o = 0; o < co; ++o)
+        for (int64_t c = 0; c < ci; ++c) {
+          std::vector<float>& dst = (c >= 128 && c < 256) ? w_in.data : w_hm.data;
+          dst.insert(dst.end(), wf.data.begin() + (o * ci + c) * kk, wf.data.begin() + (o * ci + c + 1) * kk);
+        }
+      std::fill(b0.data.begin(), b0.data.end(), 0.f);
+      raw_[g + "_hm.weight"] = w_hm; raw_[g + "_hm.bias"] = b0;
+      raw_[g + "_inp.weight"] = w_in; raw_[g + "_inp.bias"] = bf;
+      pack_conv(g + "_hm"); pack_conv(g + "_inp");
+    }
   }
   pack_conv(u + ".mask.2", "", 0.25f);  // "scale mask to balance gradients" raft/update.py:153
   pack_xpacked(u + ".encoder.convf1", 4);
@@ -883,7 +905,17 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
     TV flo1 = A.tensor(2 * B, h, w, 128), zb = A.tensor(2 * B, h, w, 128), rh = A.tensor(2 * B, h, w, 128);
     TV fh = A.tensor(2 * B, h, w, 256), mask = A.tensor(2 * B, h, w, 576);
     init_coords(cx, coords1);
-    TV hcur = hx.slice(0, 128), xin = hx.slice(128, 256);
+    TV hcur = hx.slice(0, 128), xin = hx.slice(128, 256), mot = hx.slice(256, 128);
+    // iteration-invariant share of the gate convolutions (tensor-core modes; see finalize_weights)
+    const bool hoist = cx.tc && gru_hoist_;
+    TV Pzr[2], Pq[2];
+    if (hoist)
+      for (int s = 0; s < 2; ++s) {
+        const std::string sfx = s == 0 ? "1" : "2";
+        Pzr[s] = A.tensor(2 * B, h, w, 256); Pq[s] = A.tensor(2 * B, h, w, 128);
+        N.conv(u + ".gru.convzr" + sfx + "_inp", hx.slice(128, 128), Pzr[s]);
+        N.conv(u + ".gru.convq" + sfx + "_inp", hx.slice(128, 128), Pq[s]);
+      }
     for (int it = 0; it < raft_iters; ++it) {
       corr_lookup(cx, pyr.view(0), coords1, corr);
       coords_minus_grid(cx, coords1, flow, hx.slice(382, 2));
@@ -896,6 +928,14 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
       N.conv(u + ".encoder.conv", corflo, hx.slice(256, 126), ACT_RELU);
       // SepConvGRU raft/update.py:35-73 (horizontal 1x5 then vertical 5x1)
       for (const char* sfx : {"1", "2"}) {
+        if (hoist) {
+          const int s = sfx[0] - '1';
+          ConvEpi ezr; ezr.res = Pzr[s]; ezr.act2 = ACT_SIGMOID; ezr.mul = hcur; ezr.out2 = rh; ezr.split_c = 128;
+          N.conv_e(u + ".gru.convzr" + sfx + "_hm", hcur, mot, zb, ezr);
+          ConvEpi eq; eq.res = Pq[s]; eq.act2 = ACT_TANH; eq.gru_z = zb; eq.gru_h = hcur;
+          N.conv_e(u + ".gru.convq" + sfx + "_hm", rh, mot, hcur, eq);
+          continue;
+        }
         if (cx.tc) {   // one launch for both gates: 1020 tiles instead of 2 x 510 (3.45 waves of 148 SMs each)
           ConvEpi ezr; ezr.act1 = ACT_SIGMOID; ezr.mul = hcur; ezr.out2 = rh; ezr.split_c = 128;
           N.conv_e(u + ".gru.convzr" + sfx, hx, TV(), zb, ezr);
@@ -935,7 +975,28 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
   // ------------------------------------------------------------ bidirectional volume on projected features
   if (!fin) N.conv("amt_fproj", fmap, fproj);
   // the bidirectional volume only feeds TF32 layers (AMT update blocks) -> plain TF32 is at their input precision
-  Pyramid bpyr = build_pyramid(cx, fproj, B, tc_mode_ >= 1 ? 1 : 0);   // gimmvfi_r.py:133, raft/corr.py:23-44
+  // Few interpolated frames per pair (T <= corr_direct_max_t_): no volume at all - the lookup computes the dot products its window needs
+  // (corr.cu "volume-free lookup").  Otherwise the all-pairs pyramid, looked up T times.
+  Pyramid bpyr{}; CorrFeat bfeat{};
+  const bool corr_direct = tc_mode_ >= 1 && T <= corr_direct_max_t_ && fproj.c == 256 && h >= 16 && w >= 16;
+  if (corr_direct) {
+    TV Fl = fproj;
+    bfeat.c = 256; bfeat.scale = 1.0f / std::sqrt((float)fproj.c);
+    for (int l = 0; l < 4; ++l) {
+      bfeat.h[l] = Fl.h; bfeat.w[l] = Fl.w;
+      void* hp = A.alloc_f(((size_t)Fl.pixels() * Fl.c + 1) / 2);
+      features_to_half(cx, Fl, hp);
+      bfeat.lvl[l] = static_cast<const uint16_t*>(hp);
+      if (l < 3) { TV nx = A.tensor(2 * B, Fl.h / 2, Fl.w / 2, Fl.c); avgpool2_features(cx, Fl, nx); Fl = nx; }
+    }
+  } else {
+    bpyr = build_pyramid(cx, fproj, B, tc_mode_ >= 1 ? 1 : 0);   // gimmvfi_r.py:133, raft/corr.py:23-44
+  }
+  auto bfeat_of = [&](int sample0) {
+    CorrFeat f = bfeat;
+    for (int l = 0; l < 4; ++l) f.lvl[l] = bfeat.lvl[l] + (int64_t)sample0 * f.h[l] * f.w[l] * f.c;
+    return f;
+  };
 
   // ------------------------------------------------------------ hoisted (t-independent) decoder feature upsampling
   TV fup4 = A.tensor(2 * B, H4, W4, 128);   // NewInitDecoder.upsample   fi_components.py:234-244
@@ -957,7 +1018,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
     TV a = A.tensor(2 * B, H, W, 8);
     TV b = hs ? A.tensor_h(2 * B, H, W, 32) : A.tensor(2 * B, H, W, 32), c = A.tensor_like(b, 32), d = A.tensor_like(b, 64);
     pixel_shuffle(cx, feat4, a, 2);
-    if (cx.tc && !hs) N.conv7x(p + "2.0", a, b, ACT_PRELU, N.V(p + "2.1.weight"));   // x-packed 5x5 (pack_xpacked)
+    if (cx.tc) N.conv7x(p + "2.0", a, b, ACT_PRELU, N.V(p + "2.1.weight"));   // x-packed 5x5 (pack_xpacked)
     else N.convrelu(p + "2", a, b);
     N.convrelu(p + "3", b, c); N.convrelu(p + "4", c, b); N.convrelu(p + "5", b, c);
     N.convrelu(p + "6", c, d);
@@ -1039,8 +1100,13 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
       TV cA = A.tensor(B, h, w, 2), cB = A.tensor(B, h, w, 2);
       lookup_coords(cx, grid_flow.slice(2, 2), tdev, 0, cA);  // coord + flow1 * 1/(1-t) -> volume
       lookup_coords(cx, grid_flow.slice(0, 2), tdev, 1, cB);  // coord + flow0 * 1/t     -> transposed volume
-      corr_lookup(cx, bpyr.view(0), cA, corr648.slice(0, 324));
-      corr_lookup(cx, bpyr.view(B), cB, corr648.slice(324, 324));
+      if (corr_direct) {   // rows = frame 0's pixels against frame 1's features, and the transposed volume's counterpart
+        corr_lookup_direct(cx, fproj.batch(0, B), bfeat_of(B), cA, corr648.slice(0, 324));
+        corr_lookup_direct(cx, fproj.batch(B, B), bfeat_of(0), cB, corr648.slice(324, 324));
+      } else {
+        corr_lookup(cx, bpyr.view(0), cA, corr648.slice(0, 324));
+        corr_lookup(cx, bpyr.view(B), cB, corr648.slice(324, 324));
+      }
     }
     amt_update(N, "amt_update4_low", true, ft_4, fl4, grid_flow, corr648);
     {
@@ -1345,7 +1411,7 @@ void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t wor
   if (use_graph_ && !profile_ && !debug_ && fc_ == nullptr && reinterpret_cast<uintptr_t>(stream) > 2) {
     // everything a recorded launch sequence depends on: problem, every caller pointer, the workspace, the arithmetic mode, the weights
     std::vector<uint64_t> key = {(uint64_t)p.B, (uint64_t)p.Hf, (uint64_t)p.Wf, (uint64_t)p.T, (uint64_t)p.Hc, (uint64_t)p.Wc, 0, (uint64_t)tc_mode_, (uint64_t)precise_,
-                                 (uint64_t)hypo_fast_, (uint64_t)weights_version_, (uint64_t)raft_iters, (uint64_t)workspace, (uint64_t)workspace_bytes, (uint64_t)(uintptr_t)stream};
+                                 (uint64_t)hypo_fast_, (uint64_t)corr_direct_max_t_, (uint64_t)gru_hoist_, (uint64_t)weights_version_, (uint64_t)raft_iters, (uint64_t)workspace, (uint64_t)workspace_bytes, (uint64_t)(uintptr_t)stream};
     std::memcpy(&key[6], &p.ds, sizeof(float));
     const void* ptrs[] = {io.img_xs, io.coords, io.t, io.imgt_pred, io.img_warp_4, io.flowt0_1, io.flowt1_1, io.flowt0_4, io.flowt1_4, io.raft_flow, io.nflow, io.ninrflow, io.flowt};
     for (const void* q : ptrs) key.push_back((uint64_t)(uintptr_t)q);

@@ -193,7 +193,17 @@ struct PadReflectK16 {   // half-precision tensors (2-byte elements)
 };
 void pad_reflect(Ctx& cx, const TV& src, const TV& dst, int pad) {
   if (src.f16 != dst.f16) throw std::runtime_error("pad_reflect: source and destination must have the same storage type");
-  if (src.f16) { parallel_for(cx, dst.pixels() * dst.c, PadReflectK16{src, dst, pad}, "pad_reflect"); return; }
+  if (src.f16) {
+    // a pure copy: two half channels are one 32-bit element, so an even-strided half tensor is an fp32 tensor of half the width
+    if (src.c % 8 == 0 && src.ld % 8 == 0 && dst.ld % 8 == 0 && src.sn % 8 == 0 && dst.sn % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(src.p) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst.p) & 15) == 0) {
+      TV s2 = src, d2 = dst;
+      s2.f16 = d2.f16 = 0; s2.c /= 2; d2.c /= 2; s2.ld /= 2; d2.ld /= 2; s2.sn /= 2; d2.sn /= 2;
+      parallel_for(cx, d2.pixels() * (d2.c / 4), PadReflectK4{s2, d2, pad}, "pad_reflect");
+      return;
+    }
+    parallel_for(cx, dst.pixels() * dst.c, PadReflectK16{src, dst, pad}, "pad_reflect"); return;
+  }
   if (vec4_ok(src) && vec4_ok(dst)) { parallel_for(cx, dst.pixels() * (dst.c / 4), PadReflectK4{src, dst, pad}, "pad_reflect"); return; }
   parallel_for(cx, dst.pixels() * dst.c, PadReflectK{src, dst, pad}, "pad_reflect");
 }
@@ -857,14 +867,14 @@ __global__ void __launch_bounds__(256) softsplat_tile_kernel(TV lat, TV flow, TV
 #endif
 // fused splat: returns false when the layout does not qualify (caller falls back to memset + accumulate + normalise)
 bool softsplat_fused(Ctx& cx, const TV& lat, const TV& flow, const TV& metric, const float* t_per_sample, int t_mode, const float* flow_absmax,
-                     const TV& out) {
+                     const TV& out, bool force) {
 #ifndef GV_HOSTSIM
   static int on = -1;
   // off by default: DRAM traffic is 0.85x the op's algorithmic bytes (ncu), but fp32 (and 64-bit integer) atomic adds on SHARED memory are
   // compare-and-swap loops on sm_100a (ATOMS.CAST.SPIN): 115 M warp instructions, 0.318 ms vs 0.249 ms for the three-pass form whose
   // red.global.add.v4.f32 run in the L2 atomic units (profiles/r02_hbm_kernels_probe.log, r02_ncu_softsplat_tile.jsonl)
   if (on < 0) { const char* s = getenv("GIMMVFI_SPLAT_TILE"); on = s ? atoi(s) : 0; }
-  if (!on || !flow_absmax || lat.c != 16 || out.c != 16 || !vec4_ok(lat) || !vec4_ok(out) || (reinterpret_cast<uintptr_t>(flow.p) & 7) || flow.ld % 2 || flow.sn % 2 ||
+  if ((!on && !force) || !flow_absmax || lat.c != 16 || out.c != 16 || !vec4_ok(lat) || !vec4_ok(out) || (reinterpret_cast<uintptr_t>(flow.p) & 7) || flow.ld % 2 || flow.sn % 2 ||
       flow.f16 || metric.f16)
     return false;
   if (cx.dry) return true;

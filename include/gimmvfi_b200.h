@@ -160,6 +160,12 @@ int gimmvfi_op_corr_pool_pyramid(const float* l0, float* l1, float* l2, float* l
 /* 4-level 9x9 lookup raft/corr.py:144-165: lvl[k] = (n*h*w) x (h_k*w_k) pyramids; out (n,h,w,324) */
 int gimmvfi_op_corr_lookup(const float* const lvl[4], const int32_t lvl_h[4], const int32_t lvl_w[4], const gimmvfi_view* coords,
                            const gimmvfi_view* out, void* stream);
+/* Volume-free form of the same lookup (reference: raft/corr.py:23-93 BidirCorrBlock.__call__, looked up once per interpolated frame):
+ * src = the source frame's fp32 features (n,h,w,256); tgt_half[l] = the other frame's features, 2^l x 2^l average-pooled, IEEE half,
+ * dense NHWC (n, lvl_h[l], lvl_w[l], 256); out[..., l*81 + a*9 + b] = scale * <src, bilinear sample of level l>, as gimmvfi_op_corr_lookup
+ * returns from the volume pyramid. */
+int gimmvfi_op_corr_lookup_direct(const gimmvfi_view* src, const void* const tgt_half[4], const int32_t lvl_h[4], const int32_t lvl_w[4], float scale,
+                                  const gimmvfi_view* coords, const gimmvfi_view* out, void* stream);
 /* conv2d on NHWC: weight packed [kh*kw][cin][cout_ld], act: 0 none,1 relu,2 lrelu(0.1),3 prelu,4 sigmoid,5 tanh,6 sin */
 int gimmvfi_op_conv2d(const gimmvfi_view* in0, const gimmvfi_view* in1_or_null, const float* w_packed, const float* bias, int cin,
                       int cout, int cout_ld, int kh, int kw, int stride, int pad_h, int pad_w, int reflect, int act,

@@ -80,4 +80,9 @@ levels = K.corr_pyramid(fa, fb)
 coords = (torch.stack(torch.meshgrid(torch.arange(w, device=dev), torch.arange(h, device=dev), indexing="xy"), -1).float()[None]
           + smooth_flow(1, h, w, 2.0)).contiguous()
 timeit("corr_lookup 324ch 136x240", lambda: K.corr_lookup(levels, coords), h * w * (324 * 4.0 + 4 * 100 * 4.0))
+# ---- the volume-free form of the same lookup (BidirCorrBlock): 100 dot products of 256 channels per (pixel, level); bytes = the half
+# target pyramid once + the source features + the output (what a perfect cache would move)
+hl = K.half_feature_pyramid(fb)
+timeit("corr_lookup_direct 324ch 136x240", lambda: K.corr_lookup_direct(fa, fb, coords, levels=hl),
+       h * w * (256 * 4.0 + 324 * 4.0) + sum(l.numel() * 2.0 for l in hl))
 print("done", flush=True)

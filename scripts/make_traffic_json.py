@@ -14,8 +14,12 @@ PX = 1088 * 1920
 CAPTURES = {
     "conv2d_tc_3xf16": ("gpurun_out/r02d_ncu_3xf16_gru.ncu-rep", "conv2d_tc_kernel", 0, "1x5 384->128 @2x136x240 (SepConvGRU gate), 3xF16 split kernel on CTA pairs",
                         2 * 136 * 240 * (384 + 128) * 4.0),
-    "hyponet_fused3": ("gpurun_out/r02d_ncu_hyponet.ncu-rep", "hyponet_fused3", 0, "fused 5-layer HypoNet, fp32-class, 1088x1920 pixels", PX * (32 + 3 + 2) * 4.0),
-    "hyponet_fused": ("gpurun_out/r02d_ncu_hyponet.ncu-rep", "hyponet_fused_kernel", 0, "fused 5-layer HypoNet, TF32/half operands, 1088x1920 pixels", PX * (32 + 3 + 2) * 4.0),
+    "hyponet_fused3": ("gpurun_out/r02k_ncu_hyponet.ncu-rep", "hyponet_fused3", 0, "fused 5-layer HypoNet, fp32-class, 1088x1920 pixels", PX * (32 + 3 + 2) * 4.0),
+    "hyponet_fused": ("gpurun_out/r02k_ncu_hyponet.ncu-rep", "hyponet_fused_kernel", 0, "fused 5-layer HypoNet, TF32/half operands, 1088x1920 pixels", PX * (32 + 3 + 2) * 4.0),
+    "conv2d_tc_f16": ("gpurun_out/r02k_ncu_f16_trunk.ncu-rep", "conv2d_tc_kernel", 0, "3x3 256->256 @1x1088x1920, fp16 storage, kind::f16 on CTA pairs (final-decoder trunk)",
+                      PX * (256 + 256) * 2.0),
+    "conv2d_halo_tf32": ("gpurun_out/r02k_ncu_halo.ncu-rep", "conv3x3_halo", 0, "3x3 32->32 @2x1088x1920, halo-reuse kernel (direct-store epilogue)", 2 * PX * (32 + 32) * 4.0),
+    "softsplat_fused": ("gpurun_out/r02i_ncu_splat.ncu-rep", "softsplat_tile", 0, "one-pass tile splat 16+1 ch @1088x1920 (off by default)", PX * 140.0),
     "softsplat_accumulate": ("gpurun_out/r02a_hbm_kernels.ncu-rep", "softsplat_acc", 0, "forward splat 16+1 ch @1088x1920 (accumulate pass)", PX * 140.0),
     "softsplat_normalize": ("gpurun_out/r02a_hbm_kernels.ncu-rep", "SplatNorm", 0, "zeroeps normalisation @1088x1920", PX * (20 + 16) * 4.0),
     "backwarp": ("gpurun_out/r02a_hbm_kernels.ncu-rep", "Backwarp", 0, "backward warp 64 ch @1088x1920", PX * (2 * 64 + 2) * 4.0),
@@ -23,7 +27,10 @@ CAPTURES = {
     "instnorm_partial": ("gpurun_out/r02a_hbm_kernels.ncu-rep", "InPartial", 0, "instance-norm statistics 64 ch @2x544x960", 2 * 544 * 960 * 64 * 4.0),
     "instnorm_apply": ("gpurun_out/r02a_hbm_kernels.ncu-rep", "InApply", 0, "instance-norm apply + ReLU 64 ch @2x544x960", 2 * 544 * 960 * 64 * 8.0),
     "convex_upsample": ("gpurun_out/r02a_hbm_kernels.ncu-rep", "ConvexUp", 0, "convex x8 upsample 2x136x240 -> 2x1088x1920", (2 * 136 * 240 * 578 + 2 * 2 * PX) * 4.0),
-    "corr_lookup": ("gpurun_out/r02a_hbm_kernels.ncu-rep", "CorrLookup", 0, "4-level 9x9 correlation lookup, 136x240 source pixels", 136 * 240 * (324 + 400) * 4.0),
+    "corr_lookup": ("gpurun_out/r02k_ncu_lookup.ncu-rep", "corr_lookup_warp", 0, "4-level 9x9 correlation lookup from the volume pyramid, 136x240 source pixels (warp per pixel and level)",
+                    136 * 240 * (324 + 400) * 4.0),
+    "corr_lookup_direct": ("gpurun_out/r02k_ncu_lookup.ncu-rep", "corr_lookup_direct", 0, "volume-free 4-level 9x9 lookup (100 dots of 256 ch per pixel and level), 136x240 source pixels",
+                           136 * 240 * ((256 + 324) * 4.0 + 256 * 2.0 * (1 + 1 / 4 + 1 / 16 + 1 / 64))),
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TIME = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}

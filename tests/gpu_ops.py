@@ -109,6 +109,28 @@ def corr_lookup(levels, coords, lib=None):
     return out
 
 
+def half_feature_pyramid(tgt):
+    """(n,h,w,c) fp32 features -> the 4 average-pooled levels in half, dense NHWC (what the engine prepares for the volume-free lookup)"""
+    lv, cur = [], tgt.permute(0, 3, 1, 2)
+    for l in range(4):
+        lv.append(cur.permute(0, 2, 3, 1).contiguous().half())
+        cur = torch.nn.functional.avg_pool2d(cur, 2, 2)
+    return lv
+
+
+def corr_lookup_direct(src, tgt, coords, lib=None, levels=None):
+    """src, tgt: (n,h,w,256) fp32 features of the two frames; the half pooled target pyramid is prepared here with torch"""
+    lib = lib or default_lib()
+    n, h, w, c = src.shape
+    lv = levels if levels is not None else half_feature_pyramid(tgt)
+    out = torch.empty(n, h, w, 324, device=coords.device)
+    ptrs = (C.c_void_p * 4)(*[l.data_ptr() for l in lv])
+    hs = (C.c_int32 * 4)(*[l.shape[1] for l in lv])
+    ws = (C.c_int32 * 4)(*[l.shape[2] for l in lv])
+    lib.check(lib.dll.gimmvfi_op_corr_lookup_direct(C.byref(view_of(src)), ptrs, hs, ws, 1.0 / c ** 0.5, C.byref(view_of(coords)), C.byref(view_of(out)), _stream(out)))
+    return out
+
+
 def instnorm(x, relu, lib=None):
     lib = lib or default_lib()
     n, h, w, c = x.shape

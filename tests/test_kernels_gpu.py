@@ -144,6 +144,32 @@ def test_corr_volume_pyramid_lookup():
     assert abs(g2[0, 5 * 9 + 3, y, x].item() - v0[y, x, y - 1, x + 1].item()) <= 1e-4  # a=5 -> dx=+1, b=3 -> dy=-1
 
 
+@pytest.mark.parametrize("h,w", [(16, 20), (34, 61), (17, 24)])
+def test_corr_lookup_direct_vs_oracle(h, w):
+    """volume-free BidirCorrBlock lookup (raft/corr.py:23-93): same 324 channels as the oracle's volume -> pyramid -> lookup.
+    Target features are rounded to half in the kernel (11-bit significand, the plain-TF32 volume GEMM's operand precision):
+    |corr| ~ 16, 256 products -> ~1e-2 absolute."""
+    n, C = 2, 256
+    fa, fb = rnd(n, C, h, w, seed=1), rnd(n, C, h, w, seed=2)
+    vol = O.all_pairs_corr(fa.cpu(), fb.cpu())
+    pyr = O.corr_pyramid(vol.reshape(n * h * w, 1, h, w))
+    coords = O.coords_grid(n, h, w) + 3.0 * torch.randn(n, 2, h, w, generator=torch.Generator().manual_seed(3))
+    coords[0, :, 0, 0] = torch.tensor([-20.0, 50.0])     # far outside: zero padding
+    coords[0, :, 1, 1] = torch.tensor([3.0, 5.0])        # exactly integral coordinates
+    coords[1, :, 2, 3] = torch.tensor([-0.5, h - 0.5])   # straddling the border
+    got = K.nchw(K.corr_lookup_direct(K.nhwc(fa), K.nhwc(fb), K.nhwc(coords.to(DEV))))
+    ref = O.corr_lookup(pyr, coords)
+    d = (got.cpu() - ref).abs()
+    assert d.max().item() <= 3e-2 and d.mean().item() <= 2e-3
+    # with targets that are exactly representable in half the only difference is the fp32 summation order
+    fbh = fb.half().float()
+    vol = O.all_pairs_corr(fa.cpu(), fbh.cpu())
+    pyr0 = O.corr_pyramid(vol.reshape(n * h * w, 1, h, w))
+    got = K.nchw(K.corr_lookup_direct(K.nhwc(fa), K.nhwc(fbh), K.nhwc(coords.to(DEV))))
+    ref = O.corr_lookup(pyr0[:1] + pyr[1:], coords)
+    assert (got.cpu() - ref)[:, :81].abs().max().item() <= 2e-3   # level 0 (the pooled levels round their pooled features again)
+
+
 def test_instnorm():
     x = rnd(2, 96, 20, 28, seed=1, scale=3.0) + 2.0
     got = K.nchw(K.instnorm(K.nhwc(x), True))
