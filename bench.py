@@ -211,17 +211,19 @@ def load_ncu_traffic():
         return json.load(f)
 
 
-PRECISIONS = {"fp32": 0, "tf32": 1, "3xtf32": 2, "mixed": 3, "mixed4": 4}
+PRECISIONS = {"fp32": 0, "tf32": 1, "3xtf32": 2, "mixed3": 3, "mixed": 4}
 PRECISION_NOTES = {
     "fp32": "fp32 CUDA cores everywhere",
     "tf32": "RAFT fp32 (CUDA cores); post-RAFT convs TF32 tcgen05, fp32 accumulate",
-    "3xtf32": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32, fp32 accumulate",
-    "mixed": "RAFT + correlation: tcgen05 3xTF32 (operand split, fp32 register-promoted accumulation); post-RAFT convs: tcgen05 TF32; final-decoder "
-             "residual trunk (256 ch): fp16 storage + tcgen05 kind::f16; fp32 accumulate everywhere.  Parity at this exact workload: "
+    "3xtf32": "RAFT + its correlation volume: tcgen05 3xF16 (fp16 hi/lo operand split, fp32 register-promoted accumulation: fp32-class); post-RAFT convs: "
+              "tcgen05 TF32, fp32 accumulate; HypoNet fused, fp32-class",
+    "mixed3": "as 3xtf32 + the final decoder's 256-channel residual trunk stored in fp16 on tcgen05 kind::f16; fp32 accumulate everywhere",
+    "mixed": "RAFT + its correlation volume: tcgen05 3xF16 (fp16 hi/lo operand split, fp32 register-promoted accumulation: fp32-class); HypoNet fused, "
+             "fp32-class; post-RAFT convs: tcgen05 TF32 or, where the activations are stored in fp16 (final-decoder trunk, the 32/64-channel "
+             "full-resolution chains, init-decoder trunk, decoder concat), kind::f16; fp32 accumulate everywhere.  Parity at this exact workload: "
              "tests/test_bench_parity_gpu.py::big_r_1088x1920_t0.5 (reference-generated fixture, max|d imgt_pred| <= 1e-3)",
-    "mixed4": "mixed + fp16 storage of the 32/64-channel full-resolution chains, HypoNet activations, init-decoder trunk and the decoder concat",
 }
-DTYPES = {"fp32": "f32", "tf32": "tf32", "3xtf32": "tf32", "mixed": "tf32+f16 operands, f32 accumulate", "mixed4": "tf32+f16 operands, f32 accumulate"}
+DTYPES = {"fp32": "f32", "tf32": "tf32", "3xtf32": "tf32", "mixed3": "tf32+f16 operands, f32 accumulate", "mixed": "tf32+f16 operands, f32 accumulate"}
 NOTES = {"conv2d_tc_f16": "tcgen05 kind::f16 implicit GEMM on fp16-stored activations (TMA halo tiles, TMEM fp32 accumulators)",
          "conv2d_tc_tf32": "tcgen05 kind::tf32 implicit GEMM (TMA halo tiles, TMEM accumulators); the TF32 tensor peak is half the bf16 peak used as denominator (ceiling 0.5)",
          "conv2d_tc_3xtf32": "tcgen05 3xTF32 (3 MMAs per K step + register-promoted accumulation): 'achieved' counts ALGORITHMIC flops, the tensor pipe "

@@ -331,7 +331,7 @@ bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const Con
   const int amul = h ? 8 : 4, kblk = h ? 64 : 32;              // 16-byte TMA strides
   if (h && (split || !w.w_tc_h)) return false;
   if (in1.p && (in1.f16 != 0) != h) return false;
-  if (e.mul.f16 || e.gru_z.f16 || e.gru_h.f16) return false;   // only the residual may be half
+  if (e.mul.f16 || e.gru_z.f16 || e.gru_h.f16 || (e.mul.p && e.gru_z.p)) return false;   // only the residual may be half; gate multiply and GRU blend exclude each other
   if (e.split_c && (e.split_c % 32 || !e.out2.p || e.out2.f16 || e.gru_z.p)) return false;   // (a residual is indexed by the merged channel)
   if (!al16(in0.p) || in0.ld % amul || in0.sn % amul) return false;
   if (in1.p && (!al16(in1.p) || in1.ld % amul || in1.sn % amul || in0.c % kblk)) return false;

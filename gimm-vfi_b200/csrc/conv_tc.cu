@@ -65,6 +65,8 @@ struct Params {
   int seg;                         // SPLIT: K steps accumulated in TMEM before promotion to fp32 registers
   int split_f16;                   // SPLIT: the three MMAs run on kind::f16 with fp16 hi / lo operand pairs (K step = 64 elements = two
                                    // 32-channel fp32 A boxes; weights pre-split and pre-scaled at pack time): twice the MMA rate of 3xTF32
+  int halo, halo_w, halo_h;        // 3xF16 on CTA pairs, stride 1, taps > 1: the fp32 activation tile + halo ({32 ch, halo_w, halo_h} box, two 32-channel
+  int halo_sub;                    // sub-tiles of halo_sub bytes each) is fetched ONCE per K block and every tap's A operand is split from a shifted view
   float out_scale;                 // accumulator scale applied before the bias (all-pairs correlation: 1/sqrt(C))
   const float* bias;               // padded to tiles_n * BN
   int act1; const float* slope1;
@@ -259,18 +261,23 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * BK * 4;   // PAIR: this CTA's half of the weight rows
   const bool ATM = SPLIT && p.atmem;   // TMEM columns: accumulators at 0 / 128, A ring (64 columns per stage) from 256
   const bool SF16 = SPLIT && p.split_f16;   // (implies ATM)
-  const int a_all = (SPLIT && (!ATM || SF16)) ? 2 * A_BYTES : A_BYTES;   // SF16: two 32-channel fp32 sub-tiles per 64-element K step
+  const bool HALO = SPLIT && PAIR && p.halo;   // (implies SF16): ring stages hold the weight planes only, the activations sit in two halo buffers
+  const int a_all = HALO ? 0 : ((SPLIT && (!ATM || SF16)) ? 2 * A_BYTES : A_BYTES);   // SF16: two 32-channel fp32 sub-tiles per 64-element K step
   const uint32_t acc_stride = ATM ? 128u : 256u;
   const int stage_bytes = a_all + (SPLIT ? 2 * b_bytes : b_bytes);
   const int STAGES = p.stages;
-  float* stg_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + EW * STG_WARP_BYTES);
+  uint8_t* halo_base = smem + STAGES * stage_bytes;
+  const int halo_all = HALO ? 2 * 2 * p.halo_sub : 0;
+  float* stg_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes + halo_all);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + halo_all + EW * STG_WARP_BYTES);
   uint64_t* full_bar = bars;                          // [MAX_STAGES]  TMA bytes landed
   uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]  MMAs reading the stage retired
   uint64_t* xf_bar = bars + 2 * MAX_STAGES;           // [MAX_STAGES]  (SPLIT) A_lo written
   uint64_t* tfull_bar = bars + 3 * MAX_STAGES;        // [2]
   uint64_t* tempty_bar = bars + 3 * MAX_STAGES + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+  uint64_t* hfull_bar = bars + 3 * MAX_STAGES + 5;    // [2]  (HALO) halo tile landed
+  uint64_t* hempty_bar = bars + 3 * MAX_STAGES + 7;   // [2]  (HALO) all four splitter warps are done with it
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile index -> (pixel tile, N tile): consecutive indices 2k, 2k+1 (one cluster) share the N tile (same weights)
@@ -293,7 +300,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], (PAIR && !SPLIT) ? 2 : 1); mbar_init(&empty_bar[s], PAIR ? 1 : CL); mbar_init(&xf_bar[s], (PAIR && SPLIT) ? 10 : 4); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * EW : EW); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * EW : EW); mbar_init(&hfull_bar[a], 1); mbar_init(&hempty_bar[a], 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -317,9 +324,41 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ===================================================== TMA producer
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
+      int hb = 0; uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = (tile / CL) % p.tiles_n; int r = (tile / CL) / p.tiles_n * CL + tile % CL;
         const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
+        if (HALO) {
+          // K loop order: K block outermost.  The {32 ch, 16 + kw - 1, 8 + kh - 1} activation box of a K block is fetched once (two
+          // 32-channel sub-tiles) and serves all taps; per tap only the two weight-plane halves travel.  L2 -> SM bytes per K block
+          // of a 1x5 layer: 40 KB + 5 x 16 KB instead of 5 x 48 KB (the per-tap form ran at the L2 -> SM limit: 48 KB per K step and
+          // SM against ~43 B/clk/SM of L2 throughput = 1130 clk, the 12 MMAs of a step take 768).
+          const int x0 = tx * TILE_W - p.pw, y0 = ty * TILE_H - p.ph;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait_t(&hempty_bar[hb], hphase ^ 1, SPIN, ST_A);
+            uint8_t* hdst = halo_base + hb * 2 * p.halo_sub;
+            mbar_expect_tx(&hfull_bar[hb], (uint32_t)(2 * p.halo_w * p.halo_h * 128));
+            if (kb < p.c0_blocks) {
+              tma_load_4d(hdst, &tmA0, &hfull_bar[hb], kb * p.bk, x0, y0, n);
+              tma_load_4d(hdst + p.halo_sub, &tmA0, &hfull_bar[hb], kb * p.bk + 32, x0, y0, n);
+            } else {
+              tma_load_4d(hdst, &tmA1, &hfull_bar[hb], (kb - p.c0_blocks) * p.bk, x0, y0, n);
+              tma_load_4d(hdst + p.halo_sub, &tmA1, &hfull_bar[hb], (kb - p.c0_blocks) * p.bk + 32, x0, y0, n);
+            }
+            if (++hb == 2) { hb = 0; hphase ^= 1; }
+            for (int tap = 0; tap < p.taps; ++tap) {
+              mbar_wait_t(&empty_bar[stage], phase ^ 1, SPIN, ST_A);
+              uint8_t* b_dst = smem + stage * stage_bytes;
+              const uint32_t lead_xf = mapa_shared(smem_u32(&xf_bar[stage]), 0u);
+              mbar_expect_tx_cluster(lead_xf, (uint32_t)(2 * b_bytes));
+              const int row0 = nt * p.BN + (int)cta_rank * (p.BN / 2);
+              tma_load_3d_2sm(b_dst, &tmB, lead_xf, kb * p.bk, row0, tap);
+              tma_load_3d_2sm(b_dst + b_bytes, &tmB, lead_xf, kb * p.bk, row0, tap + p.taps);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int ky = tap / p.kw, kx = tap % p.kw;
           const int x0 = tx * TILE_W * p.stride + kx - p.pw, y0 = ty * TILE_H * p.stride + ky - p.ph;
@@ -411,7 +450,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint64_t ko = (uint64_t)(k * 2);
             if (ATM && PAIR) {
               const uint32_t ahi_t = tmem_base + 256u + (uint32_t)(stage * 64 + k * 8), alo_t = ahi_t + 32u;
-              if (SF16) {   // 8 TMEM columns = 16 packed halves = one K = 16 instruction
+              if (SF16 && (p.dbg & 4)) {   // (timing experiment: one of the three terms)
+                mma_f16_ts_2sm(d_tmem, ahi_t, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
+              } else if (SF16) {   // 8 TMEM columns = 16 packed halves = one K = 16 instruction
                 mma_f16_ts_2sm(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
                 mma_f16_ts_2sm(d_tmem, alo_t, bdesc + ko, idesc, 1u);
                 mma_f16_ts_2sm(d_tmem, ahi_t, bdesc + ko, idesc, 1u);
@@ -558,6 +599,52 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // the TMA fill, one read of A and the weight reads (it is the limiter: 128 B/clk vs 3 MMAs per K step).
       const int quarter = warp & 3, r = quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256u;
+      if (HALO) {
+        // tile pixel of this thread's row: (r / 16, r % 16); tap (ky, kx) reads halo row (y + ky) * halo_w + x + kx.  The 128B swizzle
+        // is a function of the shared-memory address, i.e. of the halo row index (the halo buffers are 1024-byte aligned).
+        int hb = 0; uint32_t hphase = 0;
+        const int py = r >> 4, px = r & 15;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait_t(&hfull_bar[hb], hphase, SPIN, ST_A);
+            const uint8_t* hsrc = halo_base + hb * 2 * p.halo_sub;
+            for (int tap = 0; tap < p.taps; ++tap) {
+              const int ky = tap / p.kw, kx = tap % p.kw;
+              const int hr = (py + ky) * p.halo_w + px + kx;
+              const uint8_t* arow = hsrc + hr * 128;
+              // the TMEM slot of this ring stage is free once the MMAs that read it have retired (the per-tap form learned that from
+              // the producer, which refilled the stage's A tile only then)
+              mbar_wait(&empty_bar[stage], phase ^ 1, SPIN);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              if (!(p.dbg & 1)) {
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                  uint32_t hi[16], lo[16];
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(arow + sub * p.halo_sub + ((c ^ (hr & 7)) << 4));
+                    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+                    hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h0); hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                    lo[2 * c] = *reinterpret_cast<const uint32_t*>(&l0); lo[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+                  }
+                  tmem_st16(trow + (uint32_t)(stage * 64 + sub * 16), hi);
+                  tmem_st16(trow + (uint32_t)(stage * 64 + 32 + sub * 16), lo);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              }
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&xf_bar[stage]), 0u));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hempty_bar[hb]);
+            if (++hb == 2) { hb = 0; hphase ^= 1; }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait_t(&full_bar[stage], phase, SPIN, ST_A);
@@ -677,11 +764,11 @@ void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, 
 
 // stride 2: the box spans 2x the tile in x and y and TMA keeps every second element (elementStrides), so shared memory
 // receives the same dense 16 x 8 pixel tile as at stride 1
-static void encode_act(CUtensorMap* m, const TV& t, int stride = 1) {
+static void encode_act(CUtensorMap* m, const TV& t, int stride = 1, int box_w = 0, int box_h = 0) {
   cuuint64_t dims[4] = {(cuuint64_t)t.c, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
   const cuuint64_t es = t.f16 ? 2 : 4;
   cuuint64_t str[3] = {(cuuint64_t)t.ld * es, (cuuint64_t)t.w * t.ld * es, (cuuint64_t)t.sn * es};
-  cuuint32_t box[4] = {(cuuint32_t)(t.f16 ? 2 * BK : BK), (cuuint32_t)(TILE_W * stride), (cuuint32_t)(TILE_H * stride), 1};   // 128-byte rows either way
+  cuuint32_t box[4] = {(cuuint32_t)(t.f16 ? 2 * BK : BK), (cuuint32_t)(box_w ? box_w : TILE_W * stride), (cuuint32_t)(box_h ? box_h : TILE_H * stride), 1};   // 128-byte rows either way
   encode(m, t.p, 4, dims, str, box, t.f16 != 0, stride);
 }
 
@@ -745,6 +832,13 @@ static int tc_split_f16() {   // GIMMVFI_TC_SPLIT_F16=0: keep the 3xTF32 form of
   if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_F16"); v = s ? atoi(s) : 1; }
   return v;
 }
+static int tc_split_halo() {   // GIMMVFI_TC_SPLIT_HALO=1: the 3xF16 kernel fetches its activation tile + halo once per K block instead of once per tap.
+                               // Halves the L2 -> SM bytes of the 1x5 / 3x3 layers and leaves their time unchanged (profiles/r02_split_kernel_kstep_probe.log):
+                               // the K step is not bound by that traffic.  Off by default.
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_HALO"); v = s ? atoi(s) : 0; }
+  return v;
+}
 static int tc_seg_f16() {   // K steps (of 64 elements) per TMEM accumulation segment of the 3xF16 form.  2 (default): draining the
                             // 64 KB accumulator (TMEM reads: 64 B/clk/SM) every step costs more than the step's MMAs; full-frame parity at
                             // 1088x1920: 0 of 6.27 M values off by > 1e-3 with 1 and with 2, one outlier appears with 3 (profiles/r02_fullframe_parity.log)
@@ -800,7 +894,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
     cuuint32_t box[3] = {BK, (cuuint32_t)(BN / CL), 1};   // CL == 2: each CTA fetches half of the weight rows
     encode(&mB, w.w_tc, 3, dims, str, box);
   }
-  Params p;
+  Params p = Params();
   p.taps = taps; p.kw = w.kw; p.ph = g.ph; p.pw = g.pw; p.stride = g.stride;
   p.f16_in = f16 ? 1 : 0; p.bk = bk; p.split_f16 = sf16 ? 1 : 0;
   p.c0_blocks = in1.p ? in0.c / bk : (in0.c + bk - 1) / bk;
@@ -820,19 +914,28 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   const bool sew8 = split && tc_epi8() && tc_split_epi8() && (tc_split_epi8() == 2 || !(BN == 128 && taps * (w.cin_pad / 32) >= 48));
   // CTA pairs: N/2 rows per CTA must keep the 8-row swizzle atom (and N % 16); the 3xTF32 kernel pairs only in its TMEM-A, 8-drain-warp form
   const bool pair = CL == 2 && BN % 32 == 0 && (split ? (tc_pair() >= 2 && p.atmem && sew8) : (tc_pair() != 0));
-  const int stage_bytes = split ? (((p.atmem && !sf16) ? 1 : 2) * A_BYTES + 2 * (pair ? BN / 2 : BN) * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4);
+  // 3xF16 on CTA pairs, stride 1, several taps: activation tile + halo fetched once per K block (see the producer)
+  p.halo = (sf16 && pair && taps > 1 && g.stride == 1 && tc_split_halo() && w.kw <= 9 && w.kh <= 9) ? 1 : 0;
+  p.halo_w = TILE_W + w.kw - 1; p.halo_h = TILE_H + w.kh - 1;
+  p.halo_sub = (p.halo_w * p.halo_h * 128 + 1023) & ~1023;
+  if (p.halo) {
+    encode_act(&mA0, in0, 1, p.halo_w, p.halo_h);
+    if (in1.p) encode_act(&mA1, in1, 1, p.halo_w, p.halo_h); else mA1 = mA0;
+  }
+  const int stage_bytes = p.halo ? 2 * (BN / 2) * BK * 4
+                                 : (split ? (((p.atmem && !sf16) ? 1 : 2) * A_BYTES + 2 * (pair ? BN / 2 : BN) * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4));
   static int ew8_wide = -1;   // GIMMVFI_TC_EPI8_WIDE=0: 4 epilogue warps for N > 128 tiles of CTA pairs
   if (ew8_wide < 0) { const char* q = getenv("GIMMVFI_TC_EPI8_WIDE"); ew8_wide = q ? atoi(q) : 1; }
   // K-poor plain layers are epilogue bound: 8 epilogue warps.  CTA pairs halve the per-stage smem footprint, which leaves room
   // for the 8-warp staging area next to >= 5 stages even at N = 256 (where the f16 trunk's epilogue is as long as its main loop)
   const bool ew8 = !split && (BN <= 128 || (pair && ew8_wide)) && tc_epi8();
   const int stg_bytes = ((ew8 || sew8) ? 8 : 4) * STG_WARP_BYTES;
-  const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES;
+  const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES - (p.halo ? 4 * p.halo_sub : 0);
   p.stages = budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.atmem && p.stages > 4) p.stages = 4;   // the TMEM A ring has 4 slots of 64 columns
   if (p.stages < 2) throw std::runtime_error("conv_tc: not enough shared memory for 2 pipeline stages");
-  const int smem = p.stages * stage_bytes + stg_bytes + BAR_BYTES + 1024;
+  const int smem = p.stages * stage_bytes + (p.halo ? 4 * p.halo_sub : 0) + stg_bytes + BAR_BYTES + 1024;
   const int padded_tiles = (pix_tiles_host + CL - 1) / CL * CL * tiles_n;
   int grid = padded_tiles < cx.sm_count ? padded_tiles : cx.sm_count;
   grid -= grid % CL;
@@ -894,7 +997,7 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
     cuuint32_t box[3] = {BK, (cuuint32_t)(BN / CL), 1};
     encode(&mB, fb_planes, 3, dims, str, box);
   }
-  Params p;
+  Params p = Params();
   p.taps = 1; p.kw = 1; p.ph = 0; p.pw = 0; p.stride = 1;
   p.kblocks = sf16 ? C / 64 : C / 32; p.c0_blocks = p.kblocks; p.f16_in = 0; p.bk = sf16 ? 2 * BK : BK; p.split_f16 = sf16 ? 1 : 0;
   p.tiles_x = (fa.w + TILE_W - 1) / TILE_W; p.tiles_y = (fa.h + TILE_H - 1) / TILE_H; p.n_img = 1; p.tiles_n = tiles_n;

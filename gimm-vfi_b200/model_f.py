@@ -52,7 +52,7 @@ class GIMMVFI_F(nn.Module):
         self._weights_dirty = True
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_weights_dirty", True))
         self.aux_outputs = True
-        self.tensor_cores = 3
+        self.tensor_cores = 4
         self.flow_backend: Optional[Callable] = None   # see the module docstring
 
     def _apply(self, fn, *a, **k):

@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, call t: halo form of the 3xF16 kernel (activation tile fetched once per K block): unit tests, K-step probe, parity, bench A/B
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_conv_tc_gpu.py -q -x > gpurun_out/r02t_unit.log 2>&1; echo "unit rc=$?"; tail -n 4 gpurun_out/r02t_unit.log | cut -c1-200
+PROBE_GRU=1 timeout 600 python scripts/tc_split_probe.py PROBE_STALL=1 PROBE_STALL=1,GIMMVFI_TC_SPLIT_HALO=0 PROBE_STALL=1,PROBE_EPI=q > gpurun_out/r02t_gru_probe.log 2>&1; cut -c1-260 gpurun_out/r02t_gru_probe.log
+timeout 600 python -m pytest tests/test_bench_parity_gpu.py tests/test_forward_gpu.py -q -s > gpurun_out/r02t_parity.log 2>&1; echo "== parity rc=$?"; grep -E "^big_r|\.big_r|Fbig_r|passed|failed" gpurun_out/r02t_parity.log | cut -c1-200
+timeout 300 python bench.py --no-cpu-baseline --no-torch-baseline --profile-json gpurun_out/r02t_profile.json > gpurun_out/r02t_bench.log 2>&1; tail -n 1 gpurun_out/r02t_bench.log | cut -c1-250
+GIMMVFI_TC_SPLIT_HALO=0 timeout 300 python bench.py --no-cpu-baseline --no-torch-baseline --profile-json gpurun_out/r02t_profile_nohalo.json > gpurun_out/r02t_bench_nohalo.log 2>&1; tail -n 1 gpurun_out/r02t_bench_nohalo.log | cut -c1-250
+timeout 300 python bench.py --precision mixed4 --no-cpu-baseline --no-torch-baseline --profile-json gpurun_out/r02t_profile_mode4.json > gpurun_out/r02t_bench_mode4.log 2>&1; tail -n 1 gpurun_out/r02t_bench_mode4.log | cut -c1-250

@@ -157,6 +157,32 @@ def test_conv2d_tc_gru_epilogues(f16):
     assert (K.nchw(got) - ref).abs().max().item() <= 1e-4
 
 
+def test_conv2d_tc_gru_hoisted_epilogues_cluster():
+    """SepConvGRU with the context term hoisted (engine.cu: `_hm` / `_inp` weights) at a size that runs on CTA pairs (halo form of the
+    3xF16 kernel): two input segments [h | motion], a pre-activation residual, sigmoid / tanh as act2, gate multiply on the r half
+    (merged z | r output) and the GRU blend  (raft/update.py:52-66)."""
+    n, H, W = 2, 136, 240
+    h = rnd(n, 128, H, W, seed=1); mot = rnd(n, 128, H, W, seed=2)
+    wq = rnd(128, 256, 1, 5, seed=3, scale=0.03); bq = torch.zeros(128, device=DEV)
+    pq = rnd(n, 128, H, W, seed=4, scale=0.5)
+    z = torch.sigmoid(rnd(n, 128, H, W, seed=6))
+    rh = rnd(n, 128, H, W, seed=7)
+    hn = K.nhwc(h)
+    got = K.conv2d_tc(K.nhwc(rh), wq, bq, 0, residual=K.nhwc(pq), act2=5, x1_nhwc=K.nhwc(mot), gru_z=K.nhwc(z), gru_h=hn, split=True, split_f16=True)
+    q = torch.tanh(F.conv2d(torch.cat([rh, mot], 1).double(), wq.double(), None, padding=(0, 2)) + pq.double()).float()
+    ref = (1 - z) * h + z * q
+    err = (K.nchw(got) - ref).abs().max().item()
+    print("hoisted q gate err %.3e" % err)
+    assert err <= 1e-4
+    # vertical half, plain sigmoid gate with the residual
+    wz = rnd(128, 256, 5, 1, seed=8, scale=0.03)
+    got = K.conv2d_tc(hn, wz, bq, 0, residual=K.nhwc(pq), act2=4, x1_nhwc=K.nhwc(mot), split=True, split_f16=True)
+    ref = torch.sigmoid(F.conv2d(torch.cat([h, mot], 1).double(), wz.double(), None, padding=(2, 0)) + pq.double()).float()
+    err = (K.nchw(got) - ref).abs().max().item()
+    print("hoisted z gate err %.3e" % err)
+    assert err <= 1e-4
+
+
 CLUSTER_CASES = [
     # >= 2 pixel tiles per SM -> the 2-CTA weight-multicast path; 168x240 = 21x15 = 315 tiles (odd: exercises padding)
     (64, 64, 3, 3, 168, 240, 1, 0, False),
@@ -165,6 +191,9 @@ CLUSTER_CASES = [
     (384, 128, 1, 5, 168, 240, 1, 4, True),
     (128, 256, 3, 3, 168, 240, 1, 1, True),     # split, 2 N tiles: both CTAs of a cluster must share the N tile
     (64, 64, 3, 3, 160, 256, 2, 0, True),
+    (256, 128, 5, 1, 168, 240, 1, 5, True),     # vertical gate, tanh: halo box 16 x 12
+    (96, 96, 3, 3, 170, 250, 1, 1, True),       # ragged tiles + a K block whose upper half is beyond the tensor (TMA zero fill), halo form
+    (28, 64, 7, 1, 168, 240, 1, 1, True),       # 7 taps: halo box 16 x 14 (the x-packed 7x7 stem's shape class)
 ]
 
 
@@ -179,7 +208,7 @@ def test_conv2d_tc_cluster_multicast(case, f16):
     b = rnd(cout, seed=3, scale=0.1)
     slope = (0.25 + 0.1 * rnd(cout, seed=4)) if act1 == 3 else None
     got = K.nchw(K.conv2d_tc(K.nhwc(x), w, b, act1, slope, split=split, split_f16=f16))
-    f = {0: lambda v: v, 1: F.relu, 3: lambda v: F.prelu(v, slope.double()), 4: torch.sigmoid}[act1]
+    f = {0: lambda v: v, 1: F.relu, 3: lambda v: F.prelu(v, slope.double()), 4: torch.sigmoid, 5: torch.tanh}[act1]
     if split:
         ref = f(F.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))).float()
         tol = 1e-4

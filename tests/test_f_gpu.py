@@ -33,7 +33,7 @@ def model():
 
 
 @pytest.mark.parametrize("name", sorted(MANIFEST))
-@pytest.mark.parametrize("mode", [3, 0], ids=["default", "fp32"])
+@pytest.mark.parametrize("mode", [4, 3, 0], ids=["default", "mode3", "fp32"])
 def test_f_synthesis_matches_reference(name, mode, model):
     meta = MANIFEST[name]
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))

@@ -22,15 +22,13 @@ DEV = "cuda"
 TOL_IMG = 1e-3
 
 
-MODES = {"tc_mixed_f16_trunk": 3, "tc_3xtf32_raft+tf32": 2, "tc_tf32_post_raft": 1, "fp32": 0}
-if os.environ.get("GIMMVFI_TEST_MODE4"):   # experimental mode 4 (fp16 storage of the 32/64-channel chains): opt-in until validated on hardware
-    MODES = {"tc_mixed_f16_chains": 4, **MODES}
+MODES = {"tc_mixed_f16_chains": 4, "tc_mixed_f16_trunk": 3, "tc_3xtf32_raft+tf32": 2, "tc_tf32_post_raft": 1, "fp32": 0}
 
 
 @pytest.fixture(scope="module", params=list(MODES))
 def model(request, weights0):
-    """All precision modes: 3 = default (mode 2 + the final decoder's 256-channel residual trunk stored in fp16 on kind::f16
-    tcgen05), 2 = RAFT on 3xTF32 tcgen05 + post-RAFT TF32 tcgen05, 1 = RAFT on fp32 CUDA cores, 0 = fp32 CUDA cores everywhere."""
+    """All precision modes: 4 = default (mode 3 + the 32/64-channel full-resolution chains, the init-decoder trunk and the decoder concat
+    stored in fp16), 3 = mode 2 + the final decoder's 256-channel residual trunk stored in fp16 on kind::f16 tcgen05, 2 = RAFT on 3xTF32 tcgen05 + post-RAFT TF32 tcgen05, 1 = RAFT on fp32 CUDA cores, 0 = fp32 CUDA cores everywhere."""
     m = GIMMVFI_R(seed=0).to(DEV).eval()
     m.load_state_dict(weights0, strict=True)
     m.tensor_cores = MODES[request.param]
