@@ -42,7 +42,9 @@ namespace tc {
 
 constexpr int TILE_H = 8, TILE_W = 16, BM = 128, BK = 32, MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 4;                // 16 KB
-constexpr int STG_PITCH = 36;                       // floats per staged row (32 + 4: keeps float4 alignment)
+constexpr int STG_PITCH = 32;                       // floats per staged row; the 16-byte chunk c of row r sits at chunk c ^ (r & 7): conflict-free
+                                                    // 128-bit row writes (phase 1) and row-segment reads (phase 2) without padding - the 4.5 KB the
+                                                    // padded form cost is what lets the 3xF16 kernel keep 4 pipeline stages at N = 128
 constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;  // staging area of one epilogue warp (32 rows)
 constexpr int BAR_BYTES = 512;
 
@@ -65,8 +67,6 @@ struct Params {
   int seg;                         // SPLIT: K steps accumulated in TMEM before promotion to fp32 registers
   int split_f16;                   // SPLIT: the three MMAs run on kind::f16 with fp16 hi / lo operand pairs (K step = 64 elements = two
                                    // 32-channel fp32 A boxes; weights pre-split and pre-scaled at pack time): twice the MMA rate of 3xTF32
-  int halo, halo_w, halo_h;        // 3xF16 on CTA pairs, stride 1, taps > 1: the fp32 activation tile + halo ({32 ch, halo_w, halo_h} box, two 32-channel
-  int halo_sub;                    // sub-tiles of halo_sub bytes each) is fetched ONCE per K block and every tap's A operand is split from a shifted view
   float out_scale;                 // accumulator scale applied before the bias (all-pairs correlation: 1/sqrt(C))
   const float* bias;               // padded to tiles_n * BN
   int act1; const float* slope1;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
     act_n<32>(o, p.act1, p.slope1, cbase, p.cout);
     const uint32_t srow = stg_s + (uint32_t)(lane * STG_PITCH * 4);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sts128(srow + j * 16, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    for (int j = 0; j < 8; ++j) sts128(srow + (uint32_t)((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
   }
   __syncwarp();
   const long long tp1 = tprof ? clock64() : 0;
@@ -142,7 +142,9 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
     const bool full4 = c + 3 < p.cout;
     const int y0 = ty * TILE_H + quarter * 2, x0 = tx * TILE_W + rsub;
     const bool interior = y0 + 1 < p.H && tx * TILE_W + TILE_W <= p.W;
-    const uint32_t sbase = stg_s + (uint32_t)((rsub * STG_PITCH + q8 * 4) * 4);
+    // staged row it * 4 + rsub, logical chunk q8: its swizzle phase (row & 7) is rsub for even `it`, rsub + 4 for odd
+    const uint32_t sb_even = stg_s + (uint32_t)(rsub * STG_PITCH * 4 + ((q8 ^ rsub) << 4));
+    const uint32_t sb_odd = stg_s + (uint32_t)(rsub * STG_PITCH * 4 + ((q8 ^ (rsub + 4)) << 4));
     const bool second = p.split_c > 0 && cbase >= p.split_c;          // merged z | r convolution: this chunk belongs to out2
     const TV& O = second ? p.out2 : p.out;
     const int c_loc = c - (second ? p.split_c : 0);
@@ -157,7 +159,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
       float o[32];
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        const float4 sv = lds128(sbase + (uint32_t)(it * 4 * STG_PITCH * 4));
+        const float4 sv = lds128(((it & 1) ? sb_odd : sb_even) + (uint32_t)(it * 4 * STG_PITCH * 4));
         o[4 * it] = sv.x; o[4 * it + 1] = sv.y; o[4 * it + 2] = sv.z; o[4 * it + 3] = sv.w;
       }
       if (p.act2 != ACT_NONE) act_rows<8>(o, p.act2, p.slope2, c, p.cout);
@@ -185,7 +187,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           ok[j] = interior || (y0 + g < p.H && x0 + j * 4 < p.W);
-          const float4 sv = lds128(sbase + (uint32_t)((g * 4 + j) * 4 * STG_PITCH * 4));
+          const float4 sv = lds128(((j & 1) ? sb_odd : sb_even) + (uint32_t)((g * 4 + j) * 4 * STG_PITCH * 4));
           o[4 * j] = sv.x; o[4 * j + 1] = sv.y; o[4 * j + 2] = sv.z; o[4 * j + 3] = sv.w;
         }
         if (p.res.p) {
@@ -261,23 +263,18 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * BK * 4;   // PAIR: this CTA's half of the weight rows
   const bool ATM = SPLIT && p.atmem;   // TMEM columns: accumulators at 0 / 128, A ring (64 columns per stage) from 256
   const bool SF16 = SPLIT && p.split_f16;   // (implies ATM)
-  const bool HALO = SPLIT && PAIR && p.halo;   // (implies SF16): ring stages hold the weight planes only, the activations sit in two halo buffers
-  const int a_all = HALO ? 0 : ((SPLIT && (!ATM || SF16)) ? 2 * A_BYTES : A_BYTES);   // SF16: two 32-channel fp32 sub-tiles per 64-element K step
+  const int a_all = (SPLIT && (!ATM || SF16)) ? 2 * A_BYTES : A_BYTES;   // SF16: two 32-channel fp32 sub-tiles per 64-element K step
   const uint32_t acc_stride = ATM ? 128u : 256u;
   const int stage_bytes = a_all + (SPLIT ? 2 * b_bytes : b_bytes);
   const int STAGES = p.stages;
-  uint8_t* halo_base = smem + STAGES * stage_bytes;
-  const int halo_all = HALO ? 2 * 2 * p.halo_sub : 0;
-  float* stg_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes + halo_all);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + halo_all + EW * STG_WARP_BYTES);
+  float* stg_base = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + EW * STG_WARP_BYTES);
   uint64_t* full_bar = bars;                          // [MAX_STAGES]  TMA bytes landed
   uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]  MMAs reading the stage retired
   uint64_t* xf_bar = bars + 2 * MAX_STAGES;           // [MAX_STAGES]  (SPLIT) A_lo written
   uint64_t* tfull_bar = bars + 3 * MAX_STAGES;        // [2]
   uint64_t* tempty_bar = bars + 3 * MAX_STAGES + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
-  uint64_t* hfull_bar = bars + 3 * MAX_STAGES + 5;    // [2]  (HALO) halo tile landed
-  uint64_t* hempty_bar = bars + 3 * MAX_STAGES + 7;   // [2]  (HALO) all four splitter warps are done with it
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile index -> (pixel tile, N tile): consecutive indices 2k, 2k+1 (one cluster) share the N tile (same weights)
@@ -300,7 +297,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], (PAIR && !SPLIT) ? 2 : 1); mbar_init(&empty_bar[s], PAIR ? 1 : CL); mbar_init(&xf_bar[s], (PAIR && SPLIT) ? 10 : 4); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * EW : EW); mbar_init(&hfull_bar[a], 1); mbar_init(&hempty_bar[a], 4); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], PAIR ? 2 * EW : EW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -324,41 +321,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ===================================================== TMA producer
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      int hb = 0; uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = (tile / CL) % p.tiles_n; int r = (tile / CL) / p.tiles_n * CL + tile % CL;
         const int tx = r % p.tiles_x; r /= p.tiles_x; const int ty = r % p.tiles_y; const int n = r / p.tiles_y;
-        if (HALO) {
-          // K loop order: K block outermost.  The {32 ch, 16 + kw - 1, 8 + kh - 1} activation box of a K block is fetched once (two
-          // 32-channel sub-tiles) and serves all taps; per tap only the two weight-plane halves travel.  L2 -> SM bytes per K block
-          // of a 1x5 layer: 40 KB + 5 x 16 KB instead of 5 x 48 KB (the per-tap form ran at the L2 -> SM limit: 48 KB per K step and
-          // SM against ~43 B/clk/SM of L2 throughput = 1130 clk, the 12 MMAs of a step take 768).
-          const int x0 = tx * TILE_W - p.pw, y0 = ty * TILE_H - p.ph;
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait_t(&hempty_bar[hb], hphase ^ 1, SPIN, ST_A);
-            uint8_t* hdst = halo_base + hb * 2 * p.halo_sub;
-            mbar_expect_tx(&hfull_bar[hb], (uint32_t)(2 * p.halo_w * p.halo_h * 128));
-            if (kb < p.c0_blocks) {
-              tma_load_4d(hdst, &tmA0, &hfull_bar[hb], kb * p.bk, x0, y0, n);
-              tma_load_4d(hdst + p.halo_sub, &tmA0, &hfull_bar[hb], kb * p.bk + 32, x0, y0, n);
-            } else {
-              tma_load_4d(hdst, &tmA1, &hfull_bar[hb], (kb - p.c0_blocks) * p.bk, x0, y0, n);
-              tma_load_4d(hdst + p.halo_sub, &tmA1, &hfull_bar[hb], (kb - p.c0_blocks) * p.bk + 32, x0, y0, n);
-            }
-            if (++hb == 2) { hb = 0; hphase ^= 1; }
-            for (int tap = 0; tap < p.taps; ++tap) {
-              mbar_wait_t(&empty_bar[stage], phase ^ 1, SPIN, ST_A);
-              uint8_t* b_dst = smem + stage * stage_bytes;
-              const uint32_t lead_xf = mapa_shared(smem_u32(&xf_bar[stage]), 0u);
-              mbar_expect_tx_cluster(lead_xf, (uint32_t)(2 * b_bytes));
-              const int row0 = nt * p.BN + (int)cta_rank * (p.BN / 2);
-              tma_load_3d_2sm(b_dst, &tmB, lead_xf, kb * p.bk, row0, tap);
-              tma_load_3d_2sm(b_dst + b_bytes, &tmB, lead_xf, kb * p.bk, row0, tap + p.taps);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-          }
-          continue;
-        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int ky = tap / p.kw, kx = tap % p.kw;
           const int x0 = tx * TILE_W * p.stride + kx - p.pw, y0 = ty * TILE_H * p.stride + ky - p.ph;
@@ -450,9 +415,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint64_t ko = (uint64_t)(k * 2);
             if (ATM && PAIR) {
               const uint32_t ahi_t = tmem_base + 256u + (uint32_t)(stage * 64 + k * 8), alo_t = ahi_t + 32u;
-              if (SF16 && (p.dbg & 4)) {   // (timing experiment: one of the three terms)
-                mma_f16_ts_2sm(d_tmem, ahi_t, bdesc + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
-              } else if (SF16) {   // 8 TMEM columns = 16 packed halves = one K = 16 instruction
+              if (SF16) {   // 8 TMEM columns = 16 packed halves = one K = 16 instruction
                 mma_f16_ts_2sm(d_tmem, ahi_t, blo + ko, idesc, (!seg_start || k > 0) ? 1u : 0u);
                 mma_f16_ts_2sm(d_tmem, alo_t, bdesc + ko, idesc, 1u);
                 mma_f16_ts_2sm(d_tmem, ahi_t, bdesc + ko, idesc, 1u);
@@ -599,52 +562,6 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // the TMA fill, one read of A and the weight reads (it is the limiter: 128 B/clk vs 3 MMAs per K step).
       const int quarter = warp & 3, r = quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256u;
-      if (HALO) {
-        // tile pixel of this thread's row: (r / 16, r % 16); tap (ky, kx) reads halo row (y + ky) * halo_w + x + kx.  The 128B swizzle
-        // is a function of the shared-memory address, i.e. of the halo row index (the halo buffers are 1024-byte aligned).
-        int hb = 0; uint32_t hphase = 0;
-        const int py = r >> 4, px = r & 15;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait_t(&hfull_bar[hb], hphase, SPIN, ST_A);
-            const uint8_t* hsrc = halo_base + hb * 2 * p.halo_sub;
-            for (int tap = 0; tap < p.taps; ++tap) {
-              const int ky = tap / p.kw, kx = tap % p.kw;
-              const int hr = (py + ky) * p.halo_w + px + kx;
-              const uint8_t* arow = hsrc + hr * 128;
-              // the TMEM slot of this ring stage is free once the MMAs that read it have retired (the per-tap form learned that from
-              // the producer, which refilled the stage's A tile only then)
-              mbar_wait(&empty_bar[stage], phase ^ 1, SPIN);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              if (!(p.dbg & 1)) {
-#pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                  uint32_t hi[16], lo[16];
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) {
-                    const float4 v = *reinterpret_cast<const float4*>(arow + sub * p.halo_sub + ((c ^ (hr & 7)) << 4));
-                    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-                    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
-                    hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h0); hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-                    lo[2 * c] = *reinterpret_cast<const uint32_t*>(&l0); lo[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l1);
-                  }
-                  tmem_st16(trow + (uint32_t)(stage * 64 + sub * 16), hi);
-                  tmem_st16(trow + (uint32_t)(stage * 64 + 32 + sub * 16), lo);
-                }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-              }
-              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&xf_bar[stage]), 0u));
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hempty_bar[hb]);
-            if (++hb == 2) { hb = 0; hphase ^= 1; }
-          }
-        }
-      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait_t(&full_bar[stage], phase, SPIN, ST_A);
@@ -764,11 +681,11 @@ void encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, 
 
 // stride 2: the box spans 2x the tile in x and y and TMA keeps every second element (elementStrides), so shared memory
 // receives the same dense 16 x 8 pixel tile as at stride 1
-static void encode_act(CUtensorMap* m, const TV& t, int stride = 1, int box_w = 0, int box_h = 0) {
+static void encode_act(CUtensorMap* m, const TV& t, int stride = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)t.c, (cuuint64_t)t.w, (cuuint64_t)t.h, (cuuint64_t)t.n};
   const cuuint64_t es = t.f16 ? 2 : 4;
   cuuint64_t str[3] = {(cuuint64_t)t.ld * es, (cuuint64_t)t.w * t.ld * es, (cuuint64_t)t.sn * es};
-  cuuint32_t box[4] = {(cuuint32_t)(t.f16 ? 2 * BK : BK), (cuuint32_t)(box_w ? box_w : TILE_W * stride), (cuuint32_t)(box_h ? box_h : TILE_H * stride), 1};   // 128-byte rows either way
+  cuuint32_t box[4] = {(cuuint32_t)(t.f16 ? 2 * BK : BK), (cuuint32_t)(TILE_W * stride), (cuuint32_t)(TILE_H * stride), 1};   // 128-byte rows either way
   encode(m, t.p, 4, dims, str, box, t.f16 != 0, stride);
 }
 
@@ -830,13 +747,6 @@ static int tc_split_epi8() {   // GIMMVFI_TC_SPLIT_EPI8: 0 = 4 drain warps in th
 static int tc_split_f16() {   // GIMMVFI_TC_SPLIT_F16=0: keep the 3xTF32 form of the split kernel
   static int v = -1;
   if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_F16"); v = s ? atoi(s) : 1; }
-  return v;
-}
-static int tc_split_halo() {   // GIMMVFI_TC_SPLIT_HALO=1: the 3xF16 kernel fetches its activation tile + halo once per K block instead of once per tap.
-                               // Halves the L2 -> SM bytes of the 1x5 / 3x3 layers and leaves their time unchanged (profiles/r02_split_kernel_kstep_probe.log):
-                               // the K step is not bound by that traffic.  Off by default.
-  static int v = -1;
-  if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_HALO"); v = s ? atoi(s) : 0; }
   return v;
 }
 static int tc_seg_f16() {   // K steps (of 64 elements) per TMEM accumulation segment of the 3xF16 form.  2 (default): draining the
@@ -914,28 +824,19 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   const bool sew8 = split && tc_epi8() && tc_split_epi8() && (tc_split_epi8() == 2 || !(BN == 128 && taps * (w.cin_pad / 32) >= 48));
   // CTA pairs: N/2 rows per CTA must keep the 8-row swizzle atom (and N % 16); the 3xTF32 kernel pairs only in its TMEM-A, 8-drain-warp form
   const bool pair = CL == 2 && BN % 32 == 0 && (split ? (tc_pair() >= 2 && p.atmem && sew8) : (tc_pair() != 0));
-  // 3xF16 on CTA pairs, stride 1, several taps: activation tile + halo fetched once per K block (see the producer)
-  p.halo = (sf16 && pair && taps > 1 && g.stride == 1 && tc_split_halo() && w.kw <= 9 && w.kh <= 9) ? 1 : 0;
-  p.halo_w = TILE_W + w.kw - 1; p.halo_h = TILE_H + w.kh - 1;
-  p.halo_sub = (p.halo_w * p.halo_h * 128 + 1023) & ~1023;
-  if (p.halo) {
-    encode_act(&mA0, in0, 1, p.halo_w, p.halo_h);
-    if (in1.p) encode_act(&mA1, in1, 1, p.halo_w, p.halo_h); else mA1 = mA0;
-  }
-  const int stage_bytes = p.halo ? 2 * (BN / 2) * BK * 4
-                                 : (split ? (((p.atmem && !sf16) ? 1 : 2) * A_BYTES + 2 * (pair ? BN / 2 : BN) * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4));
+  const int stage_bytes = split ? (((p.atmem && !sf16) ? 1 : 2) * A_BYTES + 2 * (pair ? BN / 2 : BN) * BK * 4) : (A_BYTES + (pair ? BN / 2 : BN) * BK * 4);
   static int ew8_wide = -1;   // GIMMVFI_TC_EPI8_WIDE=0: 4 epilogue warps for N > 128 tiles of CTA pairs
   if (ew8_wide < 0) { const char* q = getenv("GIMMVFI_TC_EPI8_WIDE"); ew8_wide = q ? atoi(q) : 1; }
   // K-poor plain layers are epilogue bound: 8 epilogue warps.  CTA pairs halve the per-stage smem footprint, which leaves room
   // for the 8-warp staging area next to >= 5 stages even at N = 256 (where the f16 trunk's epilogue is as long as its main loop)
   const bool ew8 = !split && (BN <= 128 || (pair && ew8_wide)) && tc_epi8();
   const int stg_bytes = ((ew8 || sew8) ? 8 : 4) * STG_WARP_BYTES;
-  const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES - (p.halo ? 4 * p.halo_sub : 0);
+  const int budget = 227 * 1024 - 1024 /*align*/ - stg_bytes - BAR_BYTES;
   p.stages = budget / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.atmem && p.stages > 4) p.stages = 4;   // the TMEM A ring has 4 slots of 64 columns
   if (p.stages < 2) throw std::runtime_error("conv_tc: not enough shared memory for 2 pipeline stages");
-  const int smem = p.stages * stage_bytes + (p.halo ? 4 * p.halo_sub : 0) + stg_bytes + BAR_BYTES + 1024;
+  const int smem = p.stages * stage_bytes + stg_bytes + BAR_BYTES + 1024;
   const int padded_tiles = (pix_tiles_host + CL - 1) / CL * CL * tiles_n;
   int grid = padded_tiles < cx.sm_count ? padded_tiles : cx.sm_count;
   grid -= grid % CL;

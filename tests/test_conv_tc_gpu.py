@@ -158,8 +158,8 @@ def test_conv2d_tc_gru_epilogues(f16):
 
 
 def test_conv2d_tc_gru_hoisted_epilogues_cluster():
-    """SepConvGRU with the context term hoisted (engine.cu: `_hm` / `_inp` weights) at a size that runs on CTA pairs (halo form of the
-    3xF16 kernel): two input segments [h | motion], a pre-activation residual, sigmoid / tanh as act2, gate multiply on the r half
+    """SepConvGRU with the context term hoisted (engine.cu: `_hm` / `_inp` weights) at a size that runs on CTA pairs:
+    two input segments [h | motion], a pre-activation residual, sigmoid / tanh as act2, gate multiply on the r half
     (merged z | r output) and the GRU blend  (raft/update.py:52-66)."""
     n, H, W = 2, 136, 240
     h = rnd(n, 128, H, W, seed=1); mot = rnd(n, 128, H, W, seed=2)
@@ -191,9 +191,9 @@ CLUSTER_CASES = [
     (384, 128, 1, 5, 168, 240, 1, 4, True),
     (128, 256, 3, 3, 168, 240, 1, 1, True),     # split, 2 N tiles: both CTAs of a cluster must share the N tile
     (64, 64, 3, 3, 160, 256, 2, 0, True),
-    (256, 128, 5, 1, 168, 240, 1, 5, True),     # vertical gate, tanh: halo box 16 x 12
-    (96, 96, 3, 3, 170, 250, 1, 1, True),       # ragged tiles + a K block whose upper half is beyond the tensor (TMA zero fill), halo form
-    (28, 64, 7, 1, 168, 240, 1, 1, True),       # 7 taps: halo box 16 x 14 (the x-packed 7x7 stem's shape class)
+    (256, 128, 5, 1, 168, 240, 1, 5, True),     # vertical gate, tanh, on CTA pairs
+    (96, 96, 3, 3, 170, 250, 1, 1, True),       # ragged tiles + a K block whose upper half is beyond the tensor (TMA zero fill)
+    (28, 64, 7, 1, 168, 240, 1, 1, True),       # 7 taps (the x-packed 7x7 stem's shape class)
 ]
 
 
