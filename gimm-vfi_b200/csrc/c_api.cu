@@ -296,9 +296,10 @@ int gimmvfi_op_conv2d_halo(const gimmvfi_view* in0, const void* w_tc_h, const fl
     throw std::runtime_error("conv2d_halo is a tcgen05 kernel; not available in the host simulation");
 #else
     Ctx cx = op_ctx(stream);
-    ConvW w; w.b = bias; w.cin = cin; w.cout = cout; w.kh = 3; w.kw = 3; w.w_tc = w_tc; w.has_lo = true;
+    const int k = prepadded == 2 ? 1 : 3;   // prepadded: 0 = 3x3 zero padding 1, 1 = 3x3 on a pre-padded input, 2 = 1x1
+    ConvW w; w.b = bias; w.cin = cin; w.cout = cout; w.kh = k; w.kw = k; w.w_tc = w_tc; w.has_lo = true;
     w.cout_pad = tc_cout_pad(cout); w.cin_pad = (cin + 31) & ~31; w.w_tc_h = w_tc_h; w.cin_pad_h = (cin + 63) & ~63;
-    ConvGeom g; g.stride = 1; g.ph = prepadded ? 0 : 1; g.pw = prepadded ? 0 : 1; g.loose_w = prepadded ? 1 : 0;
+    ConvGeom g; g.stride = 1; g.ph = prepadded == 1 ? 0 : k / 2; g.pw = g.ph; g.loose_w = prepadded == 1 ? 1 : 0;
     TV a0 = to_tv(in0); TV r = to_tv(residual); TV o = to_tv(out);
     a0.f16 = half_mask & 1; o.f16 = (half_mask >> 1) & 1; if (r.p) r.f16 = (half_mask >> 2) & 1;
     ConvEpi ep; ep.act1 = act1; ep.slope1 = slope1; ep.res = r; ep.act2 = act2; ep.slope2 = slope2;

@@ -38,6 +38,7 @@ struct HaloParams {
   int pitch;        // P: pixels per halo row (16 or 10)
   int halo_bytes;   // bytes of one pipeline stage (multiple of 1024)
   int kinstr;       // MMAs per tap: ceil(cin bytes / 32) <= 4
+  int ntaps;        // 9 (3x3) or 1 (1x1: the "halo" box is the 8 x 16 tile itself, pitch 8)
   const float* bias; int act1; const float* slope1; int act2; const float* slope2;
   TV res, out;
 };
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
                                                              const __grid_constant__ HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int w_bytes = 9 * p.BN * 128;
+  const int w_bytes = p.ntaps * p.BN * 128;
   const int w_region = (w_bytes + 1023) & ~1023;
   uint8_t* wsm = smem;
   uint8_t* halo = smem + w_region;
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo_kernel(const __grid_const
         const uint32_t h_s = smem_u32(halo + stage * p.halo_bytes), w_s = smem_u32(wsm);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
+          if (tap >= p.ntaps) break;
           const int ky = tap / 3, kx = tap % 3;
           const uint64_t ad = p.copies3 ? make_smem_desc(h_s + (uint32_t)(kx * (HL_TW * HL_BH * 128) + ky * HL_TW * 128))          // copy kx, image row ky
                                         : make_desc_sbo(h_s + (uint32_t)((ky * p.pitch + kx) * 128), (uint32_t)(p.pitch * 128), p.dbg);   // shifted view of the halo tile
@@ -222,12 +224,13 @@ static int tc_halo() {   // GIMMVFI_TC_HALO=0: K-poor 3x3 layers stay on the per
 
 bool conv2d_halo_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!tc_halo() || in1.p || w.kh != 3 || w.kw != 3 || g.stride != 1 || g.reflect || w.cout > 64) return false;
+  if (!tc_halo() || in1.p || !((w.kh == 3 && w.kw == 3) || (w.kh == 1 && w.kw == 1)) || g.stride != 1 || g.reflect || w.cout > 64) return false;
   if (e.mul.p || e.gru_z.p || e.out2.p || e.split_c) return false;
   const bool h = in0.f16 != 0;
   if (h ? (!w.w_tc_h || w.cin_pad_h != 64 || in0.c > 64) : (!w.w_tc || w.cin_pad != 32 || in0.c > 32)) return false;
   if (!al16(in0.p) || in0.ld % (h ? 8 : 4) || in0.sn % (h ? 8 : 4)) return false;
-  if (g.loose_w ? (g.ph != 0 || g.pw != 0 || in0.h < out.h + 2 || in0.w < out.w + 2) : (g.ph != 1 || g.pw != 1 || in0.h != out.h || in0.w != out.w)) return false;
+  const int pad = w.kh / 2;
+  if (g.loose_w ? (g.ph != 0 || g.pw != 0 || in0.h < out.h + 2 * pad || in0.w < out.w + 2 * pad || pad == 0) : (g.ph != pad || g.pw != pad || in0.h != out.h || in0.w != out.w)) return false;
   if (out.ld % 4 || (e.res.p && e.res.ld % 4)) return false;
   return in0.n == out.n;
 }
@@ -235,6 +238,8 @@ bool conv2d_halo_supported(const TV& in0, const TV& in1, const ConvW& w, const C
 void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out) {
   using namespace tc;
   const bool f16 = in0.f16 != 0;
+  const bool one = w.kh == 1;                          // 1x1: no halo, one tap
+  const int ntaps = one ? 1 : 9;
   const int c16 = (w.cout + 15) & ~15;
   const int BN = c16 <= 32 ? 32 : 64;                 // two epilogue warps per lane quarter split BN into 16- or 32-column halves
   if (w.cout_pad < c16) throw std::runtime_error("conv2d_halo: weight padding");
@@ -243,30 +248,31 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
     const cuuint64_t es = f16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)in0.c, (cuuint64_t)in0.w, (cuuint64_t)in0.h, (cuuint64_t)in0.n};
     cuuint64_t str[3] = {(cuuint64_t)in0.ld * es, (cuuint64_t)in0.w * in0.ld * es, (cuuint64_t)in0.sn * es};
-    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)(halo_mode() == 3 ? HL_TW : HL_BW), HL_BH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)(one ? HL_TW : (halo_mode() == 3 ? HL_TW : HL_BW)), (cuuint32_t)(one ? HL_TH : HL_BH), 1};
     encode(&mA, in0.p, 4, dims, str, box, f16);
   }
   {   // weights [tap][cout_pad][K block]: rows beyond cout_pad are zero-filled by TMA
     const int kpad = f16 ? w.cin_pad_h : w.cin_pad;
     const cuuint64_t es = f16 ? 2 : 4;
-    cuuint64_t dims[3] = {(cuuint64_t)kpad, (cuuint64_t)w.cout_pad, 9};
+    cuuint64_t dims[3] = {(cuuint64_t)kpad, (cuuint64_t)w.cout_pad, (cuuint64_t)ntaps};
     cuuint64_t str[2] = {(cuuint64_t)kpad * es, (cuuint64_t)kpad * w.cout_pad * es};
-    cuuint32_t box[3] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)BN, 9};
+    cuuint32_t box[3] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)BN, (cuuint32_t)ntaps};
     encode(&mW, f16 ? w.w_tc_h : static_cast<const void*>(w.w_tc), 3, dims, str, box, f16);
   }
   HaloParams p;
   p.tiles_x = (out.w + HL_TW - 1) / HL_TW; p.tiles_y = (out.h + HL_TH - 1) / HL_TH; p.n_img = out.n; p.H = out.h; p.W = out.w; p.cout = w.cout; p.BN = BN;
-  p.origin = g.loose_w ? 0 : -1; p.f16_in = f16 ? 1 : 0; p.round_out = out.f16 ? 0 : 1;
+  p.origin = (g.loose_w || one) ? 0 : -1; p.f16_in = f16 ? 1 : 0; p.round_out = out.f16 ? 0 : 1;
   static int spin = -1;
   if (spin < 0) { const char* s = getenv("GIMMVFI_TC_SPIN_LIMIT"); spin = s ? atoi(s) : 400; }
   p.spin_limit = spin;
   { const char* d = getenv("GIMMVFI_HALO_DBG"); p.dbg = d ? atoi(d) : 0; }
   p.bias = w.b; p.act1 = e.act1; p.slope1 = e.slope1; p.act2 = e.act2; p.slope2 = e.slope2; p.res = e.res; p.out = out;
-  p.copies3 = halo_mode() == 3 ? 1 : 0;
+  p.copies3 = (!one && halo_mode() == 3) ? 1 : 0;
+  p.ntaps = ntaps;
   p.kinstr = (in0.c * (f16 ? 2 : 4) + 31) / 32;
-  p.pitch = HL_BW;
-  p.halo_bytes = p.copies3 ? 3 * HL_TW * HL_BH * 128 : ((p.pitch * HL_BH * 128 + 1023) & ~1023);
-  const int w_region = (9 * BN * 128 + 1023) & ~1023;
+  p.pitch = one ? HL_TW : HL_BW;
+  p.halo_bytes = one ? HL_TW * HL_TH * 128 : (p.copies3 ? 3 * HL_TW * HL_BH * 128 : ((p.pitch * HL_BH * 128 + 1023) & ~1023));
+  const int w_region = (ntaps * BN * 128 + 1023) & ~1023;
   const int fixed = w_region + 256 + 1024;
   p.stages = (227 * 1024 - fixed) / p.halo_bytes;
   if (p.stages > HL_MAX_STAGES) p.stages = HL_MAX_STAGES;
@@ -279,8 +285,8 @@ void conv2d_halo(Ctx& cx, const TV& in0, const ConvW& w, const ConvGeom& g, cons
   cx.launches++;
   if (cx.prof) {
     char nm[128];
-    snprintf(nm, sizeof nm, "conv2d_halo_%s k3x3 c%d>%d @%dx%dx%d", f16 ? "f16" : "tf32", w.cin, w.cout, out.n, out.h, out.w);
-    cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * 9);
+    snprintf(nm, sizeof nm, "conv2d_halo_%s k%dx%d c%d>%d @%dx%dx%d", f16 ? "f16" : "tf32", w.kh, w.kw, w.cin, w.cout, out.n, out.h, out.w);
+    cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * ntaps);
   }
   conv3x3_halo_kernel<<<grid, 320, smem, cx.stream>>>(mA, mW, p);
   gv_check_launch("conv2d_halo");

@@ -193,9 +193,10 @@ int gimmvfi_op_conv2d_tc_f16(const gimmvfi_view* in0, const gimmvfi_view* in1_or
                              const gimmvfi_view* residual_or_null, int act2, const float* slope2, int half_mask,
                              const gimmvfi_view* out, void* stream);
 /* nn.InstanceNorm2d + optional relu: raft/extractor.py:133-134; scratch >= gimmvfi_instnorm_scratch_floats */
-/* 3x3 stride-1 convolution of a K-poor layer (cin <= 32 fp32 or <= 64 half, cout <= 64): halo tile loaded once, the 9 taps as shifted
- * UMMA operand views (csrc/conv_halo.cu).  Weight packing as gimmvfi_op_conv2d_tc (plane 0) / gimmvfi_op_conv2d_tc_f16; half_mask bit 0:
- * input half, bit 1: output half, bit 2: residual half; prepadded != 0: `in0` is (h+2, w+2) and carries its own padding (valid conv). */
+/* 3x3 (or 1x1) stride-1 convolution of a K-poor layer (cin <= 32 fp32 or <= 64 half, cout <= 64): halo tile loaded once, the 9 taps as
+ * shifted UMMA operand views, weights resident in shared memory (csrc/conv_halo.cu).  Weight packing as gimmvfi_op_conv2d_tc (plane 0) /
+ * gimmvfi_op_conv2d_tc_f16; half_mask bit 0: input half, bit 1: output half, bit 2: residual half; prepadded: 0 = 3x3 with zero padding 1,
+ * 1 = 3x3, `in0` is (h+2, w+2) and carries its own padding (valid conv), 2 = 1x1. */
 int gimmvfi_op_conv2d_halo(const gimmvfi_view* in0, const void* w_tc_h_or_null, const float* w_tc, const float* bias, int cin, int cout,
                            int act1, const float* slope1, const gimmvfi_view* residual_or_null, int act2, const float* slope2,
                            int half_mask, int prepadded, const gimmvfi_view* out, void* stream);

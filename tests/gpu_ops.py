@@ -253,7 +253,7 @@ def conv2d_halo(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2
     """3x3 K-poor conv through csrc/conv_halo.cu; x (and residual) may be torch.float16 NHWC tensors"""
     lib = lib or default_lib()
     cout, cin, kh, kw = w.shape
-    assert kh == 3 and kw == 3
+    assert (kh, kw) in ((3, 3), (1, 1)) and not (prepadded and kh == 1)
     in_half = x_nhwc.dtype == torch.float16
     pw_h = pack_weight_tc_f16(w) if in_half else None
     pw = pack_weight_tc(w)
@@ -266,5 +266,5 @@ def conv2d_halo(x_nhwc, w, b, act1=0, slope1=None, residual=None, act2=0, slope2
     V = lambda t: C.byref(view_of(t)) if t is not None else None
     P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
     lib.check(lib.dll.gimmvfi_op_conv2d_halo(V(x_nhwc), P(pw_h), P(pw), P(bb), cin, cout, act1, P(slope1), V(residual), act2, P(slope2), mask,
-                                             int(prepadded), V(out), _stream(out)))
+                                             2 if kh == 1 else int(prepadded), V(out), _stream(out)))
     return out

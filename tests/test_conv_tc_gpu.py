@@ -345,6 +345,8 @@ HALO_CASES = [
     (32, 16, 34, 26, 1, 0, False, False),     # cout 16
     (64, 64, 32, 24, 1, 3, False, True),      # half-precision storage: 64 channels = one K block
     (64, 64, 35, 20, 1, 0, True, True),
+    (64, 64, 40, 56, 2, 1, False, True, 1),   # 1x1 (final-decoder upsample.7): one tap, the box is the 8 x 16 tile itself
+    (32, 48, 33, 20, 1, 3, False, False, 1),  # 1x1 fp32 / TF32, ragged tiles
 ]
 
 
@@ -352,20 +354,21 @@ HALO_CASES = [
 def test_conv2d_halo(case):
     """csrc/conv_halo.cu: the tile + halo is loaded once and every tap is an MMA on a shifted view (UMMA base offset).  Strict
     reference = fp64 convolution of the operands as the tensor core sees them (TF32-truncated activations / RN weights, or halves)."""
-    cin, cout, H, W, n, act1, use_res, half = case
+    cin, cout, H, W, n, act1, use_res, half = case[:8]
+    ks = case[8] if len(case) > 8 else 3
     x = rnd(n, cin, H, W, seed=1)
-    w = rnd(cout, cin, 3, 3, seed=2, scale=1.0 / (cin * 9) ** 0.5)
+    w = rnd(cout, cin, ks, ks, seed=2, scale=1.0 / (cin * ks * ks) ** 0.5)
     b = rnd(cout, seed=3, scale=0.1)
     slope = (0.25 + 0.1 * rnd(cout, seed=4)) if act1 == 3 else None
     res = rnd(n, cout, H, W, seed=5) if use_res else None
     xn = K.nhwc(x)
     if half:
         got = K.conv2d_halo(xn.half(), w, b, act1, slope, residual=K.nhwc(res).half() if use_res else None, out_half=True)
-        ref = F.conv2d(x.half().double(), w.half().double(), b.double(), padding=1)
+        ref = F.conv2d(x.half().double(), w.half().double(), b.double(), padding=ks // 2)
     else:
         got = K.conv2d_halo(xn, w, b, act1, slope, residual=K.nhwc(res) if use_res else None)
-        ref = F.conv2d(K.tf32_trunc(x).double(), K.tf32_rn(w).double(), b.double(), padding=1)
-    f = {0: lambda v: v, 2: lambda v: F.leaky_relu(v, 0.1), 3: lambda v: F.prelu(v, slope.double())}[act1]
+        ref = F.conv2d(K.tf32_trunc(x).double(), K.tf32_rn(w).double(), b.double(), padding=ks // 2)
+    f = {0: lambda v: v, 1: F.relu, 2: lambda v: F.leaky_relu(v, 0.1), 3: lambda v: F.prelu(v, slope.double())}[act1]
     ref = f(ref)
     if use_res:
         ref = ref + (res.half().double() if half else res.double())
