@@ -110,6 +110,117 @@ __device__ __forceinline__ void res_unpack(const Params& p, const uint4& r, floa
     t[0] = __uint_as_float(r.x); t[1] = __uint_as_float(r.y); t[2] = __uint_as_float(r.z); t[3] = __uint_as_float(r.w);
   }
 }
+// The SepConvGRU gate epilogue as its OWN kernel instantiation (template parameter EPI = 1 of conv2d_tc_kernel), chosen on the host
+// when a 3xF16 layer on CTA pairs has side tensors and the layout below holds for the whole layer:
+//   act1 = none; fp32 side tensors / outputs with 16-byte aligned 4-channel groups (cout % 4 == 0, strides % 4 == 0); act2 in {none,
+//   sigmoid, tanh}; then  v = acc + bias (+ residual) -> act2 -> (x gate multiplier | GRU blend with z, h).
+// Why a separate instantiation: in the generic kernel this path is 2.6 K executed instructions per 32 x 32 chunk inside a 15 K
+// instruction kernel (L1.5 I-cache 32 KB) - ncu: 20 K clk per chunk, 44 % of the stall samples "no instruction" - and the split
+// kernel cannot hide it (its drain warps ARE the epilogue warps).  Moving it out of line or batching its loads inline cost the hot
+// loops registers (measured); here the lean / general / prefetched-residual paths do not exist, so the straight-line
+// form - one base pointer and two strides per tensor, every load of a 4-row group issued before the first use - fits the 128
+// registers a thread of the 14-warp CTA gets.
+__device__ __forceinline__ void epi_chunk_gate(const Params& p, const uint32_t* v, uint32_t stg_s, int cbase, int quarter, int lane, int tx, int ty, int n) {
+  const int q8 = lane & 7, rsub = lane >> 3;
+  {   // phase 1 (thread = pixel row): accumulator x scale + bias, staged (swizzled) for the row-major phase 2
+    float o[32];
+    const float4* b4p = reinterpret_cast<const float4*>(p.bias + cbase);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = __ldg(b4p + j);
+      o[4 * j] = fmaf(__uint_as_float(v[4 * j]), p.out_scale, b4.x); o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), p.out_scale, b4.y);
+      o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), p.out_scale, b4.z); o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), p.out_scale, b4.w);
+    }
+    const uint32_t srow = stg_s + (uint32_t)(lane * STG_PITCH * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(srow + (uint32_t)((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+  __syncwarp();
+  const int c = cbase + q8 * 4;
+  if (c < p.cout && n < p.n_img) {
+    const int y0 = ty * TILE_H + quarter * 2, x0 = tx * TILE_W + rsub;
+    const uint32_t sb_even = stg_s + (uint32_t)(rsub * STG_PITCH * 4 + ((q8 ^ rsub) << 4));
+    const uint32_t sb_odd = stg_s + (uint32_t)(rsub * STG_PITCH * 4 + ((q8 ^ (rsub + 4)) << 4));
+    const bool second = p.split_c > 0 && cbase >= p.split_c;          // merged z | r convolution: this chunk belongs to out2
+    const int c_loc = c - (second ? p.split_c : 0);
+    const bool use_mul = p.mul.p && (p.split_c == 0 || second);
+    float* oq = (second ? p.out2.p : p.out.p) + (second ? p.out2.off(n, y0, x0) : p.out.off(n, y0, x0)) + c_loc;
+    const int64_t o_x = (int64_t)4 * (second ? p.out2.ld : p.out.ld), o_row = (int64_t)p.W * (second ? p.out2.ld : p.out.ld);
+    const float* rq = p.res.p ? p.res.p + p.res.off(n, y0, x0) + c : nullptr;
+    const float* bq = use_mul ? p.mul.p + p.mul.off(n, y0, x0) + c_loc : (p.gru_z.p ? p.gru_z.p + p.gru_z.off(n, y0, x0) + c : nullptr);
+    const float* hq = p.gru_z.p ? p.gru_h.p + p.gru_h.off(n, y0, x0) + c : nullptr;
+    const int64_t r_x = (int64_t)4 * p.res.ld, r_row = (int64_t)p.res.w * p.res.ld;
+    const int64_t b_x = (int64_t)4 * (use_mul ? p.mul.ld : p.gru_z.ld), b_row = use_mul ? (int64_t)p.mul.w * p.mul.ld : (int64_t)p.gru_z.w * p.gru_z.ld;
+    const int64_t h_x = (int64_t)4 * p.gru_h.ld, h_row = (int64_t)p.gru_h.w * p.gru_h.ld;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if (y0 + g < p.H) {
+        bool ok[4];
+        float4 r4[4], b4[4], h4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ok[j] = x0 + j * 4 < p.W;
+          r4[j] = (rq && ok[j]) ? *reinterpret_cast<const float4*>(rq + g * r_row + j * r_x) : zero4;
+          b4[j] = (bq && ok[j]) ? *reinterpret_cast<const float4*>(bq + g * b_row + j * b_x) : zero4;
+          h4[j] = (hq && ok[j]) ? *reinterpret_cast<const float4*>(hq + g * h_row + j * h_x) : zero4;
+        }
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 sv = lds128(((j & 1) ? sb_odd : sb_even) + (uint32_t)((g * 4 + j) * 4 * STG_PITCH * 4));
+          o[4 * j] = sv.x + r4[j].x; o[4 * j + 1] = sv.y + r4[j].y; o[4 * j + 2] = sv.z + r4[j].z; o[4 * j + 3] = sv.w + r4[j].w;
+        }
+        if (p.act2 == ACT_SIGMOID) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) o[u] = __fdividef(1.f, 1.f + exp2f(-1.4426950408889634f * o[u]));
+        } else if (p.act2 == ACT_TANH) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) o[u] = 1.f - __fdividef(2.f, 1.f + exp2f(2.8853900817779268f * o[u]));
+        }
+        if (hq) {          // h = (1 - z) * h + z * q   (raft/update.py:58,66)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[4 * j] = (1.f - b4[j].x) * h4[j].x + b4[j].x * o[4 * j]; o[4 * j + 1] = (1.f - b4[j].y) * h4[j].y + b4[j].y * o[4 * j + 1];
+            o[4 * j + 2] = (1.f - b4[j].z) * h4[j].z + b4[j].z * o[4 * j + 2]; o[4 * j + 3] = (1.f - b4[j].w) * h4[j].w + b4[j].w * o[4 * j + 3];
+          }
+        } else if (bq) {   // gate multiply (r * h)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { o[4 * j] *= b4[j].x; o[4 * j + 1] *= b4[j].y; o[4 * j + 2] *= b4[j].z; o[4 * j + 3] *= b4[j].w; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ok[j]) *reinterpret_cast<float4*>(oq + g * o_row + j * o_x) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// EPI = 2: the plain epilogue of the 3xF16 layers (bias, none / ReLU, fp32 output, no side tensors) straight from the TMEM layout: a thread
+// owns one pixel (tile row) and the chunk's 32 consecutive channels = 128 contiguous bytes of the NHWC output - bias, activation and
+// eight 16-byte stores from registers, no staging, no second phase (the halo kernel's epilogue; every 32-byte sector is still written
+// in full by the thread that owns it).  ~100 instructions per chunk instead of ~700 inside a kernel a third of the generic one's size.
+__device__ __forceinline__ void epi_chunk_direct(const Params& p, const uint32_t* v, int cbase, int quarter, int lane, int tx, int ty, int n) {
+  const int r = quarter * 32 + lane;
+  const int y = ty * TILE_H + (r >> 4), x = tx * TILE_W + (r & 15);
+  if (n >= p.n_img || y >= p.H || x >= p.W) return;
+  float* oq = p.out.p + p.out.off(n, y, x) + cbase;
+  const float4* b4p = reinterpret_cast<const float4*>(p.bias + cbase);
+  const bool relu = p.act1 == ACT_RELU;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (cbase + 4 * j < p.cout) {
+      const float4 b4 = __ldg(b4p + j);
+      float4 o;
+      o.x = fmaf(__uint_as_float(v[4 * j]), p.out_scale, b4.x); o.y = fmaf(__uint_as_float(v[4 * j + 1]), p.out_scale, b4.y);
+      o.z = fmaf(__uint_as_float(v[4 * j + 2]), p.out_scale, b4.z); o.w = fmaf(__uint_as_float(v[4 * j + 3]), p.out_scale, b4.w);
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      *reinterpret_cast<float4*>(oq + 4 * j) = o;
+    }
+  }
+}
+
 // One 32-row x 32-column chunk of the output tile: v[j] = accumulator of (this thread's pixel row, column c0 + j).
 // stg_s = shared-window address of this warp's 32 x STG_PITCH staging area; cbase = first output channel of the chunk.
 __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, uint32_t stg_s, int cbase, int quarter, int lane, int tx, int ty,
@@ -253,7 +364,7 @@ __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, ui
 // shared memory carries 2/3 of the bytes per MMA of the single-CTA form (whose limiter it is: 128 B/clk).  Only the
 // leader (cluster rank 0) issues MMAs; both CTAs' TMA loads signal the leader's full barrier, the MMA commits are
 // multicast to both CTAs' empty / accumulator-full barriers, and the peer's epilogue releases accumulators remotely.
-template <bool SPLIT, int CL, int EW, bool PAIR = false>
+template <bool SPLIT, int CL, int EW, bool PAIR = false, int EPI = 0>
 __global__ void __launch_bounds__(64 + 32 * EW + (SPLIT ? 128 : 0), 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ Params p) {
@@ -531,7 +642,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
-        epi_chunk(p, v, stg_s, cbase, quarter, lane, tx, ty, n, p.stall ? st_c : nullptr, SPLIT ? nullptr : rp_cur, SPLIT ? false : rp_ok);
+        if (EPI == 1) epi_chunk_gate(p, v, stg_s, cbase, quarter, lane, tx, ty, n);
+        else if (EPI == 2) epi_chunk_direct(p, v, cbase, quarter, lane, tx, ty, n);
+        else epi_chunk(p, v, stg_s, cbase, quarter, lane, tx, ty, n, p.stall ? st_c : nullptr, SPLIT ? nullptr : rp_cur, SPLIT ? false : rp_ok);
         if (!SPLIT && p.res.p) {
 #pragma unroll
           for (int i = 0; i < (SPLIT ? 1 : 8); ++i) rp_cur[i] = rp_nxt[i];
@@ -692,17 +805,17 @@ static void encode_act(CUtensorMap* m, const TV& t, int stride = 1) {
 }  // namespace tc
 
 // launch with an optional (2,1,1) thread-block cluster
-template <bool SPLIT, int CL, int EW, bool PAIR = false>
+template <bool SPLIT, int CL, int EW, bool PAIR = false, int EPI = 0>
 static void launch_tc(int grid, int threads, int smem, gvStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                       const tc::Params& p) {
   static volatile unsigned char attr_set[64];   // per (instantiation, device)
-  gv_set_max_smem(tc::conv2d_tc_kernel<SPLIT, CL, EW, PAIR>, 227 * 1024, attr_set);
+  gv_set_max_smem(tc::conv2d_tc_kernel<SPLIT, CL, EW, PAIR, EPI>, 227 * 1024, attr_set);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t er = cudaLaunchKernelEx(&cfg, tc::conv2d_tc_kernel<SPLIT, CL, EW, PAIR>, a0, a1, b, p);
+  cudaError_t er = cudaLaunchKernelEx(&cfg, tc::conv2d_tc_kernel<SPLIT, CL, EW, PAIR, EPI>, a0, a1, b, p);
   if (er != cudaSuccess) throw std::runtime_error(std::string("conv_tc: launch failed: ") + cudaGetErrorString(er));
 }
 
@@ -748,6 +861,25 @@ static int tc_split_f16() {   // GIMMVFI_TC_SPLIT_F16=0: keep the 3xTF32 form of
   static int v = -1;
   if (v < 0) { const char* s = getenv("GIMMVFI_TC_SPLIT_F16"); v = s ? atoi(s) : 1; }
   return v;
+}
+// conditions of the gate-epilogue instantiation (epi_chunk_gate)
+static bool gate_epilogue_ok(const tc::Params& p, const ConvW& w, const ConvEpi& e, const TV& out) {
+  static int on = -1;
+  if (on < 0) { const char* s = getenv("GIMMVFI_TC_GATE_EPI"); on = s ? atoi(s) : 1; }
+  auto vec = [](const TV& t) { return !t.p || (!t.f16 && t.ld % 4 == 0 && t.sn % 4 == 0 && (reinterpret_cast<uintptr_t>(t.p) & 15) == 0); };
+  if (!on || !(e.res.p || e.mul.p || e.gru_z.p) || (e.mul.p && e.gru_z.p) || e.act1 != ACT_NONE) return false;
+  if (e.act2 != ACT_NONE && e.act2 != ACT_SIGMOID && e.act2 != ACT_TANH) return false;
+  if (w.cout % 4 || p.round_out || (e.split_c && e.split_c % 4)) return false;
+  return vec(e.res) && vec(e.mul) && vec(e.gru_z) && vec(e.gru_h) && vec(out) && out.p && vec(e.out2);
+}
+// conditions of the direct-store instantiation (epi_chunk_direct)
+static bool direct_epilogue_ok(const tc::Params& p, const ConvW& w, const ConvEpi& e, const TV& out) {
+  static int on = -1;
+  if (on < 0) { const char* s = getenv("GIMMVFI_TC_DIRECT_EPI"); on = s ? atoi(s) : 1; }
+  if (!on || e.res.p || e.mul.p || e.gru_z.p || e.out2.p || e.split_c || e.act2 != ACT_NONE) return false;
+  if (e.act1 != ACT_NONE && e.act1 != ACT_RELU) return false;
+  if (w.cout % 4 || p.round_out || out.f16 || out.ld % 4 || out.sn % 4 || (reinterpret_cast<uintptr_t>(out.p) & 15)) return false;
+  return true;
 }
 static int tc_seg_f16() {   // K steps (of 64 elements) per TMEM accumulation segment of the 3xF16 form.  2 (default): draining the
                             // 64 KB accumulator (TMEM reads: 64 B/clk/SM) every step costs more than the step's MMAs; full-frame parity at
@@ -847,7 +979,9 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.n * out.h * out.w * w.cout * (double)w.cin * w.kh * w.kw);
   }
   if (split && sew8) {
-    if (pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
+    if (pair && gate_epilogue_ok(p, w, e, out)) launch_tc<true, 2, 8, true, 1>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
+    else if (pair && direct_epilogue_ok(p, w, e, out)) launch_tc<true, 2, 8, true, 2>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
+    else if (pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
     else if (CL == 2) launch_tc<true, 2, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
     else launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
   }

@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, call x: the SepConvGRU gate epilogue as its own kernel instantiation (EPI = 1): unit, probe, parity, bench A/B
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_conv_tc_gpu.py -q -x > gpurun_out/r02x_unit.log 2>&1; echo "unit rc=$?"; tail -n 3 gpurun_out/r02x_unit.log | cut -c1-200
+PROBE_GRU=1 timeout 600 python scripts/tc_split_probe.py PROBE_STALL=1,PROBE_EPI=q PROBE_STALL=1,PROBE_EPI=q,GIMMVFI_TC_GATE_EPI=0 > gpurun_out/r02x_probe.log 2>&1; cut -c1-260 gpurun_out/r02x_probe.log
+timeout 600 python -m pytest tests/test_bench_parity_gpu.py tests/test_forward_gpu.py -q -s > gpurun_out/r02x_parity.log 2>&1; echo "== parity rc=$?"; grep -E "^big_r|\.big_r|Fbig_r|passed|failed" gpurun_out/r02x_parity.log | cut -c1-200
+timeout 300 python bench.py --no-cpu-baseline --no-torch-baseline --profile-json gpurun_out/r02x_profile.json > gpurun_out/r02x_bench.log 2>&1; tail -n 1 gpurun_out/r02x_bench.log | cut -c1-250
+GIMMVFI_TC_GATE_EPI=0 timeout 300 python bench.py --no-cpu-baseline --no-torch-baseline > gpurun_out/r02x_bench_generic.log 2>&1; tail -n 1 gpurun_out/r02x_bench_generic.log | cut -c1-250
+GIMMVFI_GRU_HOIST=0 timeout 300 python bench.py --no-cpu-baseline --no-torch-baseline > gpurun_out/r02x_bench_nohoist.log 2>&1; tail -n 1 gpurun_out/r02x_bench_nohoist.log | cut -c1-250
