@@ -197,30 +197,6 @@ __device__ __forceinline__ void epi_chunk_gate(const Params& p, const uint32_t* 
   __syncwarp();
 }
 
-// EPI = 2: the plain epilogue of the 3xF16 layers (bias, none / ReLU, fp32 output, no side tensors) straight from the TMEM layout: a thread
-// owns one pixel (tile row) and the chunk's 32 consecutive channels = 128 contiguous bytes of the NHWC output - bias, activation and
-// eight 16-byte stores from registers, no staging, no second phase (the halo kernel's epilogue; every 32-byte sector is still written
-// in full by the thread that owns it).  ~100 instructions per chunk instead of ~700 inside a kernel a third of the generic one's size.
-__device__ __forceinline__ void epi_chunk_direct(const Params& p, const uint32_t* v, int cbase, int quarter, int lane, int tx, int ty, int n) {
-  const int r = quarter * 32 + lane;
-  const int y = ty * TILE_H + (r >> 4), x = tx * TILE_W + (r & 15);
-  if (n >= p.n_img || y >= p.H || x >= p.W) return;
-  float* oq = p.out.p + p.out.off(n, y, x) + cbase;
-  const float4* b4p = reinterpret_cast<const float4*>(p.bias + cbase);
-  const bool relu = p.act1 == ACT_RELU;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (cbase + 4 * j < p.cout) {
-      const float4 b4 = __ldg(b4p + j);
-      float4 o;
-      o.x = fmaf(__uint_as_float(v[4 * j]), p.out_scale, b4.x); o.y = fmaf(__uint_as_float(v[4 * j + 1]), p.out_scale, b4.y);
-      o.z = fmaf(__uint_as_float(v[4 * j + 2]), p.out_scale, b4.z); o.w = fmaf(__uint_as_float(v[4 * j + 3]), p.out_scale, b4.w);
-      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      *reinterpret_cast<float4*>(oq + 4 * j) = o;
-    }
-  }
-}
-
 // One 32-row x 32-column chunk of the output tile: v[j] = accumulator of (this thread's pixel row, column c0 + j).
 // stg_s = shared-window address of this warp's 32 x STG_PITCH staging area; cbase = first output channel of the chunk.
 __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, uint32_t stg_s, int cbase, int quarter, int lane, int tx, int ty,
@@ -643,7 +619,6 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
         if (EPI == 1) epi_chunk_gate(p, v, stg_s, cbase, quarter, lane, tx, ty, n);
-        else if (EPI == 2) epi_chunk_direct(p, v, cbase, quarter, lane, tx, ty, n);
         else epi_chunk(p, v, stg_s, cbase, quarter, lane, tx, ty, n, p.stall ? st_c : nullptr, SPLIT ? nullptr : rp_cur, SPLIT ? false : rp_ok);
         if (!SPLIT && p.res.p) {
 #pragma unroll
@@ -872,15 +847,6 @@ static bool gate_epilogue_ok(const tc::Params& p, const ConvW& w, const ConvEpi&
   if (w.cout % 4 || p.round_out || (e.split_c && e.split_c % 4)) return false;
   return vec(e.res) && vec(e.mul) && vec(e.gru_z) && vec(e.gru_h) && vec(out) && out.p && vec(e.out2);
 }
-// conditions of the direct-store instantiation (epi_chunk_direct)
-static bool direct_epilogue_ok(const tc::Params& p, const ConvW& w, const ConvEpi& e, const TV& out) {
-  static int on = -1;
-  if (on < 0) { const char* s = getenv("GIMMVFI_TC_DIRECT_EPI"); on = s ? atoi(s) : 1; }
-  if (!on || e.res.p || e.mul.p || e.gru_z.p || e.out2.p || e.split_c || e.act2 != ACT_NONE) return false;
-  if (e.act1 != ACT_NONE && e.act1 != ACT_RELU) return false;
-  if (w.cout % 4 || p.round_out || out.f16 || out.ld % 4 || out.sn % 4 || (reinterpret_cast<uintptr_t>(out.p) & 15)) return false;
-  return true;
-}
 static int tc_seg_f16() {   // K steps (of 64 elements) per TMEM accumulation segment of the 3xF16 form.  2 (default): draining the
                             // 64 KB accumulator (TMEM reads: 64 B/clk/SM) every step costs more than the step's MMAs; full-frame parity at
                             // 1088x1920: 0 of 6.27 M values off by > 1e-3 with 1 and with 2, one outlier appears with 3 (profiles/r02_fullframe_parity.log)
@@ -980,7 +946,6 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   }
   if (split && sew8) {
     if (pair && gate_epilogue_ok(p, w, e, out)) launch_tc<true, 2, 8, true, 1>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
-    else if (pair && direct_epilogue_ok(p, w, e, out)) launch_tc<true, 2, 8, true, 2>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
     else if (pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
     else if (CL == 2) launch_tc<true, 2, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
     else launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
