@@ -197,6 +197,49 @@ __device__ __forceinline__ void epi_chunk_gate(const Params& p, const uint32_t* 
   __syncwarp();
 }
 
+// EPI = 2: the plain epilogue of the 3xF16 layers (bias, none / ReLU, fp32 output, no side tensors), same two-phase shape as epi_chunk
+// (staged transpose, 128-byte row stores) but nothing else compiled in: a 5 K instead of 15 K instruction kernel for the layers whose
+// epilogue code is otherwise fetched cold (ncu: 40 % of the plain epilogue's stall samples are instruction fetch).
+// (A direct-store variant - thread = pixel, 128 contiguous bytes per thread, no staging - was measured and is slower here: 96.97 vs
+// 93.52 ms per frame on one box.)
+__device__ __forceinline__ void epi_chunk_plain(const Params& p, const uint32_t* v, uint32_t stg_s, int cbase, int quarter, int lane, int tx, int ty, int n) {
+  const int q8 = lane & 7, rsub = lane >> 3;
+  {
+    float o[32];
+    const float4* b4p = reinterpret_cast<const float4*>(p.bias + cbase);
+    const bool relu = p.act1 == ACT_RELU;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = __ldg(b4p + j);
+      o[4 * j] = fmaf(__uint_as_float(v[4 * j]), p.out_scale, b4.x); o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), p.out_scale, b4.y);
+      o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), p.out_scale, b4.z); o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), p.out_scale, b4.w);
+    }
+    if (relu) {
+#pragma unroll
+      for (int u = 0; u < 32; ++u) o[u] = fmaxf(o[u], 0.f);
+    }
+    const uint32_t srow = stg_s + (uint32_t)(lane * STG_PITCH * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(srow + (uint32_t)((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+  __syncwarp();
+  const int c = cbase + q8 * 4;
+  if (c < p.cout && n < p.n_img) {
+    const int y0 = ty * TILE_H + quarter * 2, x0 = tx * TILE_W + rsub;
+    const uint32_t sb_even = stg_s + (uint32_t)(rsub * STG_PITCH * 4 + ((q8 ^ rsub) << 4));
+    const uint32_t sb_odd = stg_s + (uint32_t)(rsub * STG_PITCH * 4 + ((q8 ^ (rsub + 4)) << 4));
+    float* oq = p.out.p + p.out.off(n, y0, x0) + c;
+    const int64_t o_x = (int64_t)4 * p.out.ld, o_row = (int64_t)p.W * p.out.ld;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int yy = it >> 2, xx = (it & 3) * 4;
+      const float4 sv = lds128(((it & 1) ? sb_odd : sb_even) + (uint32_t)(it * 4 * STG_PITCH * 4));
+      if (y0 + yy < p.H && x0 + xx < p.W) *reinterpret_cast<float4*>(oq + yy * o_row + (it & 3) * o_x) = sv;
+    }
+  }
+  __syncwarp();
+}
+
 // One 32-row x 32-column chunk of the output tile: v[j] = accumulator of (this thread's pixel row, column c0 + j).
 // stg_s = shared-window address of this warp's 32 x STG_PITCH staging area; cbase = first output channel of the chunk.
 __device__ __forceinline__ void epi_chunk(const Params& p, const uint32_t* v, uint32_t stg_s, int cbase, int quarter, int lane, int tx, int ty,
@@ -619,6 +662,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
         if (EPI == 1) epi_chunk_gate(p, v, stg_s, cbase, quarter, lane, tx, ty, n);
+        else if (EPI == 2) epi_chunk_plain(p, v, stg_s, cbase, quarter, lane, tx, ty, n);
         else epi_chunk(p, v, stg_s, cbase, quarter, lane, tx, ty, n, p.stall ? st_c : nullptr, SPLIT ? nullptr : rp_cur, SPLIT ? false : rp_ok);
         if (!SPLIT && p.res.p) {
 #pragma unroll
@@ -847,6 +891,15 @@ static bool gate_epilogue_ok(const tc::Params& p, const ConvW& w, const ConvEpi&
   if (w.cout % 4 || p.round_out || (e.split_c && e.split_c % 4)) return false;
   return vec(e.res) && vec(e.mul) && vec(e.gru_z) && vec(e.gru_h) && vec(out) && out.p && vec(e.out2);
 }
+// conditions of the plain-epilogue instantiation (epi_chunk_plain)
+static bool plain_epilogue_ok(const tc::Params& p, const ConvW& w, const ConvEpi& e, const TV& out) {
+  static int on = -1;
+  if (on < 0) { const char* s = getenv("GIMMVFI_TC_PLAIN_EPI"); on = s ? atoi(s) : 1; }
+  if (!on || e.res.p || e.mul.p || e.gru_z.p || e.out2.p || e.split_c || e.act2 != ACT_NONE) return false;
+  if (e.act1 != ACT_NONE && e.act1 != ACT_RELU) return false;
+  if (w.cout % 4 || p.round_out || out.f16 || out.ld % 4 || out.sn % 4 || (reinterpret_cast<uintptr_t>(out.p) & 15)) return false;
+  return true;
+}
 static int tc_seg_f16() {   // K steps (of 64 elements) per TMEM accumulation segment of the 3xF16 form.  2 (default): draining the
                             // 64 KB accumulator (TMEM reads: 64 B/clk/SM) every step costs more than the step's MMAs; full-frame parity at
                             // 1088x1920: 0 of 6.27 M values off by > 1e-3 with 1 and with 2, one outlier appears with 3 (profiles/r02_fullframe_parity.log)
@@ -946,6 +999,7 @@ void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const Conv
   }
   if (split && sew8) {
     if (pair && gate_epilogue_ok(p, w, e, out)) launch_tc<true, 2, 8, true, 1>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
+    else if (pair && plain_epilogue_ok(p, w, e, out)) launch_tc<true, 2, 8, true, 2>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
     else if (pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
     else if (CL == 2) launch_tc<true, 2, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
     else launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA0, mA1, mB, p);
