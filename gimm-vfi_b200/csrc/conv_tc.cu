@@ -1073,7 +1073,11 @@ void corr_volume_tc(Ctx& cx, const TV& fa, const float* fb_planes, const float* 
   grid -= grid % CL;
   cx.launches++;
   if (cx.prof) cx.prof->begin(cx.stream, split ? (sf16 ? "corr_gemm_tc_3xf16" : "corr_gemm_tc_3xtf32") : "corr_gemm_tc_tf32", 2.0 * (double)Ms * N * C);
-  if (split && pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA, mA, mB, p);
+  // plain fp32 rows of the volume: the compact plain-epilogue instantiation when every row is a whole number of 16-byte groups
+  static int plain_on = -1;
+  if (plain_on < 0) { const char* s = getenv("GIMMVFI_TC_PLAIN_EPI"); plain_on = s ? atoi(s) : 1; }
+  if (split && pair && plain_on && N % 4 == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0) launch_tc<true, 2, 8, true, 2>(grid, 448, smem, cx.stream, mA, mA, mB, p);
+  else if (split && pair) launch_tc<true, 2, 8, true>(grid, 448, smem, cx.stream, mA, mA, mB, p);
   else if (split && e8) launch_tc<true, 1, 8>(grid, 448, smem, cx.stream, mA, mA, mB, p);
   else if (split) launch_tc<true, 1, 4>(grid, 320, smem, cx.stream, mA, mA, mB, p);
   else if (pair) launch_tc<false, 2, 8, true>(grid, 320, smem, cx.stream, mA, mA, mB, p);
