@@ -127,7 +127,7 @@ GV_HD void st4v(const TV& t, int64_t eoff, const F4& v) {
 inline bool vec4_ok_any(const TV& t) {
   return (reinterpret_cast<uintptr_t>(t.p) & (t.f16 ? 7 : 15)) == 0 && t.c % 4 == 0 && t.ld % 4 == 0 && t.sn % 4 == 0;
 }
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_PRELU = 3, ACT_SIGMOID = 4, ACT_TANH = 5, ACT_SIN = 6 };
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_PRELU = 3, ACT_SIGMOID = 4, ACT_TANH = 5, ACT_SIN = 6, ACT_GELU = 7 /* exact (erf) GELU: nn.GELU() of the FlowFormer / Twins MLPs */ };
 
 GV_HD float apply_act(float v, int act, const float* slope, int ch) {
   switch (act) {
@@ -137,6 +137,7 @@ GV_HD float apply_act(float v, int act, const float* slope, int ch) {
     case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     case ACT_TANH: return tanhf(v);
     case ACT_SIN: return sinf(v);
+    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     default: return v;
   }
 }
@@ -348,7 +349,7 @@ void corr_volume(Ctx& cx, const TV& fa, const TV& fb, float* vol, float scale); 
 void corr_pool(Ctx& cx, const float* src, float* dst, int64_t rows, int h, int w); // rows x (h*w) -> rows x (h/2*w/2)
 void avgpool2_features(Ctx& cx, const TV& src, const TV& dst);   // NHWC 2x2 average, floor semantics (F.avg_pool2d(x, 2, 2))
 void corr_pool_pyramid(Ctx& cx, const float* l0, float* l1, float* l2, float* l3, int64_t rows, int h, int w);
-struct CorrPyr { const float* lvl[4]; int h[4], w[4]; int64_t rows_per_sample; };
+struct CorrPyr { const float* lvl[4]; int h[4], w[4]; int64_t rows_per_sample; int nl = 4; /* levels looked up: out has nl * 81 channels (FlowFormer: 1) */ };
 void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords /*n,h,w,2 (x,y)*/, const TV& out /*324 ch*/);
 // volume-free lookup: the other frame's features (IEEE half, NHWC, c channels; level l = the 2^l x 2^l average-pooled map, sample-major)
 struct CorrFeat { const uint16_t* lvl[4]; int h[4], w[4]; int c; float scale; };
@@ -396,6 +397,26 @@ void warp_blend(Ctx& cx, const TV& img0, const TV& img1, const TV& f0, const TV&
 void multi_flow_blend(Ctx& cx, const TV& img0, const TV& img1, const TV& f0, const TV& f1, const TV& mask, const TV& res,
                       const TV& warps9, const TV& mean3);
 void combine_output(Ctx& cx, const TV& mean3, const TV& conv3, float* dst_nchw);
+
+// ops_tokens.cu (FlowFormer / Twins token-side kernels; see the file header)
+void patchify(Ctx& cx, const TV& src, const TV& dst, int k);
+void layernorm(Ctx& cx, const TV& x, const float* g, const float* b, float eps, const TV& out /*may be larger: zero padded*/, float pe_scale = 0.f, int pe_dim = 0);
+void dwconv3x3_residual(Ctx& cx, const TV& x, const float* w9c, const float* bias, const TV& out);
+void window_attention(Ctx& cx, const TV& q, const TV& k, const TV& v /*padded maps*/, const TV& out /*unpadded*/, int heads, int ws);
+struct AttnDims {
+  int64_t nb1, nb2, nq, nk; int heads;
+  int64_t q_s1, q_s2, q_si; int64_t k_s1, k_s2, k_sj; int64_t v_s1, v_s2, v_sj; int64_t o_s1, o_s2, o_si;
+};
+void strided_attention(Ctx& cx, const float* q, const float* k, const float* v, float* out, const AttnDims& a, int head_dim);
+void concat_pe(Ctx& cx, const TV& a, const TV& b, const TV& out, int ws, bool add_pe, int grp_all, int ctx_per);
+void write_pe(Ctx& cx, const TV& out, float scale, float shift);
+void add_pe_coords(Ctx& cx, const TV& x, const TV& coords, const TV& out);
+void cost_conv1(Ctx& cx, const float* vol, int64_t maps, int h, int w, const float* wt, const float* bias, const TV& out_padded, int oh, int ow);
+void row_softmax(Ctx& cx, float* p, int64_t rows, int64_t cols, float mul);
+void gemm_nn(Ctx& cx, const float* A, const float* Bm, float* out, int64_t rows, int64_t K, int D, int64_t lda, int64_t ldb, int64_t ldo, float scale);
+void transpose_2d(Ctx& cx, const float* src, float* dst, int64_t rows, int cols, int64_t lds);
+void axpy_dev(Ctx& cx, const TV& a, const TV& b, const float* alpha, const TV& out);
+void broadcast_tokens(Ctx& cx, const float* src, const TV& out, int T);
 
 // device memory helpers (hostsim: plain host memory)
 void* dev_alloc(size_t bytes);

@@ -240,7 +240,8 @@ void corr_pool_pyramid(Ctx& cx, const float* l0, float* l1, float* l2, float* l3
 struct CorrLookupK {
   CorrPyr pyr; TV coords, out;
   GV_HD void operator()(int64_t i) const {
-    int ch = (int)(i % 324); int64_t r = i / 324;
+    const int nch = pyr.nl * 81;
+    int ch = (int)(i % nch); int64_t r = i / nch;
     int x = (int)(r % coords.w); r /= coords.w; int y = (int)(r % coords.h); int n = (int)(r / coords.h);
     int lvl = ch / 81, k = ch % 81, a = k / 9, b = k % 9;
     const float* c = coords.p + coords.off(n, y, x);
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256) corr_lookup_warp_kernel(CorrPyr pyr, TV c
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t it = warp0; it < n_items; it += nwarps) {
-    const int lvl = (int)(it & 3); int64_t r = it >> 2;
+    const int lvl = (int)(it % pyr.nl); int64_t r = it / pyr.nl;
     const int x = (int)(r % coords.w); r /= coords.w; const int y = (int)(r % coords.h); const int n = (int)(r / coords.h);
     const float* c = coords.p + coords.off(n, y, x);
     const float inv = 1.0f / (float)(1 << lvl);
@@ -321,8 +322,8 @@ void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords, const TV& out) {
   if (!out.f16 && !coords.f16) {
     if (cx.dry) return;
     cx.launches++;
-    const int64_t items = coords.pixels() * 4;
-    if (cx.prof) cx.prof->begin(cx.stream, "corr_lookup", (double)coords.pixels() * 324);
+    const int64_t items = coords.pixels() * pyr.nl;
+    if (cx.prof) cx.prof->begin(cx.stream, "corr_lookup", (double)coords.pixels() * pyr.nl * 81);
     int64_t blocks = (items + 7) / 8, cap = (int64_t)cx.sm_count * 16;
     if (blocks > cap) blocks = cap;
     corr_lookup_warp_kernel<<<(unsigned)blocks, 256, 0, cx.stream>>>(pyr, coords, out, items);
@@ -331,7 +332,7 @@ void corr_lookup(Ctx& cx, const CorrPyr& pyr, const TV& coords, const TV& out) {
     return;
   }
 #endif
-  parallel_for(cx, coords.pixels() * 324, CorrLookupK{pyr, coords, out}, "corr_lookup");
+  parallel_for(cx, coords.pixels() * pyr.nl * 81, CorrLookupK{pyr, coords, out}, "corr_lookup");
 }
 
 // -------------------------------------------------------- volume-free lookup

@@ -2,6 +2,7 @@
 // One stream, one pre-planned workspace, zero allocations / host syncs in
 // forward().  Reference call stack: gimmvfi_r.py:324-407.
 #include "engine.h"
+#include "net.h"
 
 #include <algorithm>
 
@@ -163,9 +164,12 @@ const float* Engine::vec(const std::string& key) {
 // folding (bn = name of the BatchNorm2d), output scale and output-channel permutation.
 ConvW Engine::pack_conv(const std::string& name, const std::string& bn, float out_scale, const std::vector<int>* perm) {
   const HostTensor& W = raw(name + ".weight");
-  const HostTensor& Bv = raw(name + ".bias");
-  if (W.shape.size() != 4) throw std::runtime_error("gimmvfi: '" + name + ".weight' is not 4-D");
-  const int cout = (int)W.shape[0], cin = (int)W.shape[1], kh = (int)W.shape[2], kw = (int)W.shape[3];
+  if (W.shape.size() != 4 && W.shape.size() != 2) throw std::runtime_error("gimmvfi: '" + name + ".weight' is neither a Conv2d (4-D) nor a Linear (2-D) weight");
+  const bool lin = W.shape.size() == 2;   // nn.Linear (cout, cin) = a 1x1 convolution over tokens laid out as an NHWC map
+  const int cout = (int)W.shape[0], cin = (int)W.shape[1], kh = lin ? 1 : (int)W.shape[2], kw = lin ? 1 : (int)W.shape[3];
+  HostTensor zero_bias;
+  if (!raw_.count(name + ".bias")) { zero_bias.shape = {cout}; zero_bias.data.assign(cout, 0.f); }   // bias=False layers
+  const HostTensor& Bv = raw_.count(name + ".bias") ? raw(name + ".bias") : zero_bias;
   std::vector<float> s(cout, out_scale), sh(cout, 0.f);
   if (!bn.empty()) {
     const auto& g = raw(bn + ".weight").data; const auto& be = raw(bn + ".bias").data;
@@ -299,7 +303,7 @@ void Engine::pack_xpacked(const std::string& name, int ldp) {
   const HostTensor& W = raw(name + ".weight");
   const HostTensor& Bv = raw(name + ".bias");
   const int cout = (int)W.shape[0], cin = (int)W.shape[1], kh = (int)W.shape[2], kw = (int)W.shape[3];
-  if (kh != kw || !(kh & 1) || cin > ldp) throw std::runtime_error("pack_xpacked: expected an odd k x k conv with cin <= ldp");
+  if (kh != kw || cin > ldp) throw std::runtime_error("pack_xpacked: expected a k x k conv with cin <= ldp");
   const int cout_ld = (cout + 3) & ~3, K = kw * ldp;
   std::vector<float> pw((size_t)kh * K * cout_ld, 0.f), pb(((tc_cout_pad(cout) + 31) & ~31) + 128, 0.f);
   for (int co = 0; co < cout; ++co) {
@@ -376,7 +380,7 @@ void Engine::finalize_weights() {
   pack_conv("amt_last_cproj"); pack_conv("amt_second_last_cproj"); pack_conv("amt_fproj");
   finalize_decoders();
   finalize_gimm_part();
-  finalized_ = true; gimm_only_ = false; synth_only_ = false;
+  finalized_ = true; gimm_only_ = false; synth_only_ = false; ff_ = false;
 }
 
 // AMT decoders / update blocks / combine block (fi_components.py:229-305): shared by GIMM-VFI-R and -F
@@ -424,7 +428,22 @@ void Engine::finalize_weights_synthesis() {
   fc_valid_.clear(); ++weights_version_; clear_graphs();
   finalize_decoders();
   finalize_gimm_part();
-  finalized_ = true; gimm_only_ = false; synth_only_ = true;
+  finalized_ = true; gimm_only_ = false; synth_only_ = true; ff_ = false;
+}
+
+// GIMM-VFI-F complete (gimmvfi_f.py:27-111): the synthesis half + the native FlowFormer estimator (flowformer.cu)
+void Engine::finalize_weights_f() {
+  finalize_weights_synthesis();
+  DeviceGuard dg(device_);
+  finalize_flowformer();
+  synth_only_ = false; ff_ = true;
+}
+
+void Engine::tap_copy(Ctx& cx, const std::string& name, const TV& tv) {
+  if (!debug_) return;
+  TV c = cx.arena.tensor(tv.n, tv.h, tv.w, tv.c);
+  copy_channels(cx, tv, c);
+  taps_[name] = c;
 }
 
 // GIMM's own parameters (gimm.py:36-80 == gimmvfi_r.py:86-111): motion encoder, latent refiner, HypoNet, splat-metric scalars
@@ -532,64 +551,13 @@ void Engine::finalize_weights_gimm() {
   dev_allocs_.clear(); conv_.clear(); vec_.clear();
   fc_valid_.clear(); ++weights_version_; clear_graphs();
   finalize_gimm_part();
-  finalized_ = true; gimm_only_ = true;
+  finalized_ = true; gimm_only_ = true; ff_ = false;
 }
 
 
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-struct Net {
-  Engine& E; Ctx& cx;
-  const ConvW& W(const std::string& n) const {
-    auto it = E.conv_.find(n);
-    if (it == E.conv_.end()) throw std::runtime_error("gimmvfi: conv '" + n + "' not packed");
-    return it->second;
-  }
-  const float* V(const std::string& n) const { return E.vec_.at(n); }
-  static ConvGeom geom(const ConvW& w, int stride = 1, bool reflect = false) {
-    ConvGeom g; g.stride = stride; g.ph = w.kh / 2; g.pw = w.kw / 2; g.reflect = reflect ? 1 : 0; return g;
-  }
-  // plain conv + activation
-  void conv(const std::string& name, const TV& in, const TV& out, int act = ACT_NONE, const float* slope = nullptr, int stride = 1,
-            bool reflect = false) {
-    ConvEpi e; e.act1 = act; e.slope1 = slope;
-    conv_e(name, in, TV(), out, e, stride, reflect);
-  }
-  void conv_e(const std::string& name, const TV& in0, const TV& in1, const TV& out, const ConvEpi& e, int stride = 1, bool reflect = false) {
-    const ConvW& w = W(name);
-    if (reflect && cx.tc && !in1.p && stride == 1 && w.w_tc && in0.ld % (in0.f16 ? 8 : 4) == 0 && (!in0.f16 || w.w_tc_h)) {
-      // the TMA path can only zero-fill: materialise the reflect padding once, then a "valid" conv on the padded buffer
-      Arena& A = cx.arena;
-      const size_t mk = A.mark();
-      TV pad = in0.f16 ? A.tensor_h(in0.n, in0.h + 2 * (w.kh / 2), in0.w + 2 * (w.kw / 2), in0.c)
-                       : A.tensor(in0.n, in0.h + 2 * (w.kh / 2), in0.w + 2 * (w.kw / 2), in0.c, (in0.c + 3) & ~3);
-      pad_reflect(cx, in0, pad, w.kh / 2);
-      ConvGeom g; g.stride = 1; g.ph = 0; g.pw = 0; g.loose_w = 1;
-      conv2d(cx, pad, TV(), w, g, e, out);
-      A.release(mk);
-      return;
-    }
-    conv2d(cx, in0, in1, w, geom(w, stride, reflect), e, out);
-  }
-  // 7x7 conv on few channels through the x-packed weights: zero-padded copy of `in`, then a (7 x 1) conv over 7*ldp lanes
-  void conv7x(const std::string& name, const TV& in, const TV& out, int act = ACT_NONE, const float* slope = nullptr) {
-    const ConvW& w = W(name + "#xp");
-    const int k = w.kh, ldp = w.cin / k;   // (k x k kernel packed as k x 1 over k * ldp lanes)
-    Arena& A = cx.arena;
-    const size_t mk = A.mark();
-    TV pad = A.tensor(in.n, in.h + 2 * (k / 2), in.w + 2 * (k / 2), ldp, ldp);
-    pad_zero(cx, in, pad, k / 2);
-    TV v = pad; v.c = w.cin;
-    ConvGeom g; g.stride = 1; g.ph = 0; g.pw = 0; g.loose_w = 1;
-    ConvEpi e; e.act1 = act; e.slope1 = slope;
-    conv2d(cx, v, TV(), w, g, e, out);
-    A.release(mk);
-  }
-  // Sequential(Conv2d, PReLU)  (fi_components.py:32-54)
-  void convrelu(const std::string& name, const TV& in, const TV& out) { conv(name + ".0", in, out, ACT_PRELU, V(name + ".1.weight")); }
-};
-
 static ConvW slice_cout(const ConvW& w, int co0, int cnt) {
   ConvW s = w; s.w = w.w + co0; s.b = w.b + co0; s.cout = cnt; s.w_tc = nullptr;  // TC layout is not sliceable this way
   return s;
@@ -851,6 +819,9 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
       nchw_to_nhwc(cx, fin->feat8[j], (int64_t)256 * h * w, (int64_t)h * w, feat8.batch(j * B, B), 1.f, 0.f);
       nchw_to_nhwc(cx, fin->fnet[j], (int64_t)256 * h * w, (int64_t)h * w, fproj.batch(j * B, B), 1.f, 0.f);
     }
+  } else if (ff_) {
+    // GIMM-VFI-F: the native FlowFormer estimator fills the same four products (gimmvfi_f.py:114-138); F has no feature projections
+    run_flowformer(cx, N, B, raft_in, flow_up, feat4, feat8, fproj);
   } else {
     const size_t mk = A.mark();
     TV hx = A.tensor(2 * B, h, w, 384);              // [h | inp | motion]
@@ -973,7 +944,7 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
   // Everything downstream of RAFT tolerates TF32 operands (DESIGN.md precision plan).
   cx.tc = tc_mode_ >= 1; cx.tc_split = false;
   // ------------------------------------------------------------ bidirectional volume on projected features
-  if (!fin) N.conv("amt_fproj", fmap, fproj);
+  if (!fin && !ff_) N.conv("amt_fproj", fmap, fproj);
   // the bidirectional volume only feeds TF32 layers (AMT update blocks) -> plain TF32 is at their input precision
   // Few interpolated frames per pair (T <= corr_direct_max_t_): no volume at all - the lookup computes the dot products its window needs
   // (corr.cu "volume-free lookup").  Otherwise the all-pairs pyramid, looked up T times.

@@ -68,6 +68,7 @@ class Engine {
   void finalize_weights();
   void finalize_weights_gimm();                        // a standalone GIMM checkpoint (gimm.py's module tree only)
   void finalize_weights_synthesis();                   // everything downstream of the flow estimator (GIMM-VFI-F's tree minus flow_estimator.*)
+  void finalize_weights_f();                           // the complete GIMM-VFI-F tree: synthesis half + the native FlowFormer estimator (flowformer.cu)
   size_t plan_from_flow(const Problem& p);
   void forward_from_flow(const Problem& p, const IO& io, const FlowInputs& fin, void* workspace, size_t workspace_bytes, gvStream_t stream);
   size_t plan_gimm(const Problem& p);
@@ -101,6 +102,12 @@ class Engine {
   const std::map<std::string, TV>& taps() const { return taps_; }
   std::string last_error;
   int raft_iters = 20;  // GIMMVFI_R hard-codes iters=20 (gimmvfi_r.py:126-132)
+  int ff_iters = 32;    // FlowFormer decoder_depth (flowformer/configs/submission.py:50; gimmvfi_f.py:115 passes iters=None)
+  bool is_f() const { return ff_; }
+  // debug taps from the estimator's helpers (flowformer.cu)
+  bool debug_on() const { return debug_; }
+  void tap_pub(const std::string& name, const TV& tv) { tap(name, tv); }
+  void tap_copy(Ctx& cx, const std::string& name, const TV& tv);   // a snapshot (the tensor is overwritten later in the forward)
   int device() const { return device_; }
   int64_t weights_version() const { return weights_version_; }
   const void* hyponet_blob(bool fp32_class) const { return fp32_class ? hypo_blob3_ : hypo_blob_; }   // bumped by every finalize_weights*: callers key caches on it
@@ -110,6 +117,10 @@ class Engine {
   struct Impl;
   void run(Ctx& cx, const Problem& p, const IO& io, const FlowInputs* fin = nullptr);
   void finalize_decoders();
+  void finalize_flowformer();
+  void pack_patch_conv(const std::string& name);
+  void pack_twins(const std::string& prefix);
+  void run_flowformer(Ctx& cx, Net& N, int B, const TV& img, const TV& flow_up, const TV& feat4, const TV& feat8, const TV& fproj);
   void run_gimm(Ctx& cx, const Problem& p, const GimmIO& io);
   void finalize_gimm_part();
   void gimm_encode(Net& N, const TV& nf, const TV& f01, const TV& f10, const TV& wts, const TV& X64);
@@ -122,7 +133,7 @@ class Engine {
   void tap(const std::string& name, const TV& tv) { if (debug_) taps_[name] = tv; }
 
   int device_ = 0;
-  bool finalized_ = false, debug_ = false, profile_ = false, gimm_only_ = false, synth_only_ = false;
+  bool finalized_ = false, debug_ = false, profile_ = false, gimm_only_ = false, synth_only_ = false, ff_ = false;
   int tc_mode_ = 0;
   int64_t weights_version_ = 0;
   bool use_graph_ = false;

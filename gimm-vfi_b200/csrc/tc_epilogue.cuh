@@ -30,6 +30,7 @@ static __device__ __noinline__ float act_slow(float v, int act) {
     case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     case ACT_TANH: return tanhf(v);
     case ACT_SIN: return sin_f32(v);
+    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     default: return v;
   }
 }

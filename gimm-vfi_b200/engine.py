@@ -46,10 +46,11 @@ class EngineHandle:
             pass
 
     # ------------------------------------------------------------------ weights
-    def load_state_dict(self, sd: Dict[str, torch.Tensor], gimm_only: bool = False, synthesis_only: bool = False):
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], gimm_only: bool = False, synthesis_only: bool = False, full_f: bool = False):
         """gimm_only: `sd` is a standalone GIMM checkpoint (gimm.py's module tree), only gimm_forward() is available.
         synthesis_only: `sd` is a GIMM-VFI-F state_dict; its `flow_estimator.*` (FlowFormer) entries are skipped and only
-        forward_from_flow() is available."""
+        forward_from_flow() is available.
+        full_f: `sd` is a complete GIMM-VFI-F state_dict: forward() runs the native FlowFormer estimator + the synthesis half."""
         for k, v in sd.items():
             if not v.dtype.is_floating_point:
                 continue  # num_batches_tracked
@@ -59,7 +60,8 @@ class EngineHandle:
             shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
             self.lib.check(self.lib.dll.gimmvfi_load_weight(self._h, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()), self._h)
         fin = self.lib.dll.gimmvfi_finalize_weights_gimm if gimm_only else (
-            self.lib.dll.gimmvfi_finalize_weights_synthesis if synthesis_only else self.lib.dll.gimmvfi_finalize_weights)
+            self.lib.dll.gimmvfi_finalize_weights_synthesis if synthesis_only else (
+                self.lib.dll.gimmvfi_finalize_weights_f if full_f else self.lib.dll.gimmvfi_finalize_weights))
         self.synthesis_only = synthesis_only
         self.lib.check(fin(self._h), self._h)
         self.weights_loaded = True
@@ -97,6 +99,10 @@ class EngineHandle:
 
     def set_raft_iters(self, iters: int):
         self.lib.check(self.lib.dll.gimmvfi_set_raft_iters(self._h, int(iters)), self._h)
+
+    def set_flowformer_iters(self, iters: int):
+        """decoder_depth of the native FlowFormer memory decoder (default 32)"""
+        self.lib.check(self.lib.dll.gimmvfi_set_flowformer_iters(self._h, int(iters)), self._h)
 
     @property
     def last_launches(self) -> int:

@@ -2,16 +2,14 @@
 ``state_dict`` of the reference (FlowFormer included, so published GIMM-VFI-F / F-P checkpoints load with ``strict=True``), same
 ``forward(img_xs, coord, t, ds_factor)`` and returned dict.
 
-What runs natively: EVERYTHING downstream of ``cal_bidirection_flow`` (gimmvfi_f.py:114-138) — splatting metrics, motion encoder,
-forward splat, latent refiner, HypoNet, init / final decoders, update blocks, bidirectional correlation lookups, multi-flow combine:
-the same sm_100a engine as GIMM-VFI-R (``gimmvfi_forward_from_flow``; F has no feature projections, gimmvfi_f.py:37-60).
-
-What does not (yet): the FlowFormer flow estimator itself (Twins-SVT-L encoders, cost-perceiver
-encoder, 32-iteration GMA memory decoder).  ``forward`` therefore needs ``model.flow_backend``: a callable
-``(image0_0_255, image1_0_255) -> (flow_list, [feat4 (B,128,H/4,W/4), feat8 (B,256,H/8,W/8)], fnet (B,256,H/8,W/8))`` with the
-signature of the reference's ``FlowFormer.forward(im0, im1, return_feat=True)`` (LatentCostFormer/transformer.py:45-74) — e.g. the
-reference module itself, loaded from ``self.flow_estimator_state_dict()``.  Without it ``forward`` raises: there is no silent
-PyTorch re-implementation of FlowFormer on the product path."""
+Everything runs natively on the sm_100a engine (``gimmvfi_finalize_weights_f`` + ``gimmvfi_forward``):
+  * the FlowFormer flow estimator (gimmvfi_f.py:114-138 -> LatentCostFormer/transformer.py:45-74): Twins-SVT-L encoders, cost-perceiver
+    memory encoder, 32-iteration GMA memory decoder — csrc/flowformer.cu + csrc/ops_tokens.cu, both directions batched;
+  * everything downstream of ``cal_bidirection_flow`` — the same kernels as GIMM-VFI-R (F has no feature projections,
+    gimmvfi_f.py:37-60).
+``model.flow_backend`` (optional) swaps the estimator for a caller-supplied callable with the signature of the reference's
+``FlowFormer.forward(im0, im1, return_feat=True)``; ``forward(..., flow_inputs=...)`` takes precomputed estimator outputs
+(``gimmvfi_forward_from_flow``).  There is no PyTorch re-implementation of FlowFormer on the product path."""
 from typing import Callable, Optional
 
 import torch
@@ -68,7 +66,7 @@ class GIMMVFI_F(nn.Module):
         if self._engine is None or self._engine.device != dev or self._weights_dirty:
             if self._engine is None or self._engine.device != dev:
                 self._engine = EngineHandle(dev)
-            self._engine.load_state_dict(self.state_dict(), synthesis_only=True)
+            self._engine.load_state_dict(self.state_dict(), full_f=True)
             self._engine.tensor_cores = None
             self._weights_dirty = False
         return self._engine
@@ -84,12 +82,9 @@ class GIMMVFI_F(nn.Module):
         return sample_coords(batch_size, s_shape, t_ids, self.coord_range, upsample_ratio, device)
 
     def cal_bidirection_flow(self, im0, im1):
-        """gimmvfi_f.py:114-138 through the external flow backend -> the dict gimmvfi_forward_from_flow takes."""
-        if self.flow_backend is None:
-            raise NotImplementedError(
-                "GIMMVFI_F: the FlowFormer flow estimator is not built natively yet (SURVEY 8(a) a24). Set model.flow_backend to a callable "
-                "with the signature of the reference FlowFormer.forward(im0, im1, return_feat=True); everything downstream runs on the "
-                "sm_100a engine.")
+        """gimmvfi_f.py:114-138 through an EXTERNAL flow backend (model.flow_backend) -> the dict gimmvfi_forward_from_flow takes.
+        Without a backend forward() runs the engine's native FlowFormer and never calls this."""
+        assert self.flow_backend is not None
         f01, feats0, fnet0 = self.flow_backend(im0, im1)
         f10, feats1, fnet1 = self.flow_backend(im1, im0)
         f01 = f01[0] if isinstance(f01, (list, tuple)) else f01
@@ -113,7 +108,7 @@ class GIMMVFI_F(nn.Module):
             eng.set_tensor_cores(int(self.tensor_cores))
         B = img_xs.shape[0]
         xs = img_xs.to(torch.float32).contiguous()
-        if flow_inputs is None:
+        if flow_inputs is None and self.flow_backend is not None:
             x_net = xs
             if ds_factor is not None:   # gimmvfi_f.py:309-318: the estimator sees the down-scaled frames
                 rs = lambda a: torch.nn.functional.interpolate(a, scale_factor=ds_factor, mode="bilinear", align_corners=False)

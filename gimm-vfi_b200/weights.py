@@ -64,21 +64,45 @@ def random_state_dict(seed: int = 0) -> dict:
     return sd
 
 
+def _flow_estimator_init(key: str, shape, dt: str, spec: dict, g: torch.Generator) -> torch.Tensor:
+    """Seeded init of one `flow_estimator.*` (FlowFormer) tensor of GIMM-VFI-F, shaped like a trained network's so that fixtures exercise
+    every branch (torch-default uniform fan-in bounds for Linear / Conv weights and biases, LayerNorm scales near 1, GMA gamma != 0)."""
+    U = lambda sh, b: (torch.rand(sh, generator=g) * 2 - 1) * b
+    leaf = key.rsplit(".", 1)[-1]
+    if dt == "int64":
+        return torch.zeros(shape, dtype=torch.int64)      # att.pos_emb.rel_ind: the positional term is disabled in the reference forward (gma.py:64-70)
+    if leaf == "latent_tokens":
+        return torch.randn(shape, generator=g)
+    if leaf == "gamma":
+        return torch.full(shape, 0.35)
+    is_norm = ".norm" in key.rsplit(".", 1)[0].rsplit(".", 1)[-1] or key.rsplit(".", 2)[-2].startswith("norm")
+    if len(shape) == 1 and is_norm:
+        return (1.0 + 0.1 * torch.randn(shape, generator=g)) if leaf == "weight" else 0.05 * torch.randn(shape, generator=g)
+    if leaf == "weight" and len(shape) >= 2:
+        fan_in = 1
+        for d in shape[1:]:
+            fan_in *= d
+        return U(shape, 1.0 / math.sqrt(fan_in))
+    if leaf == "bias":
+        wshape = spec.get(key[: -len("bias")] + "weight")
+        fan_in = 1
+        for d in (wshape[1:] if wshape else shape):
+            fan_in *= d
+        return U(shape, 1.0 / math.sqrt(fan_in))
+    raise KeyError(key)
+
+
 def random_state_dict_f(seed: int = 0, flow_estimator: dict = None) -> dict:
     """Seeded GIMM-VFI-F state_dict: the decoder / GIMM half takes the SAME tensors as random_state_dict(seed) (identical layout,
-    arch.param_spec_f), `flow_estimator.*` (FlowFormer) comes from the caller (e.g. a reference module's own init) or a small seeded
-    normal init — the native engine does not consume those (the flow estimator is external, model_f.py)."""
+    arch.param_spec_f); `flow_estimator.*` (FlowFormer) comes from the caller (e.g. a reference module's own init) or from the seeded
+    init above — reproducible anywhere, so GPU tests rebuild exactly the weights the reference ran when the fixtures were made."""
     r = random_state_dict(seed)
     g = torch.Generator().manual_seed(seed + 1000)
+    spec = {k: s for k, s, _ in param_spec_f()}
     sd = {}
     for key, shape, dt in param_spec_f():
         if key.startswith("flow_estimator."):
-            if flow_estimator is not None:
-                t = flow_estimator[key].detach().clone()
-            elif dt == "int64":
-                t = torch.zeros(shape, dtype=torch.int64)
-            else:
-                t = 0.02 * torch.randn(shape, generator=g)
+            t = flow_estimator[key].detach().clone() if flow_estimator is not None else _flow_estimator_init(key, shape, dt, spec, g)
             assert tuple(t.shape) == tuple(shape), key
             sd[key] = t
         else:

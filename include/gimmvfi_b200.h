@@ -89,6 +89,13 @@ typedef struct gimmvfi_flow_inputs {
 /* Weights: the GIMM-VFI-F state_dict minus flow_estimator.* (gimmvfi_load_weight each, then this instead of gimmvfi_finalize_weights).
  * A full GIMM-VFI-R engine (gimmvfi_finalize_weights) accepts gimmvfi_forward_from_flow as well (its RAFT is then skipped). */
 int gimmvfi_finalize_weights_synthesis(gimmvfi_engine* e);
+/* The COMPLETE GIMM-VFI-F state_dict (639 tensors, flow_estimator.* = FlowFormer included; gimmvfi_f.py:27-111): gimmvfi_forward then
+ * runs the native FlowFormer estimator (Twins-SVT-L x2, cost-perceiver memory encoder, 32-iteration GMA memory decoder; replaces
+ * flowformer/core/FlowFormer/LatentCostFormer/transformer.py:45-74 as called by gimmvfi_f.py:114-138) followed by the synthesis half.
+ * The network resolution (H, W after ds_factor) must be a multiple of 32. */
+int gimmvfi_finalize_weights_f(gimmvfi_engine* e);
+/* decoder_depth of the FlowFormer memory decoder (default 32, flowformer/configs/submission.py:50) */
+int gimmvfi_set_flowformer_iters(gimmvfi_engine* e, int iters);
 int gimmvfi_plan_from_flow(gimmvfi_engine* e, const gimmvfi_problem* p, size_t* workspace_bytes);
 /* io->raft_flow (optional) receives a copy of `flows` (the reference returns them as "raft_flow", gimmvfi_f.py:382). */
 int gimmvfi_forward_from_flow(gimmvfi_engine* e, const gimmvfi_problem* p, const gimmvfi_io* io, const gimmvfi_flow_inputs* fin,

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "gimm-vfi_b200", "csrc")
-SOURCES = ["ops_pointwise.cu", "corr.cu", "conv.cu", "engine.cu", "c_api.cu"]
+SOURCES = ["ops_pointwise.cu", "corr.cu", "conv.cu", "ops_tokens.cu", "flowformer.cu", "engine.cu", "c_api.cu"]
 SIM_SOURCES = ["tc_hostsim.cu"]   # the emulation of the tcgen05 kernels' arithmetic lives with the tests, not in the product tree
 OUT = os.path.join(HERE, "libgimmvfi_hostsim.so")
 
