@@ -51,7 +51,7 @@ EXPORTS = [
     "gimmvfi_create", "gimmvfi_destroy", "gimmvfi_load_weight", "gimmvfi_finalize_weights", "gimmvfi_plan",
     "gimmvfi_forward", "gimmvfi_last_error", "gimmvfi_last_launches", "gimmvfi_weights_version", "gimmvfi_set_raft_iters", "gimmvfi_set_debug",
     "gimmvfi_get_tap", "gimmvfi_build_info", "gimmvfi_set_profile", "gimmvfi_profile_json",
-    "gimmvfi_set_tensor_cores", "gimmvfi_set_cuda_graph", "gimmvfi_graph_replays", "gimmvfi_finalize_weights_gimm", "gimmvfi_finalize_weights_synthesis", "gimmvfi_finalize_weights_f", "gimmvfi_set_flowformer_iters", "gimmvfi_plan_from_flow", "gimmvfi_forward_from_flow", "gimmvfi_gimm_plan", "gimmvfi_gimm_forward", "gimmvfi_frame_cache_bytes", "gimmvfi_set_frame_cache", "gimmvfi_op_conv2d_tc", "gimmvfi_op_conv2d_tc_f16", "gimmvfi_op_conv2d_tc_strided", "gimmvfi_op_frames_u8_to_padded_f32", "gimmvfi_op_pred_to_u8", "gimmvfi_op_softsplat", "gimmvfi_op_softsplat_fused", "gimmvfi_op_backwarp", "gimmvfi_op_resize",
+    "gimmvfi_set_tensor_cores", "gimmvfi_set_cuda_graph", "gimmvfi_graph_replays", "gimmvfi_finalize_weights_gimm", "gimmvfi_finalize_weights_synthesis", "gimmvfi_finalize_weights_f", "gimmvfi_set_flowformer_iters", "gimmvfi_plan_from_flow", "gimmvfi_forward_from_flow", "gimmvfi_gimm_plan", "gimmvfi_gimm_forward", "gimmvfi_frame_cache_bytes", "gimmvfi_set_frame_cache", "gimmvfi_op_conv2d_tc", "gimmvfi_op_conv2d_tc_f16", "gimmvfi_op_conv2d_tc_strided", "gimmvfi_op_frames_u8_to_padded_f32", "gimmvfi_op_pred_to_u8", "gimmvfi_op_softsplat", "gimmvfi_op_softsplat_fused", "gimmvfi_op_backwarp", "gimmvfi_op_layernorm", "gimmvfi_op_window_attention", "gimmvfi_op_global_attention", "gimmvfi_op_patchify", "gimmvfi_op_cost_conv1", "gimmvfi_op_conv7x7_small_cout", "gimmvfi_op_resize",
     "gimmvfi_op_corr_volume", "gimmvfi_op_corr_volume_tc", "gimmvfi_op_corr_pool", "gimmvfi_op_corr_pool_pyramid", "gimmvfi_op_corr_lookup", "gimmvfi_op_corr_lookup_direct", "gimmvfi_op_conv2d",
     "gimmvfi_instnorm_scratch_floats", "gimmvfi_op_hyponet", "gimmvfi_op_conv2d_halo", "gimmvfi_op_instnorm", "gimmvfi_op_convex_upsample", "gimmvfi_op_pixel_shuffle",
 ]
@@ -116,6 +116,12 @@ class Lib:
         d.gimmvfi_op_softsplat_fused.argtypes = [PV, PV, PV, vp, i32, vp, PV, vp]
         d.gimmvfi_op_backwarp.argtypes = [PV, PV, PV, vp]
         d.gimmvfi_op_resize.argtypes = [PV, PV, f32, f32, vp]
+        d.gimmvfi_op_layernorm.argtypes = [PV, vp, vp, f32, PV, f32, i32, vp]
+        d.gimmvfi_op_window_attention.argtypes = [PV, PV, PV, PV, i32, i32, vp]
+        d.gimmvfi_op_global_attention.argtypes = [PV, PV, PV, PV, i32, vp]
+        d.gimmvfi_op_patchify.argtypes = [PV, PV, i32, vp]
+        d.gimmvfi_op_cost_conv1.argtypes = [vp, i64, i32, i32, vp, vp, PV, vp]
+        d.gimmvfi_op_conv7x7_small_cout.argtypes = [PV, vp, vp, i32, PV, vp]
         d.gimmvfi_op_corr_volume.argtypes = [PV, PV, vp, vp]
         d.gimmvfi_op_corr_pool.argtypes = [vp, vp, i64, i32, i32, vp]
         d.gimmvfi_op_corr_volume_tc.argtypes = [PV, PV, vp, vp, i32, vp]

@@ -165,6 +165,50 @@ int gimmvfi_op_resize(const gimmvfi_view* src, const gimmvfi_view* dst, float sc
     resize_bilinear(cx, to_tv(src), to_tv(dst), r, r, mult, 0, ACT_NONE);
   })
 }
+// ---- FlowFormer / Twins token-side kernels (ops_tokens.cu), NHWC views
+int gimmvfi_op_layernorm(const gimmvfi_view* x, const float* gamma, const float* beta, float eps, const gimmvfi_view* out, float pe_scale, int pe_dim,
+                         void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); layernorm(cx, to_tv(x), gamma, beta, eps, to_tv(out), pe_scale, pe_dim); })
+}
+int gimmvfi_op_window_attention(const gimmvfi_view* q, const gimmvfi_view* k, const gimmvfi_view* v, const gimmvfi_view* out, int heads, int ws,
+                                void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); window_attention(cx, to_tv(q), to_tv(k), to_tv(v), to_tv(out), heads, ws); })
+}
+int gimmvfi_op_global_attention(const gimmvfi_view* q, const gimmvfi_view* k, const gimmvfi_view* v, const gimmvfi_view* out, int heads, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    const TV Q = to_tv(q); const TV K = to_tv(k); const TV V = to_tv(v); const TV O = to_tv(out);
+    if (Q.c != O.c || K.c != Q.c || V.c != Q.c || Q.c % heads || Q.n != K.n || K.h != V.h || K.w != V.w) throw std::runtime_error("global_attention: shape mismatch");
+    AttnDims a{};
+    a.nb1 = Q.n; a.nb2 = 1; a.nq = (int64_t)Q.h * Q.w; a.nk = (int64_t)K.h * K.w; a.heads = heads;
+    a.q_s1 = Q.sn; a.q_si = Q.ld; a.k_s1 = K.sn; a.k_sj = K.ld; a.v_s1 = V.sn; a.v_sj = V.ld; a.o_s1 = O.sn; a.o_si = O.ld;
+    strided_attention(cx, Q.p, K.p, V.p, O.p, a, Q.c / heads);
+  })
+}
+int gimmvfi_op_patchify(const gimmvfi_view* src, const gimmvfi_view* dst, int k, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, { Ctx cx = op_ctx(stream); patchify(cx, to_tv(src), to_tv(dst), k); })
+}
+int gimmvfi_op_cost_conv1(const float* vol, int64_t maps, int h, int w, const float* w_host, const float* b_host, const gimmvfi_view* out_padded,
+                          void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    const TV o = to_tv(out_padded);
+    cost_conv1(cx, vol, maps, h, w, w_host, b_host, o, o.h - 4, o.w - 4);
+  })
+}
+int gimmvfi_op_conv7x7_small_cout(const gimmvfi_view* in, const float* w_tap_cin_4, const float* bias, int cout, const gimmvfi_view* out, void* stream) {
+  gimmvfi_engine* e = nullptr;
+  GV_TRY(e, {
+    Ctx cx = op_ctx(stream);
+    ConvW w; w.w = w_tap_cin_4; w.b = bias; w.cin = to_tv(in).c; w.cout = cout; w.kh = w.kw = 7; w.cout_ld = 4;
+    if (!conv7x7_small_cout(cx, to_tv(in), w, ACT_NONE, nullptr, to_tv(out))) throw std::runtime_error("conv7x7_small_cout: layer / tensors not of that class (or host simulation)");
+  })
+}
 int gimmvfi_op_corr_volume(const gimmvfi_view* fa, const gimmvfi_view* fb, float* vol, void* stream) {
   gimmvfi_engine* e = nullptr;
   GV_TRY(e, { Ctx cx = op_ctx(stream); TV a = to_tv(fa); corr_volume(cx, a, to_tv(fb), vol, 1.0f / std::sqrt((float)a.c)); })

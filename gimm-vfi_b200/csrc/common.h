@@ -329,6 +329,7 @@ GV_HD float atomic_add_f(float* addr, float v) {
 // conv.cu
 void conv2d(Ctx& cx, const TV& in0, const TV& in1 /*optional 2nd channel segment*/, const ConvW& w, const ConvGeom& g,
             const ConvEpi& e, const TV& out);
+bool conv7x7_small_cout(Ctx& cx, const TV& in, const ConvW& w /*plain packed [tap][cin][4]*/, int act, const float* slope, const TV& out);   // conv.cu
 // conv_tc.cu (sm_100a tcgen05 / TMA path; not part of the host simulation)
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
 void conv2d_tc(Ctx& cx, const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split);
@@ -411,7 +412,7 @@ void strided_attention(Ctx& cx, const float* q, const float* k, const float* v, 
 void concat_pe(Ctx& cx, const TV& a, const TV& b, const TV& out, int ws, bool add_pe, int grp_all, int ctx_per);
 void write_pe(Ctx& cx, const TV& out, float scale, float shift);
 void add_pe_coords(Ctx& cx, const TV& x, const TV& coords, const TV& out);
-void cost_conv1(Ctx& cx, const float* vol, int64_t maps, int h, int w, const float* wt, const float* bias, const TV& out_padded, int oh, int ow);
+void cost_conv1(Ctx& cx, const float* vol, int64_t maps, int h, int w, const float* wt_host /*[36][16]*/, const float* bias_host /*[16]*/, const TV& out_padded, int oh, int ow);
 void row_softmax(Ctx& cx, float* p, int64_t rows, int64_t cols, float mul);
 void gemm_nn(Ctx& cx, const float* A, const float* Bm, float* out, int64_t rows, int64_t K, int D, int64_t lda, int64_t ldb, int64_t ldo, float scale);
 void transpose_2d(Ctx& cx, const float* src, float* dst, int64_t rows, int cols, int64_t lds);

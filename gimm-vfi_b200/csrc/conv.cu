@@ -320,6 +320,73 @@ static bool conv_thin_ok(const ConvArgs& a) {
 }
 #endif
 
+#ifndef GV_HOSTSIM
+// 7x7 convolutions with <= 4 output channels on few input channels at FULL resolution (amt_comb_block.2: 18 -> 3, gimmvfi_r.py:60-64):
+// as an MMA tile this layer pays one K step per (tap row, 32 lanes) for N = 3 useful columns (1.2 ms at 1088x1920 / 1088x2048, bound by
+// the per-K-step hand-off of conv_tc.cu).  Here a CTA stages a 32 x 8 output tile's 38 x 14 halo and all weights in shared memory once;
+// a thread owns one pixel: one conflict-free LDS per input value (odd channel stride), one broadcast LDS.128 per 4 weights.  Exact fp32.
+__global__ void __launch_bounds__(256) conv7x7_small_cout_kernel(TV in, const float* __restrict__ w, const float* __restrict__ bias, TV out,
+                                                                 int cin, int cs, int cout, int act, const float* slope) {
+  extern __shared__ __align__(16) float sm_c7[];
+  float* wsm = sm_c7;                       // [49][cin][4]
+  float* tile = sm_c7 + 49 * cin * 4;       // [14][38][cs]
+  const int tid = threadIdx.y * 32 + threadIdx.x, n = blockIdx.z;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  for (int i = tid; i < 49 * cin * 4; i += 256) wsm[i] = w[i];
+  for (int i = tid; i < 14 * 38 * cin; i += 256) {
+    const int ci = i % cin; int r = i / cin; const int px = r % 38, py = r / 38;
+    const int gy = y0 + py - 3, gx = x0 + px - 3;
+    tile[(py * 38 + px) * cs + ci] = (gy >= 0 && gy < in.h && gx >= 0 && gx < in.w) ? in.p[in.off(n, gy, gx) + ci] : 0.f;
+  }
+  __syncthreads();
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float* t = tile + ((threadIdx.y + ky) * 38 + threadIdx.x + kx) * cs;
+      const float4* wp = reinterpret_cast<const float4*>(wsm) + (ky * 7 + kx) * cin;
+#pragma unroll 6
+      for (int ci = 0; ci < cin; ++ci) {
+        const float v = t[ci]; const float4 ww = wp[ci];
+        a0 = fmaf(v, ww.x, a0); a1 = fmaf(v, ww.y, a1); a2 = fmaf(v, ww.z, a2); a3 = fmaf(v, ww.w, a3);
+      }
+    }
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x < out.w && y < out.h) {
+    float* o = out.p + out.off(n, y, x);
+    const float r[4] = {a0, a1, a2, a3};
+    for (int c = 0; c < cout; ++c) o[c] = apply_act(r[c] + bias[c], act, slope, c);
+  }
+}
+#endif
+// returns false when the layer / tensors are not of that class (the caller then takes the generic path)
+bool conv7x7_small_cout(Ctx& cx, const TV& in, const ConvW& w, int act, const float* slope, const TV& out) {
+#ifdef GV_HOSTSIM
+  (void)cx; (void)in; (void)w; (void)act; (void)slope; (void)out;
+  return false;
+#else
+  if (w.kh != 7 || w.kw != 7 || w.cout > 4 || w.cout_ld != 4 || w.cin > 24 || in.c != w.cin || in.f16 || out.f16 || out.c != w.cout || in.n != out.n || in.h != out.h ||
+      in.w != out.w || act == ACT_SIGMOID || act == ACT_TANH || act == ACT_SIN || act == ACT_GELU)
+    return false;
+  if (cx.dry) return true;
+  const int cs = w.cin | 1;   // odd channel stride: x-neighbouring threads hit different banks
+  const int smem = (49 * w.cin * 4 + 14 * 38 * cs) * (int)sizeof(float);
+  static volatile unsigned char attr[64];
+  gv_set_max_smem(conv7x7_small_cout_kernel, smem, attr);
+  cx.launches++;
+  if (cx.prof) {
+    char nm[128];
+    snprintf(nm, sizeof nm, "conv7x7_small_cout c%d>%d @%dx%dx%d", w.cin, w.cout, out.n, out.h, out.w);
+    cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.pixels() * w.cout * (double)w.cin * 49);
+  }
+  dim3 grid((out.w + 31) / 32, (out.h + 7) / 8, out.n), block(32, 8);
+  conv7x7_small_cout_kernel<<<grid, block, smem, cx.stream>>>(in, w.w, w.b, out, w.cin, cs, w.cout, act, slope);
+  gv_check_launch("conv7x7_small_cout");
+  if (cx.prof) cx.prof->end(cx.stream);
+  return true;
+#endif
+}
+
 // Eligibility of a layer for the tensor-core path (conv_tc.cu; its arithmetic is emulated on the host in tests/hostsim)
 bool conv2d_tc_supported(const TV& in0, const TV& in1, const ConvW& w, const ConvGeom& g, const ConvEpi& e, const TV& out, bool split) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

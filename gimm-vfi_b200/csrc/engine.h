@@ -104,6 +104,8 @@ class Engine {
   int raft_iters = 20;  // GIMMVFI_R hard-codes iters=20 (gimmvfi_r.py:126-132)
   int ff_iters = 32;    // FlowFormer decoder_depth (flowformer/configs/submission.py:50; gimmvfi_f.py:115 passes iters=None)
   bool is_f() const { return ff_; }
+  const float* ff_c1w() const { return ff_c1w_.data(); }   // first cost-map patch-embedding layer, [36 taps][16] and [16] (host copies)
+  const float* ff_c1b() const { return ff_c1b_.data(); }
   // debug taps from the estimator's helpers (flowformer.cu)
   bool debug_on() const { return debug_; }
   void tap_pub(const std::string& name, const TV& tv) { tap(name, tv); }
@@ -142,6 +144,7 @@ class Engine {
   std::vector<GraphEntry> graphs_;
   void clear_graphs();
   int precise_ = 0;   // bit mask of post-RAFT stages in 3xTF32: 1 GIMM encoders / latent refiner, 2 HypoNet, 4 init decoder + update blocks, 8 final decoder, 16 combine
+  std::vector<float> ff_c1w_, ff_c1b_;
   float* fc_ = nullptr; size_t fc_bytes_ = 0; bool fc_load_ = false, fc_store_ = false;
   // what the cache holds (host-side bookkeeping of the last store): a load with a different buffer / problem is refused
   // (one record per cache buffer, so several video streams can share an engine; cleared when the weights change)

@@ -73,7 +73,7 @@ void Engine::finalize_flowformer() {
     if (W.shape[0] != 16 || W.shape[1] != 1 || W.shape[2] != 6) throw std::runtime_error("flowformer: unexpected cost patch embedding");
     std::vector<float> w((size_t)36 * 16);
     for (int co = 0; co < 16; ++co) for (int t = 0; t < 36; ++t) w[(size_t)t * 16 + co] = W.data[(size_t)co * 36 + t];
-    vec_[cp + ".patch_embed.proj.0.weight#t16"] = upload(w); vec(cp + ".patch_embed.proj.0.bias");
+    ff_c1w_ = w; ff_c1b_ = raw(cp + ".patch_embed.proj.0.bias").data;   // kept on the host: cost_conv1 passes them in its kernel parameter block
     pack_xpacked(cp + ".patch_embed.proj.2", 16); pack_xpacked(cp + ".patch_embed.proj.4", 32);
     pack_conv(cp + ".patch_embed.ffn_with_coord.0"); pack_conv(cp + ".patch_embed.ffn_with_coord.2");
     vec(cp + ".patch_embed.norm.weight"); vec(cp + ".patch_embed.norm.bias");
@@ -312,7 +312,7 @@ struct FF {
         TV c1 = A.tensor(cm, oh1 + 4, ow1 + 4, 16), c2 = A.tensor(cm, oh2, ow2, 32), c2p = A.tensor(cm, oh2 + 4, ow2 + 4, 32);
         TV xpe = A.tensor(cm, oh3, ow3, 128), t1 = A.tensor(cm, oh3, ow3, 128), t2 = A.tensor(cm, oh3, ow3, 128);
         TV kk = A.tensor(cm, oh3, ow3, 128), vv = A.tensor(cm, oh3, ow3, 128);
-        cost_conv1(cx, vol + ((int64_t)s * Npx + p0) * Npx, cm, h, w, V(pe + ".proj.0.weight#t16"), V(pe + ".proj.0.bias"), c1, oh1, ow1);
+        cost_conv1(cx, vol + ((int64_t)s * Npx + p0) * Npx, cm, h, w, E.ff_c1w(), E.ff_c1b(), c1, oh1, ow1);
         ConvGeom g; g.stride = 2; g.ph = 0; g.pw = 0; g.loose_w = 1;   // pre-padded inputs: the taps index the buffer directly
         { TV v1 = c1; v1.c = w2.cin; ConvEpi e; e.act1 = ACT_RELU; conv2d(cx, v1, TV(), w2, g, e, c2); }
         pad_zero(cx, c2, c2p, 2);

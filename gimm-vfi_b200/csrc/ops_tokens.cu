@@ -77,38 +77,54 @@ struct LayerNormK {
   }
 };
 #ifndef GV_HOSTSIM
-// one warp per token: coalesced row reads, shuffle reductions (the thread-per-token functor reads 32 different rows per instruction)
+// one warp per token: a lane owns 4 consecutive channels per 128-channel group (one 16-byte load / store each), shuffle reductions
+// (the first version issued 16 predicated scalar loads per lane: 1.2 TB/s, instruction bound per ncu)
 __global__ void __launch_bounds__(256) layernorm_warp_kernel(TV x, TV out, const float* __restrict__ g, const float* __restrict__ b, float eps,
                                                              float pe_scale, int pe_dim, int64_t tokens) {
   const int lane = threadIdx.x & 31;
   const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int C = x.c;
+  const int C = x.c;   // C % 4 == 0, C <= 512
   for (int64_t i = w0; i < tokens; i += nw) {
     const int px = (int)(i % out.w); int64_t r = i / out.w; const int py = (int)(r % out.h); const int n = (int)(r / out.h);
     float* o = out.p + out.off(n, py, px);
-    if (py >= x.h || px >= x.w) { for (int c = lane; c < C; c += 32) o[c] = 0.f; continue; }
+    if (py >= x.h || px >= x.w) {
+      for (int c = lane * 4; c < C; c += 128) *reinterpret_cast<float4*>(o + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     const float* s = x.p + x.off(n, py, px);
-    float v[16];   // C <= 512
+    float4 v[4];
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { const int c = lane + 32 * k; v[k] = c < C ? s[c] : 0.f; sum += v[k]; }
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane * 4 + 128 * k;
+      v[k] = c < C ? *reinterpret_cast<const float4*>(s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
     const float mean = sum / (float)C;
     float var = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { const int c = lane + 32 * k; const float dd = c < C ? v[k] - mean : 0.f; var = fmaf(dd, dd, var); }
+    for (int k = 0; k < 4; ++k) {
+      if (lane * 4 + 128 * k < C) {
+        const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+        var = fmaf(d0, d0, var); var = fmaf(d1, d1, var); var = fmaf(d2, d2, var); var = fmaf(d3, d3, var);
+      }
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
     const float rstd = 1.0f / sqrtf(var / (float)C + eps);
     const float X = (float)px * pe_scale, Y = (float)py * pe_scale;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int c = lane + 32 * k;
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane * 4 + 128 * k;
       if (c < C) {
-        float y = ((v[k] - mean) * rstd) * g[c] + b[c];
-        if (pe_dim > 0) y += pe_value(c, pe_dim, X, Y);
-        o[c] = y;
+        const float4 gg = *reinterpret_cast<const float4*>(g + c), bb = *reinterpret_cast<const float4*>(b + c);
+        float4 y;
+        y.x = ((v[k].x - mean) * rstd) * gg.x + bb.x; y.y = ((v[k].y - mean) * rstd) * gg.y + bb.y;
+        y.z = ((v[k].z - mean) * rstd) * gg.z + bb.z; y.w = ((v[k].w - mean) * rstd) * gg.w + bb.w;
+        if (pe_dim > 0) { y.x += pe_value(c, pe_dim, X, Y); y.y += pe_value(c + 1, pe_dim, X, Y); y.z += pe_value(c + 2, pe_dim, X, Y); y.w += pe_value(c + 3, pe_dim, X, Y); }
+        *reinterpret_cast<float4*>(o + c) = y;
       }
     }
   }
@@ -117,7 +133,7 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(TV x, TV out, const
 void layernorm(Ctx& cx, const TV& x, const float* g, const float* b, float eps, const TV& out, float pe_scale, int pe_dim) {
   if (out.c != x.c || out.n != x.n || out.h < x.h || out.w < x.w) throw std::runtime_error("layernorm: shape mismatch");
 #ifndef GV_HOSTSIM
-  if (x.c <= 512) {
+  if (x.c <= 512 && vec4_ok(x) && vec4_ok(out) && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0) {
     if (cx.dry) return;
     cx.launches++;
     const int64_t tokens = out.pixels();
@@ -174,20 +190,24 @@ struct WindowAttnK {
     float qv[HD], acc[HD];
     const float* qp = q.p + q.off(n, qy, qx) + hd * HD;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) { qv[d] = qp[d]; acc[d] = 0.f; }
+    for (int d = 0; d < HD; d += 4) { const F4 t = ld4(qp + d); qv[d] = t.x; qv[d + 1] = t.y; qv[d + 2] = t.z; qv[d + 3] = t.w; acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f; }
     float m = -3.0e38f, l = 0.f;
     for (int j = 0; j < W2; ++j) {
       const int ky = wy * ws + j / ws, kx = wx * ws + j % ws;
       const float* kp = k.p + k.off(n, ky, kx) + hd * HD;
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(qv[d], kp[d], s);
+      for (int d = 0; d < HD; d += 4) { const F4 t = ld4(kp + d); s = fmaf(qv[d], t.x, s); s = fmaf(qv[d + 1], t.y, s); s = fmaf(qv[d + 2], t.z, s); s = fmaf(qv[d + 3], t.w, s); }
       s *= scale;
       const float mn = fmaxf(m, s), corr = expf(m - mn), p = expf(s - mn);
       const float* vp = v.p + v.off(n, ky, kx) + hd * HD;
       l = l * corr + p;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, vp[d], acc[d] * corr);
+      for (int d = 0; d < HD; d += 4) {
+        const F4 t = ld4(vp + d);
+        acc[d] = fmaf(p, t.x, acc[d] * corr); acc[d + 1] = fmaf(p, t.y, acc[d + 1] * corr);
+        acc[d + 2] = fmaf(p, t.z, acc[d + 2] * corr); acc[d + 3] = fmaf(p, t.w, acc[d + 3] * corr);
+      }
       m = mn;
     }
     float* o = out.p + out.off(n, qy, qx) + hd * HD;
@@ -224,19 +244,23 @@ struct StridedAttnK {
     const float* vb = v + b1 * a.v_s1 + b2 * a.v_s2 + hd * HD;
     float qv[HD], acc[HD];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) { qv[d] = qp[d]; acc[d] = 0.f; }
+    for (int d = 0; d < HD; d += 4) { const F4 t = ld4(qp + d); qv[d] = t.x; qv[d + 1] = t.y; qv[d + 2] = t.z; qv[d + 3] = t.w; acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f; }
     float m = -3.0e38f, l = 0.f;
     for (int64_t j = 0; j < a.nk; ++j) {
       const float* kp = kb + j * a.k_sj;
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(qv[d], kp[d], s);
+      for (int d = 0; d < HD; d += 4) { const F4 t = ld4(kp + d); s = fmaf(qv[d], t.x, s); s = fmaf(qv[d + 1], t.y, s); s = fmaf(qv[d + 2], t.z, s); s = fmaf(qv[d + 3], t.w, s); }
       s *= scale;
       const float mn = fmaxf(m, s), corr = expf(m - mn), p = expf(s - mn);
       const float* vp = vb + j * a.v_sj;
       l = l * corr + p;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, vp[d], acc[d] * corr);
+      for (int d = 0; d < HD; d += 4) {
+        const F4 t = ld4(vp + d);
+        acc[d] = fmaf(p, t.x, acc[d] * corr); acc[d + 1] = fmaf(p, t.y, acc[d + 1] * corr);
+        acc[d + 2] = fmaf(p, t.z, acc[d + 2] * corr); acc[d + 3] = fmaf(p, t.w, acc[d + 3] * corr);
+      }
       m = mn;
     }
     float* o = out + b1 * a.o_s1 + b2 * a.o_s2 + qi * a.o_si + hd * HD;
@@ -245,9 +269,108 @@ struct StridedAttnK {
     for (int d = 0; d < HD; ++d) o[d] = acc[d] * il;
   }
 };
+#ifndef GV_HOSTSIM
+// Many queries against one key / value set per (batch, head) — Twins' sub-sampled global attention (twins.py:898-925, :466-546): a CTA
+// takes 256 queries of one (batch, head), the keys / values stream through shared memory in tiles (every thread reads the same key:
+// one broadcast LDS.128 per 4 elements instead of a global load per element), online softmax over groups of 4 keys (5 exp per 4 keys).
+template <int HD, int KT>
+__global__ void __launch_bounds__(256) attention_shared_kv_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                                                  float* __restrict__ out, AttnDims a, float scale) {
+  extern __shared__ __align__(16) float smem_kv[];
+  float* Ks = smem_kv; float* Vs = smem_kv + KT * HD;
+  const int head = blockIdx.y; const int64_t b1 = blockIdx.z;
+  const int64_t qi = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool live = qi < a.nq;
+  const float* kb = k + b1 * a.k_s1 + head * HD;
+  const float* vb = v + b1 * a.v_s1 + head * HD;
+  float qv[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) { qv[d] = 0.f; acc[d] = 0.f; }
+  if (live) {
+    const float* qp = q + b1 * a.q_s1 + qi * a.q_si + head * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) { const float4 t = *reinterpret_cast<const float4*>(qp + d); qv[d] = t.x * scale; qv[d + 1] = t.y * scale; qv[d + 2] = t.z * scale; qv[d + 3] = t.w * scale; }
+  }
+  float m = -3.0e38f, l = 0.f;
+  for (int64_t j0 = 0; j0 < a.nk; j0 += KT) {
+    const int tn = (int)((a.nk - j0) < KT ? (a.nk - j0) : KT);
+    const int tn4 = (tn + 3) & ~3;
+    __syncthreads();
+    for (int e = threadIdx.x; e < tn4 * (HD / 4); e += 256) {
+      const int j = e / (HD / 4), c = (e - j * (HD / 4)) * 4;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (j < tn) { kk = *reinterpret_cast<const float4*>(kb + (j0 + j) * a.k_sj + c); vv = *reinterpret_cast<const float4*>(vb + (j0 + j) * a.v_sj + c); }
+      *reinterpret_cast<float4*>(Ks + j * HD + c) = kk; *reinterpret_cast<float4*>(Vs + j * HD + c) = vv;
+    }
+    __syncthreads();
+    for (int j = 0; j < tn4; j += 4) {
+      float s[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* kp = Ks + (j + u) * HD;
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; d += 8) {
+          const float4 x = *reinterpret_cast<const float4*>(kp + d), y = *reinterpret_cast<const float4*>(kp + d + 4);
+          t0 = fmaf(qv[d], x.x, t0); t0 = fmaf(qv[d + 1], x.y, t0); t0 = fmaf(qv[d + 2], x.z, t0); t0 = fmaf(qv[d + 3], x.w, t0);
+          t1 = fmaf(qv[d + 4], y.x, t1); t1 = fmaf(qv[d + 5], y.y, t1); t1 = fmaf(qv[d + 6], y.z, t1); t1 = fmaf(qv[d + 7], y.w, t1);
+        }
+        s[u] = (j + u < tn) ? t0 + t1 : -3.0e38f;
+      }
+      const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+      const float corr = expf(m - mn);
+      float p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = expf(s[u] - mn);
+      l = fmaf(l, corr, (p[0] + p[1]) + (p[2] + p[3]));
+      m = mn;
+#pragma unroll
+      for (int d = 0; d < HD; d += 4) {
+        const float4 v0 = *reinterpret_cast<const float4*>(Vs + (j + 0) * HD + d), v1 = *reinterpret_cast<const float4*>(Vs + (j + 1) * HD + d);
+        const float4 v2 = *reinterpret_cast<const float4*>(Vs + (j + 2) * HD + d), v3 = *reinterpret_cast<const float4*>(Vs + (j + 3) * HD + d);
+        acc[d] = fmaf(p[3], v3.x, fmaf(p[2], v2.x, fmaf(p[1], v1.x, fmaf(p[0], v0.x, acc[d] * corr))));
+        acc[d + 1] = fmaf(p[3], v3.y, fmaf(p[2], v2.y, fmaf(p[1], v1.y, fmaf(p[0], v0.y, acc[d + 1] * corr))));
+        acc[d + 2] = fmaf(p[3], v3.z, fmaf(p[2], v2.z, fmaf(p[1], v1.z, fmaf(p[0], v0.z, acc[d + 2] * corr))));
+        acc[d + 3] = fmaf(p[3], v3.w, fmaf(p[2], v2.w, fmaf(p[1], v1.w, fmaf(p[0], v0.w, acc[d + 3] * corr))));
+      }
+    }
+  }
+  if (live) {
+    float* o = out + b1 * a.o_s1 + qi * a.o_si + head * HD;
+    const float il = 1.0f / l;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) *reinterpret_cast<float4*>(o + d) = make_float4(acc[d] * il, acc[d + 1] * il, acc[d + 2] * il, acc[d + 3] * il);
+  }
+}
+template <int HD, int KT>
+static void launch_attention_shared_kv(Ctx& cx, const float* q, const float* k, const float* v, float* out, const AttnDims& a, float scale) {
+  const int smem = 2 * KT * HD * (int)sizeof(float);
+  static volatile unsigned char attr[64];
+  gv_set_max_smem(attention_shared_kv_kernel<HD, KT>, smem, attr);
+  cx.launches++;
+  if (cx.prof) cx.prof->begin(cx.stream, HD == 16 ? "attention_shared_kv_d16" : "attention_shared_kv_d32", 4.0 * (double)a.nb1 * a.heads * a.nq * a.nk * HD);
+  dim3 grid((unsigned)((a.nq + 255) / 256), (unsigned)a.heads, (unsigned)a.nb1);
+  attention_shared_kv_kernel<HD, KT><<<grid, 256, smem, cx.stream>>>(q, k, v, out, a, scale);
+  gv_check_launch("attention_shared_kv");
+  if (cx.prof) cx.prof->end(cx.stream);
+}
+#endif
+
 void strided_attention(Ctx& cx, const float* q, const float* k, const float* v, float* out, const AttnDims& a, int head_dim) {
   const int64_t items = a.nb1 * a.nb2 * a.heads * a.nq;
   const float scale = 1.0f / std::sqrt((float)head_dim);
+#ifndef GV_HOSTSIM
+  {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool strides4 = !((a.q_s1 | a.q_si | a.k_s1 | a.k_sj | a.v_s1 | a.v_sj | a.o_s1 | a.o_si) & 3);
+    if (a.nb2 == 1 && a.nq >= 2048 && a.nk >= 32 && a.nb1 <= 65535 && (head_dim == 16 || head_dim == 32) && al(q) && al(k) && al(v) && al(out) && strides4) {
+      if (cx.dry) return;
+      if (head_dim == 16) launch_attention_shared_kv<16, 512>(cx, q, k, v, out, a, scale);
+      else launch_attention_shared_kv<32, 256>(cx, q, k, v, out, a, scale);
+      return;
+    }
+  }
+#endif
   switch (head_dim) {
     case 8: parallel_for(cx, items, StridedAttnK<8>{q, k, v, out, a, scale}, "attention_d8"); break;
     case 16: parallel_for(cx, items, StridedAttnK<16>{q, k, v, out, a, scale}, "attention_d16"); break;
@@ -308,38 +431,47 @@ void add_pe_coords(Ctx& cx, const TV& x, const TV& coords, const TV& out) { para
 // size (encoder.py:68-71).  Input: `maps` rows of the all-pairs volume (h x w each, contiguous).  Output: (maps, oh + 4, ow + 4, 16) with a
 // zero border of 2 - the pre-padded input of the next 6x6 stride-2 layer (its taps then index the buffer directly).
 struct CostConv1K {
-  const float* vol; int h, w; const float* wt /*[36][16]*/; const float* bias; TV out; int oh, ow;
+  const float* vol; int h, w; TV out; int oh, ow;
+  float wt[36 * 16]; float bias[16];   // by value: the functor is the kernel's parameter block, so every weight is a constant-bank operand
   GV_HD void operator()(int64_t i) const {
     const int px = (int)(i % out.w); int64_t r = i / out.w; const int py = (int)(r % out.h); const int64_t m = r / out.h;
     float* o = out.p + (int64_t)m * out.sn + ((int64_t)py * out.w + px) * out.ld;
     const int oy = py - 2, ox = px - 2;
-    if (oy < 0 || oy >= oh || ox < 0 || ox >= ow) {
-      for (int c = 0; c < 16; ++c) o[c] = 0.f;
-      return;
-    }
     float acc[16];
+    if (oy < 0 || oy >= oh || ox < 0 || ox >= ow) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = bias[c];
-    const float* img = vol + m * (int64_t)h * w;
-    for (int ky = 0; ky < 6; ++ky) {
-      const int sy = oy * 2 + ky - 2;
-      if (sy < 0 || sy >= h) continue;
-      for (int kx = 0; kx < 6; ++kx) {
-        const int sx = ox * 2 + kx - 2;
-        if (sx < 0 || sx >= w) continue;
-        const float a = img[(int64_t)sy * w + sx];
-        const float* wr = wt + (ky * 6 + kx) * 16;
+      for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    } else {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = fmaf(a, wr[c], acc[c]);
+      for (int c = 0; c < 16; ++c) acc[c] = bias[c];
+      const float* img = vol + m * (int64_t)h * w;
+#pragma unroll
+      for (int ky = 0; ky < 6; ++ky) {
+        const int sy = oy * 2 + ky - 2;
+        if (sy < 0 || sy >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < 6; ++kx) {
+          const int sx = ox * 2 + kx - 2;
+          if (sx < 0 || sx >= w) continue;
+          const float a = img[(int64_t)sy * w + sx];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] = fmaf(a, wt[(ky * 6 + kx) * 16 + c], acc[c]);
+        }
       }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = acc[c] > 0.f ? acc[c] : 0.f;
     }
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = acc[c] > 0.f ? acc[c] : 0.f;
+    for (int c = 0; c < 16; c += 4) { F4 t = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3]}; st4(o + c, t); }
   }
 };
-void cost_conv1(Ctx& cx, const float* vol, int64_t maps, int h, int w, const float* wt, const float* bias, const TV& out_padded, int oh, int ow) {
-  if (out_padded.n != maps || out_padded.h != oh + 4 || out_padded.w != ow + 4 || out_padded.c != 16) throw std::runtime_error("cost_conv1: shape mismatch");
-  parallel_for(cx, out_padded.pixels(), CostConv1K{vol, h, w, wt, bias, out_padded, oh, ow}, "cost_conv1_6x6s2");
+void cost_conv1(Ctx& cx, const float* vol, int64_t maps, int h, int w, const float* wt_host, const float* bias_host, const TV& out_padded, int oh, int ow) {
+  if (out_padded.n != maps || out_padded.h != oh + 4 || out_padded.w != ow + 4 || out_padded.c != 16 || out_padded.ld % 4 || (reinterpret_cast<uintptr_t>(out_padded.p) & 15))
+    throw std::runtime_error("cost_conv1: shape mismatch");
+  CostConv1K f;
+  f.vol = vol; f.h = h; f.w = w; f.out = out_padded; f.oh = oh; f.ow = ow;
+  std::memcpy(f.wt, wt_host, sizeof f.wt); std::memcpy(f.bias, bias_host, sizeof f.bias);
+  parallel_for(cx, out_padded.pixels(), f, "cost_conv1_6x6s2");
 }
 
 // ------------------------------------------------------------------ GMA attention (gma.py:56-76): softmax over each row, in place,

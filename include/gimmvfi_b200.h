@@ -156,6 +156,26 @@ int gimmvfi_op_backwarp(const gimmvfi_view* src, const gimmvfi_view* flow, const
 /* F.interpolate(bilinear, align_corners=False): modules/fi_utils.py:67-70; dst = mult * resize(src) */
 int gimmvfi_op_resize(const gimmvfi_view* src, const gimmvfi_view* dst, float scale_factor, float mult, void* stream);
 /* all-pairs correlation raft/corr.py:167-175: vol[n][i][j] = <fa[n,i,:], fb[n,j,:]> / sqrt(C) */
+/* FlowFormer / Twins-SVT token-side kernels (GIMM-VFI-F's estimator; csrc/ops_tokens.cu).  A token sequence (B, H*W, C) is an NHWC view.
+ *   layernorm        nn.LayerNorm over the channels; `out` may be larger than `x` (zero rows / columns: the padding Twins applies after
+ *                    the norm, LatentCostFormer/twins.py:835-842); pe_dim > 0 adds LinearPositionEmbeddingSine(x*pe_scale, y*pe_scale)
+ *                    (attention.py:170-182)
+ *   window_attention LocallyGroupedAttn core (twins.py:846-860): q, k, v on the padded map, ws x ws windows, softmax(q k^T / sqrt(d)) v
+ *   global_attention GlobalSubSampleAttn core (twins.py:898-921): every token of q against all tokens of the (sub-sampled) k / v map
+ *   patchify         space-to-depth: a k x k stride-k Conv2d (PatchEmbed twins.py:1142, `sr` twins.py:890) = this + a 1x1 convolution
+ *   cost_conv1       Conv2d(1, 16, 6, stride 2, padding 2) + ReLU over `maps` cost maps (encoder.py:38-48), zero-extended to a multiple of 8,
+ *                    written with a zero border of 2 (out_padded: (maps, oh+4, ow+4, 16)); weights [36][16] / bias [16] are HOST pointers
+ *   conv7x7_small_cout  7x7 stride-1 zero-padded Conv2d with <= 4 output channels (amt_comb_block.2, gimmvfi_r.py:60-64), exact fp32;
+ *                    weights [49][cin][4] / bias device pointers */
+int gimmvfi_op_layernorm(const gimmvfi_view* x, const float* gamma, const float* beta, float eps, const gimmvfi_view* out, float pe_scale, int pe_dim,
+                         void* stream);
+int gimmvfi_op_window_attention(const gimmvfi_view* q, const gimmvfi_view* k, const gimmvfi_view* v, const gimmvfi_view* out, int heads, int ws,
+                                void* stream);
+int gimmvfi_op_global_attention(const gimmvfi_view* q, const gimmvfi_view* k, const gimmvfi_view* v, const gimmvfi_view* out, int heads, void* stream);
+int gimmvfi_op_patchify(const gimmvfi_view* src, const gimmvfi_view* dst, int k, void* stream);
+int gimmvfi_op_cost_conv1(const float* vol, int64_t maps, int h, int w, const float* w_host, const float* b_host, const gimmvfi_view* out_padded,
+                          void* stream);
+int gimmvfi_op_conv7x7_small_cout(const gimmvfi_view* in, const float* w_tap_cin_4, const float* bias, int cout, const gimmvfi_view* out, void* stream);
 int gimmvfi_op_corr_volume(const gimmvfi_view* fa, const gimmvfi_view* fb, float* vol, void* stream);
 /* the same volume for ONE sample (n == 1, dense views, C % 32 == 0) as a tcgen05 GEMM: split != 0 -> 3xTF32 (RAFT's volume),
  * else TF32 (the bidirectional volume).  scratch >= 2*h*w*C + h*w + 1024 floats */

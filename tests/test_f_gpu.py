@@ -1,6 +1,8 @@
-"""GIMM-VFI-F (gimmvfi_f.py): the boundary class and the natively-run half — everything downstream of the flow estimator — against
-fixtures produced by the UNMODIFIED reference GIMMVFI_F (oracle/make_golden_f.py).  The fixtures carry the reference FlowFormer's
-outputs (flows, context features, fnet maps); `forward_from_flow` consumes them exactly where the reference's forward does."""
+"""GIMM-VFI-F (gimmvfi_f.py) against fixtures produced by the UNMODIFIED reference GIMMVFI_F:
+  * ff_* (oracle/make_golden_ff.py): the whole model natively — FlowFormer estimator (csrc/flowformer.cu) + synthesis half — on seeded
+    weights the tests rebuild (gimmvfi_b200.weights.random_state_dict_f);
+  * f_* (oracle/make_golden_f.py): the synthesis half alone, fed with the reference FlowFormer's outputs carried in the fixture
+    (`forward_from_flow` consumes them exactly where the reference's forward does)."""
 import json
 import os
 
@@ -57,8 +59,48 @@ def test_f_synthesis_matches_reference(name, mode, model):
         assert nin <= (5e-4 if mode else 5e-6), nin   # HypoNet itself is fp32-class; its latent input comes from TF32 convolutions in mode 3
 
 
+with open(os.path.join(GOLDEN_DIR, "manifest_ff.json")) as _f:
+    MANIFEST_FF = json.load(_f)
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST_FF))
+@pytest.mark.parametrize("mode", [4, 0], ids=["default", "fp32"])
+def test_f_native_flowformer_matches_reference(name, mode, model):
+    """forward() with no flow backend: the native FlowFormer (both directions batched) + synthesis.  Bars: the estimator's flows within
+    2e-3 px of the reference's (|flow| up to 25 px; fp32 mode 2e-4), its feature maps within 1e-4, the interpolated frame within the
+    1e-3 of BASELINE.json (fp32 mode: 5e-5)."""
+    meta = MANIFEST_FF[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    B, H, W, ts, ds = meta["B"], meta["H"], meta["W"], meta["timesteps"], meta["ds_factor"]
+    xs = synth_batch(B, H, W, seed=meta["input_seed"]).to(DEV)
+    ratio = 1.0 if ds is None else ds
+    coord = [(model.sample_coord_input(B, (H, W), [t], device=DEV, upsample_ratio=ratio), None) for t in ts]
+    tt = [t * torch.ones(B, device=DEV) for t in ts]
+    model.tensor_cores = mode
+    model.flow_backend = None
+    model.engine.set_debug(True)
+    try:
+        out = model(xs, coord, t=tt, ds_factor=ds)
+        torch.cuda.synchronize()
+        f8 = model.engine.tap("ff.feat8").cpu()
+        fp = model.engine.tap("ff.fproj").cpu()
+    finally:
+        model.engine.set_debug(False)
+    d_flow = (out["raft_flow"].cpu() - torch.from_numpy(g["flows"])).abs().max().item()
+    ref8 = torch.cat([torch.from_numpy(g["feat8_0"]), torch.from_numpy(g["feat8_1"])], 0).permute(0, 2, 3, 1)
+    refp = torch.cat([torch.from_numpy(g["fnet_0"]), torch.from_numpy(g["fnet_1"])], 0).permute(0, 2, 3, 1)
+    d8, dp = (f8 - ref8).abs().max().item(), (fp - refp).abs().max().item()
+    print(name, "mode", mode, "flows max %.3e px, feat8 %.3e, fnet %.3e, launches %d" % (d_flow, d8, dp, model.engine.last_launches))
+    assert d8 <= (1e-4 if mode else 2e-5) and dp <= (1e-4 if mode else 2e-5)
+    assert d_flow <= (2e-3 if mode else 2e-4)
+    for i in range(len(ts)):
+        d = (out["imgt_pred"][i].cpu() - torch.from_numpy(g["imgt_pred_%d" % i])).abs()
+        print("   imgt_pred[%d] max %.3e rmse %.3e" % (i, d.max().item(), d.pow(2).mean().sqrt().item()))
+        assert d.max().item() <= (1e-3 if mode else 5e-5)
+
+
 def test_f_boundary(model):
-    """639-key state_dict (strict), honest failure without a flow backend, and the backend hook with the reference's signature."""
+    """639-key state_dict (strict) and the optional backend hook with the reference's FlowFormer.forward signature."""
     sd = model.state_dict()
     with open(os.path.join(GOLDEN_DIR, "state_dict_spec_f.json")) as f:
         spec = json.load(f)
@@ -68,9 +110,6 @@ def test_f_boundary(model):
     xs = synth_batch(1, meta["H"], meta["W"], seed=meta["input_seed"]).to(DEV)
     coord = [(model.sample_coord_input(1, (meta["H"], meta["W"]), [0.5], device=DEV), None)]
     tt = [0.5 * torch.ones(1, device=DEV)]
-    model.flow_backend = None
-    with pytest.raises(NotImplementedError):
-        model(xs, coord, t=tt)
     fi = flow_inputs_of(g, DEV)
     calls = []
 
@@ -85,3 +124,6 @@ def test_f_boundary(model):
     model.flow_backend = None
     assert len(calls) == 2 and calls[0][0] > 1.5   # the backend sees 0..255 frames (gimmvfi_f.py:320-328)
     assert (out["imgt_pred"][0].cpu() - torch.from_numpy(g["imgt_pred_0"])).abs().max().item() <= 1e-3
+    with pytest.raises(RuntimeError):               # the Twins sub-sampling needs a multiple of 32 at the network resolution
+        c2 = [(model.sample_coord_input(1, (136, 160), [0.5], device=DEV), None)]
+        model(synth_batch(1, 136, 160, seed=1).to(DEV), c2, t=tt)

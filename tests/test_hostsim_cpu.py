@@ -167,3 +167,34 @@ def test_hostsim_f_synthesis_from_flow_matches_reference():
     assert d <= 2e-5
     with pytest.raises(GimmvfiError):   # no flow estimator weights in this engine
         e.forward(xs, coords, tt, None)
+
+
+@pytest.mark.parametrize("name,mode", [("ff_b2_128x128_t0.5", 0)])   # (the tensor-core modes: tests/test_f_gpu.py on the B200)
+def test_hostsim_f_native_flowformer_matches_reference(name, mode):
+    """GIMM-VFI-F end to end on the CPU build of the kernels: the NATIVE FlowFormer estimator (flowformer.cu: Twins x2, cost-perceiver
+    memory encoder, 32-iteration GMA decoder; both directions batched) + the synthesis half, against the UNMODIFIED reference GIMMVFI_F
+    on the same seeded weights (oracle/make_golden_ff.py).  B = 2 covers the reference's context.repeat batch order."""
+    import json, os, sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import harness
+    from conftest import GOLDEN_DIR
+    from gimmvfi_b200.weights import random_state_dict_f
+
+    torch.set_grad_enabled(False)
+    meta = json.load(open(os.path.join(GOLDEN_DIR, "manifest_ff.json")))[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    e = harness.hostsim_engine()
+    e.load_state_dict(random_state_dict_f(0), full_f=True)
+    e.set_tensor_cores(mode)
+    B, H, W = meta["B"], meta["H"], meta["W"]
+    xs = synth_batch(B, H, W, seed=meta["input_seed"])
+    coords = torch.stack([O.sample_coord_input(B, (H, W), [t], 1.0) for t in meta["timesteps"]], 0).contiguous()
+    tt = torch.stack([t * torch.ones(B) for t in meta["timesteps"]], 0).contiguous()
+    out = e.forward(xs, coords, tt, None)
+    T = lambda k: torch.from_numpy(g[k])
+    d_flow = (out["raft_flow"] - T("flows")).abs().max().item()
+    d_img = (out["imgt_pred"][0] - T("imgt_pred_0")).abs().max().item()
+    print("hostsim native F %s mode %d: flows max %.3e px (|flow| <= %.1f), imgt_pred max %.3e" % (name, mode, d_flow, meta["flow_absmax"], d_img))
+    assert d_flow <= 5e-4
+    assert d_img <= (2e-4 if mode else 5e-5)

@@ -136,3 +136,27 @@ def test_oracle_matches_reference_on_demo_frames(weights0):
     s = int(g["stride"])
     assert np.abs(out["imgt_pred"][0][..., ::s, ::s].numpy() - g["imgt_pred_0"]).max() <= TOL
     assert np.abs(out["raft_flow"][..., ::s, ::s].numpy() - g["raft_flow"]).max() <= 50 * TOL
+
+
+@pytest.mark.parametrize("name", ["ff_128x160_t0.5", "ff_b2_128x128_t0.5"])
+def test_flowformer_oracle_matches_reference(name):
+    """oracle/flowformer_oracle.py (the restatement of GIMM-VFI-F's FlowFormer estimator) against the outputs of the UNMODIFIED reference
+    FlowFormer on the same seeded weights and inputs (oracle/make_golden_ff.py): flows, context features, fnet maps, both directions."""
+    import json
+
+    import flowformer_oracle as FO
+    from gimmvfi_b200.weights import random_state_dict_f
+
+    torch.set_grad_enabled(False)
+    meta = json.load(open(os.path.join(GOLDEN_DIR, "manifest_ff.json")))[name]
+    assert meta["oracle_vs_reference"]["flow"] <= 1e-4
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    sd = random_state_dict_f(0)
+    xs = synth_batch(meta["B"], meta["H"], meta["W"], seed=meta["input_seed"])
+    im = [255 * xs[:, :, 0], 255 * xs[:, :, 1]]
+    for d in range(2):
+        (fu, fl), cf, ff = FO.flowformer_forward(sd, im[d], im[1 - d])
+        assert np.abs(fu.numpy() - g["flows"][:, :, d]).max() <= 2e-4        # px; |flow| up to ~25
+        assert np.abs(fl.numpy() - g["flow_low_%s" % ("01" if d == 0 else "10")]).max() <= 5e-5
+        assert np.abs(cf[0].numpy() - g["feat4_%d" % d]).max() <= 2e-5 and np.abs(cf[1].numpy() - g["feat8_%d" % d]).max() <= 2e-5
+        assert np.abs(ff.numpy() - g["fnet_%d" % d]).max() <= 2e-5
