@@ -322,40 +322,68 @@ static bool conv_thin_ok(const ConvArgs& a) {
 
 #ifndef GV_HOSTSIM
 // 7x7 convolutions with <= 4 output channels on few input channels at FULL resolution (amt_comb_block.2: 18 -> 3, gimmvfi_r.py:60-64):
-// as an MMA tile this layer pays one K step per (tap row, 32 lanes) for N = 3 useful columns (1.2 ms at 1088x1920 / 1088x2048, bound by
-// the per-K-step hand-off of conv_tc.cu).  Here a CTA stages a 32 x 8 output tile's 38 x 14 halo and all weights in shared memory once;
-// a thread owns one pixel: one conflict-free LDS per input value (odd channel stride), one broadcast LDS.128 per 4 weights.  Exact fp32.
+// as an MMA tile this layer pays one K step per (tap row, 32 lanes) for N = 3 useful columns (1.2 ms at 1088x1920, bound by the
+// per-K-step hand-off of conv_tc.cu).  Here a CTA owns a 128 x 8 output tile; the input halo streams through shared memory 6 channels at
+// a time, channel-major ([ci][y][x], plane pitch = 20 mod 32 banks so the staging writes of 6 channels do not collide); a thread owns 4
+// x-consecutive pixels: per (channel, tap row) THREE 16-byte loads fetch the 10 inputs its 4 windows share and SEVEN broadcast 16-byte
+// loads the weights, for 84-112 FMAs - FMA-bound instead of shared-memory-bound (the first version, one pixel per thread with one scalar
+// load per FMA triple, ran at 7.5 TFMA/s).  Exact fp32.
+constexpr int C7_TW = 128, C7_TH = 8, C7_CCH = 6, C7_RP = 136, C7_PP = 14 * C7_RP + 4;
+template <int CO>
 __global__ void __launch_bounds__(256) conv7x7_small_cout_kernel(TV in, const float* __restrict__ w, const float* __restrict__ bias, TV out,
-                                                                 int cin, int cs, int cout, int act, const float* slope) {
+                                                                 int cin, int cout, int act, const float* slope) {
   extern __shared__ __align__(16) float sm_c7[];
   float* wsm = sm_c7;                       // [49][cin][4]
-  float* tile = sm_c7 + 49 * cin * 4;       // [14][38][cs]
-  const int tid = threadIdx.y * 32 + threadIdx.x, n = blockIdx.z;
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-  for (int i = tid; i < 49 * cin * 4; i += 256) wsm[i] = w[i];
-  for (int i = tid; i < 14 * 38 * cin; i += 256) {
-    const int ci = i % cin; int r = i / cin; const int px = r % 38, py = r / 38;
-    const int gy = y0 + py - 3, gx = x0 + px - 3;
-    tile[(py * 38 + px) * cs + ci] = (gy >= 0 && gy < in.h && gx >= 0 && gx < in.w) ? in.p[in.off(n, gy, gx) + ci] : 0.f;
-  }
-  __syncthreads();
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int ky = 0; ky < 7; ++ky)
+  float* tile = sm_c7 + 49 * cin * 4;       // [C7_CCH][14][C7_RP] (+ plane padding)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, n = blockIdx.z;
+  const int x0 = blockIdx.x * C7_TW, y0 = blockIdx.y * C7_TH;
+  for (int i = threadIdx.x; i < 49 * cin * 4; i += 256) wsm[i] = w[i];
+  float acc[4][CO];
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx) {
-      const float* t = tile + ((threadIdx.y + ky) * 38 + threadIdx.x + kx) * cs;
-      const float4* wp = reinterpret_cast<const float4*>(wsm) + (ky * 7 + kx) * cin;
-#pragma unroll 6
-      for (int ci = 0; ci < cin; ++ci) {
-        const float v = t[ci]; const float4 ww = wp[ci];
-        a0 = fmaf(v, ww.x, a0); a1 = fmaf(v, ww.y, a1); a2 = fmaf(v, ww.z, a2); a3 = fmaf(v, ww.w, a3);
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[p][c] = 0.f;
+  for (int c0 = 0; c0 < cin; c0 += C7_CCH) {
+    const int cc = (cin - c0) < C7_CCH ? (cin - c0) : C7_CCH;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cc * 14 * (C7_TW + 6); i += 256) {
+      const int ci = i % cc; int r = i / cc; const int px = r % (C7_TW + 6), py = r / (C7_TW + 6);
+      const int gy = y0 + py - 3, gx = x0 + px - 3;
+      tile[ci * C7_PP + py * C7_RP + px] = (gy >= 0 && gy < in.h && gx >= 0 && gx < in.w) ? in.p[in.off(n, gy, gx) + c0 + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int ci = 0; ci < cc; ++ci) {
+      const float* tp = tile + ci * C7_PP + ty * C7_RP + tx * 4;
+      const float4* wp = reinterpret_cast<const float4*>(wsm) + (c0 + ci);
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) {
+        const float4 a0 = *reinterpret_cast<const float4*>(tp + ky * C7_RP), a1 = *reinterpret_cast<const float4*>(tp + ky * C7_RP + 4),
+                     a2 = *reinterpret_cast<const float4*>(tp + ky * C7_RP + 8);
+        const float a[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const float4 ww = wp[(ky * 7 + kx) * cin];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            acc[p][0] = fmaf(a[p + kx], ww.x, acc[p][0]); acc[p][1] = fmaf(a[p + kx], ww.y, acc[p][1]); acc[p][2] = fmaf(a[p + kx], ww.z, acc[p][2]);
+            if (CO == 4) acc[p][CO - 1] = fmaf(a[p + kx], ww.w, acc[p][CO - 1]);
+          }
+        }
       }
     }
-  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  if (x < out.w && y < out.h) {
-    float* o = out.p + out.off(n, y, x);
-    const float r[4] = {a0, a1, a2, a3};
-    for (int c = 0; c < cout; ++c) o[c] = apply_act(r[c] + bias[c], act, slope, c);
+  }
+  const int y = y0 + ty;
+  if (y < out.h) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int x = x0 + tx * 4 + p;
+      if (x < out.w) {
+        float* o = out.p + out.off(n, y, x);
+#pragma unroll
+        for (int c = 0; c < CO; ++c)
+          if (c < cout) o[c] = apply_act(acc[p][c] + bias[c], act, slope, c);
+      }
+    }
   }
 }
 #endif
@@ -369,18 +397,19 @@ bool conv7x7_small_cout(Ctx& cx, const TV& in, const ConvW& w, int act, const fl
       in.w != out.w || act == ACT_SIGMOID || act == ACT_TANH || act == ACT_SIN || act == ACT_GELU)
     return false;
   if (cx.dry) return true;
-  const int cs = w.cin | 1;   // odd channel stride: x-neighbouring threads hit different banks
-  const int smem = (49 * w.cin * 4 + 14 * 38 * cs) * (int)sizeof(float);
-  static volatile unsigned char attr[64];
-  gv_set_max_smem(conv7x7_small_cout_kernel, smem, attr);
+  const int smem = (49 * w.cin * 4 + C7_CCH * C7_PP) * (int)sizeof(float);
+  static volatile unsigned char attr3[64], attr4[64];
+  gv_set_max_smem(conv7x7_small_cout_kernel<3>, smem, attr3);
+  gv_set_max_smem(conv7x7_small_cout_kernel<4>, smem, attr4);
   cx.launches++;
   if (cx.prof) {
     char nm[128];
     snprintf(nm, sizeof nm, "conv7x7_small_cout c%d>%d @%dx%dx%d", w.cin, w.cout, out.n, out.h, out.w);
     cx.prof->begin(cx.stream, prof_intern(nm), 2.0 * (double)out.pixels() * w.cout * (double)w.cin * 49);
   }
-  dim3 grid((out.w + 31) / 32, (out.h + 7) / 8, out.n), block(32, 8);
-  conv7x7_small_cout_kernel<<<grid, block, smem, cx.stream>>>(in, w.w, w.b, out, w.cin, cs, w.cout, act, slope);
+  dim3 grid((out.w + C7_TW - 1) / C7_TW, (out.h + C7_TH - 1) / C7_TH, out.n);
+  if (w.cout == 4) conv7x7_small_cout_kernel<4><<<grid, 256, smem, cx.stream>>>(in, w.w, w.b, out, w.cin, w.cout, act, slope);
+  else conv7x7_small_cout_kernel<3><<<grid, 256, smem, cx.stream>>>(in, w.w, w.b, out, w.cin, w.cout, act, slope);
   gv_check_launch("conv7x7_small_cout");
   if (cx.prof) cx.prof->end(cx.stream);
   return true;

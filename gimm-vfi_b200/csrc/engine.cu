@@ -113,6 +113,8 @@ Engine::Engine(int device) : device_(device) {
   if (const char* kn = getenv("GIMMVFI_PRECISE")) precise_ = atoi(kn);   // builder experiments: override the 3xTF32 stage mask
   if (const char* kn = getenv("GIMMVFI_HYPO_FAST")) hypo_fast_ = atoi(kn) != 0;
   if (const char* kn = getenv("GIMMVFI_CORR_DIRECT")) corr_direct_max_t_ = atoi(kn);
+  if (const char* kn = getenv("GIMMVFI_RAFT_CORR_DIRECT")) raft_direct_ = atoi(kn);            // 1: always volume-free, 0: never, unset: by size
+  if (const char* kn = getenv("GIMMVFI_RAFT_CORR_DIRECT_GB")) raft_direct_auto_bytes_ = atof(kn) * 1e9;
   if (const char* kn = getenv("GIMMVFI_GRU_HOIST")) gru_hoist_ = atoi(kn) != 0;
 #ifndef GV_HOSTSIM
   int count = 0;
@@ -868,7 +870,31 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
     }
     tap("raft.fmap", fmap);
 
-    Pyramid pyr = build_pyramid(cx, fmap, B, tc_mode_ >= 2 ? 2 : 0);   // RAFT's volume: fp32-class only
+    // RAFT's correlation: the all-pairs volume pyramid (fp32-class GEMMs; 8.3 ms of GEMM + 20 lookups at 1080p) - or, when that
+    // pyramid would not fit the memory budget (a 4K pair without ds_factor: 2 x 78 GB at level 0 alone), NO volume: every lookup
+    // computes the 4 x 100 dot products its window needs from the other frame's (pooled, half-precision) features, like
+    // BidirCorrBlock's (the B200 successor of alt_cuda_corr).  ~5x the time of the volume path, 0 bytes instead of N^2.
+    const double pyr_bytes = 2.0 * B * (double)h * w * (double)h * w * 4.0 * (4.0 / 3.0);
+    const bool raft_direct = (raft_direct_ == 1 || (raft_direct_ < 0 && pyr_bytes > raft_direct_auto_bytes_)) && fmap.c == 256 && h >= 16 && w >= 16;
+    Pyramid pyr{}; CorrFeat rfeat{};
+    if (raft_direct) {
+      TV Fl = fmap;
+      rfeat.c = 256; rfeat.scale = 1.0f / std::sqrt((float)fmap.c);
+      for (int l = 0; l < 4; ++l) {
+        rfeat.h[l] = Fl.h; rfeat.w[l] = Fl.w;
+        void* hp = A.alloc_f(((size_t)Fl.pixels() * Fl.c + 1) / 2);
+        features_to_half(cx, Fl, hp);
+        rfeat.lvl[l] = static_cast<const uint16_t*>(hp);
+        if (l < 3) { TV nx = A.tensor(2 * B, Fl.h / 2, Fl.w / 2, Fl.c); avgpool2_features(cx, Fl, nx); Fl = nx; }
+      }
+    } else {
+      pyr = build_pyramid(cx, fmap, B, tc_mode_ >= 2 ? 2 : 0);   // fp32-class only
+    }
+    auto rfeat_of = [&](int sample0) {
+      CorrFeat f = rfeat;
+      for (int l = 0; l < 4; ++l) f.lvl[l] = rfeat.lvl[l] + (int64_t)sample0 * f.h[l] * f.w[l] * f.c;
+      return f;
+    };
     const std::string u = "flow_estimator.update_block";
     TV coords1 = A.tensor(2 * B, h, w, 2);
     TV flow = A.tensor(2 * B, h, w, 2, 4);   // ld 4: 16-byte pixel stride so the 7x7 2->128 conv can use TMA
@@ -888,7 +914,12 @@ void Engine::run(Ctx& cx, const Problem& P, const IO& io, const FlowInputs* fin)
         N.conv(u + ".gru.convq" + sfx + "_inp", hx.slice(128, 128), Pq[s]);
       }
     for (int it = 0; it < raft_iters; ++it) {
-      corr_lookup(cx, pyr.view(0), coords1, corr);
+      if (raft_direct) {   // direction 0's sources against frame 1's features and vice versa
+        corr_lookup_direct(cx, fmap.batch(0, B), rfeat_of(B), coords1.batch(0, B), corr.batch(0, B));
+        corr_lookup_direct(cx, fmap.batch(B, B), rfeat_of(0), coords1.batch(B, B), corr.batch(B, B));
+      } else {
+        corr_lookup(cx, pyr.view(0), coords1, corr);
+      }
       coords_minus_grid(cx, coords1, flow, hx.slice(382, 2));
       if (it == 0) tap("raft.corr_it0", corr);
       // BasicMotionEncoder raft/update.py:94-112
@@ -1382,7 +1413,7 @@ void Engine::forward(const Problem& p, const IO& io, void* workspace, size_t wor
   if (use_graph_ && !profile_ && !debug_ && fc_ == nullptr && reinterpret_cast<uintptr_t>(stream) > 2) {
     // everything a recorded launch sequence depends on: problem, every caller pointer, the workspace, the arithmetic mode, the weights
     std::vector<uint64_t> key = {(uint64_t)p.B, (uint64_t)p.Hf, (uint64_t)p.Wf, (uint64_t)p.T, (uint64_t)p.Hc, (uint64_t)p.Wc, 0, (uint64_t)tc_mode_, (uint64_t)precise_,
-                                 (uint64_t)hypo_fast_, (uint64_t)corr_direct_max_t_, (uint64_t)gru_hoist_, (uint64_t)weights_version_, (uint64_t)raft_iters, (uint64_t)workspace, (uint64_t)workspace_bytes, (uint64_t)(uintptr_t)stream};
+                                 (uint64_t)hypo_fast_, (uint64_t)(raft_direct_ + 2), (uint64_t)corr_direct_max_t_, (uint64_t)gru_hoist_, (uint64_t)weights_version_, (uint64_t)raft_iters, (uint64_t)workspace, (uint64_t)workspace_bytes, (uint64_t)(uintptr_t)stream};
     std::memcpy(&key[6], &p.ds, sizeof(float));
     const void* ptrs[] = {io.img_xs, io.coords, io.t, io.imgt_pred, io.img_warp_4, io.flowt0_1, io.flowt1_1, io.flowt0_4, io.flowt1_4, io.raft_flow, io.nflow, io.ninrflow, io.flowt};
     for (const void* q : ptrs) key.push_back((uint64_t)(uintptr_t)q);

@@ -167,6 +167,8 @@ class Engine {
   const void* hypo_blob3_ = nullptr;  // ... of its fp32-class variant (common.h hypo3::), the default
   bool hypo_fast_ = false;            // true: TF32 / half-operand HypoNet kernel (0.56 ms vs the fp32-class one; fails the 1e-3 bound on real frames)
   bool gru_hoist_ = true;             // SepConvGRU: the context input's share of the gate convolutions is computed once per pair (GIMMVFI_GRU_HOIST=0: every iteration)
+  int raft_direct_ = -1;              // RAFT's own lookups without a volume: -1 = when the volume pyramid exceeds raft_direct_auto_bytes_ (GIMMVFI_RAFT_CORR_DIRECT)
+  double raft_direct_auto_bytes_ = 64e9;
   int corr_direct_max_t_ = 2;         // BidirCorrBlock: volume-free lookup when a pair is interpolated at <= this many timesteps (GIMMVFI_CORR_DIRECT; 0: always the volume)
   const float* g9_ = nullptr; const float* alpha_fe_ = nullptr; const float* alpha_v_ = nullptr;
 

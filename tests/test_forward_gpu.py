@@ -232,3 +232,20 @@ def test_cuda_graph_replay_matches_eager(weights0):
     assert torch.equal(out2["raft_flow"], want)
     eng.set_cuda_graph(False)
     eng.static_outputs = False
+
+
+@pytest.mark.parametrize("name", ["r_b2_128x192_t0.25_0.75", "r_256x448_t0.5"])
+def test_forward_volume_free_raft_matches_reference_golden(name, golden_manifest, weights0, monkeypatch):
+    """RAFT's 20 lookups per pair computed on the fly from the other frame's features (no N^2 volume; selected by
+    size when the volume pyramid would not fit, forced here) - same fixtures, same bars as the volume path."""
+    monkeypatch.setenv("GIMMVFI_RAFT_CORR_DIRECT", "1")       # read when the engine is created
+    m = GIMMVFI_R(seed=0).to(DEV).eval()
+    m.load_state_dict(weights0, strict=True)
+    meta = golden_manifest[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    s = int(g["stride"])
+    _, out = run_model(m, meta)
+    rf = (out["raft_flow"].cpu()[..., :: 2 * s, :: 2 * s] - torch.from_numpy(g["raft_flow"])).abs().max().item()
+    worst = max((out["imgt_pred"][i].cpu()[..., ::s, ::s] - torch.from_numpy(g["imgt_pred_%d" % i])).abs().max().item() for i in range(len(meta["timesteps"])))
+    print(name, "volume-free RAFT: raft_flow max %.3e px, imgt_pred max %.3e" % (rf, worst))
+    assert rf <= 1e-2 and worst <= TOL_IMG

@@ -169,6 +169,27 @@ def test_hostsim_f_synthesis_from_flow_matches_reference():
         e.forward(xs, coords, tt, None)
 
 
+def test_hostsim_volume_free_raft_lookup(weights0, monkeypatch):
+    """RAFT's own lookups without the all-pairs volume (GIMMVFI_RAFT_CORR_DIRECT=1; chosen by size when the pyramid
+    would not fit) against the oracle: the other frame's features enter as halves, so the flow moves by ~2e-4 px, the frame by < 1e-5."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import harness
+
+    torch.set_grad_enabled(False)
+    monkeypatch.setenv("GIMMVFI_RAFT_CORR_DIRECT", "1")
+    e = harness.hostsim_engine()
+    e.load_state_dict(weights0)
+    B, H, W = 1, 128, 160
+    xs = synth_batch(B, H, W, seed=3)
+    coords = torch.stack([O.sample_coord_input(B, (H, W), [0.5], 1.0)], 0).contiguous()
+    tt = 0.5 * torch.ones(1, B)
+    out = e.forward(xs, coords, tt, None)
+    ref = O.gimmvfi_r_forward(weights0, xs, [(coords[0], None)], [tt[0]])
+    assert (out["raft_flow"] - ref["raft_flow"]).abs().max() <= 2e-3
+    assert (out["imgt_pred"][0] - ref["imgt_pred"][0]).abs().max() <= 1e-4
+
+
 @pytest.mark.parametrize("name,mode", [("ff_b2_128x128_t0.5", 0)])   # (the tensor-core modes: tests/test_f_gpu.py on the B200)
 def test_hostsim_f_native_flowformer_matches_reference(name, mode):
     """GIMM-VFI-F end to end on the CPU build of the kernels: the NATIVE FlowFormer estimator (flowformer.cu: Twins x2, cost-perceiver
