@@ -93,8 +93,9 @@ def cpu_threads():
 
 def workload_config(H, W, T, B=1, precision=None, world=1):
     """`config` of the JSON line — IDENTICAL in both arms (the driver compares them: same workload, same metric)."""
-    return {"workload": "%d x 1920x1080 pair per GPU (padded %dx%d), %s, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
-                        % (B, H, W, "t=0.5, T=1" if T == 1 else "T=%d frames per pair at t=i/%d" % (T, T + 1)),
+    frame = "1920x1080 pair per GPU (padded %dx%d)" % (H, W) if (H, W) == (H_PAD, W_PAD) else "%dx%d pair per GPU (--height/--width)" % (H, W)
+    return {"workload": "%d x %s, %s, GIMM-VFI-R (RAFT 20 iters), random-init weights, all reference outputs produced"
+                        % (B, frame, "t=0.5, T=1" if T == 1 else "T=%d frames per pair at t=i/%d" % (T, T + 1)),
             "height": H, "width": W, "timesteps": T, "pairs_per_step_per_gpu": B}
 
 
