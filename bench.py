@@ -263,10 +263,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="pair1080", choices=["pair1080", "batch720"],
+    ap.add_argument("--config", default="pair1080", choices=["pair1080", "batch720", "f2k", "f4k"],
                     help="pair1080 (default, BASELINE configs[1], the headline metric): one 1920x1080 pair per GPU per step, weak scaling.  "
                          "batch720 (BASELINE configs[4]): 256 1280x720 pairs (padded 736x1280) sharded across the ranks, a step = the whole "
-                         "batch in micro-batches of --micro-batch pairs per forward, ONE all-gather of the output frames, strong scaling")
+                         "batch in micro-batches of --micro-batch pairs per forward, ONE all-gather of the output frames, strong scaling.  "
+                         "f2k / f4k (BASELINE configs[2] / [3]): GIMM-VFI-F (native FlowFormer estimator) on one 2K pair at ds_factor 0.5 / one 4K "
+                         "pair at ds_factor 0.25 per GPU, N = 8 -> 7 interpolated frames per pair")
     ap.add_argument("--pairs", type=int, default=256)
     ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--height", type=int, default=0)
@@ -279,6 +281,22 @@ def main():
                     help="T interpolated frames per pair at t = i/(T+1): 1 = the headline metric (t=0.5); 7 = the reference's N=8 video setting")
     args = ap.parse_args()
     batch_mode = args.config == "batch720"
+    f_mode = args.config in ("f2k", "f4k")
+    ds = None
+    if f_mode:   # src/video_Nx.py: 2K -> ds 0.5, 4K -> ds 0.25 (README of the reference), InputPadder(32): 2048x1080 -> 1088x2048, 4096x2160 -> 2176x4096
+        ds = 0.5 if args.config == "f2k" else 0.25
+        if not args.height:
+            args.height, args.width = (1088, 2048) if args.config == "f2k" else (2176, 4096)
+        if args.timesteps == 1:
+            args.timesteps = 7
+        args.no_cpu_baseline = args.no_torch_baseline = True   # (the CPU / stock-PyTorch legs are GIMM-VFI-R's; FlowFormer on host cores takes minutes per pair)
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "GIMM-VFI-F's reference needs timm 0.4.12 + pretrained FlowFormer weights (absent offline); "
+                                  "its CPU path at this size runs for minutes per pair - the timed reference arm is the GIMM-VFI-R headline config"}))
+            return
+    fkw = {"ds_factor": ds} if f_mode else {}
+    ckw = {"upsample_ratio": ds} if f_mode else {}
     if not args.height:
         args.height, args.width = (736, 1280) if batch_mode else (H_PAD, W_PAD)
     args.warmup = max(args.warmup, 3 if not batch_mode else 1) if args.impl == "ours" else args.warmup
@@ -301,7 +319,14 @@ def main():
 
     H, W, T = args.height, args.width, max(1, args.timesteps)
     tvals = [0.5] if T == 1 else [i / (T + 1) for i in range(1, T + 1)]
-    model = GIMMVFI_R(seed=0).to(dev).eval()
+    if f_mode:
+        from gimmvfi_b200 import GIMMVFI_F
+        from gimmvfi_b200.weights import random_state_dict_f
+
+        model = GIMMVFI_F(seed=0).to(dev).eval()
+        model.load_state_dict(random_state_dict_f(0), strict=True)
+    else:
+        model = GIMMVFI_R(seed=0).to(dev).eval()
     model.tensor_cores = PRECISIONS[args.precision]
     if batch_mode:
         mine = shard_range(args.pairs, rank, world)
@@ -315,7 +340,7 @@ def main():
         B, nmb, MB = 1, 1, 1
         xs_host = synth_batch(1, H, W, seed=100 + rank).pin_memory()
     xs = xs_host.to(dev, non_blocking=True)
-    coord = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
+    coord = [(model.sample_coord_input(B, (H, W), [tv], device=dev, **ckw), None) for tv in tvals]
     tt = [tv * torch.ones(B, device=dev) for tv in tvals]
     frames_per_step_rank = (len(mine) if batch_mode else B) * T
     if batch_mode:
@@ -332,7 +357,7 @@ def main():
     def step(x=None):
         """one step on device-resident inputs: pair1080 = one forward; batch720 = this rank's shard in micro-batches + ONE all-gather"""
         if not batch_mode:
-            img = frames_of(model(xs if x is None else x, coord, t=tt), B)
+            img = frames_of(model(xs if x is None else x, coord, t=tt, **fkw), B)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, img.contiguous())   # the single output collective
             return img
@@ -406,8 +431,8 @@ def main():
             main_stream.wait_event(ev_in[i % 2])
             if i + 1 < n:
                 h2d(i + 1)
-            c = [(model.sample_coord_input(B, (H, W), [tv], device=dev), None) for tv in tvals]
-            o = model(x_dev[i % 2], c, t=[tv * torch.ones(B, device=dev) for tv in tvals])
+            c = [(model.sample_coord_input(B, (H, W), [tv], device=dev, **ckw), None) for tv in tvals]
+            o = model(x_dev[i % 2], c, t=[tv * torch.ones(B, device=dev) for tv in tvals], **fkw)
             img = frames_of(o, B)
             if world > 1 and not batch_mode:
                 dist.all_gather_into_tensor(gathered, img.contiguous())
@@ -430,7 +455,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     # ---- per-kernel breakdown (CUDA events around every launch of one extra forward)
     model.engine.set_profile(True)
-    model(xs, coord, t=tt)
+    model(xs, coord, t=tt, **fkw)
     prof = model.engine.profile()
     model.engine.set_profile(False)
     model.aux_outputs = aux
@@ -457,17 +482,30 @@ def main():
         fl = flops_per_frame(H * W, T)
         n_pairs_total = args.pairs if batch_mode else world * B
         cfg = workload_config(H, W, T, B)
+        if f_mode:
+            cfg["workload"] = ("%d x %s pair per GPU (padded %dx%d), ds_factor %s, T=%d frames per pair at t=i/%d, GIMM-VFI-F (native FlowFormer estimator, 32 "
+                               "decoder iterations, both directions), seeded random weights, all reference outputs produced"
+                               % (B, "2K (2048x1080)" if args.config == "f2k" else "4K (4096x2160)", H, W, ds, T, T + 1))
+            cfg["ds_factor"] = ds
         if batch_mode:
             cfg["workload"] = ("%d x 1280x720 pairs (padded %dx%d), t=0.5, GIMM-VFI-R (RAFT 20 iters), random-init weights, sharded over %d GPU(s), "
                                "micro-batch %d pairs per forward, frames only" % (args.pairs, H, W, world, MB))
             cfg["pairs"] = args.pairs
             cfg["micro_batch"] = MB
-        cfg.update({"precision": PRECISION_NOTES[args.precision],
+        if f_mode:
+            fl = None
+        cfg.update({"precision": PRECISION_NOTES[args.precision] if not f_mode else
+                    "FlowFormer estimator (Twins-SVT x2, cost-perceiver memory encoder, GMA decoder) and HypoNet: tcgen05 3xF16 (fp32-class) convolutions / GEMMs, fp32 "
+                    "CUDA-core attention, softmax and LayerNorm; synthesis half as GIMM-VFI-R's default mode.  Parity: tests/test_f_gpu.py (reference-generated "
+                    "ff_* fixtures: flows <= 2e-3 px, max|d imgt_pred| <= 1e-3)",
                     "parallelism": ("pairs sharded rank::world, ONE all-gather of the output frames per step" if world > 1 else "single GPU"),
                     "l2": "256 MiB L2 flush between timed steps; per-step working set ~30 GB >> L2",
-                    "algorithmic_tflop_per_frame": fl / T / 1e12, "achieved_tflops_end_to_end": n_pairs_total * fl / (ms * 1e-3) / 1e12})
+                    "algorithmic_tflop_per_frame": fl / T / 1e12 if fl else None,
+                    "achieved_tflops_end_to_end": n_pairs_total * fl / (ms * 1e-3) / 1e12 if fl else None})
         line = {
-            "metric": METRIC if not batch_mode else "interpolated frames/sec, batch of 256 1280x720 pairs, t=0.5", "value": total_frames / (ms * 1e-3), "unit": UNIT,
+            "metric": (METRIC if not batch_mode else "interpolated frames/sec, batch of 256 1280x720 pairs, t=0.5") if not f_mode else
+                      "interpolated frames/sec, %s pair DS_SCALE=%s, N=8 timesteps, GIMM-VFI-F" % ("2K" if args.config == "f2k" else "4K", ds),
+            "value": total_frames / (ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong" if batch_mode else "weak", "vs_baseline": None, "dtype": DTYPES[args.precision], "data": "synthetic",
             "config": cfg,

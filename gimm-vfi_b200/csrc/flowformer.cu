@@ -112,6 +112,26 @@ void Engine::finalize_flowformer() {
     b.shape[0] = bz.shape[0] + br.shape[0]; b.data.insert(b.data.end(), br.data.begin(), br.data.end());
     raw_[u + ".gru.convzr" + sfx + ".weight"] = w; raw_[u + ".gru.convzr" + sfx + ".bias"] = b;
     pack_conv(u + ".gru.convzr" + sfx);
+    // The GRU input is [h | inp | mf | mg] (gru.py:147-151) and `inp` (the context half, decoder.py:270-273) does not change over the 32
+    // iterations: its share of every gate convolution is computed once per pair ("_inp", carries the bias) and enters the per-iteration
+    // convolutions over [h | mf | mg] ("_hm", K = 384 instead of 512) as a pre-activation term - the scheme of RAFT's update block (engine.cu).
+    for (const char* gate : {"zr", "q"}) {
+      const std::string g = u + ".gru.conv" + gate + sfx;
+      const HostTensor& wf = raw(g + ".weight"); const HostTensor& bf = raw(g + ".bias");
+      const int64_t co = wf.shape[0], ci = wf.shape[1], kk = wf.shape[2] * wf.shape[3];
+      if (ci != 512) throw std::runtime_error("flowformer: SepConvGRU input width");
+      HostTensor w_hm, w_in, b0 = bf;
+      w_hm.shape = {co, 384, wf.shape[2], wf.shape[3]}; w_in.shape = {co, 128, wf.shape[2], wf.shape[3]};
+      for (int64_t o = 0; o < co; ++o)
+        for (int64_t c = 0; c < ci; ++c) {
+          std::vector<float>& dst = (c >= 128 && c < 256) ? w_in.data : w_hm.data;
+          dst.insert(dst.end(), wf.data.begin() + (o * ci + c) * kk, wf.data.begin() + (o * ci + c + 1) * kk);
+        }
+      std::fill(b0.data.begin(), b0.data.end(), 0.f);
+      raw_[g + "_hm.weight"] = w_hm; raw_[g + "_hm.bias"] = b0;
+      raw_[g + "_inp.weight"] = w_in; raw_[g + "_inp.bias"] = bf;
+      pack_conv(g + "_hm"); pack_conv(g + "_inp");
+    }
   }
   pack_conv(u + ".mask.2", "", 0.25f);   // mask = 0.25 * self.mask(net)  (gru.py:158)
   pack_xpacked(u + ".encoder.convf1", 4);
@@ -446,6 +466,15 @@ void Engine::run_flowformer(Ctx& cx, Net& N, int B, const TV& img, const TV& flo
   TV cor1 = A.tensor(S, h, w, 256), corflo = A.tensor(S, h, w, 256), flo1 = A.tensor(S, h, w, 128), vv = A.tensor(S, h, w, 128),
      agg = A.tensor(S, h, w, 128), zb = A.tensor(S, h, w, 128), rh = A.tensor(S, h, w, 128), fh = A.tensor(S, h, w, 256), mask = A.tensor(S, h, w, 576);
   init_coords(cx, coords1);
+  const bool hoist = cx.tc && gru_hoist_;
+  TV Pzr[2], Pq[2];
+  if (hoist)
+    for (int sx = 0; sx < 2; ++sx) {
+      const std::string sfx = sx == 0 ? "1" : "2";
+      Pzr[sx] = A.tensor(S, h, w, 256); Pq[sx] = A.tensor(S, h, w, 128);
+      N.conv(u + ".gru.convzr" + sfx + "_inp", hx.slice(128, 128), Pzr[sx]);
+      N.conv(u + ".gru.convq" + sfx + "_inp", hx.slice(128, 128), Pq[sx]);
+    }
   CorrPyr pyr{};
   for (int l = 0; l < 4; ++l) { pyr.lvl[l] = vol; pyr.h[l] = h; pyr.w[l] = w; }
   pyr.rows_per_sample = Npx; pyr.nl = 1;
@@ -493,6 +522,14 @@ void Engine::run_flowformer(Ctx& cx, Net& N, int B, const TV& img, const TV& flo
     axpy_dev(cx, mf, agg, N.V(u + ".aggregator.gamma"), mg);
     // SepConvGRU (gru.py:35-73) over [h | inp | mf | mg]
     for (const char* sfx : {"1", "2"}) {
+      if (hoist) {
+        const int sx = sfx[0] - '1';
+        ConvEpi ezr; ezr.res = Pzr[sx]; ezr.act2 = ACT_SIGMOID; ezr.mul = hcur; ezr.out2 = rh; ezr.split_c = 128;
+        N.conv_e(u + ".gru.convzr" + sfx + "_hm", hcur, hx.slice(256, 256), zb, ezr);
+        ConvEpi eq; eq.res = Pq[sx]; eq.act2 = ACT_TANH; eq.gru_z = zb; eq.gru_h = hcur;
+        N.conv_e(u + ".gru.convq" + sfx + "_hm", rh, hx.slice(256, 256), hcur, eq);
+        continue;
+      }
       if (cx.tc) {
         ConvEpi ezr; ezr.act1 = ACT_SIGMOID; ezr.mul = hcur; ezr.out2 = rh; ezr.split_c = 128;
         N.conv_e(u + ".gru.convzr" + sfx, hx, TV(), zb, ezr);
