@@ -449,7 +449,10 @@ def main():
         torch.cuda.synchronize(dev)
         return time.perf_counter() - t0
 
-    e2e_loop(2 * nmb if not batch_mode else nmb)   # untimed warm-up of the copy stream / pinned buffers / pipelined path (first-touch costs)
+    # untimed warm-up of the copy stream / pinned buffers / pipelined path: as many forwards as the timed loop, so that the caching allocator has
+    # already grown to the loop's steady state (outputs handed to the copy stream are freed late; a first-time cudaMalloc in the timed loop
+    # synchronises the device - seen as +8 ms per step in 2 of 5 otherwise identical runs)
+    e2e_loop(max(2 * nmb, n_fwd) if not batch_mode else nmb)
     e2e_ms = 1000.0 * e2e_loop(n_fwd) / args.steps
     barrier()
     clocks = sampler.stop() if sampler else None
