@@ -420,7 +420,7 @@ void Engine::run_flowformer(Ctx& cx, Net& N, int B, const TV& img, const TV& flo
   }
   // GMA attention (gma.py:56-76), once per pair: softmax(q k^T / sqrt(128)) stored * att_mul (a power of two)
   float att_mul = 1.f;
-  while (att_mul < (float)Npx) att_mul *= 2.f;
+  while (att_mul < (float)Npx && att_mul < 32768.f) att_mul *= 2.f;   // (<= 2^15: a one-hot row stays below the largest half)
   float* att = A.alloc_f((size_t)S * Npx * Npx);
   float* zeros = nullptr;
   {
