@@ -219,7 +219,29 @@ struct PadZeroK {
     dst.p[dst.off(q.n, q.y, q.x) + q.c] = v;
   }
 };
+struct PadZeroK4 {   // 4 lanes per thread (16-byte loads / stores); lanes >= src.c are written as zeros like PadZeroK does
+  TV src, dst; int pad;
+  GV_HD void operator()(int64_t i) const {
+    const int g4 = dst.ld >> 2;
+    const int g = (int)(i % g4); int64_t r = i / g4;
+    const int px = (int)(r % dst.w); r /= dst.w; const int py = (int)(r % dst.h); const int n = (int)(r / dst.h);
+    const int y = py - pad, x = px - pad, c0 = g * 4;
+    F4 v = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < src.c && y >= 0 && y < src.h && x >= 0 && x < src.w) {
+      v = ld4(src.p + src.off(n, y, x) + c0);   // (c0 + 3 < src.ld: both pixel strides are multiples of 4)
+      if (c0 + 1 >= src.c) v.y = 0.f;
+      if (c0 + 2 >= src.c) v.z = 0.f;
+      if (c0 + 3 >= src.c) v.w = 0.f;
+    }
+    st4(dst.p + dst.off(n, py, px) + c0, v);
+  }
+};
 void pad_zero(Ctx& cx, const TV& src, const TV& dst, int pad) {
+  auto al16 = [](const TV& t) { return (reinterpret_cast<uintptr_t>(t.p) & 15) == 0 && t.ld % 4 == 0 && t.sn % 4 == 0 && !t.f16; };
+  if (al16(src) && al16(dst) && ((src.c + 3) & ~3) <= src.ld) {
+    parallel_for(cx, dst.pixels() * (dst.ld / 4), PadZeroK4{src, dst, pad}, "pad_zero");
+    return;
+  }
   parallel_for(cx, dst.pixels() * dst.ld, PadZeroK{src, dst, pad}, "pad_zero");
 }
 
@@ -1060,8 +1082,53 @@ struct MultiFlowBlendK {
     mean3.p[mean3.off(q.n, q.y, q.x) + q.c] = acc / 3.f;
   }
 };
+// One thread per PIXEL (the form above runs one per (pixel, colour): every thread re-derives the three bilinear taps of both frames and
+// re-reads both flow triples): the taps are computed once per flow pair, the four corners of each frame are fetched as 16-byte pixels
+// (3 colours + padding lane), the nine blended values leave as three 16-byte stores.  Same arithmetic and summation order per value.
+struct MultiFlowBlendPxK {
+  TV i0, i1, f0, f1, m, res, w9, mean3;
+  GV_HD static void fetch3(const TV& s, int n, const BilinearTap& t, float* v) {
+    const float* b = s.p + (int64_t)n * s.sn;
+    v[0] = v[1] = v[2] = 0.f;
+    if (t.vy0 && t.vx0) { const F4 p = ld4(b + ((int64_t)t.y0 * s.w + t.x0) * s.ld); const float w = t.wx0 * t.wy0; v[0] += p.x * w; v[1] += p.y * w; v[2] += p.z * w; }
+    if (t.vy0 && t.vx1) { const F4 p = ld4(b + ((int64_t)t.y0 * s.w + t.x1) * s.ld); const float w = t.wx1 * t.wy0; v[0] += p.x * w; v[1] += p.y * w; v[2] += p.z * w; }
+    if (t.vy1 && t.vx0) { const F4 p = ld4(b + ((int64_t)t.y1 * s.w + t.x0) * s.ld); const float w = t.wx0 * t.wy1; v[0] += p.x * w; v[1] += p.y * w; v[2] += p.z * w; }
+    if (t.vy1 && t.vx1) { const F4 p = ld4(b + ((int64_t)t.y1 * s.w + t.x1) * s.ld); const float w = t.wx1 * t.wy1; v[0] += p.x * w; v[1] += p.y * w; v[2] += p.z * w; }
+  }
+  GV_HD void operator()(int64_t i) const {
+    const int x = (int)(i % w9.w); int64_t r = i / w9.w; const int y = (int)(r % w9.h); const int n = (int)(r / w9.h);
+    const float* a = f0.p + f0.off(n, y, x); const float* b = f1.p + f1.off(n, y, x);
+    const float* mp = m.p + m.off(n, y, x); const float* rp = res.p + res.off(n, y, x);
+    float out[12]; float acc[3] = {0.f, 0.f, 0.f};
+    out[9] = out[10] = out[11] = 0.f;
+    for (int k = 0; k < 3; ++k) {
+      const BilinearTap t0 = border_tap(x, y, a[2 * k], a[2 * k + 1], f0.w, f0.h, i0.w, i0.h);
+      const BilinearTap t1 = border_tap(x, y, b[2 * k], b[2 * k + 1], f1.w, f1.h, i1.w, i1.h);
+      float v0[3], v1[3];
+      fetch3(i0, n, t0, v0); fetch3(i1, n, t1, v1);
+      const float mm = mp[k];
+      for (int c = 0; c < 3; ++c) {
+        float v = mm * v0[c] + (1.f - mm) * v1[c];
+        v += rp[3 * k + c];
+        out[3 * k + c] = v;
+        acc[c] += v;
+      }
+    }
+    float* o = w9.p + w9.off(n, y, x);
+    F4 s0 = {out[0], out[1], out[2], out[3]}, s1 = {out[4], out[5], out[6], out[7]}, s2 = {out[8], out[9], out[10], out[11]};
+    st4(o, s0); st4(o + 4, s1); st4(o + 8, s2);
+    F4 mn = {acc[0] / 3.f, acc[1] / 3.f, acc[2] / 3.f, 0.f};
+    st4(mean3.p + mean3.off(n, y, x), mn);
+  }
+};
 void multi_flow_blend(Ctx& cx, const TV& img0, const TV& img1, const TV& f0, const TV& f1, const TV& mask, const TV& res,
                       const TV& warps9, const TV& mean3) {
+  auto al16 = [](const TV& t) { return (reinterpret_cast<uintptr_t>(t.p) & 15) == 0 && t.ld % 4 == 0 && t.sn % 4 == 0 && !t.f16; };
+  if (al16(img0) && al16(img1) && img0.ld >= 4 && img1.ld >= 4 && al16(warps9) && warps9.ld >= 12 && al16(mean3) && mean3.ld >= 4 && !f0.f16 && !f1.f16 &&
+      !mask.f16 && !res.f16) {
+    parallel_for(cx, warps9.pixels(), MultiFlowBlendPxK{img0, img1, f0, f1, mask, res, warps9, mean3}, "multi_flow_blend");
+    return;
+  }
   parallel_for(cx, warps9.pixels() * 3, MultiFlowBlendK{img0, img1, f0, f1, mask, res, warps9, mean3}, "multi_flow_blend");
 }
 

@@ -1,0 +1,8 @@
+#!/bin/bash
+# round 2, last verification: thread-per-pixel multi_flow_blend + 16-byte pad_zero: full GPU suite, default bench line (A/B is not possible:
+# no switch), GIMM-VFI-F lines
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r02fin3_all.log 2>&1; echo "all rc=$?"; tail -n 3 gpurun_out/r02fin3_all.log | cut -c1-200
+timeout 300 python bench.py --no-cpu-baseline --no-torch-baseline --profile-json gpurun_out/r02fin3_r_profile.json > gpurun_out/r02fin3_bench.log 2>&1; tail -n 1 gpurun_out/r02fin3_bench.log | cut -c1-260
+timeout 300 python bench.py --config f2k --profile-json gpurun_out/r02fin3_f2k_profile.json > gpurun_out/r02fin3_bench_f2k.log 2>&1; tail -n 1 gpurun_out/r02fin3_bench_f2k.log | cut -c1-260
+timeout 300 python bench.py --config f4k --steps 3 --profile-json gpurun_out/r02fin3_f4k_profile.json > gpurun_out/r02fin3_bench_f4k.log 2>&1; tail -n 1 gpurun_out/r02fin3_bench_f4k.log | cut -c1-260
