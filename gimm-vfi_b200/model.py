@@ -185,7 +185,7 @@ def _check_engine_config(config):
 
 
 def create_model(config, ema: bool = False):
-    """src/models/__init__.py:15-37 for the built model types (gimmvfi_r, gimm)."""
+    """src/models/__init__.py:15-37 for the three model types (gimmvfi_r, gimmvfi_f, gimm)."""
     model_type = config.type.lower()
     if ema:
         raise NotImplementedError("EMA wrappers are training-only (src/models/ema.py) and out of scope")
@@ -196,7 +196,7 @@ def create_model(config, ema: bool = False):
         from .gimm import GIMM
 
         return GIMM(config), None
-    if model_type == "gimmvfi_f":   # boundary + native synthesis half; the FlowFormer estimator is external (model_f.py)
+    if model_type == "gimmvfi_f":   # GIMM-VFI-F / F-P: native FlowFormer estimator + synthesis half (model_f.py)
         from .model_f import GIMMVFI_F
 
         return GIMMVFI_F(config), None

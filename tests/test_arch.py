@@ -58,3 +58,16 @@ def test_param_spec_f_matches_reference_dump():
     assert [[k, list(s), d] for k, s, d in mine] == ref
     shared = [k for k, _, _ in param_spec_r() if not k.startswith(R_ONLY_PREFIXES)]
     assert sorted(k for k, _, _ in mine if not k.startswith("flow_estimator.")) == sorted(shared)
+
+
+def test_yaml_configs_dispatch_to_the_three_boundary_classes():
+    """configs/gimmvfi/*.yaml carry the reference's `arch:` blocks; create_model (src/models/__init__.py:15-37) dispatches them to the
+    drop-in classes, each exposing the reference's state_dict (414 / 639 tensors)."""
+    import os
+
+    from gimmvfi_b200 import create_model, load_config
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "gimmvfi")
+    for fn, cls, n in (("gimmvfi_r_arb.yaml", "GIMMVFI_R", 414), ("gimmvfi_f_arb.yaml", "GIMMVFI_F", 639)):
+        m, ema = create_model(load_config(os.path.join(root, fn)).arch)
+        assert type(m).__name__ == cls and ema is None and len(m.state_dict()) == n
