@@ -21,3 +21,15 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_of_the_f_configs_says_unavailable():
+    """--config f2k / f4k (GIMM-VFI-F): the reference arm cannot run offline (timm + pretrained FlowFormer) - one json line, exit 0."""
+    for cfg in ("f2k", "f4k"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", cfg, "--impl", "reference"],
+                           capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and isinstance(d.get("unavailable"), str) and d["unavailable"]
